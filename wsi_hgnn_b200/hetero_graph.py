@@ -1,0 +1,669 @@
+"""HeteroGraph: the graph container the hot path runs on (no DGL dependency).
+
+It exposes exactly the subset of the ``DGLHeteroGraph`` surface that the
+reference models and their callers touch:
+
+* ``G.ntypes`` / ``G.canonical_etypes`` / ``G.etypes``        (reference models/HEATNet4.py:91,122,199)
+* ``G.nodes[nt].data['feat']``                                 (models/HEATNet4.py:202)
+* ``G.edata['sim']`` -> dict keyed by canonical etype           (models/HEATNet4.py:209-210)
+* ``G[s, e, d]`` relation view, ``G.local_scope()``, ``G.to()`` (models/HEATNet4.py:92,228; trainer/train_gnn.py:60,64)
+* ``G.is_homogeneous``                                          (data.py:120)
+* ``batch_size`` / ``batch_num_nodes(ntype)``                   (what dgl.readout.*_nodes consume, pooling/avg_pooling.py:15-17)
+
+Two ways of putting several slides into one object:
+
+* :func:`batch` - DGL ``dgl.batch`` semantics: all graphs must share the same
+  relation set; the cross-relation mean denominator R_t is that of the shared
+  metagraph.
+* :func:`pack`  - the reference trainer's *tuple* branch
+  (trainer/train_gnn.py:59-62, ``torch.cat([gnn(g) for g in graphs])``):
+  graphs are laid out block-diagonally but keep their own relation sets, their
+  own R_t and their own "type has no nodes" readout behaviour, so one launch
+  over the packed object equals the concatenation of independent forwards.
+
+The device-side layout the CUDA kernels consume is produced by
+:meth:`HeteroGraph.plan` (see ``GraphPlan``).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+CEType = Tuple[str, str, str]
+
+
+class _Frame(dict):
+    """A per-type (or per-relation) feature dictionary."""
+
+
+class _NodeTypeView:
+    def __init__(self, graph: "HeteroGraph", ntype: str):
+        self._g = graph
+        self._nt = ntype
+
+    @property
+    def data(self) -> _Frame:
+        return self._g._ndata[self._nt]
+
+
+class _NodesAccessor:
+    def __init__(self, graph: "HeteroGraph"):
+        self._g = graph
+
+    def __getitem__(self, ntype: str) -> _NodeTypeView:
+        if ntype not in self._g._ndata:
+            raise KeyError(ntype)
+        return _NodeTypeView(self._g, ntype)
+
+
+class _TypedDataView:
+    """``G.ndata`` / ``G.edata``: name -> tensor (one type) or {type: tensor}."""
+
+    def __init__(self, frames: Dict, keys: Sequence):
+        self._frames = frames
+        self._keys = list(keys)
+
+    def __getitem__(self, name: str):
+        if len(self._keys) == 1:
+            return self._frames[self._keys[0]][name]
+        out = {k: self._frames[k][name] for k in self._keys if name in self._frames[k]}
+        if not out:
+            raise KeyError(name)
+        return out
+
+    def __setitem__(self, name: str, value):
+        if isinstance(value, dict):
+            for k, v in value.items():
+                self._frames[k][name] = v
+        else:
+            if len(self._keys) != 1:
+                raise ValueError("a dict keyed by type is required when there is more than one type")
+            self._frames[self._keys[0]][name] = value
+
+    def __contains__(self, name: str) -> bool:
+        return any(name in self._frames[k] for k in self._keys)
+
+    def pop(self, name: str):
+        out = self[name]
+        for k in self._keys:
+            self._frames[k].pop(name, None)
+        return out
+
+    def update(self, d: Dict):
+        for k, v in d.items():
+            self[k] = v
+
+
+class RelationView:
+    """``G[s, e, d]``: one relation of the parent graph (shares its frames)."""
+
+    def __init__(self, graph: "HeteroGraph", cetype: CEType):
+        self._g = graph
+        self.cetype = cetype
+
+    @property
+    def canonical_etypes(self):
+        return [self.cetype]
+
+    def edges(self):
+        return self._g._edges[self.cetype]
+
+    def num_edges(self) -> int:
+        return int(self._g._edges[self.cetype][0].shape[0])
+
+    @property
+    def edata(self) -> _Frame:
+        return self._g._edata[self.cetype]
+
+    @property
+    def srcdata(self) -> _Frame:
+        return self._g._ndata[self.cetype[0]]
+
+    @property
+    def dstdata(self) -> _Frame:
+        return self._g._ndata[self.cetype[2]]
+
+    def num_src_nodes(self) -> int:
+        return self._g.num_nodes(self.cetype[0])
+
+    def num_dst_nodes(self) -> int:
+        return self._g.num_nodes(self.cetype[2])
+
+
+class GraphPlan:
+    """Device-resident layout of one (possibly batched/packed) graph.
+
+    Nodes are *packed type-major*: packed id = type_ptr[t] + local id, so every
+    per-type feature matrix is a contiguous row range of one [N, D] buffer and
+    a typed linear is a grouped GEMM over row segments.
+
+    Edges are sorted by (dst packed id, relation index, original edge id); one
+    dst row of the CSR therefore holds its in-edges grouped by relation, which
+    is what the per-(dst, relation, head) softmax needs
+    (reference models/HEATNet4.py:109-119).
+
+    Tensors (all on the graph's device):
+      type_ptr_dev int32 [T+1]     row range of each node type
+      seg_ptr      int32 [T*B+1]   (type, graph) readout segments, type-major
+      rowptr       int32 [N+1]     CSR over packed dst ids
+      e_src        int32 [E]       packed src id per edge (dst-sorted order)
+      e_sim        fp32  [E]       edge attribute 'sim' (0 if the graph has none)
+      e_rel        uint8 [E]       relation slot of the edge (index into rel_list)
+      node_inv_r   fp32  [N]       1/R_t for the node's (graph,) type; 0 => no incoming relation (passthrough)
+      t_rowptr     int32 [N+1]     transposed (src-major) CSR, built lazily for backward
+      t_eid        int32 [E]       position in dst-sorted order of each src-sorted edge
+      e_dst        int32 [E]       packed dst id per edge (dst-sorted order), lazily for backward
+    """
+
+    def __init__(self):
+        self.ntypes: List[str] = []
+        self.rel_list: List[CEType] = []
+        self.type_ptr: List[int] = []
+        self.N = 0
+        self.E = 0
+        self.B = 1
+        self.type_ptr_dev = None
+        self.seg_ptr = None
+        self.seg_ptr_host: List[int] = []
+        self.rowptr = None
+        self.e_src = None
+        self.e_sim = None
+        self.e_rel = None
+        self.node_inv_r = None
+        self.rel_src_type: List[int] = []
+        self.rel_dst_type: List[int] = []
+        self.r_count: List[int] = []          # R_t per type (batch mode)
+        self.max_in_degree = 0
+        self._t = None
+        self.device = torch.device("cpu")
+        self.seg_nonempty = None              # bool [T, B] on host
+        self.hub = None                       # (hub_rows int32 [Hn], ...) filled by ops when needed
+
+    def transposed(self):
+        """(t_rowptr, t_eid, e_dst) for the backward scatter to src rows."""
+        if self._t is None:
+            dev = self.device
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            e_dst = torch.repeat_interleave(torch.arange(self.N, device=dev, dtype=torch.int32), deg)
+            src64 = self.e_src.to(torch.int64)
+            order = torch.argsort(src64, stable=True)
+            counts = torch.bincount(src64, minlength=self.N)
+            t_rowptr = torch.zeros(self.N + 1, dtype=torch.int32, device=dev)
+            t_rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            self._t = (t_rowptr, order.to(torch.int32).contiguous(), e_dst.contiguous())
+        return self._t
+
+
+class HeteroGraph:
+    def __init__(self,
+                 num_nodes_dict: Dict[str, int],
+                 edges: Dict[CEType, Tuple[torch.Tensor, torch.Tensor]],
+                 ndata: Optional[Dict[str, Dict[str, torch.Tensor]]] = None,
+                 edata: Optional[Dict[CEType, Dict[str, torch.Tensor]]] = None):
+        # [DGL-mem] dgl.heterograph sorts node type names and relation tuples.
+        self.ntypes: List[str] = sorted(num_nodes_dict.keys())
+        self._num_nodes = {k: int(num_nodes_dict[k]) for k in self.ntypes}
+        self.canonical_etypes: List[CEType] = sorted(edges.keys())
+        self._edges: Dict[CEType, Tuple[torch.Tensor, torch.Tensor]] = {}
+        for ce in self.canonical_etypes:
+            s, d = edges[ce]
+            s = torch.as_tensor(s, dtype=torch.int64)
+            d = torch.as_tensor(d, dtype=torch.int64)
+            if s.shape != d.shape or s.dim() != 1:
+                raise ValueError(f"relation {ce}: src/dst must be 1-D of equal length")
+            if ce[0] not in self._num_nodes or ce[2] not in self._num_nodes:
+                raise KeyError(f"relation {ce} names an unknown node type")
+            self._edges[ce] = (s, d)
+        self._ndata: Dict[str, _Frame] = {nt: _Frame() for nt in self.ntypes}
+        self._edata: Dict[CEType, _Frame] = {ce: _Frame() for ce in self.canonical_etypes}
+        if ndata:
+            for nt, fr in ndata.items():
+                for k, v in fr.items():
+                    if v.shape[0] != self._num_nodes[nt]:
+                        raise ValueError(f"ndata[{nt}][{k}] has {v.shape[0]} rows, expected {self._num_nodes[nt]}")
+                    self._ndata[nt][k] = v
+        if edata:
+            for ce, fr in edata.items():
+                for k, v in fr.items():
+                    if v.shape[0] != self._edges[ce][0].shape[0]:
+                        raise ValueError(f"edata[{ce}][{k}] has wrong length")
+                    self._edata[ce][k] = v
+        # batching info: one graph by default
+        self._batch_num_nodes: Dict[str, List[int]] = {nt: [self._num_nodes[nt]] for nt in self.ntypes}
+        self._batch_num_edges: Dict[CEType, List[int]] = {
+            ce: [int(self._edges[ce][0].shape[0])] for ce in self.canonical_etypes}
+        self.batch_size = 1
+        # pack() mode: per-graph relation presence [B][R] (None => DGL batch semantics)
+        self._rel_present: Optional[List[List[bool]]] = None
+        self._plan: Optional[GraphPlan] = None
+
+    # ------------------------------------------------------------------ basic queries
+    @property
+    def etypes(self) -> List[str]:
+        return [ce[1] for ce in self.canonical_etypes]
+
+    @property
+    def is_homogeneous(self) -> bool:
+        return len(self.ntypes) == 1 and len(self.canonical_etypes) == 1
+
+    @property
+    def independent(self) -> bool:
+        """True when built by :func:`pack` (per-graph relation sets / readout masks)."""
+        return self._rel_present is not None
+
+    def num_nodes(self, ntype: Optional[str] = None) -> int:
+        if ntype is None:
+            return sum(self._num_nodes.values())
+        return self._num_nodes[ntype]
+
+    number_of_nodes = num_nodes
+
+    def num_edges(self, etype=None) -> int:
+        if etype is None:
+            return sum(int(s.shape[0]) for s, _ in self._edges.values())
+        return int(self._edges[self._canon(etype)][0].shape[0])
+
+    number_of_edges = num_edges
+
+    def _canon(self, etype) -> CEType:
+        if isinstance(etype, tuple):
+            if etype not in self._edges:
+                raise KeyError(etype)
+            return etype
+        hits = [ce for ce in self.canonical_etypes if ce[1] == etype]
+        if len(hits) != 1:
+            raise KeyError(f"edge type {etype!r} is ambiguous or unknown; use the canonical triple")
+        return hits[0]
+
+    def edges(self, etype=None):
+        if etype is None:
+            if len(self.canonical_etypes) != 1:
+                raise ValueError("etype is required for a graph with several relations")
+            etype = self.canonical_etypes[0]
+        return self._edges[self._canon(etype)]
+
+    def __getitem__(self, key) -> RelationView:
+        return RelationView(self, self._canon(key))
+
+    @property
+    def nodes(self) -> _NodesAccessor:
+        return _NodesAccessor(self)
+
+    @property
+    def ndata(self) -> _TypedDataView:
+        return _TypedDataView(self._ndata, self.ntypes)
+
+    @property
+    def edata(self) -> _TypedDataView:
+        return _TypedDataView(self._edata, self.canonical_etypes)
+
+    @property
+    def device(self) -> torch.device:
+        for fr in self._ndata.values():
+            for v in fr.values():
+                return v.device
+        for s, _ in self._edges.values():
+            return s.device
+        return torch.device("cpu")
+
+    def batch_num_nodes(self, ntype: Optional[str] = None) -> torch.Tensor:
+        if ntype is None:
+            if len(self.ntypes) != 1:
+                raise ValueError("ntype is required")
+            ntype = self.ntypes[0]
+        return torch.tensor(self._batch_num_nodes[ntype], dtype=torch.int64)
+
+    def batch_num_edges(self, etype=None) -> torch.Tensor:
+        ce = self._canon(etype) if etype is not None else self.canonical_etypes[0]
+        return torch.tensor(self._batch_num_edges[ce], dtype=torch.int64)
+
+    @contextlib.contextmanager
+    def local_scope(self):
+        """Feature writes made inside the scope are dropped on exit ([DGL-mem] DGLGraph.local_scope)."""
+        nsnap = {k: dict(v) for k, v in self._ndata.items()}
+        esnap = {k: dict(v) for k, v in self._edata.items()}
+        try:
+            yield self
+        finally:
+            for k in self._ndata:
+                self._ndata[k].clear()
+                self._ndata[k].update(nsnap[k])
+            for k in self._edata:
+                self._edata[k].clear()
+                self._edata[k].update(esnap[k])
+
+    # ------------------------------------------------------------------ movement / IO
+    def to(self, device, non_blocking: bool = False) -> "HeteroGraph":
+        device = torch.device(device)
+        if device == self.device and self._plan is not None and self._plan.device == device:
+            return self
+        g = HeteroGraph.__new__(HeteroGraph)
+        g.ntypes = list(self.ntypes)
+        g._num_nodes = dict(self._num_nodes)
+        g.canonical_etypes = list(self.canonical_etypes)
+        g._edges = {ce: (s.to(device, non_blocking=non_blocking), d.to(device, non_blocking=non_blocking))
+                    for ce, (s, d) in self._edges.items()}
+        g._ndata = {nt: _Frame({k: v.to(device, non_blocking=non_blocking) for k, v in fr.items()})
+                    for nt, fr in self._ndata.items()}
+        g._edata = {ce: _Frame({k: v.to(device, non_blocking=non_blocking) for k, v in fr.items()})
+                    for ce, fr in self._edata.items()}
+        g._batch_num_nodes = {k: list(v) for k, v in self._batch_num_nodes.items()}
+        g._batch_num_edges = {k: list(v) for k, v in self._batch_num_edges.items()}
+        g.batch_size = self.batch_size
+        g._rel_present = None if self._rel_present is None else [list(r) for r in self._rel_present]
+        g._plan = None
+        return g
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def cuda(self):
+        return self.to("cuda")
+
+    def state(self) -> Dict:
+        """A plain-dict form (tensors + python scalars) that ``torch.save`` can write."""
+        return {
+            "format": "wsi_hgnn_b200.HeteroGraph/1",
+            "num_nodes": dict(self._num_nodes),
+            "edges": {"|".join(ce): (s.cpu(), d.cpu()) for ce, (s, d) in self._edges.items()},
+            "ndata": {nt: {k: v.cpu() for k, v in fr.items()} for nt, fr in self._ndata.items()},
+            "edata": {"|".join(ce): {k: v.cpu() for k, v in fr.items()} for ce, fr in self._edata.items()},
+            "batch_num_nodes": self._batch_num_nodes,
+            "batch_num_edges": {"|".join(ce): v for ce, v in self._batch_num_edges.items()},
+            "batch_size": self.batch_size,
+            "rel_present": self._rel_present,
+        }
+
+    @staticmethod
+    def from_state(st: Dict) -> "HeteroGraph":
+        edges = {tuple(k.split("|")): v for k, v in st["edges"].items()}
+        g = HeteroGraph(st["num_nodes"], edges, st["ndata"],
+                        {tuple(k.split("|")): v for k, v in st["edata"].items()})
+        g._batch_num_nodes = {k: list(v) for k, v in st["batch_num_nodes"].items()}
+        g._batch_num_edges = {tuple(k.split("|")): list(v) for k, v in st["batch_num_edges"].items()}
+        g.batch_size = st["batch_size"]
+        g._rel_present = st.get("rel_present")
+        return g
+
+    def save(self, path: str):
+        torch.save(self.state(), path)
+
+    @staticmethod
+    def load(path: str) -> "HeteroGraph":
+        return HeteroGraph.from_state(torch.load(path, weights_only=False))
+
+    @staticmethod
+    def from_dgl(g) -> "HeteroGraph":
+        """Duck-typed conversion of a DGLHeteroGraph (only usable where DGL exists; data.py:96-97)."""
+        num_nodes = {nt: int(g.num_nodes(nt)) for nt in g.ntypes}
+        edges, edata = {}, {}
+        for ce in g.canonical_etypes:
+            s, d = g.edges(etype=ce)
+            edges[tuple(ce)] = (s, d)
+            edata[tuple(ce)] = {k: v for k, v in g.edges[ce].data.items()}
+        ndata = {nt: {k: v for k, v in g.nodes[nt].data.items()} for nt in g.ntypes}
+        out = HeteroGraph(num_nodes, edges, ndata, edata)
+        try:
+            bs = int(g.batch_size)
+            if bs > 1:
+                out.batch_size = bs
+                out._batch_num_nodes = {nt: [int(x) for x in g.batch_num_nodes(nt)] for nt in g.ntypes}
+                out._batch_num_edges = {tuple(ce): [int(x) for x in g.batch_num_edges(ce)]
+                                        for ce in g.canonical_etypes}
+        except Exception:
+            pass
+        return out
+
+    # ------------------------------------------------------------------ packed views
+    def type_ptr(self) -> List[int]:
+        ptr = [0]
+        for nt in self.ntypes:
+            ptr.append(ptr[-1] + self._num_nodes[nt])
+        return ptr
+
+    def packed_ndata(self, name: str = "feat", dtype=torch.float32) -> torch.Tensor:
+        """[N, F] type-major packed copy of a node feature (rows of empty types are simply absent)."""
+        parts = [self._ndata[nt][name] for nt in self.ntypes if self._num_nodes[nt] > 0]
+        if not parts:
+            raise ValueError("graph has no nodes")
+        out = torch.cat([p.to(dtype) for p in parts], 0)
+        return out.contiguous()
+
+    def invalidate_plan(self):
+        self._plan = None
+
+    def plan(self, sim_name: str = "sim") -> GraphPlan:
+        """Build (once) the device layout the kernels consume; see :class:`GraphPlan`.
+
+        Replaces what ``dgl.to_heterogeneous`` + DGL's on-demand CSC conversion do for the
+        reference (construct_graph/graph_constructor.py:285-297; [DGL-mem] HeteroGraph::GetCSCMatrix).
+        """
+        if self._plan is not None:
+            return self._plan
+        dev = self.device
+        p = GraphPlan()
+        p.device = dev
+        p.ntypes = list(self.ntypes)
+        p.rel_list = list(self.canonical_etypes)
+        if len(p.rel_list) > 255:
+            raise ValueError("at most 255 relations are supported")
+        p.type_ptr = self.type_ptr()
+        p.N = p.type_ptr[-1]
+        p.B = self.batch_size
+        tix = {nt: i for i, nt in enumerate(self.ntypes)}
+        p.rel_src_type = [tix[ce[0]] for ce in p.rel_list]
+        p.rel_dst_type = [tix[ce[2]] for ce in p.rel_list]
+        T = len(self.ntypes)
+        p.r_count = [sum(1 for d in p.rel_dst_type if d == t) for t in range(T)]
+
+        # (type, graph) readout segments
+        seg = [0]
+        nonempty = torch.zeros(T, p.B, dtype=torch.bool)
+        for t, nt in enumerate(self.ntypes):
+            for b, n in enumerate(self._batch_num_nodes[nt]):
+                seg.append(seg[-1] + n)
+                nonempty[t, b] = n > 0
+        assert seg[-1] == p.N
+        p.seg_ptr_host = seg
+        p.seg_nonempty = nonempty
+        p.seg_ptr = torch.tensor(seg, dtype=torch.int32, device=dev)
+        p.type_ptr_dev = torch.tensor(p.type_ptr, dtype=torch.int32, device=dev)
+
+        # 1/R per node.  DGL batch: R_t of the shared metagraph.  pack(): per graph.
+        inv = torch.zeros(max(p.N, 1), dtype=torch.float32)
+        if self._rel_present is None:
+            for t in range(T):
+                if p.r_count[t] > 0:
+                    inv[p.type_ptr[t]:p.type_ptr[t + 1]] = 1.0 / p.r_count[t]
+        else:
+            for t, nt in enumerate(self.ntypes):
+                off = p.type_ptr[t]
+                for b, n in enumerate(self._batch_num_nodes[nt]):
+                    r = sum(1 for ri, d in enumerate(p.rel_dst_type) if d == t and self._rel_present[b][ri])
+                    if r > 0 and n > 0:
+                        inv[off:off + n] = 1.0 / r
+                    off += n
+        p.node_inv_r = inv[:p.N].to(dev) if p.N > 0 else inv[:0].to(dev)
+
+        # dst-major, relation-grouped CSR
+        srcs, dsts, rels, sims = [], [], [], []
+        for ri, ce in enumerate(p.rel_list):
+            s, d = self._edges[ce]
+            if s.numel() == 0:
+                continue
+            srcs.append(s.to(dev) + p.type_ptr[p.rel_src_type[ri]])
+            dsts.append(d.to(dev) + p.type_ptr[p.rel_dst_type[ri]])
+            rels.append(torch.full((s.numel(),), ri, dtype=torch.int64, device=dev))
+            if sim_name in self._edata[ce]:
+                sims.append(self._edata[ce][sim_name].to(dev).reshape(-1).to(torch.float32))
+            else:
+                sims.append(torch.zeros(s.numel(), dtype=torch.float32, device=dev))
+        if srcs:
+            src = torch.cat(srcs)
+            dst = torch.cat(dsts)
+            rel = torch.cat(rels)
+            sim = torch.cat(sims)
+            if int(src.max()) >= p.N or int(dst.max()) >= p.N or int(src.min()) < 0 or int(dst.min()) < 0:
+                raise IndexError("edge endpoint out of range")
+            key = dst * 256 + rel                      # stable sort keeps original edge order inside a segment
+            order = torch.argsort(key, stable=True)
+            p.e_src = src[order].to(torch.int32).contiguous()
+            p.e_sim = sim[order].contiguous()
+            p.e_rel = rel[order].to(torch.uint8).contiguous()
+            counts = torch.bincount(dst, minlength=p.N)
+            p.max_in_degree = int(counts.max()) if p.N > 0 else 0
+            rowptr = torch.zeros(p.N + 1, dtype=torch.int32, device=dev)
+            rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            p.rowptr = rowptr
+            p.E = int(src.numel())
+        else:
+            p.e_src = torch.zeros(0, dtype=torch.int32, device=dev)
+            p.e_sim = torch.zeros(0, dtype=torch.float32, device=dev)
+            p.e_rel = torch.zeros(0, dtype=torch.uint8, device=dev)
+            p.rowptr = torch.zeros(p.N + 1, dtype=torch.int32, device=dev)
+            p.E = 0
+        self._plan = p
+        return p
+
+    def __repr__(self):
+        return (f"HeteroGraph(num_nodes={self._num_nodes}, num_edges="
+                f"{ {ce: int(s.shape[0]) for ce, (s, _) in self._edges.items()} }, batch_size={self.batch_size})")
+
+
+def heterograph(data_dict: Dict[CEType, Tuple[torch.Tensor, torch.Tensor]],
+                num_nodes_dict: Optional[Dict[str, int]] = None) -> HeteroGraph:
+    """``dgl.heterograph``-style constructor."""
+    if num_nodes_dict is None:
+        num_nodes_dict = {}
+        for (s, _, d), (u, v) in data_dict.items():
+            u = torch.as_tensor(u)
+            v = torch.as_tensor(v)
+            num_nodes_dict[s] = max(num_nodes_dict.get(s, 0), int(u.max()) + 1 if u.numel() else 0)
+            num_nodes_dict[d] = max(num_nodes_dict.get(d, 0), int(v.max()) + 1 if v.numel() else 0)
+    return HeteroGraph(num_nodes_dict, data_dict)
+
+
+def to_heterogeneous(src: torch.Tensor, dst: torch.Tensor, node_type: torch.Tensor, edge_type: torch.Tensor,
+                     ntypes: Sequence[str], etypes: Sequence[str],
+                     ndata: Optional[Dict[str, torch.Tensor]] = None,
+                     edata: Optional[Dict[str, torch.Tensor]] = None) -> HeteroGraph:
+    """Homogeneous (src, dst, _TYPE) -> HeteroGraph, as ``dgl.to_heterogeneous`` does for the
+    reference builder (construct_graph/graph_constructor.py:285-297).
+
+    [DGL-mem] all ``ntypes`` exist afterwards (possibly with 0 nodes); only the (s, e, d)
+    triples that occur become relations; local ids are the rank of a node within its type
+    (stable partition); ``_ID`` records the original ids.
+    """
+    node_type = torch.as_tensor(node_type, dtype=torch.int64)
+    edge_type = torch.as_tensor(edge_type, dtype=torch.int64)
+    src = torch.as_tensor(src, dtype=torch.int64)
+    dst = torch.as_tensor(dst, dtype=torch.int64)
+    N = node_type.numel()
+    T = len(ntypes)
+    order = torch.argsort(node_type, stable=True)
+    counts = torch.bincount(node_type, minlength=T)
+    starts = torch.cumsum(counts, 0) - counts
+    local = torch.empty(N, dtype=torch.int64, device=node_type.device)
+    local[order] = torch.arange(N, device=node_type.device) - starts[node_type[order]]
+    num_nodes = {ntypes[t]: int(counts[t]) for t in range(T)}
+    nfr = {}
+    for t in range(T):
+        ids = order[starts[t]:starts[t] + counts[t]]
+        fr = {"_ID": ids}
+        for k, v in (ndata or {}).items():
+            fr[k] = v[ids]
+        nfr[ntypes[t]] = fr
+    st, dt = node_type[src], node_type[dst]
+    key = (st * len(etypes) + edge_type) * T + dt
+    edges, efr = {}, {}
+    for kv in torch.unique(key).tolist():
+        m = torch.nonzero(key == kv).reshape(-1)
+        s_t = kv // (len(etypes) * T)
+        e_t = (kv // T) % len(etypes)
+        d_t = kv % T
+        ce = (ntypes[s_t], etypes[e_t], ntypes[d_t])
+        edges[ce] = (local[src[m]], local[dst[m]])
+        fr = {"_ID": m}
+        for k, v in (edata or {}).items():
+            fr[k] = v[m]
+        efr[ce] = fr
+    return HeteroGraph(num_nodes, edges, nfr, efr)
+
+
+def _cat_graphs(graphs: Sequence[HeteroGraph], rel_union: List[CEType]) -> HeteroGraph:
+    ntypes = graphs[0].ntypes
+    for g in graphs:
+        if g.ntypes != ntypes:
+            raise ValueError("all graphs must have the same node types")
+    num_nodes = {nt: sum(g._num_nodes[nt] for g in graphs) for nt in ntypes}
+    offs = {nt: [0] for nt in ntypes}
+    for g in graphs:
+        for nt in ntypes:
+            offs[nt].append(offs[nt][-1] + g._num_nodes[nt])
+    edges = {}
+    edata: Dict[CEType, Dict[str, torch.Tensor]] = {}
+    bne = {}
+    dev = graphs[0].device
+    for ce in rel_union:
+        ss, dd, cnt = [], [], []
+        keys = None
+        for gi, g in enumerate(graphs):
+            if ce in g._edges:
+                s, d = g._edges[ce]
+                ss.append(s + offs[ce[0]][gi])
+                dd.append(d + offs[ce[2]][gi])
+                cnt.append(int(s.shape[0]))
+                if keys is None:
+                    keys = set(g._edata[ce].keys())
+                else:
+                    keys &= set(g._edata[ce].keys())
+            else:
+                cnt.append(0)
+        edges[ce] = (torch.cat(ss) if ss else torch.zeros(0, dtype=torch.int64, device=dev),
+                     torch.cat(dd) if dd else torch.zeros(0, dtype=torch.int64, device=dev))
+        bne[ce] = cnt
+        edata[ce] = {}
+        for k in (keys or ()):
+            edata[ce][k] = torch.cat([g._edata[ce][k] for g in graphs if ce in g._edges])
+    ndata: Dict[str, Dict[str, torch.Tensor]] = {}
+    for nt in ntypes:
+        keys = None
+        for g in graphs:
+            ks = set(g._ndata[nt].keys())
+            keys = ks if keys is None else keys & ks
+        ndata[nt] = {k: torch.cat([g._ndata[nt][k] for g in graphs]) for k in (keys or ())}
+    out = HeteroGraph(num_nodes, edges, ndata, edata)
+    out.batch_size = len(graphs)
+    out._batch_num_nodes = {nt: [g._num_nodes[nt] for g in graphs] for nt in ntypes}
+    out._batch_num_edges = bne
+    return out
+
+
+def batch(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
+    """``dgl.batch``: graphs must share node types AND the relation set ([DGL-mem])."""
+    graphs = list(graphs)
+    if not graphs:
+        raise ValueError("empty batch")
+    for g in graphs:
+        if g.batch_size != 1:
+            raise ValueError("batching already-batched graphs is not supported")
+        if g.canonical_etypes != graphs[0].canonical_etypes:
+            raise ValueError("dgl.batch semantics: all graphs must have the same relations; use pack()")
+    return _cat_graphs(graphs, list(graphs[0].canonical_etypes))
+
+
+def pack(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
+    """Block-diagonal packing whose forward equals ``torch.cat([gnn(g) for g in graphs])``
+    (the reference trainer's tuple branch, trainer/train_gnn.py:59-62)."""
+    graphs = list(graphs)
+    if not graphs:
+        raise ValueError("empty pack")
+    for g in graphs:
+        if g.batch_size != 1:
+            raise ValueError("packing already-batched graphs is not supported")
+    union = sorted(set(ce for g in graphs for ce in g.canonical_etypes))
+    out = _cat_graphs(graphs, union)
+    out._rel_present = [[ce in g._edges for ce in union] for g in graphs]
+    return out
