@@ -1,0 +1,334 @@
+"""bench.py - HEATNet4 forward throughput (edges/s) on the BASELINE.json config-2 workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one HEATNet4 forward (input projection + 3 HEAT layers + typed readout + heads) over one synthetic
+TCGA-BRCA-shape slide graph (8192 patch nodes, 3 node types, 40 960 edges, F=1024, D=512, H=4, fp32).
+  value     : edges/s with the graph resident in HBM (CSR pre-built), CUDA-graph replay, CUDA-event timed,
+              L2 flushed between steps
+  e2e       : the same metric through the public API from pinned HOST buffers: features + edge arrays H2D,
+              CSR build, forward, logits D2H - all inside the timed region
+  roofline  : the edge-attention kernel (gather K/V by source, per-relation softmax, scatter to dst), HBM bound
+  cpu_baseline / --impl reference : the reference-structured CPU restatement (oracle/) on the host cores; the
+              reference itself cannot run here (DGL absent)
+N > 1 (torchrun): every rank runs its own slides (independent units, no collective in the forward): weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CFG = dict(workload="config2: TCGA-BRCA-shape synthetic slide graph, 3-layer HEATNet4 forward, fp32",
+           nodes=8192, node_types=3, k=5, edges=40960, in_dim=1024, hidden=512, heads=4, layers=3, out_dim=2,
+           graphs_per_step=1)
+METRIC = "HEATNet4 fwd edges/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def make_graph(seed: int):
+    from wsi_hgnn_b200 import synthetic
+    return synthetic.synth_slide_graph(CFG["nodes"], CFG["in_dim"], CFG["node_types"], CFG["k"], seed=seed)
+
+
+def model_kwargs():
+    T = CFG["node_types"]
+    return dict(in_dim=CFG["in_dim"], hidden_dim=CFG["hidden"], out_dim=CFG["out_dim"], n_layers=CFG["layers"],
+                n_heads=CFG["heads"], node_dict={str(i): i for i in range(T)}, dropuout=0.2)
+
+
+def build_models(want_oracle: bool, want_ours: bool):
+    import golden_util
+    ours = orc = None
+    if want_oracle:
+        from oracle.heat import OracleHEATNet4
+        torch.manual_seed(611)
+        orc = OracleHEATNet4(**model_kwargs())
+        golden_util.fill_params(orc, 611)
+        orc.eval()
+    if want_ours:
+        from wsi_hgnn_b200.models import HEATNet4
+        torch.manual_seed(611)
+        ours = HEATNet4(**model_kwargs())
+        golden_util.fill_params(ours, 611)
+        ours.eval()
+    return ours, orc
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_forward_time(orc, G, reps: int, warm: int):
+    times = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            orc(G)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    times.sort()
+    return times[len(times) // 2]
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the oracle port (oracle/), all host threads."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, orc = build_models(True, False)
+    G = make_graph(1)
+    E = G.num_edges()
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            orc(G)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc(G)
+        dt = time.perf_counter() - t0
+    v = E * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "edges/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(CFG, note="reference-structured PyTorch CPU restatement (oracle/), not DGL"),
+            "cpu_baseline": {"value": v, "unit": "edges/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full config-2 forwards"},
+            "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from wsi_hgnn_b200 import _lib, ops
+    from wsi_hgnn_b200.graphed import GraphedForward
+    from wsi_hgnn_b200.hetero_graph import HeteroGraph
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    hbm_peak, tc_peak, peak_src = peaks()
+
+    ours, orc = build_models(rank == 0 and not args.no_cpu_baseline, True)
+    ours = ours.to(dev)
+    G_host = make_graph(1 + rank)                    # every rank has its own slide (weak scaling)
+    E, N, D, L = G_host.num_edges(), G_host.num_nodes(), CFG["hidden"], CFG["layers"]
+    G = G_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # ---------------------------------------------------------------- resident-input forward (value)
+    gf = GraphedForward(ours, G, warmup=args.warmup)
+    for _ in range(args.warmup):
+        gf()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        for a, b in ev:
+            flush.zero_()                            # L2 flush between timed iterations (not timed)
+            a.record()
+            gf()
+            b.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t = torch.tensor([t_dev], device=dev, dtype=torch.float64)
+    e_tot = torch.tensor([float(E)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e_tot, op=dist.ReduceOp.SUM)
+    t_max, edges_all = float(t), float(e_tot)
+    value = edges_all * args.steps / t_max
+
+    # eager (Python-issued launches, no CUDA graph) for comparison
+    with torch.no_grad():
+        for _ in range(3):
+            ours(G)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            ours(G)
+        b.record()
+        torch.cuda.synchronize()
+    eager_ms = a.elapsed_time(b) / 10
+
+    # ---------------------------------------------------------------- end to end from host buffers (e2e)
+    state = G_host.state()
+    pinned = HeteroGraph.from_state(state)
+    h2d = 0
+    for fr in list(pinned._ndata.values()) + list(pinned._edata.values()):
+        for k_ in list(fr):
+            fr[k_] = fr[k_].pin_memory()
+            h2d += fr[k_].numel() * fr[k_].element_size()
+    for ce in list(pinned._edges):
+        s_, d_ = pinned._edges[ce]
+        pinned._edges[ce] = (s_.pin_memory(), d_.pin_memory())
+        h2d += 2 * s_.numel() * 8
+    n_e2e = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        g = pinned.to(dev, non_blocking=True)
+        with torch.no_grad():
+            out = ours(g)
+        return out.cpu()
+
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        logits = e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = edges_all * n_e2e / float(t_e2e)
+    d2h = logits.numel() * 4
+
+    # ---------------------------------------------------------------- roofline of the edge-attention kernel
+    layer = ours.gcs[0]
+    plan = G.plan()
+    with torch.no_grad():
+        x = torch.randn(N, D, device=dev)
+        order = [ours.node_dict[nt] for nt in plan.ntypes]
+        w_kvq, b_kvq, wa, ba, skip, use_perm = layer._packed(order)
+        kvq = ops.typed_linear(x, w_kvq, b_kvq, plan.type_ptr)
+        attn_args = (kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim, plan.e_rel,
+                     plan.node_inv_r, layer.e_linear.weight, layer.e_linear.bias, D, CFG["heads"], use_perm)
+        for _ in range(3):
+            ops.hetero_attn(*attn_args)
+        reps = 20
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in kev:
+            flush.zero_()
+            kvq.add_(0.0)                             # K/V/Q back in L2 as the producing GEMM leaves them
+            a.record()
+            ops.hetero_attn(*attn_args)
+            b.record()
+        torch.cuda.synchronize()
+        attn_ms = sorted(a.elapsed_time(b) for a, b in kev)[reps // 2]
+        # dense: fused K|V|Q typed GEMM
+        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in gev:
+            flush.zero_()
+            a.record()
+            ops.typed_linear(x, w_kvq, b_kvq, plan.type_ptr)
+            b.record()
+        torch.cuda.synchronize()
+        gemm_ms = sorted(a.elapsed_time(b) for a, b in gev)[reps // 2]
+    attn_bytes = E * (2 * D * 4 + 8) + N * (2 * D * 4 + 4)          # SURVEY.md §8(d) per-layer edge-phase bytes
+    achieved = attn_bytes / (attn_ms * 1e-3) / 1e9
+    gemm_flops = 2.0 * N * D * 3 * D
+    gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {"metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(CFG, l2="flushed between timed iterations (256 MB write)", launch="CUDA-graph replay",
+                           eager_ms_per_step=eager_ms, parallelism=f"dp{world} (independent slides per rank)"),
+            "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t_e2e) / n_e2e * 1e3, "steps": n_e2e,
+                    "note": "pinned host graph -> H2D -> CSR plan build -> forward -> logits D2H"},
+            "gpu_launches": gf.kernels_per_replay * args.steps,
+            "roofline": {"kernel": "attn_fwd_vec_kernel (edge attention, 1 layer)", "bound": "hbm",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes": attn_bytes,
+                         "kernel_ms": attn_ms},
+            "roofline_dense": {"kernel": "typed_linear K|V|Q [8192x512]x[512x1536] fp32-accurate", "bound": "tensor",
+                               "achieved": gemm_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tf / tc_peak,
+                               "kernel_ms": gemm_ms, "peak_source": peak_src + " (bf16 dense)"},
+            "clocks": clk.summary()}
+    if orc is not None:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        t_cpu = cpu_forward_time(orc, G_host, reps=3, warm=1)
+        line["cpu_baseline"] = {"value": E / t_cpu, "unit": "edges/s", "cores": cores, "kind": "port",
+                                "sample": "median of 3 full config-2 forwards of the oracle (reference-structured "
+                                          "PyTorch CPU restatement, not DGL)", "ms_per_step": t_cpu * 1e3}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

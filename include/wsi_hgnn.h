@@ -1,0 +1,163 @@
+/* wsi_hgnn.h - C ABI of libwsi_hgnn.so, the sm_100a CUDA library behind wsi_hgnn_b200.
+ *
+ * The reference (HKU-MedAI/WSI-HGNN) has no native code of its own: every native instruction of
+ * its hot path runs inside DGL / cuBLAS / nmslib / scipy.  Each entry point below therefore cites
+ * the reference *call site* it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *  - the caller (PyTorch caching allocator) owns every buffer, workspaces included; the library
+ *    never allocates or frees device memory and keeps no reference to caller memory;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and nothing
+ *    synchronises (graph-capturable);
+ *  - return 0 on success, <0 on error (WSI_ERR_*); the message is in wsi_last_error()
+ *    (thread-local).  No exception crosses this boundary.
+ *  - node rows are packed TYPE-MAJOR: packed id = type_ptr[t] + local id.
+ */
+#ifndef WSI_HGNN_H_
+#define WSI_HGNN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSI_ABI_VERSION 3
+
+#define WSI_ERR_ARG (-1)
+#define WSI_ERR_CUDA (-2)
+#define WSI_ERR_UNSUPPORTED (-3)
+
+/* activation codes of the typed-linear epilogue */
+#define WSI_ACT_NONE 0
+#define WSI_ACT_GELU 1 /* exact erf form == torch F.gelu default (models/HGT.py:180) */
+
+/* readout ops: pooling/avg_pooling.py:15-17, sum_pooling.py:14-16, max_pooling.py:15-17 */
+#define WSI_POOL_SUM 0
+#define WSI_POOL_MEAN 1
+#define WSI_POOL_MAX 2
+
+/* attention scoring modes */
+#define WSI_SCORE_HEAT 0 /* score = <q,k> * (w*sim+b) / sqrt(d_k)        models/HEATNet4.py:103,111 */
+#define WSI_SCORE_HGT 1  /* score = <q',k> * relation_pri[r,h] / sqrt(d_k) models/HGT.py:100         */
+
+int wsi_abi_version(void);
+const char* wsi_last_error(void);
+/* number of SMs of the current device (148 on B200); <0 on error */
+int wsi_num_sms(void);
+/* make `device` the calling thread's current CUDA device for this library (its CUDA runtime is linked statically) */
+int wsi_set_device(int device);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+int64_t wsi_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Typed linear:  Y[rows of type t] = epilogue( X[rows of type t] . W[t]^T )        (kernel K1)
+ * replaces the per-node-type nn.Linear calls  models/HEATNet4.py:100-102,134,202,219,243-245,
+ * models/HEATNet2.py:75-77,109,166,188, models/HGT.py:82-84,121,180,194.
+ *   x [N, ldx] fp32, w [T, n_out, K] fp32, bias [T, n_out] or NULL, type_ptr_host int32 [T+1].
+ * epilogue, in this order (each part optional):
+ *   v = acc + bias; v = act(v); v *= drop_mask[row, n];
+ *   if skip: a = sigmoid(skip[t]);  v = row_gate[row]!=0 ? v*a + res[row,n]*(1-a) : res[row,n]
+ *            (the sigma(skip) mix of models/HEATNet4.py:122-136 incl. its KeyError passthrough)
+ *   v *= row_scale[row]
+ * y [N, ldy] fp32.  `impl`: 0 = auto (tcgen05 tensor-core path when the shape is tile aligned,
+ * else the fp32 SIMT path), 1 = force SIMT, 2 = force tcgen05 (error if the shape does not fit).
+ * The tcgen05 path computes a 3-term bf16 split product (hi*hi + hi*lo + lo*hi, fp32 accumulate in
+ * TMEM; ~2^-16 relative) and needs `workspace` of wsi_typed_linear_workspace_bytes() bytes.
+ */
+int64_t wsi_typed_linear_workspace_bytes(int64_t n_rows, int K, int n_out, int T, int impl);
+int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w, const float* bias, int K, int n_out,
+                         const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
+                         int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,
+                         const float* row_scale, float* y, int64_t ldy, int impl, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heterogeneous edge attention forward, ONE launch for all relations of a layer        (kernel K2)
+ * replaces, per relation, apply_edges(v_dot_u) + score + edge_softmax + u_mul_e/sum and the
+ * cross-relation mean of multi_update_all:
+ *   models/HEATNet4.py:103-119 == models/HEATNet2.py:78-94  (WSI_SCORE_HEAT).
+ * Graph layout (GraphPlan): CSR over packed dst rows, in-edges of a row grouped by relation slot.
+ *   rowptr int32 [N+1], e_src int32 [E] (packed src row), e_sim fp32 [E], e_rel uint8 [E]
+ *   node_inv_r fp32 [N] : 1/R_t of the row's dst type (0 => no incoming relation => row written as 0)
+ * k/v rows are gathered by src (row strides ldk/ldv floats), q by dst.  agg [N, ldo]:
+ *   agg[v,h,:] = inv_r[v] * sum_{segments (v,r)} softmax_{e in seg}(score_e,h) . V[src e,h,:]
+ * `head_perm` != 0: the D columns of k,q,v,agg are in the "lane-grouped" physical order produced by
+ * wsi_head_perm() (requires D % 128 == 0, H a power of two <= 32); 0: natural order, any D, H.
+ * HEAT mode reads the e_linear scalars from device memory (e_w, e_b: 1 float each).
+ * If attn_out != NULL it receives the per-(edge, head) normalised attention a[e,h] ([E, H], for backward).
+ */
+int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
+                        const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
+                        const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D,
+                        int H, int head_perm, float* agg, int64_t ldo, float* attn_out, void* stream);
+
+/* Segment form used by HGT (WSI_SCORE_HGT): one work item per (dst,relation) segment.
+ *   seg_ptr int32 [S+1] edge range of segment s (dst-major order), seg_rel int32 [S] MODEL relation id,
+ *   qseg [S, ldq] = transformed query of the segment (Q[dst] . relation_att[r]^T per head,
+ *   models/HGT.py:88-92 moved to the dst side), rel_pri [R_model, H] (models/HGT.py:59,100).
+ *   out [S, ldo] = softmax-weighted sum of V[src] over the segment (before relation_msg).
+ */
+int wsi_hetero_attn_seg_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qseg,
+                            int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel, const int32_t* e_src,
+                            const float* rel_pri, int64_t n_segs, int D, int H, int head_perm, float* out,
+                            int64_t ldo, void* stream);
+
+/* Physical column order used when head_perm != 0: perm_host[p] = logical column stored at physical
+ * position p (int32 [D]).  Returns <0 if (D,H) has no lane-grouped layout. */
+int wsi_head_perm(int D, int H, int32_t* perm_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * HGT relation transforms (kernel K5)  models/HGT.py:88-93: per (relation, head) d_k x d_k maps, applied
+ * to (dst, relation) SEGMENTS instead of to every node x relation.  Segments are processed grouped by
+ * relation: grouped position i in [rel_ptr_host[r], rel_ptr_host[r+1]) belongs to model relation r.
+ *   y[y_row_idx[i], h, :] = W[r,h] . x[x_row_idx[i], h, :]      (w_kn == 0:  y_n = sum_k W[n,k] x_k)
+ *   y[y_row_idx[i], h, :] = x[x_row_idx[i], h, :] . W[r,h]      (w_kn != 0:  y_n = sum_k x_k W[k,n])
+ * x [*, ldx], w [R, H, d_k, d_k], y [*, ldy]; x_row_idx / y_row_idx int32 [S] (NULL = identity).
+ */
+int wsi_rel_transform(const float* x, int64_t ldx, const int32_t* x_row_idx, const int32_t* y_row_idx,
+                      const float* w, const int32_t* rel_ptr_host, int R, int H, int d_k, int w_kn, float* y,
+                      int64_t ldy, void* stream);
+
+/* Sum of the segment messages of each dst row, times 1/R_t:  the stack->mean of
+ * multi_update_all(..., cross_reducer='mean')  models/HGT.py:105-106.
+ *   row_seg_ptr int32 [N+1] segment range of row v; msg [S, ldm]; agg [N, ldo]. */
+int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_ptr, const float* node_inv_r,
+                        int64_t n_rows, int D, float* agg, int64_t ldo, void* stream);
+
+/* Typed LayerNorm  models/HGT.py:123-124 (nn.LayerNorm(out_dim) per node type, eps 1e-5), in place allowed.
+ *   gamma/beta [T, D]; rows of type t = [type_ptr_host[t], type_ptr_host[t+1]). */
+int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta,
+                        const int32_t* type_ptr_host, int T, int D, float eps, float* y, int64_t ldy,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Typed readout (kernel K4): dgl.readout.{sum,mean,max}_nodes(graph, 'h', ntype=)  pooling/*.py
+ *   x [N, ldx]; seg_ptr int32 [n_seg+1] row ranges of the (type, graph) segments; out [n_seg, ldo];
+ *   empty segment -> 0.  workspace: wsi_segment_pool_workspace_bytes().
+ */
+int64_t wsi_segment_pool_workspace_bytes(int64_t n_rows, int64_t n_seg, int D);
+int wsi_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, int64_t n_seg, int64_t n_rows,
+                         int D, int op, float* out, int64_t ldo, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Edge builder (kernels K6/K7): construct_graph/graph_constructor.py:256-303.
+ * wsi_knn_topk: exact k-NN in feature space, L2, self included, ordered by (distance, index);
+ *   replaces Hnsw.fit/query (graph_constructor.py:55-81,262-273).  feat [N, F] fp32 row-major.
+ *   For query rows [q_begin, q_end): nbr int32 [(q_end-q_begin), topn] = the topn nearest nodes
+ *   (rank 0 normally the node itself; the caller drops it, graph_constructor.py:270).
+ * wsi_edge_pearson: sim[e] = pearson(feat[src e], feat[dst e]) (graph_constructor.py:276-282),
+ *   etype[e] = sim > 0.
+ */
+int64_t wsi_knn_workspace_bytes(int64_t n, int F, int topn, int64_t q_begin, int64_t q_end);
+int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64_t q_begin, int64_t q_end, int32_t* nbr,
+                 float* nbr_dist, void* workspace, int64_t workspace_bytes, void* stream);
+int wsi_edge_pearson(const float* feat, int64_t n, int F, const int64_t* src, const int64_t* dst, int64_t n_edges,
+                     float* sim, uint8_t* etype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSI_HGNN_H_ */

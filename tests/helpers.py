@@ -5,7 +5,7 @@ import os
 import torch
 
 import golden_util
-from wsi_hgnn_b200.hetero_graph import HeteroGraph
+from wsi_hgnn_b200.hetero_graph import HeteroGraph, unbatch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -58,3 +58,14 @@ def rel_err(a, b):
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def run_oracle(m, G, fx=None, independent=None):
+    """Oracle logits; pack()ed graphs are the concatenation of independent per-graph forwards
+    (reference trainer/train_gnn.py:59-62)."""
+    if independent is None:
+        independent = bool(fx.get("independent")) if fx is not None else G.independent
+    with torch.no_grad():
+        if independent:
+            return torch.cat([m(g) for g in unbatch(G)], 0)
+        return m(G)

@@ -1,0 +1,83 @@
+"""GPU parity of the edge builder (k-NN + Pearson + hetero assembly) against the CPU oracle
+(oracle/knn.py: exact fp64 brute force; scipy.stats.pearsonr - the function the reference itself calls)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import knn as O
+from wsi_hgnn_b200 import ops, synthetic
+from wsi_hgnn_b200.construct_graph import GraphConstructor, Hnsw, construct_graph_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,F,radius", [(500, 64, 9), (2000, 128, 7), (33, 16, 6), (4096, 1024, 9)])
+def test_knn_edges_bit_exact(n, F, radius):
+    feats, _ = synthetic.synth_features(n, F, 3, seed=n)
+    ref = O.exact_knn_edges(feats.numpy(), radius)
+    ei, et, sim = construct_graph_arrays(feats.cuda(), radius)
+    assert ei.dtype == torch.int64 and tuple(ei.shape) == (2, n * (radius - 1))
+    assert np.array_equal(ei.cpu().numpy(), ref), "edge_index differs from the exact k-NN oracle"
+
+
+def test_knn_small_matches_literal_bruteforce_and_duplicates():
+    feats, _ = synthetic.synth_features(200, 32, 2, seed=4)
+    feats[17] = feats[3]                       # exact duplicates: ties broken by index
+    feats[150] = feats[3]
+    ref = O.exact_knn_edges_bruteforce(feats.numpy(), 6)
+    ei, _, _ = construct_graph_arrays(feats.cuda(), 6)
+    assert np.array_equal(ei.cpu().numpy(), ref)
+
+
+def test_knn_too_few_nodes_raises():
+    feats, _ = synthetic.synth_features(5, 8, 2, seed=1)
+    with pytest.raises(ValueError):
+        construct_graph_arrays(feats.cuda(), 9)
+
+
+def test_pearson_matches_scipy():
+    feats, _ = synthetic.synth_features(300, 1024, 3, seed=7)
+    ei = O.exact_knn_edges(feats.numpy(), 7)
+    g = np.random.default_rng(0)
+    rnd = g.integers(0, 300, size=(2, 600))
+    ei = np.concatenate([ei, rnd], 1)          # far pairs: correlations around 0 / negative
+    sim_ref, et_ref = O.pearson_edges_scipy(feats.numpy(), ei[:, :400])
+    sim64, et64 = O.pearson_edges(feats.numpy(), ei)
+    sim, et = ops.edge_pearson(feats.cuda(), torch.from_numpy(ei[0]).cuda(), torch.from_numpy(ei[1]).cuda())
+    sim, et = sim.cpu().numpy(), et.cpu().numpy()
+    assert np.abs(sim[:400] - sim_ref).max() < 2e-6
+    assert np.abs(sim - sim64).max() < 1e-6
+    sure = np.abs(sim64) > 1e-6
+    assert np.array_equal(et[sure], et64[sure])
+    assert (et64 == 0).sum() > 50, "the test must cover the 'neg' relation"
+
+
+def test_graph_constructor_end_to_end():
+    n, T, radius = 600, 4, 9
+    feats, ntype = synthetic.synth_features(n, 96, T, seed=11)
+    het, homo, nt = GraphConstructor({"radius": radius, "n_node_type": T}, feats.numpy(), ntype.numpy()).construct_graph()
+    ei, et, sim = O.construct_graph_arrays(feats.numpy(), ntype.numpy(), radius)
+    assert het.ntypes == [str(t) for t in range(T)]
+    assert het.num_edges() == n * (radius - 1) == homo.num_edges()
+    # rebuild the homogeneous edge list from the typed graph through the _ID back-maps
+    ids = {nt_: het.nodes[nt_].data["_ID"].cpu() for nt_ in het.ntypes}
+    got = {}
+    for ce in het.canonical_etypes:
+        s, d = het.edges(etype=ce)
+        for a, b, r in zip(ids[ce[0]][s.cpu()].tolist(), ids[ce[2]][d.cpu()].tolist(),
+                           het.edata["sim"][ce].cpu().tolist() if isinstance(het.edata["sim"], dict) else het.edata["sim"].cpu().tolist()):
+            got[(a, b)] = (ce[1], r)
+    assert len(got) == ei.shape[1]
+    for e in range(ei.shape[1]):
+        name, r = got[(int(ei[0, e]), int(ei[1, e]))]
+        assert abs(r - sim[e]) < 1e-6
+        if abs(sim[e]) > 1e-6:
+            assert name == ("pos" if et[e] else "neg")
+
+
+def test_hnsw_query_surface():
+    feats, _ = synthetic.synth_features(100, 16, 2, seed=2)
+    m = Hnsw(space="l2").fit(feats.numpy())
+    all_nbr = m.query_all(5).cpu().numpy()
+    one = m.query(feats[10].numpy(), 5)
+    assert list(one) == list(all_nbr[10])

@@ -1,0 +1,140 @@
+"""GPU parity of the model forwards (through the C-ABI kernels) against the committed golden fixtures -
+outputs of the reference's own model files - and against the CPU oracle on larger seeded inputs."""
+import pytest
+import torch
+
+import helpers
+from wsi_hgnn_b200 import synthetic
+from wsi_hgnn_b200.hetero_graph import batch, pack
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3      # north_star: "within 1e-3 relative fp32"
+
+
+@pytest.mark.parametrize("name", helpers.golden_cases())
+def test_forward_matches_reference_golden(name):
+    fx, G, m = helpers.golden_setup(name, helpers.build_ours)
+    m = m.cuda()
+    with torch.no_grad():
+        out = m(G.to("cuda"))
+    assert out.shape == fx["logits_fp32"].shape
+    err = helpers.rel_err(out, fx["logits_fp64"])
+    assert err < TOL, f"{name}: rel err {err:.3e}"
+
+
+def _pair(model, n_types, kwargs, seed=611):
+    ours = helpers.build_ours(model, n_types, kwargs)
+    orc = helpers.build_oracle(model, n_types, kwargs)
+    import golden_util
+    golden_util.fill_params(ours, seed)
+    orc.load_state_dict(ours.state_dict(), strict=True)       # same keys and shapes by construction
+    return ours.cuda().eval(), orc.eval()
+
+
+def _check(ours, orc, G, tol=TOL, embeddings=True):
+    ref = helpers.run_oracle(orc, G, independent=G.independent)
+    with torch.no_grad():
+        out = ours(G.to("cuda"))
+    err = helpers.rel_err(out, ref)
+    assert err < tol, f"logits rel err {err:.3e}"
+    if embeddings and not G.independent:
+        with torch.no_grad():
+            _, emb = ours(G.to("cuda"), return_embeddings=True)
+            _, emb_ref = orc(G, return_embeddings=True)
+        for nt in G.ntypes:
+            if G.num_nodes(nt):
+                e = helpers.rel_err(emb[nt], emb_ref[nt])
+                assert e < tol, f"node embeddings of type {nt}: rel err {e:.3e}"
+
+
+def test_config1_heatnet4():
+    """BASELINE config 1: 2 node types, 1k nodes, 5k edges, d=64, 1-layer HEATNet4."""
+    G = synthetic.synth_slide_graph(1000, 64, 2, 5, seed=0, noise_edges=0.2)
+    ours, orc = _pair("HEATNet4", 2, dict(in_dim=64, hidden_dim=64, out_dim=2, n_layers=1, n_heads=4, dropuout=0.2))
+    _check(ours, orc, G)
+
+
+@pytest.mark.parametrize("model", ["HEATNet4", "HEATNet2"])
+def test_config2_shape_reduced(model):
+    """BASELINE config 2 shape (3 types, k=5, d=512, 3 layers) at 2k nodes / in_dim 256 so the oracle runs in seconds."""
+    G = synthetic.synth_slide_graph(2048, 256, 3, 5, seed=1, noise_edges=0.2)
+    ours, orc = _pair(model, 3, dict(in_dim=256, hidden_dim=512, out_dim=2, n_layers=3, n_heads=4, dropuout=0.2))
+    _check(ours, orc, G)
+
+
+def test_config2_full_size_heatnet4():
+    """BASELINE config 2 at full size: 8192 nodes, 40 960 edges, F=1024, D=512, 3 layers."""
+    G = synthetic.synth_slide_graph(8192, 1024, 3, 5, seed=1)
+    ours, orc = _pair("HEATNet4", 3, dict(in_dim=1024, hidden_dim=512, out_dim=2, n_layers=3, n_heads=4, dropuout=0.2))
+    _check(ours, orc, G, embeddings=False)
+
+
+@pytest.mark.parametrize("hidden,heads", [(512, 4), (200, 4)])
+def test_config3_shape_hgt(hidden, heads):
+    """BASELINE config 3 shape: batch of graphs, 6 node types, k=6, HGT with nt-pooling readout."""
+    gs = [synthetic.synth_slide_graph(300 + 40 * i, 96, 6, 6, seed=100 + i, skew=True, noise_edges=0.3) for i in range(4)]
+    ours, orc = _pair("HGT", 6, dict(in_dim=96, hidden_dim=hidden, out_dim=2, n_layers=3, n_heads=heads, use_norm=True))
+    _check(ours, orc, pack(gs), embeddings=False)
+
+
+def test_batch_equals_cat_of_forwards():
+    gs = [synthetic.random_hetero_graph([40, 30, 20], 500, 32, seed=s) for s in (1, 2, 3)]
+    ours, _ = _pair("HEATNet4", 3, dict(in_dim=32, hidden_dim=128, out_dim=2, n_layers=2, n_heads=4, dropuout=0.0))
+    with torch.no_grad():
+        one = torch.cat([ours(g.to("cuda")) for g in gs], 0)
+        b = ours(batch(gs).to("cuda"))
+        p = ours(pack(gs).to("cuda"))
+    assert helpers.rel_err(b, one) < 1e-5 and helpers.rel_err(p, one) < 1e-5
+
+
+def test_hub_and_isolated_nodes():
+    """in-degree >> 32 (several 32-edge chunks per row) and nodes without in-edges."""
+    G = synthetic.random_hetero_graph([300, 200], 900, 48, seed=9, hub=700)
+    for model, kw in [("HEATNet4", dict(in_dim=48, hidden_dim=256, out_dim=2, n_layers=2, n_heads=8, dropuout=0.0)),
+                      ("HEATNet4", dict(in_dim=48, hidden_dim=96, out_dim=2, n_layers=2, n_heads=3, dropuout=0.0)),
+                      ("HGT", dict(in_dim=48, hidden_dim=128, out_dim=2, n_layers=2, n_heads=4, use_norm=True))]:
+        ours, orc = _pair(model, 2, kw)
+        _check(ours, orc, G)
+
+
+def test_node_permutation_invariance_full_size():
+    """Size-independent property at config-2 size: relabelling nodes (and shuffling the edge list) leaves the
+    logits unchanged."""
+    n, T, k = 8192, 3, 5
+    feats, ntype = synthetic.synth_features(n, 256, T, seed=5)
+    nbr = synthetic.host_knn(feats, k)
+    src = torch.arange(n).repeat_interleave(k)
+    dst = nbr.reshape(-1)
+    sim = synthetic.pearson(feats, src, dst)
+    et = (sim > 0).long()
+    from wsi_hgnn_b200.hetero_graph import to_heterogeneous
+    names = [str(t) for t in range(T)]
+    G1 = to_heterogeneous(src, dst, ntype, et, names, ["neg", "pos"], {"feat": feats}, {"sim": sim})
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(n, generator=g)             # new id of old node i
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n)
+    eperm = torch.randperm(src.numel(), generator=g)
+    G2 = to_heterogeneous(perm[src][eperm], perm[dst][eperm], ntype[inv], et[eperm], names, ["neg", "pos"],
+                          {"feat": feats[inv]}, {"sim": sim[eperm]})
+    ours, _ = _pair("HEATNet4", T, dict(in_dim=256, hidden_dim=512, out_dim=2, n_layers=3, n_heads=4, dropuout=0.0))
+    with torch.no_grad():
+        a = ours(G1.to("cuda"))
+        b = ours(G2.to("cuda"))
+    assert helpers.rel_err(a, b) < 1e-4
+
+
+def test_empty_relation_free_graph_passthrough():
+    """A graph without edges: every type takes the KeyError passthrough (models/HEATNet4.py:129-133)."""
+    from wsi_hgnn_b200.hetero_graph import HeteroGraph
+    g = torch.Generator().manual_seed(3)
+    G = HeteroGraph({"0": 7, "1": 5}, {}, {"0": {"feat": torch.randn(7, 16, generator=g)},
+                                           "1": {"feat": torch.randn(5, 16, generator=g)}})
+    ours, orc = _pair("HEATNet4", 2, dict(in_dim=16, hidden_dim=32, out_dim=2, n_layers=2, n_heads=4, dropuout=0.0))
+    with torch.no_grad():
+        out = ours(G.to("cuda"))
+        h = {nt: orc.adapt_ws[int(nt)](G.nodes[nt].data["feat"]) for nt in G.ntypes}
+        parts = [orc.linears_prediction[nt](h[nt].mean(0, keepdim=True)) for nt in G.ntypes]
+        ref = orc.head(orc.head_1(orc.head_2(torch.cat(parts, 1))))
+    assert helpers.rel_err(out, ref) < 1e-4

@@ -1,0 +1,202 @@
+"""GPU parity of the individual C-ABI kernels against the CPU oracle primitives (oracle/primitives.py)
+and fp64 torch restatements, on seeded random inputs incl. the edge cases of the domain
+(empty types / segments, ragged rows, hubs, zero in-degree)."""
+import math
+
+import pytest
+import torch
+
+from oracle import primitives as P
+from wsi_hgnn_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("counts,K,n_out", [([70, 0, 133], 48, 96), ([1, 2, 3], 7, 5), ([300], 200, 200),
+                                            ([128, 256], 512, 1536), ([0, 0, 5], 16, 256)])
+@pytest.mark.parametrize("impl", [ops.IMPL_SIMT, ops.IMPL_AUTO])
+def test_typed_linear_epilogues(counts, K, n_out, impl):
+    g = torch.Generator().manual_seed(sum(counts) + K)
+    T = len(counts)
+    ptr = [0]
+    for c in counts:
+        ptr.append(ptr[-1] + c)
+    N = ptr[-1]
+    x = torch.randn(N, K, generator=g)
+    w = torch.randn(T, n_out, K, generator=g) / math.sqrt(K)
+    b = torch.randn(T, n_out, generator=g)
+    skip = torch.randn(T, generator=g)
+    res = torch.randn(N, n_out, generator=g)
+    mask = (torch.rand(N, n_out, generator=g) > 0.3).float() / 0.7
+    gate = (torch.rand(N, generator=g) > 0.25).float()
+    scale = (torch.rand(N, generator=g) > 0.5).float()
+
+    def ref(act=False, use_skip=False, use_mask=False, use_gate=False, use_scale=False):
+        out = torch.empty(N, n_out, dtype=torch.float64)
+        for t in range(T):
+            a, z = ptr[t], ptr[t + 1]
+            v = x[a:z].double() @ w[t].double().T + b[t].double()
+            if act:
+                v = torch.nn.functional.gelu(v)
+            if use_mask:
+                v = v * mask[a:z].double()
+            if use_skip:
+                al = torch.sigmoid(skip[t].double())
+                mixed = v * al + res[a:z].double() * (1 - al)
+                v = torch.where(gate[a:z, None] != 0, mixed, res[a:z].double()) if use_gate else mixed
+            if use_scale:
+                v = v * scale[a:z, None].double()
+            out[a:z] = v
+        return out
+
+    c = lambda t: t.cuda()
+    y = ops.typed_linear(c(x), c(w), c(b), ptr, impl=impl)
+    assert rel(y, ref()) < 2e-5
+    y = ops.typed_linear(c(x), c(w), c(b), ptr, act=ops.ACT_GELU, impl=impl)
+    assert rel(y, ref(act=True)) < 2e-5
+    y = ops.typed_linear(c(x), c(w), c(b), ptr, skip=c(skip), res=c(res), drop_mask=c(mask), row_gate=c(gate),
+                         row_scale=c(scale), impl=impl)
+    assert rel(y, ref(use_skip=True, use_mask=True, use_gate=True, use_scale=True)) < 2e-5
+    # strided input / output views (the K|V|Q fused buffer is sliced by column)
+    big = torch.zeros(N, n_out + 8, device="cuda")
+    ops.typed_linear(c(x), c(w), None, ptr, out=big[:, 8:], impl=impl)
+    assert rel(big[:, 8:], ref() - torch.cat([b[t].double().expand(counts[t], n_out) for t in range(T)])) < 2e-5
+    assert float(big[:, :8].abs().sum()) == 0.0
+
+
+def _random_csr(n_dst, n_src, n_edges, n_rel, g, hub=0, isolated=0.2):
+    dst = torch.randint(0, n_dst, (n_edges,), generator=g)
+    iso = torch.rand(n_dst, generator=g) < isolated
+    dst = dst[~iso[dst]]
+    if hub:
+        dst = torch.cat([dst, torch.zeros(hub, dtype=torch.int64)])
+    E = dst.numel()
+    src = torch.randint(0, n_src, (E,), generator=g)
+    rel = torch.randint(0, n_rel, (E,), generator=g)
+    sim = torch.rand(E, generator=g) * 2 - 1
+    order = torch.argsort(dst * 256 + rel, stable=True)
+    dst, src, rel, sim = dst[order], src[order], rel[order], sim[order]
+    rowptr = torch.zeros(n_dst + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n_dst), 0)
+    return rowptr, src, dst, rel, sim
+
+
+def _heat_attn_ref(k, v, q, src, dst, rel, sim, inv_r, ew, eb, H, n_rel):
+    """per relation: v_dot_u -> score -> edge_softmax -> u_mul_e/sum; then sum over relations * inv_r."""
+    N, D = q.shape
+    dk = D // H
+    k3, v3, q3 = (t.double().view(-1, H, dk) for t in (k, v, q))
+    out = torch.zeros(N, H, dk, dtype=torch.float64)
+    attn = torch.zeros(src.numel(), H, dtype=torch.float64)
+    for r in range(n_rel):
+        m = torch.nonzero(rel == r).reshape(-1)
+        if m.numel() == 0:
+            continue
+        t = P.v_dot_u(q3, k3, src[m], dst[m])
+        score = t.sum(-1) * (ew * sim[m].double() + eb).view(-1, 1) / math.sqrt(dk)
+        a = P.edge_softmax(score, dst[m], N)
+        attn[m] = a
+        out += P.u_mul_e_sum(v3, a.unsqueeze(-1), src[m], dst[m], N)
+    return (out * inv_r.double().view(-1, 1, 1)).view(N, D), attn
+
+
+@pytest.mark.parametrize("D,H,perm", [(128, 4, True), (256, 8, True), (512, 4, True), (512, 1, True),
+                                      (1024, 32, True), (384, 2, True), (128, 4, False), (200, 4, False),
+                                      (64, 4, False), (96, 3, False), (512, 4, False), (32, 4, False)])
+def test_hetero_attn_fwd(D, H, perm):
+    g = torch.Generator().manual_seed(D * 7 + H)
+    n_dst, n_rel = 257, 5
+    rowptr, src, dst, rel, sim = _random_csr(n_dst, n_dst, 1500, n_rel, g, hub=150)
+    k = torch.randn(n_dst, D, generator=g)
+    v = torch.randn(n_dst, D, generator=g)
+    q = torch.randn(n_dst, D, generator=g) * 0.5
+    inv_r = torch.full((n_dst,), 1.0 / n_rel)
+    inv_r[torch.rand(n_dst, generator=g) < 0.1] = 0.0          # passthrough rows
+    ew, eb = 0.9, -0.3
+    ref, attn_ref = _heat_attn_ref(k, v, q, src, dst, rel, sim, inv_r, ew, eb, H, n_rel)
+    kvq = torch.cat([k, v, q], 1)
+    if perm:
+        p = ops.head_perm(D, H)
+        kvq = torch.cat([k[:, p], v[:, p], q[:, p]], 1)
+    kvq = kvq.cuda()
+    c = lambda t, dt: t.to(dt).cuda()
+    agg, attn = ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], c(rowptr, torch.int32),
+                                c(src, torch.int32), c(sim, torch.float32), c(rel, torch.uint8), inv_r.cuda(),
+                                torch.tensor([[ew]]).cuda(), torch.tensor([eb]).cuda(), D, H, perm, want_attn=True)
+    agg = agg.cpu()
+    if perm:
+        un = torch.empty_like(agg)
+        un[:, p] = agg
+        agg = un
+    assert rel_ok(agg, ref, 2e-5)
+    live = inv_r[dst] != 0
+    assert rel_ok(attn.cpu()[live], attn_ref[live], 2e-5)
+    assert float(agg[inv_r == 0].abs().sum()) == 0.0
+
+
+def rel_ok(a, b, tol):
+    e = rel(a, b)
+    assert e < tol, f"rel err {e:.3e}"
+    return True
+
+
+@pytest.mark.parametrize("op", ["sum", "mean", "max"])
+@pytest.mark.parametrize("D", [512, 200, 5])
+def test_segment_pool(op, D):
+    g = torch.Generator().manual_seed(D)
+    lens = [0, 17, 1, 0, 300, 2500, 0, 64]
+    ptr = [0]
+    for n in lens:
+        ptr.append(ptr[-1] + n)
+    x = torch.randn(ptr[-1], D, generator=g)
+    ref = P.segment_readout(x.double(), torch.tensor(lens), op)
+    out = ops.segment_pool(x.cuda(), torch.tensor(ptr, dtype=torch.int32).cuda(), len(lens), op)
+    assert rel(out, ref) < 1e-5
+    # one huge segment: goes through the split + finish path
+    x = torch.randn(40000, D, generator=g)
+    ref = P.segment_readout(x.double(), torch.tensor([40000]), op)
+    out = ops.segment_pool(x.cuda(), torch.tensor([0, 40000], dtype=torch.int32).cuda(), 1, op)
+    assert rel(out, ref) < 1e-5
+
+
+def test_typed_layernorm():
+    g = torch.Generator().manual_seed(1)
+    counts, D = [33, 0, 80], 200
+    ptr = [0, 33, 33, 113]
+    x = torch.randn(113, D, generator=g) * 3 + 1
+    gamma = torch.randn(3, D, generator=g)
+    beta = torch.randn(3, D, generator=g)
+    ref = torch.cat([torch.nn.functional.layer_norm(x[ptr[t]:ptr[t + 1]].double(), (D,), gamma[t].double(),
+                                                    beta[t].double(), 1e-5) for t in range(3)])
+    y = ops.typed_layernorm(x.cuda(), gamma.cuda(), beta.cuda(), ptr)
+    assert rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("dk,H", [(50, 4), (128, 4), (32, 8)])
+def test_rel_transform(dk, H):
+    g = torch.Generator().manual_seed(dk)
+    R, S, Nrows = 6, 300, 120
+    seg_rel = torch.randint(0, R, (S,), generator=g)
+    seg_rel[seg_rel == 2] = 3                       # an empty relation group
+    seg_row = torch.randint(0, Nrows, (S,), generator=g)
+    x = torch.randn(Nrows, H * dk, generator=g)
+    w = torch.randn(R, H, dk, dk, generator=g) / math.sqrt(dk)
+    order = torch.argsort(seg_rel, stable=True)
+    rel_ptr = [0] + torch.cumsum(torch.bincount(seg_rel, minlength=R), 0).tolist()
+    xs = x[seg_row].double().view(S, H, dk)
+    for w_kn in (False, True):
+        eq = "shk,shkn->shn" if w_kn else "shk,shnk->shn"
+        ref = torch.einsum(eq, xs, w[seg_rel].double()).reshape(S, H * dk)
+        y = ops.rel_transform(x.cuda(), seg_row[order].to(torch.int32).cuda(), order.to(torch.int32).cuda(), w.cuda(),
+                              ops.host_i32(rel_ptr), R, H, dk, w_kn, S)
+        assert rel(y, ref) < 2e-5
+
+
+def test_ops_reject_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        ops.typed_linear(torch.zeros(4, 4), torch.zeros(1, 4, 4), None, [0, 4])

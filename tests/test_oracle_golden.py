@@ -10,8 +10,7 @@ import helpers
 @pytest.mark.parametrize("name", helpers.golden_cases())
 def test_oracle_matches_reference_golden(name):
     fx, G, m = helpers.golden_setup(name, helpers.build_oracle)
-    with torch.no_grad():
-        out32 = m(G)
+    out32 = helpers.run_oracle(m, G, fx)
     assert out32.shape == fx["logits_fp32"].shape
     assert helpers.rel_err(out32, fx["logits_fp32"]) < 2e-5
     # fp64 oracle vs fp64 reference: pins the semantics far below the 1e-3 product tolerance
@@ -21,8 +20,7 @@ def test_oracle_matches_reference_golden(name):
             mod.e_linear.float()           # the reference casts sim to fp32 (models/HEATNet4.py:103)
     for nt in G.ntypes:
         G.nodes[nt].data["feat"] = G.nodes[nt].data["feat"].double()
-    with torch.no_grad():
-        out64 = m64(G)
+    out64 = helpers.run_oracle(m64, G, fx)
     assert helpers.rel_err(out64, fx["logits_fp64"]) < 1e-10
 
 

@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dgl_shim  # noqa: E402
 import golden_util  # noqa: E402
 from wsi_hgnn_b200 import synthetic  # noqa: E402
-from wsi_hgnn_b200.hetero_graph import batch  # noqa: E402
+from wsi_hgnn_b200.hetero_graph import batch, pack  # noqa: E402
 
 # HEATNet4.py:240 hard-codes `.cuda()` for empty node types; on this CPU-only box make it a no-op.
 torch.Tensor.cuda = lambda self, *a, **k: self
@@ -61,6 +61,30 @@ CASES = [
     dict(name="hgt_dk50_T2_nonorm_sum", model="HGT",
          graph=lambda: synthetic.random_hetero_graph([16, 12], 110, 20, seed=12),
          kw=dict(in_dim=20, hidden_dim=200, out_dim=2, n_layers=2, n_heads=4, use_norm=False, graph_pooling_type="sum")),
+    # shapes that take the lane-grouped vector attention kernel (D % 128 == 0) and the tcgen05 typed GEMM
+    dict(name="heat4_vec_D128_T3", model="HEATNet4",
+         graph=lambda: synthetic.random_hetero_graph([70, 50, 40], 700, 64, seed=21, hub=45),
+         kw=dict(in_dim=64, hidden_dim=128, out_dim=2, n_layers=2, n_heads=4, dropuout=0.2, graph_pooling_type="mean")),
+    dict(name="heat4_vec_D512_T3_knn", model="HEATNet4",
+         graph=lambda: synthetic.synth_slide_graph(300, 128, 3, 5, seed=22, noise_edges=0.25),
+         kw=dict(in_dim=128, hidden_dim=512, out_dim=2, n_layers=3, n_heads=4, dropuout=0.2, graph_pooling_type="mean")),
+    dict(name="heat2_vec_D256_H8_T2", model="HEATNet2",
+         graph=lambda: synthetic.random_hetero_graph([90, 60], 600, 64, seed=23),
+         kw=dict(in_dim=64, hidden_dim=256, out_dim=3, n_layers=2, n_heads=8, dropuout=0.2, graph_pooling_type="sum")),
+    dict(name="hgt_D128_T3_norm", model="HGT",
+         graph=lambda: synthetic.random_hetero_graph([60, 45, 30], 600, 64, seed=24, hub=40),
+         kw=dict(in_dim=64, hidden_dim=128, out_dim=2, n_layers=3, n_heads=4, use_norm=True, graph_pooling_type="mean")),
+    # the trainer's tuple branch (trainer/train_gnn.py:59-62): cat of independent forwards of graphs with
+    # DIFFERENT relation sets / empty types, which pack() reproduces in one launch
+    dict(name="heat4_pack3_T3", model="HEATNet4", independent=True,
+         graph=lambda: [synthetic.random_hetero_graph([14, 9, 11], 60, 16, seed=31),
+                        synthetic.random_hetero_graph([10, 0, 12], 25, 16, seed=32),
+                        synthetic.random_hetero_graph([6, 7, 5], 12, 16, seed=33)],
+         kw=dict(in_dim=16, hidden_dim=32, out_dim=2, n_layers=2, n_heads=4, dropuout=0.2, graph_pooling_type="mean")),
+    dict(name="hgt_pack2_T2", model="HGT", independent=True,
+         graph=lambda: [synthetic.random_hetero_graph([12, 9], 50, 16, seed=34),
+                        synthetic.random_hetero_graph([8, 11], 9, 16, seed=35)],
+         kw=dict(in_dim=16, hidden_dim=32, out_dim=3, n_layers=2, n_heads=4, use_norm=True, graph_pooling_type="mean")),
 ]
 
 
@@ -75,6 +99,10 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     for case in CASES:
         G = case["graph"]()
+        graphs = [G]
+        if case.get("independent"):
+            graphs = G
+            G = pack(graphs)
         T = len(G.ntypes)
         node_dict = {str(i): i for i in range(T)}
         kw = dict(case["kw"])
@@ -91,13 +119,17 @@ def main():
             for mod in m.modules():             # the reference casts sim to fp32 before e_linear (HEATNet4.py:103)
                 if hasattr(mod, "e_linear"):
                     mod.e_linear.float()
-            sg = dgl_shim.shim_graph_from(G)
-            for nt in sg.ntypes:
-                sg._nframes[nt]["feat"] = sg._nframes[nt]["feat"].to(dt)
-            with torch.no_grad():
-                outs[dt] = m(sg).detach().clone()
+            rows = []
+            for g1 in graphs:
+                sg = dgl_shim.shim_graph_from(g1)
+                for nt in sg.ntypes:
+                    sg._nframes[nt]["feat"] = sg._nframes[nt]["feat"].to(dt)
+                with torch.no_grad():
+                    rows.append(m(sg).detach().clone())
+            outs[dt] = torch.cat(rows, 0)
         ref.to(torch.float32)
         fx = dict(name=case["name"], model=case["model"], kwargs=kw, graph=G.state(),
+                  independent=bool(case.get("independent")),
                   param_seed=PARAM_SEED, param_checksum=chk,
                   param_shapes={k: tuple(v.shape) for k, v in ref.state_dict().items()},
                   logits_fp32=outs[torch.float32], logits_fp64=outs[torch.float64],

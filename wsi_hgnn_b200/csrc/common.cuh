@@ -1,0 +1,87 @@
+// Shared helpers for the wsi_hgnn_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/wsi_hgnn.h"
+
+#define WSI_OK 0
+
+// Row groups of a grouped GEMM: node types of a typed linear (T <= 6 in the reference configs) or
+// relations of a relation-grouped transform (R <= 72).
+#define WSI_MAX_TYPES 128
+
+void wsi_set_error(const char* fmt, ...);
+
+#define WSI_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      wsi_set_error(__VA_ARGS__);                \
+      return WSI_ERR_ARG;                        \
+    }                                            \
+  } while (0)
+
+#define WSI_CHECK_CUDA(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      wsi_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return WSI_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+void wsi_count_launch();
+#define WSI_CHECK_LAUNCH()              \
+  do {                                  \
+    wsi_count_launch();                 \
+    WSI_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// Row ranges of the groups of a packed [N, *] matrix, passed to kernels by value.
+struct TypeSegs {
+  int T;
+  int ptr[WSI_MAX_TYPES + 1];        // row range of group t: [ptr[t], ptr[t+1])
+  int tile_start[WSI_MAX_TYPES + 1]; // first m-tile of group t (prefix of ceil(n_t / BM))
+};
+
+static inline int wsi_make_segs(TypeSegs* s, const int32_t* type_ptr_host, int T, int BM) {
+  if (T < 1 || T > WSI_MAX_TYPES) return -1;
+  s->T = T;
+  s->tile_start[0] = 0;
+  for (int t = 0; t <= T; ++t) s->ptr[t] = type_ptr_host[t];
+  for (int t = 0; t < T; ++t) {
+    int n = s->ptr[t + 1] - s->ptr[t];
+    if (n < 0) return -1;
+    s->tile_start[t + 1] = s->tile_start[t] + (n + BM - 1) / BM;
+  }
+  return 0;
+}
+
+// group of m-tile `tile` (binary search over the tile prefix; empty groups are skipped)
+__device__ __forceinline__ int wsi_tile_group(const TypeSegs& segs, int tile) {
+  int lo = 0, hi = segs.T - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (segs.tile_start[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  // tile_start is non-decreasing; several empty groups may share the value - take the one that owns the tile
+  while (lo + 1 < segs.T && segs.tile_start[lo + 1] <= tile) ++lo;
+  return lo;
+}
+
+__device__ __forceinline__ float wsi_gelu(float x) {   // exact erf form == torch F.gelu default
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float wsi_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~2^-17 relative.
+__device__ __forceinline__ void wsi_split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+static inline cudaStream_t wsi_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -1,0 +1,342 @@
+// Heterogeneous edge attention forward (kernel K2): one launch per layer for ALL relations.
+//
+// Replaces, per relation, the reference's apply_edges(fn.v_dot_u) + score scaling + dgl edge_softmax +
+// update_all(u_mul_e, sum) and the cross-relation mean of multi_update_all
+// (models/HEATNet4.py:103-119 == models/HEATNet2.py:78-94; models/HGT.py:95-106).
+//
+// Work item = one dst row of the relation-grouped CSR (HEAT) or one (dst, relation) segment (HGT).
+// One warp per work item: the 32 lanes span the D feature columns, the source rows K[src], V[src] are
+// gathered with coalesced 16-byte loads (512 B per warp instruction), the per-(segment, head) softmax is
+// computed online (running max / running sum, rescaled accumulator) so every gathered byte is touched once.
+//
+// HBM-bound: algorithmic bytes per edge = 2*D*4 (K and V rows) + 9 (src id, sim, relation slot);
+// per dst row = 2*D*4 (q in, agg out) + 8 (rowptr, 1/R).
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARPS = 8;
+constexpr unsigned FULL = 0xffffffffu;
+
+enum { MODE_HEAT = 0, MODE_HGT_SEG = 1 };
+
+struct AttnArgs {
+  const float* K; int64_t ldk;
+  const float* V; int64_t ldv;
+  const float* Q; int64_t ldq;
+  const int* rowptr;          // [n_items + 1] edge range of the work item
+  const int* e_src;
+  const float* e_sim;         // HEAT
+  const uint8_t* e_rel;       // HEAT: relation slot per edge (segment boundaries inside a row)
+  const float* inv_r;         // HEAT: 1/R_t per row (0 => passthrough row, written as 0)
+  const float* e_w; const float* e_b;   // HEAT: e_linear scalars (device)
+  const int* seg_rel;         // HGT: model relation id per segment
+  const float* rel_pri;       // HGT: [R_model, H]
+  int n_items;
+  int D, H, dk;
+  float inv_sqrt_dk;
+  float* out; int64_t ldo;
+  float* attn;                // optional [E, H] normalised attention (for backward)
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// Lane-grouped fast path: D = 128*NV, H | 32.  Lane l owns float4 slots {i*32 + l}, all of head l / G
+// (G = 32/H lanes per head) thanks to the head_perm column order (wsi_head_perm).
+template <int NV, int MODE>
+__global__ void __launch_bounds__(WARPS * 32) attn_fwd_vec_kernel(AttnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int G = 32 / a.H;
+  const int head = lane / G;
+  const int n_warps = gridDim.x * WARPS;
+  float ew = 0.f, eb = 0.f;
+  if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
+
+  for (int item = blockIdx.x * WARPS + (threadIdx.x >> 5); item < a.n_items; item += n_warps) {
+    float4 out[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int beg = __ldg(a.rowptr + item), end = __ldg(a.rowptr + item + 1);
+    float invr = 1.f, seg_scale = 0.f;
+    if (MODE == MODE_HEAT) invr = __ldg(a.inv_r + item);
+    else seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + item) * a.H + head) * a.inv_sqrt_dk;
+
+    if (invr != 0.f && end > beg) {
+      float4 q[NV];
+      const float* qr = a.Q + (int64_t)item * a.ldq;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) q[i] = ld4(qr + (i * 32 + lane) * 4);
+      float m = -INFINITY, ssum = 0.f;
+      float4 acc[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cur_rel = -1, seg_beg = beg;
+
+      for (int base = beg; base < end; base += 32) {
+        const int n = min(32, end - base);
+        int my_src = 0, my_rel = 0;
+        float my_sim = 0.f;
+        if (lane < n) {
+          my_src = __ldg(a.e_src + base + lane);
+          if (MODE == MODE_HEAT) { my_sim = __ldg(a.e_sim + base + lane); my_rel = __ldg(a.e_rel + base + lane); }
+        }
+        for (int j = 0; j < n; ++j) {
+          const int src = __shfl_sync(FULL, my_src, j);
+          float scale = seg_scale;
+          if (MODE == MODE_HEAT) {
+            const int rel = __shfl_sync(FULL, my_rel, j);
+            const float sim = __shfl_sync(FULL, my_sim, j);
+            if (rel != cur_rel) {                       // warp-uniform: close the running segment
+              if (cur_rel >= 0) {
+                const float inv = 1.f / ssum;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                  out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
+                  out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
+                  acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (a.attn && lane % G == 0)
+                  for (int e = seg_beg; e < base + j; ++e) {
+                    float* p = a.attn + (int64_t)e * a.H + head;
+                    *p = __expf(*p - m) * inv;
+                  }
+              }
+              m = -INFINITY; ssum = 0.f; cur_rel = rel; seg_beg = base + j;
+            }
+            scale = fmaf(ew, sim, eb) * a.inv_sqrt_dk;
+          }
+          const float* kr = a.K + (int64_t)src * a.ldk;
+          const float* vr = a.V + (int64_t)src * a.ldv;
+          float4 kk[NV], vv[NV];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) kk[i] = ld4(kr + (i * 32 + lane) * 4);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) vv[i] = ld4(vr + (i * 32 + lane) * 4);
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            d = fmaf(q[i].x, kk[i].x, d); d = fmaf(q[i].y, kk[i].y, d);
+            d = fmaf(q[i].z, kk[i].z, d); d = fmaf(q[i].w, kk[i].w, d);
+          }
+          for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+          const float s = d * scale;
+          if (a.attn && lane % G == 0) a.attn[(int64_t)(base + j) * a.H + head] = s;
+          const float mn = fmaxf(m, s);
+          const float corr = __expf(m - mn);            // m = -inf on the first edge -> 0
+          const float p = __expf(s - mn);
+          ssum = fmaf(ssum, corr, p);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            acc[i].x = fmaf(acc[i].x, corr, p * vv[i].x); acc[i].y = fmaf(acc[i].y, corr, p * vv[i].y);
+            acc[i].z = fmaf(acc[i].z, corr, p * vv[i].z); acc[i].w = fmaf(acc[i].w, corr, p * vv[i].w);
+          }
+          m = mn;
+        }
+      }
+      {                                                 // close the last segment
+        const float inv = 1.f / ssum;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          out[i].x = fmaf(acc[i].x, inv, out[i].x) * invr; out[i].y = fmaf(acc[i].y, inv, out[i].y) * invr;
+          out[i].z = fmaf(acc[i].z, inv, out[i].z) * invr; out[i].w = fmaf(acc[i].w, inv, out[i].w) * invr;
+        }
+        if (a.attn && lane % G == 0)
+          for (int e = seg_beg; e < end; ++e) {
+            float* p = a.attn + (int64_t)e * a.H + head;
+            *p = __expf(*p - m) * inv;
+          }
+      }
+    }
+    float* o = a.out + (int64_t)item * a.ldo;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic path: any D, H (natural column order).  One warp per work item, heads processed one after the
+// other; lane l owns columns {l + 32 j} of the current head (MAXJ >= ceil(d_k / 32)).
+template <int MAXJ, int MODE>
+__global__ void __launch_bounds__(WARPS * 32) attn_fwd_generic_kernel(AttnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int n_warps = gridDim.x * WARPS;
+  const int dk = a.dk;
+  float ew = 0.f, eb = 0.f;
+  if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
+
+  for (int item = blockIdx.x * WARPS + (threadIdx.x >> 5); item < a.n_items; item += n_warps) {
+    const int beg = __ldg(a.rowptr + item), end = __ldg(a.rowptr + item + 1);
+    float invr = 1.f;
+    int model_rel = 0;
+    if (MODE == MODE_HEAT) invr = __ldg(a.inv_r + item);
+    else model_rel = __ldg(a.seg_rel + item);
+    const bool live = invr != 0.f && end > beg;
+    for (int h = 0; h < a.H; ++h) {
+      float out[MAXJ];
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) out[j] = 0.f;
+      if (live) {
+        const float seg_scale = MODE == MODE_HEAT ? 0.f : __ldg(a.rel_pri + (int64_t)model_rel * a.H + h) * a.inv_sqrt_dk;
+        float q[MAXJ], acc[MAXJ];
+        const float* qr = a.Q + (int64_t)item * a.ldq + h * dk;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          int c = lane + 32 * j;
+          q[j] = c < dk ? __ldg(qr + c) : 0.f;
+          acc[j] = 0.f;
+        }
+        float m = -INFINITY, ssum = 0.f;
+        int cur_rel = -1, seg_beg = beg;
+        for (int e = beg; e < end; ++e) {
+          const int src = __ldg(a.e_src + e);
+          float scale = seg_scale;
+          if (MODE == MODE_HEAT) {
+            const int rel = __ldg(a.e_rel + e);
+            if (rel != cur_rel) {
+              if (cur_rel >= 0) {
+                const float inv = 1.f / ssum;
+#pragma unroll
+                for (int j = 0; j < MAXJ; ++j) { out[j] = fmaf(acc[j], inv, out[j]); acc[j] = 0.f; }
+                if (a.attn && lane == 0)
+                  for (int e2 = seg_beg; e2 < e; ++e2) {
+                    float* p = a.attn + (int64_t)e2 * a.H + h;
+                    *p = __expf(*p - m) * inv;
+                  }
+              }
+              m = -INFINITY; ssum = 0.f; cur_rel = rel; seg_beg = e;
+            }
+            scale = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
+          }
+          const float* kr = a.K + (int64_t)src * a.ldk + h * dk;
+          const float* vr = a.V + (int64_t)src * a.ldv + h * dk;
+          float vv[MAXJ];
+          float d = 0.f;
+#pragma unroll
+          for (int j = 0; j < MAXJ; ++j) {
+            int c = lane + 32 * j;
+            float kk = c < dk ? __ldg(kr + c) : 0.f;
+            vv[j] = c < dk ? __ldg(vr + c) : 0.f;
+            d = fmaf(q[j], kk, d);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+          const float s = d * scale;
+          if (a.attn && lane == 0) a.attn[(int64_t)e * a.H + h] = s;
+          const float mn = fmaxf(m, s);
+          const float corr = __expf(m - mn);
+          const float p = __expf(s - mn);
+          ssum = fmaf(ssum, corr, p);
+#pragma unroll
+          for (int j = 0; j < MAXJ; ++j) acc[j] = fmaf(acc[j], corr, p * vv[j]);
+          m = mn;
+        }
+        const float inv = 1.f / ssum;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) out[j] = fmaf(acc[j], inv, out[j]) * invr;
+        if (a.attn && lane == 0)
+          for (int e2 = seg_beg; e2 < end; ++e2) {
+            float* p = a.attn + (int64_t)e2 * a.H + h;
+            *p = __expf(*p - m) * inv;
+          }
+      }
+      float* o = a.out + (int64_t)item * a.ldo + h * dk;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        int c = lane + 32 * j;
+        if (c < dk) o[c] = out[j];
+      }
+    }
+  }
+}
+
+bool vec_ok(int D, int H) { return D % 128 == 0 && D <= 1024 && H >= 1 && H <= 32 && (H & (H - 1)) == 0; }
+
+template <int MODE>
+int launch(const AttnArgs& a, int head_perm, cudaStream_t stream) {
+  if (a.n_items == 0) return WSI_OK;
+  int sms = wsi_num_sms();
+  if (sms <= 0) return WSI_ERR_CUDA;
+  int blocks = (a.n_items + WARPS - 1) / WARPS;
+  int cap = sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (head_perm) {
+    if (!vec_ok(a.D, a.H)) {
+      wsi_set_error("hetero_attn: head_perm layout needs D %% 128 == 0, D <= 1024, H a power of two <= 32 (D=%d H=%d)", a.D, a.H);
+      return WSI_ERR_UNSUPPORTED;
+    }
+    switch (a.D / 128) {
+#define CASE(NV) case NV: attn_fwd_vec_kernel<NV, MODE><<<blocks, WARPS * 32, 0, stream>>>(a); break;
+      CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+  } else {
+    int mj = (a.dk + 31) / 32;
+    if (mj <= 1) attn_fwd_generic_kernel<1, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
+    else if (mj <= 2) attn_fwd_generic_kernel<2, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
+    else if (mj <= 4) attn_fwd_generic_kernel<4, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
+    else if (mj <= 8) attn_fwd_generic_kernel<8, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
+    else {
+      wsi_set_error("hetero_attn: d_k=%d > 256 is not supported", a.dk);
+      return WSI_ERR_UNSUPPORTED;
+    }
+  }
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}
+
+}  // namespace
+
+extern "C" int wsi_head_perm(int D, int H, int32_t* perm_host) {
+  WSI_CHECK_ARG(perm_host, "head_perm: null output");
+  if (!vec_ok(D, H) || D % H != 0) {
+    wsi_set_error("head_perm: no lane-grouped layout for D=%d H=%d", D, H);
+    return WSI_ERR_UNSUPPORTED;
+  }
+  const int G = 32 / H, dk = D / H, NV = D / 128;
+  for (int i = 0; i < NV; ++i)
+    for (int l = 0; l < 32; ++l)
+      for (int c = 0; c < 4; ++c) {
+        int head = l / G;
+        int within = i * (G * 4) + (l % G) * 4 + c;
+        perm_host[(i * 32 + l) * 4 + c] = head * dk + within;
+      }
+  return WSI_OK;
+}
+
+extern "C" int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q,
+                                   int64_t ldq, const int32_t* rowptr, const int32_t* e_src, const float* e_sim,
+                                   const uint8_t* e_rel, const float* node_inv_r, const float* e_w,
+                                   const float* e_b, int64_t n_rows, int D, int H, int head_perm, float* agg,
+                                   int64_t ldo, float* attn_out, void* stream) {
+  WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hetero_attn_fwd: bad n_rows");
+  if (n_rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(k && v && q && rowptr && node_inv_r && e_w && e_b && agg, "hetero_attn_fwd: null pointer");
+  WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0, "hetero_attn_fwd: D=%d is not a multiple of H=%d", D, H);
+  WSI_CHECK_ARG(!head_perm || (ldk % 4 == 0 && ldv % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0),
+                "hetero_attn_fwd: row strides must be multiples of 4 floats for the vector path");
+  AttnArgs a{};
+  a.K = k; a.ldk = ldk; a.V = v; a.ldv = ldv; a.Q = q; a.ldq = ldq;
+  a.rowptr = rowptr; a.e_src = e_src; a.e_sim = e_sim; a.e_rel = e_rel; a.inv_r = node_inv_r;
+  a.e_w = e_w; a.e_b = e_b; a.n_items = (int)n_rows; a.D = D; a.H = H; a.dk = D / H;
+  a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
+  a.out = agg; a.ldo = ldo; a.attn = attn_out;
+  return launch<MODE_HEAT>(a, head_perm, wsi_stream(stream));
+}
+
+extern "C" int wsi_hetero_attn_seg_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qseg,
+                                       int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel,
+                                       const int32_t* e_src, const float* rel_pri, int64_t n_segs, int D, int H,
+                                       int head_perm, float* out, int64_t ldo, void* stream) {
+  WSI_CHECK_ARG(n_segs >= 0 && n_segs < (1ll << 31), "hetero_attn_seg_fwd: bad n_segs");
+  if (n_segs == 0) return WSI_OK;
+  WSI_CHECK_ARG(k && v && qseg && seg_ptr && seg_rel && e_src && rel_pri && out, "hetero_attn_seg_fwd: null pointer");
+  WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0, "hetero_attn_seg_fwd: D=%d is not a multiple of H=%d", D, H);
+  AttnArgs a{};
+  a.K = k; a.ldk = ldk; a.V = v; a.ldv = ldv; a.Q = qseg; a.ldq = ldq;
+  a.rowptr = seg_ptr; a.e_src = e_src; a.seg_rel = seg_rel; a.rel_pri = rel_pri;
+  a.n_items = (int)n_segs; a.D = D; a.H = H; a.dk = D / H;
+  a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
+  a.out = out; a.ldo = ldo;
+  return launch<MODE_HGT_SEG>(a, head_perm, wsi_stream(stream));
+}

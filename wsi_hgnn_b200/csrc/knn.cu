@@ -1,0 +1,188 @@
+// Edge builder kernels (K6 / K7): exact k-NN in feature space and per-edge Pearson correlation.
+// Replaces Hnsw.fit / Hnsw.query (nmslib HNSW, approximate) and the per-edge scipy.pearsonr Python loop of the
+// reference: construct_graph/graph_constructor.py:55-81, 262-282.
+//
+// k-NN = (1) dot products of a chunk of query rows with ALL rows by the typed-linear GEMM (tensor cores when the
+// shape allows), (2) a streaming per-row selection of the 32 best candidates by the expanded form
+// ||b||^2 - 2 a.b (warp-resident sorted list, one slot per lane), (3) an exact fp64 direct-form re-rank of those
+// candidates ordered by (distance, index) - so the emitted neighbour lists equal the brute-force answer.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CAND = 32;          // candidates kept per query row (>= topn + slack)
+
+__global__ void __launch_bounds__(256)
+row_sqnorm_kernel(const float* __restrict__ feat, int64_t n, int F, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * 8) {
+    const float* p = feat + row * F;
+    float s = 0.f;
+    for (int c = lane; c < F; c += 32) { float v = __ldg(p + c); s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) out[row] = s;
+  }
+}
+
+__device__ __forceinline__ bool pair_less(float d1, int i1, float d2, int i2) {
+  return d1 < d2 || (d1 == d2 && i1 < i2);
+}
+
+// one warp per query row: scan dot[q, 0..n) and keep the CAND smallest (||b||^2 - 2 a.b, index) pairs sorted across
+// the lanes; then re-rank them by the exact fp64 distance and emit the first `topn`.
+__global__ void __launch_bounds__(256)
+knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn, const float* __restrict__ dot,
+                  int64_t n, int F, int topn, int64_t q0, int n_q, int32_t* __restrict__ nbr,
+                  float* __restrict__ nbr_dist) {
+  const int lane = threadIdx.x & 31;
+  for (int qi = blockIdx.x * 8 + (threadIdx.x >> 5); qi < n_q; qi += gridDim.x * 8) {
+    const float* drow = dot + (int64_t)qi * n;
+    float best_d = INFINITY;       // lane i holds the i-th smallest pair so far
+    int best_i = 0x7fffffff;
+    float thresh = INFINITY;       // = pair held by lane CAND-1
+    int thresh_i = 0x7fffffff;
+    for (int64_t base = 0; base < n; base += 32) {
+      const int64_t c = base + lane;
+      float d = INFINITY;
+      if (c < n) d = fmaf(-2.f, __ldg(drow + c), __ldg(sqn + c));
+      unsigned hits = __ballot_sync(FULL, c < n && pair_less(d, (int)c, thresh, thresh_i));
+      while (hits) {
+        const int src_lane = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const float xd = __shfl_sync(FULL, d, src_lane);
+        const int xi = (int)base + src_lane;
+        if (!pair_less(xd, xi, thresh, thresh_i)) continue;      // threshold moved since the ballot
+        const unsigned smaller = __ballot_sync(FULL, pair_less(best_d, best_i, xd, xi));
+        const int pos = __popc(smaller);                          // list is sorted: `smaller` is a prefix mask
+        const float up_d = __shfl_up_sync(FULL, best_d, 1);
+        const int up_i = __shfl_up_sync(FULL, best_i, 1);
+        if (lane > pos) { best_d = up_d; best_i = up_i; }
+        else if (lane == pos) { best_d = xd; best_i = xi; }
+        thresh = __shfl_sync(FULL, best_d, CAND - 1);
+        thresh_i = __shfl_sync(FULL, best_i, CAND - 1);
+      }
+    }
+    // exact re-rank: candidate j (held by lane j) gets its fp64 direct-form distance, computed by the whole warp
+    const float* a = feat + (q0 + qi) * F;
+    double my_d = INFINITY;
+    const int n_cand = n < CAND ? (int)n : CAND;
+    for (int j = 0; j < n_cand; ++j) {
+      const int cj = __shfl_sync(FULL, best_i, j);
+      const float* b = feat + (int64_t)cj * F;
+      double s = 0.0;
+      for (int c = lane; c < F; c += 32) { double df = (double)__ldg(a + c) - (double)__ldg(b + c); s = fma(df, df, s); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+      if (lane == j) my_d = s;
+    }
+    int rank = 0;
+    for (int j = 0; j < n_cand; ++j) {
+      const double dj = __shfl_sync(FULL, my_d, j);
+      const int ij = __shfl_sync(FULL, best_i, j);
+      if (dj < my_d || (dj == my_d && ij < best_i)) ++rank;
+    }
+    if (lane < n_cand && rank < topn) {
+      nbr[(int64_t)qi * topn + rank] = best_i;
+      if (nbr_dist) nbr_dist[(int64_t)qi * topn + rank] = (float)sqrt(my_d);
+    }
+  }
+}
+
+// Pearson r of two feature rows per edge: one warp per edge, fp32 loads, fp64 two-pass accumulation.
+__global__ void __launch_bounds__(256)
+edge_pearson_kernel(const float* __restrict__ feat, int F, const int64_t* __restrict__ src,
+                    const int64_t* __restrict__ dst, int64_t n_edges, float* __restrict__ sim,
+                    uint8_t* __restrict__ etype) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); e < n_edges; e += (int64_t)gridDim.x * 8) {
+    const float* a = feat + src[e] * F;
+    const float* b = feat + dst[e] * F;
+    double sa = 0.0, sb = 0.0;
+    for (int c = lane; c < F; c += 32) { sa += (double)__ldg(a + c); sb += (double)__ldg(b + c); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(FULL, sa, o); sb += __shfl_xor_sync(FULL, sb, o); }
+    const double ma = sa / F, mb = sb / F;
+    double ab = 0.0, aa = 0.0, bb = 0.0;
+    for (int c = lane; c < F; c += 32) {
+      const double x = (double)__ldg(a + c) - ma, y = (double)__ldg(b + c) - mb;
+      ab = fma(x, y, ab); aa = fma(x, x, aa); bb = fma(y, y, bb);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ab += __shfl_xor_sync(FULL, ab, o); aa += __shfl_xor_sync(FULL, aa, o); bb += __shfl_xor_sync(FULL, bb, o);
+    }
+    if (lane == 0) {
+      double r = ab / (sqrt(aa) * sqrt(bb));
+      r = fmin(1.0, fmax(-1.0, r));
+      sim[e] = (float)r;
+      if (etype) etype[e] = r > 0.0 ? 1 : 0;        // 'pos' = 1, 'neg' = 0 (graph_constructor.py:281,296)
+    }
+  }
+}
+
+int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+
+int64_t query_chunk(int64_t n, int64_t n_q) {
+  int64_t c = (1ll << 28) / (n > 0 ? n : 1);      // <= 1 GiB of fp32 dot products per chunk
+  c = c / 128 * 128;
+  if (c < 128) c = 128;
+  return c < n_q ? c : n_q;
+}
+
+}  // namespace
+
+extern "C" int64_t wsi_knn_workspace_bytes(int64_t n, int F, int topn, int64_t q_begin, int64_t q_end) {
+  (void)topn;
+  if (n <= 0 || q_end <= q_begin) return 0;
+  const int64_t qc = query_chunk(n, q_end - q_begin);
+  return align256(n * 4) + align256(qc * n * 4) + align256(wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0));
+}
+
+extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64_t q_begin, int64_t q_end,
+                            int32_t* nbr, float* nbr_dist, void* workspace, int64_t workspace_bytes, void* stream) {
+  WSI_CHECK_ARG(n >= 0 && n < (1ll << 31) && F >= 1, "knn_topk: bad n / F");
+  WSI_CHECK_ARG(0 <= q_begin && q_begin <= q_end && q_end <= n, "knn_topk: bad query range");
+  if (q_end == q_begin) return WSI_OK;
+  WSI_CHECK_ARG(topn >= 1 && topn <= CAND - 8, "knn_topk: topn must be in [1, %d]", CAND - 8);
+  // the reference fails the slide when HNSW returns fewer than `radius` hits (np.stack -> ValueError,
+  // graph_constructor.py:268-272 / get_graph.py:293-294)
+  WSI_CHECK_ARG(topn <= n, "knn_topk: fewer than topn=%d nodes (n=%lld)", topn, (long long)n);
+  WSI_CHECK_ARG(feat && nbr && workspace, "knn_topk: null pointer");
+  WSI_CHECK_ARG(workspace_bytes >= wsi_knn_workspace_bytes(n, F, topn, q_begin, q_end), "knn_topk: workspace too small");
+  cudaStream_t st = wsi_stream(stream);
+  const int64_t qc = query_chunk(n, q_end - q_begin);
+  char* ws = (char*)workspace;
+  float* sqn = (float*)ws;
+  float* dot = (float*)(ws + align256(n * 4));
+  void* lin_ws = ws + align256(n * 4) + align256(qc * n * 4);
+  const int64_t lin_ws_bytes = wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0);
+  int blocks = (int)((n + 7) / 8 < 148 * 16 ? (n + 7) / 8 : 148 * 16);
+  row_sqnorm_kernel<<<blocks, 256, 0, st>>>(feat, n, F, sqn);
+  WSI_CHECK_LAUNCH();
+  for (int64_t q0 = q_begin; q0 < q_end; q0 += qc) {
+    const int n_q = (int)((q_end - q0) < qc ? (q_end - q0) : qc);
+    int32_t tp[2] = {0, n_q};
+    int rc = wsi_typed_linear_f32(feat + q0 * F, F, feat, nullptr, F, (int)n, tp, 1, WSI_ACT_NONE, nullptr, nullptr, 0,
+                                  nullptr, 0, nullptr, nullptr, dot, n, 0, lin_ws, lin_ws_bytes, stream);
+    if (rc != WSI_OK) return rc;
+    int sb = (n_q + 7) / 8 < 148 * 16 ? (n_q + 7) / 8 : 148 * 16;
+    knn_select_kernel<<<sb, 256, 0, st>>>(feat, sqn, dot, n, F, topn, q0, n_q, nbr + (q0 - q_begin) * topn,
+                                          nbr_dist ? nbr_dist + (q0 - q_begin) * topn : nullptr);
+    WSI_CHECK_LAUNCH();
+  }
+  return WSI_OK;
+}
+
+extern "C" int wsi_edge_pearson(const float* feat, int64_t n, int F, const int64_t* src, const int64_t* dst,
+                                int64_t n_edges, float* sim, uint8_t* etype, void* stream) {
+  WSI_CHECK_ARG(n_edges >= 0 && F >= 1 && n >= 0, "edge_pearson: bad sizes");
+  if (n_edges == 0) return WSI_OK;
+  WSI_CHECK_ARG(feat && src && dst && sim, "edge_pearson: null pointer");
+  int64_t want = (n_edges + 7) / 8;
+  int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  edge_pearson_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(feat, F, src, dst, n_edges, sim, etype);
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}

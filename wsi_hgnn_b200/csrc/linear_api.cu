@@ -1,0 +1,48 @@
+// C-ABI front of the typed linear (include/wsi_hgnn.h): argument validation and dispatch between the
+// tcgen05 tensor-core path (linear_tc.cu) and the fp32 SIMT path (linear_simt.cu).
+#include "epilogue.cuh"
+
+int wsi_typed_linear_simt_launch(const float* x, int64_t ldx, const float* w, int K, const int32_t* type_ptr_host,
+                                 int T, const LinearEpilogue& ep, cudaStream_t stream);
+// linear_tc.cu
+bool wsi_typed_linear_tc_supported(int64_t n_rows, int K, int n_out, int64_t ldx);
+int64_t wsi_typed_linear_tc_workspace(int64_t n_rows, int K, int n_out, int T);
+int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int K, const int32_t* type_ptr_host,
+                               int T, const LinearEpilogue& ep, void* workspace, int64_t workspace_bytes,
+                               cudaStream_t stream);
+
+extern "C" int64_t wsi_typed_linear_workspace_bytes(int64_t n_rows, int K, int n_out, int T, int impl) {
+  if (impl == 1) return 0;
+  if (!wsi_typed_linear_tc_supported(n_rows, K, n_out, K)) return 0;
+  return wsi_typed_linear_tc_workspace(n_rows, K, n_out, T);
+}
+
+extern "C" int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w, const float* bias, int K, int n_out,
+                                    const int32_t* type_ptr_host, int T, int act, const float* skip,
+                                    const float* res, int64_t ldres, const float* drop_mask, int64_t ldmask,
+                                    const float* row_gate, const float* row_scale, float* y, int64_t ldy, int impl,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+  WSI_CHECK_ARG(type_ptr_host && T >= 1 && T <= WSI_MAX_TYPES, "typed_linear: bad type_ptr / T=%d", T);
+  WSI_CHECK_ARG(K >= 1 && n_out >= 1, "typed_linear: bad K=%d n_out=%d", K, n_out);
+  WSI_CHECK_ARG(act == WSI_ACT_NONE || act == WSI_ACT_GELU, "typed_linear: unknown activation %d", act);
+  WSI_CHECK_ARG(!skip || res, "typed_linear: skip mix needs a residual");
+  WSI_CHECK_ARG(impl >= 0 && impl <= 2, "typed_linear: unknown impl %d", impl);
+  const int64_t n_rows = type_ptr_host[T];
+  if (n_rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(x && w && y, "typed_linear: null pointer");
+  WSI_CHECK_ARG(ldx >= K && ldy >= n_out, "typed_linear: row stride smaller than the row");
+  LinearEpilogue ep{};
+  ep.bias = bias; ep.act = act; ep.skip = skip; ep.res = res; ep.ldres = ldres;
+  ep.drop_mask = drop_mask; ep.ldmask = ldmask; ep.row_gate = row_gate; ep.row_scale = row_scale;
+  ep.y = y; ep.ldy = ldy; ep.n_out = n_out;
+  const bool tc_ok = wsi_typed_linear_tc_supported(n_rows, K, n_out, ldx);
+  if (impl == 2 && !tc_ok) {
+    wsi_set_error("typed_linear: shape (rows=%lld K=%d n_out=%d ldx=%lld) does not fit the tcgen05 path",
+                  (long long)n_rows, K, n_out, (long long)ldx);
+    return WSI_ERR_UNSUPPORTED;
+  }
+  if (impl == 2 || (impl == 0 && tc_ok))
+    return wsi_typed_linear_tc_launch(x, ldx, w, K, type_ptr_host, T, ep, workspace, workspace_bytes,
+                                      wsi_stream(stream));
+  return wsi_typed_linear_simt_launch(x, ldx, w, K, type_ptr_host, T, ep, wsi_stream(stream));
+}

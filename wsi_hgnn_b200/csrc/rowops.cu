@@ -1,0 +1,198 @@
+// Row-wise HBM-bound kernels: typed readout (K4), typed LayerNorm, HGT segment combine.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// Typed readout: dgl.readout.{sum,mean,max}_nodes(graph, 'h', ntype=) (reference pooling/avg_pooling.py:15-17,
+// sum_pooling.py:14-16, max_pooling.py:15-17).  grid = (segment, 128-column chunk, row split); every CTA
+// reduces a contiguous slab of rows with coalesced float4 loads; partials of split segments go through the
+// caller's workspace and are combined by a second tiny kernel (deterministic, no atomics).
+constexpr int POOL_THREADS = 256;   // 8 warps; a warp covers 128 columns, warps stride over rows
+
+__device__ __forceinline__ float4 pool_comb(float4 a, float4 b, int op) {
+  if (op == WSI_POOL_MAX) return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+__global__ void __launch_bounds__(POOL_THREADS)
+segment_pool_kernel(const float* __restrict__ x, int64_t ldx, const int* __restrict__ seg_ptr, int D, int op,
+                    int n_split, float* __restrict__ out, int64_t ldo, float* __restrict__ partial) {
+  __shared__ float4 sm[POOL_THREADS / 32][32];
+  const int seg = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = (blockIdx.y * 32 + lane) * 4;
+  const int beg = seg_ptr[seg], end = seg_ptr[seg + 1];
+  const int n = end - beg;
+  const int per = (n + n_split - 1) / n_split;
+  const int r0 = beg + blockIdx.z * per;
+  const int r1 = min(end, r0 + per);
+  const float ident = op == WSI_POOL_MAX ? -INFINITY : 0.f;
+  float4 acc = make_float4(ident, ident, ident, ident);
+  const bool vec = (col + 3 < D) && (ldx % 4 == 0);
+  for (int r = r0 + warp; r < r1; r += POOL_THREADS / 32) {
+    const float* p = x + (int64_t)r * ldx + col;
+    float4 v;
+    if (vec) v = __ldg(reinterpret_cast<const float4*>(p));
+    else {
+      v.x = col < D ? __ldg(p) : ident;         v.y = col + 1 < D ? __ldg(p + 1) : ident;
+      v.z = col + 2 < D ? __ldg(p + 2) : ident; v.w = col + 3 < D ? __ldg(p + 3) : ident;
+    }
+    acc = pool_comb(acc, v, op);
+  }
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 1; w < POOL_THREADS / 32; ++w) acc = pool_comb(acc, sm[w][lane], op);
+    float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (n_split == 1) {
+      const float scale = op == WSI_POOL_MEAN ? 1.f / (float)max(n, 1) : 1.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (col + c < D) out[(int64_t)seg * ldo + col + c] = n > 0 ? vals[c] * scale : 0.f;
+    } else {
+      float* p = partial + ((int64_t)blockIdx.z * gridDim.x + seg) * D;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (col + c < D) p[col + c] = vals[c];
+    }
+  }
+}
+
+__global__ void segment_pool_finish_kernel(const float* __restrict__ partial, const int* __restrict__ seg_ptr,
+                                           int64_t n_seg, int D, int op, int n_split, float* __restrict__ out,
+                                           int64_t ldo) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_seg * D) return;
+  int64_t seg = idx / D;
+  int c = (int)(idx % D);
+  int n = seg_ptr[seg + 1] - seg_ptr[seg];
+  float acc = op == WSI_POOL_MAX ? -INFINITY : 0.f;
+  for (int z = 0; z < n_split; ++z) {
+    float v = partial[((int64_t)z * n_seg + seg) * D + c];
+    acc = op == WSI_POOL_MAX ? fmaxf(acc, v) : acc + v;
+  }
+  if (op == WSI_POOL_MEAN) acc /= (float)max(n, 1);
+  out[seg * ldo + c] = n > 0 ? acc : 0.f;
+}
+
+int pool_splits(int64_t n_rows, int64_t n_seg, int D) {
+  // enough CTAs to fill the chip even when one (type, graph) segment holds all the rows
+  int chunks = (D + 127) / 128;
+  int64_t ctas = n_seg * chunks;
+  int64_t want = 148 * 4;
+  int s = (int)((want + ctas - 1) / ctas);
+  int64_t max_by_rows = (n_rows + 255) / 256;     // at least ~256 rows per slab
+  if (s > max_by_rows) s = (int)max_by_rows;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Typed LayerNorm (reference models/HGT.py:123-124): one warp per row, two-pass mean / variance.
+__global__ void __launch_bounds__(256)
+typed_layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, TypeSegs segs, int D, float eps, float* __restrict__ y,
+                       int64_t ldy) {
+  const int lane = threadIdx.x & 31;
+  const int n_rows = segs.ptr[segs.T];
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 8) {
+    int t = 0;
+    while (t + 1 < segs.T && row >= segs.ptr[t + 1]) ++t;
+    const float* xr = x + (int64_t)row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += xr[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    const float mean = s / (float)D;
+    float v = 0.f;
+    for (int c = lane; c < D; c += 32) { float d = xr[c] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    const float rstd = rsqrtf(v / (float)D + eps);
+    const float* g = gamma + (int64_t)t * D;
+    const float* b = beta + (int64_t)t * D;
+    float* yr = y + (int64_t)row * ldy;
+    for (int c = lane; c < D; c += 32) yr[c] = (xr[c] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HGT: agg[v] = inv_r[v] * sum of the messages of the (v, relation) segments of row v
+// (stack->mean of multi_update_all(..., cross_reducer='mean'), reference models/HGT.py:105-106).
+__global__ void __launch_bounds__(256)
+segment_combine_kernel(const float* __restrict__ msg, int64_t ldm, const int* __restrict__ row_seg_ptr,
+                       const float* __restrict__ inv_r, int n_rows, int D, float* __restrict__ agg, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 8) {
+    const int s0 = row_seg_ptr[row], s1 = row_seg_ptr[row + 1];
+    const float ir = inv_r[row];
+    for (int c = lane; c < D; c += 32) {
+      float acc = 0.f;
+      for (int s = s0; s < s1; ++s) acc += __ldg(msg + (int64_t)s * ldm + c);
+      agg[(int64_t)row * ldo + c] = acc * ir;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t wsi_segment_pool_workspace_bytes(int64_t n_rows, int64_t n_seg, int D) {
+  int s = pool_splits(n_rows, n_seg, D);
+  return s > 1 ? (int64_t)s * n_seg * D * (int64_t)sizeof(float) : 0;
+}
+
+extern "C" int wsi_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, int64_t n_seg,
+                                    int64_t n_rows, int D, int op, float* out, int64_t ldo, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  WSI_CHECK_ARG(op == WSI_POOL_SUM || op == WSI_POOL_MEAN || op == WSI_POOL_MAX, "segment_pool: unknown op %d", op);
+  WSI_CHECK_ARG(n_seg >= 0 && n_seg < 65536ll * 32768 && D >= 1, "segment_pool: bad n_seg / D");
+  if (n_seg == 0) return WSI_OK;
+  WSI_CHECK_ARG(seg_ptr && out && (x || n_rows == 0), "segment_pool: null pointer");
+  const int splits = pool_splits(n_rows, n_seg, D);
+  WSI_CHECK_ARG(splits == 1 || (workspace && workspace_bytes >= wsi_segment_pool_workspace_bytes(n_rows, n_seg, D)),
+                "segment_pool: workspace too small");
+  cudaStream_t st = wsi_stream(stream);
+  dim3 grid((unsigned)n_seg, (D + 127) / 128, splits);
+  segment_pool_kernel<<<grid, POOL_THREADS, 0, st>>>(x, ldx, seg_ptr, D, op, splits, out, ldo, (float*)workspace);
+  WSI_CHECK_LAUNCH();
+  if (splits > 1) {
+    int64_t total = n_seg * D;
+    segment_pool_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, seg_ptr,
+                                                                                n_seg, D, op, splits, out, ldo);
+    WSI_CHECK_LAUNCH();
+  }
+  return WSI_OK;
+}
+
+extern "C" int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta,
+                                   const int32_t* type_ptr_host, int T, int D, float eps, float* y, int64_t ldy,
+                                   void* stream) {
+  WSI_CHECK_ARG(x && gamma && beta && y && type_ptr_host, "typed_layernorm: null pointer");
+  TypeSegs segs;
+  WSI_CHECK_ARG(wsi_make_segs(&segs, type_ptr_host, T, 1) == 0, "typed_layernorm: bad type_ptr (T=%d)", T);
+  int n_rows = segs.ptr[T];
+  if (n_rows == 0) return WSI_OK;
+  int blocks = (n_rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  typed_layernorm_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(x, ldx, gamma, beta, segs, D, eps, y, ldy);
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}
+
+extern "C" int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_ptr, const float* node_inv_r,
+                                   int64_t n_rows, int D, float* agg, int64_t ldo, void* stream) {
+  WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "segment_combine: bad n_rows");
+  if (n_rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(row_seg_ptr && node_inv_r && agg, "segment_combine: null pointer");
+  int blocks = (int)((n_rows + 7) / 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  segment_combine_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(msg, ldm, row_seg_ptr, node_inv_r, (int)n_rows, D,
+                                                                 agg, ldo);
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}

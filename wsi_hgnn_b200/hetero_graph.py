@@ -179,7 +179,52 @@ class GraphPlan:
         self._t = None
         self.device = torch.device("cpu")
         self.seg_nonempty = None              # bool [T, B] on host
-        self.hub = None                       # (hub_rows int32 [Hn], ...) filled by ops when needed
+        self.cache: Dict = {}                 # per-model derived tensors (relation id maps, packed feats, ...)
+        self._segs = None
+
+    def type_ptr_c(self):
+        """type_ptr as a ctypes int32 array (host argument of the typed kernels)."""
+        if "type_ptr_c" not in self.cache:
+            import ctypes
+            self.cache["type_ptr_c"] = (ctypes.c_int32 * len(self.type_ptr))(*self.type_ptr)
+        return self.cache["type_ptr_c"]
+
+    def readout_ptr(self) -> List[int]:
+        """Row ranges of the pooled [T*B, D] matrix by node type (type-major)."""
+        return [t * self.B for t in range(len(self.ntypes) + 1)]
+
+    def segments(self):
+        """(dst, relation) segments of the dst-sorted edge array, for the HGT path.
+
+        Returns dict: S, seg_ptr int32 [S+1], seg_dst int32 [S], seg_slot int64 [S] (graph relation
+        slot), row_seg_ptr int32 [N+1] (segments of each dst row are contiguous)."""
+        if self._segs is None:
+            dev = self.device
+            E = self.E
+            if E == 0:
+                z32 = torch.zeros(0, dtype=torch.int32, device=dev)
+                self._segs = dict(S=0, seg_ptr=torch.zeros(1, dtype=torch.int32, device=dev), seg_dst=z32,
+                                  seg_slot=torch.zeros(0, dtype=torch.int64, device=dev),
+                                  row_seg_ptr=torch.zeros(self.N + 1, dtype=torch.int32, device=dev))
+                return self._segs
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            e_dst = torch.repeat_interleave(torch.arange(self.N, device=dev, dtype=torch.int64), deg)
+            rel = self.e_rel.to(torch.int64)
+            key = e_dst * 256 + rel
+            new = torch.ones(E, dtype=torch.bool, device=dev)
+            new[1:] = key[1:] != key[:-1]
+            starts = torch.nonzero(new).reshape(-1)
+            S = int(starts.numel())
+            seg_ptr = torch.empty(S + 1, dtype=torch.int32, device=dev)
+            seg_ptr[:S] = starts.to(torch.int32)
+            seg_ptr[S] = E
+            seg_dst = e_dst[starts]
+            counts = torch.bincount(seg_dst, minlength=self.N)
+            row_seg_ptr = torch.zeros(self.N + 1, dtype=torch.int32, device=dev)
+            row_seg_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            self._segs = dict(S=S, seg_ptr=seg_ptr, seg_dst=seg_dst.to(torch.int32).contiguous(),
+                              seg_slot=rel[starts].contiguous(), row_seg_ptr=row_seg_ptr)
+        return self._segs
 
     def transposed(self):
         """(t_rowptr, t_eid, e_dst) for the backward scatter to src rows."""
@@ -625,7 +670,7 @@ def _cat_graphs(graphs: Sequence[HeteroGraph], rel_union: List[CEType]) -> Heter
                      torch.cat(dd) if dd else torch.zeros(0, dtype=torch.int64, device=dev))
         bne[ce] = cnt
         edata[ce] = {}
-        for k in (keys or ()):
+        for k in sorted(keys or ()):
             edata[ce][k] = torch.cat([g._edata[ce][k] for g in graphs if ce in g._edges])
     ndata: Dict[str, Dict[str, torch.Tensor]] = {}
     for nt in ntypes:
@@ -633,7 +678,7 @@ def _cat_graphs(graphs: Sequence[HeteroGraph], rel_union: List[CEType]) -> Heter
         for g in graphs:
             ks = set(g._ndata[nt].keys())
             keys = ks if keys is None else keys & ks
-        ndata[nt] = {k: torch.cat([g._ndata[nt][k] for g in graphs]) for k in (keys or ())}
+        ndata[nt] = {k: torch.cat([g._ndata[nt][k] for g in graphs]) for k in sorted(keys or ())}
     out = HeteroGraph(num_nodes, edges, ndata, edata)
     out.batch_size = len(graphs)
     out._batch_num_nodes = {nt: [g._num_nodes[nt] for g in graphs] for nt in ntypes}
@@ -666,4 +711,34 @@ def pack(graphs: Sequence[HeteroGraph]) -> HeteroGraph:
     union = sorted(set(ce for g in graphs for ce in g.canonical_etypes))
     out = _cat_graphs(graphs, union)
     out._rel_present = [[ce in g._edges for ce in union] for g in graphs]
+    return out
+
+
+def unbatch(G: HeteroGraph) -> List[HeteroGraph]:
+    """Inverse of :func:`batch` / :func:`pack` (``dgl.unbatch``): the per-slide graphs, with the relation
+    set each one had (pack) or the shared one (batch)."""
+    B = G.batch_size
+    if B == 1:
+        return [G]
+    noff = {nt: [0] for nt in G.ntypes}
+    for nt in G.ntypes:
+        for n in G._batch_num_nodes[nt]:
+            noff[nt].append(noff[nt][-1] + n)
+    eoff = {ce: [0] for ce in G.canonical_etypes}
+    for ce in G.canonical_etypes:
+        for n in G._batch_num_edges[ce]:
+            eoff[ce].append(eoff[ce][-1] + n)
+    out = []
+    for b in range(B):
+        num_nodes = {nt: G._batch_num_nodes[nt][b] for nt in G.ntypes}
+        edges, edata = {}, {}
+        for ri, ce in enumerate(G.canonical_etypes):
+            if G._rel_present is not None and not G._rel_present[b][ri]:
+                continue
+            a, z = eoff[ce][b], eoff[ce][b + 1]
+            s, d = G._edges[ce]
+            edges[ce] = (s[a:z] - noff[ce[0]][b], d[a:z] - noff[ce[2]][b])
+            edata[ce] = {k: v[a:z] for k, v in G._edata[ce].items()}
+        ndata = {nt: {k: v[noff[nt][b]:noff[nt][b + 1]] for k, v in G._ndata[nt].items()} for nt in G.ntypes}
+        out.append(HeteroGraph(num_nodes, edges, ndata, edata))
     return out

@@ -1,0 +1,217 @@
+"""HEATNet2 / HEATNet4 with the reference's constructor, forward() and state_dict contracts,
+running on the sm_100a kernels of libwsi_hgnn.so.
+
+Reference: models/HEATNet4.py:49-138 (HEATLayer), :141-247 (HEATNet4); models/HEATNet2.py:24-113
+(same layer), :116-196 (HEATNet2).  Differences in HOW, not WHAT:
+  * K/Q/V are projected once per node TYPE by one fused typed GEMM (the reference re-projects them
+    for every relation, models/HEATNet4.py:95-102);
+  * all relations of a layer run in ONE edge-attention launch over a relation-grouped CSR instead of a
+    Python loop of DGL calls (models/HEATNet4.py:91-119);
+  * the sigma(skip) mix, dropout mask and KeyError-passthrough are the epilogue of the a_linear GEMM
+    (models/HEATNet4.py:122-136).
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..hetero_graph import GraphPlan, HeteroGraph
+from ._packing import PackCache, stack_linears
+
+_POOLS = ("mean", "sum", "max")
+
+
+def _check_pool(name: str) -> str:
+    if name not in _POOLS:
+        # 'att' (GlobalAttentionPooling) cannot take ntype= and raises in the reference too; anything else
+        # is NotImplementedError there as well (models/HEATNet4.py:182-189).
+        raise NotImplementedError(name)
+    return name
+
+
+def _graph_type_order(plan: GraphPlan, node_dict: Dict[str, int]):
+    return [node_dict[nt] for nt in plan.ntypes]        # KeyError for an unknown type, as in the reference
+
+
+def packed_features(G: HeteroGraph, plan: GraphPlan, h: Optional[Dict[str, torch.Tensor]], name: str = "feat"):
+    """[N, F] type-major packed input features (G.nodes[nt].data['feat'] or the caller's dict)."""
+    if h is None:
+        if name not in plan.cache:
+            plan.cache[name] = G.packed_ndata(name, torch.float32)
+        return plan.cache[name]
+    parts = [h[nt].to(torch.float32) for nt in plan.ntypes if G.num_nodes(nt) > 0]
+    return torch.cat(parts, 0).contiguous()
+
+
+def unpack_rows(plan: GraphPlan, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+    return {nt: x[plan.type_ptr[t]:plan.type_ptr[t + 1]] for t, nt in enumerate(plan.ntypes)}
+
+
+def readout_scale(plan: GraphPlan, independent: bool) -> torch.Tensor:
+    """[T*B] 0/1 mask of the readout rows: 0 where the reference emits a zero block instead of
+    linears_prediction(pool) - a node type without nodes (models/HEATNet4.py:217-221,240); per graph
+    for pack()ed graphs, per batch for dgl.batch semantics."""
+    key = ("readout_scale", independent)
+    if key not in plan.cache:
+        ne = plan.seg_nonempty
+        m = ne if independent else ne.any(dim=1, keepdim=True).expand_as(ne)
+        plan.cache[key] = m.to(torch.float32).reshape(-1).contiguous().to(plan.device)
+    return plan.cache[key]
+
+
+class HEATLayer(nn.Module):
+    """reference models/HEATNet4.py:49-138 (== models/HEATNet2.py:24-113)."""
+
+    def __init__(self, in_size, out_size, node_dict, n_heads, dropout=0.2):
+        super().__init__()
+        self.weight = nn.Linear(in_size, out_size)     # "W_r": created, never used (models/HEATNet4.py:53-54)
+        self.in_size = in_size
+        self.out_size = out_size
+        self.node_dict = node_dict
+        self.num_ntypes = len(node_dict)
+        self.n_heads = n_heads
+        self.d_k = out_size // n_heads
+        self.sqrt_dk = math.sqrt(self.d_k)
+        T = self.num_ntypes
+        self.k_linears = nn.ModuleList([nn.Linear(in_size, out_size) for _ in range(T)])
+        self.q_linears = nn.ModuleList([nn.Linear(in_size, out_size) for _ in range(T)])
+        self.v_linears = nn.ModuleList([nn.Linear(in_size, out_size) for _ in range(T)])
+        self.a_linears = nn.ModuleList([nn.Linear(out_size, out_size) for _ in range(T)])
+        self.e_linear = nn.Linear(1, 1)
+        self.skip = nn.Parameter(torch.ones(T))
+        self.drop = nn.Dropout(dropout)
+        self._packs = PackCache()
+
+    def _packed(self, order):
+        D, H = self.out_size, self.n_heads
+        perm = ops.head_perm(D, H)
+        params = [p for p in self.parameters()]
+
+        def build():
+            dev = self.skip.device
+            pm = perm.to(dev) if perm is not None else None
+            wk, bk = stack_linears(self.k_linears, order, row_perm=pm)
+            wv, bv = stack_linears(self.v_linears, order, row_perm=pm)
+            wq, bq = stack_linears(self.q_linears, order, row_perm=pm)
+            w_kvq = torch.cat([wk, wv, wq], 1).contiguous()          # [T, 3D, in]
+            b_kvq = torch.cat([bk, bv, bq], 1).contiguous()
+            wa, ba = stack_linears(self.a_linears, order, col_perm=pm)
+            skip = self.skip[torch.tensor(order, device=dev)].contiguous()
+            return w_kvq, b_kvq, wa, ba, skip
+
+        return self._packs.get(tuple(order), params, build) + (perm is not None,)
+
+    def forward_packed(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
+        """x [N, in] type-major packed -> [N, out]."""
+        D, H = self.out_size, self.n_heads
+        order = _graph_type_order(plan, self.node_dict)
+        w_kvq, b_kvq, wa, ba, skip, use_perm = self._packed(order)
+        tpc = plan.type_ptr_c()
+        kvq = ops.typed_linear(x, w_kvq, b_kvq, plan.type_ptr, type_ptr_c=tpc)
+        agg = ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
+                              plan.e_rel, plan.node_inv_r, self.e_linear.weight, self.e_linear.bias, D, H, use_perm)
+        mask = None
+        if self.training and self.drop.p > 0:
+            mask = F.dropout(torch.ones_like(agg), self.drop.p, True)
+        return ops.typed_linear(agg, wa, ba, plan.type_ptr, skip=skip, res=x, row_gate=plan.node_inv_r,
+                                drop_mask=mask, type_ptr_c=tpc)
+
+    def forward(self, G: HeteroGraph, feat_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        plan = G.plan()
+        x = packed_features(G, plan, feat_dict)
+        return unpack_rows(plan, self.forward_packed(plan, x))
+
+
+class _AttnParams(nn.Module):
+    """Parameters of the reference's LinearAttentionBlock (models/HEATNet4.py:20-42).  The block is the
+    identity on its first argument in every reachable call (softmax over an axis of length 1), so only
+    the state_dict entry `attn.{k}.op.weight [1, 256, 1]` is kept."""
+
+    def __init__(self):
+        super().__init__()
+        self.op = nn.Conv1d(256, 1, kernel_size=1, padding=0, bias=False)
+
+
+class _HEATBase(nn.Module):
+    def _trunk(self, G: HeteroGraph, h):
+        plan = G.plan()
+        order = _graph_type_order(plan, self.node_dict)
+        x = packed_features(G, plan, h)
+        params = [p for m in self.adapt_ws for p in m.parameters()]
+        w_in, b_in = self._packs.get(("in", tuple(order)), params, lambda: stack_linears(self.adapt_ws, order))
+        x = ops.typed_linear(x, w_in, b_in, plan.type_ptr, type_ptr_c=plan.type_ptr_c())    # HEATNet4.py:198-206
+        for layer in self.gcs:                                                               # :213-214
+            x = layer.forward_packed(plan, x)
+        return plan, x
+
+    def _readout(self, G, plan, x):
+        """[T*B, n_pred] = linears_prediction[type](pool_type(x)) with the empty-type zero block."""
+        pooled = ops.segment_pool(x, plan.seg_ptr, len(plan.ntypes) * plan.B, self.graph_pooling_type)
+        names = list(plan.ntypes)
+        params = [p for nt in names for p in self.linears_prediction[nt].parameters()]
+
+        def build():
+            ws = torch.stack([self.linears_prediction[nt].weight for nt in names]).contiguous()
+            bs = torch.stack([self.linears_prediction[nt].bias for nt in names]).contiguous()
+            return ws, bs
+
+        w_p, b_p = self._packs.get(("pred", tuple(names)), params, build)
+        return ops.typed_linear(pooled, w_p, b_p, plan.readout_ptr(), row_scale=readout_scale(plan, G.independent))
+
+
+class HEATNet4(_HEATBase):
+    """reference models/HEATNet4.py:141-247.  forward(G, h=None) -> logits [B, out_dim]."""
+
+    def __init__(self, in_dim, hidden_dim, out_dim, n_layers, n_heads, node_dict, dropuout,
+                 graph_pooling_type="mean"):
+        super().__init__()
+        self.node_dict = node_dict
+        self.n_layers = n_layers
+        self.graph_pooling_type = _check_pool(graph_pooling_type)
+        self.linears_prediction = nn.ModuleDict({k: nn.Linear(hidden_dim, 256) for k in node_dict})
+        self.adapt_ws = nn.ModuleList([nn.Linear(in_dim, hidden_dim) for _ in node_dict])
+        self.gcs = nn.ModuleList([HEATLayer(hidden_dim, hidden_dim, node_dict, n_heads, dropuout)
+                                  for _ in range(n_layers)])
+        self.attn = nn.ModuleDict({k: _AttnParams() for k in node_dict})
+        self.head_2 = nn.Linear(256 * len(node_dict), 256)
+        self.head_1 = nn.Linear(256, 64)
+        self.head = nn.Linear(64, out_dim)
+        self._packs = PackCache()
+
+    def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
+        plan, x = self._trunk(G, h)
+        T, B = len(plan.ntypes), plan.B
+        o = self._readout(G, plan, x)                                   # [T*B, 256]      :216-240
+        z = o if B == 1 else o.view(T, B, 256).permute(1, 0, 2).contiguous()
+        z = z.view(B, T * 256)                                          # cat(dim=1) in G.ntypes order
+        one = [0, B]
+        z = ops.typed_linear(z, self.head_2.weight.unsqueeze(0), self.head_2.bias.unsqueeze(0), one)   # :243
+        z = ops.typed_linear(z, self.head_1.weight.unsqueeze(0), self.head_1.bias.unsqueeze(0), one)   # :244
+        g = ops.typed_linear(z, self.head.weight.unsqueeze(0), self.head.bias.unsqueeze(0), one)       # :245
+        return (g, unpack_rows(plan, x)) if return_embeddings else g
+
+
+class HEATNet2(_HEATBase):
+    """reference models/HEATNet2.py:116-196.  forward(G, h=None) -> logits [B, out_dim]."""
+
+    def __init__(self, in_dim, hidden_dim, out_dim, n_layers, n_heads, node_dict, dropuout,
+                 graph_pooling_type="mean"):
+        super().__init__()
+        self.node_dict = node_dict
+        self.n_layers = n_layers
+        self.graph_pooling_type = _check_pool(graph_pooling_type)
+        self.linears_prediction = nn.ModuleDict({k: nn.Linear(hidden_dim, out_dim) for k in node_dict})
+        self.adapt_ws = nn.ModuleList([nn.Linear(in_dim, hidden_dim) for _ in node_dict])
+        self.gcs = nn.ModuleList([HEATLayer(hidden_dim, hidden_dim, node_dict, n_heads, dropuout)
+                                  for _ in range(n_layers)])
+        self._packs = PackCache()
+
+    def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
+        plan, x = self._trunk(G, h)
+        T, B = len(plan.ntypes), plan.B
+        o = self._readout(G, plan, x)                                   # [T*B, out]   HEATNet2.py:181-194
+        g = o.view(T, B, -1).sum(0)
+        return (g, unpack_rows(plan, x)) if return_embeddings else g

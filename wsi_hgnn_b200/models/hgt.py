@@ -1,0 +1,200 @@
+"""HGT with the reference's constructor, forward() and state_dict contracts on the sm_100a kernels.
+
+Reference: models/HGT.py:21-127 (HGTLayer), :130-209 (HGT).  Same maths, different schedule:
+  * K/Q/V once per node type (fused typed GEMM) instead of once per relation (models/HGT.py:75-84);
+  * the per-relation d_k x d_k maps relation_att / relation_msg (models/HGT.py:88-93) are applied to
+    (dst, relation) SEGMENTS - the query side  <Q, K A> = <A Q, K>  before the edge kernel and the message
+    side  sum_e a_e (V M) = (sum_e a_e V) M  after it - instead of to every source node x relation;
+  * one edge-attention launch over all segments (models/HGT.py:95-106), then the cross-relation mean.
+"""
+import math
+from typing import Dict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..hetero_graph import GraphPlan, HeteroGraph
+from ._packing import PackCache, stack_linears
+from .heat import _check_pool, _graph_type_order, packed_features, readout_scale, unpack_rows
+
+
+def _relation_groups(plan: GraphPlan, edge_dict: Dict, tag):
+    """Per (graph, model) tensors that order the (dst, relation) segments by MODEL relation id."""
+    key = ("hgt_groups", tag)
+    if key not in plan.cache:
+        segs = plan.segments()
+        R = len(edge_dict)
+        slot2model = torch.tensor([edge_dict[ce] for ce in plan.rel_list] or [0], dtype=torch.int64,
+                                  device=plan.device)          # KeyError for an unknown relation (models/HGT.py:86)
+        seg_rel = slot2model[segs["seg_slot"]] if segs["S"] else torch.zeros(0, dtype=torch.int64, device=plan.device)
+        order = torch.argsort(seg_rel, stable=True)
+        counts = torch.bincount(seg_rel, minlength=R)
+        rel_ptr = [0] + torch.cumsum(counts, 0).tolist()
+        plan.cache[key] = dict(
+            seg_rel=seg_rel.to(torch.int32).contiguous(),
+            order=order.to(torch.int32).contiguous(),
+            dst_of_order=segs["seg_dst"][order].contiguous(),
+            rel_ptr_c=ops.host_i32(rel_ptr), R=R)
+    return plan.cache[key]
+
+
+class HGTLayer(nn.Module):
+    """reference models/HGT.py:21-127."""
+
+    def __init__(self, in_dim, out_dim, node_dict, edge_dict, n_heads, dropout=0.2, use_norm=False):
+        super().__init__()
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        self.node_dict = node_dict
+        self.edge_dict = edge_dict
+        self.num_types = len(node_dict)
+        self.num_relations = len(edge_dict)
+        self.total_rel = self.num_types * self.num_relations * self.num_types
+        self.n_heads = n_heads
+        self.d_k = out_dim // n_heads
+        self.sqrt_dk = math.sqrt(self.d_k)
+        self.att = None
+        self.use_norm = use_norm
+        T = self.num_types
+        self.k_linears = nn.ModuleList([nn.Linear(in_dim, out_dim) for _ in range(T)])
+        self.q_linears = nn.ModuleList([nn.Linear(in_dim, out_dim) for _ in range(T)])
+        self.v_linears = nn.ModuleList([nn.Linear(in_dim, out_dim) for _ in range(T)])
+        self.a_linears = nn.ModuleList([nn.Linear(out_dim, out_dim) for _ in range(T)])
+        self.norms = nn.ModuleList([nn.LayerNorm(out_dim) for _ in range(T)] if use_norm else [])
+        self.relation_pri = nn.Parameter(torch.ones(self.num_relations, self.n_heads))
+        self.relation_att = nn.Parameter(torch.Tensor(self.num_relations, n_heads, self.d_k, self.d_k))
+        self.relation_msg = nn.Parameter(torch.Tensor(self.num_relations, n_heads, self.d_k, self.d_k))
+        self.skip = nn.Parameter(torch.ones(T))
+        self.drop = nn.Dropout(dropout)
+        nn.init.xavier_uniform_(self.relation_att)
+        nn.init.xavier_uniform_(self.relation_msg)
+        self._packs = PackCache()
+
+    def _packed(self, order):
+        params = [p for p in self.parameters()]
+
+        def build():
+            dev = self.skip.device
+            wk, bk = stack_linears(self.k_linears, order)
+            wv, bv = stack_linears(self.v_linears, order)
+            wq, bq = stack_linears(self.q_linears, order)
+            w_kvq = torch.cat([wk, wv, wq], 1).contiguous()
+            b_kvq = torch.cat([bk, bv, bq], 1).contiguous()
+            wa, ba = stack_linears(self.a_linears, order)
+            skip = self.skip[torch.tensor(order, device=dev)].contiguous()
+            if self.use_norm:
+                gamma = torch.stack([self.norms[i].weight for i in order]).contiguous()
+                beta = torch.stack([self.norms[i].bias for i in order]).contiguous()
+            else:
+                gamma = beta = None
+            return w_kvq, b_kvq, wa, ba, skip, gamma, beta
+
+        return self._packs.get(tuple(order), params, build)
+
+    def forward_packed(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
+        D, H, dk = self.out_dim, self.n_heads, self.d_k
+        order = _graph_type_order(plan, self.node_dict)
+        w_kvq, b_kvq, wa, ba, skip, gamma, beta = self._packed(order)
+        tpc = plan.type_ptr_c()
+        segs = plan.segments()
+        grp = _relation_groups(plan, self.edge_dict, id(self.edge_dict))
+        S = segs["S"]
+        kvq = ops.typed_linear(x, w_kvq, b_kvq, plan.type_ptr, type_ptr_c=tpc)
+        k, v, q = kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:]
+        # q'_seg = relation_att[r,h] . q[dst,h]   (w_kn=0: y_n = sum_k W[n,k] x_k)
+        qseg = ops.rel_transform(q, grp["dst_of_order"], grp["order"], self.relation_att, grp["rel_ptr_c"], grp["R"],
+                                 H, dk, False, S)
+        aggseg = ops.hetero_attn_seg(k, v, qseg, segs["seg_ptr"], grp["seg_rel"], plan.e_src, self.relation_pri,
+                                     D, H)
+        # msg_seg = aggseg[h] . relation_msg[r,h]   (w_kn=1: y_n = sum_k x_k W[k,n])
+        msgseg = ops.rel_transform(aggseg, grp["order"], grp["order"], self.relation_msg, grp["rel_ptr_c"], grp["R"],
+                                   H, dk, True, S)
+        agg = ops.segment_combine(msgseg, segs["row_seg_ptr"], plan.node_inv_r, plan.N, D)
+        mask = None
+        if self.training and self.drop.p > 0:
+            mask = F.dropout(torch.ones_like(agg), self.drop.p, True)
+        out = ops.typed_linear(agg, wa, ba, plan.type_ptr, skip=skip, res=x, row_gate=plan.node_inv_r,
+                               drop_mask=mask, type_ptr_c=tpc)
+        if self.use_norm:
+            # NB the reference normalises only types that received a message (models/HGT.py:118-126);
+            # passthrough types keep h unchanged, so the LayerNorm is applied row-gated below.
+            out = _gated_layernorm(out, gamma, beta, plan, tpc)
+        return out
+
+    def forward(self, G: HeteroGraph, h: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        plan = G.plan()
+        x = packed_features(G, plan, h)
+        return unpack_rows(plan, self.forward_packed(plan, x))
+
+
+def _gated_layernorm(x, gamma, beta, plan: GraphPlan, tpc):
+    """LayerNorm on the rows of node types that have an incoming relation; other types pass through
+    (reference models/HGT.py:118-120 `continue`s before the norm)."""
+    if "ln_segments" not in plan.cache:
+        T = len(plan.ntypes)
+        live = []
+        for t in range(T):
+            a, b = plan.type_ptr[t], plan.type_ptr[t + 1]
+            live.append(b > a and bool((plan.node_inv_r[a:b] != 0).all().item()))
+        plan.cache["ln_segments"] = live
+    live = plan.cache["ln_segments"]
+    if all(live[t] or plan.type_ptr[t] == plan.type_ptr[t + 1] for t in range(len(live))):
+        return ops.typed_layernorm(x, gamma, beta, plan.type_ptr, type_ptr_c=tpc, inplace=True)
+    for t, ok in enumerate(live):
+        a, b = plan.type_ptr[t], plan.type_ptr[t + 1]
+        if ok:
+            ops.typed_layernorm(x[a:b], gamma[t:t + 1], beta[t:t + 1], [0, b - a], inplace=True)
+    return x
+
+
+class HGT(nn.Module):
+    """reference models/HGT.py:130-209.  forward(G, h=None) -> logits [B, out_dim]."""
+
+    def __init__(self, node_dict, edge_dict, in_dim, hidden_dim, out_dim, n_layers, n_heads, use_norm=True,
+                 graph_pooling_type="mean"):
+        super().__init__()
+        self.node_dict = node_dict
+        self.edge_dict = edge_dict
+        self.gcs = nn.ModuleList()
+        self.in_dim = in_dim
+        self.hidden_dim = hidden_dim
+        self.out_dim = out_dim
+        self.n_layers = n_layers
+        self.graph_pooling_type = _check_pool(graph_pooling_type)
+        self.adapt_ws = nn.ModuleList([nn.Linear(in_dim, hidden_dim) for _ in range(len(node_dict))])
+        for _ in range(n_layers):
+            self.gcs.append(HGTLayer(hidden_dim, hidden_dim, node_dict, edge_dict, n_heads, use_norm=use_norm))
+        self.out = nn.Linear(hidden_dim, out_dim)                         # unused (models/HGT.py:150)
+        self.linears_prediction = nn.ModuleDict({
+            k: nn.ModuleList([nn.Linear(hidden_dim, out_dim) for _ in range(n_layers + 1)]) for k in node_dict})
+        self._packs = PackCache()
+
+    def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
+        plan = G.plan()
+        T, B = len(plan.ntypes), plan.B
+        order = _graph_type_order(plan, self.node_dict)
+        names = list(plan.ntypes)
+        x = packed_features(G, plan, h)
+        params = [p for m in self.adapt_ws for p in m.parameters()]
+        w_in, b_in = self._packs.get(("in", tuple(order)), params, lambda: stack_linears(self.adapt_ws, order))
+        x = ops.typed_linear(x, w_in, b_in, plan.type_ptr, act=ops.ACT_GELU, type_ptr_c=plan.type_ptr_c())  # :176-184
+        scale = readout_scale(plan, G.independent)
+        hg = None
+        n_run = self.n_layers if return_embeddings else self.n_layers
+        for i in range(n_run):                                             # :189-199
+            pooled = ops.segment_pool(x, plan.seg_ptr, T * B, self.graph_pooling_type)
+            pp = [p for nt in names for p in self.linears_prediction[nt][i].parameters()]
+            w_p, b_p = self._packs.get(("pred", i, tuple(names)), pp, lambda i=i: (
+                torch.stack([self.linears_prediction[nt][i].weight for nt in names]).contiguous(),
+                torch.stack([self.linears_prediction[nt][i].bias for nt in names]).contiguous()))
+            o = ops.typed_linear(pooled, w_p, b_p, plan.readout_ptr(), row_scale=scale).view(T, B, -1).sum(0)
+            hg = o if hg is None else hg + o
+            # the output of the LAST layer is never read by the reference (models/HGT.py:199-209);
+            # it is computed only when the caller asks for the embeddings
+            if i + 1 < self.n_layers or return_embeddings:
+                x = self.gcs[i].forward_packed(plan, x)
+        if hg is None:
+            hg = torch.zeros(B, self.out_dim, device=x.device)
+        return (hg, unpack_rows(plan, x)) if return_embeddings else hg

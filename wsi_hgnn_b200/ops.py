@@ -1,0 +1,240 @@
+"""Tensor-level wrappers of the C-ABI kernels (include/wsi_hgnn.h).
+
+Every function validates dtype / device / strides, takes raw device pointers of torch tensors and
+enqueues the kernel on torch's current CUDA stream (so torch.cuda.graph capture works).  PyTorch is
+used for device memory and streams only; there is no CPU or PyTorch fallback - a CPU tensor raises.
+"""
+import ctypes
+from functools import lru_cache
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU = 0, 1
+POOL_OPS = {"sum": 0, "mean": 1, "max": 2}
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+
+_cur_device = [None]
+
+
+def _prep(t: torch.Tensor):
+    """The library has its own (static) CUDA runtime: keep its current device in step with the tensor's."""
+    if not t.is_cuda:
+        raise RuntimeError("wsi_hgnn_b200 ops need CUDA tensors: the hot path has no CPU fallback "
+                           "(the CPU oracle under oracle/ is test infrastructure only)")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if _cur_device[0] != idx:
+        _lib.check(_lib.load().wsi_set_device(idx), "wsi_set_device")
+        _cur_device[0] = idx
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _rows(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
+    """(pointer, row stride) of a 2-D row-strided tensor (unit column stride), or (None, 0)."""
+    if t is None:
+        return None, 0
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor")
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name}: expected a 2-D tensor with unit column stride, got shape {tuple(t.shape)} "
+                         f"strides {t.stride()}")
+    return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+
+
+def _vec(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
+    if t is None:
+        return None
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise TypeError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} on {t.device}")
+    return t.data_ptr()
+
+
+def host_i32(values: Sequence[int]):
+    return (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+
+
+@lru_cache(maxsize=None)
+def head_perm(D: int, H: int) -> Optional[torch.Tensor]:
+    """Lane-grouped column order of the vector attention kernel, or None when (D, H) has none.
+    perm[p] = logical column stored at physical position p."""
+    if D % 128 != 0 or D > 1024 or H < 1 or H > 32 or (H & (H - 1)) != 0 or D % H != 0:
+        return None
+    buf = (ctypes.c_int32 * D)()
+    _lib.check(_lib.load().wsi_head_perm(D, H, buf), "wsi_head_perm")
+    return torch.tensor(list(buf), dtype=torch.int64)
+
+
+def typed_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], type_ptr: Sequence[int], *,
+                 act: int = ACT_NONE, skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+                 drop_mask: Optional[torch.Tensor] = None, row_gate: Optional[torch.Tensor] = None,
+                 row_scale: Optional[torch.Tensor] = None, impl: int = IMPL_AUTO,
+                 out: Optional[torch.Tensor] = None, type_ptr_c=None) -> torch.Tensor:
+    """y[rows of type t] = epilogue(x[rows of type t] @ w[t].T); see wsi_typed_linear_f32."""
+    lib = _lib.load()
+    stream = _prep(x)
+    T = len(type_ptr) - 1
+    if w.dim() != 3 or w.shape[0] != T:
+        raise ValueError(f"typed_linear: w must be [T={T}, n_out, K], got {tuple(w.shape)}")
+    n_out, K = int(w.shape[1]), int(w.shape[2])
+    N = int(type_ptr[-1])
+    if x.shape[0] != N or x.shape[1] != K:
+        raise ValueError(f"typed_linear: x is {tuple(x.shape)}, expected [{N}, {K}]")
+    xp, ldx = _rows(x, "x")
+    wp = _vec(w, "w")
+    bp = _vec(bias, "bias")
+    if bias is not None and tuple(bias.shape) != (T, n_out):
+        raise ValueError("typed_linear: bias must be [T, n_out]")
+    if out is None:
+        out = torch.empty((N, n_out), dtype=torch.float32, device=x.device)
+    yp, ldy = _rows(out, "out")
+    rp, ldres = _rows(res, "res")
+    mp, ldm = _rows(drop_mask, "drop_mask")
+    ws_bytes = lib.wsi_typed_linear_workspace_bytes(N, K, n_out, T, impl)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+    tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
+    rc = lib.wsi_typed_linear_f32(xp, ldx, wp, bp, K, n_out, tp, T, act, _vec(skip, "skip"), rp, ldres, mp, ldm,
+                                  _vec(row_gate, "row_gate"), _vec(row_scale, "row_scale"), yp, ldy, impl,
+                                  ws.data_ptr() if ws is not None else None, ws_bytes, stream)
+    _lib.check(rc, "wsi_typed_linear_f32")
+    return out
+
+
+def hetero_attn(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, rowptr: torch.Tensor, e_src: torch.Tensor,
+                e_sim: torch.Tensor, e_rel: torch.Tensor, node_inv_r: torch.Tensor, e_w: torch.Tensor,
+                e_b: torch.Tensor, D: int, H: int, use_head_perm: bool, want_attn: bool = False):
+    """HEAT edge attention for all relations of one layer; see wsi_hetero_attn_fwd."""
+    lib = _lib.load()
+    stream = _prep(q)
+    N = int(q.shape[0])
+    kp, ldk = _rows(k, "k")
+    vp, ldv = _rows(v, "v")
+    qp, ldq = _rows(q, "q")
+    agg = torch.empty((N, D), dtype=torch.float32, device=q.device)
+    attn = torch.empty((int(e_src.shape[0]), H), dtype=torch.float32, device=q.device) if want_attn else None
+    rc = lib.wsi_hetero_attn_fwd(kp, ldk, vp, ldv, qp, ldq, _vec(rowptr, "rowptr", torch.int32),
+                                 _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
+                                 _vec(e_rel, "e_rel", torch.uint8), _vec(node_inv_r, "node_inv_r"),
+                                 _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, D, H,
+                                 1 if use_head_perm else 0, agg.data_ptr(), D,
+                                 attn.data_ptr() if attn is not None else None, stream)
+    _lib.check(rc, "wsi_hetero_attn_fwd")
+    return (agg, attn) if want_attn else agg
+
+
+def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int, use_head_perm: bool = False):
+    """HGT edge attention over (dst, relation) segments; see wsi_hetero_attn_seg_fwd."""
+    lib = _lib.load()
+    stream = _prep(qseg)
+    S = int(qseg.shape[0])
+    kp, ldk = _rows(k, "k")
+    vp, ldv = _rows(v, "v")
+    qp, ldq = _rows(qseg, "qseg")
+    out = torch.empty((S, D), dtype=torch.float32, device=qseg.device)
+    rc = lib.wsi_hetero_attn_seg_fwd(kp, ldk, vp, ldv, qp, ldq, _vec(seg_ptr, "seg_ptr", torch.int32),
+                                     _vec(seg_rel, "seg_rel", torch.int32), _vec(e_src, "e_src", torch.int32),
+                                     _vec(rel_pri, "rel_pri"), S, D, H, 1 if use_head_perm else 0,
+                                     out.data_ptr(), D, stream)
+    _lib.check(rc, "wsi_hetero_attn_seg_fwd")
+    return out
+
+
+def rel_transform(x, x_row_idx, y_row_idx, w, rel_ptr_c, R: int, H: int, d_k: int, w_kn: bool, n_out_rows: int):
+    """Per-(relation, head) d_k x d_k transform of relation-grouped segments; see wsi_rel_transform."""
+    lib = _lib.load()
+    stream = _prep(x)
+    xp, ldx = _rows(x, "x")
+    if tuple(w.shape) != (R, H, d_k, d_k):
+        raise ValueError(f"rel_transform: w must be [{R}, {H}, {d_k}, {d_k}], got {tuple(w.shape)}")
+    y = torch.empty((n_out_rows, H * d_k), dtype=torch.float32, device=x.device)
+    rc = lib.wsi_rel_transform(xp, ldx, _vec(x_row_idx, "x_row_idx", torch.int32),
+                               _vec(y_row_idx, "y_row_idx", torch.int32), _vec(w, "w"), rel_ptr_c, R, H, d_k,
+                               1 if w_kn else 0, y.data_ptr(), H * d_k, stream)
+    _lib.check(rc, "wsi_rel_transform")
+    return y
+
+
+def segment_combine(msg, row_seg_ptr, node_inv_r, N: int, D: int):
+    lib = _lib.load()
+    stream = _prep(node_inv_r)
+    mp, ldm = _rows(msg, "msg")
+    agg = torch.empty((N, D), dtype=torch.float32, device=node_inv_r.device)
+    rc = lib.wsi_segment_combine(mp, ldm, _vec(row_seg_ptr, "row_seg_ptr", torch.int32),
+                                 _vec(node_inv_r, "node_inv_r"), N, D, agg.data_ptr(), D, stream)
+    _lib.check(rc, "wsi_segment_combine")
+    return agg
+
+
+def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, type_ptr_c=None, inplace=False):
+    lib = _lib.load()
+    stream = _prep(x)
+    T = len(type_ptr) - 1
+    D = int(x.shape[1])
+    if tuple(gamma.shape) != (T, D) or tuple(beta.shape) != (T, D):
+        raise ValueError("typed_layernorm: gamma/beta must be [T, D]")
+    xp, ldx = _rows(x, "x")
+    y = x if inplace else torch.empty_like(x)
+    yp, ldy = _rows(y, "y")
+    tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
+    rc = lib.wsi_typed_layernorm(xp, ldx, _vec(gamma, "gamma"), _vec(beta, "beta"), tp, T, D, float(eps), yp, ldy,
+                                 stream)
+    _lib.check(rc, "wsi_typed_layernorm")
+    return y
+
+
+def segment_pool(x: torch.Tensor, seg_ptr: torch.Tensor, n_seg: int, op: str) -> torch.Tensor:
+    """[n_seg, D] typed readout over (type, graph) row segments; see wsi_segment_pool_fwd."""
+    if op not in POOL_OPS:
+        raise NotImplementedError(op)
+    lib = _lib.load()
+    stream = _prep(x)
+    N, D = int(x.shape[0]), int(x.shape[1])
+    xp, ldx = _rows(x, "x")
+    out = torch.empty((n_seg, D), dtype=torch.float32, device=x.device)
+    ws_bytes = lib.wsi_segment_pool_workspace_bytes(N, n_seg, D)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+    rc = lib.wsi_segment_pool_fwd(xp, ldx, _vec(seg_ptr, "seg_ptr", torch.int32), n_seg, N, D, POOL_OPS[op],
+                                  out.data_ptr(), D, ws.data_ptr() if ws is not None else None, ws_bytes, stream)
+    _lib.check(rc, "wsi_segment_pool_fwd")
+    return out
+
+
+def knn_topk(feat: torch.Tensor, topn: int, q_begin: int = 0, q_end: Optional[int] = None, want_dist: bool = False):
+    """Exact L2 k-NN (self included, ordered by (distance, index)); see wsi_knn_topk.
+    -> int32 [q_end - q_begin, topn] (and the fp32 distances)."""
+    lib = _lib.load()
+    stream = _prep(feat)
+    if feat.dtype != torch.float32 or feat.dim() != 2 or not feat.is_contiguous():
+        raise TypeError("knn_topk: features must be a contiguous fp32 [N, F] tensor")
+    n, F = int(feat.shape[0]), int(feat.shape[1])
+    q_end = n if q_end is None else q_end
+    if topn > n:
+        # HNSW would return < radius hits -> np.stack fails -> ValueError (graph_constructor.py:268-272)
+        raise ValueError(f"fewer than topn={topn} nodes (n={n})")
+    nq = q_end - q_begin
+    nbr = torch.empty((nq, topn), dtype=torch.int32, device=feat.device)
+    dist = torch.empty((nq, topn), dtype=torch.float32, device=feat.device) if want_dist else None
+    ws_bytes = lib.wsi_knn_workspace_bytes(n, F, topn, q_begin, q_end)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=feat.device)
+    rc = lib.wsi_knn_topk(feat.data_ptr(), n, F, topn, q_begin, q_end, nbr.data_ptr(),
+                          dist.data_ptr() if dist is not None else None, ws.data_ptr(), ws_bytes, stream)
+    _lib.check(rc, "wsi_knn_topk")
+    return (nbr, dist) if want_dist else nbr
+
+
+def edge_pearson(feat: torch.Tensor, src: torch.Tensor, dst: torch.Tensor):
+    """(sim fp32 [E], etype uint8 [E]) = Pearson r of the two feature rows of every edge; see wsi_edge_pearson."""
+    lib = _lib.load()
+    stream = _prep(feat)
+    if feat.dtype != torch.float32 or feat.dim() != 2 or not feat.is_contiguous():
+        raise TypeError("edge_pearson: features must be a contiguous fp32 [N, F] tensor")
+    E = int(src.shape[0])
+    sim = torch.empty(E, dtype=torch.float32, device=feat.device)
+    et = torch.empty(E, dtype=torch.uint8, device=feat.device)
+    rc = lib.wsi_edge_pearson(feat.data_ptr(), int(feat.shape[0]), int(feat.shape[1]), _vec(src, "src", torch.int64),
+                              _vec(dst, "dst", torch.int64), E, sim.data_ptr(), et.data_ptr(), stream)
+    _lib.check(rc, "wsi_edge_pearson")
+    return sim, et
