@@ -17,9 +17,15 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("counts,K,n_out", [([70, 0, 133], 48, 96), ([1, 2, 3], 7, 5), ([300], 200, 200),
-                                            ([128, 256], 512, 1536), ([0, 0, 5], 16, 256)])
-@pytest.mark.parametrize("impl", [ops.IMPL_SIMT, ops.IMPL_AUTO])
+TC_SHAPES = [([600, 0, 700], 512, 1536), ([128, 256, 300], 200, 200), ([1000], 1024, 512), ([513], 64, 64),
+             ([130, 1, 127, 500, 0, 3], 256, 520), ([2731, 2731, 2730], 512, 512)]
+
+
+@pytest.mark.parametrize("counts,K,n_out,impl",
+                         [(c, k, n, i) for c, k, n in [([70, 0, 133], 48, 96), ([1, 2, 3], 7, 5), ([300], 200, 200),
+                                                       ([128, 256], 512, 1536), ([0, 0, 5], 16, 256)]
+                          for i in (ops.IMPL_SIMT, ops.IMPL_AUTO)] +
+                         [(c, k, n, ops.IMPL_TC) for c, k, n in TC_SHAPES])
 def test_typed_linear_epilogues(counts, K, n_out, impl):
     g = torch.Generator().manual_seed(sum(counts) + K)
     T = len(counts)
@@ -67,6 +73,14 @@ def test_typed_linear_epilogues(counts, K, n_out, impl):
     ops.typed_linear(c(x), c(w), None, ptr, out=big[:, 8:], impl=impl)
     assert rel(big[:, 8:], ref() - torch.cat([b[t].double().expand(counts[t], n_out) for t in range(T)])) < 2e-5
     assert float(big[:, :8].abs().sum()) == 0.0
+
+
+def test_typed_linear_tc_refuses_unfit_shapes():
+    """impl=2 (force tcgen05) must fail loudly - never silently take another path."""
+    x = torch.randn(8, 7, device="cuda")
+    w = torch.randn(1, 5, 7, device="cuda")
+    with pytest.raises(NotImplementedError):
+        ops.typed_linear(x, w, None, [0, 8], impl=ops.IMPL_TC)
 
 
 def _random_csr(n_dst, n_src, n_edges, n_rel, g, hub=0, isolated=0.2):
