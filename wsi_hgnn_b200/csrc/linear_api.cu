@@ -35,7 +35,9 @@ extern "C" int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w,
   ep.bias = bias; ep.act = act; ep.skip = skip; ep.res = res; ep.ldres = ldres;
   ep.drop_mask = drop_mask; ep.ldmask = ldmask; ep.row_gate = row_gate; ep.row_scale = row_scale;
   ep.y = y; ep.ldy = ldy; ep.n_out = n_out;
-  const bool ptr_ok = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && ldy % 4 == 0;
+  const bool ptr_ok = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) |
+                        reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(drop_mask)) & 15) == 0 &&
+                      ldy % 4 == 0 && (!res || ldres % 4 == 0) && (!drop_mask || ldmask % 4 == 0);
   const bool tc_ok = wsi_typed_linear_tc_supported(n_rows, K, n_out, ldx) && ptr_ok && workspace != nullptr;
   if (impl == 2 && !tc_ok) {
     wsi_set_error("typed_linear: shape (rows=%lld K=%d n_out=%d ldx=%lld) does not fit the tcgen05 path",

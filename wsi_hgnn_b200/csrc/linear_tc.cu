@@ -7,14 +7,20 @@
 // is split into two bf16 values  x = hi + lo  (|lo| <= 2^-9 |x|)  and the product is formed from three
 // bf16 x bf16 -> fp32 MMAs   hi.hi + hi.lo + lo.hi   (the dropped lo.lo term is ~2^-18 relative):
 //   1. split_bf16_kernel      X, W (fp32) -> workspace [X_hi; X_lo] and [W_hi; W_lo]   (HBM-bound pre-pass)
-//   2. typed_linear_tc_kernel persistent, warp-specialised, one CTA per SM:
-//        warp 0      TMA producer: per k-block loads the four 128B-swizzled tiles A_hi, A_lo, B_hi, B_lo
-//        warp 1      MMA issuer  : 3 tcgen05.mma (M=128, N=256, K=16) per 16-wide k-slice into TMEM
-//        warps 2..5  epilogue    : tcgen05.ld -> smem transpose -> fused epilogue (epilogue.cuh) -> coalesced
-//                                  16 B global stores; double-buffered TMEM (2 x 256 columns) so the epilogue of
-//                                  tile i overlaps the MMAs of tile i+1
+//   2. typed_linear_tc_kernel persistent, warp-specialised, one CTA PAIR (cluster of 2, cta_group::2) per two SMs;
+//      a pair owns a 256 x 256 output tile: each CTA stages its own 128 rows of A and HALF of the W tile, so the
+//      L2 -> smem traffic per output (the limiter of the 3-term product) is 2/3 of a single-CTA 128 x 256 tile:
+//        warp 0      TMA producer (each CTA): per k-block the four 128B-swizzled tiles A_hi, A_lo, B_hi/2, B_lo/2,
+//                    completion bytes posted on the LEADER CTA's full barrier
+//        warp 1      MMA issuer (leader CTA): 3 tcgen05.mma.cta_group::2 (M=256, N=256, K=16) per 16-wide k-slice,
+//                    tcgen05.commit multicast to both CTAs' empty / tmem-full barriers
+//        warps 2..5  epilogue (each CTA, its own 128 TMEM lanes): tcgen05.ld -> smem transpose -> fused epilogue
+//                    (epilogue.cuh) -> coalesced 16 B global stores; double-buffered TMEM (2 x 256 columns) so the
+//                    epilogue of tile i overlaps the MMAs of tile i+1
 // Tensor-pipe bound: algorithmic flops 2*N*K*n_out (x3 MMAs issued for the split).
 #include <cuda.h>
+
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -22,27 +28,47 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2, UMMA_K = 16;
+constexpr int BM = 128;            // rows per CTA (TMEM lanes)
+constexpr int BN = 256;            // columns per tile (UMMA N; each CTA of the pair stages BN/2 rows of W)
+constexpr int BK = 64;             // bf16 per k-block = one 128 B swizzle row
+constexpr int STAGES = 3, UMMA_K = 16;
+constexpr int PAIR_M = 2 * BM;     // rows per CTA pair (UMMA M = 256, cta_group::2)
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int B_TILE_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-constexpr int EPI_LD = 36;                               // staging row pitch in floats (16 B aligned, conflict free)
+constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;       // per CTA
+constexpr int EPI_LD = 32;                               // staging row pitch in floats; float4 slots XOR-swizzled by row
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 4 * EPI_WARP_FLOATS * 4 + 256;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                             // 2 warps per TMEM lane quarter, each takes half of the columns
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * EPI_WARP_FLOATS * 4 + 256;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// arrive on a barrier anywhere in the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -55,27 +81,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+// TMA tile load into THIS CTA's smem; completion bytes are posted on `cluster_bar`, the leader CTA's barrier
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t cluster_bar, uint32_t dst, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrive (once the MMAs issued so far retire) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32
+// D[tmem, 256 x N over the CTA pair] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i).  Asynchronous:
+// the registers are valid after tc_ld_wait().
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -87,8 +117,8 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B):
 // start address >> 4 | LBO 1 (unused for swizzled K-major) | SBO 1024 B >> 4 | version 1 (sm_100) | SWIZZLE_128B
@@ -102,7 +132,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   return d;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------ pre-pass
 // fp32 -> [hi; lo] bf16.  src rows have stride ld_src floats; dst is dense [2 * rows, K] (lo half at row `rows`).
@@ -131,34 +161,32 @@ struct TcArgs {
   int n_rows;        // N  (row offset of the lo half of the A workspace)
   int w_rows;        // T * n_out (row offset of the lo half of the W workspace)
   int K, n_out;
-  int n_tiles_m, n_tiles_n;
-  int vec_epi;       // 1: every epilogue operand is 16 B aligned -> float4 loads
+  int n_tiles_m, n_tiles_n;   // n_tiles_m counts 256-row PAIR tiles
+  int dbg;           // development only (env WSI_TC_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads, bit 2 = skip the epilogue body
 };
 
-__device__ __forceinline__ float4 epi_apply4(const LinearEpilogue& ep, float4 acc, int t, int64_t row, int n,
-                                             float alpha, bool gate_open, float rscale, bool vec) {
+// FULL = false: v = act(acc + bias).  FULL = true: + dropout mask, sigma(skip) residual mix with row gate, row scale.
+template <bool FULL>
+__device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc, float4 bb, float4 mm, float4 rr,
+                                           float alpha, bool gate_open, float rscale) {
   float a[4] = {acc.x, acc.y, acc.z, acc.w};
-  if (vec) {
-    float bb[4] = {0.f, 0.f, 0.f, 0.f}, mm[4] = {1.f, 1.f, 1.f, 1.f}, rr[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ep.bias) *reinterpret_cast<float4*>(bb) = __ldg(reinterpret_cast<const float4*>(ep.bias + (int64_t)t * ep.n_out + n));
-    if (ep.drop_mask) *reinterpret_cast<float4*>(mm) = __ldg(reinterpret_cast<const float4*>(ep.drop_mask + row * ep.ldmask + n));
-    if (ep.skip) *reinterpret_cast<float4*>(rr) = __ldg(reinterpret_cast<const float4*>(ep.res + row * ep.ldres + n));
+  const float b4[4] = {bb.x, bb.y, bb.z, bb.w}, m4[4] = {mm.x, mm.y, mm.z, mm.w}, r4[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v = a[i] + bb[i];
-      if (ep.act == WSI_ACT_GELU) v = wsi_gelu(v);
-      v *= mm[i];
-      if (ep.skip) v = gate_open ? (v * alpha + rr[i] * (1.0f - alpha)) : rr[i];
-      a[i] = v * rscale;
+  for (int i = 0; i < 4; ++i) {
+    float v = a[i] + b4[i];
+    if (ep.act == WSI_ACT_GELU) v = wsi_gelu(v);
+    if (FULL) {
+      v *= m4[i];
+      if (ep.skip) v = gate_open ? (v * alpha + r4[i] * (1.0f - alpha)) : r4[i];
+      v *= rscale;
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = wsi_epilogue_value(ep, a[i], t, row, n + i, alpha, gate_open, rscale);
+    a[i] = v;
   }
   return make_float4(a[0], a[1], a[2], a[3]);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool FULL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ TypeSegs segs, const __grid_constant__ LinearEpilogue ep, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -166,137 +194,175 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* gen = smem_raw + (base - raw);
   float* epi_stage = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
-  const uint32_t bars = base + STAGES * STAGE_BYTES + 4 * EPI_WARP_FLOATS * 4;
+  const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_WARPS * EPI_WARP_FLOATS * 4;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES,
                  tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16;
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                           // 0 = leader (issues the MMAs of the pair)
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int num_kb = (a.K + BK - 1) / BK;
   const int total_tiles = a.n_tiles_m * a.n_tiles_n;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 4); }
+    // full: the leader's expect_tx arrive + the peer's plain arrive; empty / tmem_full: one tcgen05.commit;
+    // tmem_empty (leader's is the one waited on): the epilogue warps of both CTAs
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();                                                    // peer barriers are initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const int tm = tile / a.n_tiles_n, tn = tile - tm * a.n_tiles_n;
         const int t = wsi_tile_group(segs, tm);
-        const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * BM;
-        const int wrow0 = t * a.n_out + tn * BN;
+        const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * PAIR_M + (int)rank * BM;
+        const int wrow0 = t * a.n_out + tn * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = full_bar + 8 * stage;
+          const uint32_t fb = mapa(full_bar + 8 * stage, 0);
           const uint32_t s0 = base + stage * STAGE_BYTES;
-          mbar_expect_tx(fb, STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(full_bar + 8 * stage, (a.dbg & 2) ? 0 : 2 * STAGE_BYTES);
+          if (!(a.dbg & 2)) {
           tma_load_2d(&tmA, fb, s0, kb * BK, row0);
           tma_load_2d(&tmA, fb, s0 + A_TILE_BYTES, kb * BK, a.n_rows + row0);
           tma_load_2d(&tmB, fb, s0 + 2 * A_TILE_BYTES, kb * BK, wrow0);
           tma_load_2d(&tmB, fb, s0 + 2 * A_TILE_BYTES + B_TILE_BYTES, kb * BK, a.w_rows + wrow0);
+          }
+          if (rank != 0) mbar_arrive_cluster(fb);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one elected lane)
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);                // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar + 8 * stage, phase);
+    // ===================================================================== MMA issuer (leader CTA, one elected lane)
+    if (rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);              // both epilogues have drained this accumulator
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t s0 = base + stage * STAGE_BYTES;
-          const uint64_t a_hi = make_smem_desc(s0), a_lo = make_smem_desc(s0 + A_TILE_BYTES);
-          const uint64_t b_hi = make_smem_desc(s0 + 2 * A_TILE_BYTES),
-                         b_lo = make_smem_desc(s0 + 2 * A_TILE_BYTES + B_TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t s0 = base + stage * STAGE_BYTES;
+            const uint64_t a_hi = make_smem_desc(s0), a_lo = make_smem_desc(s0 + A_TILE_BYTES);
+            const uint64_t b_hi = make_smem_desc(s0 + 2 * A_TILE_BYTES),
+                           b_lo = make_smem_desc(s0 + 2 * A_TILE_BYTES + B_TILE_BYTES);
+            if (!(a.dbg & 1))
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);   // +32 B per k-slice inside the swizzle atom
-            tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kb | ks) != 0);
-            tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1);
-            tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);   // +32 B per k-slice inside the swizzle atom
+              tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kb | ks) != 0);
+              {
+              tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1);
+              tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
+              }
+            }
+            tc_commit_pair(empty_bar + 8 * stage);                   // smem slot free (both CTAs) once these retire
+            if (kb == num_kb - 1) tc_commit_pair(tfull_bar + 8 * acc);   // accumulator complete (both CTAs)
           }
-          tc_commit(empty_bar + 8 * stage);                          // smem slot free once these MMAs retire
-          if (kb == num_kb - 1) tc_commit(tfull_bar + 8 * acc);      // accumulator complete
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================================================================== epilogue warps (TMEM lane quarter = warp % 4)
-    const int q = warp & 3;
+    // ===================================================================== epilogue warps
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the BN columns in halves.
+    const int q = warp & 3, half = (warp - 2) >> 2;
     float* stg = epi_stage + (warp - 2) * EPI_WARP_FLOATS;
-    const bool vec = a.vec_epi != 0;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    const int rsub = lane >> 3, c4 = (lane & 7) << 2;
+    constexpr int CHUNKS = BN / 32 / 2;                              // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const int tm = tile / a.n_tiles_n, tn = tile - tm * a.n_tiles_n;
       const int t = wsi_tile_group(segs, tm);
-      const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * BM + q * 32;
-      const int row_end = segs.ptr[t + 1];
-      const int n0 = tn * BN;
-      const float alpha = ep.skip ? wsi_sigmoid(__ldg(ep.skip + t)) : 1.0f;
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
-      const int rsub = lane >> 3, c4 = (lane & 7) << 2;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n0 + c * 32 >= a.n_out || row0 >= row_end) break;        // warp-uniform
-        float v[32];
-        tc_ld_32x32(taddr + c * 32, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int n = n0 + c * 32 + c4;
+      const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * PAIR_M + (int)rank * BM + q * 32;
+      const int rows_left = segs.ptr[t + 1] - (row0 + rsub);         // this lane handles rows row0 + rsub + 4 it
+      const int n0 = tn * BN + half * (BN / 2) + c4;                 // this lane's first column
+      const float alpha = (FULL && ep.skip) ? wsi_sigmoid(__ldg(ep.skip + t)) : 1.0f;
+      float* yp = ep.y + (int64_t)(row0 + rsub) * ep.ldy + n0;
+      const float* bias_p = ep.bias ? ep.bias + (int64_t)t * ep.n_out + n0 : nullptr;
+      const float* res_p = (FULL && ep.skip) ? ep.res + (int64_t)(row0 + rsub) * ep.ldres + n0 : nullptr;
+      const float* mask_p = (FULL && ep.drop_mask) ? ep.drop_mask + (int64_t)(row0 + rsub) * ep.ldmask + n0 : nullptr;
+      float gate[8], rscl[8];
+      if (FULL) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rsub;
-          const int64_t row = row0 + rr;
-          if (row < row_end && n < a.n_out) {
-            const float4 accv = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + c4);
-            const bool gate_open = ep.row_gate ? __ldg(ep.row_gate + row) != 0.f : true;
-            const float rscale = ep.row_scale ? __ldg(ep.row_scale + row) : 1.0f;
-            const float4 o = epi_apply4(ep, accv, t, row, n, alpha, gate_open, rscale, vec);
-            *reinterpret_cast<float4*>(ep.y + row * ep.ldy + n) = o;
+          const bool ok = it * 4 < rows_left;
+          gate[it] = (ep.row_gate && ok) ? __ldg(ep.row_gate + row0 + rsub + it * 4) : 1.f;
+          rscl[it] = (ep.row_scale && ok) ? __ldg(ep.row_scale + row0 + rsub + it * 4) : 1.f;
+        }
+      }
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        if (n0 - c4 + c * 32 >= a.n_out || rows_left + rsub <= 0 || (a.dbg & 4)) break;   // warp-uniform: nothing left to store
+        float v[32];
+        tc_ld_32x32(taddr + c * 32, v);
+        const bool n_ok = n0 + c * 32 < a.n_out;
+        // issue every global load of this chunk before waiting on TMEM
+        float4 bb = zero4, mm[8], rr[8];
+        if (bias_p && n_ok) bb = __ldg(reinterpret_cast<const float4*>(bias_p + c * 32));
+        if (FULL) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const bool ok = n_ok && it * 4 < rows_left;
+            mm[it] = (mask_p && ok) ? __ldg(reinterpret_cast<const float4*>(mask_p + (int64_t)it * 4 * ep.ldmask + c * 32)) : one4;
+            rr[it] = (res_p && ok) ? __ldg(reinterpret_cast<const float4*>(res_p + (int64_t)it * 4 * ep.ldres + c * 32)) : zero4;
+          }
+        }
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * EPI_LD + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (n_ok && it * 4 < rows_left ) {
+            const float4 accv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * EPI_LD + ((((lane & 7) ^ ((it * 4 + rsub) & 7))) << 2));
+            const float4 o = FULL ? epi_mix4<true>(ep, accv, bb, mm[it], rr[it], alpha, gate[it] != 0.f, rscl[it])
+                                  : epi_mix4<false>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
+            *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
           }
         }
         __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar + 8 * acc, 0));   // on the leader's barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync();                                                    // nobody touches the peer's smem / TMEM after this
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -363,12 +429,14 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
   __nv_bfloat16* w_ws = reinterpret_cast<__nv_bfloat16*>(wsp + align256(2 * n_rows * K * 2));
 
   TypeSegs segs;
-  if (wsi_make_segs(&segs, type_ptr_host, T, BM) != 0) { wsi_set_error("typed_linear: bad type_ptr"); return WSI_ERR_ARG; }
+  if (wsi_make_segs(&segs, type_ptr_host, T, PAIR_M) != 0) { wsi_set_error("typed_linear: bad type_ptr"); return WSI_ERR_ARG; }
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(typed_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(typed_linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(typed_linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   WSI_CHECK_CUDA(attr_err);
   int sms = wsi_num_sms();
@@ -386,18 +454,21 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a_ws, 2 * n_rows, K, BM);
   if (rc != WSI_OK) return rc;
-  rc = make_map(&tmB, w_ws, 2 * (int64_t)T * n_out, K, BN);
+  rc = make_map(&tmB, w_ws, 2 * (int64_t)T * n_out, K, BN / 2);
   if (rc != WSI_OK) return rc;
   TcArgs a{};
   a.n_rows = (int)n_rows; a.w_rows = T * n_out; a.K = K; a.n_out = n_out;
   a.n_tiles_m = segs.tile_start[T]; a.n_tiles_n = (n_out + BN - 1) / BN;
-  a.vec_epi = (!ep.bias || (aligned16(ep.bias) && n_out % 4 == 0)) &&
-              (!ep.drop_mask || (aligned16(ep.drop_mask) && ep.ldmask % 4 == 0)) &&
-              (!ep.res || (aligned16(ep.res) && ep.ldres % 4 == 0));
+  WSI_CHECK_ARG((!ep.bias || aligned16(ep.bias)) && (!ep.drop_mask || (aligned16(ep.drop_mask) && ep.ldmask % 4 == 0)) &&
+                    (!ep.res || (aligned16(ep.res) && ep.ldres % 4 == 0)),
+                "typed_linear(tcgen05): bias / drop_mask / res must be 16 B aligned with row strides multiple of 4 floats");
+  const bool full = ep.skip || ep.drop_mask || ep.row_scale;
+  { const char* d = getenv("WSI_TC_DEBUG"); a.dbg = d ? atoi(d) : 0; }
   const int total = a.n_tiles_m * a.n_tiles_n;
   if (total == 0) return WSI_OK;
-  const int grid = total < sms ? total : sms;
-  typed_linear_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
+  const int pairs = total < sms / 2 ? total : sms / 2;               // one CTA pair (cluster of 2) per two SMs
+  if (full) typed_linear_tc_kernel<true><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
+  else typed_linear_tc_kernel<false><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }
