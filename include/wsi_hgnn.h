@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 3
+#define WSI_ABI_VERSION 4
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -92,6 +92,20 @@ int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv
                         const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
                         const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D,
                         int H, int head_perm, float* agg, int64_t ldo, float* attn_out, void* stream);
+
+/* Same computation driven by a WORK LIST that balances the heavy-tailed in-degree of k-NN graphs (hubs):
+ *   items int32 [n_items, 4] = (row, e_beg, e_end, slot).  slot < 0: [e_beg, e_end) is the whole row, written
+ *   to agg[row] (zero in-degree rows need an item too).  slot >= 0: a chunk of ONE (row, relation) segment whose
+ *   online-softmax partial goes to part_ms [n_part, 64] (per-lane max | sum) and part_acc [n_part, D].
+ *   The split rows are finished by a merge launch: split_row int32 [n_split], split_ptr int32 [n_split + 1]
+ *   (partial slots of each split row, in edge order), part_rel int32 [n_part] (relation slot of each partial).
+ * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work(). */
+int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
+                             const int32_t* e_src, const float* e_sim, const uint8_t* e_rel, const float* node_inv_r,
+                             const float* e_w, const float* e_b, int64_t n_rows, int D, int H, const int32_t* items,
+                             int64_t n_items, const int32_t* split_row, const int32_t* split_ptr,
+                             const int32_t* part_rel, int64_t n_split, int64_t n_part, float* part_ms,
+                             float* part_acc, float* agg, int64_t ldo, void* stream);
 
 /* Segment form used by HGT (WSI_SCORE_HGT): one work item per (dst,relation) segment.
  *   seg_ptr int32 [S+1] edge range of segment s (dst-major order), seg_rel int32 [S] MODEL relation id,

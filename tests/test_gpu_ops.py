@@ -153,6 +153,38 @@ def test_hetero_attn_fwd(D, H, perm):
     assert float(agg[inv_r == 0].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("D,H,chunk", [(512, 4, 16), (128, 4, 4), (256, 8, 1), (1024, 32, 16), (384, 2, 7), (512, 1, 64)])
+def test_hetero_attn_work_list(D, H, chunk):
+    """Hub-balanced work list (chunks of split rows + merge launch) == whole-row reference."""
+    from wsi_hgnn_b200.hetero_graph import GraphPlan
+    g = torch.Generator().manual_seed(D + H + chunk)
+    n_dst, n_rel = 301, 5
+    rowptr, src, dst, rel, sim = _random_csr(n_dst, n_dst, 1800, n_rel, g, hub=200)
+    k = torch.randn(n_dst, D, generator=g)
+    v = torch.randn(n_dst, D, generator=g)
+    q = torch.randn(n_dst, D, generator=g) * 0.5
+    inv_r = torch.full((n_dst,), 1.0 / n_rel)
+    inv_r[torch.rand(n_dst, generator=g) < 0.1] = 0.0
+    inv_r[0] = 1.0 / n_rel                                       # the hub row stays live
+    ew, eb = -0.7, 0.2
+    ref, _ = _heat_attn_ref(k, v, q, src, dst, rel, sim, inv_r, ew, eb, H, n_rel)
+    p = ops.head_perm(D, H)
+    kvq = torch.cat([k[:, p], v[:, p], q[:, p]], 1).cuda()
+    plan = GraphPlan()
+    plan.N, plan.E, plan.device = n_dst, int(src.numel()), torch.device("cuda")
+    plan.rowptr = rowptr.to(torch.int32).cuda()
+    plan.e_rel = rel.to(torch.uint8).cuda()
+    work = plan.attn_work(chunk)
+    assert work["n_split"] > 0 and work["n_part"] > work["n_split"]
+    agg = ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, src.to(torch.int32).cuda(),
+                               sim.float().cuda(), plan.e_rel, inv_r.cuda(), torch.tensor([[ew]]).cuda(),
+                               torch.tensor([eb]).cuda(), D, H).cpu()
+    un = torch.empty_like(agg)
+    un[:, p] = agg
+    assert rel_ok(un, ref, 2e-5)
+    assert float(un[inv_r == 0].abs().sum()) == 0.0
+
+
 def rel_ok(a, b, tol):
     e = rel(a, b)
     assert e < tol, f"rel err {e:.3e}"

@@ -86,7 +86,31 @@ def main():
                                  plan.e_rel, plan.node_inv_r, ew, eb, D, H, use_perm)
     ms = timeit(fn, args.reps, flush)
     nbytes = E * (2 * D * 4 + 8) + N * (2 * D * 4 + 4)
-    print(json.dumps({"kernel": "hetero_attn_fwd (cold L2)", "E": E, "ms": ms, "gbs": nbytes / ms / 1e6,
+    print(json.dumps({"kernel": "hetero_attn_fwd whole rows (cold L2)", "E": E, "ms": ms, "gbs": nbytes / ms / 1e6,
+                      "frac_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"]}), flush=True)
+    for chunk in (8, 16, 32):
+        work = plan.attn_work(chunk)
+        fn = lambda: ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, plan.e_src, plan.e_sim,
+                                          plan.e_rel, plan.node_inv_r, ew, eb, D, H)
+        ms = timeit(fn, args.reps, flush)
+        print(json.dumps({"kernel": f"hetero_attn_work_fwd chunk={chunk} (cold L2)", "n_items": work["n_items"],
+                          "n_part": work["n_part"], "ms": ms, "gbs": nbytes / ms / 1e6,
+                          "frac_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"]}), flush=True)
+
+        def warm():
+            kvq.add_(0.0)
+        # K/V/Q left in L2 by the producing GEMM (the in-model situation)
+        for _ in range(3):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.reps)]
+        for a_, b_ in ev:
+            flush.zero_(); warm(); a_.record(); fn(); b_.record()
+        torch.cuda.synchronize()
+        msw = sorted(a_.elapsed_time(b_) for a_, b_ in ev)[len(ev) // 2]
+        print(json.dumps({"kernel": f"hetero_attn_work_fwd chunk={chunk} (K|V|Q warm in L2)", "ms": msw,
+                          "gbs": nbytes / msw / 1e6, "frac_hbm_peak": nbytes / msw / 1e6 / peaks["hbm_gbs"]}), flush=True)
+    ms = timeit(fn, args.reps, flush)
+    print(json.dumps({"kernel": "hetero_attn_work_fwd last (cold L2)", "E": E, "ms": ms, "gbs": nbytes / ms / 1e6,
                       "frac_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"]}), flush=True)
 
 

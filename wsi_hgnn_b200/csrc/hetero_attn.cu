@@ -4,10 +4,15 @@
 // update_all(u_mul_e, sum) and the cross-relation mean of multi_update_all
 // (models/HEATNet4.py:103-119 == models/HEATNet2.py:78-94; models/HGT.py:95-106).
 //
-// Work item = one dst row of the relation-grouped CSR (HEAT) or one (dst, relation) segment (HGT).
+// Work item = an edge range inside one dst row of the relation-grouped CSR (HEAT) or inside one (dst, relation)
+// segment (HGT).  Without a work list every row / segment is one item; with one (wsi_hetero_attn_work_fwd) rows with
+// many in-edges (k-NN hubs: in-degree is heavy tailed although out-degree is fixed) are cut into chunks of one
+// segment each, whose online-softmax partials (max, sum, unnormalised accumulator) are combined by attn_merge_kernel,
+// so that no warp walks a 100+ edge row alone while the other SMs idle.
 // One warp per work item: the 32 lanes span the D feature columns, the source rows K[src], V[src] are
-// gathered with coalesced 16-byte loads (512 B per warp instruction), the per-(segment, head) softmax is
-// computed online (running max / running sum, rescaled accumulator) so every gathered byte is touched once.
+// gathered with coalesced 16-byte loads (512 B per warp instruction), GROUP edges at a time (all K rows of the group in
+// flight, then all V rows), the per-(segment, head) softmax is computed online (running max / running sum, rescaled
+// accumulator) so every gathered byte is touched once.
 //
 // HBM-bound: algorithmic bytes per edge = 2*D*4 (K and V rows) + 9 (src id, sim, relation slot);
 // per dst row = 2*D*4 (q in, agg out) + 8 (rowptr, 1/R).
@@ -15,7 +20,7 @@
 
 namespace {
 
-constexpr int WARPS = 8;
+constexpr int WARPS = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
 enum { MODE_HEAT = 0, MODE_HGT_SEG = 1 };
@@ -37,6 +42,9 @@ struct AttnArgs {
   float inv_sqrt_dk;
   float* out; int64_t ldo;
   float* attn;                // optional [E, H] normalised attention (for backward)
+  const int4* items;          // optional work list [n_items]: (row, e_beg, e_end, slot); slot < 0: the whole row
+  float* part_ms;             // [P, 2, 32] per-lane (max, sum) of partial slot p
+  float* part_acc;            // [P, D] unnormalised accumulator of partial slot p (physical column order)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -44,8 +52,10 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret
 // ------------------------------------------------------------------------------------------------
 // Lane-grouped fast path: D = 128*NV, H | 32.  Lane l owns float4 slots {i*32 + l}, all of head l / G
 // (G = 32/H lanes per head) thanks to the head_perm column order (wsi_head_perm).
+// GROUP = edges whose K (then V) rows are in flight together (bounded by the register file: GROUP * NV float4)
 template <int NV, int MODE>
-__global__ void __launch_bounds__(WARPS * 32) attn_fwd_vec_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 2) attn_fwd_vec_kernel(AttnArgs a) {
+  constexpr int GROUP = NV <= 2 ? 8 : (NV <= 4 ? 4 : 2);
   const int lane = threadIdx.x & 31;
   const int G = 32 / a.H;
   const int head = lane / G;
@@ -54,23 +64,30 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_vec_kernel(AttnArgs a) {
   if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
 
   for (int item = blockIdx.x * WARPS + (threadIdx.x >> 5); item < a.n_items; item += n_warps) {
+    int row = item, beg, end, slot = -1;
+    if (a.items) {
+      const int4 it = __ldg(a.items + item);
+      row = it.x; beg = it.y; end = it.z; slot = it.w;
+    } else {
+      beg = __ldg(a.rowptr + item); end = __ldg(a.rowptr + item + 1);
+    }
     float4 out[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int beg = __ldg(a.rowptr + item), end = __ldg(a.rowptr + item + 1);
     float invr = 1.f, seg_scale = 0.f;
-    if (MODE == MODE_HEAT) invr = __ldg(a.inv_r + item);
-    else seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + item) * a.H + head) * a.inv_sqrt_dk;
+    if (MODE == MODE_HEAT) invr = __ldg(a.inv_r + row);
+    else seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + row) * a.H + head) * a.inv_sqrt_dk;
+
+    float m = -INFINITY, ssum = 0.f;
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     if (invr != 0.f && end > beg) {
       float4 q[NV];
-      const float* qr = a.Q + (int64_t)item * a.ldq;
+      const float* qr = a.Q + (int64_t)row * a.ldq;
 #pragma unroll
       for (int i = 0; i < NV; ++i) q[i] = ld4(qr + (i * 32 + lane) * 4);
-      float m = -INFINITY, ssum = 0.f;
-      float4 acc[NV];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       int cur_rel = -1, seg_beg = beg;
 
       for (int base = beg; base < end; base += 32) {
@@ -81,12 +98,14 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_vec_kernel(AttnArgs a) {
           my_src = __ldg(a.e_src + base + lane);
           if (MODE == MODE_HEAT) { my_sim = __ldg(a.e_sim + base + lane); my_rel = __ldg(a.e_rel + base + lane); }
         }
-        for (int j = 0; j < n; ++j) {
-          const int src = __shfl_sync(FULL, my_src, j);
-          float scale = seg_scale;
+        int j = 0;
+        while (j < n) {
+          int g = min(GROUP, n - j);
           if (MODE == MODE_HEAT) {
             const int rel = __shfl_sync(FULL, my_rel, j);
-            const float sim = __shfl_sync(FULL, my_sim, j);
+            // edges j.. of the same relation (segments are contiguous): run length, capped at GROUP
+            const unsigned same = __ballot_sync(FULL, lane >= j && lane < n && my_rel == rel) >> j;
+            g = min(g, same == FULL ? 32 : __ffs(~same) - 1);   // (__ffs(0) == 0)
             if (rel != cur_rel) {                       // warp-uniform: close the running segment
               if (cur_rel >= 0) {
                 const float inv = 1.f / ssum;
@@ -104,37 +123,73 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_vec_kernel(AttnArgs a) {
               }
               m = -INFINITY; ssum = 0.f; cur_rel = rel; seg_beg = base + j;
             }
-            scale = fmaf(ew, sim, eb) * a.inv_sqrt_dk;
           }
-          const float* kr = a.K + (int64_t)src * a.ldk;
-          const float* vr = a.V + (int64_t)src * a.ldv;
-          float4 kk[NV], vv[NV];
+          // ---- K rows of the group, scores
+          float4 buf[GROUP][NV];
+          float sc[GROUP];
 #pragma unroll
-          for (int i = 0; i < NV; ++i) kk[i] = ld4(kr + (i * 32 + lane) * 4);
+          for (int u = 0; u < GROUP; ++u) {
+            if (u < g) {
+              const int src = __shfl_sync(FULL, my_src, j + u);
+              const float* kr = a.K + (int64_t)src * a.ldk;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) vv[i] = ld4(vr + (i * 32 + lane) * 4);
-          float d = 0.f;
+              for (int i = 0; i < NV; ++i) buf[u][i] = ld4(kr + (i * 32 + lane) * 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < GROUP; ++u) {
+            sc[u] = -INFINITY;
+            if (u < g) {
+              float d = 0.f;
+#pragma unroll
+              for (int i = 0; i < NV; ++i) {
+                d = fmaf(q[i].x, buf[u][i].x, d); d = fmaf(q[i].y, buf[u][i].y, d);
+                d = fmaf(q[i].z, buf[u][i].z, d); d = fmaf(q[i].w, buf[u][i].w, d);
+              }
+              for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+              float scale = seg_scale;
+              if (MODE == MODE_HEAT) scale = fmaf(ew, __shfl_sync(FULL, my_sim, j + u), eb) * a.inv_sqrt_dk;
+              sc[u] = d * scale;
+              if (a.attn && lane % G == 0) a.attn[(int64_t)(base + j + u) * a.H + head] = sc[u];
+            }
+          }
+          // ---- V rows of the group (issued before the exponentials)
+#pragma unroll
+          for (int u = 0; u < GROUP; ++u) {
+            if (u < g) {
+              const int src = __shfl_sync(FULL, my_src, j + u);
+              const float* vr = a.V + (int64_t)src * a.ldv;
+#pragma unroll
+              for (int i = 0; i < NV; ++i) buf[u][i] = ld4(vr + (i * 32 + lane) * 4);
+            }
+          }
+          float mn = m;
+#pragma unroll
+          for (int u = 0; u < GROUP; ++u) mn = fmaxf(mn, sc[u]);
+          const float corr = __expf(m - mn);            // m = -inf on the first group -> 0
+          float p[GROUP], psum = 0.f;
+#pragma unroll
+          for (int u = 0; u < GROUP; ++u) { p[u] = __expf(sc[u] - mn); psum += p[u]; }   // exp(-inf) = 0 for u >= g
+          ssum = fmaf(ssum, corr, psum);
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            d = fmaf(q[i].x, kk[i].x, d); d = fmaf(q[i].y, kk[i].y, d);
-            d = fmaf(q[i].z, kk[i].z, d); d = fmaf(q[i].w, kk[i].w, d);
+            acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr;
           }
-          for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
-          const float s = d * scale;
-          if (a.attn && lane % G == 0) a.attn[(int64_t)(base + j) * a.H + head] = s;
-          const float mn = fmaxf(m, s);
-          const float corr = __expf(m - mn);            // m = -inf on the first edge -> 0
-          const float p = __expf(s - mn);
-          ssum = fmaf(ssum, corr, p);
 #pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            acc[i].x = fmaf(acc[i].x, corr, p * vv[i].x); acc[i].y = fmaf(acc[i].y, corr, p * vv[i].y);
-            acc[i].z = fmaf(acc[i].z, corr, p * vv[i].z); acc[i].w = fmaf(acc[i].w, corr, p * vv[i].w);
+          for (int u = 0; u < GROUP; ++u) {
+            if (u < g) {
+#pragma unroll
+              for (int i = 0; i < NV; ++i) {
+                acc[i].x = fmaf(p[u], buf[u][i].x, acc[i].x); acc[i].y = fmaf(p[u], buf[u][i].y, acc[i].y);
+                acc[i].z = fmaf(p[u], buf[u][i].z, acc[i].z); acc[i].w = fmaf(p[u], buf[u][i].w, acc[i].w);
+              }
+            }
           }
           m = mn;
+          j += g;
         }
       }
-      {                                                 // close the last segment
+      if (slot < 0) {                                   // close the last segment
         const float inv = 1.f / ssum;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -148,10 +203,86 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_vec_kernel(AttnArgs a) {
           }
       }
     }
-    float* o = a.out + (int64_t)item * a.ldo;
+    if (slot < 0) {
+      float* o = a.out + (int64_t)row * a.ldo;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
+      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
+    } else {                                            // partial of one segment chunk: (m, sum, unnormalised acc)
+      a.part_ms[(int64_t)slot * 64 + lane] = m;
+      a.part_ms[(int64_t)slot * 64 + 32 + lane] = ssum;
+      float* o = a.part_acc + (int64_t)slot * a.D;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = acc[i];
+    }
   }
+}
+
+// Combine the chunk partials of the split rows (HEAT) / split segments (HGT): one warp per split row.
+//   split_row[h] = output row, split_ptr[h..h+1] = its partial slots (in edge order), part_rel[p] = relation slot
+//   of partial p (a new value closes the running segment).  out[row] = inv_r[row] * sum_segments acc / sum.
+struct MergeArgs {
+  const int* split_row; const int* split_ptr; const int* part_rel;
+  const float* part_ms; const float* part_acc; const float* inv_r;
+  int n_split, D;
+  float* out; int64_t ldo;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32) attn_merge_kernel(MergeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (h >= a.n_split) return;
+  const int row = __ldg(a.split_row + h);
+  const int pb = __ldg(a.split_ptr + h), pe = __ldg(a.split_ptr + h + 1);
+  const float invr = a.inv_r ? __ldg(a.inv_r + row) : 1.f;
+  float4 out[NV], acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc[i] = out[i]; }
+  float m = -INFINITY, ssum = 0.f;
+  int cur_rel = -1;
+  for (int p = pb; p < pe; ++p) {
+    const int rel = __ldg(a.part_rel + p);
+    if (rel != cur_rel) {
+      if (cur_rel >= 0 && ssum > 0.f) {
+        const float inv = 1.f / ssum;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
+          out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      m = -INFINITY; ssum = 0.f; cur_rel = rel;
+    }
+    const float mp = __ldg(a.part_ms + (int64_t)p * 64 + lane), sp = __ldg(a.part_ms + (int64_t)p * 64 + 32 + lane);
+    if (sp > 0.f) {                                     // (an untouched partial has sum 0: passthrough row)
+      const float mn = fmaxf(m, mp);
+      const float c0 = __expf(m - mn), c1 = __expf(mp - mn);
+      ssum = fmaf(ssum, c0, sp * c1);
+      const float* pa = a.part_acc + (int64_t)p * a.D;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 x = ld4(pa + (i * 32 + lane) * 4);
+        acc[i].x = fmaf(acc[i].x, c0, x.x * c1); acc[i].y = fmaf(acc[i].y, c0, x.y * c1);
+        acc[i].z = fmaf(acc[i].z, c0, x.z * c1); acc[i].w = fmaf(acc[i].w, c0, x.w * c1);
+      }
+      m = mn;
+    }
+  }
+  if (cur_rel >= 0 && ssum > 0.f) {
+    const float inv = 1.f / ssum;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
+      out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
+    }
+  }
+  float* o = a.out + (int64_t)row * a.ldo;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) =
+        make_float4(out[i].x * invr, out[i].y * invr, out[i].z * invr, out[i].w * invr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -285,6 +416,18 @@ int launch(const AttnArgs& a, int head_perm, cudaStream_t stream) {
   return WSI_OK;
 }
 
+int launch_merge(const MergeArgs& m, cudaStream_t stream) {
+  if (m.n_split == 0) return WSI_OK;
+  const int blocks = (m.n_split + WARPS - 1) / WARPS;
+  switch (m.D / 128) {
+#define CASE(NV) case NV: attn_merge_kernel<NV><<<blocks, WARPS * 32, 0, stream>>>(m); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}
+
 }  // namespace
 
 extern "C" int wsi_head_perm(int D, int H, int32_t* perm_host) {
@@ -322,6 +465,37 @@ extern "C" int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, 
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.out = agg; a.ldo = ldo; a.attn = attn_out;
   return launch<MODE_HEAT>(a, head_perm, wsi_stream(stream));
+}
+
+extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q,
+                                        int64_t ldq, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
+                                        const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows,
+                                        int D, int H, const int32_t* items, int64_t n_items,
+                                        const int32_t* split_row, const int32_t* split_ptr, const int32_t* part_rel,
+                                        int64_t n_split, int64_t n_part, float* part_ms, float* part_acc, float* agg,
+                                        int64_t ldo, void* stream) {
+  WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && n_items >= 0 && n_items < (1ll << 31), "hetero_attn_work_fwd: bad sizes");
+  if (n_rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(k && v && q && node_inv_r && e_w && e_b && agg && items, "hetero_attn_work_fwd: null pointer");
+  WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0 && vec_ok(D, H),
+                "hetero_attn_work_fwd: needs the lane-grouped layout (D %% 128 == 0, D <= 1024, H a power of two <= 32), got D=%d H=%d", D, H);
+  WSI_CHECK_ARG(ldk % 4 == 0 && ldv % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0,
+                "hetero_attn_work_fwd: row strides must be multiples of 4 floats");
+  WSI_CHECK_ARG(n_split == 0 || (split_row && split_ptr && part_rel && part_ms && part_acc && n_part > 0),
+                "hetero_attn_work_fwd: split rows need the partial buffers");
+  AttnArgs a{};
+  a.K = k; a.ldk = ldk; a.V = v; a.ldv = ldv; a.Q = q; a.ldq = ldq;
+  a.e_src = e_src; a.e_sim = e_sim; a.e_rel = e_rel; a.inv_r = node_inv_r;
+  a.e_w = e_w; a.e_b = e_b; a.n_items = (int)n_items; a.D = D; a.H = H; a.dk = D / H;
+  a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
+  a.out = agg; a.ldo = ldo; a.attn = nullptr;
+  a.items = reinterpret_cast<const int4*>(items); a.part_ms = part_ms; a.part_acc = part_acc;
+  int rc = launch<MODE_HEAT>(a, 1, wsi_stream(stream));
+  if (rc != WSI_OK) return rc;
+  MergeArgs m{};
+  m.split_row = split_row; m.split_ptr = split_ptr; m.part_rel = part_rel; m.part_ms = part_ms; m.part_acc = part_acc;
+  m.inv_r = node_inv_r; m.n_split = (int)n_split; m.D = D; m.out = agg; m.ldo = ldo;
+  return launch_merge(m, wsi_stream(stream));
 }
 
 extern "C" int wsi_hetero_attn_seg_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qseg,

@@ -226,6 +226,54 @@ class GraphPlan:
                               seg_slot=rel[starts].contiguous(), row_seg_ptr=row_seg_ptr)
         return self._segs
 
+    def attn_work(self, chunk: int = 16):
+        """Work list of the edge-attention kernel (wsi_hetero_attn_work_fwd): rows with at most `chunk`
+        in-edges are one item; rows with more (k-NN hubs) are cut, per (row, relation) segment, into chunks
+        of <= `chunk` edges whose partials a merge launch combines.  The chunk items come first (they are the
+        largest).  dict: items int32 [n_items, 4], n_items, split_row, split_ptr, part_rel, n_split, n_part."""
+        key = ("attn_work", chunk)
+        if key in self.cache:
+            return self.cache[key]
+        dev = self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        rowptr = self.rowptr.to(torch.int64)
+        deg = rowptr[1:] - rowptr[:-1]
+        split = deg > chunk
+        rows_c = torch.nonzero(~split).reshape(-1)
+        items_c = torch.stack([rows_c, rowptr[rows_c], rowptr[rows_c + 1], torch.full_like(rows_c, -1)], 1)
+        n_split = int(split.sum()) if self.N > 0 else 0
+        if n_split == 0:
+            work = dict(items=items_c.to(torch.int32).contiguous(), n_items=int(items_c.shape[0]),
+                        split_row=torch.zeros(1, **i32), split_ptr=torch.zeros(2, **i32),
+                        part_rel=torch.zeros(1, **i32), n_split=0, n_part=0)
+            self.cache[key] = work
+            return work
+        segs = self.segments()
+        seg_ptr = segs["seg_ptr"].to(torch.int64)
+        seg_dst = segs["seg_dst"].to(torch.int64)
+        sel = torch.nonzero(split[seg_dst]).reshape(-1)              # segments of the split rows, in edge order
+        s_beg, s_end, s_dst = seg_ptr[sel], seg_ptr[sel + 1], seg_dst[sel]
+        n_ch = (s_end - s_beg + chunk - 1) // chunk
+        seg_of = torch.repeat_interleave(torch.arange(sel.numel(), device=dev), n_ch)
+        first = torch.cumsum(n_ch, 0) - n_ch
+        c_idx = torch.arange(seg_of.numel(), device=dev) - first[seg_of]
+        p_beg = s_beg[seg_of] + c_idx * chunk
+        p_end = torch.minimum(p_beg + chunk, s_end[seg_of])
+        n_part = int(seg_of.numel())
+        slots = torch.arange(n_part, device=dev)
+        items_p = torch.stack([s_dst[seg_of], p_beg, p_end, slots], 1)
+        part_rel = segs["seg_slot"][sel][seg_of].to(torch.int32).contiguous()
+        split_row = torch.nonzero(split).reshape(-1)
+        per_row = torch.zeros(self.N, dtype=torch.int64, device=dev).index_add_(0, s_dst, n_ch)
+        split_ptr = torch.zeros(n_split + 1, dtype=torch.int64, device=dev)
+        split_ptr[1:] = torch.cumsum(per_row[split_row], 0)
+        items = torch.cat([items_p, items_c], 0).to(torch.int32).contiguous()
+        work = dict(items=items, n_items=int(items.shape[0]), split_row=split_row.to(torch.int32).contiguous(),
+                    split_ptr=split_ptr.to(torch.int32).contiguous(), part_rel=part_rel, n_split=n_split,
+                    n_part=n_part)
+        self.cache[key] = work
+        return work
+
     def transposed(self):
         """(t_rowptr, t_eid, e_dst) for the backward scatter to src rows."""
         if self._t is None:

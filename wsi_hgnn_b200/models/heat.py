@@ -111,8 +111,13 @@ class HEATLayer(nn.Module):
         w_kvq, b_kvq, wa, ba, skip, use_perm = self._packed(order)
         tpc = plan.type_ptr_c()
         kvq = ops.typed_linear(x, w_kvq, b_kvq, plan.type_ptr, type_ptr_c=tpc)
-        agg = ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
-                              plan.e_rel, plan.node_inv_r, self.e_linear.weight, self.e_linear.bias, D, H, use_perm)
+        if use_perm:                      # lane-grouped layout: hub-balanced work list
+            agg = ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.attn_work(), plan.e_src,
+                                       plan.e_sim, plan.e_rel, plan.node_inv_r, self.e_linear.weight,
+                                       self.e_linear.bias, D, H)
+        else:
+            agg = ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
+                                  plan.e_rel, plan.node_inv_r, self.e_linear.weight, self.e_linear.bias, D, H, False)
         mask = None
         if self.training and self.drop.p > 0:
             mask = F.dropout(torch.ones_like(agg), self.drop.p, True)

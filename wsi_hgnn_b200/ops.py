@@ -125,6 +125,37 @@ def hetero_attn(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, rowptr: torch
     return (agg, attn) if want_attn else agg
 
 
+def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: dict, e_src: torch.Tensor,
+                     e_sim: torch.Tensor, e_rel: torch.Tensor, node_inv_r: torch.Tensor, e_w: torch.Tensor,
+                     e_b: torch.Tensor, D: int, H: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """HEAT edge attention driven by the hub-balancing work list of GraphPlan.attn_work();
+    see wsi_hetero_attn_work_fwd.  k/v/q/agg columns are in the head_perm(D, H) order."""
+    lib = _lib.load()
+    stream = _prep(q)
+    N = int(q.shape[0])
+    kp, ldk = _rows(k, "k")
+    vp, ldv = _rows(v, "v")
+    qp, ldq = _rows(q, "q")
+    agg = out if out is not None else torch.empty((N, D), dtype=torch.float32, device=q.device)
+    ap, ldo = _rows(agg, "agg")
+    n_part, n_split = work["n_part"], work["n_split"]
+    part_ms = part_acc = None
+    if n_part > 0:
+        part_ms = torch.empty((n_part, 64), dtype=torch.float32, device=q.device)
+        part_acc = torch.empty((n_part, D), dtype=torch.float32, device=q.device)
+    rc = lib.wsi_hetero_attn_work_fwd(kp, ldk, vp, ldv, qp, ldq, _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
+                                      _vec(e_rel, "e_rel", torch.uint8), _vec(node_inv_r, "node_inv_r"),
+                                      _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, D, H,
+                                      _vec(work["items"], "items", torch.int32), work["n_items"],
+                                      _vec(work["split_row"], "split_row", torch.int32),
+                                      _vec(work["split_ptr"], "split_ptr", torch.int32),
+                                      _vec(work["part_rel"], "part_rel", torch.int32), n_split, n_part,
+                                      part_ms.data_ptr() if part_ms is not None else None,
+                                      part_acc.data_ptr() if part_acc is not None else None, ap, ldo, stream)
+    _lib.check(rc, "wsi_hetero_attn_work_fwd")
+    return agg
+
+
 def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int, use_head_perm: bool = False):
     """HGT edge attention over (dst, relation) segments; see wsi_hetero_attn_seg_fwd."""
     lib = _lib.load()
