@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 4
+#define WSI_ABI_VERSION 5
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -73,6 +73,20 @@ int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w, const floa
                          const float* row_scale, float* y, int64_t ldy, int impl, void* workspace,
                          int64_t workspace_bytes, void* stream);
 
+/* Pre-split operands for chains of tensor-core GEMMs (no per-call conversion pass):
+ * wsi_split_bf16: fp32 [rows, K] (row stride ld_src) -> dst bf16 [2 * rows, K]: rows [0, rows) = hi = bf16(x),
+ *   rows [rows, 2 rows) = lo = bf16(x - hi).  K % 8 == 0.  Weights [T, n_out, K] are split as rows = T * n_out.
+ * wsi_typed_linear_split: the typed linear of wsi_typed_linear_f32 on the tcgen05 path with x and w given in that
+ *   split form (x_split [2N, K], w_split [2 T n_out, K], both 128 B aligned); y_split != NULL additionally emits
+ *   the epilogue result in split form [2N, n_out] (n_out % 8 == 0) for the next GEMM; y may be NULL then.
+ *   Returns WSI_ERR_UNSUPPORTED when wsi_typed_linear_tc_ok(N, K, n_out) == 0. */
+int wsi_typed_linear_tc_ok(int64_t n_rows, int K, int n_out);
+int wsi_split_bf16(const float* src, int64_t ld_src, int64_t rows, int K, void* dst, void* stream);
+int wsi_typed_linear_split(const void* x_split, const void* w_split, const float* bias, int K, int n_out,
+                           const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
+                           int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,
+                           const float* row_scale, float* y, int64_t ldy, void* y_split, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Heterogeneous edge attention forward, ONE launch for all relations of a layer        (kernel K2)
  * replaces, per relation, apply_edges(v_dot_u) + score + edge_softmax + u_mul_e/sum and the
@@ -99,13 +113,15 @@ int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   online-softmax partial goes to part_ms [n_part, 64] (per-lane max | sum) and part_acc [n_part, D].
  *   The split rows are finished by a merge launch: split_row int32 [n_split], split_ptr int32 [n_split + 1]
  *   (partial slots of each split row, in edge order), part_rel int32 [n_part] (relation slot of each partial).
- * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work(). */
+ * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work().
+ *   agg_split != NULL: the result is (also) written as bf16 [2 * n_rows, D] (hi rows, then lo rows: x = hi + lo),
+ *   the A operand layout of wsi_typed_linear_split; agg may then be NULL. */
 int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
                              const int32_t* e_src, const float* e_sim, const uint8_t* e_rel, const float* node_inv_r,
                              const float* e_w, const float* e_b, int64_t n_rows, int D, int H, const int32_t* items,
                              int64_t n_items, const int32_t* split_row, const int32_t* split_ptr,
                              const int32_t* part_rel, int64_t n_split, int64_t n_part, float* part_ms,
-                             float* part_acc, float* agg, int64_t ldo, void* stream);
+                             float* part_acc, float* agg, int64_t ldo, void* agg_split, void* stream);
 
 /* Segment form used by HGT (WSI_SCORE_HGT): one work item per (dst,relation) segment.
  *   seg_ptr int32 [S+1] edge range of segment s (dst-major order), seg_rel int32 [S] MODEL relation id,

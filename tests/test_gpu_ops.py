@@ -75,6 +75,43 @@ def test_typed_linear_epilogues(counts, K, n_out, impl):
     assert float(big[:, :8].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("counts,K,n_out", [([600, 0, 700], 512, 512), ([513], 64, 136), ([300, 300, 424], 1024, 256)])
+def test_typed_linear_split_chain(counts, K, n_out):
+    """Pre-split bf16 [hi; lo] operands in, fp32 + split result out (the operand of the next GEMM)."""
+    g = torch.Generator().manual_seed(K + n_out)
+    T = len(counts)
+    ptr = [0]
+    for c in counts:
+        ptr.append(ptr[-1] + c)
+    N = ptr[-1]
+    x = torch.randn(N, K, generator=g)
+    w = torch.randn(T, n_out, K, generator=g) / math.sqrt(K)
+    b = torch.randn(T, n_out, generator=g)
+    skip = torch.randn(T, generator=g)
+    res = torch.randn(N, n_out, generator=g)
+    gate = (torch.rand(N, generator=g) > 0.25).float()
+    xs = ops.split_bf16(x.cuda())
+    assert xs.shape == (2 * N, K) and xs.dtype == torch.bfloat16
+    back = xs[:N].float() + xs[N:].float()
+    assert float((back.cpu() - x).abs().max() / x.abs().max()) < 2 ** -15
+    ws = ops.split_bf16(w.cuda())
+    ref = torch.empty(N, n_out, dtype=torch.float64)
+    for t in range(T):
+        a, z = ptr[t], ptr[t + 1]
+        v = x[a:z].double() @ w[t].double().T + b[t].double()
+        al = torch.sigmoid(skip[t].double())
+        ref[a:z] = torch.where(gate[a:z, None] != 0, v * al + res[a:z].double() * (1 - al), res[a:z].double())
+    y, ys = ops.typed_linear_split(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(), row_gate=gate.cuda(),
+                                   want_split=True)
+    assert rel(y, ref) < 2e-5
+    assert rel(ys[:N].float() + ys[N:].float(), ref) < 2e-5
+    y2, none = ops.typed_linear_split(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(), row_gate=gate.cuda())
+    assert none is None and torch.equal(y2, y)
+    only, ys2 = ops.typed_linear_split(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(),
+                                       row_gate=gate.cuda(), want_y=False, want_split=True)
+    assert only is None and torch.equal(ys2, ys)
+
+
 def test_typed_linear_tc_refuses_unfit_shapes():
     """impl=2 (force tcgen05) must fail loudly - never silently take another path."""
     x = torch.randn(8, 7, device="cuda")
@@ -183,6 +220,13 @@ def test_hetero_attn_work_list(D, H, chunk):
     un[:, p] = agg
     assert rel_ok(un, ref, 2e-5)
     assert float(un[inv_r == 0].abs().sum()) == 0.0
+    # split-form output: bf16 [hi; lo] of the same result
+    sp = ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, src.to(torch.int32).cuda(),
+                              sim.float().cuda(), plan.e_rel, inv_r.cuda(), torch.tensor([[ew]]).cuda(),
+                              torch.tensor([eb]).cuda(), D, H, split_out=True)
+    assert sp.dtype == torch.bfloat16 and sp.shape == (2 * n_dst, D)
+    back = (sp[:n_dst].float() + sp[n_dst:].float()).cpu()
+    assert float((back - agg).abs().max()) <= 2 ** -15 * float(agg.abs().max())
 
 
 def rel_ok(a, b, tol):

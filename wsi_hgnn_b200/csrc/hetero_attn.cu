@@ -45,7 +45,18 @@ struct AttnArgs {
   const int4* items;          // optional work list [n_items]: (row, e_beg, e_end, slot); slot < 0: the whole row
   float* part_ms;             // [P, 2, 32] per-lane (max, sum) of partial slot p
   float* part_acc;            // [P, D] unnormalised accumulator of partial slot p (physical column order)
+  __nv_bfloat16* out_split;   // optional [2 * n_rows, D] bf16 (hi; lo) form of `out`: A operand of the a_linear GEMM
+  int64_t split_lo;           // element offset of the lo half (n_rows * D)
 };
+
+__device__ __forceinline__ void st_split4(__nv_bfloat16* dst, int64_t lo_off, float4 v) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  wsi_split_bf16(v.x, h0, l0); wsi_split_bf16(v.y, h1, l1); wsi_split_bf16(v.z, h2, l2); wsi_split_bf16(v.w, h3, l3);
+  __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
+  __nv_bfloat162 lv[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
+  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hv);
+  *reinterpret_cast<uint2*>(dst + lo_off) = *reinterpret_cast<uint2*>(lv);
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -204,9 +215,16 @@ __global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 2) attn_fwd_vec_kern
       }
     }
     if (slot < 0) {
-      float* o = a.out + (int64_t)row * a.ldo;
+      if (a.out) {
+        float* o = a.out + (int64_t)row * a.ldo;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
+        for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
+      }
+      if (a.out_split) {
+        __nv_bfloat16* o = a.out_split + (int64_t)row * a.D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) st_split4(o + (i * 32 + lane) * 4, a.split_lo, out[i]);
+      }
     } else {                                            // partial of one segment chunk: (m, sum, unnormalised acc)
       a.part_ms[(int64_t)slot * 64 + lane] = m;
       a.part_ms[(int64_t)slot * 64 + 32 + lane] = ssum;
@@ -225,6 +243,7 @@ struct MergeArgs {
   const float* part_ms; const float* part_acc; const float* inv_r;
   int n_split, D;
   float* out; int64_t ldo;
+  __nv_bfloat16* out_split; int64_t split_lo;
 };
 
 template <int NV>
@@ -278,11 +297,12 @@ __global__ void __launch_bounds__(WARPS * 32) attn_merge_kernel(MergeArgs a) {
       out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
     }
   }
-  float* o = a.out + (int64_t)row * a.ldo;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-    *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) =
-        make_float4(out[i].x * invr, out[i].y * invr, out[i].z * invr, out[i].w * invr);
+  for (int i = 0; i < NV; ++i) {
+    const float4 r = make_float4(out[i].x * invr, out[i].y * invr, out[i].z * invr, out[i].w * invr);
+    if (a.out) *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + (i * 32 + lane) * 4) = r;
+    if (a.out_split) st_split4(a.out_split + (int64_t)row * a.D + (i * 32 + lane) * 4, a.split_lo, r);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -473,10 +493,11 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
                                         int D, int H, const int32_t* items, int64_t n_items,
                                         const int32_t* split_row, const int32_t* split_ptr, const int32_t* part_rel,
                                         int64_t n_split, int64_t n_part, float* part_ms, float* part_acc, float* agg,
-                                        int64_t ldo, void* stream) {
+                                        int64_t ldo, void* agg_split, void* stream) {
   WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && n_items >= 0 && n_items < (1ll << 31), "hetero_attn_work_fwd: bad sizes");
   if (n_rows == 0) return WSI_OK;
-  WSI_CHECK_ARG(k && v && q && node_inv_r && e_w && e_b && agg && items, "hetero_attn_work_fwd: null pointer");
+  WSI_CHECK_ARG(k && v && q && node_inv_r && e_w && e_b && (agg || agg_split) && items, "hetero_attn_work_fwd: null pointer");
+  WSI_CHECK_ARG((reinterpret_cast<uintptr_t>(agg_split) & 7) == 0, "hetero_attn_work_fwd: agg_split must be 8 B aligned");
   WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0 && vec_ok(D, H),
                 "hetero_attn_work_fwd: needs the lane-grouped layout (D %% 128 == 0, D <= 1024, H a power of two <= 32), got D=%d H=%d", D, H);
   WSI_CHECK_ARG(ldk % 4 == 0 && ldv % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0,
@@ -490,11 +511,13 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.out = agg; a.ldo = ldo; a.attn = nullptr;
   a.items = reinterpret_cast<const int4*>(items); a.part_ms = part_ms; a.part_acc = part_acc;
+  a.out_split = reinterpret_cast<__nv_bfloat16*>(agg_split); a.split_lo = n_rows * D;
   int rc = launch<MODE_HEAT>(a, 1, wsi_stream(stream));
   if (rc != WSI_OK) return rc;
   MergeArgs m{};
   m.split_row = split_row; m.split_ptr = split_ptr; m.part_rel = part_rel; m.part_ms = part_ms; m.part_acc = part_acc;
   m.inv_r = node_inv_r; m.n_split = (int)n_split; m.D = D; m.out = agg; m.ldo = ldo;
+  m.out_split = a.out_split; m.split_lo = a.split_lo;
   return launch_merge(m, wsi_stream(stream));
 }
 

@@ -11,6 +11,46 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
                                int T, const LinearEpilogue& ep, void* workspace, int64_t workspace_bytes,
                                cudaStream_t stream);
 
+int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const int32_t* type_ptr_host, int T,
+                             const LinearEpilogue& ep, void* y_split, cudaStream_t stream);
+int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_dst, const float* b_src, int64_t b_ld,
+                     int64_t b_rows, void* b_dst, int K, cudaStream_t stream);
+
+extern "C" int wsi_typed_linear_tc_ok(int64_t n_rows, int K, int n_out) {
+  return wsi_typed_linear_tc_supported(n_rows, K, n_out, K) ? 1 : 0;
+}
+
+extern "C" int wsi_split_bf16(const float* src, int64_t ld_src, int64_t rows, int K, void* dst, void* stream) {
+  WSI_CHECK_ARG(rows >= 0 && K >= 8, "split_bf16: bad shape");
+  if (rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(src && dst && ld_src >= K, "split_bf16: null pointer / short row stride");
+  return wsi_split_launch(src, ld_src, rows, dst, nullptr, 4, 0, nullptr, K, wsi_stream(stream));
+}
+
+extern "C" int wsi_typed_linear_split(const void* x_split, const void* w_split, const float* bias, int K, int n_out,
+                                      const int32_t* type_ptr_host, int T, int act, const float* skip,
+                                      const float* res, int64_t ldres, const float* drop_mask, int64_t ldmask,
+                                      const float* row_gate, const float* row_scale, float* y, int64_t ldy,
+                                      void* y_split, void* stream) {
+  WSI_CHECK_ARG(type_ptr_host && T >= 1 && T <= WSI_MAX_TYPES, "typed_linear_split: bad type_ptr / T=%d", T);
+  WSI_CHECK_ARG(act == WSI_ACT_NONE || act == WSI_ACT_GELU, "typed_linear_split: unknown activation %d", act);
+  WSI_CHECK_ARG(!skip || res, "typed_linear_split: skip mix needs a residual");
+  const int64_t n_rows = type_ptr_host[T];
+  if (n_rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(x_split && w_split && (y || y_split), "typed_linear_split: null pointer");
+  WSI_CHECK_ARG(!y || ldy >= n_out, "typed_linear_split: row stride smaller than the row");
+  if (!wsi_typed_linear_tc_supported(n_rows, K, n_out, K)) {
+    wsi_set_error("typed_linear_split: shape (rows=%lld K=%d n_out=%d) does not fit the tcgen05 path",
+                  (long long)n_rows, K, n_out);
+    return WSI_ERR_UNSUPPORTED;
+  }
+  LinearEpilogue ep{};
+  ep.bias = bias; ep.act = act; ep.skip = skip; ep.res = res; ep.ldres = ldres;
+  ep.drop_mask = drop_mask; ep.ldmask = ldmask; ep.row_gate = row_gate; ep.row_scale = row_scale;
+  ep.y = y; ep.ldy = ldy; ep.n_out = n_out;
+  return wsi_typed_linear_tc_gemm(x_split, w_split, K, type_ptr_host, T, ep, y_split, wsi_stream(stream));
+}
+
 extern "C" int64_t wsi_typed_linear_workspace_bytes(int64_t n_rows, int K, int n_out, int T, int impl) {
   if (impl == 1) return 0;
   if (!wsi_typed_linear_tc_supported(n_rows, K, n_out, K)) return 0;

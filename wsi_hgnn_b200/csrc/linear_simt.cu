@@ -104,6 +104,61 @@ typed_linear_simt_kernel(SimtGemmArgs a, TypeSegs segs, LinearEpilogue ep) {
   }
 }
 
+// Few-row variant (the [T*B, D] readout and the [B, *] prediction heads at small batch, models/HEATNet4.py:219,243-245):
+// one warp per (group, output column): the lanes stride over K with 16-byte loads of the W row and of up to RMAX
+// activation rows, warp-shuffle reduction, fused epilogue by lane 0.  Launch-latency bound; the point is to spread
+// the W read over many warps instead of one 64 x 64 tile block.
+constexpr int RMAX = 8;
+
+__global__ void __launch_bounds__(128)
+typed_linear_fewrows_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int K,
+                            TypeSegs segs, LinearEpilogue ep, int vec4) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int t = blockIdx.y;
+  if (n >= ep.n_out) return;
+  const int r0 = segs.ptr[t], r1 = segs.ptr[t + 1];
+  if (r1 <= r0) return;
+  const float* w = W + ((int64_t)t * ep.n_out + n) * K;
+  const float alpha = ep.skip ? wsi_sigmoid(__ldg(ep.skip + t)) : 1.f;
+  for (int rb = r0; rb < r1; rb += RMAX) {
+    const int nr = min(RMAX, r1 - rb);
+    float acc[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
+    if (vec4) {
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < nr) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(X + (int64_t)(rb + r) * ldx + k));
+            acc[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[r]))));
+          }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(w + k);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < nr) acc[r] = fmaf(wv, __ldg(X + (int64_t)(rb + r) * ldx + k), acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      float v = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && r < nr) {
+        const int64_t row = rb + r;
+        const bool open = ep.row_gate ? (__ldg(ep.row_gate + row) != 0.f) : true;
+        const float rs = ep.row_scale ? __ldg(ep.row_scale + row) : 1.f;
+        ep.y[row * ep.ldy + n] = wsi_epilogue_value(ep, v, t, row, n, alpha, open, rs);
+      }
+    }
+  }
+}
+
 int launch(const SimtGemmArgs& a, const int32_t* group_ptr_host, int T, const LinearEpilogue& ep, int batch,
            cudaStream_t stream) {
   TypeSegs segs;
@@ -123,6 +178,22 @@ int launch(const SimtGemmArgs& a, const int32_t* group_ptr_host, int T, const Li
 
 int wsi_typed_linear_simt_launch(const float* x, int64_t ldx, const float* w, int K, const int32_t* type_ptr_host,
                                  int T, const LinearEpilogue& ep, cudaStream_t stream) {
+  int max_rows = 0;
+  for (int t = 0; t < T; ++t) max_rows = max_rows > type_ptr_host[t + 1] - type_ptr_host[t] ? max_rows : type_ptr_host[t + 1] - type_ptr_host[t];
+  if (max_rows <= 4 * RMAX && T <= 65535) {                // few rows per group: warp per output column
+    TypeSegs segs;
+    if (wsi_make_segs(&segs, type_ptr_host, T, 64) != 0) {
+      wsi_set_error("typed_linear: bad type_ptr (T=%d, max %d)", T, WSI_MAX_TYPES);
+      return WSI_ERR_ARG;
+    }
+    if (max_rows == 0) return WSI_OK;
+    const int vec4 = K % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+    dim3 grid((ep.n_out + 3) / 4, T);
+    typed_linear_fewrows_kernel<<<grid, 128, 0, stream>>>(x, ldx, w, K, segs, ep, vec4);
+    WSI_CHECK_LAUNCH();
+    return WSI_OK;
+  }
   SimtGemmArgs a{};
   a.X = x; a.ldx = ldx; a.W = w; a.w_group_stride = (int64_t)ep.n_out * K; a.K = K;
   return launch(a, type_ptr_host, T, ep, 1, stream);

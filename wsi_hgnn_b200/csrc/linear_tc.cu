@@ -162,6 +162,7 @@ struct TcArgs {
   int w_rows;        // T * n_out (row offset of the lo half of the W workspace)
   int K, n_out;
   int n_tiles_m, n_tiles_n;   // n_tiles_m counts 256-row PAIR tiles
+  __nv_bfloat16* y_split;   // optional [2 * n_rows, n_out] bf16 (hi; lo) copy of y: the next GEMM's A operand
   int dbg;           // development only (env WSI_TC_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads, bit 2 = skip the epilogue body
 };
 
@@ -301,7 +302,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int rows_left = segs.ptr[t + 1] - (row0 + rsub);         // this lane handles rows row0 + rsub + 4 it
       const int n0 = tn * BN + half * (BN / 2) + c4;                 // this lane's first column
       const float alpha = (FULL && ep.skip) ? wsi_sigmoid(__ldg(ep.skip + t)) : 1.0f;
-      float* yp = ep.y + (int64_t)(row0 + rsub) * ep.ldy + n0;
+      float* yp = ep.y ? ep.y + (int64_t)(row0 + rsub) * ep.ldy + n0 : nullptr;
       const float* bias_p = ep.bias ? ep.bias + (int64_t)t * ep.n_out + n0 : nullptr;
       const float* res_p = (FULL && ep.skip) ? ep.res + (int64_t)(row0 + rsub) * ep.ldres + n0 : nullptr;
       const float* mask_p = (FULL && ep.drop_mask) ? ep.drop_mask + (int64_t)(row0 + rsub) * ep.ldmask + n0 : nullptr;
@@ -345,7 +346,16 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const float4 accv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * EPI_LD + ((((lane & 7) ^ ((it * 4 + rsub) & 7))) << 2));
             const float4 o = FULL ? epi_mix4<true>(ep, accv, bb, mm[it], rr[it], alpha, gate[it] != 0.f, rscl[it])
                                   : epi_mix4<false>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
-            *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
+            if (ep.y) *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
+            if (a.y_split) {
+              __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+              wsi_split_bf16(o.x, h0, l0); wsi_split_bf16(o.y, h1, l1); wsi_split_bf16(o.z, h2, l2); wsi_split_bf16(o.w, h3, l3);
+              __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
+              __nv_bfloat162 lv[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
+              __nv_bfloat16* ys = a.y_split + (int64_t)(row0 + rsub + it * 4) * a.n_out + n0 + c * 32;
+              *reinterpret_cast<uint2*>(ys) = *reinterpret_cast<uint2*>(hv);
+              *reinterpret_cast<uint2*>(ys + (int64_t)a.n_rows * a.n_out) = *reinterpret_cast<uint2*>(lv);
+            }
           }
         }
         __syncwarp();
@@ -415,19 +425,19 @@ int64_t wsi_typed_linear_tc_workspace(int64_t n_rows, int K, int n_out, int T) {
   return align256(2 * n_rows * K * 2) + align256(2 * (int64_t)T * n_out * K * 2) + 1024;
 }
 
-int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int K, const int32_t* type_ptr_host,
-                               int T, const LinearEpilogue& ep, void* workspace, int64_t workspace_bytes,
-                               cudaStream_t stream) {
+// GEMM on pre-split operands: a_ws bf16 [2 * n_rows, K] (hi rows, then lo rows), w_ws bf16 [2 * T * n_out, K].
+int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const int32_t* type_ptr_host, int T,
+                             const LinearEpilogue& ep, void* y_split, cudaStream_t stream) {
   const int64_t n_rows = type_ptr_host[T];
   const int n_out = ep.n_out;
-  WSI_CHECK_ARG(workspace && workspace_bytes >= wsi_typed_linear_tc_workspace(n_rows, K, n_out, T),
-                "typed_linear(tcgen05): workspace of %lld bytes needed", (long long)wsi_typed_linear_tc_workspace(n_rows, K, n_out, T));
-  WSI_CHECK_ARG(aligned16(x) && aligned16(ep.y) && ep.ldy % 4 == 0,
-                "typed_linear(tcgen05): x / y must be 16 B aligned with row strides that are multiples of 4 floats");
-  uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023;
-  __nv_bfloat16* a_ws = reinterpret_cast<__nv_bfloat16*>(wsp);
-  __nv_bfloat16* w_ws = reinterpret_cast<__nv_bfloat16*>(wsp + align256(2 * n_rows * K * 2));
-
+  WSI_CHECK_ARG((ep.y || y_split) && (!ep.y || (aligned16(ep.y) && ep.ldy % 4 == 0)),
+                "typed_linear(tcgen05): y must be 16 B aligned with a row stride that is a multiple of 4 floats");
+  WSI_CHECK_ARG((reinterpret_cast<uintptr_t>(a_ws) & 127) == 0 && (reinterpret_cast<uintptr_t>(w_ws) & 127) == 0 &&
+                    (!y_split || (reinterpret_cast<uintptr_t>(y_split) & 15) == 0),
+                "typed_linear(tcgen05): split operands must be 128 B aligned");
+  WSI_CHECK_ARG((!ep.bias || aligned16(ep.bias)) && (!ep.drop_mask || (aligned16(ep.drop_mask) && ep.ldmask % 4 == 0)) &&
+                    (!ep.res || (aligned16(ep.res) && ep.ldres % 4 == 0)),
+                "typed_linear(tcgen05): bias / drop_mask / res must be 16 B aligned with row strides multiple of 4 floats");
   TypeSegs segs;
   if (wsi_make_segs(&segs, type_ptr_host, T, PAIR_M) != 0) { wsi_set_error("typed_linear: bad type_ptr"); return WSI_ERR_ARG; }
 
@@ -442,15 +452,6 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
   int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
 
-  // 1. split pre-pass
-  SplitJob ja{x, ldx, n_rows, a_ws}, jb{w, (int64_t)K, (int64_t)T * n_out, w_ws};
-  const int64_t groups = (ja.rows + jb.rows) * (K / 4);
-  int sblocks = (int)((groups + 255) / 256);
-  if (sblocks > sms * 8) sblocks = sms * 8;
-  split_bf16_kernel<<<sblocks, 256, 0, stream>>>(ja, jb, K);
-  WSI_CHECK_LAUNCH();
-
-  // 2. tensor-core GEMM
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a_ws, 2 * n_rows, K, BM);
   if (rc != WSI_OK) return rc;
@@ -459,9 +460,7 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
   TcArgs a{};
   a.n_rows = (int)n_rows; a.w_rows = T * n_out; a.K = K; a.n_out = n_out;
   a.n_tiles_m = segs.tile_start[T]; a.n_tiles_n = (n_out + BN - 1) / BN;
-  WSI_CHECK_ARG((!ep.bias || aligned16(ep.bias)) && (!ep.drop_mask || (aligned16(ep.drop_mask) && ep.ldmask % 4 == 0)) &&
-                    (!ep.res || (aligned16(ep.res) && ep.ldres % 4 == 0)),
-                "typed_linear(tcgen05): bias / drop_mask / res must be 16 B aligned with row strides multiple of 4 floats");
+  a.y_split = reinterpret_cast<__nv_bfloat16*>(y_split);
   const bool full = ep.skip || ep.drop_mask || ep.row_scale;
   { const char* d = getenv("WSI_TC_DEBUG"); a.dbg = d ? atoi(d) : 0; }
   const int total = a.n_tiles_m * a.n_tiles_n;
@@ -471,4 +470,38 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
   else typed_linear_tc_kernel<false><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
+}
+
+// fp32 -> [hi; lo] bf16 of up to two row-strided matrices in one launch (b.rows == 0: only a)
+int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_dst, const float* b_src, int64_t b_ld,
+                     int64_t b_rows, void* b_dst, int K, cudaStream_t stream) {
+  WSI_CHECK_ARG(K % 8 == 0 && a_ld % 4 == 0 && (b_rows == 0 || b_ld % 4 == 0) && aligned16(a_src) && aligned16(b_src) &&
+                    (reinterpret_cast<uintptr_t>(a_dst) & 7) == 0 && (reinterpret_cast<uintptr_t>(b_dst) & 7) == 0,
+                "split_bf16: K must be a multiple of 8, rows 16 B aligned");
+  int sms = wsi_num_sms();
+  if (sms <= 0) return WSI_ERR_CUDA;
+  SplitJob ja{a_src, a_ld, a_rows, reinterpret_cast<__nv_bfloat16*>(a_dst)};
+  SplitJob jb{b_src, b_ld, b_rows, reinterpret_cast<__nv_bfloat16*>(b_dst)};
+  const int64_t groups = (ja.rows + jb.rows) * (K / 4);
+  if (groups == 0) return WSI_OK;
+  int sblocks = (int)((groups + 255) / 256);
+  if (sblocks > sms * 8) sblocks = sms * 8;
+  split_bf16_kernel<<<sblocks, 256, 0, stream>>>(ja, jb, K);
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}
+
+int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int K, const int32_t* type_ptr_host,
+                               int T, const LinearEpilogue& ep, void* workspace, int64_t workspace_bytes,
+                               cudaStream_t stream) {
+  const int64_t n_rows = type_ptr_host[T];
+  const int n_out = ep.n_out;
+  WSI_CHECK_ARG(workspace && workspace_bytes >= wsi_typed_linear_tc_workspace(n_rows, K, n_out, T),
+                "typed_linear(tcgen05): workspace of %lld bytes needed", (long long)wsi_typed_linear_tc_workspace(n_rows, K, n_out, T));
+  uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023;
+  void* a_ws = reinterpret_cast<void*>(wsp);
+  void* w_ws = reinterpret_cast<void*>(wsp + align256(2 * n_rows * K * 2));
+  int rc = wsi_split_launch(x, ldx, n_rows, a_ws, w, K, (int64_t)T * n_out, w_ws, K, stream);
+  if (rc != WSI_OK) return rc;
+  return wsi_typed_linear_tc_gemm(a_ws, w_ws, K, type_ptr_host, T, ep, nullptr, stream);
 }

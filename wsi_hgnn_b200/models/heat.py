@@ -104,6 +104,37 @@ class HEATLayer(nn.Module):
 
         return self._packs.get(tuple(order), params, build) + (perm is not None,)
 
+    def _packed_split(self, order):
+        """bf16 [hi; lo] forms of the K|V|Q and a_linear weight stacks (operands of the tcgen05 GEMM chain)."""
+        w_kvq, b_kvq, wa, ba, skip, _ = self._packed(order)
+        params = [p for p in self.parameters()]
+        return self._packs.get(("split", tuple(order)), params, lambda: (ops.split_bf16(w_kvq), ops.split_bf16(wa)))
+
+    def tc_chain_ok(self, plan: GraphPlan) -> bool:
+        """The pre-split tensor-core chain needs tile-friendly shapes and the lane-grouped attention layout."""
+        D = self.out_size
+        return (self.in_size == D and ops.head_perm(D, self.n_heads) is not None and
+                ops.tc_ok(plan.N, D, 3 * D) and ops.tc_ok(plan.N, D, D))
+
+    def forward_split(self, plan: GraphPlan, x: torch.Tensor, x_split: torch.Tensor, want_split: bool):
+        """One layer on the pre-split chain: x fp32 [N, D] (residual) and its bf16 [hi; lo] form in, the same two
+        out (x_split only if `want_split`, i.e. another layer follows).  No fp32 -> bf16 conversion pass: the
+        attention kernel and the a_linear epilogue emit the split form directly."""
+        D, H = self.out_size, self.n_heads
+        order = _graph_type_order(plan, self.node_dict)
+        w_kvq, b_kvq, wa, ba, skip, _ = self._packed(order)
+        w_kvq_s, wa_s = self._packed_split(order)
+        tpc = plan.type_ptr_c()
+        kvq, _ = ops.typed_linear_split(x_split, w_kvq_s, b_kvq, plan.type_ptr, 3 * D, type_ptr_c=tpc)
+        agg_s = ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.attn_work(), plan.e_src,
+                                     plan.e_sim, plan.e_rel, plan.node_inv_r, self.e_linear.weight,
+                                     self.e_linear.bias, D, H, split_out=True)
+        mask = None
+        if self.training and self.drop.p > 0:
+            mask = F.dropout(torch.ones((plan.N, D), dtype=torch.float32, device=x.device), self.drop.p, True)
+        return ops.typed_linear_split(agg_s, wa_s, ba, plan.type_ptr, D, skip=skip, res=x, row_gate=plan.node_inv_r,
+                                      drop_mask=mask, want_split=want_split, type_ptr_c=tpc)
+
     def forward_packed(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
         """x [N, in] type-major packed -> [N, out]."""
         D, H = self.out_size, self.n_heads
@@ -147,6 +178,16 @@ class _HEATBase(nn.Module):
         x = packed_features(G, plan, h)
         params = [p for m in self.adapt_ws for p in m.parameters()]
         w_in, b_in = self._packs.get(("in", tuple(order)), params, lambda: stack_linears(self.adapt_ws, order))
+        F_in, D = int(x.shape[1]), int(w_in.shape[1])
+        if len(self.gcs) > 0 and ops.tc_ok(plan.N, F_in, D) and all(l.tc_chain_ok(plan) for l in self.gcs):
+            # tensor-core chain on pre-split bf16 [hi; lo] operands: one conversion pass for the raw features,
+            # every later operand is emitted in split form by the kernel that produces it
+            w_in_s = self._packs.get(("in_split", tuple(order)), params, lambda: ops.split_bf16(w_in))
+            x, xs = ops.typed_linear_split(ops.split_bf16(x), w_in_s, b_in, plan.type_ptr, D, want_split=True,
+                                           type_ptr_c=plan.type_ptr_c())                     # HEATNet4.py:198-206
+            for i, layer in enumerate(self.gcs):                                             # :213-214
+                x, xs = layer.forward_split(plan, x, xs, want_split=i + 1 < len(self.gcs))
+            return plan, x
         x = ops.typed_linear(x, w_in, b_in, plan.type_ptr, type_ptr_c=plan.type_ptr_c())    # HEATNet4.py:198-206
         for layer in self.gcs:                                                               # :213-214
             x = layer.forward_packed(plan, x)

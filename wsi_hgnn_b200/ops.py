@@ -103,6 +103,54 @@ def typed_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
     return out
 
 
+def tc_ok(n_rows: int, K: int, n_out: int) -> bool:
+    """True when the tcgen05 typed linear takes this shape (wsi_typed_linear_tc_ok)."""
+    return bool(_lib.load().wsi_typed_linear_tc_ok(int(n_rows), int(K), int(n_out)))
+
+
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, K] -> bf16 [2 * rows, K] = [hi; lo] with x = hi + lo (wsi_split_bf16): the operand form of
+    typed_linear_split.  A weight stack [T, n_out, K] is split as [T * n_out, K]."""
+    lib = _lib.load()
+    stream = _prep(x)
+    if x.dim() == 3:
+        x = x.reshape(-1, x.shape[-1])
+    xp, ld = _rows(x, "x")
+    rows, K = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((2 * rows, K), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.wsi_split_bf16(xp, ld, rows, K, out.data_ptr(), stream), "wsi_split_bf16")
+    return out
+
+
+def typed_linear_split(x_split: torch.Tensor, w_split: torch.Tensor, bias: Optional[torch.Tensor],
+                       type_ptr: Sequence[int], n_out: int, *, act: int = ACT_NONE,
+                       skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+                       drop_mask: Optional[torch.Tensor] = None, row_gate: Optional[torch.Tensor] = None,
+                       row_scale: Optional[torch.Tensor] = None, want_y: bool = True, want_split: bool = False,
+                       type_ptr_c=None):
+    """tcgen05 typed linear on pre-split bf16 operands; see wsi_typed_linear_split.
+    -> y fp32 [N, n_out] (or None), y_split bf16 [2N, n_out] (or None)."""
+    lib = _lib.load()
+    stream = _prep(x_split)
+    T = len(type_ptr) - 1
+    N, K = int(type_ptr[-1]), int(x_split.shape[1])
+    for name, t, rows in (("x_split", x_split, 2 * N), ("w_split", w_split, 2 * T * n_out)):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or tuple(t.shape) != (rows, K):
+            raise ValueError(f"typed_linear_split: {name} must be a contiguous bf16 [{rows}, {K}] tensor, "
+                             f"got {t.dtype} {tuple(t.shape)}")
+    y = torch.empty((N, n_out), dtype=torch.float32, device=x_split.device) if want_y else None
+    ys = torch.empty((2 * N, n_out), dtype=torch.bfloat16, device=x_split.device) if want_split else None
+    rp, ldres = _rows(res, "res")
+    mp, ldm = _rows(drop_mask, "drop_mask")
+    tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
+    rc = lib.wsi_typed_linear_split(x_split.data_ptr(), w_split.data_ptr(), _vec(bias, "bias"), K, n_out, tp, T, act,
+                                    _vec(skip, "skip"), rp, ldres, mp, ldm, _vec(row_gate, "row_gate"),
+                                    _vec(row_scale, "row_scale"), y.data_ptr() if y is not None else None, n_out,
+                                    ys.data_ptr() if ys is not None else None, stream)
+    _lib.check(rc, "wsi_typed_linear_split")
+    return y, ys
+
+
 def hetero_attn(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, rowptr: torch.Tensor, e_src: torch.Tensor,
                 e_sim: torch.Tensor, e_rel: torch.Tensor, node_inv_r: torch.Tensor, e_w: torch.Tensor,
                 e_b: torch.Tensor, D: int, H: int, use_head_perm: bool, want_attn: bool = False):
@@ -127,17 +175,24 @@ def hetero_attn(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, rowptr: torch
 
 def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: dict, e_src: torch.Tensor,
                      e_sim: torch.Tensor, e_rel: torch.Tensor, node_inv_r: torch.Tensor, e_w: torch.Tensor,
-                     e_b: torch.Tensor, D: int, H: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     e_b: torch.Tensor, D: int, H: int, out: Optional[torch.Tensor] = None,
+                     split_out: bool = False) -> torch.Tensor:
     """HEAT edge attention driven by the hub-balancing work list of GraphPlan.attn_work();
-    see wsi_hetero_attn_work_fwd.  k/v/q/agg columns are in the head_perm(D, H) order."""
+    see wsi_hetero_attn_work_fwd.  k/v/q/agg columns are in the head_perm(D, H) order.
+    split_out: return the result as bf16 [2N, D] = [hi; lo] (operand of typed_linear_split) instead of fp32."""
     lib = _lib.load()
     stream = _prep(q)
     N = int(q.shape[0])
     kp, ldk = _rows(k, "k")
     vp, ldv = _rows(v, "v")
     qp, ldq = _rows(q, "q")
-    agg = out if out is not None else torch.empty((N, D), dtype=torch.float32, device=q.device)
-    ap, ldo = _rows(agg, "agg")
+    agg = agg_split = None
+    if split_out:
+        agg_split = torch.empty((2 * N, D), dtype=torch.bfloat16, device=q.device)
+        ap, ldo = None, D
+    else:
+        agg = out if out is not None else torch.empty((N, D), dtype=torch.float32, device=q.device)
+        ap, ldo = _rows(agg, "agg")
     n_part, n_split = work["n_part"], work["n_split"]
     part_ms = part_acc = None
     if n_part > 0:
@@ -151,9 +206,10 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
                                       _vec(work["split_ptr"], "split_ptr", torch.int32),
                                       _vec(work["part_rel"], "part_rel", torch.int32), n_split, n_part,
                                       part_ms.data_ptr() if part_ms is not None else None,
-                                      part_acc.data_ptr() if part_acc is not None else None, ap, ldo, stream)
+                                      part_acc.data_ptr() if part_acc is not None else None, ap, ldo,
+                                      agg_split.data_ptr() if agg_split is not None else None, stream)
     _lib.check(rc, "wsi_hetero_attn_work_fwd")
-    return agg
+    return agg_split if split_out else agg
 
 
 def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int, use_head_perm: bool = False):
