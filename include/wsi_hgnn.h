@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 5
+#define WSI_ABI_VERSION 6
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -161,6 +161,32 @@ int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_pt
 int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta,
                         const int32_t* type_ptr_host, int T, int D, float eps, float* y, int64_t ldy,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph plan builder (kernel K8): what dgl.to_heterogeneous + DGL's on-demand CSC conversion do for the reference
+ * (construct_graph/graph_constructor.py:285-297; the per-relation sub_graph views of models/HEATNet4.py:91-92).
+ * Input: the per-relation COO arrays concatenated in relation order, LOCAL node ids (as a heterograph stores them):
+ *   src, dst int64 [E]; the edge attribute as sim fp32 [E] or sim64 fp64 [E] (old pickles, graph_constructor.py:292)
+ *   or neither (0); rel_table (DEVICE) int32 [3, R + 1]: row 0 = edge range of relation r, row 1 = packed-id offset
+ *   of its src type, row 2 = of its dst type.
+ * Output: rowptr int32 [N + 1], e_src int32 [E], e_sim fp32 [E], e_rel uint8 [E], optional e_dst int32 [E]: edges
+ *   sorted by (packed dst, relation, original position).  stats (DEVICE) int32 [4]: [0] max in-degree, [1] != 0 if an
+ *   edge endpoint was out of range (such edges are dropped; the caller raises).  Deterministic. */
+int64_t wsi_plan_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+int wsi_plan_build_csr(const int64_t* src, const int64_t* dst, const float* sim, const double* sim64,
+                       const int32_t* rel_table, int R, int64_t n_nodes, int64_t n_edges, int32_t* rowptr,
+                       int32_t* e_src, float* e_sim, uint8_t* e_rel, int32_t* e_dst, int32_t* stats, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+/* Work list of wsi_hetero_attn_work_fwd in two phases (the host reads the two totals in between to size the arrays):
+ *   count: chunk_base, split_idx int32 [N + 1] = exclusive scans of (chunks of row, row is split); last entries =
+ *          n_part, n_split.  workspace: wsi_plan_workspace_bytes(N, 0).
+ *   fill : items [n_part + N - n_split, 4], split_row [n_split], split_ptr [n_split + 1], part_rel [n_part]. */
+int wsi_plan_attn_work_count(const int32_t* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
+                             int32_t* chunk_base, int32_t* split_idx, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+int wsi_plan_attn_work_fill(const int32_t* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
+                            const int32_t* chunk_base, const int32_t* split_idx, int64_t n_part, int64_t n_split,
+                            int32_t* items, int32_t* split_row, int32_t* split_ptr, int32_t* part_rel, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Typed readout (kernel K4): dgl.readout.{sum,mean,max}_nodes(graph, 'h', ntype=)  pooling/*.py

@@ -81,3 +81,39 @@ def test_hnsw_query_surface():
     all_nbr = m.query_all(5).cpu().numpy()
     one = m.query(feats[10].numpy(), 5)
     assert list(one) == list(all_nbr[10])
+
+
+@pytest.mark.parametrize("seed,n,T,hub", [(0, 3000, 3, 0), (1, 500, 6, 300), (2, 70000, 2, 0)])
+def test_native_plan_matches_host_plan(seed, n, T, hub):
+    """wsi_plan_build_csr / wsi_plan_attn_work_* == the host (torch ops) statement of the same layout: bit-exact."""
+    import torch
+    from wsi_hgnn_b200 import synthetic
+    if hub:
+        G = synthetic.random_hetero_graph([n // T] * T, 4 * n, 8, seed=seed, hub=hub)
+    else:
+        G = synthetic.synth_slide_graph(n, 16, T, 5, seed=seed, noise_edges=0.3)
+    host = G.plan()                                   # CPU graph -> host path
+    Gd = G.to("cuda")
+    dev = Gd.plan()                                   # CUDA graph -> plan-builder kernels
+    assert dev._stats is not None
+    for name in ("rowptr", "e_src", "e_rel", "e_sim"):
+        assert torch.equal(getattr(dev, name).cpu(), getattr(host, name)), name
+    for chunk in (4, 16):
+        wd, wh = dev.attn_work(chunk), host.attn_work(chunk)
+        assert (wd["n_items"], wd["n_split"], wd["n_part"]) == (wh["n_items"], wh["n_split"], wh["n_part"])
+        assert torch.equal(wd["items"][:wd["n_items"]].cpu(), wh["items"])
+        if wh["n_split"]:
+            assert torch.equal(wd["split_row"].cpu(), wh["split_row"])
+            assert torch.equal(wd["split_ptr"].cpu(), wh["split_ptr"])
+            assert torch.equal(wd["part_rel"].cpu(), wh["part_rel"])
+    assert dev.max_in_degree == host.max_in_degree
+
+
+def test_native_plan_rejects_out_of_range_edges():
+    import torch
+    from wsi_hgnn_b200.hetero_graph import HeteroGraph
+    G = HeteroGraph({"0": 4, "1": 3}, {("0", "pos", "1"): (torch.tensor([0, 1, 3]), torch.tensor([0, 7, 2]))},
+                    {"0": {"feat": torch.zeros(4, 8)}, "1": {"feat": torch.zeros(3, 8)}})
+    with pytest.raises(IndexError):
+        p = G.to("cuda").plan()
+        p.check()

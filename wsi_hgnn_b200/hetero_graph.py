@@ -175,12 +175,32 @@ class GraphPlan:
         self.rel_src_type: List[int] = []
         self.rel_dst_type: List[int] = []
         self.r_count: List[int] = []          # R_t per type (batch mode)
-        self.max_in_degree = 0
+        self._max_in_degree = 0
+        self._stats = None                    # device int32 [4] of the native builder, read lazily
         self._t = None
         self.device = torch.device("cpu")
         self.seg_nonempty = None              # bool [T, B] on host
         self.cache: Dict = {}                 # per-model derived tensors (relation id maps, packed feats, ...)
         self._segs = None
+
+    def check(self):
+        """Raise if the native builder flagged an out-of-range edge endpoint (reads 8 bytes back: a host sync,
+        so it runs with the first work-list build rather than inside plan())."""
+        if self._stats is not None:
+            mx, bad = self._stats[:2].tolist()
+            self._stats = None
+            self._max_in_degree = mx
+            if bad:
+                raise IndexError("edge endpoint out of range")
+
+    @property
+    def max_in_degree(self) -> int:
+        self.check()
+        return self._max_in_degree
+
+    @max_in_degree.setter
+    def max_in_degree(self, v: int):
+        self._max_in_degree = int(v)
 
     def type_ptr_c(self):
         """type_ptr as a ctypes int32 array (host argument of the typed kernels)."""
@@ -199,6 +219,7 @@ class GraphPlan:
         Returns dict: S, seg_ptr int32 [S+1], seg_dst int32 [S], seg_slot int64 [S] (graph relation
         slot), row_seg_ptr int32 [N+1] (segments of each dst row are contiguous)."""
         if self._segs is None:
+            self.check()
             dev = self.device
             E = self.E
             if E == 0:
@@ -235,6 +256,16 @@ class GraphPlan:
         if key in self.cache:
             return self.cache[key]
         dev = self.device
+        if dev.type == "cuda":
+            from . import ops
+            work = ops.plan_attn_work(self.rowptr, self.e_rel, self.N, chunk, self._stats)
+            if self._stats is not None:
+                self._stats = None
+                self._max_in_degree = work["max_in_degree"]
+                if work["bad_edges"]:
+                    raise IndexError("edge endpoint out of range")
+            self.cache[key] = work
+            return work
         i32 = dict(dtype=torch.int32, device=dev)
         rowptr = self.rowptr.to(torch.int64)
         deg = rowptr[1:] - rowptr[:-1]
@@ -581,6 +612,52 @@ class HeteroGraph:
         p.node_inv_r = inv[:p.N].to(dev) if p.N > 0 else inv[:0].to(dev)
 
         # dst-major, relation-grouped CSR
+        p.E = sum(int(self._edges[ce][0].numel()) for ce in p.rel_list)
+        if dev.type == "cuda":
+            self._plan_csr_native(p, sim_name)
+        else:
+            self._plan_csr_host(p, sim_name)
+        self._plan = p
+        return p
+
+    def _plan_csr_native(self, p: GraphPlan, sim_name: str):
+        """CSR via the plan-builder kernels (wsi_plan_build_csr): a handful of launches on the end-to-end path."""
+        from . import ops
+        dev = p.device
+        R = len(p.rel_list)
+        if p.E == 0:
+            p.e_src = torch.zeros(0, dtype=torch.int32, device=dev)
+            p.e_sim = torch.zeros(0, dtype=torch.float32, device=dev)
+            p.e_rel = torch.zeros(0, dtype=torch.uint8, device=dev)
+            p.rowptr = torch.zeros(p.N + 1, dtype=torch.int32, device=dev)
+            return
+        srcs = [self._edges[ce][0] for ce in p.rel_list]
+        dsts = [self._edges[ce][1] for ce in p.rel_list]
+        have_sim = [sim_name in self._edata[ce] for ce in p.rel_list]
+        sim = None
+        if all(have_sim):
+            sims = [self._edata[ce][sim_name].reshape(-1) for ce in p.rel_list]
+            if any(s.dtype != sims[0].dtype for s in sims) or sims[0].dtype not in (torch.float32, torch.float64):
+                sims = [s.to(torch.float32) for s in sims]
+            sim = torch.cat(sims) if R > 1 else sims[0].contiguous()
+        elif any(have_sim):
+            sim = torch.cat([self._edata[ce][sim_name].reshape(-1).to(torch.float32) if h else
+                             torch.zeros(self._edges[ce][0].numel(), dtype=torch.float32, device=dev)
+                             for ce, h in zip(p.rel_list, have_sim)])
+        src = (torch.cat(srcs) if R > 1 else srcs[0]).to(torch.int64).contiguous()
+        dst = (torch.cat(dsts) if R > 1 else dsts[0]).to(torch.int64).contiguous()
+        ptr = [0]
+        for s in srcs:
+            ptr.append(ptr[-1] + int(s.numel()))
+        table = torch.tensor([ptr, [p.type_ptr[t] for t in p.rel_src_type] + [0],
+                              [p.type_ptr[t] for t in p.rel_dst_type] + [0]], dtype=torch.int32).to(dev)
+        p.rowptr, p.e_src, p.e_sim, p.e_rel, _, stats = ops.plan_build_csr(src, dst, sim, table, R, p.N)
+        p._stats = stats                  # [0] max in-degree, [1] range-error flag: read lazily (no sync here)
+
+    def _plan_csr_host(self, p: GraphPlan, sim_name: str):
+        """Host-side (torch ops) statement of the same layout: CPU graphs in the tests, and the cross-check of the
+        native builder."""
+        dev = p.device
         srcs, dsts, rels, sims = [], [], [], []
         for ri, ce in enumerate(p.rel_list):
             s, d = self._edges[ce]
@@ -610,15 +687,11 @@ class HeteroGraph:
             rowptr = torch.zeros(p.N + 1, dtype=torch.int32, device=dev)
             rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
             p.rowptr = rowptr
-            p.E = int(src.numel())
         else:
             p.e_src = torch.zeros(0, dtype=torch.int32, device=dev)
             p.e_sim = torch.zeros(0, dtype=torch.float32, device=dev)
             p.e_rel = torch.zeros(0, dtype=torch.uint8, device=dev)
             p.rowptr = torch.zeros(p.N + 1, dtype=torch.int32, device=dev)
-            p.E = 0
-        self._plan = p
-        return p
 
     def __repr__(self):
         return (f"HeteroGraph(num_nodes={self._num_nodes}, num_edges="

@@ -10,6 +10,15 @@ from typing import Callable, Dict, Sequence, Tuple
 import torch
 
 
+def param_list(module, tag: str, fn):
+    """Parameter list `fn()` of `module`, enumerated once (walking nn.Module.parameters() on every forward costs
+    more host time than the launches it feeds).  The set of Parameter objects of a built model never changes."""
+    cache = module.__dict__.setdefault("_plists", {})
+    if tag not in cache:
+        cache[tag] = list(fn())
+    return cache[tag]
+
+
 class PackCache:
     def __init__(self):
         self._store: Dict = {}

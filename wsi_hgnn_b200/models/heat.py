@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..hetero_graph import GraphPlan, HeteroGraph
-from ._packing import PackCache, stack_linears
+from ._packing import PackCache, param_list, stack_linears
 
 _POOLS = ("mean", "sum", "max")
 
@@ -88,7 +88,7 @@ class HEATLayer(nn.Module):
     def _packed(self, order):
         D, H = self.out_size, self.n_heads
         perm = ops.head_perm(D, H)
-        params = [p for p in self.parameters()]
+        params = param_list(self, "all", self.parameters)
 
         def build():
             dev = self.skip.device
@@ -107,7 +107,7 @@ class HEATLayer(nn.Module):
     def _packed_split(self, order):
         """bf16 [hi; lo] forms of the K|V|Q and a_linear weight stacks (operands of the tcgen05 GEMM chain)."""
         w_kvq, b_kvq, wa, ba, skip, _ = self._packed(order)
-        params = [p for p in self.parameters()]
+        params = param_list(self, "all", self.parameters)
         return self._packs.get(("split", tuple(order)), params, lambda: (ops.split_bf16(w_kvq), ops.split_bf16(wa)))
 
     def tc_chain_ok(self, plan: GraphPlan) -> bool:
@@ -147,6 +147,7 @@ class HEATLayer(nn.Module):
                                        plan.e_sim, plan.e_rel, plan.node_inv_r, self.e_linear.weight,
                                        self.e_linear.bias, D, H)
         else:
+            plan.check()
             agg = ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
                                   plan.e_rel, plan.node_inv_r, self.e_linear.weight, self.e_linear.bias, D, H, False)
         mask = None
@@ -176,7 +177,7 @@ class _HEATBase(nn.Module):
         plan = G.plan()
         order = _graph_type_order(plan, self.node_dict)
         x = packed_features(G, plan, h)
-        params = [p for m in self.adapt_ws for p in m.parameters()]
+        params = param_list(self, "in", lambda: (p for m in self.adapt_ws for p in m.parameters()))
         w_in, b_in = self._packs.get(("in", tuple(order)), params, lambda: stack_linears(self.adapt_ws, order))
         F_in, D = int(x.shape[1]), int(w_in.shape[1])
         if len(self.gcs) > 0 and ops.tc_ok(plan.N, F_in, D) and all(l.tc_chain_ok(plan) for l in self.gcs):
@@ -197,7 +198,7 @@ class _HEATBase(nn.Module):
         """[T*B, n_pred] = linears_prediction[type](pool_type(x)) with the empty-type zero block."""
         pooled = ops.segment_pool(x, plan.seg_ptr, len(plan.ntypes) * plan.B, self.graph_pooling_type)
         names = list(plan.ntypes)
-        params = [p for nt in names for p in self.linears_prediction[nt].parameters()]
+        params = param_list(self, ("pred", tuple(names)), lambda: (p for nt in names for p in self.linears_prediction[nt].parameters()))
 
         def build():
             ws = torch.stack([self.linears_prediction[nt].weight for nt in names]).contiguous()

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..hetero_graph import GraphPlan, HeteroGraph
-from ._packing import PackCache, stack_linears
+from ._packing import PackCache, param_list, stack_linears
 from .heat import _check_pool, _graph_type_order, packed_features, readout_scale, unpack_rows
 
 
@@ -73,7 +73,7 @@ class HGTLayer(nn.Module):
         self._packs = PackCache()
 
     def _packed(self, order):
-        params = [p for p in self.parameters()]
+        params = param_list(self, "all", self.parameters)
 
         def build():
             dev = self.skip.device
@@ -177,7 +177,7 @@ class HGT(nn.Module):
         order = _graph_type_order(plan, self.node_dict)
         names = list(plan.ntypes)
         x = packed_features(G, plan, h)
-        params = [p for m in self.adapt_ws for p in m.parameters()]
+        params = param_list(self, "in", lambda: (p for m in self.adapt_ws for p in m.parameters()))
         w_in, b_in = self._packs.get(("in", tuple(order)), params, lambda: stack_linears(self.adapt_ws, order))
         x = ops.typed_linear(x, w_in, b_in, plan.type_ptr, act=ops.ACT_GELU, type_ptr_c=plan.type_ptr_c())  # :176-184
         scale = readout_scale(plan, G.independent)
@@ -185,7 +185,7 @@ class HGT(nn.Module):
         n_run = self.n_layers if return_embeddings else self.n_layers
         for i in range(n_run):                                             # :189-199
             pooled = ops.segment_pool(x, plan.seg_ptr, T * B, self.graph_pooling_type)
-            pp = [p for nt in names for p in self.linears_prediction[nt][i].parameters()]
+            pp = param_list(self, ("pred", i, tuple(names)), lambda: (p for nt in names for p in self.linears_prediction[nt][i].parameters()))
             w_p, b_p = self._packs.get(("pred", i, tuple(names)), pp, lambda i=i: (
                 torch.stack([self.linears_prediction[nt][i].weight for nt in names]).contiguous(),
                 torch.stack([self.linears_prediction[nt][i].bias for nt in names]).contiguous()))

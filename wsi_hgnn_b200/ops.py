@@ -289,6 +289,67 @@ def segment_pool(x: torch.Tensor, seg_ptr: torch.Tensor, n_seg: int, op: str) ->
     return out
 
 
+def plan_build_csr(src: torch.Tensor, dst: torch.Tensor, sim: Optional[torch.Tensor], rel_table: torch.Tensor, R: int,
+                   n_nodes: int, want_dst: bool = False):
+    """Relation-grouped dst-major CSR of the packed graph; see wsi_plan_build_csr.
+    -> rowptr, e_src, e_sim, e_rel, e_dst (or None), stats (device int32 [4])."""
+    lib = _lib.load()
+    stream = _prep(rel_table)
+    dev = rel_table.device
+    E = int(src.shape[0])
+    rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+    e_src = torch.empty(E, dtype=torch.int32, device=dev)
+    e_sim = torch.empty(E, dtype=torch.float32, device=dev)
+    e_rel = torch.empty(E, dtype=torch.uint8, device=dev)
+    e_dst = torch.empty(E, dtype=torch.int32, device=dev) if want_dst else None
+    stats = torch.empty(4, dtype=torch.int32, device=dev)
+    ws_bytes = lib.wsi_plan_workspace_bytes(n_nodes, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    sim32 = sim64 = None
+    if sim is not None:
+        if sim.dtype == torch.float64:
+            sim64 = _vec(sim, "sim", torch.float64)
+        else:
+            sim32 = _vec(sim, "sim", torch.float32)
+    rc = lib.wsi_plan_build_csr(_vec(src, "src", torch.int64), _vec(dst, "dst", torch.int64), sim32, sim64,
+                                _vec(rel_table, "rel_table", torch.int32), R, n_nodes, E, rowptr.data_ptr(),
+                                e_src.data_ptr(), e_sim.data_ptr(), e_rel.data_ptr(),
+                                e_dst.data_ptr() if e_dst is not None else None, stats.data_ptr(), ws.data_ptr(),
+                                ws_bytes, stream)
+    _lib.check(rc, "wsi_plan_build_csr")
+    return rowptr, e_src, e_sim, e_rel, e_dst, stats
+
+
+def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chunk: int,
+                   stats: Optional[torch.Tensor] = None) -> dict:
+    """Hub-balancing work list of hetero_attn_work; see wsi_plan_attn_work_count / _fill (one host sync for the
+    two totals that size the arrays)."""
+    lib = _lib.load()
+    stream = _prep(rowptr)
+    dev = rowptr.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    scans = torch.empty((2, n_nodes + 1), **i32)
+    ws_bytes = lib.wsi_plan_workspace_bytes(n_nodes, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rp, rl = _vec(rowptr, "rowptr", torch.int32), _vec(e_rel, "e_rel", torch.uint8)
+    _lib.check(lib.wsi_plan_attn_work_count(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(),
+                                            ws.data_ptr(), ws_bytes, stream), "wsi_plan_attn_work_count")
+    if stats is not None:                                             # the one host sync (totals + builder flags)
+        n_part, n_split, max_deg, bad = torch.cat([scans[:, n_nodes], stats[:2]]).tolist()
+    else:
+        (n_part, n_split), max_deg, bad = scans[:, n_nodes].tolist(), None, 0
+    n_items = n_part + n_nodes - n_split
+    items = torch.empty((max(n_items, 1), 4), **i32)
+    split_row = torch.empty(max(n_split, 1), **i32)
+    split_ptr = torch.empty(n_split + 1, **i32)
+    part_rel = torch.empty(max(n_part, 1), **i32)
+    _lib.check(lib.wsi_plan_attn_work_fill(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(), n_part,
+                                           n_split, items.data_ptr(), split_row.data_ptr(), split_ptr.data_ptr(),
+                                           part_rel.data_ptr(), stream), "wsi_plan_attn_work_fill")
+    return dict(items=items, n_items=n_items, split_row=split_row, split_ptr=split_ptr, part_rel=part_rel,
+                n_split=n_split, n_part=n_part, max_in_degree=max_deg, bad_edges=bool(bad))
+
+
 def knn_topk(feat: torch.Tensor, topn: int, q_begin: int = 0, q_end: Optional[int] = None, want_dist: bool = False):
     """Exact L2 k-NN (self included, ordered by (distance, index)); see wsi_knn_topk.
     -> int32 [q_end - q_begin, topn] (and the fp32 distances)."""
