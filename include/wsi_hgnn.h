@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 6
+#define WSI_ABI_VERSION 8
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -113,6 +113,8 @@ int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   online-softmax partial goes to part_ms [n_part, 64] (per-lane max | sum) and part_acc [n_part, D].
  *   The split rows are finished by a merge launch: split_row int32 [n_split], split_ptr int32 [n_split + 1]
  *   (partial slots of each split row, in edge order), part_rel int32 [n_part] (relation slot of each partial).
+ *   With split_cnt int32 [n_split] (ZERO before the first launch; the kernel leaves it zero) and part_split int32
+ *   [n_part] the merge is fused: the warp finishing a row's last chunk merges that row; else a second launch does.
  * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work().
  *   agg_split != NULL: the result is (also) written as bf16 [2 * n_rows, D] (hi rows, then lo rows: x = hi + lo),
  *   the A operand layout of wsi_typed_linear_split; agg may then be NULL. */
@@ -120,7 +122,8 @@ int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_
                              const int32_t* e_src, const float* e_sim, const uint8_t* e_rel, const float* node_inv_r,
                              const float* e_w, const float* e_b, int64_t n_rows, int D, int H, const int32_t* items,
                              int64_t n_items, const int32_t* split_row, const int32_t* split_ptr,
-                             const int32_t* part_rel, int64_t n_split, int64_t n_part, float* part_ms,
+                             const int32_t* part_rel, const int32_t* part_split, int32_t* split_cnt,
+                             int64_t n_split, int64_t n_part, float* part_ms,
                              float* part_acc, float* agg, int64_t ldo, void* agg_split, void* stream);
 
 /* Segment form used by HGT (WSI_SCORE_HGT): one work item per (dst,relation) segment.
@@ -179,14 +182,19 @@ int wsi_plan_build_csr(const int64_t* src, const int64_t* dst, const float* sim,
                        int64_t workspace_bytes, void* stream);
 /* Work list of wsi_hetero_attn_work_fwd in two phases (the host reads the two totals in between to size the arrays):
  *   count: chunk_base, split_idx int32 [N + 1] = exclusive scans of (chunks of row, row is split); last entries =
- *          n_part, n_split.  workspace: wsi_plan_workspace_bytes(N, 0).
- *   fill : items [n_part + N - n_split, 4], split_row [n_split], split_ptr [n_split + 1], part_rel [n_part]. */
+ *          n_part, n_split; class_hist int32 [2 * (chunk + 1)] scratch shared by the two phases (chunk <= 255).
+ *          workspace: wsi_plan_workspace_bytes(N, 0).
+ *   fill : items [n_part + N - n_split, 4] = the chunk items (edge order), then the whole-row items sorted by edge
+ *          count, largest first (order inside a size class arbitrary: it only affects scheduling);
+ *          split_row [n_split], split_ptr [n_split + 1], part_rel [n_part], part_split [n_part] (optional: split
+ *          index of each partial, for the fused merge). */
 int wsi_plan_attn_work_count(const int32_t* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
-                             int32_t* chunk_base, int32_t* split_idx, void* workspace, int64_t workspace_bytes,
-                             void* stream);
+                             int32_t* chunk_base, int32_t* split_idx, int32_t* class_hist, void* workspace,
+                             int64_t workspace_bytes, void* stream);
 int wsi_plan_attn_work_fill(const int32_t* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
                             const int32_t* chunk_base, const int32_t* split_idx, int64_t n_part, int64_t n_split,
-                            int32_t* items, int32_t* split_row, int32_t* split_ptr, int32_t* part_rel, void* stream);
+                            int32_t* class_hist, int32_t* items, int32_t* split_row, int32_t* split_ptr,
+                            int32_t* part_rel, int32_t* part_split, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Typed readout (kernel K4): dgl.readout.{sum,mean,max}_nodes(graph, 'h', ntype=)  pooling/*.py

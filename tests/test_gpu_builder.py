@@ -83,7 +83,7 @@ def test_hnsw_query_surface():
     assert list(one) == list(all_nbr[10])
 
 
-@pytest.mark.parametrize("seed,n,T,hub", [(0, 3000, 3, 0), (1, 500, 6, 300), (2, 70000, 2, 0)])
+@pytest.mark.parametrize("seed,n,T,hub", [(0, 3000, 3, 0), (1, 500, 6, 300), (2, 20000, 2, 0)])
 def test_native_plan_matches_host_plan(seed, n, T, hub):
     """wsi_plan_build_csr / wsi_plan_attn_work_* == the host (torch ops) statement of the same layout: bit-exact."""
     import torch
@@ -101,11 +101,17 @@ def test_native_plan_matches_host_plan(seed, n, T, hub):
     for chunk in (4, 16):
         wd, wh = dev.attn_work(chunk), host.attn_work(chunk)
         assert (wd["n_items"], wd["n_split"], wd["n_part"]) == (wh["n_items"], wh["n_split"], wh["n_part"])
-        assert torch.equal(wd["items"][:wd["n_items"]].cpu(), wh["items"])
+        di, hi = wd["items"][:wd["n_items"]].cpu(), wh["items"]
+        npart = wh["n_part"]
+        assert torch.equal(di[:npart], hi[:npart])                       # chunk items: edge order, exact
+        assert torch.equal(di[npart:, 2] - di[npart:, 1], hi[npart:, 2] - hi[npart:, 1])   # same size sequence
+        key = lambda x: x[torch.argsort(x[:, 0])]                        # order inside a size class is arbitrary
+        assert torch.equal(key(di[npart:]), key(hi[npart:]))
         if wh["n_split"]:
             assert torch.equal(wd["split_row"].cpu(), wh["split_row"])
             assert torch.equal(wd["split_ptr"].cpu(), wh["split_ptr"])
             assert torch.equal(wd["part_rel"].cpu(), wh["part_rel"])
+            assert torch.equal(wd["part_split"].cpu(), wh["part_split"])
     assert dev.max_in_degree == host.max_in_degree
 
 

@@ -179,6 +179,11 @@ def test_hetero_attn_fwd(D, H, perm):
     agg, attn = ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], c(rowptr, torch.int32),
                                 c(src, torch.int32), c(sim, torch.float32), c(rel, torch.uint8), inv_r.cuda(),
                                 torch.tensor([[ew]]).cuda(), torch.tensor([eb]).cuda(), D, H, perm, want_attn=True)
+    # without the attention output the lane-grouped layout takes the TMA-ring kernel (whole rows, hub of 150+ edges)
+    agg2 = ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], c(rowptr, torch.int32),
+                           c(src, torch.int32), c(sim, torch.float32), c(rel, torch.uint8), inv_r.cuda(),
+                           torch.tensor([[ew]]).cuda(), torch.tensor([eb]).cuda(), D, H, perm)
+    assert rel_ok(agg2, agg, 1e-5)
     agg = agg.cpu()
     if perm:
         un = torch.empty_like(agg)

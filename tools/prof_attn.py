@@ -10,9 +10,11 @@ plan = G.plan()
 kvq = torch.randn(N, 3 * D, device=dev)
 ew, eb = torch.ones(1, device=dev), torch.zeros(1, device=dev)
 use_perm = ops.head_perm(D, H) is not None
+work = plan.attn_work()
 for _ in range(5):
-    ops.hetero_attn(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
-                    plan.e_rel, plan.node_inv_r, ew, eb, D, H, use_perm)
+    kvq.add_(0.0)
+    ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, plan.e_src, plan.e_sim,
+                         plan.e_rel, plan.node_inv_r, ew, eb, D, H)
 torch.cuda.synchronize()
 deg = (plan.rowptr[1:] - plan.rowptr[:-1]).float()
 print("in-degree: mean %.2f max %d zero %d" % (deg.mean().item(), int(deg.max()), int((deg == 0).sum())))

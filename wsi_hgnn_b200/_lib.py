@@ -6,7 +6,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 6
+ABI_VERSION = 8
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -20,8 +20,8 @@ PROTOTYPES = {
     "wsi_typed_linear_workspace_bytes": (_L, [_L, _I, _I, _I, _I]),
     "wsi_typed_linear_f32": (_I, [_P, _L, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _I, _P, _L, _P]),
     "wsi_hetero_attn_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P, _P]),
-    "wsi_hetero_attn_work_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _P, _P, _L, _L,
-                                      _P, _P, _P, _L, _P, _P]),
+    "wsi_hetero_attn_work_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _P, _P, _P, _P,
+                                      _L, _L, _P, _P, _P, _L, _P, _P]),
     "wsi_typed_linear_tc_ok": (_I, [_L, _I, _I]),
     "wsi_split_bf16": (_I, [_P, _L, _L, _I, _P, _P]),
     "wsi_typed_linear_split": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _P]),
@@ -32,8 +32,8 @@ PROTOTYPES = {
     "wsi_typed_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _F, _P, _L, _P]),
     "wsi_plan_workspace_bytes": (_L, [_L, _L]),
     "wsi_plan_build_csr": (_I, [_P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
-    "wsi_plan_attn_work_count": (_I, [_P, _P, _L, _I, _P, _P, _P, _L, _P]),
-    "wsi_plan_attn_work_fill": (_I, [_P, _P, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "wsi_plan_attn_work_count": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),
+    "wsi_plan_attn_work_fill": (_I, [_P, _P, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P]),
     "wsi_segment_pool_workspace_bytes": (_L, [_L, _L, _I]),
     "wsi_segment_pool_fwd": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _L, _P, _L, _P]),
     "wsi_knn_workspace_bytes": (_L, [_L, _I, _I, _L, _L]),

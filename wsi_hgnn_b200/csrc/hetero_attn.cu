@@ -16,6 +16,8 @@
 //
 // HBM-bound: algorithmic bytes per edge = 2*D*4 (K and V rows) + 9 (src id, sim, relation slot);
 // per dst row = 2*D*4 (q in, agg out) + 8 (rowptr, 1/R).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -47,6 +49,9 @@ struct AttnArgs {
   float* part_acc;            // [P, D] unnormalised accumulator of partial slot p (physical column order)
   __nv_bfloat16* out_split;   // optional [2 * n_rows, D] bf16 (hi; lo) form of `out`: A operand of the a_linear GEMM
   int64_t split_lo;           // element offset of the lo half (n_rows * D)
+  // fused merge of the split rows (TMA kernel): split index of every partial, per-split-row arrival counter
+  const int* part_split; int* split_cnt;
+  const int* split_row; const int* split_ptr; const int* part_rel;
 };
 
 __device__ __forceinline__ void st_split4(__nv_bfloat16* dst, int64_t lo_off, float4 v) {
@@ -238,6 +243,8 @@ __global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 2) attn_fwd_vec_kern
 // Combine the chunk partials of the split rows (HEAT) / split segments (HGT): one warp per split row.
 //   split_row[h] = output row, split_ptr[h..h+1] = its partial slots (in edge order), part_rel[p] = relation slot
 //   of partial p (a new value closes the running segment).  out[row] = inv_r[row] * sum_segments acc / sum.
+// Runs either fused into the TMA kernel (the warp that finishes the LAST chunk of a row merges it: per-row arrival
+// counter split_cnt, self-resetting) or as its own launch after the register-path kernel.
 struct MergeArgs {
   const int* split_row; const int* split_ptr; const int* part_rel;
   const float* part_ms; const float* part_acc; const float* inv_r;
@@ -247,10 +254,8 @@ struct MergeArgs {
 };
 
 template <int NV>
-__global__ void __launch_bounds__(WARPS * 32) attn_merge_kernel(MergeArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int h = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (h >= a.n_split) return;
+__device__ __forceinline__ void merge_row(const MergeArgs& a, int h, int lane) {
+  constexpr int MB = 4;                                 // partials whose loads are in flight together
   const int row = __ldg(a.split_row + h);
   const int pb = __ldg(a.split_ptr + h), pe = __ldg(a.split_ptr + h + 1);
   const float invr = a.inv_r ? __ldg(a.inv_r + row) : 1.f;
@@ -259,34 +264,51 @@ __global__ void __launch_bounds__(WARPS * 32) attn_merge_kernel(MergeArgs a) {
   for (int i = 0; i < NV; ++i) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc[i] = out[i]; }
   float m = -INFINITY, ssum = 0.f;
   int cur_rel = -1;
-  for (int p = pb; p < pe; ++p) {
-    const int rel = __ldg(a.part_rel + p);
-    if (rel != cur_rel) {
-      if (cur_rel >= 0 && ssum > 0.f) {
-        const float inv = 1.f / ssum;
+  for (int p0 = pb; p0 < pe; p0 += MB) {
+    const int nb = min(MB, pe - p0);
+    int rl[MB];
+    float mp[MB], sp[MB];
+    float4 x[MB][NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
-          out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
+    for (int u = 0; u < MB; ++u) {
+      if (u < nb) {                                     // partials were written by this kernel: L2-coherent loads
+        const int p = p0 + u;
+        rl[u] = __ldg(a.part_rel + p);
+        mp[u] = __ldcg(a.part_ms + (int64_t)p * 64 + lane);
+        sp[u] = __ldcg(a.part_ms + (int64_t)p * 64 + 32 + lane);
+        const float* pa = a.part_acc + (int64_t)p * a.D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) x[u][i] = __ldcg(reinterpret_cast<const float4*>(pa + (i * 32 + lane) * 4));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < MB; ++u) {
+      if (u < nb) {
+        if (rl[u] != cur_rel) {
+          if (cur_rel >= 0 && ssum > 0.f) {
+            const float inv = 1.f / ssum;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
+              out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          m = -INFINITY; ssum = 0.f; cur_rel = rl[u];
+        }
+        if (sp[u] > 0.f) {                              // (an untouched partial has sum 0: passthrough row)
+          const float mn = fmaxf(m, mp[u]);
+          const float c0 = __expf(m - mn), c1 = __expf(mp[u] - mn);
+          ssum = fmaf(ssum, c0, sp[u] * c1);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            acc[i].x = fmaf(acc[i].x, c0, x[u][i].x * c1); acc[i].y = fmaf(acc[i].y, c0, x[u][i].y * c1);
+            acc[i].z = fmaf(acc[i].z, c0, x[u][i].z * c1); acc[i].w = fmaf(acc[i].w, c0, x[u][i].w * c1);
+          }
+          m = mn;
         }
       }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      m = -INFINITY; ssum = 0.f; cur_rel = rel;
-    }
-    const float mp = __ldg(a.part_ms + (int64_t)p * 64 + lane), sp = __ldg(a.part_ms + (int64_t)p * 64 + 32 + lane);
-    if (sp > 0.f) {                                     // (an untouched partial has sum 0: passthrough row)
-      const float mn = fmaxf(m, mp);
-      const float c0 = __expf(m - mn), c1 = __expf(mp - mn);
-      ssum = fmaf(ssum, c0, sp * c1);
-      const float* pa = a.part_acc + (int64_t)p * a.D;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 x = ld4(pa + (i * 32 + lane) * 4);
-        acc[i].x = fmaf(acc[i].x, c0, x.x * c1); acc[i].y = fmaf(acc[i].y, c0, x.y * c1);
-        acc[i].z = fmaf(acc[i].z, c0, x.z * c1); acc[i].w = fmaf(acc[i].w, c0, x.w * c1);
-      }
-      m = mn;
     }
   }
   if (cur_rel >= 0 && ssum > 0.f) {
@@ -302,6 +324,258 @@ __global__ void __launch_bounds__(WARPS * 32) attn_merge_kernel(MergeArgs a) {
     const float4 r = make_float4(out[i].x * invr, out[i].y * invr, out[i].z * invr, out[i].w * invr);
     if (a.out) *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + (i * 32 + lane) * 4) = r;
     if (a.out_split) st_split4(a.out_split + (int64_t)row * a.D + (i * 32 + lane) * 4, a.split_lo, r);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32) attn_merge_kernel(MergeArgs a) {
+  const int h = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (h < a.n_split) merge_row<NV>(a, h, threadIdx.x & 31);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant of the fast path (the one the forward uses): every warp owns a ring of shared-memory slots, one
+// slot = the K row and the V row of one edge (2 * D * 4 bytes), filled by cp.async.bulk (the TMA engine's 1-D bulk
+// copy, SASS UBLKCP) and signalled through one mbarrier per slot.  All edges of a work item (up to the ring depth) are
+// in flight at once while the registers only hold q / acc / out - the gather no longer waits one L2 round trip per
+// group of edges, and 8 warps x ring x 4 KB = 192 KB per SM are in flight.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int TMA_WARPS = 4;
+constexpr int BMAX = 4;      // edges per batch of the TMA kernel
+
+template <int NV, int MODE>
+__global__ void __launch_bounds__(TMA_WARPS * 32) attn_fwd_tma_kernel(AttnArgs a, int ring) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int ROW_BYTES = NV * 512, SLOT_BYTES = 2 * ROW_BYTES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = 32 / a.H;
+  const int head = lane / G;
+  const int n_warps = gridDim.x * TMA_WARPS;
+  uint8_t* my_slots = smem + (size_t)warp * ring * SLOT_BYTES;
+  const uint32_t slots_u32 = smem_u32(my_slots);
+  const uint32_t bars_u32 = smem_u32(smem + (size_t)TMA_WARPS * ring * SLOT_BYTES) + warp * ring * 8;
+  if (lane == 0) {
+    for (int s = 0; s < ring; ++s) mbar_init(bars_u32 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float ew = 0.f, eb = 0.f;
+  if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
+  int rs = 0;                 // ring slot of the next edge to consume
+  uint32_t rpar = 0;          // its mbarrier phase parity
+
+  for (int item = blockIdx.x * TMA_WARPS + warp; item < a.n_items; item += n_warps) {
+    int row = item, beg, end, slot = -1;
+    if (a.items) {
+      const int4 it = __ldg(a.items + item);
+      row = it.x; beg = it.y; end = it.z; slot = it.w;
+    } else {
+      beg = __ldg(a.rowptr + item); end = __ldg(a.rowptr + item + 1);
+    }
+    float4 out[NV], acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc[i] = out[i]; }
+    float invr = 1.f, seg_scale = 0.f;
+    if (MODE == MODE_HEAT) invr = __ldg(a.inv_r + row);
+    else seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + row) * a.H + head) * a.inv_sqrt_dk;
+    float m = -INFINITY, ssum = 0.f;
+
+    if (invr != 0.f && end > beg) {
+      int cur_rel = -1;
+      // the first window's edge ids first: their K/V rows are requested before q is even loaded
+      float4 q[NV];
+      bool have_q = false;
+      for (int base = beg; base < end; base += 32) {
+        const int n = min(32, end - base);
+        int my_src = 0, my_rel = 0;
+        float my_sim = 0.f;
+        if (lane < n) {
+          my_src = __ldg(a.e_src + base + lane);
+          if (MODE == MODE_HEAT) { my_sim = __ldg(a.e_sim + base + lane); my_rel = __ldg(a.e_rel + base + lane); }
+        }
+        const int pre = min(n, ring);
+        {
+          int s = rs;
+          for (int j = 0; j < pre; ++j) {
+            const int src = __shfl_sync(FULL, my_src, j);
+            if (lane == 0) {
+              const uint32_t bar = bars_u32 + 8 * s, dst = slots_u32 + s * SLOT_BYTES;
+              mbar_expect_tx(bar, SLOT_BYTES);
+              bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
+              bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+            }
+            if (++s == ring) s = 0;
+          }
+        }
+        if (!have_q) {
+          const float* qr = a.Q + (int64_t)row * a.ldq;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) q[i] = ld4(qr + (i * 32 + lane) * 4);
+          have_q = true;
+        }
+        // edges are consumed in batches of up to BMAX (same relation): all scores first (independent dot products),
+        // one rescale of the accumulator per batch, then the weighted V rows
+        int j = 0;
+        while (j < n) {
+          int g = min(min(BMAX, ring), n - j);
+          if (MODE == MODE_HEAT) {
+            const int rel = __shfl_sync(FULL, my_rel, j);
+            const unsigned same = __ballot_sync(FULL, lane >= j && lane < n && my_rel == rel) >> j;
+            g = min(g, same == FULL ? 32 : __ffs(~same) - 1);        // (__ffs(0) == 0)
+            if (rel != cur_rel) {                       // warp-uniform: close the running segment
+              if (cur_rel >= 0) {
+                const float inv = 1.f / ssum;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                  out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
+                  out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
+                  acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              }
+              m = -INFINITY; ssum = 0.f; cur_rel = rel;
+            }
+          }
+          float sc[BMAX];
+          const float* slot_ptr[BMAX];
+#pragma unroll
+          for (int u = 0; u < BMAX; ++u) {
+            sc[u] = -INFINITY;
+            slot_ptr[u] = nullptr;
+            if (u < g) {
+              int su = rs + u;
+              uint32_t pu = rpar;
+              if (su >= ring) { su -= ring; pu ^= 1; }
+              mbar_wait(bars_u32 + 8 * su, pu);
+              const float* ks = reinterpret_cast<const float*>(my_slots + (size_t)su * SLOT_BYTES);
+              slot_ptr[u] = ks;
+              float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < NV; ++i) {
+                const float4 kk = *reinterpret_cast<const float4*>(ks + (i * 32 + lane) * 4);
+                d0 = fmaf(q[i].x, kk.x, d0); d1 = fmaf(q[i].y, kk.y, d1);
+                d0 = fmaf(q[i].z, kk.z, d0); d1 = fmaf(q[i].w, kk.w, d1);
+              }
+              sc[u] = d0 + d1;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < BMAX; ++u) {
+            if (u < g) {
+              float d = sc[u];
+              for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+              float scale = seg_scale;
+              if (MODE == MODE_HEAT) scale = fmaf(ew, __shfl_sync(FULL, my_sim, j + u), eb) * a.inv_sqrt_dk;
+              sc[u] = d * scale;
+            }
+          }
+          float mn = m;
+#pragma unroll
+          for (int u = 0; u < BMAX; ++u) mn = fmaxf(mn, sc[u]);
+          const float corr = __expf(m - mn);            // m = -inf on the first batch -> 0
+          float p[BMAX], psum = 0.f;
+#pragma unroll
+          for (int u = 0; u < BMAX; ++u) { p[u] = __expf(sc[u] - mn); psum += p[u]; }   // exp(-inf) = 0 for u >= g
+          ssum = fmaf(ssum, corr, psum);
+          m = mn;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr; }
+#pragma unroll
+          for (int u = 0; u < BMAX; ++u) {
+            if (u < g) {
+              const float* vs = slot_ptr[u] + NV * 128;
+#pragma unroll
+              for (int i = 0; i < NV; ++i) {
+                const float4 vv = *reinterpret_cast<const float4*>(vs + (i * 32 + lane) * 4);
+                acc[i].x = fmaf(p[u], vv.x, acc[i].x); acc[i].y = fmaf(p[u], vv.y, acc[i].y);
+                acc[i].z = fmaf(p[u], vv.z, acc[i].z); acc[i].w = fmaf(p[u], vv.w, acc[i].w);
+              }
+            }
+          }
+          __syncwarp();                                 // every lane is done with these g slots
+          for (int u = 0; u < g; ++u) {                 // refill them with the edges `ring` positions ahead
+            const int nxt = j + u + ring;
+            const int src = __shfl_sync(FULL, my_src, nxt & 31);
+            if (nxt < n && lane == 0) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              const uint32_t bar = bars_u32 + 8 * rs, dst = slots_u32 + rs * SLOT_BYTES;
+              mbar_expect_tx(bar, SLOT_BYTES);
+              bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
+              bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+            }
+            if (++rs == ring) { rs = 0; rpar ^= 1; }
+          }
+          j += g;
+        }
+      }
+      if (slot < 0) {                                   // close the last segment
+        const float inv = 1.f / ssum;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          out[i].x = fmaf(acc[i].x, inv, out[i].x) * invr; out[i].y = fmaf(acc[i].y, inv, out[i].y) * invr;
+          out[i].z = fmaf(acc[i].z, inv, out[i].z) * invr; out[i].w = fmaf(acc[i].w, inv, out[i].w) * invr;
+        }
+      }
+    }
+    if (slot < 0) {
+      if (a.out) {
+        float* o = a.out + (int64_t)row * a.ldo;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
+      }
+      if (a.out_split) {
+        __nv_bfloat16* o = a.out_split + (int64_t)row * a.D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) st_split4(o + (i * 32 + lane) * 4, a.split_lo, out[i]);
+      }
+    } else {                                            // partial of one segment chunk: (m, sum, unnormalised acc)
+      a.part_ms[(int64_t)slot * 64 + lane] = m;
+      a.part_ms[(int64_t)slot * 64 + 32 + lane] = ssum;
+      float* o = a.part_acc + (int64_t)slot * a.D;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = acc[i];
+      if (a.split_cnt) {                                // the warp that completes the row's last chunk merges it
+        const int h = __ldg(a.part_split + slot);
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          const int n_chunks = __ldg(a.split_ptr + h + 1) - __ldg(a.split_ptr + h);
+          last = atomicAdd(a.split_cnt + h, 1) == n_chunks - 1;
+          if (last) a.split_cnt[h] = 0;                 // self-resetting: ready for the next launch
+        }
+        last = __shfl_sync(FULL, last, 0);
+        if (last) {
+          __threadfence();
+          MergeArgs mg;
+          mg.split_row = a.split_row; mg.split_ptr = a.split_ptr; mg.part_rel = a.part_rel;
+          mg.part_ms = a.part_ms; mg.part_acc = a.part_acc; mg.inv_r = a.inv_r; mg.n_split = 0; mg.D = a.D;
+          mg.out = a.out; mg.ldo = a.ldo; mg.out_split = a.out_split; mg.split_lo = a.split_lo;
+          merge_row<NV>(mg, h, lane);
+        }
+      }
+    }
   }
 }
 
@@ -403,8 +677,11 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_generic_kernel(AttnArgs a
 
 bool vec_ok(int D, int H) { return D % 128 == 0 && D <= 1024 && H >= 1 && H <= 32 && (H & (H - 1)) == 0; }
 
+// *fused_merge (optional): set to true when the launched kernel merges the split rows itself
 template <int MODE>
-int launch(const AttnArgs& a, int head_perm, cudaStream_t stream) {
+int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused_merge = nullptr) {
+  AttnArgs a = a_in;
+  if (fused_merge) *fused_merge = false;
   if (a.n_items == 0) return WSI_OK;
   int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
@@ -416,6 +693,27 @@ int launch(const AttnArgs& a, int head_perm, cudaStream_t stream) {
       wsi_set_error("hetero_attn: head_perm layout needs D %% 128 == 0, D <= 1024, H a power of two <= 32 (D=%d H=%d)", a.D, a.H);
       return WSI_ERR_UNSUPPORTED;
     }
+    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && !getenv("WSI_ATTN_NO_TMA")) {
+      // TMA-staged ring: ~24 KB of K/V rows in flight per warp, 2 blocks of 4 warps per SM
+      const int slot_bytes = 2 * a.D * 4;
+      int ring = 24576 / slot_bytes;
+      ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
+      const int smem = TMA_WARPS * ring * slot_bytes + TMA_WARPS * ring * 8;
+      int tb = (a.n_items + TMA_WARPS - 1) / TMA_WARPS;
+      if (tb > sms * 2) tb = sms * 2;
+      switch (a.D / 128) {
+#define CASE(NV) case NV: { \
+        static bool attr_set = false; \
+        if (!attr_set) { WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; } \
+        attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+      }
+      WSI_CHECK_LAUNCH();
+      if (fused_merge) *fused_merge = a.split_cnt != nullptr;
+      return WSI_OK;
+    }
+    a.split_cnt = nullptr;                              // register-path kernel: the caller launches the merge
     switch (a.D / 128) {
 #define CASE(NV) case NV: attn_fwd_vec_kernel<NV, MODE><<<blocks, WARPS * 32, 0, stream>>>(a); break;
       CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
@@ -492,8 +790,9 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
                                         const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows,
                                         int D, int H, const int32_t* items, int64_t n_items,
                                         const int32_t* split_row, const int32_t* split_ptr, const int32_t* part_rel,
-                                        int64_t n_split, int64_t n_part, float* part_ms, float* part_acc, float* agg,
-                                        int64_t ldo, void* agg_split, void* stream) {
+                                        const int32_t* part_split, int32_t* split_cnt, int64_t n_split,
+                                        int64_t n_part, float* part_ms, float* part_acc, float* agg, int64_t ldo,
+                                        void* agg_split, void* stream) {
   WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && n_items >= 0 && n_items < (1ll << 31), "hetero_attn_work_fwd: bad sizes");
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(k && v && q && node_inv_r && e_w && e_b && (agg || agg_split) && items, "hetero_attn_work_fwd: null pointer");
@@ -504,6 +803,7 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
                 "hetero_attn_work_fwd: row strides must be multiples of 4 floats");
   WSI_CHECK_ARG(n_split == 0 || (split_row && split_ptr && part_rel && part_ms && part_acc && n_part > 0),
                 "hetero_attn_work_fwd: split rows need the partial buffers");
+  WSI_CHECK_ARG(!split_cnt || part_split, "hetero_attn_work_fwd: split_cnt needs part_split");
   AttnArgs a{};
   a.K = k; a.ldk = ldk; a.V = v; a.ldv = ldv; a.Q = q; a.ldq = ldq;
   a.e_src = e_src; a.e_sim = e_sim; a.e_rel = e_rel; a.inv_r = node_inv_r;
@@ -512,8 +812,13 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
   a.out = agg; a.ldo = ldo; a.attn = nullptr;
   a.items = reinterpret_cast<const int4*>(items); a.part_ms = part_ms; a.part_acc = part_acc;
   a.out_split = reinterpret_cast<__nv_bfloat16*>(agg_split); a.split_lo = n_rows * D;
-  int rc = launch<MODE_HEAT>(a, 1, wsi_stream(stream));
-  if (rc != WSI_OK) return rc;
+  if (n_split > 0 && split_cnt) {
+    a.part_split = part_split; a.split_cnt = split_cnt;
+    a.split_row = split_row; a.split_ptr = split_ptr; a.part_rel = part_rel;
+  }
+  bool fused = false;
+  int rc = launch<MODE_HEAT>(a, 1, wsi_stream(stream), &fused);
+  if (rc != WSI_OK || fused) return rc;
   MergeArgs m{};
   m.split_row = split_row; m.split_ptr = split_ptr; m.part_rel = part_rel; m.part_ms = part_ms; m.part_acc = part_acc;
   m.inv_r = node_inv_r; m.n_split = (int)n_split; m.D = D; m.out = agg; m.ldo = ldo;

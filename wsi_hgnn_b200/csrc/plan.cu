@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(256) csr_emit_kernel(const int64_t* src, const
 
 // ---------------------------------------------------------------------------------------------- attention work list
 // chunks of a split row = sum over its (row, relation) segments of ceil(len / chunk); 0 for rows with <= chunk edges
+// class_hist int32 [2 * (chunk + 1)]: [0, chunk] = number of whole-row items with chunk - c edges (largest first);
+// the second half is the fill cursor of each class (zeroed here, used by work_fill_kernel)
 __global__ void __launch_bounds__(256) work_count_kernel(const int* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
-                                                         int* row_chunks, int* row_split) {
+                                                         int* row_chunks, int* row_split, int* class_hist) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_nodes) return;
   const int beg = rowptr[row], end = rowptr[row + 1];
@@ -177,19 +179,27 @@ __global__ void __launch_bounds__(256) work_count_kernel(const int* rowptr, cons
   }
   row_chunks[row] = chunks;
   row_split[row] = chunks > 0;
+  if (chunks == 0) atomicAdd(class_hist + (chunk - (end - beg)), 1);
 }
 
 __global__ void __launch_bounds__(256) work_fill_kernel(const int* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
                                                         const int* chunk_base, const int* split_idx, int n_part,
-                                                        int n_split, int4* items, int* split_row, int* split_ptr,
-                                                        int* part_rel) {
+                                                        int n_split, int* class_hist, int4* items, int* split_row,
+                                                        int* split_ptr, int* part_rel, int* part_split) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row == 0 && n_split >= 0) split_ptr[n_split] = n_part;
   if (row >= n_nodes) return;
   const int beg = rowptr[row], end = rowptr[row + 1];
   const int si = split_idx[row];
-  if (end - beg <= chunk) {                               // whole row: after the chunk items, in row order
-    items[n_part + (int)row - si] = make_int4((int)row, beg, end, -1);
+  if (end - beg <= chunk) {
+    // whole row: after the chunk items, LARGEST FIRST (the kernel deals items to its warps round-robin, so a
+    // size-sorted list balances them).  The order inside a size class is arbitrary (atomic cursor): it only
+    // decides which warp runs the item, never a result.
+    const int c = chunk - (end - beg);
+    int base = n_part;
+    for (int i = 0; i < c; ++i) base += class_hist[i];
+    const int pos = base + atomicAdd(class_hist + (chunk + 1) + c, 1);
+    items[pos] = make_int4((int)row, beg, end, -1);
     return;
   }
   int slot = chunk_base[row];
@@ -203,6 +213,7 @@ __global__ void __launch_bounds__(256) work_fill_kernel(const int* rowptr, const
     for (int c = e; c < seg_end; c += chunk) {
       items[slot] = make_int4((int)row, c, min(c + chunk, seg_end), slot);
       part_rel[slot] = rel;
+      if (part_split) part_split[slot] = si;
       ++slot;
     }
     e = seg_end;
@@ -257,18 +268,19 @@ extern "C" int wsi_plan_build_csr(const int64_t* src, const int64_t* dst, const 
 // Phase 1: per-row chunk counts and their scans.  chunk_base / split_idx int32 [N + 1] (exclusive scans; the last
 // entries are n_part and n_split - read them on the host to size the buffers of phase 2).
 extern "C" int wsi_plan_attn_work_count(const int32_t* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
-                                        int32_t* chunk_base, int32_t* split_idx, void* workspace, int64_t workspace_bytes,
-                                        void* stream_) {
+                                        int32_t* chunk_base, int32_t* split_idx, int32_t* class_hist, void* workspace,
+                                        int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = wsi_stream(stream_);
-  WSI_CHECK_ARG(n_nodes >= 0 && n_nodes < (1ll << 31) && chunk >= 1, "plan_attn_work_count: bad sizes");
-  WSI_CHECK_ARG(rowptr && chunk_base && split_idx, "plan_attn_work_count: null pointer");
+  WSI_CHECK_ARG(n_nodes >= 0 && n_nodes < (1ll << 31) && chunk >= 1 && chunk <= 255, "plan_attn_work_count: bad sizes (1 <= chunk <= 255)");
+  WSI_CHECK_ARG(rowptr && chunk_base && split_idx && class_hist, "plan_attn_work_count: null pointer");
+  WSI_CHECK_CUDA(cudaMemsetAsync(class_hist, 0, 2 * (chunk + 1) * sizeof(int), stream));
   WSI_CHECK_ARG(workspace_bytes >= wsi_plan_workspace_bytes(n_nodes, 0) && workspace, "plan_attn_work_count: workspace too small");
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   int* row_chunks = reinterpret_cast<int*>(ws);
   int* row_split = reinterpret_cast<int*>(ws + align256((n_nodes + 1) * 4));
   int* tile_sums = reinterpret_cast<int*>(ws + 2 * align256((n_nodes + 1) * 4));
   if (n_nodes > 0) {
-    work_count_kernel<<<(int)((n_nodes + 255) / 256), 256, 0, stream>>>(rowptr, e_rel, n_nodes, chunk, row_chunks, row_split);
+    work_count_kernel<<<(int)((n_nodes + 255) / 256), 256, 0, stream>>>(rowptr, e_rel, n_nodes, chunk, row_chunks, row_split, class_hist);
     WSI_CHECK_LAUNCH();
   }
   int rc = exclusive_scan(row_chunks, n_nodes, chunk_base, tile_sums, stream);
@@ -279,17 +291,17 @@ extern "C" int wsi_plan_attn_work_count(const int32_t* rowptr, const uint8_t* e_
 // Phase 2: items int32 [n_part + (N - n_split), 4], split_row [n_split], split_ptr [n_split + 1], part_rel [n_part]
 extern "C" int wsi_plan_attn_work_fill(const int32_t* rowptr, const uint8_t* e_rel, int64_t n_nodes, int chunk,
                                        const int32_t* chunk_base, const int32_t* split_idx, int64_t n_part,
-                                       int64_t n_split, int32_t* items, int32_t* split_row, int32_t* split_ptr,
-                                       int32_t* part_rel, void* stream_) {
+                                       int64_t n_split, int32_t* class_hist, int32_t* items, int32_t* split_row,
+                                       int32_t* split_ptr, int32_t* part_rel, int32_t* part_split, void* stream_) {
   cudaStream_t stream = wsi_stream(stream_);
   WSI_CHECK_ARG(n_nodes >= 0 && n_nodes < (1ll << 31) && chunk >= 1 && n_part >= 0 && n_split >= 0, "plan_attn_work_fill: bad sizes");
   if (n_nodes == 0) return WSI_OK;
-  WSI_CHECK_ARG(rowptr && chunk_base && split_idx && items && split_ptr, "plan_attn_work_fill: null pointer");
+  WSI_CHECK_ARG(rowptr && chunk_base && split_idx && items && split_ptr && class_hist, "plan_attn_work_fill: null pointer");
   WSI_CHECK_ARG(n_split == 0 || (split_row && part_rel), "plan_attn_work_fill: null pointer");
   work_fill_kernel<<<(int)((n_nodes + 255) / 256), 256, 0, stream>>>(rowptr, e_rel, n_nodes, chunk, chunk_base, split_idx,
-                                                                    (int)n_part, (int)n_split,
+                                                                    (int)n_part, (int)n_split, class_hist,
                                                                     reinterpret_cast<int4*>(items), split_row, split_ptr,
-                                                                    part_rel);
+                                                                    part_rel, part_split);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }

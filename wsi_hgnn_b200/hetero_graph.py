@@ -250,8 +250,8 @@ class GraphPlan:
     def attn_work(self, chunk: int = 16):
         """Work list of the edge-attention kernel (wsi_hetero_attn_work_fwd): rows with at most `chunk`
         in-edges are one item; rows with more (k-NN hubs) are cut, per (row, relation) segment, into chunks
-        of <= `chunk` edges whose partials a merge launch combines.  The chunk items come first (they are the
-        largest).  dict: items int32 [n_items, 4], n_items, split_row, split_ptr, part_rel, n_split, n_part."""
+        of <= `chunk` edges whose partials a merge launch combines.  The chunk items come first, then the
+        whole rows sorted by edge count, largest first (the kernel deals items to warps round-robin).  dict: items int32 [n_items, 4], n_items, split_row, split_ptr, part_rel, n_split, n_part."""
         key = ("attn_work", chunk)
         if key in self.cache:
             return self.cache[key]
@@ -271,6 +271,7 @@ class GraphPlan:
         deg = rowptr[1:] - rowptr[:-1]
         split = deg > chunk
         rows_c = torch.nonzero(~split).reshape(-1)
+        rows_c = rows_c[torch.argsort(deg[rows_c], descending=True, stable=True)]     # largest first
         items_c = torch.stack([rows_c, rowptr[rows_c], rowptr[rows_c + 1], torch.full_like(rows_c, -1)], 1)
         n_split = int(split.sum()) if self.N > 0 else 0
         if n_split == 0:
@@ -299,9 +300,11 @@ class GraphPlan:
         split_ptr = torch.zeros(n_split + 1, dtype=torch.int64, device=dev)
         split_ptr[1:] = torch.cumsum(per_row[split_row], 0)
         items = torch.cat([items_p, items_c], 0).to(torch.int32).contiguous()
+        part_split = torch.repeat_interleave(torch.arange(n_split, device=dev), per_row[split_row])
         work = dict(items=items, n_items=int(items.shape[0]), split_row=split_row.to(torch.int32).contiguous(),
                     split_ptr=split_ptr.to(torch.int32).contiguous(), part_rel=part_rel, n_split=n_split,
-                    n_part=n_part)
+                    n_part=n_part, part_split=part_split.to(torch.int32).contiguous(),
+                    split_cnt=torch.zeros(n_split, dtype=torch.int32, device=dev))
         self.cache[key] = work
         return work
 

@@ -204,7 +204,9 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
                                       _vec(work["items"], "items", torch.int32), work["n_items"],
                                       _vec(work["split_row"], "split_row", torch.int32),
                                       _vec(work["split_ptr"], "split_ptr", torch.int32),
-                                      _vec(work["part_rel"], "part_rel", torch.int32), n_split, n_part,
+                                      _vec(work["part_rel"], "part_rel", torch.int32),
+                                      _vec(work.get("part_split"), "part_split", torch.int32),
+                                      _vec(work.get("split_cnt"), "split_cnt", torch.int32), n_split, n_part,
                                       part_ms.data_ptr() if part_ms is not None else None,
                                       part_acc.data_ptr() if part_acc is not None else None, ap, ldo,
                                       agg_split.data_ptr() if agg_split is not None else None, stream)
@@ -329,11 +331,13 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
     dev = rowptr.device
     i32 = dict(dtype=torch.int32, device=dev)
     scans = torch.empty((2, n_nodes + 1), **i32)
+    hist = torch.empty(2 * (chunk + 1), **i32)
     ws_bytes = lib.wsi_plan_workspace_bytes(n_nodes, 0)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rp, rl = _vec(rowptr, "rowptr", torch.int32), _vec(e_rel, "e_rel", torch.uint8)
     _lib.check(lib.wsi_plan_attn_work_count(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(),
-                                            ws.data_ptr(), ws_bytes, stream), "wsi_plan_attn_work_count")
+                                            hist.data_ptr(), ws.data_ptr(), ws_bytes, stream),
+               "wsi_plan_attn_work_count")
     if stats is not None:                                             # the one host sync (totals + builder flags)
         n_part, n_split, max_deg, bad = torch.cat([scans[:, n_nodes], stats[:2]]).tolist()
     else:
@@ -343,10 +347,14 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
     split_row = torch.empty(max(n_split, 1), **i32)
     split_ptr = torch.empty(n_split + 1, **i32)
     part_rel = torch.empty(max(n_part, 1), **i32)
+    part_split = torch.empty(max(n_part, 1), **i32)
+    split_cnt = torch.zeros(max(n_split, 1), **i32)                  # arrival counters of the fused merge (self-resetting)
     _lib.check(lib.wsi_plan_attn_work_fill(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(), n_part,
-                                           n_split, items.data_ptr(), split_row.data_ptr(), split_ptr.data_ptr(),
-                                           part_rel.data_ptr(), stream), "wsi_plan_attn_work_fill")
+                                           n_split, hist.data_ptr(), items.data_ptr(), split_row.data_ptr(),
+                                           split_ptr.data_ptr(), part_rel.data_ptr(), part_split.data_ptr(), stream),
+               "wsi_plan_attn_work_fill")
     return dict(items=items, n_items=n_items, split_row=split_row, split_ptr=split_ptr, part_rel=part_rel,
+                part_split=part_split, split_cnt=split_cnt,
                 n_split=n_split, n_part=n_part, max_in_degree=max_deg, bad_edges=bool(bad))
 
 
