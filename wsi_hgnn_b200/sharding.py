@@ -1,0 +1,55 @@
+"""Data-parallel sharding of slides over the GPUs of one box.
+
+Slides are independent units - the reference itself treats a hetero batch as independent per-graph forwards
+(trainer/train_gnn.py:59-62) - so the forward needs NO data-path collective: every rank (one process per GPU) runs
+the slides it owns and the logits are gathered once at the end.  Slide sizes vary by 10x (2k-20k nodes), so the
+assignment is greedy longest-processing-time on the edge count, not round-robin on the slide count.
+"""
+from typing import List, Sequence
+
+import torch
+
+
+def lpt_assign(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Greedy LPT: slides in decreasing cost order, each to the currently lightest rank.
+    -> per-rank lists of slide indices (each list in increasing index order).  Deterministic."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * world
+    owned: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owned[r].append(i)
+        load[r] += float(costs[i])
+    return [sorted(o) for o in owned]
+
+
+def shard_slides(graphs: Sequence, rank: int, world: int):
+    """(indices, graphs) of the slides rank `rank` owns; cost = number of edges (+ nodes, for edge-free slides)."""
+    costs = [g.num_edges() + 0.1 * g.num_nodes() for g in graphs]
+    mine = lpt_assign(costs, world)[rank]
+    return mine, [graphs[i] for i in mine]
+
+
+def gather_logits(local: torch.Tensor, mine: Sequence[int], n_total: int, group=None) -> torch.Tensor:
+    """All ranks' per-slide logits [len(mine), C] -> [n_total, C] in the original slide order, on every rank.
+    One all_gather of a padded block (the only collective of the inference path)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    C = int(local.shape[1]) if local.dim() == 2 else 0
+    cnt = torch.tensor([len(mine)], dtype=torch.int64, device=local.device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    mx = int(max(int(c) for c in cnts))
+    pad = torch.zeros((mx, C + 1), dtype=local.dtype, device=local.device)
+    pad[:len(mine), :C] = local
+    pad[:len(mine), C] = torch.tensor(list(mine), dtype=local.dtype, device=local.device)      # slide index rides along
+    blocks = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(blocks, pad, group=group)
+    out = torch.zeros((n_total, C), dtype=local.dtype, device=local.device)
+    for b, c in zip(blocks, cnts):
+        k = int(c)
+        if k:
+            out[b[:k, C].round().to(torch.int64)] = b[:k, :C]
+    return out
