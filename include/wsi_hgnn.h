@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 8
+#define WSI_ABI_VERSION 9
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -205,6 +205,19 @@ int64_t wsi_segment_pool_workspace_bytes(int64_t n_rows, int64_t n_seg, int D);
 int wsi_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, int64_t n_seg, int64_t n_rows,
                          int D, int op, float* out, int64_t ldo, void* workspace, int64_t workspace_bytes,
                          void* stream);
+
+/* Typed readout fused with the (narrow, affine) prediction that follows it:
+ *   out[b, o] (+)= b_total[o] + sum_t seg_scale[t*B + b] * ( <M[t, o, :], pool(x rows of segment t*B + b)> + c[t, o] )
+ * covers models/HEATNet2.py:181-194 (M = linears_prediction weights), the per-layer readout of models/HGT.py:189-199
+ * (accumulate != 0) and, for inference, models/HEATNet4.py:216-245 whose linears_prediction -> cat -> head_2 ->
+ * head_1 -> head chain has no nonlinearity and is collapsed on the host into one [out, D] map per node type.
+ *   seg_ptr int32 [T*B + 1] type-major segments; M [T, n_out, D]; c [T, n_out] or NULL; b_total [n_out] or NULL;
+ *   seg_scale [T*B] or NULL (0 => the reference's zero block for an empty node type); 1 <= n_out <= 8. */
+int64_t wsi_segment_pool_affine_workspace_bytes(int64_t n_rows, int64_t n_seg, int D);
+int wsi_segment_pool_affine_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, int T, int B, int64_t n_rows, int D,
+                                int op, const float* M, const float* c, const float* b_total, const float* seg_scale,
+                                int n_out, int accumulate, float* out, int64_t ldo, void* workspace,
+                                int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Edge builder (kernels K6/K7): construct_graph/graph_constructor.py:256-303.

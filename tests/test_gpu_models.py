@@ -78,6 +78,21 @@ def test_config3_shape_hgt(hidden, heads):
     _check(ours, orc, pack(gs), embeddings=False)
 
 
+def test_heatnet4_explicit_heads_equal_collapsed_readout():
+    """The collapsed affine readout (one fused launch pair) == the explicit linears_prediction / head_2 / head_1 / head
+    GEMM chain of models/HEATNet4.py:216-245, on a batch with an empty node type."""
+    gs = [synthetic.random_hetero_graph([40, 0, 20], 300, 32, seed=s) for s in (1, 2)] + \
+         [synthetic.random_hetero_graph([30, 25, 20], 300, 32, seed=3)]
+    ours, orc = _pair("HEATNet4", 3, dict(in_dim=32, hidden_dim=128, out_dim=2, n_layers=1, n_heads=4, dropuout=0.0))
+    G = pack(gs)
+    with torch.no_grad():
+        a = ours(G.to("cuda"))
+        ours.explicit_heads = True
+        b = ours(G.to("cuda"))
+    assert helpers.rel_err(a, b) < 1e-5
+    assert helpers.rel_err(a, helpers.run_oracle(orc, G, independent=True)) < TOL
+
+
 def test_batch_equals_cat_of_forwards():
     gs = [synthetic.random_hetero_graph([40, 30, 20], 500, 32, seed=s) for s in (1, 2, 3)]
     ours, _ = _pair("HEATNet4", 3, dict(in_dim=32, hidden_dim=128, out_dim=2, n_layers=2, n_heads=4, dropuout=0.0))

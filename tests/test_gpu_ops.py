@@ -259,6 +259,31 @@ def test_segment_pool(op, D):
     assert rel(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("op", ["sum", "mean", "max"])
+@pytest.mark.parametrize("T,B,D,n_out", [(3, 1, 512, 2), (2, 5, 200, 8), (6, 3, 128, 1)])
+def test_segment_pool_affine(op, T, B, D, n_out):
+    """fused typed readout + narrow affine prediction == pool, per-type linear, sum over types."""
+    g = torch.Generator().manual_seed(T * 100 + B * 10 + n_out)
+    lens = torch.randint(0, 400, (T * B,), generator=g)
+    lens[1 % (T * B)] = 0                                   # an empty (type, graph) segment
+    lens[0] = 5000                                          # one long segment (several row slabs)
+    ptr = torch.zeros(T * B + 1, dtype=torch.int64)
+    ptr[1:] = torch.cumsum(lens, 0)
+    x = torch.randn(int(ptr[-1]), D, generator=g)
+    M = torch.randn(T, n_out, D, generator=g) / math.sqrt(D)
+    c = torch.randn(T, n_out, generator=g)
+    bt = torch.randn(n_out, generator=g)
+    scale = (lens > 0).float()
+    pooled = P.segment_readout(x.double(), lens, op)                          # [T*B, D]
+    ref = bt.double() + sum(scale.view(T, B)[t].double()[:, None] *
+                            (pooled.view(T, B, D)[t] @ M[t].double().T + c[t].double()) for t in range(T))
+    out = ops.segment_pool_affine(x.cuda(), ptr.to(torch.int32).cuda(), T, B, op, M.cuda(), c.cuda(), bt.cuda(), scale.cuda())
+    assert rel(out, ref) < 1e-5
+    out2 = ops.segment_pool_affine(x.cuda(), ptr.to(torch.int32).cuda(), T, B, op, M.cuda(), c.cuda(), bt.cuda(), scale.cuda(),
+                                   out=out.clone(), accumulate=True)
+    assert rel(out2, 2 * ref) < 1e-5
+
+
 def test_typed_layernorm():
     g = torch.Generator().manual_seed(1)
     counts, D = [33, 0, 80], 200

@@ -6,7 +6,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -36,6 +36,8 @@ PROTOTYPES = {
     "wsi_plan_attn_work_fill": (_I, [_P, _P, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P]),
     "wsi_segment_pool_workspace_bytes": (_L, [_L, _L, _I]),
     "wsi_segment_pool_fwd": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _L, _P, _L, _P]),
+    "wsi_segment_pool_affine_workspace_bytes": (_L, [_L, _L, _I]),
+    "wsi_segment_pool_affine_fwd": (_I, [_P, _L, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _I, _I, _P, _L, _P, _L, _P]),
     "wsi_knn_workspace_bytes": (_L, [_L, _I, _I, _L, _L]),
     "wsi_knn_topk": (_I, [_P, _L, _I, _I, _L, _L, _P, _P, _P, _L, _P]),
     "wsi_edge_pearson": (_I, [_P, _L, _I, _P, _P, _L, _P, _P, _P]),

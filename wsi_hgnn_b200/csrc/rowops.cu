@@ -19,7 +19,8 @@ __device__ __forceinline__ float4 pool_comb(float4 a, float4 b, int op) {
 
 __global__ void __launch_bounds__(POOL_THREADS)
 segment_pool_kernel(const float* __restrict__ x, int64_t ldx, const int* __restrict__ seg_ptr, int D, int op,
-                    int n_split, float* __restrict__ out, int64_t ldo, float* __restrict__ partial) {
+                    int n_split, float* __restrict__ out, int64_t ldo, float* __restrict__ partial, int force_partial,
+                    const float* __restrict__ aff_M, int aff_n_out, int aff_B, float* __restrict__ aff_pdots) {
   __shared__ float4 sm[POOL_THREADS / 32][32];
   const int seg = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -32,7 +33,19 @@ segment_pool_kernel(const float* __restrict__ x, int64_t ldx, const int* __restr
   const float ident = op == WSI_POOL_MAX ? -INFINITY : 0.f;
   float4 acc = make_float4(ident, ident, ident, ident);
   const bool vec = (col + 3 < D) && (ldx % 4 == 0);
-  for (int r = r0 + warp; r < r1; r += POOL_THREADS / 32) {
+  constexpr int W = POOL_THREADS / 32;
+  int r = r0 + warp;
+  if (vec) {                                            // 4 rows in flight per thread
+    for (; r + 3 * W < r1; r += 4 * W) {
+      const float* p = x + (int64_t)r * ldx + col;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * ldx));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)2 * W * ldx));
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)3 * W * ldx));
+      acc = pool_comb(pool_comb(acc, v0, op), pool_comb(pool_comb(v1, v2, op), v3, op), op);
+    }
+  }
+  for (; r < r1; r += W) {
     const float* p = x + (int64_t)r * ldx + col;
     float4 v;
     if (vec) v = __ldg(reinterpret_cast<const float4*>(p));
@@ -48,7 +61,24 @@ segment_pool_kernel(const float* __restrict__ x, int64_t ldx, const int* __restr
 #pragma unroll
     for (int w = 1; w < POOL_THREADS / 32; ++w) acc = pool_comb(acc, sm[w][lane], op);
     float vals[4] = {acc.x, acc.y, acc.z, acc.w};
-    if (n_split == 1) {
+    if (aff_pdots) {
+      // sum / mean readout followed by an affine map: the map is linear in the slab sums, so this CTA contributes
+      // its own <M[t, o, cols], slab sum> and the [.., D] partial never goes to memory
+      const int t = seg / aff_B;
+      float* pd = aff_pdots + (((int64_t)blockIdx.z * gridDim.x + seg) * gridDim.y + blockIdx.y) * aff_n_out;
+      for (int o = 0; o < aff_n_out; ++o) {
+        const float* mrow = aff_M + ((int64_t)t * aff_n_out + o) * D + col;
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (col + c < D) d = fmaf(vals[c], __ldg(mrow + c), d);
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
+        if (lane == 0) pd[o] = d;
+      }
+      return;
+    }
+    if (n_split == 1 && !force_partial) {
       const float scale = op == WSI_POOL_MEAN ? 1.f / (float)max(n, 1) : 1.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -71,12 +101,124 @@ __global__ void segment_pool_finish_kernel(const float* __restrict__ partial, co
   int c = (int)(idx % D);
   int n = seg_ptr[seg + 1] - seg_ptr[seg];
   float acc = op == WSI_POOL_MAX ? -INFINITY : 0.f;
+#pragma unroll 8
   for (int z = 0; z < n_split; ++z) {
     float v = partial[((int64_t)z * n_seg + seg) * D + c];
     acc = op == WSI_POOL_MAX ? fmaxf(acc, v) : acc + v;
   }
   if (op == WSI_POOL_MEAN) acc /= (float)max(n, 1);
   out[seg * ldo + c] = n > 0 ? acc : 0.f;
+}
+
+// Fused finish of the typed readout when what follows the pooling is affine and narrow (HEATNet2's
+// sum_t linears_prediction[t](pool_t), models/HEATNet2.py:181-194; HGT's per-layer readout, models/HGT.py:189-199; and
+// HEATNet4's linears_prediction -> cat -> head_2 -> head_1 -> head, which has no nonlinearity
+// (models/HEATNet4.py:216-245) and is collapsed on the host into one [out, D] map per node type):
+//   out[b, o] (+)= b_total[o] + sum_t scale[t*B + b] * ( <M[t, o, :], pool(t, b)> + c[t, o] )
+// one block per graph b: threads own columns, reduce the pooling partials of their column, multiply by M, block-reduce.
+constexpr int AFF_MAX_OUT = 8;
+
+// sum / mean: the slab dots of segment_pool_kernel -> out.  pdots [n_split, T*B, chunks, n_out]
+__global__ void __launch_bounds__(128)
+segment_pool_affine_dots_finish_kernel(const float* __restrict__ pdots, const int* __restrict__ seg_ptr, int T, int B,
+                                       int chunks, int op, int n_split, const float* __restrict__ c,
+                                       const float* __restrict__ b_total, const float* __restrict__ seg_scale, int n_out,
+                                       int accumulate, float* __restrict__ out, int64_t ldo) {
+  __shared__ float red[4][AFF_MAX_OUT];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_seg = (int64_t)T * B;
+  float tot[AFF_MAX_OUT];
+#pragma unroll
+  for (int o = 0; o < AFF_MAX_OUT; ++o) tot[o] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const int64_t seg = (int64_t)t * B + b;
+    const int n = seg_ptr[seg + 1] - seg_ptr[seg];
+    float sc = seg_scale ? seg_scale[seg] : 1.f;
+    if (n == 0 || sc == 0.f) continue;                  // empty type: zero block (models/HEATNet4.py:240)
+    const float pool_scale = op == WSI_POOL_MEAN ? 1.f / (float)n : 1.f;
+    for (int i = threadIdx.x; i < n_split * chunks; i += blockDim.x) {
+      const int z = i / chunks, ch = i - z * chunks;
+      const float* pd = pdots + (((int64_t)z * n_seg + seg) * chunks + ch) * n_out;
+#pragma unroll
+      for (int o = 0; o < AFF_MAX_OUT; ++o)
+        if (o < n_out) tot[o] = fmaf(sc * pool_scale, pd[o], tot[o]);
+    }
+    if (threadIdx.x == 0 && c)
+#pragma unroll
+      for (int o = 0; o < AFF_MAX_OUT; ++o)
+        if (o < n_out) tot[o] = fmaf(sc, __ldg(c + (int64_t)t * n_out + o), tot[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < AFF_MAX_OUT; ++o) {
+    float v = tot[o];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[warp][o] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_out) {
+    float v = b_total ? b_total[threadIdx.x] : 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    float* p = out + (int64_t)b * ldo + threadIdx.x;
+    *p = accumulate ? *p + v : v;
+  }
+}
+
+// max: not linear - reduce the [.., D] partials first
+__global__ void __launch_bounds__(256)
+segment_pool_affine_finish_kernel(const float* __restrict__ partial, const int* __restrict__ seg_ptr, int T, int B, int D,
+                                  int op, int n_split, const float* __restrict__ M, const float* __restrict__ c,
+                                  const float* __restrict__ b_total, const float* __restrict__ seg_scale, int n_out,
+                                  int accumulate, float* __restrict__ out, int64_t ldo) {
+  __shared__ float red[8][AFF_MAX_OUT];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_seg = (int64_t)T * B;
+  float tot[AFF_MAX_OUT];
+#pragma unroll
+  for (int o = 0; o < AFF_MAX_OUT; ++o) tot[o] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const int64_t seg = (int64_t)t * B + b;
+    const int n = seg_ptr[seg + 1] - seg_ptr[seg];
+    const float sc = seg_scale ? seg_scale[seg] : 1.f;
+    if (n == 0 || sc == 0.f) continue;                  // empty type: zero block (models/HEATNet4.py:240)
+    float dot[AFF_MAX_OUT];
+#pragma unroll
+    for (int o = 0; o < AFF_MAX_OUT; ++o) dot[o] = 0.f;
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+      float acc = op == WSI_POOL_MAX ? -INFINITY : 0.f;
+#pragma unroll 8
+      for (int z = 0; z < n_split; ++z) {
+        const float v = partial[((int64_t)z * n_seg + seg) * D + col];
+        acc = op == WSI_POOL_MAX ? fmaxf(acc, v) : acc + v;
+      }
+      if (op == WSI_POOL_MEAN) acc /= (float)n;
+#pragma unroll
+      for (int o = 0; o < AFF_MAX_OUT; ++o)
+        if (o < n_out) dot[o] = fmaf(__ldg(M + ((int64_t)t * n_out + o) * D + col), acc, dot[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < AFF_MAX_OUT; ++o) tot[o] = fmaf(sc, dot[o], tot[o]);
+    if (threadIdx.x == 0 && c)
+#pragma unroll
+      for (int o = 0; o < AFF_MAX_OUT; ++o)
+        if (o < n_out) tot[o] = fmaf(sc, __ldg(c + (int64_t)t * n_out + o), tot[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < AFF_MAX_OUT; ++o) {
+    float v = tot[o];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[warp][o] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_out) {
+    float v = b_total ? b_total[threadIdx.x] : 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    float* p = out + (int64_t)b * ldo + threadIdx.x;
+    *p = accumulate ? *p + v : v;
+  }
 }
 
 int pool_splits(int64_t n_rows, int64_t n_seg, int D) {
@@ -158,7 +300,8 @@ extern "C" int wsi_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* 
                 "segment_pool: workspace too small");
   cudaStream_t st = wsi_stream(stream);
   dim3 grid((unsigned)n_seg, (D + 127) / 128, splits);
-  segment_pool_kernel<<<grid, POOL_THREADS, 0, st>>>(x, ldx, seg_ptr, D, op, splits, out, ldo, (float*)workspace);
+  segment_pool_kernel<<<grid, POOL_THREADS, 0, st>>>(x, ldx, seg_ptr, D, op, splits, out, ldo, (float*)workspace, 0,
+                                                     nullptr, 0, 1, nullptr);
   WSI_CHECK_LAUNCH();
   if (splits > 1) {
     int64_t total = n_seg * D;
@@ -166,6 +309,46 @@ extern "C" int wsi_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* 
                                                                                 n_seg, D, op, splits, out, ldo);
     WSI_CHECK_LAUNCH();
   }
+  return WSI_OK;
+}
+
+// workspace: max(1, splits) * T * B * D floats (wsi_segment_pool_affine_workspace_bytes)
+extern "C" int64_t wsi_segment_pool_affine_workspace_bytes(int64_t n_rows, int64_t n_seg, int D) {
+  int s = pool_splits(n_rows, n_seg, D);
+  return (int64_t)s * n_seg * D * (int64_t)sizeof(float);
+}
+
+extern "C" int wsi_segment_pool_affine_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, int T, int B,
+                                           int64_t n_rows, int D, int op, const float* M, const float* c,
+                                           const float* b_total, const float* seg_scale, int n_out, int accumulate,
+                                           float* out, int64_t ldo, void* workspace, int64_t workspace_bytes,
+                                           void* stream) {
+  WSI_CHECK_ARG(op == WSI_POOL_SUM || op == WSI_POOL_MEAN || op == WSI_POOL_MAX, "segment_pool_affine: unknown op %d", op);
+  WSI_CHECK_ARG(T >= 1 && B >= 0 && D >= 1 && (int64_t)T * B < 65536ll * 32768, "segment_pool_affine: bad T / B / D");
+  WSI_CHECK_ARG(n_out >= 1 && n_out <= AFF_MAX_OUT, "segment_pool_affine: 1 <= n_out <= %d (got %d)", AFF_MAX_OUT, n_out);
+  if (B == 0) return WSI_OK;
+  WSI_CHECK_ARG(seg_ptr && M && out && (x || n_rows == 0), "segment_pool_affine: null pointer");
+  const int64_t n_seg = (int64_t)T * B;
+  const int splits = pool_splits(n_rows, n_seg, D);
+  WSI_CHECK_ARG(workspace && workspace_bytes >= wsi_segment_pool_affine_workspace_bytes(n_rows, n_seg, D),
+                "segment_pool_affine: workspace too small");
+  cudaStream_t st = wsi_stream(stream);
+  dim3 grid((unsigned)n_seg, (D + 127) / 128, splits);
+  if (op != WSI_POOL_MAX) {                               // linear readout: per-slab dots, [.., D] partials never stored
+    segment_pool_kernel<<<grid, POOL_THREADS, 0, st>>>(x, ldx, seg_ptr, D, op, splits, nullptr, 0, nullptr, 1, M, n_out, B,
+                                                       (float*)workspace);
+    WSI_CHECK_LAUNCH();
+    segment_pool_affine_dots_finish_kernel<<<B, 128, 0, st>>>((const float*)workspace, seg_ptr, T, B, (int)grid.y, op, splits,
+                                                             c, b_total, seg_scale, n_out, accumulate, out, ldo);
+    WSI_CHECK_LAUNCH();
+    return WSI_OK;
+  }
+  segment_pool_kernel<<<grid, POOL_THREADS, 0, st>>>(x, ldx, seg_ptr, D, op, splits, nullptr, 0, (float*)workspace, 1,
+                                                     nullptr, 0, 1, nullptr);
+  WSI_CHECK_LAUNCH();
+  segment_pool_affine_finish_kernel<<<B, 256, 0, st>>>((const float*)workspace, seg_ptr, T, B, D, op, splits, M, c, b_total,
+                                                      seg_scale, n_out, accumulate, out, ldo);
+  WSI_CHECK_LAUNCH();
   return WSI_OK;
 }
 

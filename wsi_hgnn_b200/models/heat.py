@@ -209,6 +209,38 @@ class _HEATBase(nn.Module):
         return ops.typed_linear(pooled, w_p, b_p, plan.readout_ptr(), row_scale=readout_scale(plan, G.independent))
 
 
+    def _readout_affine(self, G, plan, x, collapse_heads: bool):
+        """[B, out_dim] logits by the fused pool + affine kernel.  HEATNet2: M_t = linears_prediction[t]
+        (models/HEATNet2.py:181-194).  HEATNet4: the chain linears_prediction -> cat -> head_2 -> head_1 -> head
+        (models/HEATNet4.py:216-245) contains no nonlinearity (and LinearAttentionBlock is the identity), so it equals
+        one [out, D] map per node type plus a constant; the composite is formed in fp64 on the host side of the pack
+        cache and rebuilt whenever one of the parameters changes."""
+        names = list(plan.ntypes)
+        T, B = len(names), plan.B
+        heads = [self.head_2, self.head_1, self.head] if collapse_heads else []
+        params = param_list(self, ("affine", tuple(names)), lambda: (
+            [p for nt in names for p in self.linears_prediction[nt].parameters()] + [p for h in heads for p in h.parameters()]))
+
+        def build():
+            wp = torch.stack([self.linears_prediction[nt].weight for nt in names]).double()      # [T, n_pred, D]
+            bp = torch.stack([self.linears_prediction[nt].bias for nt in names]).double()        # [T, n_pred]
+            if not collapse_heads:
+                return wp.float().contiguous(), bp.float().contiguous(), None
+            w2, b2 = self.head_2.weight.double(), self.head_2.bias.double()
+            w1, b1 = self.head_1.weight.double(), self.head_1.bias.double()
+            wh, bh = self.head.weight.double(), self.head.bias.double()
+            wc = wh @ w1 @ w2                                                                    # [out, 256 T]
+            b_total = wh @ (w1 @ b2 + b1) + bh
+            blocks = wc.view(wc.shape[0], T, -1).permute(1, 0, 2)                                # [T, out, 256]
+            M = torch.bmm(blocks, wp)                                                            # [T, out, D]
+            c = torch.bmm(blocks, bp.unsqueeze(-1)).squeeze(-1)                                  # [T, out]
+            return M.float().contiguous(), c.float().contiguous(), b_total.float().contiguous()
+
+        M, c, b_total = self._packs.get(("affine", tuple(names)), params, build)
+        return ops.segment_pool_affine(x, plan.seg_ptr, T, B, self.graph_pooling_type, M, c, b_total,
+                                       readout_scale(plan, G.independent))
+
+
 class HEATNet4(_HEATBase):
     """reference models/HEATNet4.py:141-247.  forward(G, h=None) -> logits [B, out_dim]."""
 
@@ -226,11 +258,15 @@ class HEATNet4(_HEATBase):
         self.head_2 = nn.Linear(256 * len(node_dict), 256)
         self.head_1 = nn.Linear(256, 64)
         self.head = nn.Linear(64, out_dim)
+        self.explicit_heads = False      # True: run linears_prediction / head_2 / head_1 / head as separate GEMMs
         self._packs = PackCache()
 
     def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
         plan, x = self._trunk(G, h)
         T, B = len(plan.ntypes), plan.B
+        if self.head.out_features <= ops.AFFINE_MAX_OUT and not self.explicit_heads:
+            g = self._readout_affine(G, plan, x, collapse_heads=True)   # :216-245 as one fused launch pair
+            return (g, unpack_rows(plan, x)) if return_embeddings else g
         o = self._readout(G, plan, x)                                   # [T*B, 256]      :216-240
         z = o if B == 1 else o.view(T, B, 256).permute(1, 0, 2).contiguous()
         z = z.view(B, T * 256)                                          # cat(dim=1) in G.ntypes order
@@ -259,6 +295,10 @@ class HEATNet2(_HEATBase):
     def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
         plan, x = self._trunk(G, h)
         T, B = len(plan.ntypes), plan.B
+        n_pred = next(iter(self.linears_prediction.values())).out_features
+        if n_pred <= ops.AFFINE_MAX_OUT:
+            g = self._readout_affine(G, plan, x, collapse_heads=False)  # HEATNet2.py:181-194
+            return (g, unpack_rows(plan, x)) if return_embeddings else g
         o = self._readout(G, plan, x)                                   # [T*B, out]   HEATNet2.py:181-194
         g = o.view(T, B, -1).sum(0)
         return (g, unpack_rows(plan, x)) if return_embeddings else g

@@ -184,13 +184,17 @@ class HGT(nn.Module):
         hg = None
         n_run = self.n_layers if return_embeddings else self.n_layers
         for i in range(n_run):                                             # :189-199
-            pooled = ops.segment_pool(x, plan.seg_ptr, T * B, self.graph_pooling_type)
             pp = param_list(self, ("pred", i, tuple(names)), lambda: (p for nt in names for p in self.linears_prediction[nt][i].parameters()))
             w_p, b_p = self._packs.get(("pred", i, tuple(names)), pp, lambda i=i: (
                 torch.stack([self.linears_prediction[nt][i].weight for nt in names]).contiguous(),
                 torch.stack([self.linears_prediction[nt][i].bias for nt in names]).contiguous()))
-            o = ops.typed_linear(pooled, w_p, b_p, plan.readout_ptr(), row_scale=scale).view(T, B, -1).sum(0)
-            hg = o if hg is None else hg + o
+            if self.out_dim <= ops.AFFINE_MAX_OUT:        # fused pool + per-type prediction + sum over types / layers
+                hg = ops.segment_pool_affine(x, plan.seg_ptr, T, B, self.graph_pooling_type, w_p, b_p, None, scale,
+                                             out=hg, accumulate=hg is not None)
+            else:
+                pooled = ops.segment_pool(x, plan.seg_ptr, T * B, self.graph_pooling_type)
+                o = ops.typed_linear(pooled, w_p, b_p, plan.readout_ptr(), row_scale=scale).view(T, B, -1).sum(0)
+                hg = o if hg is None else hg + o
             # the output of the LAST layer is never read by the reference (models/HGT.py:199-209);
             # it is computed only when the caller asks for the embeddings
             if i + 1 < self.n_layers or return_embeddings:

@@ -358,6 +358,36 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
                 n_split=n_split, n_part=n_part, max_in_degree=max_deg, bad_edges=bool(bad))
 
 
+AFFINE_MAX_OUT = 8
+
+
+def segment_pool_affine(x: torch.Tensor, seg_ptr: torch.Tensor, T: int, B: int, op: str, M: torch.Tensor,
+                        c: Optional[torch.Tensor], b_total: Optional[torch.Tensor], seg_scale: Optional[torch.Tensor],
+                        out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """Typed readout fused with the narrow affine prediction that follows it -> [B, n_out];
+    see wsi_segment_pool_affine_fwd."""
+    if op not in POOL_OPS:
+        raise NotImplementedError(op)
+    lib = _lib.load()
+    stream = _prep(x)
+    N, D = int(x.shape[0]), int(x.shape[1])
+    n_out = int(M.shape[1])
+    if tuple(M.shape) != (T, n_out, D) or n_out > AFFINE_MAX_OUT:
+        raise ValueError(f"segment_pool_affine: M must be [T={T}, n_out<={AFFINE_MAX_OUT}, D={D}], got {tuple(M.shape)}")
+    xp, ldx = _rows(x, "x")
+    if out is None:
+        out = torch.empty((B, n_out), dtype=torch.float32, device=x.device)
+        accumulate = False
+    ws_bytes = lib.wsi_segment_pool_affine_workspace_bytes(N, T * B, D)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
+    rc = lib.wsi_segment_pool_affine_fwd(xp, ldx, _vec(seg_ptr, "seg_ptr", torch.int32), T, B, N, D, POOL_OPS[op],
+                                         _vec(M, "M"), _vec(c, "c"), _vec(b_total, "b_total"),
+                                         _vec(seg_scale, "seg_scale"), n_out, 1 if accumulate else 0, out.data_ptr(),
+                                         n_out, ws.data_ptr(), ws_bytes, stream)
+    _lib.check(rc, "wsi_segment_pool_affine_fwd")
+    return out
+
+
 def knn_topk(feat: torch.Tensor, topn: int, q_begin: int = 0, q_end: Optional[int] = None, want_dist: bool = False):
     """Exact L2 k-NN (self included, ordered by (distance, index)); see wsi_knn_topk.
     -> int32 [q_end - q_begin, topn] (and the fp32 distances)."""
