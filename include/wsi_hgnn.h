@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 9
+#define WSI_ABI_VERSION 10
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -115,6 +115,8 @@ int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   (partial slots of each split row, in edge order), part_rel int32 [n_part] (relation slot of each partial).
  *   With split_cnt int32 [n_split] (ZERO before the first launch; the kernel leaves it zero) and part_split int32
  *   [n_part] the merge is fused: the warp finishing a row's last chunk merges that row; else a second launch does.
+ *   sched int32 [2] (optional, ZERO before the first launch, left zero): device-side work queue - warps pull items in
+ *   list order (largest first = LPT) instead of a static round-robin.
  * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work().
  *   agg_split != NULL: the result is (also) written as bf16 [2 * n_rows, D] (hi rows, then lo rows: x = hi + lo),
  *   the A operand layout of wsi_typed_linear_split; agg may then be NULL. */
@@ -122,7 +124,7 @@ int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_
                              const int32_t* e_src, const float* e_sim, const uint8_t* e_rel, const float* node_inv_r,
                              const float* e_w, const float* e_b, int64_t n_rows, int D, int H, const int32_t* items,
                              int64_t n_items, const int32_t* split_row, const int32_t* split_ptr,
-                             const int32_t* part_rel, const int32_t* part_split, int32_t* split_cnt,
+                             const int32_t* part_rel, const int32_t* part_split, int32_t* split_cnt, int32_t* sched,
                              int64_t n_split, int64_t n_part, float* part_ms,
                              float* part_acc, float* agg, int64_t ldo, void* agg_split, void* stream);
 

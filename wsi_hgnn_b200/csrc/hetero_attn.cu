@@ -51,6 +51,8 @@ struct AttnArgs {
   int64_t split_lo;           // element offset of the lo half (n_rows * D)
   // fused merge of the split rows (TMA kernel): split index of every partial, per-split-row arrival counter
   const int* part_split; int* split_cnt;
+  int dbg;                    // development only (env WSI_ATTN_DEBUG): 1 = gather only 64 distinct rows
+  int* sched;                 // optional int32 [2], zero before the first launch: dynamic work queue (next item | warps done)
   const int* split_row; const int* split_ptr; const int* part_rel;
 };
 
@@ -254,7 +256,7 @@ struct MergeArgs {
 };
 
 template <int NV>
-__device__ __forceinline__ void merge_row(const MergeArgs& a, int h, int lane) {
+__device__ __noinline__ void merge_row(const MergeArgs& a, int h, int lane) {
   constexpr int MB = 4;                                 // partials whose loads are in flight together
   const int row = __ldg(a.split_row + h);
   const int pb = __ldg(a.split_ptr + h), pe = __ldg(a.split_ptr + h + 1);
@@ -366,7 +368,7 @@ constexpr int TMA_WARPS = 4;
 constexpr int BMAX = 4;      // edges per batch of the TMA kernel
 
 template <int NV, int MODE>
-__global__ void __launch_bounds__(TMA_WARPS * 32) attn_fwd_tma_kernel(AttnArgs a, int ring) {
+__global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_kernel(AttnArgs a, int ring) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int ROW_BYTES = NV * 512, SLOT_BYTES = 2 * ROW_BYTES;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -383,10 +385,22 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) attn_fwd_tma_kernel(AttnArgs a
   __syncthreads();
   float ew = 0.f, eb = 0.f;
   if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
+  const bool kv_adjacent = a.V == a.K + a.D && a.ldk == a.ldv;
   int rs = 0;                 // ring slot of the next edge to consume
   uint32_t rpar = 0;          // its mbarrier phase parity
 
-  for (int item = blockIdx.x * TMA_WARPS + warp; item < a.n_items; item += n_warps) {
+  // Work distribution: with a.sched the warps pull items from a device-side queue (the item list is sorted largest
+  // first, so this is LPT scheduling and no warp is left with a long tail); the next index is fetched one item ahead
+  // so the atomic's latency hides behind the current item.  Without it: static round-robin.
+  int item = blockIdx.x * TMA_WARPS + warp;
+  int next_item = 0;
+  if (a.sched) {
+    if (lane == 0) { item = atomicAdd(a.sched, 1); }
+    item = __shfl_sync(FULL, item, 0);
+  }
+  while (item < a.n_items) {
+    if (a.sched) { if (lane == 0) next_item = atomicAdd(a.sched, 1); }
+    else next_item = item + n_warps;
     int row = item, beg, end, slot = -1;
     if (a.items) {
       const int4 it = __ldg(a.items + item);
@@ -413,6 +427,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) attn_fwd_tma_kernel(AttnArgs a
         float my_sim = 0.f;
         if (lane < n) {
           my_src = __ldg(a.e_src + base + lane);
+          if (a.dbg == 1) my_src &= 63;
           if (MODE == MODE_HEAT) { my_sim = __ldg(a.e_sim + base + lane); my_rel = __ldg(a.e_rel + base + lane); }
         }
         const int pre = min(n, ring);
@@ -423,8 +438,12 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) attn_fwd_tma_kernel(AttnArgs a
             if (lane == 0) {
               const uint32_t bar = bars_u32 + 8 * s, dst = slots_u32 + s * SLOT_BYTES;
               mbar_expect_tx(bar, SLOT_BYTES);
-              bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
-              bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+              if (kv_adjacent) {                        // K|V of a node are one contiguous 2 * D * 4 byte run
+                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, SLOT_BYTES, bar);
+              } else {
+                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
+                bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+              }
             }
             if (++s == ring) s = 0;
           }
@@ -521,8 +540,12 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) attn_fwd_tma_kernel(AttnArgs a
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               const uint32_t bar = bars_u32 + 8 * rs, dst = slots_u32 + rs * SLOT_BYTES;
               mbar_expect_tx(bar, SLOT_BYTES);
-              bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
-              bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+              if (kv_adjacent) {                        // K|V of a node are one contiguous 2 * D * 4 byte run
+                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, SLOT_BYTES, bar);
+              } else {
+                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
+                bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+              }
             }
             if (++rs == ring) { rs = 0; rpar ^= 1; }
           }
@@ -576,6 +599,11 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) attn_fwd_tma_kernel(AttnArgs a
         }
       }
     }
+    item = a.sched ? __shfl_sync(FULL, next_item, 0) : next_item;
+  }
+  if (a.sched && lane == 0) {                           // the last warp to leave re-arms the queue for the next launch
+    __threadfence();
+    if (atomicAdd(a.sched + 1, 1) == n_warps - 1) { a.sched[0] = 0; a.sched[1] = 0; }
   }
 }
 
@@ -694,13 +722,15 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       return WSI_ERR_UNSUPPORTED;
     }
     if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && !getenv("WSI_ATTN_NO_TMA")) {
-      // TMA-staged ring: ~24 KB of K/V rows in flight per warp, 2 blocks of 4 warps per SM
+      // TMA-staged ring: ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM
       const int slot_bytes = 2 * a.D * 4;
-      int ring = 24576 / slot_bytes;
+      int ring = 12288 / slot_bytes;
       ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
+      if (const char* r = getenv("WSI_ATTN_RING")) ring = atoi(r);          // development knob
       const int smem = TMA_WARPS * ring * slot_bytes + TMA_WARPS * ring * 8;
       int tb = (a.n_items + TMA_WARPS - 1) / TMA_WARPS;
-      if (tb > sms * 2) tb = sms * 2;
+      const int per_sm = 200 * 1024 / (smem + 1024) < 1 ? 1 : 200 * 1024 / (smem + 1024);
+      if (tb > sms * per_sm) tb = sms * per_sm;
       switch (a.D / 128) {
 #define CASE(NV) case NV: { \
         static bool attr_set = false; \
@@ -714,6 +744,7 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       return WSI_OK;
     }
     a.split_cnt = nullptr;                              // register-path kernel: the caller launches the merge
+    a.sched = nullptr;
     switch (a.D / 128) {
 #define CASE(NV) case NV: attn_fwd_vec_kernel<NV, MODE><<<blocks, WARPS * 32, 0, stream>>>(a); break;
       CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
@@ -790,7 +821,7 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
                                         const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows,
                                         int D, int H, const int32_t* items, int64_t n_items,
                                         const int32_t* split_row, const int32_t* split_ptr, const int32_t* part_rel,
-                                        const int32_t* part_split, int32_t* split_cnt, int64_t n_split,
+                                        const int32_t* part_split, int32_t* split_cnt, int32_t* sched, int64_t n_split,
                                         int64_t n_part, float* part_ms, float* part_acc, float* agg, int64_t ldo,
                                         void* agg_split, void* stream) {
   WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && n_items >= 0 && n_items < (1ll << 31), "hetero_attn_work_fwd: bad sizes");
@@ -816,6 +847,8 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
     a.part_split = part_split; a.split_cnt = split_cnt;
     a.split_row = split_row; a.split_ptr = split_ptr; a.part_rel = part_rel;
   }
+  a.sched = sched;
+  { const char* d = getenv("WSI_ATTN_DEBUG"); a.dbg = d ? atoi(d) : 0; }
   bool fused = false;
   int rc = launch<MODE_HEAT>(a, 1, wsi_stream(stream), &fused);
   if (rc != WSI_OK || fused) return rc;

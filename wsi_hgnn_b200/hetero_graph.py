@@ -277,7 +277,7 @@ class GraphPlan:
         if n_split == 0:
             work = dict(items=items_c.to(torch.int32).contiguous(), n_items=int(items_c.shape[0]),
                         split_row=torch.zeros(1, **i32), split_ptr=torch.zeros(2, **i32),
-                        part_rel=torch.zeros(1, **i32), n_split=0, n_part=0)
+                        part_rel=torch.zeros(1, **i32), n_split=0, n_part=0, sched=torch.zeros(2, **i32))
             self.cache[key] = work
             return work
         segs = self.segments()
@@ -304,7 +304,8 @@ class GraphPlan:
         work = dict(items=items, n_items=int(items.shape[0]), split_row=split_row.to(torch.int32).contiguous(),
                     split_ptr=split_ptr.to(torch.int32).contiguous(), part_rel=part_rel, n_split=n_split,
                     n_part=n_part, part_split=part_split.to(torch.int32).contiguous(),
-                    split_cnt=torch.zeros(n_split, dtype=torch.int32, device=dev))
+                    split_cnt=torch.zeros(n_split, dtype=torch.int32, device=dev),
+                    sched=torch.zeros(2, dtype=torch.int32, device=dev))
         self.cache[key] = work
         return work
 

@@ -206,7 +206,8 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
                                       _vec(work["split_ptr"], "split_ptr", torch.int32),
                                       _vec(work["part_rel"], "part_rel", torch.int32),
                                       _vec(work.get("part_split"), "part_split", torch.int32),
-                                      _vec(work.get("split_cnt"), "split_cnt", torch.int32), n_split, n_part,
+                                      _vec(work.get("split_cnt"), "split_cnt", torch.int32),
+                                      _vec(work.get("sched"), "sched", torch.int32), n_split, n_part,
                                       part_ms.data_ptr() if part_ms is not None else None,
                                       part_acc.data_ptr() if part_acc is not None else None, ap, ldo,
                                       agg_split.data_ptr() if agg_split is not None else None, stream)
@@ -354,7 +355,7 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
                                            split_ptr.data_ptr(), part_rel.data_ptr(), part_split.data_ptr(), stream),
                "wsi_plan_attn_work_fill")
     return dict(items=items, n_items=n_items, split_row=split_row, split_ptr=split_ptr, part_rel=part_rel,
-                part_split=part_split, split_cnt=split_cnt,
+                part_split=part_split, split_cnt=split_cnt, sched=torch.zeros(2, **i32),
                 n_split=n_split, n_part=n_part, max_in_degree=max_deg, bad_edges=bool(bad))
 
 
