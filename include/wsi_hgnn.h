@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 10
+#define WSI_ABI_VERSION 11
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -127,6 +127,17 @@ int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_
                              const int32_t* part_rel, const int32_t* part_split, int32_t* split_cnt, int32_t* sched,
                              int64_t n_split, int64_t n_part, float* part_ms,
                              float* part_acc, float* agg, int64_t ldo, void* agg_split, void* stream);
+
+/* Backward of wsi_hetero_attn_fwd (kernel K3; HEAT scoring, lane-grouped column order): what DGL's GSDDMM / EdgeSoftmax /
+ * GSpMM backward compute under loss.backward() (trainer/train_gnn.py:68-71 through models/HEATNet4.py:103-119).
+ *   d_agg [N, ldg] = gradient of agg.  dk, dv [N, ld*]: ACCUMULATED into (zero them first; rows are shared between
+ *   destinations -> vector atomics); dq [N, lddq]: written; d_e [2] = (d e_linear.weight, d e_linear.bias): accumulated.
+ *   Nothing is saved by the forward: the segment softmax is recomputed from k, v, q. */
+int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
+                        const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
+                        const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D, int H,
+                        const float* d_agg, int64_t ldg, float* dk, int64_t lddk, float* dv, int64_t lddv, float* dq,
+                        int64_t lddq, float* d_e, void* stream);
 
 /* Segment form used by HGT (WSI_SCORE_HGT): one work item per (dst,relation) segment.
  *   seg_ptr int32 [S+1] edge range of segment s (dst-major order), seg_rel int32 [S] MODEL relation id,

@@ -71,3 +71,48 @@ def test_two_rank_sharded_inference_matches_single_process():
     assert owned == list(range(7))
     for _, _, full in res:
         assert torch.allclose(full, ref, rtol=0, atol=0)
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wsi_hgnn_b200.parallel import FlatGradAllReduce
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        frozen = torch.nn.Linear(2, 2)                                   # a parameter that never gets a grad
+        params = list(m.parameters()) + list(frozen.parameters())
+        g = torch.Generator().manual_seed(1)
+        X, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+        mine = list(range(rank, 8, world))                               # this rank's samples
+        loss = torch.nn.functional.cross_entropy(m(X[mine]), y[mine], reduction="sum") / 8.0
+        loss.backward()
+        FlatGradAllReduce(params)()
+        q.put((rank, [p.grad.clone() for p in m.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_equals_full_batch_gradient():
+    """sum over ranks of d(sum local CE / B_global) == d(mean CE over the whole batch) (reference loss, parser.py:182-183)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    g = torch.Generator().manual_seed(1)
+    X, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+    torch.nn.functional.cross_entropy(m(X), y).backward()
+    for _, grads in res:
+        for a, p in zip(grads, m.parameters()):
+            assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-7)

@@ -1,0 +1,77 @@
+"""torch.autograd wiring of the C-ABI kernels: what makes `loss.backward()` of the reference's training step
+(trainer/train_gnn.py:55-79) work on the CUDA path.  Forward and backward both run libwsi_hgnn.so kernels; the one
+library call is the weight-gradient GEMM dW_t = dY_t^T X_t (a plain dense GEMM: cuBLAS through torch.matmul, see
+DESIGN.md "Training")."""
+from typing import Sequence
+
+import torch
+
+from . import ops
+
+
+class TypedLinearFn(torch.autograd.Function):
+    """y[rows of type t] = x[rows of type t] @ w[t].T + b[t]   (reference: the per-node-type nn.Linear calls)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, type_ptr: Sequence[int], type_ptr_c):
+        x = x.contiguous()
+        w = w.contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.type_ptr, ctx.type_ptr_c, ctx.has_bias = list(type_ptr), type_ptr_c, b is not None
+        return ops.typed_linear(x, w, b.contiguous() if b is not None else None, type_ptr, type_ptr_c=type_ptr_c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        tp = ctx.type_ptr
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:                      # dgrad: the same typed GEMM with W^T
+            dx = ops.typed_linear(dy, w.transpose(1, 2).contiguous(), None, tp, type_ptr_c=ctx.type_ptr_c)
+        if ctx.needs_input_grad[1]:                      # wgrad: plain dense GEMM per node type (cuBLAS)
+            dw = torch.stack([dy[tp[t]:tp[t + 1]].t() @ x[tp[t]:tp[t + 1]] for t in range(len(tp) - 1)])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.stack([dy[tp[t]:tp[t + 1]].sum(0) for t in range(len(tp) - 1)])
+        return dx, dw, db, None, None
+
+
+class HeteroAttnFn(torch.autograd.Function):
+    """agg = edge attention of one HEAT layer over all relations (models/HEATNet4.py:103-119); kvq [N, 3D] = K | V | Q in
+    the lane-grouped column order."""
+
+    @staticmethod
+    def forward(ctx, kvq, e_w, e_b, plan, D: int, H: int):
+        ctx.save_for_backward(kvq, e_w, e_b)
+        ctx.plan, ctx.D, ctx.H = plan, D, H
+        return ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.attn_work(), plan.e_src, plan.e_sim,
+                                    plan.e_rel, plan.node_inv_r, e_w, e_b, D, H)
+
+    @staticmethod
+    def backward(ctx, d_agg):
+        kvq, e_w, e_b = ctx.saved_tensors
+        plan, D, H = ctx.plan, ctx.D, ctx.H
+        d_kvq = torch.zeros_like(kvq)
+        d_e = ops.hetero_attn_bwd(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
+                                  plan.e_rel, plan.node_inv_r, e_w, e_b, D, H, d_agg.contiguous(), d_kvq[:, :D],
+                                  d_kvq[:, D:2 * D], d_kvq[:, 2 * D:])
+        return d_kvq, d_e[0].reshape(e_w.shape), d_e[1].reshape(e_b.shape), None, None, None
+
+
+class SegmentPoolFn(torch.autograd.Function):
+    """Typed readout dgl.readout.{mean,sum}_nodes(graph, 'h', ntype=) (pooling/avg_pooling.py, sum_pooling.py)."""
+
+    @staticmethod
+    def forward(ctx, x, plan, n_seg: int, op: str):
+        ctx.plan, ctx.op, ctx.n_seg = plan, op, n_seg
+        if op == "max":
+            raise NotImplementedError("max pooling has no backward yet: train with graph_pooling_type 'mean' or 'sum'")
+        return ops.segment_pool(x, plan.seg_ptr, n_seg, op)
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        plan = ctx.plan
+        seg_of_row, inv_n = plan.row_segments()
+        d = d_pooled.index_select(0, seg_of_row)
+        if ctx.op == "mean":
+            d = d * inv_n.unsqueeze(1)
+        return d, None, None, None

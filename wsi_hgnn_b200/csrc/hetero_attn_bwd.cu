@@ -1,0 +1,195 @@
+// Heterogeneous edge attention backward (kernel K3): gradients of wsi_hetero_attn_fwd (HEAT scoring) with respect to
+// K, V, Q and the e_linear scalars - what DGL's GSDDMM / EdgeSoftmax / GSpMM backward functions compute for the
+// reference's loss.backward() (trainer/train_gnn.py:68-71 through models/HEATNet4.py:103-119).
+//
+// One warp per dst row, lanes span D in the lane-grouped column order (wsi_head_perm).  Nothing is saved by the forward:
+// per (row, relation) segment the scores are recomputed in three streaming passes over the segment's edges
+//   A  m = max_e s_e, Z = sum_e exp(s_e - m)                               (reads K[src])
+//   B  delta = sum_e a_e <g, V[src]>        a_e = exp(s_e - m) / Z         (reads K[src], V[src])
+//   C  ds_e = a_e (<g, V[src]> - delta)                                    (reads K[src], V[src] - L1/L2 hits)
+//      dQ[row] += ds_e c_e K[src];  dK[src] += ds_e c_e q;  dV[src] += a_e g;   d c_e = ds_e <q, K[src]>
+// with g = dAgg[row] / R_t and c_e = (w sim_e + b) / sqrt(d_k).  dQ rows are owned by their warp; dK / dV rows are
+// shared between destinations and accumulated with 16-byte vector atomics (fp32 red.add: the summation order, not the
+// set of terms, depends on scheduling).  HBM/L2 bound: per edge 3 K + 2 V row reads and 2 row atomics.
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARPS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct BwdArgs {
+  const float* K; int64_t ldk;
+  const float* V; int64_t ldv;
+  const float* Q; int64_t ldq;
+  const int* rowptr; const int* e_src; const float* e_sim; const uint8_t* e_rel;
+  const float* inv_r; const float* e_w; const float* e_b;
+  const float* dAgg; int64_t ldg;
+  float* dK; int64_t lddk;
+  float* dV; int64_t lddv;
+  float* dQ; int64_t lddq;
+  float* d_e;                 // [2]: d e_linear.weight, d e_linear.bias (accumulated)
+  int n_rows, D, H;
+  float inv_sqrt_dk;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+#if __CUDA_ARCH__ >= 900
+  atomicAdd(reinterpret_cast<float4*>(p), v);
+#else
+  atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+#endif
+}
+
+template <int NV>
+__device__ __forceinline__ float head_dot(const float4* a, const float4* b, int G) {
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    d0 = fmaf(a[i].x, b[i].x, d0); d1 = fmaf(a[i].y, b[i].y, d1);
+    d0 = fmaf(a[i].z, b[i].z, d0); d1 = fmaf(a[i].w, b[i].w, d1);
+  }
+  float d = d0 + d1;
+  for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+  return d;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32) attn_bwd_kernel(BwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int G = 32 / a.H;
+  const int n_warps = gridDim.x * WARPS;
+  const float ew = __ldg(a.e_w), eb = __ldg(a.e_b);
+  float dw_acc = 0.f, db_acc = 0.f;
+
+  for (int row = blockIdx.x * WARPS + (threadIdx.x >> 5); row < a.n_rows; row += n_warps) {
+    const int beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
+    const float invr = __ldg(a.inv_r + row);
+    float4 dq[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (invr != 0.f && end > beg) {
+      float4 q[NV], g[NV];
+      const float* qr = a.Q + (int64_t)row * a.ldq;
+      const float* gr = a.dAgg + (int64_t)row * a.ldg;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        q[i] = ld4(qr + (i * 32 + lane) * 4);
+        g[i] = ld4(gr + (i * 32 + lane) * 4);
+        g[i].x *= invr; g[i].y *= invr; g[i].z *= invr; g[i].w *= invr;
+      }
+      int seg_beg = beg;
+      while (seg_beg < end) {
+        const int rel = __ldg(a.e_rel + seg_beg);
+        int seg_end = seg_beg + 1;
+        while (seg_end < end && __ldg(a.e_rel + seg_end) == rel) ++seg_end;
+        // ---- pass A: softmax statistics of the segment
+        float m = -INFINITY, z = 0.f;
+        for (int e = seg_beg; e < seg_end; ++e) {
+          const int src = __ldg(a.e_src + e);
+          const float c = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
+          float4 kk[NV];
+          const float* kr = a.K + (int64_t)src * a.ldk;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) kk[i] = ld4(kr + (i * 32 + lane) * 4);
+          const float s = head_dot<NV>(q, kk, G) * c;
+          const float mn = fmaxf(m, s);
+          z = fmaf(z, __expf(m - mn), __expf(s - mn));
+          m = mn;
+        }
+        const float inv_z = 1.f / z;
+        // ---- pass B: delta = sum_e a_e <g, v_e>
+        float delta = 0.f;
+        for (int e = seg_beg; e < seg_end; ++e) {
+          const int src = __ldg(a.e_src + e);
+          const float c = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
+          float4 kk[NV], vv[NV];
+          const float* kr = a.K + (int64_t)src * a.ldk;
+          const float* vr = a.V + (int64_t)src * a.ldv;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { kk[i] = ld4(kr + (i * 32 + lane) * 4); vv[i] = ld4(vr + (i * 32 + lane) * 4); }
+          const float at = __expf(head_dot<NV>(q, kk, G) * c - m) * inv_z;
+          delta = fmaf(at, head_dot<NV>(g, vv, G), delta);
+        }
+        // ---- pass C: the gradients
+        for (int e = seg_beg; e < seg_end; ++e) {
+          const int src = __ldg(a.e_src + e);
+          const float sim = __ldg(a.e_sim + e);
+          const float c = fmaf(ew, sim, eb) * a.inv_sqrt_dk;
+          float4 kk[NV], vv[NV];
+          const float* kr = a.K + (int64_t)src * a.ldk;
+          const float* vr = a.V + (int64_t)src * a.ldv;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { kk[i] = ld4(kr + (i * 32 + lane) * 4); vv[i] = ld4(vr + (i * 32 + lane) * 4); }
+          const float d = head_dot<NV>(q, kk, G);
+          const float at = __expf(d * c - m) * inv_z;
+          const float ds = at * (head_dot<NV>(g, vv, G) - delta);
+          const float dsc = ds * c;
+          float* dkr = a.dK + (int64_t)src * a.lddk;
+          float* dvr = a.dV + (int64_t)src * a.lddv;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            dq[i].x = fmaf(dsc, kk[i].x, dq[i].x); dq[i].y = fmaf(dsc, kk[i].y, dq[i].y);
+            dq[i].z = fmaf(dsc, kk[i].z, dq[i].z); dq[i].w = fmaf(dsc, kk[i].w, dq[i].w);
+            red_add4(dkr + (i * 32 + lane) * 4, make_float4(dsc * q[i].x, dsc * q[i].y, dsc * q[i].z, dsc * q[i].w));
+            red_add4(dvr + (i * 32 + lane) * 4, make_float4(at * g[i].x, at * g[i].y, at * g[i].z, at * g[i].w));
+          }
+          if (lane % G == 0) {                            // one lane per head carries the head's d c_e
+            const float dc = ds * d * a.inv_sqrt_dk;
+            dw_acc = fmaf(dc, sim, dw_acc);
+            db_acc += dc;
+          }
+        }
+        seg_beg = seg_end;
+      }
+    }
+    float* o = a.dQ + (int64_t)row * a.lddq;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = dq[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dw_acc += __shfl_xor_sync(FULL, dw_acc, o);
+    db_acc += __shfl_xor_sync(FULL, db_acc, o);
+  }
+  if (lane == 0 && (dw_acc != 0.f || db_acc != 0.f)) { atomicAdd(a.d_e, dw_acc); atomicAdd(a.d_e + 1, db_acc); }
+}
+
+}  // namespace
+
+// dK, dV: ACCUMULATED into (zero them first); dQ: written; d_e [2]: accumulated.
+extern "C" int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
+                                   const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
+                                   const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D,
+                                   int H, const float* d_agg, int64_t ldg, float* dk, int64_t lddk, float* dv,
+                                   int64_t lddv, float* dq, int64_t lddq, float* d_e, void* stream) {
+  WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hetero_attn_bwd: bad n_rows");
+  if (n_rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(k && v && q && rowptr && node_inv_r && e_w && e_b && d_agg && dk && dv && dq && d_e,
+                "hetero_attn_bwd: null pointer");
+  if (!(D % 128 == 0 && D <= 1024 && H >= 1 && H <= 32 && (H & (H - 1)) == 0 && D % H == 0)) {
+    wsi_set_error("hetero_attn_bwd: needs the lane-grouped layout (D %% 128 == 0, D <= 1024, H a power of two <= 32), got D=%d H=%d", D, H);
+    return WSI_ERR_UNSUPPORTED;
+  }
+  WSI_CHECK_ARG(ldk % 4 == 0 && ldv % 4 == 0 && ldq % 4 == 0 && ldg % 4 == 0 && lddk % 4 == 0 && lddv % 4 == 0 && lddq % 4 == 0,
+                "hetero_attn_bwd: row strides must be multiples of 4 floats");
+  BwdArgs a{};
+  a.K = k; a.ldk = ldk; a.V = v; a.ldv = ldv; a.Q = q; a.ldq = ldq;
+  a.rowptr = rowptr; a.e_src = e_src; a.e_sim = e_sim; a.e_rel = e_rel; a.inv_r = node_inv_r; a.e_w = e_w; a.e_b = e_b;
+  a.dAgg = d_agg; a.ldg = ldg; a.dK = dk; a.lddk = lddk; a.dV = dv; a.lddv = lddv; a.dQ = dq; a.lddq = lddq; a.d_e = d_e;
+  a.n_rows = (int)n_rows; a.D = D; a.H = H; a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
+  int sms = wsi_num_sms();
+  if (sms <= 0) return WSI_ERR_CUDA;
+  int blocks = (int)((n_rows + WARPS - 1) / WARPS);
+  if (blocks > sms * 16) blocks = sms * 16;
+  cudaStream_t st = wsi_stream(stream);
+  switch (D / 128) {
+#define CASE(NV) case NV: attn_bwd_kernel<NV><<<blocks, WARPS * 32, 0, st>>>(a); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}

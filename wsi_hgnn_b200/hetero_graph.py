@@ -247,6 +247,23 @@ class GraphPlan:
                               seg_slot=rel[starts].contiguous(), row_seg_ptr=row_seg_ptr)
         return self._segs
 
+    def row_segments(self):
+        """(segment index of every packed row int64 [N], 1 / rows-in-segment fp32 [N]) - backward of the typed readout."""
+        if "row_segments" not in self.cache:
+            lens = (self.seg_ptr[1:] - self.seg_ptr[:-1]).to(torch.int64)
+            seg = torch.repeat_interleave(torch.arange(lens.numel(), device=self.device), lens)
+            inv = (1.0 / lens.clamp_min(1).to(torch.float32)).index_select(0, seg)
+            self.cache["row_segments"] = (seg, inv)
+        return self.cache["row_segments"]
+
+    def row_types(self):
+        """node-type index of every packed row, int64 [N]."""
+        if "row_types" not in self.cache:
+            counts = torch.tensor([self.type_ptr[t + 1] - self.type_ptr[t] for t in range(len(self.ntypes))],
+                                  device=self.device)
+            self.cache["row_types"] = torch.repeat_interleave(torch.arange(len(self.ntypes), device=self.device), counts)
+        return self.cache["row_types"]
+
     def attn_work(self, chunk: int = 16):
         """Work list of the edge-attention kernel (wsi_hetero_attn_work_fwd): rows with at most `chunk`
         in-edges are one item; rows with more (k-NN hubs) are cut, per (row, relation) segment, into chunks

@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from ..autograd import HeteroAttnFn, SegmentPoolFn, TypedLinearFn
 from ..hetero_graph import GraphPlan, HeteroGraph
 from ._packing import PackCache, param_list, stack_linears
 
@@ -135,6 +136,28 @@ class HEATLayer(nn.Module):
         return ops.typed_linear_split(agg_s, wa_s, ba, plan.type_ptr, D, skip=skip, res=x, row_gate=plan.node_inv_r,
                                       drop_mask=mask, want_split=want_split, type_ptr_c=tpc)
 
+    def forward_train(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
+        """Differentiable layer (autograd.py): the packed weights are built WITH grad tracking so that the gradients
+        of the fused / permuted stacks flow back to the reference-shaped nn.Linear parameters."""
+        D, H = self.out_size, self.n_heads
+        perm = ops.head_perm(D, H)
+        if perm is None:
+            raise NotImplementedError(f"training needs the lane-grouped attention layout (D % 128 == 0, H a power of "
+                                      f"two <= 32); got D={D}, H={H}")
+        order = _graph_type_order(plan, self.node_dict)
+        pm = perm.to(x.device)
+        wk, bk = stack_linears(self.k_linears, order, row_perm=pm)
+        wv, bv = stack_linears(self.v_linears, order, row_perm=pm)
+        wq, bq = stack_linears(self.q_linears, order, row_perm=pm)
+        wa, ba = stack_linears(self.a_linears, order, col_perm=pm)
+        tpc = plan.type_ptr_c()
+        kvq = TypedLinearFn.apply(x, torch.cat([wk, wv, wq], 1), torch.cat([bk, bv, bq], 1), plan.type_ptr, tpc)
+        agg = HeteroAttnFn.apply(kvq, self.e_linear.weight, self.e_linear.bias, plan, D, H)        # HEATNet4.py:103-119
+        lin = self.drop(TypedLinearFn.apply(agg, wa, ba, plan.type_ptr, tpc))                      # :134
+        alpha = torch.sigmoid(self.skip[torch.tensor(order, device=x.device)])[plan.row_types()].unsqueeze(1)
+        out = lin * alpha + x * (1 - alpha)                                                        # :135
+        return torch.where(plan.node_inv_r.unsqueeze(1) != 0, out, x)                              # KeyError passthrough :129-133
+
     def forward_packed(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
         """x [N, in] type-major packed -> [N, out]."""
         D, H = self.out_size, self.n_heads
@@ -179,6 +202,12 @@ class _HEATBase(nn.Module):
         x = packed_features(G, plan, h)
         params = param_list(self, "in", lambda: (p for m in self.adapt_ws for p in m.parameters()))
         w_in, b_in = self._packs.get(("in", tuple(order)), params, lambda: stack_linears(self.adapt_ws, order))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in param_list(self, "all", self.parameters)):
+            w_in_g, b_in_g = stack_linears(self.adapt_ws, order)                             # with grad tracking
+            x = TypedLinearFn.apply(x, w_in_g, b_in_g, plan.type_ptr, plan.type_ptr_c())
+            for layer in self.gcs:
+                x = layer.forward_train(plan, x)
+            return plan, x
         F_in, D = int(x.shape[1]), int(w_in.shape[1])
         if len(self.gcs) > 0 and ops.tc_ok(plan.N, F_in, D) and all(l.tc_chain_ok(plan) for l in self.gcs):
             # tensor-core chain on pre-split bf16 [hi; lo] operands: one conversion pass for the raw features,
@@ -208,6 +237,15 @@ class _HEATBase(nn.Module):
         w_p, b_p = self._packs.get(("pred", tuple(names)), params, build)
         return ops.typed_linear(pooled, w_p, b_p, plan.readout_ptr(), row_scale=readout_scale(plan, G.independent))
 
+
+    def _readout_train(self, G, plan, x):
+        """[T*B, n_pred] = linears_prediction[type](pool_type(x)) with the empty-type zero block, differentiable."""
+        names = list(plan.ntypes)
+        pooled = SegmentPoolFn.apply(x, plan, len(names) * plan.B, self.graph_pooling_type)
+        w_p = torch.stack([self.linears_prediction[nt].weight for nt in names])
+        b_p = torch.stack([self.linears_prediction[nt].bias for nt in names])
+        o = TypedLinearFn.apply(pooled, w_p, b_p, plan.readout_ptr(), None)
+        return o * readout_scale(plan, G.independent).unsqueeze(1)
 
     def _readout_affine(self, G, plan, x, collapse_heads: bool):
         """[B, out_dim] logits by the fused pool + affine kernel.  HEATNet2: M_t = linears_prediction[t]
@@ -264,6 +302,13 @@ class HEATNet4(_HEATBase):
     def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
         plan, x = self._trunk(G, h)
         T, B = len(plan.ntypes), plan.B
+        if x.requires_grad:                                             # training: explicit, differentiable chain
+            o = self._readout_train(G, plan, x)                         # [T*B, 256]      :216-240
+            z = o.view(T, B, 256).permute(1, 0, 2).reshape(B, T * 256)  # cat(dim=1) in G.ntypes order
+            one = [0, B]
+            for head in (self.head_2, self.head_1, self.head):          # :243-245
+                z = TypedLinearFn.apply(z, head.weight.unsqueeze(0), head.bias.unsqueeze(0), one, None)
+            return (z, unpack_rows(plan, x)) if return_embeddings else z
         if self.head.out_features <= ops.AFFINE_MAX_OUT and not self.explicit_heads:
             g = self._readout_affine(G, plan, x, collapse_heads=True)   # :216-245 as one fused launch pair
             return (g, unpack_rows(plan, x)) if return_embeddings else g
@@ -295,6 +340,9 @@ class HEATNet2(_HEATBase):
     def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
         plan, x = self._trunk(G, h)
         T, B = len(plan.ntypes), plan.B
+        if x.requires_grad:                                             # training: differentiable readout
+            g = self._readout_train(G, plan, x).view(T, B, -1).sum(0)   # HEATNet2.py:181-194
+            return (g, unpack_rows(plan, x)) if return_embeddings else g
         n_pred = next(iter(self.linears_prediction.values())).out_features
         if n_pred <= ops.AFFINE_MAX_OUT:
             g = self._readout_affine(G, plan, x, collapse_heads=False)  # HEATNet2.py:181-194

@@ -215,6 +215,30 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
     return agg_split if split_out else agg
 
 
+def hetero_attn_bwd(k, v, q, rowptr, e_src, e_sim, e_rel, node_inv_r, e_w, e_b, D: int, H: int, d_agg: torch.Tensor,
+                    dk: torch.Tensor, dv: torch.Tensor, dq: torch.Tensor) -> torch.Tensor:
+    """Backward of the HEAT edge attention; see wsi_hetero_attn_bwd.  dk / dv must be zero-filled (accumulated into),
+    dq is written.  -> d_e fp32 [2] = (d e_linear.weight, d e_linear.bias)."""
+    lib = _lib.load()
+    stream = _prep(q)
+    N = int(q.shape[0])
+    kp, ldk = _rows(k, "k")
+    vp, ldv = _rows(v, "v")
+    qp, ldq = _rows(q, "q")
+    gp, ldg = _rows(d_agg, "d_agg")
+    dkp, lddk = _rows(dk, "dk")
+    dvp, lddv = _rows(dv, "dv")
+    dqp, lddq = _rows(dq, "dq")
+    d_e = torch.zeros(2, dtype=torch.float32, device=q.device)
+    rc = lib.wsi_hetero_attn_bwd(kp, ldk, vp, ldv, qp, ldq, _vec(rowptr, "rowptr", torch.int32),
+                                 _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
+                                 _vec(e_rel, "e_rel", torch.uint8), _vec(node_inv_r, "node_inv_r"),
+                                 _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, D, H, gp, ldg, dkp, lddk,
+                                 dvp, lddv, dqp, lddq, d_e.data_ptr(), stream)
+    _lib.check(rc, "wsi_hetero_attn_bwd")
+    return d_e
+
+
 def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int, use_head_perm: bool = False):
     """HGT edge attention over (dst, relation) segments; see wsi_hetero_attn_seg_fwd."""
     lib = _lib.load()
