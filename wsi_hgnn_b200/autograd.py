@@ -9,6 +9,36 @@ import torch
 from . import ops
 
 
+_MM_OUT_DTYPE = [None]      # does torch.mm(bf16, bf16, out_dtype=fp32) exist in this build?
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, tp: Sequence[int]) -> torch.Tensor:
+    """dW[t] = dY_t^T X_t, a plain dense GEMM per node type -> library call (cuBLAS).  fp32-accurate at tensor-core
+    speed: both operands go through the product's own fp32 -> bf16 [hi; lo] split kernel and the product is
+    hi.hi + hi.lo + lo.hi accumulated in fp32 (the same 3-term scheme as the forward GEMM); plain fp32 cuBLAS when this
+    torch build has no mm(out_dtype=)."""
+    T = len(tp) - 1
+    N = int(tp[-1])
+    if _MM_OUT_DTYPE[0] is not False and N > 0 and x.shape[1] % 8 == 0 and dy.shape[1] % 8 == 0:
+        try:
+            xs, ds = ops.split_bf16(x), ops.split_bf16(dy)
+            out = []
+            for t in range(T):
+                a, z = tp[t], tp[t + 1]
+                dh, dl, xh, xl = ds[a:z].t(), ds[N + a:N + z].t(), xs[a:z], xs[N + a:N + z]
+                w = torch.mm(dh, xh, out_dtype=torch.float32)
+                w += torch.mm(dh, xl, out_dtype=torch.float32)
+                w += torch.mm(dl, xh, out_dtype=torch.float32)
+                out.append(w)
+            _MM_OUT_DTYPE[0] = True
+            return torch.stack(out)
+        except (TypeError, NotImplementedError, RuntimeError):
+            if _MM_OUT_DTYPE[0] is True:
+                raise
+            _MM_OUT_DTYPE[0] = False
+    return torch.stack([dy[tp[t]:tp[t + 1]].t() @ x[tp[t]:tp[t + 1]] for t in range(T)])
+
+
 class TypedLinearFn(torch.autograd.Function):
     """y[rows of type t] = x[rows of type t] @ w[t].T + b[t]   (reference: the per-node-type nn.Linear calls)."""
 
@@ -29,7 +59,7 @@ class TypedLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:                      # dgrad: the same typed GEMM with W^T
             dx = ops.typed_linear(dy, w.transpose(1, 2).contiguous(), None, tp, type_ptr_c=ctx.type_ptr_c)
         if ctx.needs_input_grad[1]:                      # wgrad: plain dense GEMM per node type (cuBLAS)
-            dw = torch.stack([dy[tp[t]:tp[t + 1]].t() @ x[tp[t]:tp[t + 1]] for t in range(len(tp) - 1)])
+            dw = _wgrad(dy, x, tp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.stack([dy[tp[t]:tp[t + 1]].sum(0) for t in range(len(tp) - 1)])
         return dx, dw, db, None, None
@@ -75,3 +105,29 @@ class SegmentPoolFn(torch.autograd.Function):
         if ctx.op == "mean":
             d = d * inv_n.unsqueeze(1)
         return d, None, None, None
+
+
+class SkipMixFn(torch.autograd.Function):
+    """out = lin * sigma(skip_t) + x * (1 - sigma(skip_t)) per node type; rows whose type has no incoming relation keep x
+    (models/HEATNet4.py:122-136 incl. the KeyError passthrough :129-133).  Written as one Function because the
+    generic autograd of a per-row gather of sigma(skip) is an atomic scatter of N values into T addresses."""
+
+    @staticmethod
+    def forward(ctx, lin, x, skip_t, type_ptr: Sequence[int], gate):
+        T = len(type_ptr) - 1
+        counts = torch.tensor([type_ptr[t + 1] - type_ptr[t] for t in range(T)], device=x.device)
+        alpha_t = torch.sigmoid(skip_t)
+        a_row = torch.repeat_interleave(alpha_t, counts).unsqueeze(1) * (gate != 0).unsqueeze(1)   # 0 => passthrough
+        ctx.save_for_backward(lin, x, a_row, alpha_t)
+        ctx.type_ptr = list(type_ptr)
+        return lin * a_row + x * (1 - a_row)
+
+    @staticmethod
+    def backward(ctx, dout):
+        lin, x, a_row, alpha_t = ctx.saved_tensors
+        tp = ctx.type_ptr
+        d_lin = dout * a_row
+        d_x = dout * (1 - a_row)
+        s_row = (dout * (lin - x)).sum(1) * (a_row.squeeze(1) != 0)
+        d_alpha = torch.stack([s_row[tp[t]:tp[t + 1]].sum() for t in range(len(tp) - 1)])
+        return d_lin, d_x, d_alpha * alpha_t * (1 - alpha_t), None, None

@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..autograd import HeteroAttnFn, SegmentPoolFn, TypedLinearFn
+from ..autograd import HeteroAttnFn, SegmentPoolFn, SkipMixFn, TypedLinearFn
 from ..hetero_graph import GraphPlan, HeteroGraph
 from ._packing import PackCache, param_list, stack_linears
 
@@ -154,9 +154,8 @@ class HEATLayer(nn.Module):
         kvq = TypedLinearFn.apply(x, torch.cat([wk, wv, wq], 1), torch.cat([bk, bv, bq], 1), plan.type_ptr, tpc)
         agg = HeteroAttnFn.apply(kvq, self.e_linear.weight, self.e_linear.bias, plan, D, H)        # HEATNet4.py:103-119
         lin = self.drop(TypedLinearFn.apply(agg, wa, ba, plan.type_ptr, tpc))                      # :134
-        alpha = torch.sigmoid(self.skip[torch.tensor(order, device=x.device)])[plan.row_types()].unsqueeze(1)
-        out = lin * alpha + x * (1 - alpha)                                                        # :135
-        return torch.where(plan.node_inv_r.unsqueeze(1) != 0, out, x)                              # KeyError passthrough :129-133
+        skip_t = self.skip[torch.tensor(order, device=x.device)]
+        return SkipMixFn.apply(lin, x, skip_t, plan.type_ptr, plan.node_inv_r)                     # :135, passthrough :129-133
 
     def forward_packed(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
         """x [N, in] type-major packed -> [N, out]."""
