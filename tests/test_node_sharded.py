@@ -1,0 +1,192 @@
+"""Node-sharded single-slide forward: host-side planning on CPU, the exchange plumbing over
+gloo (world_size 2), and - on the GPU - parity of the sharded path (virtual ranks on one device, the very same rank
+code) with the unsharded CUDA forward and with the oracle."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import golden_util
+import helpers
+from wsi_hgnn_b200 import synthetic
+from wsi_hgnn_b200.node_sharded import (DistComm, LocalComm, _assemble_edges, _resolve_local, balanced_row_ranges,
+                                        clip_ptr, padded_ids)
+
+
+def test_balanced_row_ranges_cover_and_balance():
+    g = torch.Generator().manual_seed(3)
+    deg = torch.randint(0, 12, (5000,), generator=g)
+    deg[::500] = 400                                                    # hubs
+    rowptr = [0] + torch.cumsum(deg, 0).tolist()
+    for world in (1, 2, 3, 4, 8):
+        b = balanced_row_ranges(rowptr, world, row_cost=8.0)
+        assert b[0] == 0 and b[-1] == 5000 and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        cost = [(rowptr[b[p + 1]] - rowptr[b[p]]) + 8.0 * (b[p + 1] - b[p]) for p in range(world)]
+        assert max(cost) <= sum(cost) / world + 400 + 8 + 1e-6          # off by at most one (hub) row
+    assert balanced_row_ranges([0], 3) == [0, 0, 0, 0]                  # empty graph
+    with pytest.raises(ValueError):
+        balanced_row_ranges(rowptr, 0)
+
+
+def test_clip_ptr_and_padded_ids():
+    assert clip_ptr([0, 10, 25, 40], 8, 30) == [0, 2, 17, 22]
+    assert clip_ptr([0, 10, 25, 40], 0, 40) == [0, 10, 25, 40]
+    assert clip_ptr([0, 10, 25, 40], 30, 30) == [0, 0, 0, 0]
+    bounds, n_max = [0, 4, 4, 9, 12], 5                                 # rank 1 owns nothing
+    ids = torch.arange(12)
+    pad = padded_ids(ids, bounds, n_max).tolist()
+    assert pad == [0, 1, 2, 3, 10, 11, 12, 13, 14, 15, 16, 17]
+
+
+def test_local_comm_collectives():
+    hub = LocalComm(3)
+    bufs = [torch.zeros(3, 2, 4) for _ in range(3)]
+    for r in range(3):
+        bufs[r][r] = r + 1.0
+        hub.view(r).all_gather_blocks(bufs[r])
+    _resolve_local(hub)
+    for r in range(3):
+        assert all(float(bufs[r][p].mean()) == p + 1.0 for p in range(3))
+    red = [torch.full((2, 2), float(r)) for r in range(3)]
+    mx = [torch.full((2,), float(-r)) for r in range(3)]
+    for r in range(3):
+        hub.view(r).all_reduce(red[r], "sum")
+        hub.view(r).all_reduce(mx[r], "max")
+    _resolve_local(hub)
+    assert all(float(t[0, 0]) == 3.0 for t in red) and all(float(t[0]) == 0.0 for t in mx)
+    hub.view(0).all_reduce(red[0], "sum")
+    with pytest.raises(RuntimeError):
+        _resolve_local(hub)
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = DistComm()
+        g = torch.Generator().manual_seed(5)
+        N, C, k = 37, 6, 3
+        full = torch.randn(N, C, generator=g)
+        nbr_full = torch.randint(0, N, (N, k), generator=g, dtype=torch.int32)
+        rowptr = [0] + torch.cumsum(torch.randint(0, 9, (N,), generator=g), 0).tolist()
+        bounds = balanced_row_ranges(rowptr, world, 2.0)
+        n_max = max(bounds[p + 1] - bounds[p] for p in range(world))
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        # K|V-style exchange: own rows -> padded blocks -> gather by remapped ids == gather from the full matrix
+        buf = torch.zeros(world, n_max, C)
+        buf[rank, :r1 - r0] = full[r0:r1]
+        comm.all_gather_blocks(buf)
+        ids = torch.randint(0, N, (200,), generator=g)
+        got = buf.view(world * n_max, C)[padded_ids(ids, bounds, n_max).long()]
+        ok_gather = bool(torch.equal(got, full[ids]))
+        # readout-style reduction: partial (sum | count) of a row segment -> mean over all rows
+        part = torch.cat([full[r0:r1].sum(0), torch.tensor([float(r1 - r0)])])
+        comm.all_reduce(part, "sum")
+        ok_mean = bool(torch.allclose(part[:C] / part[C], full.mean(0), atol=1e-6))
+        mx = full[r0:r1].max(0).values if r1 > r0 else torch.full((C,), float("-inf"))
+        comm.all_reduce(mx, "max")
+        ok_max = bool(torch.equal(mx, full.max(0).values))
+        # edge-builder assembly from per-rank neighbour blocks
+        nb = torch.zeros(world, n_max, k, dtype=torch.int32)
+        sm = torch.zeros(world, n_max, k)
+        nb[rank, :r1 - r0] = nbr_full[r0:r1]
+        sm[rank, :r1 - r0] = nbr_full[r0:r1].float() - 3.0
+        comm.all_gather_blocks(nb)
+        comm.all_gather_blocks(sm)
+        ei, et, sim = _assemble_edges(nb, sm, bounds, k)
+        ok_edges = (bool(torch.equal(ei[1], nbr_full.reshape(-1).long())) and
+                    bool(torch.equal(ei[0], torch.arange(N).repeat_interleave(k))) and
+                    bool(torch.equal(et, (sim > 0).to(torch.uint8))))
+        q.put((rank, ok_gather, ok_mean, ok_max, ok_edges))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_over_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert all(r[1:]), r
+
+
+# ------------------------------------------------------------------------------------------------ GPU parity
+def _model_and_graph(cls_name, pooling, n=3000, T=3, D=128, F=96, L=2, seed=4):
+    kw = dict(in_dim=F, hidden_dim=D, out_dim=3, n_layers=L, n_heads=4, dropuout=0.0, graph_pooling_type=pooling)
+    ours = helpers.build_ours(cls_name, T, kw)
+    orc = helpers.build_oracle(cls_name, T, kw)
+    golden_util.fill_params(ours, 23)
+    orc.load_state_dict(ours.state_dict(), strict=True)
+    G = synthetic.synth_slide_graph(n, F, T, 6, seed=seed, noise_edges=0.1)
+    return ours.eval(), orc.eval(), G
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls_name,pooling", [("HEATNet4", "mean"), ("HEATNet4", "max"), ("HEATNet2", "sum")])
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_virtual_ranks_match_unsharded_and_oracle(cls_name, pooling, world):
+    from wsi_hgnn_b200.node_sharded import run_virtual_ranks
+    ours, orc, G = _model_and_graph(cls_name, pooling)
+    dev = torch.device("cuda", 0)
+    ours = ours.to(dev)
+    Gd = G.to(dev)
+    with torch.no_grad():
+        ref_logits, ref_emb = ours(Gd, return_embeddings=True)
+        orc_logits = orc(G)
+    logits, per_rank, embs, ranks = run_virtual_ranks(ours, Gd, world)
+    for o in per_rank:                                                   # identical on every rank
+        assert torch.equal(o, logits)
+    plan = Gd.plan()
+    full = torch.cat([ref_emb[nt] for nt in plan.ntypes if ref_emb[nt].shape[0] > 0], 0)
+    got = torch.cat(embs, 0)
+    assert got.shape == full.shape
+    assert helpers.rel_err(got, full) < 2e-5                             # same kernels, different row grouping
+    assert helpers.rel_err(logits, ref_logits) < 2e-5
+    assert helpers.rel_err(logits, orc_logits) < 1e-3                    # north_star tolerance
+    assert sum(s.n_loc for s in ranks) == plan.N
+
+
+@pytest.mark.gpu
+def test_virtual_ranks_uneven_and_empty_rank():
+    from wsi_hgnn_b200.node_sharded import run_virtual_ranks
+    ours, orc, G = _model_and_graph("HEATNet4", "mean", n=1500)
+    dev = torch.device("cuda", 0)
+    ours = ours.to(dev)
+    Gd = G.to(dev)
+    with torch.no_grad():
+        ref = ours(Gd)
+    N = Gd.plan().N
+    logits, _, _, _ = run_virtual_ranks(ours, Gd, 3, bounds=[0, 700, 700, N])     # rank 1 owns no rows
+    assert helpers.rel_err(logits, ref) < 2e-5
+
+
+@pytest.mark.gpu
+def test_sharded_edge_builder_is_bit_exact():
+    from wsi_hgnn_b200.construct_graph.graph_constructor import construct_graph_arrays
+    from wsi_hgnn_b200.node_sharded import knn_edges_rank
+    dev = torch.device("cuda", 0)
+    feats = synthetic.synth_features(2500, 64, 3, seed=9)[0].to(dev).contiguous()
+    radius, world = 7, 3
+    ei, et, sim = construct_graph_arrays(feats, radius)
+    n = feats.shape[0]
+    bounds = [n * p // world for p in range(world + 1)]
+    n_max = max(bounds[p + 1] - bounds[p] for p in range(world))
+    nb = torch.zeros(world, n_max, radius - 1, dtype=torch.int32, device=dev)
+    sm = torch.zeros(world, n_max, radius - 1, device=dev)
+    for p in range(world):
+        nb[p, :bounds[p + 1] - bounds[p]], sm[p, :bounds[p + 1] - bounds[p]] = knn_edges_rank(feats, radius, bounds[p], bounds[p + 1])
+    ei2, et2, sim2 = _assemble_edges(nb, sm, bounds, radius - 1)
+    assert torch.equal(ei, ei2) and torch.equal(et, et2) and torch.equal(sim, sim2)

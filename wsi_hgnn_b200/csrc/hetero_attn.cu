@@ -51,7 +51,7 @@ struct AttnArgs {
   int64_t split_lo;           // element offset of the lo half (n_rows * D)
   // fused merge of the split rows (TMA kernel): split index of every partial, per-split-row arrival counter
   const int* part_split; int* split_cnt;
-  int dbg;                    // development only (env WSI_ATTN_DEBUG): 1 = gather only 64 distinct rows
+  int dbg;                    // development only (env WSI_ATTN_DEBUG): 1 = gather only 64 distinct rows, 2 = no bulk copies, 3 = no math
   int* sched;                 // optional int32 [2], zero before the first launch: dynamic work queue (next item | warps done)
   const int* split_row; const int* split_ptr; const int* part_rel;
 };
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
           int s = rs;
           for (int j = 0; j < pre; ++j) {
             const int src = __shfl_sync(FULL, my_src, j);
-            if (lane == 0) {
+            if (lane == 0 && a.dbg != 2) {
               const uint32_t bar = bars_u32 + 8 * s, dst = slots_u32 + s * SLOT_BYTES;
               mbar_expect_tx(bar, SLOT_BYTES);
               if (kv_adjacent) {                        // K|V of a node are one contiguous 2 * D * 4 byte run
@@ -486,10 +486,11 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
               int su = rs + u;
               uint32_t pu = rpar;
               if (su >= ring) { su -= ring; pu ^= 1; }
-              mbar_wait(bars_u32 + 8 * su, pu);
+              if (a.dbg != 2) mbar_wait(bars_u32 + 8 * su, pu);
               const float* ks = reinterpret_cast<const float*>(my_slots + (size_t)su * SLOT_BYTES);
               slot_ptr[u] = ks;
               float d0 = 0.f, d1 = 0.f;
+              if (a.dbg != 3)
 #pragma unroll
               for (int i = 0; i < NV; ++i) {
                 const float4 kk = *reinterpret_cast<const float4*>(ks + (i * 32 + lane) * 4);
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
           for (int i = 0; i < NV; ++i) { acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr; }
 #pragma unroll
           for (int u = 0; u < BMAX; ++u) {
-            if (u < g) {
+            if (u < g && a.dbg != 3) {
               const float* vs = slot_ptr[u] + NV * 128;
 #pragma unroll
               for (int i = 0; i < NV; ++i) {
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
           for (int u = 0; u < g; ++u) {                 // refill them with the edges `ring` positions ahead
             const int nxt = j + u + ring;
             const int src = __shfl_sync(FULL, my_src, nxt & 31);
-            if (nxt < n && lane == 0) {
+            if (nxt < n && lane == 0 && a.dbg != 2) {
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               const uint32_t bar = bars_u32 + 8 * rs, dst = slots_u32 + rs * SLOT_BYTES;
               mbar_expect_tx(bar, SLOT_BYTES);
@@ -731,10 +732,11 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       int tb = (a.n_items + TMA_WARPS - 1) / TMA_WARPS;
       const int per_sm = 200 * 1024 / (smem + 1024) < 1 ? 1 : 200 * 1024 / (smem + 1024);
       if (tb > sms * per_sm) tb = sms * per_sm;
+      if (const char* b = getenv("WSI_ATTN_BLOCKS")) { const int cap = sms * atoi(b); if (cap > 0 && tb > cap) tb = cap; }   // development knob
       switch (a.D / 128) {
 #define CASE(NV) case NV: { \
         static bool attr_set = false; \
-        if (!attr_set) { WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; } \
+        if (!attr_set) { WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; } \
         attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE

@@ -167,7 +167,7 @@ struct TcArgs {
 };
 
 // FULL = false: v = act(acc + bias).  FULL = true: + dropout mask, sigma(skip) residual mix with row gate, row scale.
-template <bool FULL>
+template <bool FULL, bool GELU>
 __device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc, float4 bb, float4 mm, float4 rr,
                                            float alpha, bool gate_open, float rscale) {
   float a[4] = {acc.x, acc.y, acc.z, acc.w};
@@ -175,7 +175,7 @@ __device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc,
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float v = a[i] + b4[i];
-    if (ep.act == WSI_ACT_GELU) v = wsi_gelu(v);
+    if (GELU) v = wsi_gelu(v);
     if (FULL) {
       v *= m4[i];
       if (ep.skip) v = gate_open ? (v * alpha + r4[i] * (1.0f - alpha)) : r4[i];
@@ -186,7 +186,7 @@ __device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc,
   return make_float4(a[0], a[1], a[2], a[3]);
 }
 
-template <bool FULL>
+template <bool FULL, bool GELU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ TypeSegs segs, const __grid_constant__ LinearEpilogue ep, TcArgs a) {
@@ -344,8 +344,8 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int it = 0; it < 8; ++it) {
           if (n_ok && it * 4 < rows_left ) {
             const float4 accv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * EPI_LD + ((((lane & 7) ^ ((it * 4 + rsub) & 7))) << 2));
-            const float4 o = FULL ? epi_mix4<true>(ep, accv, bb, mm[it], rr[it], alpha, gate[it] != 0.f, rscl[it])
-                                  : epi_mix4<false>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
+            const float4 o = FULL ? epi_mix4<true, GELU>(ep, accv, bb, mm[it], rr[it], alpha, gate[it] != 0.f, rscl[it])
+                                  : epi_mix4<false, GELU>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
             if (ep.y) *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
             if (a.y_split) {
               __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
@@ -444,9 +444,10 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(typed_linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(typed_linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    const void* fns[4] = {(const void*)typed_linear_tc_kernel<false, false>, (const void*)typed_linear_tc_kernel<true, false>,
+                          (const void*)typed_linear_tc_kernel<false, true>, (const void*)typed_linear_tc_kernel<true, true>};
+    for (int i = 0; i < 4 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   WSI_CHECK_CUDA(attr_err);
   int sms = wsi_num_sms();
@@ -466,8 +467,11 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   const int total = a.n_tiles_m * a.n_tiles_n;
   if (total == 0) return WSI_OK;
   const int pairs = total < sms / 2 ? total : sms / 2;               // one CTA pair (cluster of 2) per two SMs
-  if (full) typed_linear_tc_kernel<true><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
-  else typed_linear_tc_kernel<false><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
+  const bool gelu = ep.act == WSI_ACT_GELU;       // compile-time in the kernel: the erf code must not sit (predicated off) in the plain epilogue
+  if (full && gelu) typed_linear_tc_kernel<true, true><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
+  else if (full) typed_linear_tc_kernel<true, false><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
+  else if (gelu) typed_linear_tc_kernel<false, true><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
+  else typed_linear_tc_kernel<false, false><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }

@@ -225,6 +225,10 @@ class _HEATBase(nn.Module):
     def _readout(self, G, plan, x):
         """[T*B, n_pred] = linears_prediction[type](pool_type(x)) with the empty-type zero block."""
         pooled = ops.segment_pool(x, plan.seg_ptr, len(plan.ntypes) * plan.B, self.graph_pooling_type)
+        return self._predict_pooled(G, plan, pooled)
+
+    def _predict_pooled(self, G, plan, pooled):
+        """[T*B, D] pooled (type-major) -> [T*B, n_pred] = linears_prediction[type](pooled) with the empty-type zero block."""
         names = list(plan.ntypes)
         params = param_list(self, ("pred", tuple(names)), lambda: (p for nt in names for p in self.linears_prediction[nt].parameters()))
 
@@ -311,14 +315,21 @@ class HEATNet4(_HEATBase):
         if self.head.out_features <= ops.AFFINE_MAX_OUT and not self.explicit_heads:
             g = self._readout_affine(G, plan, x, collapse_heads=True)   # :216-245 as one fused launch pair
             return (g, unpack_rows(plan, x)) if return_embeddings else g
-        o = self._readout(G, plan, x)                                   # [T*B, 256]      :216-240
+        g = self._heads(self._readout(G, plan, x), T, B)                # :216-245
+        return (g, unpack_rows(plan, x)) if return_embeddings else g
+
+    def _heads(self, o, T, B):
+        """[T*B, 256] per-type predictions -> cat(dim=1) in G.ntypes order -> head_2 -> head_1 -> head (:240-245)."""
         z = o if B == 1 else o.view(T, B, 256).permute(1, 0, 2).contiguous()
-        z = z.view(B, T * 256)                                          # cat(dim=1) in G.ntypes order
+        z = z.view(B, T * 256)
         one = [0, B]
         z = ops.typed_linear(z, self.head_2.weight.unsqueeze(0), self.head_2.bias.unsqueeze(0), one)   # :243
         z = ops.typed_linear(z, self.head_1.weight.unsqueeze(0), self.head_1.bias.unsqueeze(0), one)   # :244
-        g = ops.typed_linear(z, self.head.weight.unsqueeze(0), self.head.bias.unsqueeze(0), one)       # :245
-        return (g, unpack_rows(plan, x)) if return_embeddings else g
+        return ops.typed_linear(z, self.head.weight.unsqueeze(0), self.head.bias.unsqueeze(0), one)    # :245
+
+    def logits_from_pooled(self, G, plan, pooled):
+        """[T*B, D] typed readout (already reduced, e.g. over the ranks of a node-sharded slide) -> logits [B, out]."""
+        return self._heads(self._predict_pooled(G, plan, pooled), len(plan.ntypes), plan.B)
 
 
 class HEATNet2(_HEATBase):
@@ -349,3 +360,7 @@ class HEATNet2(_HEATBase):
         o = self._readout(G, plan, x)                                   # [T*B, out]   HEATNet2.py:181-194
         g = o.view(T, B, -1).sum(0)
         return (g, unpack_rows(plan, x)) if return_embeddings else g
+
+    def logits_from_pooled(self, G, plan, pooled):
+        """[T*B, D] typed readout (already reduced over the ranks of a node-sharded slide) -> logits [B, out]."""
+        return self._predict_pooled(G, plan, pooled).view(len(plan.ntypes), plan.B, -1).sum(0)
