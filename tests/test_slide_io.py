@@ -1,0 +1,83 @@
+"""Flat slide format and the streaming evaluator (8f-1)."""
+import os
+
+import pytest
+import torch
+
+import golden_util
+import helpers
+from wsi_hgnn_b200 import synthetic
+from wsi_hgnn_b200.slide_io import FlatSlide, stream_forward
+
+
+def _same_graph(a, b):
+    assert a.ntypes == b.ntypes and a.canonical_etypes == b.canonical_etypes
+    for nt in a.ntypes:
+        assert a.num_nodes(nt) == b.num_nodes(nt)
+        if a.num_nodes(nt):
+            assert torch.equal(a.nodes[nt].data["feat"].cpu(), b.nodes[nt].data["feat"].cpu())
+    for ce in a.canonical_etypes:
+        for x, y in zip(a._edges[ce], b._edges[ce]):
+            assert torch.equal(x.cpu(), y.cpu())
+        assert torch.equal(a._edata[ce]["sim"].cpu().float(), b._edata[ce]["sim"].cpu().float())
+
+
+def test_flat_round_trip_memory_and_file(tmp_path):
+    G = synthetic.random_hetero_graph([40, 0, 25], 300, 12, seed=3)          # one empty node type
+    fs = FlatSlide.from_graph(G)
+    _same_graph(G, fs.to_graph("cpu"))
+    p = os.path.join(tmp_path, "slide.wsiflat")
+    fs.save(p)
+    for mmap in (True, False):
+        back = FlatSlide.load(p, mmap=mmap)
+        assert back.header == fs.header
+        _same_graph(G, back.to_graph("cpu"))
+    with open(p, "r+b") as f:
+        f.write(b"garbage!")
+    with pytest.raises(ValueError):
+        FlatSlide.load(p)
+
+
+def test_flat_packed_view_is_zero_copy_and_plan_matches():
+    G = synthetic.random_hetero_graph([30, 20], 200, 8, seed=5)
+    H = FlatSlide.from_graph(G).to_graph("cpu")
+    packed = H.packed_ndata("feat")
+    assert packed.data_ptr() == H.nodes[H.ntypes[0]].data["feat"].data_ptr()          # no concatenation copy
+    assert torch.equal(packed, G.packed_ndata("feat"))
+    pa, pb = G.plan(), H.plan()
+    for name in ("rowptr", "e_src", "e_sim", "e_rel", "node_inv_r"):
+        assert torch.equal(getattr(pa, name), getattr(pb, name)), name
+    H.nodes[H.ntypes[0]].data["feat"] = torch.zeros(30, 8)                             # user replaces a tensor:
+    assert torch.equal(H.packed_ndata("feat")[:30], torch.zeros(30, 8))                # the view must not be used
+
+
+def test_flat_rejects_batched_and_short_blob():
+    from wsi_hgnn_b200.hetero_graph import batch
+    gs = [synthetic.random_hetero_graph([10, 10], 40, 4, seed=s) for s in (1, 2)]
+    with pytest.raises(ValueError):
+        FlatSlide.from_graph(batch(gs))
+    fs = FlatSlide.from_graph(gs[0])
+    with pytest.raises(ValueError):
+        FlatSlide(fs.header, fs.blob[:16])
+
+
+@pytest.mark.gpu
+def test_stream_forward_matches_per_slide_forward():
+    dev = torch.device("cuda", 0)
+    T = 3
+    kw = dict(in_dim=64, hidden_dim=128, out_dim=3, n_layers=2, n_heads=4, dropuout=0.0)
+    ours = helpers.build_ours("HEATNet4", T, kw)
+    golden_util.fill_params(ours, 31)
+    ours = ours.to(dev).eval()
+    graphs = [synthetic.synth_slide_graph(400 + 173 * i, 64, T, 5, seed=60 + i, noise_edges=0.1) for i in range(7)]
+    slides = [FlatSlide.from_graph(g, pin=True) for g in graphs]
+    with torch.no_grad():
+        ref = [ours(g.to(dev)).cpu() for g in graphs]
+    for depth in (1, 2, 3):
+        outs = list(stream_forward(ours, slides, dev, depth=depth))
+        assert len(outs) == len(ref)
+        for o, r in zip(outs, ref):
+            assert torch.equal(o, r)                                  # same kernels, same inputs: bit-identical
+    assert list(stream_forward(ours, [], dev)) == []
+    with pytest.raises(RuntimeError):
+        list(stream_forward(ours, slides, "cpu"))

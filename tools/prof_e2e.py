@@ -1,39 +1,47 @@
-"""Where the end-to-end (host buffers -> logits) time of one config-2 slide goes: H2D, plan build, forward."""
-import os, sys, time
+"""Where the end-to-end (pinned host blob -> logits) time of config-2 slides goes: stage timings of one slide and a
+cProfile of slide_io.stream_forward (the host side is what bounds the streamed path)."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
 import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import bench
-from wsi_hgnn_b200.hetero_graph import HeteroGraph
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+from wsi_hgnn_b200.slide_io import FlatSlide, stream_forward  # noqa: E402
 
 dev = torch.device("cuda", 0)
 ours, _ = bench.build_models(False, True)
 ours = ours.to(dev)
-G_host = bench.make_graph(1)
-pinned = HeteroGraph.from_state(G_host.state())
-for fr in list(pinned._ndata.values()) + list(pinned._edata.values()):
-    for k_ in list(fr):
-        fr[k_] = fr[k_].pin_memory()
-for ce in list(pinned._edges):
-    s_, d_ = pinned._edges[ce]
-    pinned._edges[ce] = (s_.pin_memory(), d_.pin_memory())
+slides = [FlatSlide.from_graph(bench.make_graph(1 + i), pin=True) for i in range(4)]
 
-def sync(): torch.cuda.synchronize()
-def t(): sync(); return time.perf_counter()
+
+def t():
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
 for it in range(6):
-    t0 = t(); g = pinned.to(dev, non_blocking=True); t1 = t()
+    s = slides[it % 4]
+    t0 = t(); blob = s.blob[:s.header["nbytes"]].to(dev, non_blocking=True); t1 = t()
+    g = s.graph_on(blob); t1b = t()
     plan = g.plan(); t2 = t()
-    w = plan.attn_work(); t3 = t()
-    with torch.no_grad(): out = ours(g)
+    ours.prepare_plan(plan); t3 = t()
+    with torch.no_grad():
+        out = ours(g)
     t4 = t(); o = out.cpu(); t5 = t()
-    with torch.no_grad(): out = ours(g)
-    t6 = t()
     if it >= 3:
-        print(f"h2d {1e3*(t1-t0):.3f} ms | plan {1e3*(t2-t1):.3f} | attn_work {1e3*(t3-t2):.3f} | fwd(first on graph) {1e3*(t4-t3):.3f} | d2h {1e3*(t5-t4):.3f} | fwd(again) {1e3*(t6-t5):.3f}")
-import cProfile, pstats
-g = pinned.to(dev); sync()
+        print(f"h2d {1e3*(t1-t0):.3f} ms | graph views {1e3*(t1b-t1):.3f} | plan {1e3*(t2-t1b):.3f} | work list {1e3*(t3-t2):.3f} "
+              f"| fwd {1e3*(t4-t3):.3f} | d2h {1e3*(t5-t4):.3f}")
+many = [slides[i % 4] for i in range(40)]
+list(stream_forward(ours, many[:8], dev))
+t0 = t(); outs = list(stream_forward(ours, many, dev)); t1 = t()
+print(f"stream_forward: {1e3*(t1-t0)/len(many):.3f} ms / slide")
 pr = cProfile.Profile(); pr.enable()
-for _ in range(20):
-    with torch.no_grad(): ours(g)
-sync(); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+outs = list(stream_forward(ours, many, dev))
+torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(35)

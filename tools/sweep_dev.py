@@ -20,15 +20,22 @@ from wsi_hgnn_b200 import ops, synthetic  # noqa: E402
 
 
 def timeit(fn, reps, flush, warm=None):
+    """GPU time of fn: captured into a CUDA graph (so that the Python / ctypes cost of the call cannot show up as
+    GPU idle time between the two events), L2 flushed (and optionally re-warmed) before every replay."""
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for a, b in ev:
         flush.zero_()
         if warm is not None:
             warm()
         a.record()
-        fn()
+        g.replay()
         b.record()
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in ev)
@@ -47,6 +54,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--nodes", type=int, default=8192)
+    ap.add_argument("--gemm-dbg", action="store_true", help="also time the WSI_TC_DEBUG variants of the GEMM")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -63,7 +71,8 @@ def main():
         if full:
             kw = dict(skip=torch.ones(T, device=dev), res=torch.randn(N, n_out, device=dev),
                       row_gate=torch.ones(N, device=dev))
-        for dbg, tag in ((0, "full"), (1, "no MMA"), (2, "no TMA"), (4, "no epilogue body"), (5, "TMA only"), (6, "MMA only")):
+        tags = ((0, "full"), (1, "no MMA"), (2, "no TMA"), (4, "no epilogue body"), (5, "TMA only"), (6, "MMA only"))
+        for dbg, tag in (tags if args.gemm_dbg else tags[:1]):
             setenv(WSI_TC_DEBUG=dbg or None)
             for want_split in (False, True):
                 ms = timeit(lambda: ops.typed_linear_split(xs, ws, b, ptr, n_out, want_split=want_split, **kw), args.reps, flush)
@@ -83,10 +92,8 @@ def main():
     def warm():
         kvq.add_(0.0)
 
-    variants = [dict(), dict(WSI_ATTN_RING=2), dict(WSI_ATTN_RING=4), dict(WSI_ATTN_RING=6), dict(WSI_ATTN_DEBUG=1),
-                dict(WSI_ATTN_DEBUG=2), dict(WSI_ATTN_DEBUG=3), dict(WSI_ATTN_NO_TMA=1),
-                dict(WSI_ATTN_BLOCKS=1), dict(WSI_ATTN_BLOCKS=2), dict(WSI_ATTN_BLOCKS=3),
-                dict(WSI_ATTN_BLOCKS=2, WSI_ATTN_RING=6), dict(WSI_ATTN_BLOCKS=1, WSI_ATTN_RING=12)]
+    variants = [dict(), dict(WSI_ATTN_VARIANT="g4b3"), dict(WSI_ATTN_VARIANT="g1b5"), dict(WSI_ATTN_VARIANT="g1b6"),
+                dict(WSI_ATTN_VARIANT="g2b5"), dict(WSI_ATTN_KERNEL="ring")]
     keys = sorted({k for v in variants for k in v})
     for var in variants:
         setenv(**{k: var.get(k) for k in keys})

@@ -17,6 +17,7 @@
 // HBM-bound: algorithmic bytes per edge = 2*D*4 (K and V rows) + 9 (src id, sim, relation slot);
 // per dst row = 2*D*4 (q in, agg out) + 8 (rowptr, 1/R).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -67,13 +68,16 @@ __device__ __forceinline__ void st_split4(__nv_bfloat16* dst, int64_t lo_off, fl
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+struct MergeArgs;
+template <int NV> __device__ __noinline__ void merge_row(const MergeArgs& a, int h, int lane);
+template <int NV> __device__ __forceinline__ void vec_fused_merge(const AttnArgs& a, int slot, int lane);
+
 // ------------------------------------------------------------------------------------------------
 // Lane-grouped fast path: D = 128*NV, H | 32.  Lane l owns float4 slots {i*32 + l}, all of head l / G
 // (G = 32/H lanes per head) thanks to the head_perm column order (wsi_head_perm).
 // GROUP = edges whose K (then V) rows are in flight together (bounded by the register file: GROUP * NV float4)
-template <int NV, int MODE>
-__global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 2) attn_fwd_vec_kernel(AttnArgs a) {
-  constexpr int GROUP = NV <= 2 ? 8 : (NV <= 4 ? 4 : 2);
+template <int NV, int MODE, int GROUP, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs a) {
   const int lane = threadIdx.x & 31;
   const int G = 32 / a.H;
   const int head = lane / G;
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 2) attn_fwd_vec_kern
       float* o = a.part_acc + (int64_t)slot * a.D;
 #pragma unroll
       for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = acc[i];
+      if (a.split_cnt) vec_fused_merge<NV>(a, slot, lane);
     }
   }
 }
@@ -326,6 +331,30 @@ __device__ __noinline__ void merge_row(const MergeArgs& a, int h, int lane) {
     const float4 r = make_float4(out[i].x * invr, out[i].y * invr, out[i].z * invr, out[i].w * invr);
     if (a.out) *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + (i * 32 + lane) * 4) = r;
     if (a.out_split) st_split4(a.out_split + (int64_t)row * a.D + (i * 32 + lane) * 4, a.split_lo, r);
+  }
+}
+
+// Fused merge: the warp that writes the LAST chunk partial of a split row combines the row (per-row arrival counter,
+// self-resetting so the next launch starts from zero).
+template <int NV>
+__device__ __forceinline__ void vec_fused_merge(const AttnArgs& a, int slot, int lane) {
+  const int h = __ldg(a.part_split + slot);
+  __threadfence();
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    const int n_chunks = __ldg(a.split_ptr + h + 1) - __ldg(a.split_ptr + h);
+    last = atomicAdd(a.split_cnt + h, 1) == n_chunks - 1;
+    if (last) a.split_cnt[h] = 0;
+  }
+  last = __shfl_sync(FULL, last, 0);
+  if (last) {
+    __threadfence();
+    MergeArgs mg;
+    mg.split_row = a.split_row; mg.split_ptr = a.split_ptr; mg.part_rel = a.part_rel;
+    mg.part_ms = a.part_ms; mg.part_acc = a.part_acc; mg.inv_r = a.inv_r; mg.n_split = 0; mg.D = a.D;
+    mg.out = a.out; mg.ldo = a.ldo; mg.out_split = a.out_split; mg.split_lo = a.split_lo;
+    merge_row<NV>(mg, h, lane);
   }
 }
 
@@ -609,6 +638,294 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Item-pipelined TMA kernel (the one the forward uses).  The ring kernel above hides the K/V latency INSIDE an item,
+// but a work item is only ~5 edges and the dependent chain  queue index -> item descriptor -> edge ids -> K|V rows
+// is four serial memory round trips per item (ncu: the warps sit on the SHFL of the freshly loaded edge ids and on
+// the descriptor load).  Here every warp runs that chain as a software pipeline over its items:
+//     iteration i:  queue index of item i+4 | descriptor of i+3 | edge ids, sim, relation, 1/R of i+2 | q row of i+1
+//                   | K|V bulk copies of item i+1 go out as soon as item i's last copies are issued | math of item i
+// so each load was requested one whole item earlier than it is consumed and the per-warp ring of K|V slots stays full
+// across item boundaries (slots are consumed in FIFO order: item i's edges, then item i+1's).
+struct ItemDesc { int row, beg, end, slot; };
+struct ItemMeta { int src; float scale; int rel; float invr; float seg_scale; };
+
+template <int MODE>
+__device__ __forceinline__ ItemDesc pipe_load_desc(const AttnArgs& a, int idx) {
+  ItemDesc d; d.row = 0; d.beg = 0; d.end = 0; d.slot = -1;
+  if (idx < a.n_items) {
+    if (a.items) { const int4 it = __ldg(a.items + idx); d.row = it.x; d.beg = it.y; d.end = it.z; d.slot = it.w; }
+    else { d.row = idx; d.beg = __ldg(a.rowptr + idx); d.end = __ldg(a.rowptr + idx + 1); }
+  }
+  return d;
+}
+
+// edge window [beg, beg + 32) of an item: lane l holds edge beg + l
+template <int MODE>
+__device__ __forceinline__ ItemMeta pipe_load_meta(const AttnArgs& a, const ItemDesc& d, int beg, int lane, int head,
+                                                   float ew, float eb) {
+  ItemMeta m; m.src = 0; m.scale = 0.f; m.rel = 0; m.invr = 1.f; m.seg_scale = 0.f;
+  if (beg + lane < d.end) {
+    m.src = __ldg(a.e_src + beg + lane);
+    if (a.dbg == 1) m.src &= 63;
+    if (MODE == MODE_HEAT) {
+      m.scale = fmaf(ew, __ldg(a.e_sim + beg + lane), eb) * a.inv_sqrt_dk;
+      m.rel = __ldg(a.e_rel + beg + lane);
+    }
+  }
+  if (d.end > d.beg) {
+    if (MODE == MODE_HEAT) m.invr = __ldg(a.inv_r + d.row);
+    else m.seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + d.row) * a.H + head) * a.inv_sqrt_dk;
+  }
+  return m;
+}
+
+template <int NV, int MODE, int MINB>
+__global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? MINB : 1) attn_fwd_pipe_kernel(AttnArgs a, int ring) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int ROW_BYTES = NV * 512, SLOT_BYTES = 2 * ROW_BYTES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = 32 / a.H;
+  const int head = lane / G;
+  const int n_warps = gridDim.x * TMA_WARPS;
+  uint8_t* my_slots = smem + (size_t)warp * ring * SLOT_BYTES;
+  const uint32_t slots_u32 = smem_u32(my_slots);
+  const uint32_t bars_u32 = smem_u32(smem + (size_t)TMA_WARPS * ring * SLOT_BYTES) + warp * ring * 8;
+  if (lane == 0) {
+    for (int s = 0; s < ring; ++s) mbar_init(bars_u32 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float ew = 0.f, eb = 0.f;
+  if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
+  const bool kv_adjacent = a.V == a.K + a.D && a.ldk == a.ldv;
+  const int bmax = min(BMAX, ring);
+
+  int rs = 0; uint32_t rpar = 0;          // consumer side of the ring: next slot to read, its phase parity
+  int ws = 0;                             // producer side: next slot to fill
+  int inflight = 0;                       // slots filled or being filled
+
+  // issue the K|V copy of one edge into ring slot ws (all lanes call; lane 0 issues)
+  auto issue = [&](int src) {
+    if (lane == 0 && a.dbg != 2) {
+      const uint32_t bar = bars_u32 + 8 * ws, dst = slots_u32 + ws * SLOT_BYTES;
+      mbar_expect_tx(bar, SLOT_BYTES);
+      if (kv_adjacent) {
+        bulk_g2s(dst, a.K + (int64_t)src * a.ldk, SLOT_BYTES, bar);
+      } else {
+        bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
+        bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+      }
+    }
+    if (++ws == ring) ws = 0;
+    ++inflight;
+  };
+  // Queue index of a later item.  Dynamic queue: lane 0's atomicAdd result is NOT broadcast here - the shuffle would
+  // wait for the atomic's round trip; it is broadcast one iteration later, when the value is first needed.
+  auto next_index_raw = [&](int prev) -> int {
+    int v = prev + n_warps;
+    if (a.sched) { v = 0; if (lane == 0) v = atomicAdd(a.sched, 1); }
+    return v;
+  };
+  auto bcast = [&](int raw) -> int { return a.sched ? __shfl_sync(FULL, raw, 0) : raw; };
+
+  // ---- prologue: fill the pipeline (items 0..3 of this warp)
+  int idx0 = blockIdx.x * TMA_WARPS + warp;
+  if (a.sched) idx0 = bcast(next_index_raw(0));
+  int idx1 = bcast(next_index_raw(idx0)), idx2 = bcast(next_index_raw(idx1));
+  int idx3_raw = next_index_raw(idx2);
+  ItemDesc d0 = pipe_load_desc<MODE>(a, idx0), d1 = pipe_load_desc<MODE>(a, idx1), d2 = pipe_load_desc<MODE>(a, idx2);
+  ItemMeta m0 = pipe_load_meta<MODE>(a, d0, d0.beg, lane, head, ew, eb);
+  ItemMeta m1 = pipe_load_meta<MODE>(a, d1, d1.beg, lane, head, ew, eb);
+  int cur_issued = 0;                     // copies of the current item's window already issued
+
+  while (idx0 < a.n_items) {
+    // ---- prefetch stages for the following items (each consumed one iteration after it is requested)
+    const int idx3 = bcast(idx3_raw);
+    const int idx4_raw = next_index_raw(idx3);
+    const ItemDesc d3 = pipe_load_desc<MODE>(a, idx3);
+    const ItemMeta m2 = pipe_load_meta<MODE>(a, d2, d2.beg, lane, head, ew, eb);
+    if (d1.end > d1.beg && lane < NV * 4)              // next item's q row: pull its 128 B lines into L2 / L1
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Q + (int64_t)d1.row * a.ldq + lane * 32));
+    const int n1 = (m1.invr != 0.f) ? min(32, d1.end - d1.beg) : 0;     // first window of the next item
+    int nxt_issued = 0;
+    float4 q0[NV];
+    if (m0.invr != 0.f && d0.end > d0.beg) {
+      const float* qr = a.Q + (int64_t)d0.row * a.ldq;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) q0[i] = ld4(qr + (i * 32 + lane) * 4);
+    }
+
+    // ---- item i
+    const int row = d0.row, slot = d0.slot;
+    float4 out[NV], acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc[i] = out[i]; }
+    const float invr = m0.invr;
+    float m = -INFINITY, ssum = 0.f;
+    const bool live = invr != 0.f && d0.end > d0.beg;
+    int cur_rel = -1;
+    for (int base = d0.beg; base < d0.end || base == d0.beg; base += 32) {
+      const int n = live ? min(32, d0.end - base) : 0;
+      const bool last_window = base + 32 >= d0.end;
+      if (base != d0.beg) {               // rows with more than 32 edges per item: the later windows are not prefetched
+        m0 = pipe_load_meta<MODE>(a, d0, base, lane, head, ew, eb);
+        cur_issued = 0;
+      }
+      int j = 0;
+      while (true) {
+        // refill the ring: this window's edges first, then (last window only) the next item's
+        if (inflight < ring && (cur_issued < n || (last_window && nxt_issued < n1))) {
+          // the freed slots were read through the generic proxy; order those reads before the async-proxy writes
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          while (inflight < ring) {
+            if (cur_issued < n) { issue(__shfl_sync(FULL, m0.src, cur_issued)); ++cur_issued; }
+            else if (last_window && nxt_issued < n1) { issue(__shfl_sync(FULL, m1.src, nxt_issued)); ++nxt_issued; }
+            else break;
+          }
+        }
+        if (j >= n) break;
+        int g = min(bmax, n - j);
+        if (MODE == MODE_HEAT) {
+          const int rel = __shfl_sync(FULL, m0.rel, j);
+          const unsigned same = __ballot_sync(FULL, lane >= j && lane < n && m0.rel == rel) >> j;
+          g = min(g, same == FULL ? 32 : __ffs(~same) - 1);        // (__ffs(0) == 0)
+          if (rel != cur_rel) {                       // warp-uniform: close the running segment
+            if (cur_rel >= 0) {
+              const float inv = 1.f / ssum;
+#pragma unroll
+              for (int i = 0; i < NV; ++i) {
+                out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
+                out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
+                acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            m = -INFINITY; ssum = 0.f; cur_rel = rel;
+          }
+        }
+        float sc[BMAX];
+        const float* slot_ptr[BMAX];
+#pragma unroll
+        for (int u = 0; u < BMAX; ++u) {
+          sc[u] = -INFINITY;
+          slot_ptr[u] = nullptr;
+          if (u < g) {
+            int su = rs + u;
+            uint32_t pu = rpar;
+            if (su >= ring) { su -= ring; pu ^= 1; }
+            if (a.dbg != 2) mbar_wait(bars_u32 + 8 * su, pu);
+            const float* ks = reinterpret_cast<const float*>(my_slots + (size_t)su * SLOT_BYTES);
+            slot_ptr[u] = ks;
+            float d0_ = 0.f, d1_ = 0.f;
+            if (a.dbg != 3)
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              const float4 kk = *reinterpret_cast<const float4*>(ks + (i * 32 + lane) * 4);
+              d0_ = fmaf(q0[i].x, kk.x, d0_); d1_ = fmaf(q0[i].y, kk.y, d1_);
+              d0_ = fmaf(q0[i].z, kk.z, d0_); d1_ = fmaf(q0[i].w, kk.w, d1_);
+            }
+            sc[u] = d0_ + d1_;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < BMAX; ++u) {
+          if (u < g) {
+            float d = sc[u];
+            for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+            float scale = m0.seg_scale;
+            if (MODE == MODE_HEAT) scale = __shfl_sync(FULL, m0.scale, j + u);
+            sc[u] = d * scale;
+          }
+        }
+        float mn = m;
+#pragma unroll
+        for (int u = 0; u < BMAX; ++u) mn = fmaxf(mn, sc[u]);
+        const float corr = __expf(m - mn);            // m = -inf on the first batch -> 0
+        float p[BMAX], psum = 0.f;
+#pragma unroll
+        for (int u = 0; u < BMAX; ++u) { p[u] = __expf(sc[u] - mn); psum += p[u]; }   // exp(-inf) = 0 for u >= g
+        ssum = fmaf(ssum, corr, psum);
+        m = mn;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr; }
+#pragma unroll
+        for (int u = 0; u < BMAX; ++u) {
+          if (u < g && a.dbg != 3) {
+            const float* vs = slot_ptr[u] + NV * 128;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              const float4 vv = *reinterpret_cast<const float4*>(vs + (i * 32 + lane) * 4);
+              acc[i].x = fmaf(p[u], vv.x, acc[i].x); acc[i].y = fmaf(p[u], vv.y, acc[i].y);
+              acc[i].z = fmaf(p[u], vv.z, acc[i].z); acc[i].w = fmaf(p[u], vv.w, acc[i].w);
+            }
+          }
+        }
+        __syncwarp();                                 // every lane is done with these g slots
+        rs += g;
+        if (rs >= ring) { rs -= ring; rpar ^= 1; }
+        inflight -= g;
+        j += g;
+      }
+      if (!live) break;
+    }
+    if (live && slot < 0) {                           // close the last segment
+      const float inv = 1.f / ssum;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        out[i].x = fmaf(acc[i].x, inv, out[i].x) * invr; out[i].y = fmaf(acc[i].y, inv, out[i].y) * invr;
+        out[i].z = fmaf(acc[i].z, inv, out[i].z) * invr; out[i].w = fmaf(acc[i].w, inv, out[i].w) * invr;
+      }
+    }
+    if (slot < 0) {
+      if (a.out) {
+        float* o = a.out + (int64_t)row * a.ldo;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
+      }
+      if (a.out_split) {
+        __nv_bfloat16* o = a.out_split + (int64_t)row * a.D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) st_split4(o + (i * 32 + lane) * 4, a.split_lo, out[i]);
+      }
+    } else {                                          // partial of one segment chunk: (m, sum, unnormalised acc)
+      a.part_ms[(int64_t)slot * 64 + lane] = m;
+      a.part_ms[(int64_t)slot * 64 + 32 + lane] = ssum;
+      float* o = a.part_acc + (int64_t)slot * a.D;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = acc[i];
+      if (a.split_cnt) {                              // the warp that completes the row's last chunk merges it
+        const int h = __ldg(a.part_split + slot);
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          const int n_chunks = __ldg(a.split_ptr + h + 1) - __ldg(a.split_ptr + h);
+          last = atomicAdd(a.split_cnt + h, 1) == n_chunks - 1;
+          if (last) a.split_cnt[h] = 0;               // self-resetting: ready for the next launch
+        }
+        last = __shfl_sync(FULL, last, 0);
+        if (last) {
+          __threadfence();
+          MergeArgs mg;
+          mg.split_row = a.split_row; mg.split_ptr = a.split_ptr; mg.part_rel = a.part_rel;
+          mg.part_ms = a.part_ms; mg.part_acc = a.part_acc; mg.inv_r = a.inv_r; mg.n_split = 0; mg.D = a.D;
+          mg.out = a.out; mg.ldo = a.ldo; mg.out_split = a.out_split; mg.split_lo = a.split_lo;
+          merge_row<NV>(mg, h, lane);
+        }
+      }
+    }
+    // ---- rotate the pipeline
+    idx0 = idx1; idx1 = idx2; idx2 = idx3; idx3_raw = idx4_raw;
+    d0 = d1; d1 = d2; d2 = d3;
+    m0 = m1; m1 = m2;
+    cur_issued = nxt_issued;
+  }
+  if (a.sched && lane == 0) {                         // the last warp to leave re-arms the queue for the next launch
+    __threadfence();
+    if (atomicAdd(a.sched + 1, 1) == n_warps - 1) { a.sched[0] = 0; a.sched[1] = 0; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic path: any D, H (natural column order).  One warp per work item, heads processed one after the
 // other; lane l owns columns {l + 32 j} of the current head (MAXJ >= ceil(d_k / 32)).
 template <int MAXJ, int MODE>
@@ -715,19 +1032,24 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
   int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
   int blocks = (a.n_items + WARPS - 1) / WARPS;
-  int cap = sms * 16;
-  if (blocks > cap) blocks = cap;
+  // one work item per warp: the hardware block scheduler deals the (largest-first) items out as blocks retire, which
+  // balances better than a persistent grid-stride loop; WSI_ATTN_CAP (development knob) = blocks per SM of a persistent grid
+  if (const char* c = getenv("WSI_ATTN_CAP")) { const int cap = sms * atoi(c); if (cap > 0 && blocks > cap) blocks = cap; }
   if (head_perm) {
     if (!vec_ok(a.D, a.H)) {
       wsi_set_error("hetero_attn: head_perm layout needs D %% 128 == 0, D <= 1024, H a power of two <= 32 (D=%d H=%d)", a.D, a.H);
       return WSI_ERR_UNSUPPORTED;
     }
-    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && !getenv("WSI_ATTN_NO_TMA")) {
-      // TMA-staged ring: ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM
+    const char* kern = getenv("WSI_ATTN_KERNEL");       // development knob: "ring" / "pipe" = the TMA bulk-copy kernels
+    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && kern && (kern[0] == 'r' || kern[0] == 'p')) {
       const int slot_bytes = 2 * a.D * 4;
-      int ring = 12288 / slot_bytes;
+      const bool pipe = kern[0] == 'p';
+      // ring kernel: ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM;
+      // item-pipelined kernel: ~24 KB per warp (the ring spans item boundaries), 2 blocks of 4 warps per SM, no spills
+      int ring = (pipe ? 24576 : 12288) / slot_bytes;
       ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
       if (const char* r = getenv("WSI_ATTN_RING")) ring = atoi(r);          // development knob
+      if (ring < 1) ring = 1;
       const int smem = TMA_WARPS * ring * slot_bytes + TMA_WARPS * ring * 8;
       int tb = (a.n_items + TMA_WARPS - 1) / TMA_WARPS;
       const int per_sm = 200 * 1024 / (smem + 1024) < 1 ? 1 : 200 * 1024 / (smem + 1024);
@@ -736,8 +1058,14 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       switch (a.D / 128) {
 #define CASE(NV) case NV: { \
         static bool attr_set = false; \
-        if (!attr_set) { WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; } \
-        attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
+        if (!attr_set) { \
+          WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+          WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+          WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+          attr_set = true; } \
+        if (pipe && per_sm >= 3) attn_fwd_pipe_kernel<NV, MODE, 3><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); \
+        else if (pipe) attn_fwd_pipe_kernel<NV, MODE, 2><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); \
+        else attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
       }
@@ -745,13 +1073,30 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       if (fused_merge) *fused_merge = a.split_cnt != nullptr;
       return WSI_OK;
     }
-    a.split_cnt = nullptr;                              // register-path kernel: the caller launches the merge
+    // register-path kernel (default): one work item per warp, the block scheduler is the work queue; rows are gathered
+    // with 16-byte loads straight into registers, GROUP edges in flight; split rows merged through arrival counters
     a.sched = nullptr;
-    switch (a.D / 128) {
-#define CASE(NV) case NV: attn_fwd_vec_kernel<NV, MODE><<<blocks, WARPS * 32, 0, stream>>>(a); break;
-      CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+    if (getenv("WSI_ATTN_SEPARATE_MERGE")) a.split_cnt = nullptr;      // development knob: merge as its own launch
+    // GROUP edges in flight per warp x MINB resident blocks per SM: measured on config 2 (D = 512) the kernel is bound
+    // by latency per warp, not by bytes in flight, so more (lighter) warps win: GROUP 2 at 4 blocks / SM (128
+    // registers) beats GROUP 4 at 3.  WSI_ATTN_VARIANT (development knob, D = 512 only): "g4b3" | "g1b5" | "g1b6" | "g2b5"
+    const char* var = getenv("WSI_ATTN_VARIANT");
+    if (var && a.D == 512) {
+      if (!strcmp(var, "g4b3")) attn_fwd_vec_kernel<4, MODE, 4, 3><<<blocks, WARPS * 32, 0, stream>>>(a);
+      else if (!strcmp(var, "g1b5")) attn_fwd_vec_kernel<4, MODE, 1, 5><<<blocks, WARPS * 32, 0, stream>>>(a);
+      else if (!strcmp(var, "g1b6")) attn_fwd_vec_kernel<4, MODE, 1, 6><<<blocks, WARPS * 32, 0, stream>>>(a);
+      else if (!strcmp(var, "g2b5")) attn_fwd_vec_kernel<4, MODE, 2, 5><<<blocks, WARPS * 32, 0, stream>>>(a);
+      else attn_fwd_vec_kernel<4, MODE, 2, 4><<<blocks, WARPS * 32, 0, stream>>>(a);
+    } else {
+      switch (a.D / 128) {
+#define CASE(NV, GRP, MINB) case NV: attn_fwd_vec_kernel<NV, MODE, GRP, MINB><<<blocks, WARPS * 32, 0, stream>>>(a); break;
+        CASE(1, 4, 4) CASE(2, 4, 4) CASE(3, 2, 4) CASE(4, 2, 4) CASE(5, 2, 2) CASE(6, 2, 2) CASE(7, 2, 2) CASE(8, 2, 2)
 #undef CASE
+      }
     }
+    WSI_CHECK_LAUNCH();
+    if (fused_merge) *fused_merge = a.split_cnt != nullptr;
+    return WSI_OK;
   } else {
     int mj = (a.dk + 31) / 32;
     if (mj <= 1) attn_fwd_generic_kernel<1, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
@@ -849,7 +1194,7 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
     a.part_split = part_split; a.split_cnt = split_cnt;
     a.split_row = split_row; a.split_ptr = split_ptr; a.part_rel = part_rel;
   }
-  a.sched = sched;
+  a.sched = getenv("WSI_ATTN_STATIC") ? nullptr : sched;                    // development knob: static round-robin
   { const char* d = getenv("WSI_ATTN_DEBUG"); a.dbg = d ? atoi(d) : 0; }
   bool fused = false;
   int rc = launch<MODE_HEAT>(a, 1, wsi_stream(stream), &fused);

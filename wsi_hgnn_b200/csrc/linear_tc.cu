@@ -315,24 +315,36 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           rscl[it] = (ep.row_scale && ok) ? __ldg(ep.row_scale + row0 + rsub + it * 4) : 1.f;
         }
       }
+      // residual rows of chunk 0 are requested BEFORE waiting for the accumulator, those of chunk c+1 while chunk c is
+      // processed: with one tile per CTA pair (the a_linear shapes) the epilogue is exposed and was bound by the
+      // latency of these loads, 4 KB per warp in flight
+      float4 rr[2][8];
+      auto load_res = [&](int c, float4* dst) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const bool ok = n0 + c * 32 < a.n_out && it * 4 < rows_left;
+          dst[it] = (res_p && ok) ? __ldg(reinterpret_cast<const float4*>(res_p + (int64_t)it * 4 * ep.ldres + c * 32)) : zero4;
+        }
+      };
+      if (FULL) load_res(0, rr[0]);
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
         if (n0 - c4 + c * 32 >= a.n_out || rows_left + rsub <= 0 || (a.dbg & 4)) break;   // warp-uniform: nothing left to store
         float v[32];
         tc_ld_32x32(taddr + c * 32, v);
         const bool n_ok = n0 + c * 32 < a.n_out;
         // issue every global load of this chunk before waiting on TMEM
-        float4 bb = zero4, mm[8], rr[8];
+        float4 bb = zero4, mm[8];
         if (bias_p && n_ok) bb = __ldg(reinterpret_cast<const float4*>(bias_p + c * 32));
         if (FULL) {
+          if (c + 1 < CHUNKS) load_res(c + 1, rr[(c + 1) & 1]);
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const bool ok = n_ok && it * 4 < rows_left;
             mm[it] = (mask_p && ok) ? __ldg(reinterpret_cast<const float4*>(mask_p + (int64_t)it * 4 * ep.ldmask + c * 32)) : one4;
-            rr[it] = (res_p && ok) ? __ldg(reinterpret_cast<const float4*>(res_p + (int64_t)it * 4 * ep.ldres + c * 32)) : zero4;
           }
         }
         tc_ld_wait();
@@ -344,7 +356,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int it = 0; it < 8; ++it) {
           if (n_ok && it * 4 < rows_left ) {
             const float4 accv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * EPI_LD + ((((lane & 7) ^ ((it * 4 + rsub) & 7))) << 2));
-            const float4 o = FULL ? epi_mix4<true, GELU>(ep, accv, bb, mm[it], rr[it], alpha, gate[it] != 0.f, rscl[it])
+            const float4 o = FULL ? epi_mix4<true, GELU>(ep, accv, bb, mm[it], rr[c & 1][it], alpha, gate[it] != 0.f, rscl[it])
                                   : epi_mix4<false, GELU>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
             if (ep.y) *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
             if (a.y_split) {

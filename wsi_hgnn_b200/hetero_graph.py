@@ -132,6 +132,13 @@ class RelationView:
         return self._g.num_nodes(self.cetype[2])
 
 
+def _to_device_async(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """small host array -> device without a stream synchronisation (pinned staging + non-blocking copy on CUDA)."""
+    if dev.type != "cuda":
+        return t.to(dev)
+    return t.pin_memory().to(dev, non_blocking=True)
+
+
 class GraphPlan:
     """Device-resident layout of one (possibly batched/packed) graph.
 
@@ -573,6 +580,16 @@ class HeteroGraph:
         parts = [self._ndata[nt][name] for nt in self.ntypes if self._num_nodes[nt] > 0]
         if not parts:
             raise ValueError("graph has no nodes")
+        whole = getattr(self, "_packed_feat_view", None)
+        if whole is not None and whole.dtype == dtype and whole.is_contiguous() and whole.shape[0] == sum(p.shape[0] for p in parts):
+            # flat-format graphs (slide_io.FlatSlide): the per-type tensors are consecutive row slices of one packed
+            # buffer; hand that buffer out instead of concatenating a copy (checked by address, not assumed)
+            off, ok = whole.data_ptr(), True
+            for p in parts:
+                ok = ok and p.dtype == dtype and p.is_contiguous() and p.data_ptr() == off and p.shape[1:] == whole.shape[1:]
+                off += p.numel() * p.element_size()
+            if ok:
+                return whole
         out = torch.cat([p.to(dtype) for p in parts], 0)
         return out.contiguous()
 
@@ -613,24 +630,31 @@ class HeteroGraph:
         assert seg[-1] == p.N
         p.seg_ptr_host = seg
         p.seg_nonempty = nonempty
-        p.seg_ptr = torch.tensor(seg, dtype=torch.int32, device=dev)
-        p.type_ptr_dev = torch.tensor(p.type_ptr, dtype=torch.int32, device=dev)
-
-        # 1/R per node.  DGL batch: R_t of the shared metagraph.  pack(): per graph.
-        inv = torch.zeros(max(p.N, 1), dtype=torch.float32)
-        if self._rel_present is None:
-            for t in range(T):
-                if p.r_count[t] > 0:
-                    inv[p.type_ptr[t]:p.type_ptr[t + 1]] = 1.0 / p.r_count[t]
-        else:
-            for t, nt in enumerate(self.ntypes):
-                off = p.type_ptr[t]
-                for b, n in enumerate(self._batch_num_nodes[nt]):
+        # 1/R per (type, graph) segment.  DGL batch: R_t of the shared metagraph.  pack(): per graph.
+        seg_inv = []
+        for t, nt in enumerate(self.ntypes):
+            for b, n in enumerate(self._batch_num_nodes[nt]):
+                if self._rel_present is None:
+                    r = p.r_count[t]
+                else:
                     r = sum(1 for ri, d in enumerate(p.rel_dst_type) if d == t and self._rel_present[b][ri])
-                    if r > 0 and n > 0:
-                        inv[off:off + n] = 1.0 / r
-                    off += n
-        p.node_inv_r = inv[:p.N].to(dev) if p.N > 0 else inv[:0].to(dev)
+                seg_inv.append(1.0 / r if r > 0 else 0.0)
+        # every small host-side array of the plan travels in ONE buffer (pinned + non-blocking on CUDA: a pageable
+        # torch.tensor(..., device=cuda) synchronises the stream, which would serialise the streaming evaluator)
+        n_seg = len(seg) - 1
+        head = torch.empty(len(seg) + len(p.type_ptr) + n_seg, dtype=torch.int32)
+        head[:len(seg)] = torch.tensor(seg, dtype=torch.int32)
+        head[len(seg):len(seg) + len(p.type_ptr)] = torch.tensor(p.type_ptr, dtype=torch.int32)
+        head[len(seg) + len(p.type_ptr):] = torch.tensor(seg_inv, dtype=torch.float32).view(torch.int32)
+        head = _to_device_async(head, dev)
+        p.seg_ptr = head[:len(seg)]
+        p.type_ptr_dev = head[len(seg):len(seg) + len(p.type_ptr)]
+        seg_inv_dev = head[len(seg) + len(p.type_ptr):].view(torch.float32)
+        if p.N > 0:
+            lens = (p.seg_ptr[1:] - p.seg_ptr[:-1]).to(torch.int64)
+            p.node_inv_r = torch.repeat_interleave(seg_inv_dev, lens, output_size=p.N).contiguous()
+        else:
+            p.node_inv_r = torch.zeros(0, dtype=torch.float32, device=dev)
 
         # dst-major, relation-grouped CSR
         p.E = sum(int(self._edges[ce][0].numel()) for ce in p.rel_list)
@@ -656,6 +680,17 @@ class HeteroGraph:
         dsts = [self._edges[ce][1] for ce in p.rel_list]
         have_sim = [sim_name in self._edata[ce] for ce in p.rel_list]
         sim = None
+        flat = self._flat_edge_views(p, srcs, dsts, sim_name, have_sim)
+        if flat is not None:                  # flat-format graph: the per-relation tensors are slices of three arrays
+            src, dst, sim = flat
+            ptr = [0]
+            for s in srcs:
+                ptr.append(ptr[-1] + int(s.numel()))
+            table = _to_device_async(torch.tensor([ptr, [p.type_ptr[t] for t in p.rel_src_type] + [0],
+                                                   [p.type_ptr[t] for t in p.rel_dst_type] + [0]], dtype=torch.int32), dev)
+            p.rowptr, p.e_src, p.e_sim, p.e_rel, _, stats = ops.plan_build_csr(src, dst, sim, table, R, p.N)
+            p._stats = stats
+            return
         if all(have_sim):
             sims = [self._edata[ce][sim_name].reshape(-1) for ce in p.rel_list]
             if any(s.dtype != sims[0].dtype for s in sims) or sims[0].dtype not in (torch.float32, torch.float64):
@@ -670,10 +705,31 @@ class HeteroGraph:
         ptr = [0]
         for s in srcs:
             ptr.append(ptr[-1] + int(s.numel()))
-        table = torch.tensor([ptr, [p.type_ptr[t] for t in p.rel_src_type] + [0],
-                              [p.type_ptr[t] for t in p.rel_dst_type] + [0]], dtype=torch.int32).to(dev)
+        table = _to_device_async(torch.tensor([ptr, [p.type_ptr[t] for t in p.rel_src_type] + [0],
+                                               [p.type_ptr[t] for t in p.rel_dst_type] + [0]], dtype=torch.int32), dev)
         p.rowptr, p.e_src, p.e_sim, p.e_rel, _, stats = ops.plan_build_csr(src, dst, sim, table, R, p.N)
         p._stats = stats                  # [0] max in-degree, [1] range-error flag: read lazily (no sync here)
+
+    def _flat_edge_views(self, p: GraphPlan, srcs, dsts, sim_name: str, have_sim):
+        """(src, dst, sim) of ALL relations without concatenating, when the per-relation tensors are consecutive
+        slices of the three arrays a FlatSlide graph was built on (checked by address, not assumed)."""
+        flat = getattr(self, "_flat_edges", None)
+        if flat is None or not all(have_sim):
+            return None
+        src, dst, sim = flat
+        if src.numel() != p.E or src.dtype != torch.int64 or sim.dtype != torch.float32:
+            return None
+        o_s, o_d, o_m = src.data_ptr(), dst.data_ptr(), sim.data_ptr()
+        for ce, s, d in zip(p.rel_list, srcs, dsts):
+            m = self._edata[ce][sim_name]
+            n = s.numel()
+            if n and (s.data_ptr() != o_s or d.data_ptr() != o_d or m.data_ptr() != o_m or m.dtype != torch.float32
+                      or s.dtype != torch.int64 or d.dtype != torch.int64 or m.numel() != n):
+                return None
+            o_s += 8 * n
+            o_d += 8 * n
+            o_m += 4 * n
+        return src, dst, sim
 
     def _plan_csr_host(self, p: GraphPlan, sim_name: str):
         """Host-side (torch ops) statement of the same layout: CPU graphs in the tests, and the cross-check of the

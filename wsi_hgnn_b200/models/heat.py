@@ -195,6 +195,14 @@ class _AttnParams(nn.Module):
 
 
 class _HEATBase(nn.Module):
+    def prepare_plan(self, plan: GraphPlan):
+        """Build ahead of time the plan-side structures the forward needs that cost a host read (the hub-balancing
+        work list): the streaming evaluator calls this on its planning stream, one slide ahead."""
+        if len(self.gcs) and ops.head_perm(self.gcs[0].out_size, self.gcs[0].n_heads) is not None:
+            plan.attn_work()
+        else:
+            plan.check()
+
     def _trunk(self, G: HeteroGraph, h):
         plan = G.plan()
         order = _graph_type_order(plan, self.node_dict)

@@ -171,6 +171,12 @@ class HGT(nn.Module):
             k: nn.ModuleList([nn.Linear(hidden_dim, out_dim) for _ in range(n_layers + 1)]) for k in node_dict})
         self._packs = PackCache()
 
+    def prepare_plan(self, plan: GraphPlan):
+        """Plan-side structures with host reads (segments, relation groups), built ahead by the streaming evaluator."""
+        plan.segments()
+        if self.gcs:
+            _relation_groups(plan, self.edge_dict, id(self.edge_dict))
+
     def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
         plan = G.plan()
         T, B = len(plan.ntypes), plan.B

@@ -28,7 +28,7 @@ def _prep(t: torch.Tensor):
     if _cur_device[0] != idx:
         _lib.check(_lib.load().wsi_set_device(idx), "wsi_set_device")
         _cur_device[0] = idx
-    return torch.cuda.current_stream(t.device).cuda_stream
+    return torch._C._cuda_getCurrentRawStream(idx)       # raw cudaStream_t of torch's current stream (no Stream object)
 
 
 def _rows(t: Optional[torch.Tensor], name: str, dtype=torch.float32):

@@ -1,0 +1,232 @@
+"""Flat slide format + streaming inference over host-resident slides.
+
+The reference stores every slide as a pickled DGLHeteroGraph (get_graph.py:279-289; read back by data.py:96-97) and
+evaluates one graph at a time with a synchronous `.to(device)` + D2H read per slide (evaluator/eval_homo_graph.py:
+61-95).  Here a slide is ONE contiguous byte blob + a small JSON-able header:
+
+    [ features  fp32 [N, F]  type-major packed (the GraphPlan row order) ]
+    [ src       int64 [E]    local ids, relation-major (canonical_etypes order) ]
+    [ dst       int64 [E] ]
+    [ sim       fp32  [E] ]
+
+so that (a) a file is written / read with one sequential IO (or mmap'ed), (b) the host -> device move is ONE
+cudaMemcpyAsync from pinned memory instead of one per tensor (a config-2 slide has ~60 tensors), and (c) the device
+HeteroGraph is a set of zero-copy views of the device blob.  `stream_forward` runs the model over an iterable of
+flat slides with the copy of slide i+1 (copy engine, its own stream) overlapping the forward of slide i, and the
+logits of slide i-1 read back asynchronously: the per-epoch evaluation loop without a host sync per slide.
+"""
+import json
+import struct
+from typing import Dict, Iterable, Iterator, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .hetero_graph import HeteroGraph
+
+MAGIC = b"WSIFLAT1"
+_ALIGN = 256
+
+
+def _align(n: int) -> int:
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class FlatSlide:
+    """One slide in the flat format (host memory: pageable, pinned or an mmap of a file)."""
+
+    def __init__(self, header: Dict, blob: torch.Tensor):
+        if blob.dtype != torch.uint8 or blob.dim() != 1:
+            raise TypeError("FlatSlide: blob must be a 1-D uint8 tensor")
+        if blob.numel() < header["nbytes"]:
+            raise ValueError("FlatSlide: blob shorter than the header says")
+        self.header, self.blob = header, blob
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def from_graph(G: HeteroGraph, feat_name: str = "feat", sim_name: str = "sim", pin: bool = False) -> "FlatSlide":
+        if G.batch_size != 1:
+            raise ValueError("FlatSlide holds one slide; flatten the graphs before batching / packing them")
+        ntypes, cets = list(G.ntypes), list(G.canonical_etypes)
+        n_per = [G.num_nodes(nt) for nt in ntypes]
+        N = sum(n_per)
+        feats = [G.nodes[nt].data[feat_name] for nt in ntypes if G.num_nodes(nt) > 0]
+        F = int(feats[0].shape[1]) if feats else 0
+        e_per = [int(G._edges[ce][0].numel()) for ce in cets]
+        E = sum(e_per)
+        off_feat = 0
+        off_src = _align(off_feat + N * F * 4)
+        off_dst = _align(off_src + E * 8)
+        off_sim = _align(off_dst + E * 8)
+        nbytes = _align(off_sim + E * 4)
+        blob = torch.zeros(nbytes, dtype=torch.uint8)
+        if pin and torch.cuda.is_available():
+            blob = blob.pin_memory()
+        if N * F:
+            blob[off_feat:off_feat + N * F * 4].view(torch.float32).view(N, F).copy_(
+                torch.cat([f.detach().to("cpu", torch.float32) for f in feats], 0))
+        if E:
+            src = torch.cat([G._edges[ce][0].detach().to("cpu", torch.int64) for ce in cets])
+            dst = torch.cat([G._edges[ce][1].detach().to("cpu", torch.int64) for ce in cets])
+            sim = torch.cat([(G._edata[ce][sim_name].detach().reshape(-1).to("cpu", torch.float32) if sim_name in G._edata[ce]
+                              else torch.zeros(n, dtype=torch.float32)) for ce, n in zip(cets, e_per)])
+            blob[off_src:off_src + E * 8].view(torch.int64).copy_(src)
+            blob[off_dst:off_dst + E * 8].view(torch.int64).copy_(dst)
+            blob[off_sim:off_sim + E * 4].view(torch.float32).copy_(sim)
+        header = {"format": "wsi_hgnn_b200.FlatSlide/1", "ntypes": ntypes, "num_nodes": n_per,
+                  "canonical_etypes": [list(ce) for ce in cets], "num_edges": e_per, "feat_dim": F,
+                  "feat_name": feat_name, "sim_name": sim_name,
+                  "off": {"feat": off_feat, "src": off_src, "dst": off_dst, "sim": off_sim}, "nbytes": nbytes}
+        return FlatSlide(header, blob)
+
+    def pin(self) -> "FlatSlide":
+        return self if self.blob.is_pinned() else FlatSlide(self.header, self.blob.pin_memory())
+
+    # ------------------------------------------------------------------ file IO
+    def save(self, path: str):
+        hb = json.dumps(self.header).encode()
+        pad = _align(len(MAGIC) + 8 + len(hb)) - (len(MAGIC) + 8 + len(hb))
+        with open(path, "wb") as f:
+            f.write(MAGIC)
+            f.write(struct.pack("<Q", len(hb) + pad))
+            f.write(hb + b" " * pad)
+            f.write(self.blob[:self.header["nbytes"]].numpy().tobytes())
+
+    @staticmethod
+    def load(path: str, mmap: bool = True) -> "FlatSlide":
+        with open(path, "rb") as f:
+            if f.read(len(MAGIC)) != MAGIC:
+                raise ValueError(f"{path}: not a FlatSlide file")
+            (hlen,) = struct.unpack("<Q", f.read(8))
+            header = json.loads(f.read(hlen).decode())
+            off = len(MAGIC) + 8 + hlen
+            if mmap:
+                arr = np.memmap(path, dtype=np.uint8, mode="r", offset=off, shape=(header["nbytes"],))
+                blob = torch.from_numpy(np.asarray(arr))         # read-only view of the page cache
+            else:
+                blob = torch.frombuffer(bytearray(f.read(header["nbytes"])), dtype=torch.uint8)
+        return FlatSlide(header, blob)
+
+    # ------------------------------------------------------------------ views
+    def graph_on(self, blob: torch.Tensor) -> HeteroGraph:
+        """HeteroGraph whose tensors are zero-copy views of `blob` (this slide's bytes on any device)."""
+        h = self.header
+        off, F = h["off"], h["feat_dim"]
+        n_per, e_per = h["num_nodes"], h["num_edges"]
+        N, E = sum(n_per), sum(e_per)
+        feat = blob[off["feat"]:off["feat"] + N * F * 4].view(torch.float32).view(N, F)
+        src = blob[off["src"]:off["src"] + E * 8].view(torch.int64)
+        dst = blob[off["dst"]:off["dst"] + E * 8].view(torch.int64)
+        sim = blob[off["sim"]:off["sim"] + E * 4].view(torch.float32)
+        ndata, edges, edata = {}, {}, {}
+        r = 0
+        for nt, n in zip(h["ntypes"], n_per):
+            ndata[nt] = {h["feat_name"]: feat[r:r + n]}
+            r += n
+        e = 0
+        for ce, n in zip(h["canonical_etypes"], e_per):
+            edges[tuple(ce)] = (src[e:e + n], dst[e:e + n])
+            edata[tuple(ce)] = {h["sim_name"]: sim[e:e + n]}
+            e += n
+        G = HeteroGraph(dict(zip(h["ntypes"], n_per)), edges, ndata, edata)
+        G._packed_feat_view = feat                                # packed_ndata() returns it without a copy
+        G._flat_edges = (src, dst, sim)                           # plan() reads them without concatenating
+        return G
+
+    def to_graph(self, device="cpu", non_blocking: bool = False) -> HeteroGraph:
+        dev = torch.device(device)
+        blob = self.blob[:self.header["nbytes"]]
+        return self.graph_on(blob if dev.type == "cpu" else blob.to(dev, non_blocking=non_blocking))
+
+    def num_edges(self) -> int:
+        return sum(self.header["num_edges"])
+
+    def num_nodes(self) -> int:
+        return sum(self.header["num_nodes"])
+
+
+def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 3) -> Iterator[torch.Tensor]:
+    """Yield the logits ([1, out_dim], host tensor) of every slide, in order.
+
+    Three stages run concurrently on three streams, each one slide ahead of the next:
+        copy stream   slide i+2: ONE host -> device copy of its blob (copy engine)
+        plan stream   slide i+1: CSR + work-list build on the device blob (the two small host reads of the planner
+                      wait only for this stream, i.e. for a copy that was queued a whole slide earlier)
+        main stream   slide i:   forward, logits -> pinned host memory (asynchronous)
+    The host never waits for the main stream except on a slide's own `done` event, `depth` slides later, so the
+    Python / launch cost of slide i+1 overlaps the GPU time of slide i.  `depth` = device blob buffers (>= 3).
+    The blobs should be pinned (FlatSlide.pin()) for the copies to be asynchronous."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("stream_forward needs a CUDA device (there is no CPU fallback)")
+    nbuf = max(3, int(depth))
+    main = torch.cuda.current_stream(dev)
+    copy_stream, plan_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    bufs: List[Optional[torch.Tensor]] = [None] * nbuf
+    free_ev: List[Optional[torch.cuda.Event]] = [None] * nbuf       # forward that last read the buffer has finished
+    was_training = model.training
+    model.eval()
+
+    def upload(i: int, s: FlatSlide):
+        k, n = i % nbuf, s.header["nbytes"]
+        with torch.cuda.stream(copy_stream):
+            if bufs[k] is None or bufs[k].numel() < n:
+                if free_ev[k] is not None:
+                    free_ev[k].synchronize()
+                bufs[k] = torch.empty(int(n * 1.25) + _ALIGN, dtype=torch.uint8, device=dev)
+            elif free_ev[k] is not None:
+                copy_stream.wait_event(free_ev[k])
+            bufs[k][:n].copy_(s.blob[:n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return s, k, ev
+
+    def plan(staged):
+        s, k, uploaded = staged
+        with torch.cuda.stream(plan_stream), torch.no_grad():
+            plan_stream.wait_event(uploaded)
+            G = s.graph_on(bufs[k][:s.header["nbytes"]])
+            p = G.plan()
+            if hasattr(model, "prepare_plan"):
+                model.prepare_plan(p)                               # work list etc.: everything with a host read
+            ev = torch.cuda.Event()
+            ev.record(plan_stream)
+        return G, k, ev
+
+    pending: List[Tuple[torch.Tensor, torch.cuda.Event, HeteroGraph]] = []
+    try:
+        it = iter(slides)
+        up: List = []                                               # uploaded, not yet planned (at most 1 in flight)
+        for _ in range(2):
+            s = next(it, None)
+            if s is not None:
+                up.append(upload(len(up), s))
+        n_up = len(up)
+        planned = plan(up.pop(0)) if up else None
+        while planned is not None:
+            s = next(it, None)
+            if s is not None:                                       # stage 1: slide i+2
+                up.append(upload(n_up, s))
+                n_up += 1
+            nxt = plan(up.pop(0)) if up else None                   # stage 2: slide i+1
+            G, k, ready = planned                                   # stage 3: slide i
+            main.wait_event(ready)
+            with torch.no_grad():
+                out = model(G)
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            free_ev[k] = done
+            pending.append((host, done, G))                         # G (and its plan tensors, allocated on the plan
+            if len(pending) >= nbuf:                                # stream) stay alive until the forward has finished
+                h, ev, _ = pending.pop(0)
+                ev.synchronize()
+                yield h
+            planned = nxt
+        for h, ev, _ in pending:
+            ev.synchronize()
+            yield h
+    finally:
+        if was_training:
+            model.train()
