@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 11
+#define WSI_ABI_VERSION 12
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -246,6 +246,61 @@ int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64_t q_begin,
                  float* nbr_dist, void* workspace, int64_t workspace_bytes, void* stream);
 int wsi_edge_pearson(const float* feat, int64_t n, int F, const int64_t* src, const int64_t* dst, int64_t n_edges,
                      float* sim, uint8_t* etype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-forward driver: HEATNet2.forward / HEATNet4.forward (models/HEATNet4.py:195-247, models/HEATNet2.py:159-196)
+ * in inference, as ONE host call that enqueues the kernel chain on `stream`
+ *   split(feat) -> adapt_ws GEMM -> L x [ K|V|Q GEMM -> edge attention (work list) -> a_linear GEMM + skip mix ]
+ *   -> fused typed readout + collapsed affine heads
+ * (the same launches the Python modules issue one by one; here the host cost per slide is a few microseconds per
+ * kernel, which is what bounds the streamed end-to-end path).  Preconditions = those of the tcgen05 chain:
+ * wsi_typed_linear_tc_ok(n_rows, F, D), (n_rows, D, 3D), (n_rows, D, D); wsi_head_perm(D, H) exists; n_out <= 8.
+ * All weights are in the forms the kernels consume: bf16 [hi; lo] stacks in the GRAPH's node-type order
+ * (wsi_split_bf16), K|V|Q fused along the output dimension, K/V/Q rows and a_linear columns in head_perm order.
+ */
+typedef struct wsi_heat_graph {
+  int64_t n_rows;                 /* N packed nodes */
+  int32_t T, B;                   /* node types of the graph, graphs in the batch */
+  const int32_t* type_ptr_host;   /* [T+1] HOST */
+  const int32_t* seg_ptr;         /* [T*B+1] readout segments, type-major */
+  const int32_t* e_src;           /* CSR arrays of wsi_plan_build_csr */
+  const float* e_sim;
+  const uint8_t* e_rel;
+  const float* node_inv_r;
+  const int32_t* items;           /* work list of wsi_plan_attn_work_fill */
+  int64_t n_items;
+  const int32_t* split_row;
+  const int32_t* split_ptr;
+  const int32_t* part_rel;
+  const int32_t* part_split;
+  int32_t* split_cnt;
+  int32_t* sched;                 /* may be NULL */
+  int64_t n_split, n_part;
+} wsi_heat_graph;
+
+typedef struct wsi_heat_params {
+  int32_t F, D, H, L;             /* input / hidden width, heads, layers */
+  const void* w_in_split;         /* bf16 [2*T*D, F] */
+  const float* b_in;              /* [T, D] */
+  const void* const* w_kvq_split; /* HOST array [L] of bf16 [2*T*3D, D] */
+  const float* const* b_kvq;      /* HOST array [L] of [T, 3D] */
+  const void* const* w_a_split;   /* HOST array [L] of bf16 [2*T*D, D] */
+  const float* const* b_a;        /* HOST array [L] of [T, D] */
+  const float* const* skip;       /* HOST array [L] of [T] */
+  const float* const* e_w;        /* HOST array [L] of device scalars (e_linear.weight) */
+  const float* const* e_b;        /* HOST array [L] of device scalars (e_linear.bias) */
+  int32_t pool_op, n_out;         /* WSI_POOL_*, logits width (<= 8) */
+  const float* M;                 /* [T, n_out, D] collapsed prediction maps (wsi_segment_pool_affine_fwd) */
+  const float* c;                 /* [T, n_out] or NULL */
+  const float* b_total;           /* [n_out] or NULL */
+  const float* seg_scale;         /* [T*B] or NULL */
+} wsi_heat_params;
+
+int64_t wsi_heat_forward_workspace_bytes(int64_t n_rows, int F, int D, int64_t n_part, int T, int B);
+/* feat fp32 [N, ldf] type-major packed; x_out [N, ldx] final node embeddings (head_perm column order is NOT applied to
+ * x: embeddings are in natural order) or NULL; logits [B, ldl]. */
+int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_graph* g, const wsi_heat_params* p, float* x_out,
+                     int64_t ldx, float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -153,3 +153,40 @@ def test_empty_relation_free_graph_passthrough():
         parts = [orc.linears_prediction[nt](h[nt].mean(0, keepdim=True)) for nt in G.ntypes]
         ref = orc.head(orc.head_1(orc.head_2(torch.cat(parts, 1))))
     assert helpers.rel_err(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("model,pooling", [("HEATNet4", "mean"), ("HEATNet4", "max"), ("HEATNet2", "sum")])
+def test_native_driver_matches_per_op_path(model, pooling):
+    """wsi_heat_forward (one host call for the whole inference chain) == the same kernels issued op by op from Python,
+    for single, batched (DGL semantics) and packed (independent) graphs, with and without embeddings."""
+    kw = dict(in_dim=96, hidden_dim=256, out_dim=3, n_layers=3, n_heads=4, dropuout=0.3, graph_pooling_type=pooling)
+    ours, orc = _pair(model, 3, kw)
+    gs = [synthetic.synth_slide_graph(700 + 300 * i, 96, 3, 6, seed=20 + i, noise_edges=0.15) for i in range(3)]
+    for G in (gs[0], batch(gs), pack(gs)):
+        Gd = G.to("cuda")
+        plan = Gd.plan()
+        with torch.no_grad():
+            assert ours._native_ok(Gd, plan, None, 3), "the driver should take this shape"
+            ours.native_forward = True
+            out_n, emb_n = ours(Gd, return_embeddings=True)
+            out_n2 = ours(Gd)
+            ours.native_forward = False
+            out_p, emb_p = ours(Gd, return_embeddings=True)
+            ours.native_forward = True
+        assert torch.equal(out_n, out_n2)
+        assert helpers.rel_err(out_n, out_p) < 1e-6
+        for nt in G.ntypes:
+            if G.num_nodes(nt):
+                assert helpers.rel_err(emb_n[nt], emb_p[nt]) < 1e-6
+        ref = helpers.run_oracle(orc, G, independent=G.independent)
+        assert helpers.rel_err(out_n, ref) < TOL
+    # shapes the driver does not take fall back to the per-op CUDA path (still no CPU path)
+    small = synthetic.synth_slide_graph(200, 96, 3, 6, seed=5).to("cuda")
+    with torch.no_grad():
+        assert not ours._native_ok(small, small.plan(), None, 3)
+        assert ours(small).shape == (1, 3)
+    big = gs[0].to("cuda")
+    assert not ours._native_ok(big, big.plan(), None, 3)              # gradients wanted
+    ours.train()
+    with torch.no_grad():
+        assert not ours._native_ok(big, big.plan(), None, 3)          # dropout active

@@ -2,13 +2,33 @@
 library is missing or fails to load, importing an op raises."""
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+
+
+
+class HeatGraph(Structure):
+    """struct wsi_heat_graph (include/wsi_hgnn.h)."""
+    _fields_ = [("n_rows", c_int64), ("T", c_int32), ("B", c_int32), ("type_ptr_host", c_void_p), ("seg_ptr", c_void_p),
+                ("e_src", c_void_p), ("e_sim", c_void_p), ("e_rel", c_void_p), ("node_inv_r", c_void_p),
+                ("items", c_void_p), ("n_items", c_int64), ("split_row", c_void_p), ("split_ptr", c_void_p),
+                ("part_rel", c_void_p), ("part_split", c_void_p), ("split_cnt", c_void_p), ("sched", c_void_p),
+                ("n_split", c_int64), ("n_part", c_int64)]
+
+
+class HeatParams(Structure):
+    """struct wsi_heat_params (include/wsi_hgnn.h)."""
+    _fields_ = [("F", c_int32), ("D", c_int32), ("H", c_int32), ("L", c_int32), ("w_in_split", c_void_p),
+                ("b_in", c_void_p), ("w_kvq_split", POINTER(c_void_p)), ("b_kvq", POINTER(c_void_p)),
+                ("w_a_split", POINTER(c_void_p)), ("b_a", POINTER(c_void_p)), ("skip", POINTER(c_void_p)),
+                ("e_w", POINTER(c_void_p)), ("e_b", POINTER(c_void_p)), ("pool_op", c_int32), ("n_out", c_int32),
+                ("M", c_void_p), ("c", c_void_p), ("b_total", c_void_p), ("seg_scale", c_void_p)]
+
 
 # name -> (restype, argtypes); must list every symbol include/wsi_hgnn.h declares (checked by tests)
 PROTOTYPES = {
@@ -43,6 +63,8 @@ PROTOTYPES = {
     "wsi_knn_workspace_bytes": (_L, [_L, _I, _I, _L, _L]),
     "wsi_knn_topk": (_I, [_P, _L, _I, _I, _L, _L, _P, _P, _P, _L, _P]),
     "wsi_edge_pearson": (_I, [_P, _L, _I, _P, _P, _L, _P, _P, _P]),
+    "wsi_heat_forward_workspace_bytes": (_L, [_L, _I, _I, _L, _I, _I]),
+    "wsi_heat_forward": (_I, [_P, _L, POINTER(HeatGraph), POINTER(HeatParams), _P, _L, _P, _L, _P, _L, _P]),
 }
 
 _lib = None

@@ -1,0 +1,90 @@
+// Whole-forward driver (wsi_heat_forward): the HEATNet2 / HEATNet4 inference chain as one host call.
+// Replaces the Python-level sequencing of models/HEATNet4.py:195-247 (reference) / wsi_hgnn_b200/models/heat.py (ours):
+// it only SEQUENCES the C-ABI kernels of this library on the caller's stream and carves their buffers out of one
+// caller-owned workspace; no arithmetic lives here.
+#include "common.cuh"
+
+namespace {
+inline int64_t al(int64_t v) { return (v + 1023) & ~(int64_t)1023; }
+
+struct Carve {
+  uintptr_t p, end;
+  void* take(int64_t bytes) {
+    p = (p + 1023) & ~(uintptr_t)1023;
+    void* r = reinterpret_cast<void*>(p);
+    p += bytes;
+    return r;
+  }
+};
+}  // namespace
+
+extern "C" int64_t wsi_heat_forward_workspace_bytes(int64_t n_rows, int F, int D, int64_t n_part, int T, int B) {
+  const int64_t N = n_rows;
+  int64_t b = 2048;
+  b += al(2 * N * F * 2);                 // feat [hi; lo]
+  b += 2 * al(2 * N * D * 2);             // x [hi; lo], agg [hi; lo]
+  b += al(N * 3 * D * 4);                 // K|V|Q
+  b += 2 * al(N * D * 4);                 // x ping-pong
+  b += al(n_part * 64 * 4) + al(n_part * D * 4);
+  b += al(wsi_segment_pool_affine_workspace_bytes(N, (int64_t)T * B, D));
+  return b;
+}
+
+extern "C" int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_graph* g, const wsi_heat_params* p,
+                                float* x_out, int64_t ldx, float* logits, int64_t ldl, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  WSI_CHECK_ARG(g && p && feat && logits, "heat_forward: null pointer");
+  const int64_t N = g->n_rows;
+  const int T = g->T, B = g->B, F = p->F, D = p->D, H = p->H, L = p->L;
+  WSI_CHECK_ARG(N > 0 && T >= 1 && T <= WSI_MAX_TYPES && B >= 1 && L >= 0 && g->type_ptr_host && g->type_ptr_host[T] == N,
+                "heat_forward: bad graph (N=%lld T=%d B=%d)", (long long)N, T, B);
+  WSI_CHECK_ARG(wsi_typed_linear_tc_ok(N, F, D) && (L == 0 || (wsi_typed_linear_tc_ok(N, D, 3 * D) && wsi_typed_linear_tc_ok(N, D, D))),
+                "heat_forward: shapes (N=%lld F=%d D=%d) do not fit the tcgen05 chain", (long long)N, F, D);
+  WSI_CHECK_ARG(p->n_out >= 1 && p->n_out <= 8 && p->M, "heat_forward: n_out=%d must be in [1, 8]", p->n_out);
+  WSI_CHECK_ARG(!x_out || ldx >= D, "heat_forward: x_out row stride smaller than D");
+  const int64_t need = wsi_heat_forward_workspace_bytes(N, F, D, g->n_part, T, B);
+  WSI_CHECK_ARG(workspace && workspace_bytes >= need, "heat_forward: workspace of %lld bytes needed", (long long)need);
+
+  Carve cv{reinterpret_cast<uintptr_t>(workspace), reinterpret_cast<uintptr_t>(workspace) + (uintptr_t)workspace_bytes};
+  void* feat_s = cv.take(2 * N * F * 2);
+  void* xs = cv.take(2 * N * D * 2);
+  void* aggs = cv.take(2 * N * D * 2);
+  float* kvq = static_cast<float*>(cv.take(N * 3 * D * 4));
+  float* xa = static_cast<float*>(cv.take(N * D * 4));
+  float* xb = static_cast<float*>(cv.take(N * D * 4));
+  float* part_ms = static_cast<float*>(cv.take(g->n_part * 64 * 4));
+  float* part_acc = static_cast<float*>(cv.take(g->n_part * D * 4));
+  const int64_t pool_bytes = wsi_segment_pool_affine_workspace_bytes(N, (int64_t)T * B, D);
+  void* pool_ws = cv.take(pool_bytes);
+  const int32_t* tp = g->type_ptr_host;
+
+  int rc = wsi_split_bf16(feat, ldf, N, F, feat_s, stream);
+  if (rc) return rc;
+  // x = adapt_ws[type](feat)                                                   models/HEATNet4.py:198-206
+  float* x = (L == 0 && x_out) ? x_out : xa;
+  int64_t ld = (L == 0 && x_out) ? ldx : D;
+  rc = wsi_typed_linear_split(feat_s, p->w_in_split, p->b_in, F, D, tp, T, WSI_ACT_NONE, nullptr, nullptr, 0, nullptr, 0,
+                              nullptr, nullptr, x, ld, L > 0 ? xs : nullptr, stream);
+  if (rc) return rc;
+  for (int l = 0; l < L; ++l) {                                                // models/HEATNet4.py:213-214
+    rc = wsi_typed_linear_split(xs, p->w_kvq_split[l], p->b_kvq[l], D, 3 * D, tp, T, WSI_ACT_NONE, nullptr, nullptr, 0,
+                                nullptr, 0, nullptr, nullptr, kvq, 3 * D, nullptr, stream);     // :91-102, once per type
+    if (rc) return rc;
+    rc = wsi_hetero_attn_work_fwd(kvq, 3 * D, kvq + D, 3 * D, kvq + 2 * D, 3 * D, g->e_src, g->e_sim, g->e_rel,
+                                  g->node_inv_r, p->e_w[l], p->e_b[l], N, D, H, g->items, g->n_items, g->split_row,
+                                  g->split_ptr, g->part_rel, g->part_split, g->split_cnt, g->sched, g->n_split, g->n_part,
+                                  part_ms, part_acc, nullptr, D, aggs, stream);                    // :103-119
+    if (rc) return rc;
+    const bool last = l + 1 == L;
+    float* y = (last && x_out) ? x_out : (x == xa ? xb : xa);
+    const int64_t ldy = (last && x_out) ? ldx : D;
+    rc = wsi_typed_linear_split(aggs, p->w_a_split[l], p->b_a[l], D, D, tp, T, WSI_ACT_NONE, p->skip[l], x, ld, nullptr, 0,
+                                g->node_inv_r, nullptr, y, ldy, last ? nullptr : xs, stream);      // :121-136
+    if (rc) return rc;
+    x = y;
+    ld = ldy;
+  }
+  // typed readout + linears_prediction (+ head_2 -> head_1 -> head, collapsed)   models/HEATNet4.py:216-245
+  return wsi_segment_pool_affine_fwd(x, ld, g->seg_ptr, T, B, N, D, p->pool_op, p->M, p->c, p->b_total, p->seg_scale,
+                                     p->n_out, 0, logits, ldl, pool_ws, pool_bytes, stream);
+}

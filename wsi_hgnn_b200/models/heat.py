@@ -203,6 +203,92 @@ class _HEATBase(nn.Module):
         else:
             plan.check()
 
+    # ------------------------------------------------------------------ native whole-forward driver
+    def _native_ok(self, G: HeteroGraph, plan: GraphPlan, h, n_out: int) -> bool:
+        """The one-call C driver (wsi_heat_forward) covers inference on the tensor-core chain with the fused readout."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in param_list(self, "all", self.parameters)):
+            return False
+        if h is not None or getattr(self, "explicit_heads", False) or n_out > ops.AFFINE_MAX_OUT or plan.N == 0:
+            return False
+        if any(l.training and l.drop.p > 0 for l in self.gcs):
+            return False
+        F_in, D = self.adapt_ws[0].in_features, self.adapt_ws[0].out_features
+        return (len(self.gcs) > 0 and ops.tc_ok(plan.N, F_in, D) and all(l.tc_chain_ok(plan) for l in self.gcs))
+
+    def _native_params(self, plan: GraphPlan, order, names, collapse_heads: bool):
+        """struct wsi_heat_params for this (graph type order, weights version); rebuilt when a parameter changes."""
+        import ctypes
+        from .. import _lib
+        params = param_list(self, "all", self.parameters)
+
+        def build():
+            w_in, b_in = stack_linears(self.adapt_ws, order)
+            keep = [ops.split_bf16(w_in), b_in]
+            L = len(self.gcs)
+            arr = lambda: (ctypes.c_void_p * max(L, 1))()
+            w_kvq, b_kvq, w_a, b_a, skip, e_w, e_b = arr(), arr(), arr(), arr(), arr(), arr(), arr()
+            for i, layer in enumerate(self.gcs):
+                wk, bk, wa, ba, sk, _ = layer._packed(order)
+                wks, was = layer._packed_split(order)
+                ew, eb = layer.e_linear.weight.detach().reshape(-1).contiguous(), layer.e_linear.bias.detach().reshape(-1).contiguous()
+                keep += [wks, bk, was, ba, sk, ew, eb]
+                w_kvq[i], b_kvq[i], w_a[i], b_a[i], skip[i] = wks.data_ptr(), bk.data_ptr(), was.data_ptr(), ba.data_ptr(), sk.data_ptr()
+                e_w[i], e_b[i] = ew.data_ptr(), eb.data_ptr()
+            M, c, b_total = self._affine_maps(names, collapse_heads)
+            keep += [M, c, b_total, w_kvq, b_kvq, w_a, b_a, skip, e_w, e_b]
+            P = _lib.HeatParams()
+            P.F, P.D, P.H, P.L = w_in.shape[2], w_in.shape[1], self.gcs[0].n_heads, L
+            P.w_in_split, P.b_in = keep[0].data_ptr(), b_in.data_ptr()
+            P.w_kvq_split, P.b_kvq, P.w_a_split, P.b_a, P.skip, P.e_w, P.e_b = w_kvq, b_kvq, w_a, b_a, skip, e_w, e_b
+            P.pool_op, P.n_out = ops.POOL_OPS[self.graph_pooling_type], M.shape[1]
+            P.M, P.c = M.data_ptr(), (c.data_ptr() if c is not None else None)
+            P.b_total = b_total.data_ptr() if b_total is not None else None
+            return P, keep
+
+        return self._packs.get(("native", tuple(order), tuple(names), collapse_heads), params, build)
+
+    def _forward_native(self, G: HeteroGraph, plan: GraphPlan, collapse_heads: bool, return_embeddings: bool):
+        import ctypes
+        from .. import _lib
+        lib = _lib.load()
+        order = _graph_type_order(plan, self.node_dict)
+        names = list(plan.ntypes)
+        P, _keep = self._native_params(plan, order, names, collapse_heads)
+        key = ("native_graph", G.independent)
+        if key not in plan.cache:
+            w = plan.attn_work()
+            g = _lib.HeatGraph()
+            g.n_rows, g.T, g.B = plan.N, len(names), plan.B
+            tpc = plan.type_ptr_c()
+            g.type_ptr_host = ctypes.cast(tpc, ctypes.c_void_p)
+            g.seg_ptr = plan.seg_ptr.data_ptr()
+            g.e_src, g.e_sim, g.e_rel, g.node_inv_r = (plan.e_src.data_ptr(), plan.e_sim.data_ptr(), plan.e_rel.data_ptr(),
+                                                       plan.node_inv_r.data_ptr())
+            g.items, g.n_items = w["items"].data_ptr(), w["n_items"]
+            g.split_row, g.split_ptr, g.part_rel = w["split_row"].data_ptr(), w["split_ptr"].data_ptr(), w["part_rel"].data_ptr()
+            g.part_split = w["part_split"].data_ptr() if w.get("part_split") is not None else None
+            g.split_cnt = w["split_cnt"].data_ptr() if w.get("split_cnt") is not None else None
+            g.sched = w["sched"].data_ptr() if w.get("sched") is not None else None
+            g.n_split, g.n_part = w["n_split"], w["n_part"]
+            scale = readout_scale(plan, G.independent)
+            ws_bytes = lib.wsi_heat_forward_workspace_bytes(plan.N, P.F, P.D, w["n_part"], len(names), plan.B)
+            plan.cache[key] = (g, scale, ws_bytes, tpc, w)
+        g, scale, ws_bytes, _, _ = plan.cache[key]
+        feat = packed_features(G, plan, None)
+        if feat.dtype != torch.float32 or feat.stride(1) != 1:
+            feat = feat.float().contiguous()
+        stream = ops._prep(feat)
+        P.seg_scale = scale.data_ptr()
+        dev = feat.device
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        logits = torch.empty((plan.B, P.n_out), dtype=torch.float32, device=dev)
+        x_out = torch.empty((plan.N, P.D), dtype=torch.float32, device=dev) if return_embeddings else None
+        rc = lib.wsi_heat_forward(feat.data_ptr(), feat.stride(0), ctypes.byref(g), ctypes.byref(P),
+                                  x_out.data_ptr() if x_out is not None else None, P.D, logits.data_ptr(), P.n_out,
+                                  ws.data_ptr(), ws_bytes, stream)
+        _lib.check(rc, "wsi_heat_forward")
+        return (logits, unpack_rows(plan, x_out)) if return_embeddings else logits
+
     def _trunk(self, G: HeteroGraph, h):
         plan = G.plan()
         order = _graph_type_order(plan, self.node_dict)
@@ -258,14 +344,9 @@ class _HEATBase(nn.Module):
         o = TypedLinearFn.apply(pooled, w_p, b_p, plan.readout_ptr(), None)
         return o * readout_scale(plan, G.independent).unsqueeze(1)
 
-    def _readout_affine(self, G, plan, x, collapse_heads: bool):
-        """[B, out_dim] logits by the fused pool + affine kernel.  HEATNet2: M_t = linears_prediction[t]
-        (models/HEATNet2.py:181-194).  HEATNet4: the chain linears_prediction -> cat -> head_2 -> head_1 -> head
-        (models/HEATNet4.py:216-245) contains no nonlinearity (and LinearAttentionBlock is the identity), so it equals
-        one [out, D] map per node type plus a constant; the composite is formed in fp64 on the host side of the pack
-        cache and rebuilt whenever one of the parameters changes."""
-        names = list(plan.ntypes)
-        T, B = len(names), plan.B
+    def _affine_maps(self, names, collapse_heads: bool):
+        """(M [T, out, D], c [T, out], b_total [out] | None): the per-type affine maps of the readout (see _readout_affine)."""
+        T = len(names)
         heads = [self.head_2, self.head_1, self.head] if collapse_heads else []
         params = param_list(self, ("affine", tuple(names)), lambda: (
             [p for nt in names for p in self.linears_prediction[nt].parameters()] + [p for h in heads for p in h.parameters()]))
@@ -285,7 +366,17 @@ class _HEATBase(nn.Module):
             c = torch.bmm(blocks, bp.unsqueeze(-1)).squeeze(-1)                                  # [T, out]
             return M.float().contiguous(), c.float().contiguous(), b_total.float().contiguous()
 
-        M, c, b_total = self._packs.get(("affine", tuple(names)), params, build)
+        return self._packs.get(("affine", tuple(names)), params, build)
+
+    def _readout_affine(self, G, plan, x, collapse_heads: bool):
+        """[B, out_dim] logits by the fused pool + affine kernel.  HEATNet2: M_t = linears_prediction[t]
+        (models/HEATNet2.py:181-194).  HEATNet4: the chain linears_prediction -> cat -> head_2 -> head_1 -> head
+        (models/HEATNet4.py:216-245) contains no nonlinearity (and LinearAttentionBlock is the identity), so it equals
+        one [out, D] map per node type plus a constant; the composite is formed in fp64 on the host side of the pack
+        cache and rebuilt whenever one of the parameters changes."""
+        names = list(plan.ntypes)
+        T, B = len(names), plan.B
+        M, c, b_total = self._affine_maps(names, collapse_heads)
         return ops.segment_pool_affine(x, plan.seg_ptr, T, B, self.graph_pooling_type, M, c, b_total,
                                        readout_scale(plan, G.independent))
 
@@ -308,9 +399,14 @@ class HEATNet4(_HEATBase):
         self.head_1 = nn.Linear(256, 64)
         self.head = nn.Linear(64, out_dim)
         self.explicit_heads = False      # True: run linears_prediction / head_2 / head_1 / head as separate GEMMs
+        self.native_forward = True       # inference through the one-call C driver (wsi_heat_forward) when it applies
         self._packs = PackCache()
 
     def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
+        if self.native_forward and G.device.type == "cuda":
+            plan = G.plan()
+            if self._native_ok(G, plan, h, self.head.out_features):     # inference: the whole chain in one host call
+                return self._forward_native(G, plan, True, return_embeddings)
         plan, x = self._trunk(G, h)
         T, B = len(plan.ntypes), plan.B
         if x.requires_grad:                                             # training: explicit, differentiable chain
@@ -353,9 +449,15 @@ class HEATNet2(_HEATBase):
         self.adapt_ws = nn.ModuleList([nn.Linear(in_dim, hidden_dim) for _ in node_dict])
         self.gcs = nn.ModuleList([HEATLayer(hidden_dim, hidden_dim, node_dict, n_heads, dropuout)
                                   for _ in range(n_layers)])
+        self.native_forward = True       # inference through the one-call C driver (wsi_heat_forward) when it applies
         self._packs = PackCache()
 
     def forward(self, G: HeteroGraph, h=None, return_embeddings: bool = False):
+        if self.native_forward and G.device.type == "cuda":
+            plan = G.plan()
+            n_pred = next(iter(self.linears_prediction.values())).out_features
+            if self._native_ok(G, plan, h, n_pred):                     # inference: the whole chain in one host call
+                return self._forward_native(G, plan, False, return_embeddings)
         plan, x = self._trunk(G, h)
         T, B = len(plan.ntypes), plan.B
         if x.requires_grad:                                             # training: differentiable readout

@@ -145,6 +145,21 @@ class FlatSlide:
         return sum(self.header["num_nodes"])
 
 
+_STREAM_CTX: Dict = {}
+
+
+def _stream_ctx(dev: torch.device, nbuf: int) -> Dict:
+    """per-device streams + blob buffers of stream_forward, reused by successive (non-overlapping) calls."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), nbuf)
+    ctx = _STREAM_CTX.get(key)
+    if ctx is None or ctx["busy"]:
+        ctx = {"copy": torch.cuda.Stream(device=dev), "plan": torch.cuda.Stream(device=dev), "bufs": [None] * nbuf,
+               "busy": False}
+        _STREAM_CTX.setdefault(key, ctx)
+    ctx["busy"] = True
+    return ctx
+
+
 def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 3) -> Iterator[torch.Tensor]:
     """Yield the logits ([1, out_dim], host tensor) of every slide, in order.
 
@@ -161,8 +176,10 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 3) -
         raise RuntimeError("stream_forward needs a CUDA device (there is no CPU fallback)")
     nbuf = max(3, int(depth))
     main = torch.cuda.current_stream(dev)
-    copy_stream, plan_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    bufs: List[Optional[torch.Tensor]] = [None] * nbuf
+    # streams and device blob buffers persist across calls (per device): a new stream per call would make the caching
+    # allocator cudaMalloc fresh buffers every time, and cudaMalloc stalls for tens of ms once CUDA graphs exist
+    ctx = _stream_ctx(dev, nbuf)
+    copy_stream, plan_stream, bufs = ctx["copy"], ctx["plan"], ctx["bufs"]
     free_ev: List[Optional[torch.cuda.Event]] = [None] * nbuf       # forward that last read the buffer has finished
     was_training = model.training
     model.eval()
@@ -228,5 +245,6 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 3) -
             ev.synchronize()
             yield h
     finally:
+        ctx["busy"] = False
         if was_training:
             model.train()
