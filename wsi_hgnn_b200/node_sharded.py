@@ -78,17 +78,20 @@ class DistComm:
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 
-    def all_gather_blocks(self, buf: torch.Tensor):
-        """buf [world, n_max, C]: block `rank` holds this rank's rows; on return every block is filled."""
+    def all_gather_blocks(self, buf: torch.Tensor, async_op: bool = False):
+        """buf [world, n_max, C]: block `rank` holds this rank's rows; on completion every block is filled.
+        async_op: return a work handle (wait() orders the current stream after the collective) so that the exchange
+        overlaps whatever is enqueued in between - the Q projection in the node-sharded layer."""
         if self.world == 1:
-            return
+            return None
         flat = buf.view(self.world, -1)
         try:
-            self.dist.all_gather_into_tensor(flat.view(-1), flat[self.rank], group=self.group)   # in place (NCCL)
+            w = self.dist.all_gather_into_tensor(flat.view(-1), flat[self.rank], group=self.group, async_op=async_op)
         except (RuntimeError, NotImplementedError):
             outs = [flat[r] for r in range(self.world)]
             mine = flat[self.rank].clone()
-            self.dist.all_gather(outs, mine, group=self.group)
+            w = self.dist.all_gather(outs, mine, group=self.group, async_op=async_op)
+        return w if async_op else None
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum"):
         if self.world > 1:
@@ -118,8 +121,9 @@ class _LocalRankComm:
     def __init__(self, hub: LocalComm, rank: int):
         self.hub, self.rank, self.world = hub, rank, hub.world
 
-    def all_gather_blocks(self, buf: torch.Tensor):
+    def all_gather_blocks(self, buf: torch.Tensor, async_op: bool = False):
         self.hub.post(self.rank, "gather", buf)
+        return None
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum"):
         self.hub.post(self.rank, "reduce_" + op, t)
@@ -187,7 +191,8 @@ class NodeShardedHEAT:
         self.D = D
         self.kv_all = torch.zeros((self.world, self.n_max, 2 * D), dtype=torch.float32, device=dev)
         self.x: Optional[torch.Tensor] = None
-        self.kvq: Optional[torch.Tensor] = None
+        self.q: Optional[torch.Tensor] = None
+        self._gather = None
         self.pool_buf: Optional[torch.Tensor] = None
         self.halo_bytes_per_layer = (self.world - 1) * self.n_max * 2 * D * 4      # received per rank per layer
 
@@ -204,27 +209,35 @@ class NodeShardedHEAT:
                   if self.n_loc > 0 else feat_local.new_zeros((0, w_in.shape[1])))
 
     def project(self, l: int):
-        """K|V|Q of the own rows; K|V into this rank's block of the gather buffer; posts the all-gather."""
+        """K|V of the own rows straight into this rank's block of the gather buffer, the all-gather posted
+        asynchronously, then Q of the own rows while the K|V rows travel."""
         layer = self.model.gcs[l]
         w_kvq, b_kvq, _, _, _, use_perm = layer._packed(self.order)
         if not use_perm:
             raise NotImplementedError("node-sharded forward needs the lane-grouped attention layout "
                                       "(D % 128 == 0, H a power of two <= 32)")
         D = self.D
+        w_kv, b_kv, w_q, b_q = layer._packs.get(("kv|q", tuple(self.order)), [w_kvq, b_kvq], lambda: (
+            w_kvq[:, :2 * D].contiguous(), b_kvq[:, :2 * D].contiguous(), w_kvq[:, 2 * D:].contiguous(),
+            b_kvq[:, 2 * D:].contiguous()))
         if self.n_loc > 0:
-            self.kvq = ops.typed_linear(self.x, w_kvq, b_kvq, self.type_ptr)
-            self.kv_all[self.rank, :self.n_loc].copy_(self.kvq[:, :2 * D])
-        self.comm.all_gather_blocks(self.kv_all)
+            ops.typed_linear(self.x, w_kv, b_kv, self.type_ptr, out=self.kv_all[self.rank, :self.n_loc])
+        self._gather = self.comm.all_gather_blocks(self.kv_all, async_op=True)
+        if self.n_loc > 0:
+            self.q = ops.typed_linear(self.x, w_q, b_q, self.type_ptr)
 
     def aggregate(self, l: int):
         """edge attention over the own dst rows (sources from the gathered K|V) + a_linear / skip epilogue."""
         layer = self.model.gcs[l]
         _, _, wa, ba, skip, _ = layer._packed(self.order)
         D, H = self.D, layer.n_heads
+        if self._gather is not None:
+            self._gather.wait()
+            self._gather = None
         if self.n_loc == 0:
             return
         kv = self.kv_all.view(self.world * self.n_max, 2 * D)
-        agg = ops.hetero_attn_work(kv[:, :D], kv[:, D:], self.kvq[:, 2 * D:], self.work, self.e_src, self.e_sim,
+        agg = ops.hetero_attn_work(kv[:, :D], kv[:, D:], self.q, self.work, self.e_src, self.e_sim,
                                    self.e_rel, self.inv_r, layer.e_linear.weight, layer.e_linear.bias, D, H)
         self.x = ops.typed_linear(agg, wa, ba, self.type_ptr, skip=skip, res=self.x, row_gate=self.inv_r)
 
