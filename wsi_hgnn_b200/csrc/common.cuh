@@ -85,3 +85,29 @@ __device__ __forceinline__ void wsi_split_bf16(float x, __nv_bfloat16& hi, __nv_
 }
 
 static inline cudaStream_t wsi_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch (PDL): a kernel launched through wsi_launch_pdl may start while the previous kernel of
+// the stream is still draining - its blocks are scheduled as SMs free up and run their prologue (barrier init, TMEM
+// allocation, loads of PLAN data that no kernel writes) - and must call wsi_pdl_wait() before it touches anything an
+// earlier kernel produced.  wsi_pdl_trigger() lets the NEXT kernel's blocks be scheduled early in the same way.
+// A forward is ~13 kernels of 10-45 us: launch latency + prologue + tail of each were ~15 % of the step.
+__device__ __forceinline__ void wsi_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void wsi_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool wsi_pdl_enabled();      // error.cu: false when the environment has WSI_NO_PDL (development knob)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t wsi_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = wsi_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

@@ -1,4 +1,6 @@
 // Error channel and device queries of libwsi_hgnn.so (see include/wsi_hgnn.h "Conventions").
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/wsi_hgnn.h"
 
@@ -26,6 +28,8 @@ extern "C" int wsi_set_device(int device) {
   WSI_CHECK_CUDA(cudaSetDevice(device));
   return WSI_OK;
 }
+
+bool wsi_pdl_enabled() { return getenv("WSI_NO_PDL") == nullptr; }
 
 // Kernel-launch counter (bench.py reports it as `gpu_launches`): every WSI_CHECK_LAUNCH() bumps it.
 static unsigned long long g_launches = 0;

@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs
   float ew = 0.f, eb = 0.f;
   if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
 
+  wsi_pdl_trigger();
+  bool upstream_ready = false;      // PDL: the item descriptor and 1/R (plan data) are fetched before the previous kernel is waited for
   for (int item = blockIdx.x * WARPS + (threadIdx.x >> 5); item < a.n_items; item += n_warps) {
     int row = item, beg, end, slot = -1;
     if (a.items) {
@@ -98,7 +100,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs
     for (int i = 0; i < NV; ++i) out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float invr = 1.f, seg_scale = 0.f;
     if (MODE == MODE_HEAT) invr = __ldg(a.inv_r + row);
-    else seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + row) * a.H + head) * a.inv_sqrt_dk;
+    if (!upstream_ready) { wsi_pdl_wait(); upstream_ready = true; }
+    if (MODE != MODE_HEAT) seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + row) * a.H + head) * a.inv_sqrt_dk;
 
     float m = -INFINITY, ssum = 0.f;
     float4 acc[NV];
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs
       if (a.split_cnt) vec_fused_merge<NV>(a, slot, lane);
     }
   }
+  if (!upstream_ready) wsi_pdl_wait();                  // (a warp without an item)
 }
 
 // Combine the chunk partials of the split rows (HEAT) / split segments (HGT): one warp per split row.
@@ -1082,14 +1086,16 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
     // registers) beats GROUP 4 at 3.  WSI_ATTN_VARIANT (development knob, D = 512 only): "g4b3" | "g1b5" | "g1b6" | "g2b5"
     const char* var = getenv("WSI_ATTN_VARIANT");
     if (var && a.D == 512) {
-      if (!strcmp(var, "g4b3")) attn_fwd_vec_kernel<4, MODE, 4, 3><<<blocks, WARPS * 32, 0, stream>>>(a);
-      else if (!strcmp(var, "g1b5")) attn_fwd_vec_kernel<4, MODE, 1, 5><<<blocks, WARPS * 32, 0, stream>>>(a);
-      else if (!strcmp(var, "g1b6")) attn_fwd_vec_kernel<4, MODE, 1, 6><<<blocks, WARPS * 32, 0, stream>>>(a);
-      else if (!strcmp(var, "g2b5")) attn_fwd_vec_kernel<4, MODE, 2, 5><<<blocks, WARPS * 32, 0, stream>>>(a);
-      else attn_fwd_vec_kernel<4, MODE, 2, 4><<<blocks, WARPS * 32, 0, stream>>>(a);
+      const dim3 g_(blocks), b_(WARPS * 32);
+      if (!strcmp(var, "g4b3")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 4, 3>, g_, b_, 0, stream, a));
+      else if (!strcmp(var, "g1b5")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 1, 5>, g_, b_, 0, stream, a));
+      else if (!strcmp(var, "g1b6")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 1, 6>, g_, b_, 0, stream, a));
+      else if (!strcmp(var, "g2b5")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 2, 5>, g_, b_, 0, stream, a));
+      else WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 2, 4>, g_, b_, 0, stream, a));
     } else {
       switch (a.D / 128) {
-#define CASE(NV, GRP, MINB) case NV: attn_fwd_vec_kernel<NV, MODE, GRP, MINB><<<blocks, WARPS * 32, 0, stream>>>(a); break;
+#define CASE(NV, GRP, MINB) case NV: \
+        WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<NV, MODE, GRP, MINB>, dim3(blocks), dim3(WARPS * 32), 0, stream, a)); break;
         CASE(1, 4, 4) CASE(2, 4, 4) CASE(3, 2, 4) CASE(4, 2, 4) CASE(5, 2, 2) CASE(6, 2, 2) CASE(7, 2, 2) CASE(8, 2, 2)
 #undef CASE
       }

@@ -139,6 +139,7 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >
 struct SplitJob { const float* src; int64_t ld_src; int64_t rows; __nv_bfloat16* dst; };
 
 __global__ void __launch_bounds__(256) split_bf16_kernel(SplitJob a, SplitJob b, int K) {
+  wsi_pdl_trigger();                                      // the GEMM that follows may set itself up while this drains
   const int kv = K >> 2;                                  // float4 groups per row (K % 8 == 0)
   const int64_t na = a.rows * kv, total = na + b.rows * kv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -224,6 +225,10 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   cluster_sync();                                                    // peer barriers are initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
+  // everything above (barriers, TMEM, tensor-map prefetch) may run while the previous kernel of the stream drains;
+  // from here on its outputs are read
+  wsi_pdl_trigger();
+  wsi_pdl_wait();
 
   if (warp == 0) {
     // ===================================================================== TMA producer (one lane per CTA)
@@ -480,10 +485,13 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   if (total == 0) return WSI_OK;
   const int pairs = total < sms / 2 ? total : sms / 2;               // one CTA pair (cluster of 2) per two SMs
   const bool gelu = ep.act == WSI_ACT_GELU;       // compile-time in the kernel: the erf code must not sit (predicated off) in the plain epilogue
-  if (full && gelu) typed_linear_tc_kernel<true, true><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
-  else if (full) typed_linear_tc_kernel<true, false><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
-  else if (gelu) typed_linear_tc_kernel<false, true><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
-  else typed_linear_tc_kernel<false, false><<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, segs, ep, a);
+  const dim3 grid(2 * pairs), block(THREADS);
+  cudaError_t le;
+  if (full && gelu) le = wsi_launch_pdl(typed_linear_tc_kernel<true, true>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
+  else if (full) le = wsi_launch_pdl(typed_linear_tc_kernel<true, false>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
+  else if (gelu) le = wsi_launch_pdl(typed_linear_tc_kernel<false, true>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
+  else le = wsi_launch_pdl(typed_linear_tc_kernel<false, false>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
+  WSI_CHECK_CUDA(le);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }
