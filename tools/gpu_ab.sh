@@ -4,6 +4,7 @@ TAG=${1:-ab}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 tail -8 gpurun_out/${TAG}_pytest.log
+timeout 300 python tools/sweep_dev.py > gpurun_out/${TAG}_sweep.jsonl 2>&1
 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_a.json 2> gpurun_out/${TAG}_bench_a.err
 env $2 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_b.json 2> gpurun_out/${TAG}_bench_b.err
 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_a2.json 2>> gpurun_out/${TAG}_bench_a.err

@@ -72,13 +72,18 @@ def main():
             kw = dict(skip=torch.ones(T, device=dev), res=torch.randn(N, n_out, device=dev),
                       row_gate=torch.ones(N, device=dev))
         tags = ((0, "full"), (1, "no MMA"), (2, "no TMA"), (4, "no epilogue body"), (5, "TMA only"), (6, "MMA only"))
-        for dbg, tag in (tags if args.gemm_dbg else tags[:1]):
-            setenv(WSI_TC_DEBUG=dbg or None)
-            for want_split in (False, True):
-                ms = timeit(lambda: ops.typed_linear_split(xs, ws, b, ptr, n_out, want_split=want_split, **kw), args.reps, flush)
-                print(json.dumps({"kernel": f"typed_linear_split[{name}]", "variant": tag, "y_split": want_split, "ms": ms,
-                                  "tflops": 2.0 * N * K * n_out / (ms * 1e-3) / 1e12}), flush=True)
-        setenv(WSI_TC_DEBUG=None)
+        for bn in (None, 128, 256):
+            setenv(WSI_TC_BN=bn)
+            for dbg, tag in (tags if args.gemm_dbg else tags[:1]):
+                setenv(WSI_TC_DEBUG=dbg or None)
+                for want_split in (False, True):
+                    ms = timeit(lambda: ops.typed_linear_split(xs, ws, b, ptr, n_out, want_split=want_split, **kw), args.reps, flush)
+                    print(json.dumps({"kernel": f"typed_linear_split[{name}]", "variant": f"{tag} BN={bn or 'auto'}", "y_split": want_split,
+                                      "ms": ms, "tflops": 2.0 * N * K * n_out / (ms * 1e-3) / 1e12}), flush=True)
+        setenv(WSI_TC_DEBUG=None, WSI_TC_BN=None)
+    # measurement floor: an (almost) empty kernel timed the same way
+    z = torch.zeros(32, device=dev)
+    print(json.dumps({"kernel": "floor: z.add_(1) on 32 floats", "ms": timeit(lambda: z.add_(1.0), args.reps, flush)}), flush=True)
 
     D, H = 512, 4
     G = synthetic.synth_slide_graph(N, 64, T, 5, seed=1).to(dev)
@@ -92,8 +97,7 @@ def main():
     def warm():
         kvq.add_(0.0)
 
-    variants = [dict(), dict(WSI_ATTN_VARIANT="g4b3"), dict(WSI_ATTN_VARIANT="g1b5"), dict(WSI_ATTN_VARIANT="g1b6"),
-                dict(WSI_ATTN_VARIANT="g2b5"), dict(WSI_ATTN_KERNEL="ring")]
+    variants = [dict(), dict(WSI_NO_PDL=1)]
     keys = sorted({k for v in variants for k in v})
     for var in variants:
         setenv(**{k: var.get(k) for k in keys})

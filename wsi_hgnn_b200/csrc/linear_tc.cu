@@ -29,17 +29,21 @@
 namespace {
 
 constexpr int BM = 128;            // rows per CTA (TMEM lanes)
-constexpr int BN = 256;            // columns per tile (UMMA N; each CTA of the pair stages BN/2 rows of W)
+// Two tile shapes (template parameter BN = columns per tile = UMMA N; each CTA of the pair stages BN/2 rows of W):
+//   BN 256, 3-stage ring: the fewest L2 -> smem bytes per flop; used when there are several tiles per CTA pair
+//   BN 128, 4-stage ring: twice as many (half-size) tiles, so that with one 256-wide tile per CTA pair the epilogue of
+//                         the first half tile overlaps the MMAs of the second - measured slower (more operand bytes),
+//                         kept behind WSI_TC_BN=128
 constexpr int BK = 64;             // bf16 per k-block = one 128 B swizzle row
-constexpr int STAGES = 3, UMMA_K = 16;
+constexpr int UMMA_K = 16;
 constexpr int PAIR_M = 2 * BM;     // rows per CTA pair (UMMA M = 256, cta_group::2)
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;       // per CTA
 constexpr int EPI_LD = 32;                               // staging row pitch in floats; float4 slots XOR-swizzled by row
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
 constexpr int EPI_WARPS = 8;                             // 2 warps per TMEM lane quarter, each takes half of the columns
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * EPI_WARP_FLOATS * 4 + 256;
+constexpr int stages_of(int bn) { return bn == 256 ? 3 : 4; }
+constexpr int stage_bytes_of(int bn) { return 2 * A_TILE_BYTES + 2 * (bn / 2) * BK * 2; }       // per CTA
+constexpr int smem_bytes_of(int bn) { return 1024 + stages_of(bn) * stage_bytes_of(bn) + EPI_WARPS * EPI_WARP_FLOATS * 4 + 256; }
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -132,7 +136,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   return d;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
+constexpr uint32_t idesc_of(int bn) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24); }
 
 // ------------------------------------------------------------------------------------------ pre-pass
 // fp32 -> [hi; lo] bf16.  src rows have stride ld_src floats; dst is dense [2 * rows, K] (lo half at row `rows`).
@@ -187,10 +191,12 @@ __device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc,
   return make_float4(a[0], a[1], a[2], a[3]);
 }
 
-template <bool FULL, bool GELU>
+template <bool FULL, bool GELU, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ TypeSegs segs, const __grid_constant__ LinearEpilogue ep, TcArgs a) {
+  constexpr int STAGES = stages_of(BN), STAGE_BYTES = stage_bytes_of(BN), B_TILE_BYTES = (BN / 2) * BK * 2;
+  constexpr uint32_t IDESC = idesc_of(BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B tiles need 1024 B alignment
@@ -458,17 +464,25 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   TypeSegs segs;
   if (wsi_make_segs(&segs, type_ptr_host, T, PAIR_M) != 0) { wsi_set_error("typed_linear: bad type_ptr"); return WSI_ERR_ARG; }
 
+  // tile shape: 256-wide tiles unless they leave every CTA pair with at most one tile (see the top of the file)
+  int sms = wsi_num_sms();
+  if (sms <= 0) return WSI_ERR_CUDA;
+  // Measured (config 2, tools/sweep_dev.py): the 128-wide tiling loses even for the one-tile-per-pair shapes (a_linear
+  // 32.8 vs 28.7 us, adapt_ws 47.1 vs 34.8 us) - the kernel is bound by L2 -> smem operand bytes, which the narrower
+  // tile raises by 50 %, not by the exposed epilogue.  It stays selectable for experiments only.
+  int BN = 256;
+  if (const char* f = getenv("WSI_TC_BN")) BN = atoi(f) == 128 ? 128 : 256;        // development knob
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    const void* fns[4] = {(const void*)typed_linear_tc_kernel<false, false>, (const void*)typed_linear_tc_kernel<true, false>,
-                          (const void*)typed_linear_tc_kernel<false, true>, (const void*)typed_linear_tc_kernel<true, true>};
-    for (int i = 0; i < 4 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    const void* fns[8] = {(const void*)typed_linear_tc_kernel<false, false, 256>, (const void*)typed_linear_tc_kernel<true, false, 256>,
+                          (const void*)typed_linear_tc_kernel<false, true, 256>, (const void*)typed_linear_tc_kernel<true, true, 256>,
+                          (const void*)typed_linear_tc_kernel<false, false, 128>, (const void*)typed_linear_tc_kernel<true, false, 128>,
+                          (const void*)typed_linear_tc_kernel<false, true, 128>, (const void*)typed_linear_tc_kernel<true, true, 128>};
+    for (int i = 0; i < 8 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(i < 4 ? 256 : 128));
   });
   WSI_CHECK_CUDA(attr_err);
-  int sms = wsi_num_sms();
-  if (sms <= 0) return WSI_ERR_CUDA;
 
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a_ws, 2 * n_rows, K, BM);
@@ -487,10 +501,15 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   const bool gelu = ep.act == WSI_ACT_GELU;       // compile-time in the kernel: the erf code must not sit (predicated off) in the plain epilogue
   const dim3 grid(2 * pairs), block(THREADS);
   cudaError_t le;
-  if (full && gelu) le = wsi_launch_pdl(typed_linear_tc_kernel<true, true>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
-  else if (full) le = wsi_launch_pdl(typed_linear_tc_kernel<true, false>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
-  else if (gelu) le = wsi_launch_pdl(typed_linear_tc_kernel<false, true>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
-  else le = wsi_launch_pdl(typed_linear_tc_kernel<false, false>, grid, block, SMEM_BYTES, stream, tmA, tmB, segs, ep, a);
+#define TC_LAUNCH(F, G, B) le = wsi_launch_pdl(typed_linear_tc_kernel<F, G, B>, grid, block, smem_bytes_of(B), stream, tmA, tmB, segs, ep, a)
+  if (BN == 256) {
+    if (full && gelu) TC_LAUNCH(true, true, 256); else if (full) TC_LAUNCH(true, false, 256);
+    else if (gelu) TC_LAUNCH(false, true, 256); else TC_LAUNCH(false, false, 256);
+  } else {
+    if (full && gelu) TC_LAUNCH(true, true, 128); else if (full) TC_LAUNCH(true, false, 128);
+    else if (gelu) TC_LAUNCH(false, true, 128); else TC_LAUNCH(false, false, 128);
+  }
+#undef TC_LAUNCH
   WSI_CHECK_CUDA(le);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
