@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 12
+#define WSI_ABI_VERSION 13
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -132,12 +132,13 @@ int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_
  * GSpMM backward compute under loss.backward() (trainer/train_gnn.py:68-71 through models/HEATNet4.py:103-119).
  *   d_agg [N, ldg] = gradient of agg.  dk, dv [N, ld*]: ACCUMULATED into (zero them first; rows are shared between
  *   destinations -> vector atomics); dq [N, lddq]: written; d_e [2] = (d e_linear.weight, d e_linear.bias): accumulated.
- *   Nothing is saved by the forward: the segment softmax is recomputed from k, v, q. */
+ *   Nothing is saved by the forward: the segment softmax is recomputed from k, v, q.
+ *   row_order int32 [N] or NULL: processing order of the dst rows (largest in-degree first balances the k-NN hubs). */
 int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
                         const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
                         const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D, int H,
                         const float* d_agg, int64_t ldg, float* dk, int64_t lddk, float* dv, int64_t lddv, float* dq,
-                        int64_t lddq, float* d_e, void* stream);
+                        int64_t lddq, float* d_e, const int32_t* row_order, void* stream);
 
 /* Segment form used by HGT (WSI_SCORE_HGT): one work item per (dst,relation) segment.
  *   seg_ptr int32 [S+1] edge range of segment s (dst-major order), seg_rel int32 [S] MODEL relation id,

@@ -11,7 +11,8 @@ from wsi_hgnn_b200.construct_graph import GraphConstructor, Hnsw, construct_grap
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n,F,radius", [(500, 64, 9), (2000, 128, 7), (33, 16, 6), (4096, 1024, 9)])
+@pytest.mark.parametrize("n,F,radius", [(500, 64, 9), (2000, 128, 7), (33, 16, 6), (4096, 1024, 9), (2503, 128, 7), (1201, 64, 9),
+                                        (1022, 256, 6)])   # incl. N % 4 != 0 on the tensor-core dot-product path
 def test_knn_edges_bit_exact(n, F, radius):
     feats, _ = synthetic.synth_features(n, F, 3, seed=n)
     ref = O.exact_knn_edges(feats.numpy(), radius)

@@ -6,7 +6,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -46,7 +46,7 @@ PROTOTYPES = {
     "wsi_split_bf16": (_I, [_P, _L, _L, _I, _P, _P]),
     "wsi_typed_linear_split": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _P]),
     "wsi_hetero_attn_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _L,
-                                 _P, _P]),
+                                 _P, _P, _P]),
     "wsi_hetero_attn_seg_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P]),
     "wsi_head_perm": (_I, [_I, _I, _P]),
     "wsi_rel_transform": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _L, _P]),

@@ -83,7 +83,7 @@ class HeteroAttnFn(torch.autograd.Function):
         d_kvq = torch.zeros_like(kvq)
         d_e = ops.hetero_attn_bwd(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
                                   plan.e_rel, plan.node_inv_r, e_w, e_b, D, H, d_agg.contiguous(), d_kvq[:, :D],
-                                  d_kvq[:, D:2 * D], d_kvq[:, 2 * D:])
+                                  d_kvq[:, D:2 * D], d_kvq[:, 2 * D:], row_order=plan.rows_by_degree())
         return d_kvq, d_e[0].reshape(e_w.shape), d_e[1].reshape(e_b.shape), None, None, None
 
 

@@ -3,11 +3,11 @@
 // reference's loss.backward() (trainer/train_gnn.py:68-71 through models/HEATNet4.py:103-119).
 //
 // One warp per dst row, lanes span D in the lane-grouped column order (wsi_head_perm).  Nothing is saved by the forward:
-// per (row, relation) segment the scores are recomputed in three streaming passes over the segment's edges
-//   A  m = max_e s_e, Z = sum_e exp(s_e - m)                               (reads K[src])
-//   B  delta = sum_e a_e <g, V[src]>        a_e = exp(s_e - m) / Z         (reads K[src], V[src])
+// per (row, relation) segment the scores are recomputed
+//   AB m = max_e s_e, Z = sum_e exp(s_e - m), delta = sum_e a_e <g, V[src]>  (one online sweep over K[src], V[src])
 //   C  ds_e = a_e (<g, V[src]> - delta)                                    (reads K[src], V[src] - L1/L2 hits)
 //      dQ[row] += ds_e c_e K[src];  dK[src] += ds_e c_e q;  dV[src] += a_e g;   d c_e = ds_e <q, K[src]>
+// (segments of one or two edges, the common case, keep their rows in registers and read them once)
 // with g = dAgg[row] / R_t and c_e = (w sim_e + b) / sqrt(d_k).  dQ rows are owned by their warp; dK / dV rows are
 // shared between destinations and accumulated with 16-byte vector atomics (fp32 red.add: the summation order, not the
 // set of terms, depends on scheduling).  HBM/L2 bound: per edge 3 K + 2 V row reads and 2 row atomics.
@@ -29,6 +29,7 @@ struct BwdArgs {
   float* dV; int64_t lddv;
   float* dQ; int64_t lddq;
   float* d_e;                 // [2]: d e_linear.weight, d e_linear.bias (accumulated)
+  const int* order;           // optional [n_rows]: processing order of the rows (largest in-degree first)
   int n_rows, D, H;
   float inv_sqrt_dk;
 };
@@ -56,15 +57,37 @@ __device__ __forceinline__ float head_dot(const float4* a, const float4* b, int 
   return d;
 }
 
+// per-edge gradient contributions of one edge whose K / V rows are in registers
 template <int NV>
-__global__ void __launch_bounds__(WARPS * 32) attn_bwd_kernel(BwdArgs a) {
+__device__ __forceinline__ void bwd_edge(const BwdArgs& a, int lane, int src, float dsc, float at, const float4* kk,
+                                         const float4* q, const float4* g, float4* dq) {
+  float* dkr = a.dK + (int64_t)src * a.lddk;
+  float* dvr = a.dV + (int64_t)src * a.lddv;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    dq[i].x = fmaf(dsc, kk[i].x, dq[i].x); dq[i].y = fmaf(dsc, kk[i].y, dq[i].y);
+    dq[i].z = fmaf(dsc, kk[i].z, dq[i].z); dq[i].w = fmaf(dsc, kk[i].w, dq[i].w);
+    red_add4(dkr + (i * 32 + lane) * 4, make_float4(dsc * q[i].x, dsc * q[i].y, dsc * q[i].z, dsc * q[i].w));
+    red_add4(dvr + (i * 32 + lane) * 4, make_float4(at * g[i].x, at * g[i].y, at * g[i].z, at * g[i].w));
+  }
+}
+
+// One dst row per warp (rows are dealt out largest first through `order`, one row per warp, so the block scheduler
+// balances the heavy-tailed in-degrees).  Per (row, relation) segment:
+//   n <= 2 edges (the common case of a k-NN graph spread over up to 2 T^2 relations): K and V rows are read ONCE into
+//       registers, everything else is arithmetic on them;
+//   longer segments: pass AB (online softmax statistics and delta together; K and V rows, two edges in flight),
+//       pass C (gradients; K and V rows again, two edges in flight).
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 1) attn_bwd_kernel(BwdArgs a) {
   const int lane = threadIdx.x & 31;
   const int G = 32 / a.H;
   const int n_warps = gridDim.x * WARPS;
   const float ew = __ldg(a.e_w), eb = __ldg(a.e_b);
   float dw_acc = 0.f, db_acc = 0.f;
 
-  for (int row = blockIdx.x * WARPS + (threadIdx.x >> 5); row < a.n_rows; row += n_warps) {
+  for (int idx = blockIdx.x * WARPS + (threadIdx.x >> 5); idx < a.n_rows; idx += n_warps) {
+    const int row = a.order ? __ldg(a.order + idx) : idx;
     const int beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
     const float invr = __ldg(a.inv_r + row);
     float4 dq[NV];
@@ -82,64 +105,95 @@ __global__ void __launch_bounds__(WARPS * 32) attn_bwd_kernel(BwdArgs a) {
       }
       int seg_beg = beg;
       while (seg_beg < end) {
+        // segment = run of edges of one relation; its ids / sims / relation bytes are read lane-parallel, 32 at a time
         const int rel = __ldg(a.e_rel + seg_beg);
-        int seg_end = seg_beg + 1;
-        while (seg_end < end && __ldg(a.e_rel + seg_end) == rel) ++seg_end;
-        // ---- pass A: softmax statistics of the segment
-        float m = -INFINITY, z = 0.f;
-        for (int e = seg_beg; e < seg_end; ++e) {
-          const int src = __ldg(a.e_src + e);
-          const float c = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
-          float4 kk[NV];
-          const float* kr = a.K + (int64_t)src * a.ldk;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) kk[i] = ld4(kr + (i * 32 + lane) * 4);
-          const float s = head_dot<NV>(q, kk, G) * c;
-          const float mn = fmaxf(m, s);
-          z = fmaf(z, __expf(m - mn), __expf(s - mn));
-          m = mn;
+        int seg_end = seg_beg;
+        for (int w0 = seg_beg; w0 < end; w0 += 32) {
+          const int r = (w0 + lane < end) ? (int)__ldg(a.e_rel + w0 + lane) : -1;
+          const unsigned diff = __ballot_sync(FULL, r != rel);
+          if (diff) { seg_end = w0 + __ffs(diff) - 1; break; }
+          seg_end = min(end, w0 + 32);
         }
-        const float inv_z = 1.f / z;
-        // ---- pass B: delta = sum_e a_e <g, v_e>
-        float delta = 0.f;
-        for (int e = seg_beg; e < seg_end; ++e) {
-          const int src = __ldg(a.e_src + e);
-          const float c = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
-          float4 kk[NV], vv[NV];
-          const float* kr = a.K + (int64_t)src * a.ldk;
-          const float* vr = a.V + (int64_t)src * a.ldv;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) { kk[i] = ld4(kr + (i * 32 + lane) * 4); vv[i] = ld4(vr + (i * 32 + lane) * 4); }
-          const float at = __expf(head_dot<NV>(q, kk, G) * c - m) * inv_z;
-          delta = fmaf(at, head_dot<NV>(g, vv, G), delta);
-        }
-        // ---- pass C: the gradients
-        for (int e = seg_beg; e < seg_end; ++e) {
-          const int src = __ldg(a.e_src + e);
-          const float sim = __ldg(a.e_sim + e);
-          const float c = fmaf(ew, sim, eb) * a.inv_sqrt_dk;
-          float4 kk[NV], vv[NV];
-          const float* kr = a.K + (int64_t)src * a.ldk;
-          const float* vr = a.V + (int64_t)src * a.ldv;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) { kk[i] = ld4(kr + (i * 32 + lane) * 4); vv[i] = ld4(vr + (i * 32 + lane) * 4); }
-          const float d = head_dot<NV>(q, kk, G);
-          const float at = __expf(d * c - m) * inv_z;
-          const float ds = at * (head_dot<NV>(g, vv, G) - delta);
-          const float dsc = ds * c;
-          float* dkr = a.dK + (int64_t)src * a.lddk;
-          float* dvr = a.dV + (int64_t)src * a.lddv;
+        const int n = seg_end - seg_beg;
+        if (n <= 2) {
+          // ---- register path: both rows of K and V read once
+          const int s0 = __ldg(a.e_src + seg_beg), s1 = n > 1 ? __ldg(a.e_src + seg_beg + 1) : s0;
+          const float sim0 = __ldg(a.e_sim + seg_beg), sim1 = n > 1 ? __ldg(a.e_sim + seg_beg + 1) : 0.f;
+          float4 k0[NV], k1[NV], v0[NV], v1[NV];
+          const float* kr0 = a.K + (int64_t)s0 * a.ldk; const float* kr1 = a.K + (int64_t)s1 * a.ldk;
+          const float* vr0 = a.V + (int64_t)s0 * a.ldv; const float* vr1 = a.V + (int64_t)s1 * a.ldv;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            dq[i].x = fmaf(dsc, kk[i].x, dq[i].x); dq[i].y = fmaf(dsc, kk[i].y, dq[i].y);
-            dq[i].z = fmaf(dsc, kk[i].z, dq[i].z); dq[i].w = fmaf(dsc, kk[i].w, dq[i].w);
-            red_add4(dkr + (i * 32 + lane) * 4, make_float4(dsc * q[i].x, dsc * q[i].y, dsc * q[i].z, dsc * q[i].w));
-            red_add4(dvr + (i * 32 + lane) * 4, make_float4(at * g[i].x, at * g[i].y, at * g[i].z, at * g[i].w));
+            k0[i] = ld4(kr0 + (i * 32 + lane) * 4); k1[i] = ld4(kr1 + (i * 32 + lane) * 4);
+            v0[i] = ld4(vr0 + (i * 32 + lane) * 4); v1[i] = ld4(vr1 + (i * 32 + lane) * 4);
           }
+          const float c0 = fmaf(ew, sim0, eb) * a.inv_sqrt_dk, c1 = fmaf(ew, sim1, eb) * a.inv_sqrt_dk;
+          const float d0 = head_dot<NV>(q, k0, G), d1 = head_dot<NV>(q, k1, G);
+          const float sc0 = d0 * c0, sc1 = n > 1 ? d1 * c1 : -INFINITY;
+          const float m = fmaxf(sc0, sc1);
+          const float p0 = __expf(sc0 - m), p1 = __expf(sc1 - m);        // exp(-inf) = 0 for the absent edge
+          const float inv_z = 1.f / (p0 + p1);
+          const float a0 = p0 * inv_z, a1 = p1 * inv_z;
+          const float t0 = head_dot<NV>(g, v0, G), t1 = head_dot<NV>(g, v1, G);
+          const float delta = a0 * t0 + a1 * t1;
+          const float ds0 = a0 * (t0 - delta), ds1 = a1 * (t1 - delta);
+          bwd_edge<NV>(a, lane, s0, ds0 * c0, a0, k0, q, g, dq);
+          if (n > 1) bwd_edge<NV>(a, lane, s1, ds1 * c1, a1, k1, q, g, dq);
           if (lane % G == 0) {                            // one lane per head carries the head's d c_e
-            const float dc = ds * d * a.inv_sqrt_dk;
-            dw_acc = fmaf(dc, sim, dw_acc);
-            db_acc += dc;
+            const float dc0 = ds0 * d0 * a.inv_sqrt_dk, dc1 = n > 1 ? ds1 * d1 * a.inv_sqrt_dk : 0.f;
+            dw_acc = fmaf(dc0, sim0, fmaf(dc1, sim1, dw_acc));
+            db_acc += dc0 + dc1;
+          }
+        } else {
+          // ---- pass AB: m, Z and delta in one sweep (online softmax), two edges in flight
+          float m = -INFINITY, z = 0.f, num = 0.f;
+          for (int e = seg_beg; e < seg_end; e += 2) {
+            const bool two = e + 1 < seg_end;
+            const int s0 = __ldg(a.e_src + e), s1 = two ? __ldg(a.e_src + e + 1) : s0;
+            const float c0 = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
+            const float c1 = two ? fmaf(ew, __ldg(a.e_sim + e + 1), eb) * a.inv_sqrt_dk : 0.f;
+            float4 k0[NV], k1[NV], v0[NV], v1[NV];
+            const float* kr0 = a.K + (int64_t)s0 * a.ldk; const float* kr1 = a.K + (int64_t)s1 * a.ldk;
+            const float* vr0 = a.V + (int64_t)s0 * a.ldv; const float* vr1 = a.V + (int64_t)s1 * a.ldv;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              k0[i] = ld4(kr0 + (i * 32 + lane) * 4); k1[i] = ld4(kr1 + (i * 32 + lane) * 4);
+              v0[i] = ld4(vr0 + (i * 32 + lane) * 4); v1[i] = ld4(vr1 + (i * 32 + lane) * 4);
+            }
+            const float sc0 = head_dot<NV>(q, k0, G) * c0, sc1 = two ? head_dot<NV>(q, k1, G) * c1 : -INFINITY;
+            const float t0 = head_dot<NV>(g, v0, G), t1 = head_dot<NV>(g, v1, G);
+            const float mn = fmaxf(m, fmaxf(sc0, sc1));
+            const float corr = __expf(m - mn), p0 = __expf(sc0 - mn), p1 = __expf(sc1 - mn);
+            z = fmaf(z, corr, p0 + p1);
+            num = fmaf(num, corr, fmaf(p0, t0, p1 * t1));
+            m = mn;
+          }
+          const float inv_z = 1.f / z;
+          const float delta = num * inv_z;
+          // ---- pass C: the gradients, two edges in flight
+          for (int e = seg_beg; e < seg_end; e += 2) {
+            const bool two = e + 1 < seg_end;
+            const int s0 = __ldg(a.e_src + e), s1 = two ? __ldg(a.e_src + e + 1) : s0;
+            const float sim0 = __ldg(a.e_sim + e), sim1 = two ? __ldg(a.e_sim + e + 1) : 0.f;
+            const float c0 = fmaf(ew, sim0, eb) * a.inv_sqrt_dk, c1 = fmaf(ew, sim1, eb) * a.inv_sqrt_dk;
+            float4 k0[NV], k1[NV], v0[NV], v1[NV];
+            const float* kr0 = a.K + (int64_t)s0 * a.ldk; const float* kr1 = a.K + (int64_t)s1 * a.ldk;
+            const float* vr0 = a.V + (int64_t)s0 * a.ldv; const float* vr1 = a.V + (int64_t)s1 * a.ldv;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              k0[i] = ld4(kr0 + (i * 32 + lane) * 4); k1[i] = ld4(kr1 + (i * 32 + lane) * 4);
+              v0[i] = ld4(vr0 + (i * 32 + lane) * 4); v1[i] = ld4(vr1 + (i * 32 + lane) * 4);
+            }
+            const float d0 = head_dot<NV>(q, k0, G), d1 = head_dot<NV>(q, k1, G);
+            const float a0 = __expf(d0 * c0 - m) * inv_z, a1 = two ? __expf(d1 * c1 - m) * inv_z : 0.f;
+            const float ds0 = a0 * (head_dot<NV>(g, v0, G) - delta), ds1 = a1 * (head_dot<NV>(g, v1, G) - delta);
+            bwd_edge<NV>(a, lane, s0, ds0 * c0, a0, k0, q, g, dq);
+            if (two) bwd_edge<NV>(a, lane, s1, ds1 * c1, a1, k1, q, g, dq);
+            if (lane % G == 0) {
+              const float dc0 = ds0 * d0 * a.inv_sqrt_dk, dc1 = two ? ds1 * d1 * a.inv_sqrt_dk : 0.f;
+              dw_acc = fmaf(dc0, sim0, fmaf(dc1, sim1, dw_acc));
+              db_acc += dc0 + dc1;
+            }
           }
         }
         seg_beg = seg_end;
@@ -164,7 +218,8 @@ extern "C" int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, 
                                    const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
                                    const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D,
                                    int H, const float* d_agg, int64_t ldg, float* dk, int64_t lddk, float* dv,
-                                   int64_t lddv, float* dq, int64_t lddq, float* d_e, void* stream) {
+                                   int64_t lddv, float* dq, int64_t lddq, float* d_e, const int32_t* row_order,
+                                   void* stream) {
   WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hetero_attn_bwd: bad n_rows");
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(k && v && q && rowptr && node_inv_r && e_w && e_b && d_agg && dk && dv && dq && d_e,
@@ -180,10 +235,8 @@ extern "C" int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, 
   a.rowptr = rowptr; a.e_src = e_src; a.e_sim = e_sim; a.e_rel = e_rel; a.inv_r = node_inv_r; a.e_w = e_w; a.e_b = e_b;
   a.dAgg = d_agg; a.ldg = ldg; a.dK = dk; a.lddk = lddk; a.dV = dv; a.lddv = lddv; a.dQ = dq; a.lddq = lddq; a.d_e = d_e;
   a.n_rows = (int)n_rows; a.D = D; a.H = H; a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
-  int sms = wsi_num_sms();
-  if (sms <= 0) return WSI_ERR_CUDA;
-  int blocks = (int)((n_rows + WARPS - 1) / WARPS);
-  if (blocks > sms * 16) blocks = sms * 16;
+  a.order = row_order;
+  const int blocks = (int)((n_rows + WARPS - 1) / WARPS);     // one row per warp: the block scheduler is the queue
   cudaStream_t st = wsi_stream(stream);
   switch (D / 128) {
 #define CASE(NV) case NV: attn_bwd_kernel<NV><<<blocks, WARPS * 32, 0, st>>>(a); break;

@@ -34,11 +34,11 @@ __device__ __forceinline__ bool pair_less(float d1, int i1, float d2, int i2) {
 // the lanes; then re-rank them by the exact fp64 distance and emit the first `topn`.
 __global__ void __launch_bounds__(256)
 knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn, const float* __restrict__ dot,
-                  int64_t n, int F, int topn, int64_t q0, int n_q, int32_t* __restrict__ nbr,
+                  int64_t ld_dot, int64_t n, int F, int topn, int64_t q0, int n_q, int32_t* __restrict__ nbr,
                   float* __restrict__ nbr_dist) {
   const int lane = threadIdx.x & 31;
   for (int qi = blockIdx.x * 8 + (threadIdx.x >> 5); qi < n_q; qi += gridDim.x * 8) {
-    const float* drow = dot + (int64_t)qi * n;
+    const float* drow = dot + (int64_t)qi * ld_dot;
     float best_d = INFINITY;       // lane i holds the i-th smallest pair so far
     int best_i = 0x7fffffff;
     float thresh = INFINITY;       // = pair held by lane CAND-1
@@ -137,7 +137,8 @@ extern "C" int64_t wsi_knn_workspace_bytes(int64_t n, int F, int topn, int64_t q
   (void)topn;
   if (n <= 0 || q_end <= q_begin) return 0;
   const int64_t qc = query_chunk(n, q_end - q_begin);
-  return align256(n * 4) + align256(qc * n * 4) + align256(wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0));
+  const int64_t n4 = (n + 3) & ~(int64_t)3;       // row pitch of the dot-product matrix (16 B rows for the tcgen05 epilogue)
+  return align256(n * 4) + align256(qc * n4 * 4) + align256(wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0));
 }
 
 extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64_t q_begin, int64_t q_end,
@@ -155,8 +156,9 @@ extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64
   const int64_t qc = query_chunk(n, q_end - q_begin);
   char* ws = (char*)workspace;
   float* sqn = (float*)ws;
+  const int64_t n4 = (n + 3) & ~(int64_t)3;
   float* dot = (float*)(ws + align256(n * 4));
-  void* lin_ws = ws + align256(n * 4) + align256(qc * n * 4);
+  void* lin_ws = ws + align256(n * 4) + align256(qc * n4 * 4);
   const int64_t lin_ws_bytes = wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0);
   int blocks = (int)((n + 7) / 8 < 148 * 16 ? (n + 7) / 8 : 148 * 16);
   row_sqnorm_kernel<<<blocks, 256, 0, st>>>(feat, n, F, sqn);
@@ -165,10 +167,10 @@ extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64
     const int n_q = (int)((q_end - q0) < qc ? (q_end - q0) : qc);
     int32_t tp[2] = {0, n_q};
     int rc = wsi_typed_linear_f32(feat + q0 * F, F, feat, nullptr, F, (int)n, tp, 1, WSI_ACT_NONE, nullptr, nullptr, 0,
-                                  nullptr, 0, nullptr, nullptr, dot, n, 0, lin_ws, lin_ws_bytes, stream);
+                                  nullptr, 0, nullptr, nullptr, dot, n4, 0, lin_ws, lin_ws_bytes, stream);
     if (rc != WSI_OK) return rc;
     int sb = (n_q + 7) / 8 < 148 * 16 ? (n_q + 7) / 8 : 148 * 16;
-    knn_select_kernel<<<sb, 256, 0, st>>>(feat, sqn, dot, n, F, topn, q0, n_q, nbr + (q0 - q_begin) * topn,
+    knn_select_kernel<<<sb, 256, 0, st>>>(feat, sqn, dot, n4, n, F, topn, q0, n_q, nbr + (q0 - q_begin) * topn,
                                           nbr_dist ? nbr_dist + (q0 - q_begin) * topn : nullptr);
     WSI_CHECK_LAUNCH();
   }

@@ -17,7 +17,7 @@ int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_d
                      int64_t b_rows, void* b_dst, int K, cudaStream_t stream);
 
 extern "C" int wsi_typed_linear_tc_ok(int64_t n_rows, int K, int n_out) {
-  return wsi_typed_linear_tc_supported(n_rows, K, n_out, K) ? 1 : 0;
+  return (wsi_typed_linear_tc_supported(n_rows, K, n_out, K) && n_out % 4 == 0) ? 1 : 0;
 }
 
 extern "C" int wsi_split_bf16(const float* src, int64_t ld_src, int64_t rows, int K, void* dst, void* stream) {
@@ -39,7 +39,7 @@ extern "C" int wsi_typed_linear_split(const void* x_split, const void* w_split, 
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(x_split && w_split && (y || y_split), "typed_linear_split: null pointer");
   WSI_CHECK_ARG(!y || ldy >= n_out, "typed_linear_split: row stride smaller than the row");
-  if (!wsi_typed_linear_tc_supported(n_rows, K, n_out, K)) {
+  if (!wsi_typed_linear_tc_supported(n_rows, K, n_out, K) || n_out % 4 != 0) {
     wsi_set_error("typed_linear_split: shape (rows=%lld K=%d n_out=%d) does not fit the tcgen05 path",
                   (long long)n_rows, K, n_out);
     return WSI_ERR_UNSUPPORTED;
@@ -77,7 +77,11 @@ extern "C" int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w,
   ep.y = y; ep.ldy = ldy; ep.n_out = n_out;
   const bool ptr_ok = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) |
                         reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(drop_mask)) & 15) == 0 &&
-                      ldy % 4 == 0 && (!res || ldres % 4 == 0) && (!drop_mask || ldmask % 4 == 0);
+                      ldy % 4 == 0 && (!res || ldres % 4 == 0) && (!drop_mask || ldmask % 4 == 0) &&
+                      // a width that is not a multiple of 4 (the k-NN dot products against N candidates): the epilogue's
+                      // last float4 spills into the row padding, so the pitch must cover it and there must be no
+                      // per-column vector that would be read past its end
+                      (n_out % 4 == 0 || (ldy >= ((n_out + 3) & ~3) && !bias && !res && !drop_mask));
   const bool tc_ok = wsi_typed_linear_tc_supported(n_rows, K, n_out, ldx) && ptr_ok && workspace != nullptr;
   if (impl == 2 && !tc_ok) {
     wsi_set_error("typed_linear: shape (rows=%lld K=%d n_out=%d ldx=%lld) does not fit the tcgen05 path",

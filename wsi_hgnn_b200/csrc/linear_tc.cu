@@ -440,7 +440,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Shapes the tensor-core path takes: K a multiple of 8 (16 B rows for TMA / float4 split), output rows 16 B
 // aligned, and enough work to fill 128-row MMA tiles (small [B, D] readout GEMMs stay on the SIMT path).
 bool wsi_typed_linear_tc_supported(int64_t n_rows, int K, int n_out, int64_t ldx) {
-  return n_rows >= 512 && n_rows < (1ll << 30) && K >= 64 && K % 8 == 0 && n_out >= 64 && n_out % 4 == 0 &&
+  // (n_out % 4 != 0 is accepted here; the callers then require a padded output pitch and no per-column vectors:
+  //  the epilogue stores whole float4 groups, see wsi_typed_linear_f32)
+  return n_rows >= 512 && n_rows < (1ll << 30) && K >= 64 && K % 8 == 0 && n_out >= 64 &&
          ldx % 4 == 0 && (int64_t)n_out * WSI_MAX_TYPES < (1ll << 30);
 }
 

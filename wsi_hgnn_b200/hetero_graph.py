@@ -333,6 +333,14 @@ class GraphPlan:
         self.cache[key] = work
         return work
 
+    def rows_by_degree(self):
+        """int32 [N]: dst rows in decreasing in-degree order (ties by row id) - the processing order of the attention
+        backward, whose one-row-per-warp blocks are dealt out by the hardware scheduler (heaviest rows first)."""
+        if "rows_by_degree" not in self.cache:
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            self.cache["rows_by_degree"] = torch.argsort(deg, descending=True, stable=True).to(torch.int32).contiguous()
+        return self.cache["rows_by_degree"]
+
     def transposed(self):
         """(t_rowptr, t_eid, e_dst) for the backward scatter to src rows."""
         if self._t is None:

@@ -216,9 +216,11 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
 
 
 def hetero_attn_bwd(k, v, q, rowptr, e_src, e_sim, e_rel, node_inv_r, e_w, e_b, D: int, H: int, d_agg: torch.Tensor,
-                    dk: torch.Tensor, dv: torch.Tensor, dq: torch.Tensor) -> torch.Tensor:
+                    dk: torch.Tensor, dv: torch.Tensor, dq: torch.Tensor,
+                    row_order: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Backward of the HEAT edge attention; see wsi_hetero_attn_bwd.  dk / dv must be zero-filled (accumulated into),
-    dq is written.  -> d_e fp32 [2] = (d e_linear.weight, d e_linear.bias)."""
+    dq is written.  row_order: int32 [N] processing order of the rows (GraphPlan.rows_by_degree()).
+    -> d_e fp32 [2] = (d e_linear.weight, d e_linear.bias)."""
     lib = _lib.load()
     stream = _prep(q)
     N = int(q.shape[0])
@@ -234,7 +236,7 @@ def hetero_attn_bwd(k, v, q, rowptr, e_src, e_sim, e_rel, node_inv_r, e_w, e_b, 
                                  _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
                                  _vec(e_rel, "e_rel", torch.uint8), _vec(node_inv_r, "node_inv_r"),
                                  _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, D, H, gp, ldg, dkp, lddk,
-                                 dvp, lddv, dqp, lddq, d_e.data_ptr(), stream)
+                                 dvp, lddv, dqp, lddq, d_e.data_ptr(), _vec(row_order, "row_order", torch.int32), stream)
     _lib.check(rc, "wsi_hetero_attn_bwd")
     return d_e
 
