@@ -180,6 +180,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # torchrun pins OMP_NUM_THREADS=1; the synthetic slides are generated on the host (exact fp64 k-NN), so give every
+    # rank its share of the cores for that set-up phase
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
