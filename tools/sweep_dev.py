@@ -72,15 +72,15 @@ def main():
             kw = dict(skip=torch.ones(T, device=dev), res=torch.randn(N, n_out, device=dev),
                       row_gate=torch.ones(N, device=dev))
         tags = ((0, "full"), (1, "no MMA"), (2, "no TMA"), (4, "no epilogue body"), (5, "TMA only"), (6, "MMA only"))
-        for bn in (None, 128, 256):
-            setenv(WSI_TC_BN=bn)
+        for bn, cl in ((256, 2), (256, 4)):
+            setenv(WSI_TC_BN=bn, WSI_TC_CL=cl)
             for dbg, tag in (tags if args.gemm_dbg else tags[:1]):
                 setenv(WSI_TC_DEBUG=dbg or None)
                 for want_split in (False, True):
                     ms = timeit(lambda: ops.typed_linear_split(xs, ws, b, ptr, n_out, want_split=want_split, **kw), args.reps, flush)
-                    print(json.dumps({"kernel": f"typed_linear_split[{name}]", "variant": f"{tag} BN={bn or 'auto'}", "y_split": want_split,
+                    print(json.dumps({"kernel": f"typed_linear_split[{name}]", "variant": f"{tag} BN={bn} CL={cl}", "y_split": want_split,
                                       "ms": ms, "tflops": 2.0 * N * K * n_out / (ms * 1e-3) / 1e12}), flush=True)
-        setenv(WSI_TC_DEBUG=None, WSI_TC_BN=None)
+        setenv(WSI_TC_DEBUG=None, WSI_TC_BN=None, WSI_TC_CL=None)
     # measurement floor: an (almost) empty kernel timed the same way
     z = torch.zeros(32, device=dev)
     print(json.dumps({"kernel": "floor: z.add_(1) on 32 floats", "ms": timeit(lambda: z.add_(1.0), args.reps, flush)}), flush=True)

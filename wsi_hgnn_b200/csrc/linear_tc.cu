@@ -91,12 +91,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t clu
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
 }
+// same, multicast: the box lands at the same smem offset in every CTA of `mask` (cluster ranks) and each copy posts its
+// bytes on the full barrier of the destination CTA's pair leader (barrier operand with the peer bit clear)
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint32_t cluster_bar, uint32_t dst, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // arrive (once the MMAs issued so far retire) on the barrier at this smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+__device__ __forceinline__ void tc_commit_mask(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
+               ::"r"(bar), "h"(mask) : "memory");
 }
 // D[tmem, 256 x N over the CTA pair] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -191,12 +200,19 @@ __device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc,
   return make_float4(a[0], a[1], a[2], a[3]);
 }
 
-template <bool FULL, bool GELU, int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+// CL = CTAs per cluster.  CL 2: one CTA pair per cluster (as described at the top).  CL 4: TWO pairs that work on the two
+// neighbouring column tiles (tn, tn + 1) of the same 256 rows and SHARE the A operand: each CTA loads only half of the
+// A rows it needs (64 of 128, hi and lo) and TMA-multicasts them to the CTA of the other pair that needs the same rows,
+// which cuts the L2 -> smem operand bytes per flop by 25 % - the measured limiter of this kernel.  A ring slot is then
+// written from both pairs, so it is released by the tcgen05.commit of BOTH pairs (empty barriers count 2, commit
+// multicast to all four CTAs).
+template <bool FULL, bool GELU, int BN, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ TypeSegs segs, const __grid_constant__ LinearEpilogue ep, TcArgs a) {
   constexpr int STAGES = stages_of(BN), STAGE_BYTES = stage_bytes_of(BN), B_TILE_BYTES = (BN / 2) * BK * 2;
   constexpr uint32_t IDESC = idesc_of(BN);
+  constexpr bool MC = CL == 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B tiles need 1024 B alignment
@@ -208,17 +224,22 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();                           // 0 = leader (issues the MMAs of the pair)
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;                                   // 0 = leader (issues the MMAs of the pair)
+  const uint32_t pc = crank >> 1;                                    // pair index inside the cluster (0 when CL == 2)
+  const uint32_t leader = crank & ~1u;                               // cluster rank of this pair's leader
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pc));             // both CTAs of this pair
+  const int pair = blockIdx.x / CL, n_pairs = gridDim.x / CL;        // (cluster index / count: a cluster owns a tile or, CL 4, a tile pair)
   const int num_kb = (a.K + BK - 1) / BK;
-  const int total_tiles = a.n_tiles_m * a.n_tiles_n;
+  const int n_tn = MC ? a.n_tiles_n / 2 : a.n_tiles_n;              // column (super)tiles
+  const int total_tiles = a.n_tiles_m * n_tn;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     // full: the leader's expect_tx arrive + the peer's plain arrive; empty / tmem_full: one tcgen05.commit;
     // tmem_empty (leader's is the one waited on): the epilogue warps of both CTAs
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -240,19 +261,26 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===================================================================== TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const uint16_t a_mask = (uint16_t)(5u << rank);                // the CTAs (one per pair) that need the same A rows
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const int tm = tile / a.n_tiles_n, tn = tile - tm * a.n_tiles_n;
+        const int tm = tile / n_tn, tn = MC ? 2 * (tile - tm * n_tn) + (int)pc : tile - tm * n_tn;
         const int t = wsi_tile_group(segs, tm);
         const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * PAIR_M + (int)rank * BM;
         const int wrow0 = t * a.n_out + tn * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = mapa(full_bar + 8 * stage, 0);
+          const uint32_t fb = mapa(full_bar + 8 * stage, leader);
           const uint32_t s0 = base + stage * STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(full_bar + 8 * stage, (a.dbg & 2) ? 0 : 2 * STAGE_BYTES);
           if (!(a.dbg & 2)) {
-          tma_load_2d(&tmA, fb, s0, kb * BK, row0);
-          tma_load_2d(&tmA, fb, s0 + A_TILE_BYTES, kb * BK, a.n_rows + row0);
+          if (MC) {                                                  // my half (64 rows) of the shared A rows, to both pairs
+            const int half_rows = BM / 2, off = (int)pc * half_rows;
+            tma_load_2d_mc(&tmA, fb, s0 + off * BK * 2, kb * BK, row0 + off, a_mask);
+            tma_load_2d_mc(&tmA, fb, s0 + A_TILE_BYTES + off * BK * 2, kb * BK, a.n_rows + row0 + off, a_mask);
+          } else {
+            tma_load_2d(&tmA, fb, s0, kb * BK, row0);
+            tma_load_2d(&tmA, fb, s0 + A_TILE_BYTES, kb * BK, a.n_rows + row0);
+          }
           tma_load_2d(&tmB, fb, s0 + 2 * A_TILE_BYTES, kb * BK, wrow0);
           tma_load_2d(&tmB, fb, s0 + 2 * A_TILE_BYTES + B_TILE_BYTES, kb * BK, a.w_rows + wrow0);
           }
@@ -288,8 +316,9 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
               }
             }
-            tc_commit_pair(empty_bar + 8 * stage);                   // smem slot free (both CTAs) once these retire
-            if (kb == num_kb - 1) tc_commit_pair(tfull_bar + 8 * acc);   // accumulator complete (both CTAs)
+            // smem slot free once these retire: in both CTAs of the pair, and - with shared A tiles - in the other pair too
+            tc_commit_mask(empty_bar + 8 * stage, MC ? (uint16_t)0xF : pair_mask);
+            if (kb == num_kb - 1) tc_commit_mask(tfull_bar + 8 * acc, pair_mask);   // accumulator complete (both CTAs)
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -307,7 +336,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr int CHUNKS = BN / 32 / 2;                              // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-      const int tm = tile / a.n_tiles_n, tn = tile - tm * a.n_tiles_n;
+      const int tm = tile / n_tn, tn = MC ? 2 * (tile - tm * n_tn) + (int)pc : tile - tm * n_tn;
       const int t = wsi_tile_group(segs, tm);
       const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * PAIR_M + (int)rank * BM + q * 32;
       const int rows_left = segs.ptr[t + 1] - (row0 + rsub);         // this lane handles rows row0 + rsub + 4 it
@@ -385,7 +414,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar + 8 * acc, 0));   // on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar + 8 * acc, leader));   // on the leader's barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -474,20 +503,48 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   // tile raises by 50 %, not by the exposed epilogue.  It stays selectable for experiments only.
   int BN = 256;
   if (const char* f = getenv("WSI_TC_BN")) BN = atoi(f) == 128 ? 128 : 256;        // development knob
+  // cluster shape.  The 4-CTA variant (two pairs sharing the A operand by TMA multicast) is bit-identical and was
+  // measured on config 2: K|V|Q 43.0 vs 43.0 us, a_linear 28.7 vs 28.7 us, adapt_ws (K = 1024) 32.8 vs 34.8 us, whole
+  // forward +0.5 % - the L2 evidently already merges the two pairs' concurrent reads of the same A tile, and only 33
+  // four-CTA clusters (132 of 148 SMs) are co-resident.  Default stays one pair per cluster; WSI_TC_CL=4 selects it.
+  int CL = 2;
+  if (const char* f = getenv("WSI_TC_CL")) CL = (atoi(f) == 4 && BN == 256 && ((n_out + BN - 1) / BN) % 2 == 0) ? 4 : 2;   // development knob
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
+  static int max_clusters4 = 0;
   std::call_once(attr_once, [] {
-    const void* fns[8] = {(const void*)typed_linear_tc_kernel<false, false, 256>, (const void*)typed_linear_tc_kernel<true, false, 256>,
-                          (const void*)typed_linear_tc_kernel<false, true, 256>, (const void*)typed_linear_tc_kernel<true, true, 256>,
-                          (const void*)typed_linear_tc_kernel<false, false, 128>, (const void*)typed_linear_tc_kernel<true, false, 128>,
-                          (const void*)typed_linear_tc_kernel<false, true, 128>, (const void*)typed_linear_tc_kernel<true, true, 128>};
-    for (int i = 0; i < 8 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(i < 4 ? 256 : 128));
+    const void* fns[12] = {(const void*)typed_linear_tc_kernel<false, false, 256, 2>, (const void*)typed_linear_tc_kernel<true, false, 256, 2>,
+                           (const void*)typed_linear_tc_kernel<false, true, 256, 2>, (const void*)typed_linear_tc_kernel<true, true, 256, 2>,
+                           (const void*)typed_linear_tc_kernel<false, false, 256, 4>, (const void*)typed_linear_tc_kernel<true, false, 256, 4>,
+                           (const void*)typed_linear_tc_kernel<false, true, 256, 4>, (const void*)typed_linear_tc_kernel<true, true, 256, 4>,
+                           (const void*)typed_linear_tc_kernel<false, false, 128, 2>, (const void*)typed_linear_tc_kernel<true, false, 128, 2>,
+                           (const void*)typed_linear_tc_kernel<false, true, 128, 2>, (const void*)typed_linear_tc_kernel<true, true, 128, 2>};
+    for (int i = 0; i < 12 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(i < 8 ? 256 : 128));
+    if (attr_err == cudaSuccess) {                                   // how many 4-CTA clusters (1 CTA / SM) fit on the chip at once
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes_of(256);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      int n = 0;
+      for (int with_attr = 0; with_attr < 2 && n <= 0; ++with_attr) {      // (the kernel carries __cluster_dims__ itself)
+        cfg.numAttrs = with_attr;
+        if (cudaOccupancyMaxActiveClusters(&n, (const void*)typed_linear_tc_kernel<false, false, 256, 4>, &cfg) != cudaSuccess) {
+          (void)cudaGetLastError();
+          n = 0;
+        }
+      }
+      max_clusters4 = n;
+      if (getenv("WSI_TC_VERBOSE")) fprintf(stderr, "[wsi] typed_linear(tcgen05): %d co-resident 4-CTA clusters\n", n);
+    }
   });
   WSI_CHECK_CUDA(attr_err);
+  if (CL == 4 && max_clusters4 < 8) CL = 2;                          // (no usable 4-CTA placement on this device)
 
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, a_ws, 2 * n_rows, K, BM);
+  int rc = make_map(&tmA, a_ws, 2 * n_rows, K, CL == 4 ? BM / 2 : BM);
   if (rc != WSI_OK) return rc;
   rc = make_map(&tmB, w_ws, 2 * (int64_t)T * n_out, K, BN / 2);
   if (rc != WSI_OK) return rc;
@@ -497,19 +554,23 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   a.y_split = reinterpret_cast<__nv_bfloat16*>(y_split);
   const bool full = ep.skip || ep.drop_mask || ep.row_scale;
   { const char* d = getenv("WSI_TC_DEBUG"); a.dbg = d ? atoi(d) : 0; }
-  const int total = a.n_tiles_m * a.n_tiles_n;
+  const int total = a.n_tiles_m * (CL == 4 ? a.n_tiles_n / 2 : a.n_tiles_n);       // tiles (CL 2) or tile pairs (CL 4)
   if (total == 0) return WSI_OK;
-  const int pairs = total < sms / 2 ? total : sms / 2;               // one CTA pair (cluster of 2) per two SMs
+  const int max_clusters = CL == 4 ? max_clusters4 : sms / 2;        // persistent: one cluster per CL SMs
+  const int clusters = total < max_clusters ? total : max_clusters;
   const bool gelu = ep.act == WSI_ACT_GELU;       // compile-time in the kernel: the erf code must not sit (predicated off) in the plain epilogue
-  const dim3 grid(2 * pairs), block(THREADS);
+  const dim3 grid(CL * clusters), block(THREADS);
   cudaError_t le;
-#define TC_LAUNCH(F, G, B) le = wsi_launch_pdl(typed_linear_tc_kernel<F, G, B>, grid, block, smem_bytes_of(B), stream, tmA, tmB, segs, ep, a)
-  if (BN == 256) {
-    if (full && gelu) TC_LAUNCH(true, true, 256); else if (full) TC_LAUNCH(true, false, 256);
-    else if (gelu) TC_LAUNCH(false, true, 256); else TC_LAUNCH(false, false, 256);
+#define TC_LAUNCH(F, G, B, C) le = wsi_launch_pdl(typed_linear_tc_kernel<F, G, B, C>, grid, block, smem_bytes_of(B), stream, tmA, tmB, segs, ep, a)
+  if (BN == 256 && CL == 4) {
+    if (full && gelu) TC_LAUNCH(true, true, 256, 4); else if (full) TC_LAUNCH(true, false, 256, 4);
+    else if (gelu) TC_LAUNCH(false, true, 256, 4); else TC_LAUNCH(false, false, 256, 4);
+  } else if (BN == 256) {
+    if (full && gelu) TC_LAUNCH(true, true, 256, 2); else if (full) TC_LAUNCH(true, false, 256, 2);
+    else if (gelu) TC_LAUNCH(false, true, 256, 2); else TC_LAUNCH(false, false, 256, 2);
   } else {
-    if (full && gelu) TC_LAUNCH(true, true, 128); else if (full) TC_LAUNCH(true, false, 128);
-    else if (gelu) TC_LAUNCH(false, true, 128); else TC_LAUNCH(false, false, 128);
+    if (full && gelu) TC_LAUNCH(true, true, 128, 2); else if (full) TC_LAUNCH(true, false, 128, 2);
+    else if (gelu) TC_LAUNCH(false, true, 128, 2); else TC_LAUNCH(false, false, 128, 2);
   }
 #undef TC_LAUNCH
   WSI_CHECK_CUDA(le);
