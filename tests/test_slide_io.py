@@ -73,11 +73,23 @@ def test_stream_forward_matches_per_slide_forward():
     slides = [FlatSlide.from_graph(g, pin=True) for g in graphs]
     with torch.no_grad():
         ref = [ours(g.to(dev)).cpu() for g in graphs]
-    for depth in (1, 2, 3):
-        outs = list(stream_forward(ours, slides, dev, depth=depth))
-        assert len(outs) == len(ref)
-        for o, r in zip(outs, ref):
-            assert torch.equal(o, r)                                  # same kernels, same inputs: bit-identical
-    assert list(stream_forward(ours, [], dev)) == []
+    for threaded in (True, False):
+        for depth in (1, 3, 5):
+            outs = list(stream_forward(ours, slides, dev, depth=depth, threaded=threaded))
+            assert len(outs) == len(ref)
+            for o, r in zip(outs, ref):
+                assert torch.equal(o, r)                              # same kernels, same inputs: bit-identical
+        assert list(stream_forward(ours, [], dev, threaded=threaded)) == []
+        assert len(list(stream_forward(ours, slides[:1], dev, threaded=threaded))) == 1
+    # an abandoned generator must not leave the worker thread behind, and a failing slide source surfaces its error
+    gen = stream_forward(ours, slides * 3, dev)
+    assert torch.equal(next(gen), ref[0])
+    gen.close()
+
+    def bad():
+        yield slides[0]
+        raise ValueError("broken slide source")
+    with pytest.raises(ValueError, match="broken slide source"):
+        list(stream_forward(ours, bad(), dev))
     with pytest.raises(RuntimeError):
         list(stream_forward(ours, slides, "cpu"))

@@ -71,8 +71,9 @@ def main():
         if full:
             kw = dict(skip=torch.ones(T, device=dev), res=torch.randn(N, n_out, device=dev),
                       row_gate=torch.ones(N, device=dev))
-        tags = ((0, "full"), (1, "no MMA"), (2, "no TMA"), (4, "no epilogue body"), (5, "TMA only"), (6, "MMA only"))
-        for bn, cl in ((256, 2), (256, 4)):
+        tags = ((0, "full"), (4, "no epilogue body"), (8, "epilogue w/o global stores"), (16, "epilogue w/o TMEM reads"),
+                (24, "epilogue: smem transposes only"), (5, "TMA only"), (6, "MMA only"), (3, "epilogue only"))
+        for bn, cl in ((256, 2),):
             setenv(WSI_TC_BN=bn, WSI_TC_CL=cl)
             for dbg, tag in (tags if args.gemm_dbg else tags[:1]):
                 setenv(WSI_TC_DEBUG=dbg or None)

@@ -74,6 +74,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// same without release semantics: for signals that order nothing in memory (the epilogue's "accumulator drained": the
+// TMEM reads are already complete - tcgen05.wait::ld - and a release would first wait for the warp's global stores)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -177,7 +182,8 @@ struct TcArgs {
   int K, n_out;
   int n_tiles_m, n_tiles_n;   // n_tiles_m counts 256-row PAIR tiles
   __nv_bfloat16* y_split;   // optional [2 * n_rows, n_out] bf16 (hi; lo) copy of y: the next GEMM's A operand
-  int dbg;           // development only (env WSI_TC_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads, bit 2 = skip the epilogue body
+  int dbg;           // development only (env WSI_TC_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads, bit 2 = skip the epilogue body,
+                     // bit 3 = no global stores in the epilogue, bit 4 = no TMEM reads in the epilogue
 };
 
 // FULL = false: v = act(acc + bias).  FULL = true: + dropout mask, sigma(skip) residual mix with row gate, row scale.
@@ -367,6 +373,12 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
       };
       if (FULL) load_res(0, rr[0]);
+      // the bias vectors of all chunks too: a load issued inside the chunk loop sat in the dependent chain of every chunk
+      // (the "epilogue only" knob timing was 1.9 us per 32 x 32 chunk, almost all of it this L2 round trip)
+      float4 bb_all[CHUNKS];
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c)
+        bb_all[c] = (bias_p && n0 + c * 32 < a.n_out) ? __ldg(reinterpret_cast<const float4*>(bias_p + c * 32)) : zero4;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
@@ -374,11 +386,16 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int c = 0; c < CHUNKS; ++c) {
         if (n0 - c4 + c * 32 >= a.n_out || rows_left + rsub <= 0 || (a.dbg & 4)) break;   // warp-uniform: nothing left to store
         float v[32];
-        tc_ld_32x32(taddr + c * 32, v);
+        if (a.dbg & 16) {                                            // development: no TMEM read
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        } else {
+          tc_ld_32x32(taddr + c * 32, v);
+        }
         const bool n_ok = n0 + c * 32 < a.n_out;
         // issue every global load of this chunk before waiting on TMEM
-        float4 bb = zero4, mm[8];
-        if (bias_p && n_ok) bb = __ldg(reinterpret_cast<const float4*>(bias_p + c * 32));
+        const float4 bb = bb_all[c];
+        float4 mm[8];
         if (FULL) {
           if (c + 1 < CHUNKS) load_res(c + 1, rr[(c + 1) & 1]);
 #pragma unroll
@@ -398,8 +415,9 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const float4 accv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * EPI_LD + ((((lane & 7) ^ ((it * 4 + rsub) & 7))) << 2));
             const float4 o = FULL ? epi_mix4<true, GELU>(ep, accv, bb, mm[it], rr[c & 1][it], alpha, gate[it] != 0.f, rscl[it])
                                   : epi_mix4<false, GELU>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
-            if (ep.y) *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
-            if (a.y_split) {
+            if (ep.y && !(a.dbg & 8)) *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
+            else if (a.dbg & 8) { if (o.x == 123456.789f) yp[0] = o.y; }       // development: no global stores (keep the math alive)
+            if (a.y_split && !(a.dbg & 8)) {
               __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
               wsi_split_bf16(o.x, h0, l0); wsi_split_bf16(o.y, h1, l1); wsi_split_bf16(o.z, h2, l2); wsi_split_bf16(o.w, h3, l3);
               __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
@@ -414,7 +432,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar + 8 * acc, leader));   // on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar + 8 * acc, leader));   // on the leader's barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

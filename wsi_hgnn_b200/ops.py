@@ -16,7 +16,9 @@ ACT_NONE, ACT_GELU = 0, 1
 POOL_OPS = {"sum": 0, "mean": 1, "max": 2}
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 
-_cur_device = [None]
+import threading
+
+_cur_device = threading.local()      # cudaSetDevice is per host thread (the streaming evaluator plans on a worker thread)
 
 
 def _prep(t: torch.Tensor):
@@ -25,9 +27,9 @@ def _prep(t: torch.Tensor):
         raise RuntimeError("wsi_hgnn_b200 ops need CUDA tensors: the hot path has no CPU fallback "
                            "(the CPU oracle under oracle/ is test infrastructure only)")
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
-    if _cur_device[0] != idx:
+    if getattr(_cur_device, "idx", None) != idx:
         _lib.check(_lib.load().wsi_set_device(idx), "wsi_set_device")
-        _cur_device[0] = idx
+        _cur_device.idx = idx
     return torch._C._cuda_getCurrentRawStream(idx)       # raw cudaStream_t of torch's current stream (no Stream object)
 
 

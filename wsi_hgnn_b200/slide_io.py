@@ -16,7 +16,9 @@ flat slides with the copy of slide i+1 (copy engine, its own stream) overlapping
 logits of slide i-1 read back asynchronously: the per-epoch evaluation loop without a host sync per slide.
 """
 import json
+import queue
 import struct
+import threading
 from typing import Dict, Iterable, Iterator, List, Optional, Tuple
 
 import numpy as np
@@ -160,16 +162,18 @@ def _stream_ctx(dev: torch.device, nbuf: int) -> Dict:
     return ctx
 
 
-def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 3) -> Iterator[torch.Tensor]:
+def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, threaded: bool = False) -> Iterator[torch.Tensor]:
     """Yield the logits ([1, out_dim], host tensor) of every slide, in order.
 
-    Three stages run concurrently on three streams, each one slide ahead of the next:
-        copy stream   slide i+2: ONE host -> device copy of its blob (copy engine)
-        plan stream   slide i+1: CSR + work-list build on the device blob (the two small host reads of the planner
-                      wait only for this stream, i.e. for a copy that was queued a whole slide earlier)
-        main stream   slide i:   forward, logits -> pinned host memory (asynchronous)
-    The host never waits for the main stream except on a slide's own `done` event, `depth` slides later, so the
-    Python / launch cost of slide i+1 overlaps the GPU time of slide i.  `depth` = device blob buffers (>= 3).
+    Three stages run concurrently on three streams, each ahead of the next:
+        copy stream   ONE host -> device copy of the slide's blob (copy engine)
+        plan stream   CSR + work-list build on the device blob (the two small host reads of the planner wait only for
+                      this stream, i.e. for a copy that was queued a whole slide earlier)
+        main stream   forward (wsi_heat_forward), logits -> pinned host memory (asynchronous)
+    The caller's thread interleaves the stages one slide apart; with `threaded` the first two stages are issued by a
+    worker thread instead (planning is the larger part of the host cost per slide, but most of it holds the GIL: on
+    config-2 slides it measured no faster - 0.97 vs 0.93 ms / slide - so it is not the default).  The host never waits for the main stream except on a
+    slide's own `done` event, `depth` slides later.  `depth` = device blob buffers (>= 3).
     The blobs should be pinned (FlatSlide.pin()) for the copies to be asynchronous."""
     dev = torch.device(device)
     if dev.type != "cuda":
@@ -180,19 +184,18 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 3) -
     # allocator cudaMalloc fresh buffers every time, and cudaMalloc stalls for tens of ms once CUDA graphs exist
     ctx = _stream_ctx(dev, nbuf)
     copy_stream, plan_stream, bufs = ctx["copy"], ctx["plan"], ctx["bufs"]
-    free_ev: List[Optional[torch.cuda.Event]] = [None] * nbuf       # forward that last read the buffer has finished
     was_training = model.training
     model.eval()
 
-    def upload(i: int, s: FlatSlide):
-        k, n = i % nbuf, s.header["nbytes"]
+    def upload(k: int, s: FlatSlide, free_ev):
+        n = s.header["nbytes"]
         with torch.cuda.stream(copy_stream):
             if bufs[k] is None or bufs[k].numel() < n:
-                if free_ev[k] is not None:
-                    free_ev[k].synchronize()
+                if free_ev is not None:
+                    free_ev.synchronize()
                 bufs[k] = torch.empty(int(n * 1.25) + _ALIGN, dtype=torch.uint8, device=dev)
-            elif free_ev[k] is not None:
-                copy_stream.wait_event(free_ev[k])
+            elif free_ev is not None:
+                copy_stream.wait_event(free_ev)                     # the forward that last read this buffer
             bufs[k][:n].copy_(s.blob[:n], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
@@ -210,41 +213,105 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 3) -
             ev.record(plan_stream)
         return G, k, ev
 
+    def forward(planned):
+        G, k, ready = planned
+        main.wait_event(ready)
+        with torch.no_grad():
+            out = model(G)
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        return host, done, G                                        # G (and its plan tensors, allocated on the plan
+                                                                    # stream) stay alive until the forward has finished
     pending: List[Tuple[torch.Tensor, torch.cuda.Event, HeteroGraph]] = []
+    stop = threading.Event()
+    worker = None
     try:
-        it = iter(slides)
-        up: List = []                                               # uploaded, not yet planned (at most 1 in flight)
-        for _ in range(2):
-            s = next(it, None)
-            if s is not None:
-                up.append(upload(len(up), s))
-        n_up = len(up)
-        planned = plan(up.pop(0)) if up else None
-        while planned is not None:
-            s = next(it, None)
-            if s is not None:                                       # stage 1: slide i+2
-                up.append(upload(n_up, s))
-                n_up += 1
-            nxt = plan(up.pop(0)) if up else None                   # stage 2: slide i+1
-            G, k, ready = planned                                   # stage 3: slide i
-            main.wait_event(ready)
-            with torch.no_grad():
-                out = model(G)
-            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-            host.copy_(out, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(main)
-            free_ev[k] = done
-            pending.append((host, done, G))                         # G (and its plan tensors, allocated on the plan
-            if len(pending) >= nbuf:                                # stream) stay alive until the forward has finished
-                h, ev, _ = pending.pop(0)
-                ev.synchronize()
-                yield h
-            planned = nxt
+        if threaded:
+            ready_q: "queue.Queue" = queue.Queue(maxsize=max(1, nbuf - 2))
+            free_q = [queue.Queue() for _ in range(nbuf)]           # per buffer: `done` event of the forward that read it
+
+            def produce():
+                try:
+                    torch.cuda.set_device(dev)
+                    up = None
+                    for i, s in enumerate(slides):
+                        if stop.is_set():
+                            return
+                        k, free_ev = i % nbuf, None
+                        if i >= nbuf:
+                            while free_ev is None and not stop.is_set():
+                                try:
+                                    free_ev = free_q[k].get(timeout=0.05)
+                                except queue.Empty:
+                                    pass
+                        nxt = upload(k, s, free_ev)                 # slide i's copy is queued before slide i-1 is planned
+                        if up is not None:
+                            ready_q.put(plan(up))
+                        up = nxt
+                    if up is not None and not stop.is_set():
+                        ready_q.put(plan(up))
+                    ready_q.put(None)
+                except BaseException as e:                          # surfaces in the consumer
+                    ready_q.put(e)
+
+            worker = threading.Thread(target=produce, name="wsi-stream-plan", daemon=True)
+            worker.start()
+            while True:
+                item = ready_q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                host, done, G = forward(item)
+                free_q[item[1]].put(done)
+                pending.append((host, done, G))
+                if len(pending) >= nbuf:
+                    h, ev, _ = pending.pop(0)
+                    ev.synchronize()
+                    yield h
+        else:
+            free_ev: List[Optional[torch.cuda.Event]] = [None] * nbuf
+            it = iter(slides)
+            up: List = []                                           # uploaded, not yet planned
+            n_up = 0
+            for _ in range(2):
+                s = next(it, None)
+                if s is not None:
+                    up.append(upload(n_up % nbuf, s, None))
+                    n_up += 1
+            planned = plan(up.pop(0)) if up else None
+            while planned is not None:
+                s = next(it, None)
+                if s is not None:                                   # stage 1: slide i+2
+                    up.append(upload(n_up % nbuf, s, free_ev[n_up % nbuf]))
+                    n_up += 1
+                nxt = plan(up.pop(0)) if up else None               # stage 2: slide i+1
+                host, done, G = forward(planned)                    # stage 3: slide i
+                free_ev[planned[1]] = done
+                pending.append((host, done, G))
+                if len(pending) >= nbuf:
+                    h, ev, _ = pending.pop(0)
+                    ev.synchronize()
+                    yield h
+                planned = nxt
         for h, ev, _ in pending:
             ev.synchronize()
             yield h
+        pending = []
     finally:
+        stop.set()
+        if worker is not None:
+            try:                                                    # unblock a producer waiting on a full queue
+                while worker.is_alive():
+                    try:
+                        ready_q.get_nowait()
+                    except queue.Empty:
+                        worker.join(timeout=0.05)
+            except Exception:
+                pass
+        torch.cuda.current_stream(dev).synchronize() if pending else None
         ctx["busy"] = False
         if was_training:
             model.train()
