@@ -79,23 +79,48 @@ def build_models(want_oracle: bool, want_ours: bool):
 
 
 class ClockSampler:
-    """nvidia-smi SM clock / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md clocks line).  NVML in-process (one sample
+    per millisecond: the timed region is only tens of ms long); nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.stop = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.th = threading.Thread(target=self.run, daemon=True)
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop.is_set():
             try:
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                    self.stop.wait(0.001)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
-                pass
+                self.nvml = None
             self.stop.wait(0.1)
 
     def __enter__(self):
@@ -112,7 +137,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_forward_time(orc, G, reps: int, warm: int):
