@@ -93,3 +93,24 @@ def test_stream_forward_matches_per_slide_forward():
         list(stream_forward(ours, bad(), dev))
     with pytest.raises(RuntimeError):
         list(stream_forward(ours, slides, "cpu"))
+
+
+@pytest.mark.gpu
+def test_stream_forward_hgt_and_heatnet2():
+    """the streaming evaluator is model-agnostic: HGT (segment planner structures) and HEATNet2 (per-op path at a width
+    the one-call driver does not take) give the same logits as slide-at-a-time forwards"""
+    dev = torch.device("cuda", 0)
+    T = 2
+    graphs = [synthetic.synth_slide_graph(500 + 111 * i, 48, T, 5, seed=80 + i, noise_edges=0.2) for i in range(5)]
+    slides = [FlatSlide.from_graph(g, pin=True) for g in graphs]
+    for name, kw in (("HGT", dict(in_dim=48, hidden_dim=128, out_dim=2, n_layers=2, n_heads=4, use_norm=True)),
+                     ("HEATNet2", dict(in_dim=48, hidden_dim=96, out_dim=2, n_layers=2, n_heads=4, dropuout=0.0))):
+        m = helpers.build_ours(name, T, kw)
+        golden_util.fill_params(m, 5)
+        m = m.to(dev).eval()
+        with torch.no_grad():
+            ref = [m(g.to(dev)).cpu() for g in graphs]
+        outs = list(stream_forward(m, slides, dev))
+        assert len(outs) == len(ref)
+        for o, r in zip(outs, ref):
+            assert helpers.rel_err(o, r) < 1e-6

@@ -49,6 +49,41 @@ def _rebuild(g: HeteroGraph, num_nodes: Dict[str, int], edges, ndata, edata) -> 
     return HeteroGraph(num_nodes, edges, ndata, edata)
 
 
+def keep_nodes(g: HeteroGraph, keep: Dict[str, torch.Tensor]) -> HeteroGraph:
+    """Node-induced subgraph: `keep[nt]` bool [n_nt] (node types not listed keep all their nodes).  Survivors keep their
+    relative order and are relabelled 0..n'-1 per node type; edges with a removed endpoint disappear; every node type
+    and relation of `g` stays in the result, possibly empty (dgl.remove_nodes semantics [DGL-mem])."""
+    dev = g.device
+    new_id: Dict[str, torch.Tensor] = {}
+    counts: List[torch.Tensor] = []
+    masks: Dict[str, torch.Tensor] = {}
+    for nt in g.ntypes:
+        k = keep.get(nt)
+        if k is None:
+            k = torch.ones(g.num_nodes(nt), dtype=torch.bool, device=dev)
+        masks[nt] = k
+        new_id[nt] = torch.cumsum(k.to(torch.int64), 0) - 1                # valid where k
+        counts.append(k.sum())
+    num_nodes, ndata = {}, {}
+    for nt, c in zip(g.ntypes, torch.stack(counts).tolist() if counts else []):        # one host read for all types
+        num_nodes[nt] = int(c)
+        ndata[nt] = {name: v[masks[nt]] for name, v in g.nodes[nt].data.items()}
+    edges, edata = {}, {}
+    for ce in g.canonical_etypes:
+        s, d = g._edges[ce]
+        m = masks[ce[0]][s] & masks[ce[2]][d] if s.numel() else torch.zeros(0, dtype=torch.bool, device=dev)
+        edges[ce] = (new_id[ce[0]][s[m]], new_id[ce[2]][d[m]])
+        edata[ce] = {name: v[m] for name, v in g._edata[ce].items()}
+    return _rebuild(g, num_nodes, edges, ndata, edata)
+
+
+def remove_nodes(g: HeteroGraph, nids, ntype: str) -> HeteroGraph:
+    """dgl.remove_nodes(g, nids, ntype=...) (explainers/gem_het.py:34)."""
+    k = torch.ones(g.num_nodes(ntype), dtype=torch.bool, device=g.device)
+    k[torch.as_tensor(nids, device=g.device).reshape(-1).long()] = False
+    return keep_nodes(g, {ntype: k})
+
+
 class DropNode(BaseTransform):
     def __init__(self, p: float = 0.5, generator: Optional[torch.Generator] = None):
         if not 0.0 <= p <= 1.0:
@@ -58,28 +93,7 @@ class DropNode(BaseTransform):
     def __call__(self, g: HeteroGraph) -> HeteroGraph:
         if self.p == 0:
             return g
-        dev = g.device
-        keep: Dict[str, torch.Tensor] = {}
-        new_id: Dict[str, torch.Tensor] = {}
-        num_nodes: Dict[str, int] = {}
-        ndata = {}
-        counts: List[torch.Tensor] = []
-        for nt in g.ntypes:
-            n = g.num_nodes(nt)
-            k = _rand(n, dev, self.generator) >= self.p
-            keep[nt] = k
-            new_id[nt] = torch.cumsum(k.to(torch.int64), 0) - 1            # valid where k
-            counts.append(k.sum())
-        for nt, c in zip(g.ntypes, torch.stack(counts).tolist() if counts else []):    # one host read for all types
-            num_nodes[nt] = int(c)
-            ndata[nt] = {name: v[keep[nt]] for name, v in g.nodes[nt].data.items()}
-        edges, edata = {}, {}
-        for ce in g.canonical_etypes:
-            s, d = g._edges[ce]
-            m = keep[ce[0]][s] & keep[ce[2]][d] if s.numel() else torch.zeros(0, dtype=torch.bool, device=dev)
-            edges[ce] = (new_id[ce[0]][s[m]], new_id[ce[2]][d[m]])
-            edata[ce] = {name: v[m] for name, v in g._edata[ce].items()}
-        return _rebuild(g, num_nodes, edges, ndata, edata)
+        return keep_nodes(g, {nt: _rand(g.num_nodes(nt), g.device, self.generator) >= self.p for nt in g.ntypes})
 
 
 class DropEdge(BaseTransform):
