@@ -650,14 +650,22 @@ class HeteroGraph:
         # every small host-side array of the plan travels in ONE buffer (pinned + non-blocking on CUDA: a pageable
         # torch.tensor(..., device=cuda) synchronises the stream, which would serialise the streaming evaluator)
         n_seg = len(seg) - 1
-        head = torch.empty(len(seg) + len(p.type_ptr) + n_seg, dtype=torch.int32)
-        head[:len(seg)] = torch.tensor(seg, dtype=torch.int32)
-        head[len(seg):len(seg) + len(p.type_ptr)] = torch.tensor(p.type_ptr, dtype=torch.int32)
-        head[len(seg) + len(p.type_ptr):] = torch.tensor(seg_inv, dtype=torch.float32).view(torch.int32)
+        R = len(p.rel_list)
+        eptr = [0]
+        for ce in p.rel_list:
+            eptr.append(eptr[-1] + int(self._edges[ce][0].numel()))
+        table = eptr + [p.type_ptr[t] for t in p.rel_src_type] + [0] + [p.type_ptr[t] for t in p.rel_dst_type] + [0]
+        n0, n1, n2 = len(seg), len(seg) + len(p.type_ptr), len(seg) + len(p.type_ptr) + n_seg
+        head = torch.empty(n2 + len(table), dtype=torch.int32)
+        head[:n0] = torch.tensor(seg, dtype=torch.int32)
+        head[n0:n1] = torch.tensor(p.type_ptr, dtype=torch.int32)
+        head[n1:n2] = torch.tensor(seg_inv, dtype=torch.float32).view(torch.int32)
+        head[n2:] = torch.tensor(table, dtype=torch.int32)
         head = _to_device_async(head, dev)
-        p.seg_ptr = head[:len(seg)]
-        p.type_ptr_dev = head[len(seg):len(seg) + len(p.type_ptr)]
-        seg_inv_dev = head[len(seg) + len(p.type_ptr):].view(torch.float32)
+        p.seg_ptr = head[:n0]
+        p.type_ptr_dev = head[n0:n1]
+        seg_inv_dev = head[n1:n2].view(torch.float32)
+        p._rel_table = head[n2:].view(3, R + 1) if (n2 * 4) % 16 == 0 else head[n2:].clone().view(3, R + 1)
         if p.N > 0:
             lens = (p.seg_ptr[1:] - p.seg_ptr[:-1]).to(torch.int64)
             p.node_inv_r = torch.repeat_interleave(seg_inv_dev, lens, output_size=p.N).contiguous()
@@ -691,12 +699,7 @@ class HeteroGraph:
         flat = self._flat_edge_views(p, srcs, dsts, sim_name, have_sim)
         if flat is not None:                  # flat-format graph: the per-relation tensors are slices of three arrays
             src, dst, sim = flat
-            ptr = [0]
-            for s in srcs:
-                ptr.append(ptr[-1] + int(s.numel()))
-            table = _to_device_async(torch.tensor([ptr, [p.type_ptr[t] for t in p.rel_src_type] + [0],
-                                                   [p.type_ptr[t] for t in p.rel_dst_type] + [0]], dtype=torch.int32), dev)
-            p.rowptr, p.e_src, p.e_sim, p.e_rel, _, stats = ops.plan_build_csr(src, dst, sim, table, R, p.N)
+            p.rowptr, p.e_src, p.e_sim, p.e_rel, _, stats = ops.plan_build_csr(src, dst, sim, p._rel_table, R, p.N)
             p._stats = stats
             return
         if all(have_sim):
@@ -710,12 +713,7 @@ class HeteroGraph:
                              for ce, h in zip(p.rel_list, have_sim)])
         src = (torch.cat(srcs) if R > 1 else srcs[0]).to(torch.int64).contiguous()
         dst = (torch.cat(dsts) if R > 1 else dsts[0]).to(torch.int64).contiguous()
-        ptr = [0]
-        for s in srcs:
-            ptr.append(ptr[-1] + int(s.numel()))
-        table = _to_device_async(torch.tensor([ptr, [p.type_ptr[t] for t in p.rel_src_type] + [0],
-                                               [p.type_ptr[t] for t in p.rel_dst_type] + [0]], dtype=torch.int32), dev)
-        p.rowptr, p.e_src, p.e_sim, p.e_rel, _, stats = ops.plan_build_csr(src, dst, sim, table, R, p.N)
+        p.rowptr, p.e_src, p.e_sim, p.e_rel, _, stats = ops.plan_build_csr(src, dst, sim, p._rel_table, R, p.N)
         p._stats = stats                  # [0] max in-degree, [1] range-error flag: read lazily (no sync here)
 
     def _flat_edge_views(self, p: GraphPlan, srcs, dsts, sim_name: str, have_sim):

@@ -55,6 +55,20 @@ def _vec(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
     return t.data_ptr()
 
 
+_DT_SIZE = {torch.int32: 4, torch.float32: 4, torch.uint8: 1, torch.int64: 8, torch.bfloat16: 2}
+
+
+def _arena(dev, specs):
+    """Several device arrays out of ONE allocation (each torch.empty costs the host ~5 us: the planner of the streamed
+    end-to-end path makes ~20 of them per slide).  specs: [(numel, dtype)] -> list of 1-D views, 256 B aligned."""
+    offs, total = [], 0
+    for n, dt in specs:
+        offs.append(total)
+        total += (max(int(n), 0) * _DT_SIZE[dt] + 255) // 256 * 256
+    buf = torch.empty(max(total, 256), dtype=torch.uint8, device=dev)
+    return [buf[o:o + max(int(n), 0) * _DT_SIZE[dt]].view(dt) for o, (n, dt) in zip(offs, specs)], buf
+
+
 def host_i32(values: Sequence[int]):
     return (ctypes.c_int32 * len(values))(*[int(v) for v in values])
 
@@ -328,14 +342,12 @@ def plan_build_csr(src: torch.Tensor, dst: torch.Tensor, sim: Optional[torch.Ten
     stream = _prep(rel_table)
     dev = rel_table.device
     E = int(src.shape[0])
-    rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
-    e_src = torch.empty(E, dtype=torch.int32, device=dev)
-    e_sim = torch.empty(E, dtype=torch.float32, device=dev)
-    e_rel = torch.empty(E, dtype=torch.uint8, device=dev)
-    e_dst = torch.empty(E, dtype=torch.int32, device=dev) if want_dst else None
-    stats = torch.empty(4, dtype=torch.int32, device=dev)
     ws_bytes = lib.wsi_plan_workspace_bytes(n_nodes, E)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    (rowptr, e_src, e_sim, e_rel, e_dst, stats, ws), _ = _arena(dev, [
+        (n_nodes + 1, torch.int32), (E, torch.int32), (E, torch.float32), (E, torch.uint8),
+        (E if want_dst else 0, torch.int32), (4, torch.int32), (ws_bytes, torch.uint8)])
+    if not want_dst:
+        e_dst = None
     sim32 = sim64 = None
     if sim is not None:
         if sim.dtype == torch.float64:
@@ -358,11 +370,10 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
     lib = _lib.load()
     stream = _prep(rowptr)
     dev = rowptr.device
-    i32 = dict(dtype=torch.int32, device=dev)
-    scans = torch.empty((2, n_nodes + 1), **i32)
-    hist = torch.empty(2 * (chunk + 1), **i32)
     ws_bytes = lib.wsi_plan_workspace_bytes(n_nodes, 0)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    (scans, hist, ws), _ = _arena(dev, [(2 * (n_nodes + 1), torch.int32), (2 * (chunk + 1), torch.int32),
+                                        (ws_bytes, torch.uint8)])
+    scans = scans.view(2, n_nodes + 1)
     rp, rl = _vec(rowptr, "rowptr", torch.int32), _vec(e_rel, "e_rel", torch.uint8)
     _lib.check(lib.wsi_plan_attn_work_count(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(),
                                             hist.data_ptr(), ws.data_ptr(), ws_bytes, stream),
@@ -372,18 +383,20 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
     else:
         (n_part, n_split), max_deg, bad = scans[:, n_nodes].tolist(), None, 0
     n_items = n_part + n_nodes - n_split
-    items = torch.empty((max(n_items, 1), 4), **i32)
-    split_row = torch.empty(max(n_split, 1), **i32)
-    split_ptr = torch.empty(n_split + 1, **i32)
-    part_rel = torch.empty(max(n_part, 1), **i32)
-    part_split = torch.empty(max(n_part, 1), **i32)
-    split_cnt = torch.zeros(max(n_split, 1), **i32)                  # arrival counters of the fused merge (self-resetting)
+    i32 = torch.int32
+    # (split_cnt | sched) adjacent: the arrival counters of the fused merge (self-resetting) and the queue words, zeroed once
+    (items, split_row, split_ptr, part_rel, part_split, zeroed), _ = _arena(dev, [
+        (4 * max(n_items, 1), i32), (max(n_split, 1), i32), (n_split + 1, i32), (max(n_part, 1), i32),
+        (max(n_part, 1), i32), (max(n_split, 1) + 64, i32)])
+    items = items.view(max(n_items, 1), 4)
+    zeroed.zero_()
+    split_cnt, sched = zeroed[:max(n_split, 1)], zeroed[max(n_split, 1) + 62:max(n_split, 1) + 64]
     _lib.check(lib.wsi_plan_attn_work_fill(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(), n_part,
                                            n_split, hist.data_ptr(), items.data_ptr(), split_row.data_ptr(),
                                            split_ptr.data_ptr(), part_rel.data_ptr(), part_split.data_ptr(), stream),
                "wsi_plan_attn_work_fill")
     return dict(items=items, n_items=n_items, split_row=split_row, split_ptr=split_ptr, part_rel=part_rel,
-                part_split=part_split, split_cnt=split_cnt, sched=torch.zeros(2, **i32),
+                part_split=part_split, split_cnt=split_cnt, sched=sched,
                 n_split=n_split, n_part=n_part, max_in_degree=max_deg, bad_edges=bool(bad))
 
 
