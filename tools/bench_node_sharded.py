@@ -58,7 +58,10 @@ def main():
         return time.perf_counter()
 
     # ---- edge builder, query rows sharded
-    knn_edges_sharded(feats[:4096].contiguous(), args.radius, comm) if world > 1 else None      # warm-up
+    if world > 1:                                                                              # warm-up (one-time set-up costs)
+        knn_edges_sharded(feats[:4096].contiguous(), args.radius, comm)
+    else:
+        construct_graph_arrays(feats[:4096].contiguous(), args.radius)
     t0 = sync_time()
     if world > 1:
         ei, et, sim = knn_edges_sharded(feats, args.radius, comm)
