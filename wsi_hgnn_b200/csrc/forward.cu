@@ -42,6 +42,13 @@ extern "C" int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_g
                 "heat_forward: shapes (N=%lld F=%d D=%d) do not fit the tcgen05 chain", (long long)N, F, D);
   WSI_CHECK_ARG(p->n_out >= 1 && p->n_out <= 8 && p->M, "heat_forward: n_out=%d must be in [1, 8]", p->n_out);
   WSI_CHECK_ARG(!x_out || ldx >= D, "heat_forward: x_out row stride smaller than D");
+  WSI_CHECK_ARG(ldf >= F && ldl >= p->n_out, "heat_forward: feat / logits row stride smaller than the row");
+  WSI_CHECK_ARG(p->w_in_split && g->seg_ptr && g->node_inv_r && g->e_src && g->e_sim && g->e_rel && g->items &&
+                    (L == 0 || (p->w_kvq_split && p->b_kvq && p->w_a_split && p->b_a && p->skip && p->e_w && p->e_b)),
+                "heat_forward: null pointer in the graph / parameter structs");
+  for (int l = 0; l < L; ++l)
+    WSI_CHECK_ARG(p->w_kvq_split[l] && p->w_a_split[l] && p->skip[l] && p->e_w[l] && p->e_b[l],
+                  "heat_forward: null per-layer pointer (layer %d)", l);
   const int64_t need = wsi_heat_forward_workspace_bytes(N, F, D, g->n_part, T, B);
   WSI_CHECK_ARG(workspace && workspace_bytes >= need, "heat_forward: workspace of %lld bytes needed", (long long)need);
 

@@ -184,6 +184,7 @@ class GraphPlan:
         self.r_count: List[int] = []          # R_t per type (batch mode)
         self._max_in_degree = 0
         self._stats = None                    # device int32 [4] of the native builder, read lazily
+        self._rel_table = None                # device int32 [3, R + 1]: edge range / src offset / dst offset per relation
         self._t = None
         self.device = torch.device("cpu")
         self.seg_nonempty = None              # bool [T, B] on host

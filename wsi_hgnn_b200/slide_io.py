@@ -311,7 +311,8 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
                         worker.join(timeout=0.05)
             except Exception:
                 pass
-        torch.cuda.current_stream(dev).synchronize() if pending else None
+        if pending:                                                 # abandoned mid-way: let the queued forwards finish
+            torch.cuda.current_stream(dev).synchronize()            # before their buffers are handed to the next call
         ctx["busy"] = False
         if was_training:
             model.train()
