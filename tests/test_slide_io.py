@@ -114,3 +114,27 @@ def test_stream_forward_hgt_and_heatnet2():
         assert len(outs) == len(ref)
         for o, r in zip(outs, ref):
             assert helpers.rel_err(o, r) < 1e-6
+
+
+@pytest.mark.gpu
+def test_plan_on_equals_graph_plan():
+    """the header-driven planner of the streaming path builds exactly the plan HeteroGraph.plan() builds"""
+    dev = torch.device("cuda", 0)
+    for G in (synthetic.synth_slide_graph(900, 32, 3, 5, seed=3, noise_edges=0.2),
+              synthetic.random_hetero_graph([40, 0, 25], 300, 12, seed=3, hub=70),
+              synthetic.random_hetero_graph([30, 20], 0, 8, seed=1)):
+        s = FlatSlide.from_graph(G, pin=True)
+        blob = s.blob[:s.header["nbytes"]].to(dev)
+        p, feat = s.plan_on(blob)
+        Gd = s.graph_on(blob)
+        q = Gd.plan()
+        assert (p.ntypes, p.rel_list, p.type_ptr, p.N, p.E, p.B) == (q.ntypes, q.rel_list, q.type_ptr, q.N, q.E, q.B)
+        assert (p.rel_src_type, p.rel_dst_type, p.r_count, p.seg_ptr_host) == (q.rel_src_type, q.rel_dst_type, q.r_count, q.seg_ptr_host)
+        assert torch.equal(p.seg_nonempty, q.seg_nonempty)
+        for name in ("seg_ptr", "type_ptr_dev", "rowptr", "e_src", "e_sim", "e_rel", "node_inv_r"):
+            assert torch.equal(getattr(p, name), getattr(q, name)), name
+        assert torch.equal(feat, Gd.packed_ndata("feat"))
+        if p.E:
+            wa, wb = p.attn_work(), q.attn_work()
+            assert wa["n_items"] == wb["n_items"] and wa["n_part"] == wb["n_part"] and wa["n_split"] == wb["n_split"]
+            assert torch.equal(wa["split_ptr"], wb["split_ptr"]) and torch.equal(wa["part_rel"][:wa["n_part"]], wb["part_rel"][:wb["n_part"]])

@@ -248,13 +248,27 @@ class _HEATBase(nn.Module):
         return self._packs.get(("native", tuple(order), tuple(names), collapse_heads), params, build)
 
     def _forward_native(self, G: HeteroGraph, plan: GraphPlan, collapse_heads: bool, return_embeddings: bool):
+        return self._forward_native_core(plan, packed_features(G, plan, None), G.independent, collapse_heads,
+                                         return_embeddings)
+
+    def forward_planned(self, plan: GraphPlan, feat: torch.Tensor, independent: bool = False):
+        """Inference from an already built plan and the packed [N, F] features (no HeteroGraph): the entry the
+        streaming evaluator uses.  -> logits, or None when the one-call driver does not take this shape / mode (the
+        caller then goes through forward(G))."""
+        n_out = self.head.out_features if hasattr(self, "head") else next(iter(self.linears_prediction.values())).out_features
+        if not self.native_forward or not self._native_ok(None, plan, None, n_out):
+            return None
+        return self._forward_native_core(plan, feat, independent, hasattr(self, "head"), False)
+
+    def _forward_native_core(self, plan: GraphPlan, feat: torch.Tensor, independent: bool, collapse_heads: bool,
+                             return_embeddings: bool):
         import ctypes
         from .. import _lib
         lib = _lib.load()
         order = _graph_type_order(plan, self.node_dict)
         names = list(plan.ntypes)
         P, _keep = self._native_params(plan, order, names, collapse_heads)
-        key = ("native_graph", G.independent)
+        key = ("native_graph", independent)
         if key not in plan.cache:
             w = plan.attn_work()
             g = _lib.HeatGraph()
@@ -270,11 +284,10 @@ class _HEATBase(nn.Module):
             g.split_cnt = w["split_cnt"].data_ptr() if w.get("split_cnt") is not None else None
             g.sched = w["sched"].data_ptr() if w.get("sched") is not None else None
             g.n_split, g.n_part = w["n_split"], w["n_part"]
-            scale = readout_scale(plan, G.independent)
+            scale = readout_scale(plan, independent)
             ws_bytes = lib.wsi_heat_forward_workspace_bytes(plan.N, P.F, P.D, w["n_part"], len(names), plan.B)
             plan.cache[key] = (g, scale, ws_bytes, tpc, w)
         g, scale, ws_bytes, _, _ = plan.cache[key]
-        feat = packed_features(G, plan, None)
         if feat.dtype != torch.float32 or feat.stride(1) != 1:
             feat = feat.float().contiguous()
         stream = ops._prep(feat)

@@ -135,6 +135,76 @@ class FlatSlide:
         G._flat_edges = (src, dst, sim)                           # plan() reads them without concatenating
         return G
 
+    def _plan_head(self):
+        """Host side of the plan of this (single) slide, computed once per FlatSlide: everything GraphPlan needs that
+        follows from the header alone, and ONE pinned int32 buffer [seg_ptr | rel table | node_inv_r] for the device."""
+        if getattr(self, "_head", None) is None:
+            h = self.header
+            ntypes, n_per = h["ntypes"], h["num_nodes"]
+            rel_list = [tuple(ce) for ce in h["canonical_etypes"]]
+            if len(rel_list) > 255:
+                raise ValueError("at most 255 relations are supported")
+            tix = {nt: i for i, nt in enumerate(ntypes)}
+            type_ptr = [0]
+            for n in n_per:
+                type_ptr.append(type_ptr[-1] + n)
+            src_t, dst_t = [tix[ce[0]] for ce in rel_list], [tix[ce[2]] for ce in rel_list]
+            T, R, N = len(ntypes), len(rel_list), type_ptr[-1]
+            r_count = [sum(1 for d in dst_t if d == t) for t in range(T)]
+            eptr = [0]
+            for n in h["num_edges"]:
+                eptr.append(eptr[-1] + n)
+            table = eptr + [type_ptr[t] for t in src_t] + [0] + [type_ptr[t] for t in dst_t] + [0]
+            inv = np.repeat(np.array([1.0 / r if r > 0 else 0.0 for r in r_count], dtype=np.float32), n_per)
+            n0 = T + 1
+            n1 = n0 + len(table)
+            n1p = (n1 + 3) // 4 * 4                                  # node_inv_r starts 16 B aligned
+            buf = torch.zeros(n1p + N, dtype=torch.int32)
+            buf[:n0] = torch.tensor(type_ptr, dtype=torch.int32)
+            buf[n0:n1] = torch.tensor(table, dtype=torch.int32)
+            if N:
+                buf[n1p:] = torch.from_numpy(inv).view(torch.int32)
+            if torch.cuda.is_available():
+                buf = buf.pin_memory()
+            self._head = dict(ntypes=list(ntypes), rel_list=rel_list, type_ptr=type_ptr, src_t=src_t, dst_t=dst_t,
+                              r_count=r_count, N=N, E=eptr[-1], R=R, T=T, n0=n0, n1=n1, n1p=n1p, buf=buf,
+                              nonempty=torch.tensor([[n > 0] for n in n_per], dtype=torch.bool).reshape(T, 1))
+        return self._head
+
+    def plan_on(self, blob: torch.Tensor):
+        """(GraphPlan, packed features [N, F]) of this slide built straight from its device blob - the same plan
+        HeteroGraph.plan() builds for `graph_on(blob)`, without materialising the per-type / per-relation views
+        (~60 tensor objects for a config-2 slide): the host path of the streaming evaluator."""
+        from . import ops
+        from .hetero_graph import GraphPlan
+        hd, h = self._plan_head(), self.header
+        dev = blob.device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatSlide.plan_on needs the blob on a CUDA device")
+        off, F = h["off"], h["feat_dim"]
+        N, E, R, T = hd["N"], hd["E"], hd["R"], hd["T"]
+        head = hd["buf"].to(dev, non_blocking=True)
+        p = GraphPlan()
+        p.device, p.ntypes, p.rel_list = dev, list(hd["ntypes"]), list(hd["rel_list"])
+        p.type_ptr, p.N, p.E, p.B = list(hd["type_ptr"]), N, E, 1
+        p.rel_src_type, p.rel_dst_type, p.r_count = list(hd["src_t"]), list(hd["dst_t"]), list(hd["r_count"])
+        p.seg_ptr_host, p.seg_nonempty = list(hd["type_ptr"]), hd["nonempty"]
+        p.seg_ptr = p.type_ptr_dev = head[:hd["n0"]]
+        p._rel_table = head[hd["n0"]:hd["n1"]].view(3, R + 1)
+        p.node_inv_r = head[hd["n1p"]:].view(torch.float32)
+        feat = blob[off["feat"]:off["feat"] + N * F * 4].view(torch.float32).view(N, F)
+        if E == 0:
+            p.e_src = torch.zeros(0, dtype=torch.int32, device=dev)
+            p.e_sim = torch.zeros(0, dtype=torch.float32, device=dev)
+            p.e_rel = torch.zeros(0, dtype=torch.uint8, device=dev)
+            p.rowptr = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+            return p, feat
+        src = blob[off["src"]:off["src"] + E * 8].view(torch.int64)
+        dst = blob[off["dst"]:off["dst"] + E * 8].view(torch.int64)
+        sim = blob[off["sim"]:off["sim"] + E * 4].view(torch.float32)
+        p.rowptr, p.e_src, p.e_sim, p.e_rel, _, p._stats = ops.plan_build_csr(src, dst, sim, p._rel_table, R, N)
+        return p, feat
+
     def to_graph(self, device="cpu", non_blocking: bool = False) -> HeteroGraph:
         dev = torch.device(device)
         blob = self.blob[:self.header["nbytes"]]
@@ -201,12 +271,19 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
             ev.record(copy_stream)
         return s, k, ev
 
+    fast = hasattr(model, "forward_planned")                        # plan + forward without a HeteroGraph per slide
+
     def plan(staged):
         s, k, uploaded = staged
         with torch.cuda.stream(plan_stream), torch.no_grad():
             plan_stream.wait_event(uploaded)
-            G = s.graph_on(bufs[k][:s.header["nbytes"]])
-            p = G.plan()
+            blob = bufs[k][:s.header["nbytes"]]
+            if fast and s.num_nodes() > 0:
+                p, feat = s.plan_on(blob)
+                G = (s, blob, p, feat)
+            else:
+                G = s.graph_on(blob)
+                p = G.plan()
             if hasattr(model, "prepare_plan"):
                 model.prepare_plan(p)                               # work list etc.: everything with a host read
             ev = torch.cuda.Event()
@@ -217,7 +294,17 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
         G, k, ready = planned
         main.wait_event(ready)
         with torch.no_grad():
-            out = model(G)
+            out = None
+            if isinstance(G, tuple):
+                s, blob, p, feat = G
+                out = model.forward_planned(p, feat)
+                if out is None:                                     # a shape / mode the one-call driver does not take
+                    Gg = s.graph_on(blob)
+                    Gg._plan = p
+                    G = (Gg, blob, p, feat)
+                    out = model(Gg)
+            else:
+                out = model(G)
         host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
         host.copy_(out, non_blocking=True)
         done = torch.cuda.Event()
