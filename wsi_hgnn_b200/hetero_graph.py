@@ -283,7 +283,10 @@ class GraphPlan:
         dev = self.device
         if dev.type == "cuda":
             from . import ops
-            work = ops.plan_attn_work(self.rowptr, self.e_rel, self.N, chunk, self._stats)
+            begun = self.cache.pop(("attn_work_begun", chunk), None)
+            if begun is None:
+                begun = ops.plan_attn_work_begin(self.rowptr, self.e_rel, self.N, chunk, self._stats)
+            work = ops.plan_attn_work_finish(begun)
             if self._stats is not None:
                 self._stats = None
                 self._max_in_degree = work["max_in_degree"]
@@ -341,6 +344,14 @@ class GraphPlan:
             deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
             self.cache["rows_by_degree"] = torch.argsort(deg, descending=True, stable=True).to(torch.int32).contiguous()
         return self.cache["rows_by_degree"]
+
+    def attn_work_begin(self, chunk: int = 16):
+        """Enqueue the counting half of the work-list build (no host wait); attn_work() completes it."""
+        if self.device.type == "cuda" and self.E > 0 and ("attn_work", chunk) not in self.cache and \
+                ("attn_work_begun", chunk) not in self.cache:
+            from . import ops
+            self.cache[("attn_work_begun", chunk)] = ops.plan_attn_work_begin(self.rowptr, self.e_rel, self.N, chunk,
+                                                                               self._stats)
 
     def transposed(self):
         """(t_rowptr, t_eid, e_dst) for the backward scatter to src rows."""

@@ -195,6 +195,12 @@ class _AttnParams(nn.Module):
 
 
 class _HEATBase(nn.Module):
+    def prepare_plan_begin(self, plan: GraphPlan):
+        """The asynchronous half of prepare_plan (kernels + a non-blocking read of the totals): lets the caller enqueue
+        other work before prepare_plan waits."""
+        if len(self.gcs) and ops.head_perm(self.gcs[0].out_size, self.gcs[0].n_heads) is not None:
+            plan.attn_work_begin()
+
     def prepare_plan(self, plan: GraphPlan):
         """Build ahead of time the plan-side structures the forward needs that cost a host read (the hub-balancing
         work list): the streaming evaluator calls this on its planning stream, one slide ahead."""

@@ -363,25 +363,43 @@ def plan_build_csr(src: torch.Tensor, dst: torch.Tensor, sim: Optional[torch.Ten
     return rowptr, e_src, e_sim, e_rel, e_dst, stats
 
 
-def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chunk: int,
-                   stats: Optional[torch.Tensor] = None) -> dict:
-    """Hub-balancing work list of hetero_attn_work; see wsi_plan_attn_work_count / _fill (one host sync for the
-    two totals that size the arrays)."""
+def plan_attn_work_begin(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chunk: int,
+                         stats: Optional[torch.Tensor] = None) -> dict:
+    """First half of plan_attn_work: the counting kernels and an ASYNCHRONOUS read of the totals into pinned host
+    memory (event recorded on the current stream).  The caller can enqueue other work before plan_attn_work_finish
+    waits for that event - the streaming evaluator launches the previous slide's forward in between."""
     lib = _lib.load()
     stream = _prep(rowptr)
     dev = rowptr.device
     ws_bytes = lib.wsi_plan_workspace_bytes(n_nodes, 0)
-    (scans, hist, ws), _ = _arena(dev, [(2 * (n_nodes + 1), torch.int32), (2 * (chunk + 1), torch.int32),
-                                        (ws_bytes, torch.uint8)])
+    (scans, hist, ws, totals), _ = _arena(dev, [(2 * (n_nodes + 1), torch.int32), (2 * (chunk + 1), torch.int32),
+                                                (ws_bytes, torch.uint8), (4, torch.int32)])
     scans = scans.view(2, n_nodes + 1)
     rp, rl = _vec(rowptr, "rowptr", torch.int32), _vec(e_rel, "e_rel", torch.uint8)
     _lib.check(lib.wsi_plan_attn_work_count(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(),
                                             hist.data_ptr(), ws.data_ptr(), ws_bytes, stream),
                "wsi_plan_attn_work_count")
-    if stats is not None:                                             # the one host sync (totals + builder flags)
-        n_part, n_split, max_deg, bad = torch.cat([scans[:, n_nodes], stats[:2]]).tolist()
-    else:
-        (n_part, n_split), max_deg, bad = scans[:, n_nodes].tolist(), None, 0
+    totals[:2] = scans[:, n_nodes]
+    if stats is not None:
+        totals[2:] = stats[:2]
+    host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+    host.copy_(totals, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return dict(rowptr=rowptr, e_rel=e_rel, n_nodes=n_nodes, chunk=chunk, scans=scans, hist=hist, ws=ws, host=host, ev=ev,
+                has_stats=stats is not None)
+
+
+def plan_attn_work_finish(ctx: dict) -> dict:
+    """Second half: wait for the totals (the one host sync of the planner), size the arrays, fill them."""
+    lib = _lib.load()
+    rowptr, e_rel, n_nodes, chunk, scans, hist = (ctx[k] for k in ("rowptr", "e_rel", "n_nodes", "chunk", "scans", "hist"))
+    stream = _prep(rowptr)
+    dev = rowptr.device
+    ctx["ev"].synchronize()
+    n_part, n_split, max_deg, bad = ctx["host"].tolist()
+    if not ctx["has_stats"]:
+        max_deg, bad = None, 0
     n_items = n_part + n_nodes - n_split
     i32 = torch.int32
     # (split_cnt | sched) adjacent: the arrival counters of the fused merge (self-resetting) and the queue words, zeroed once
@@ -391,6 +409,7 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
     items = items.view(max(n_items, 1), 4)
     zeroed.zero_()
     split_cnt, sched = zeroed[:max(n_split, 1)], zeroed[max(n_split, 1) + 62:max(n_split, 1) + 64]
+    rp, rl = _vec(rowptr, "rowptr", torch.int32), _vec(e_rel, "e_rel", torch.uint8)
     _lib.check(lib.wsi_plan_attn_work_fill(rp, rl, n_nodes, chunk, scans[0].data_ptr(), scans[1].data_ptr(), n_part,
                                            n_split, hist.data_ptr(), items.data_ptr(), split_row.data_ptr(),
                                            split_ptr.data_ptr(), part_rel.data_ptr(), part_split.data_ptr(), stream),
@@ -398,6 +417,13 @@ def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chun
     return dict(items=items, n_items=n_items, split_row=split_row, split_ptr=split_ptr, part_rel=part_rel,
                 part_split=part_split, split_cnt=split_cnt, sched=sched,
                 n_split=n_split, n_part=n_part, max_in_degree=max_deg, bad_edges=bool(bad))
+
+
+def plan_attn_work(rowptr: torch.Tensor, e_rel: torch.Tensor, n_nodes: int, chunk: int,
+                   stats: Optional[torch.Tensor] = None) -> dict:
+    """Hub-balancing work list of hetero_attn_work; see wsi_plan_attn_work_count / _fill (one host sync for the
+    two totals that size the arrays)."""
+    return plan_attn_work_finish(plan_attn_work_begin(rowptr, e_rel, n_nodes, chunk, stats))
 
 
 AFFINE_MAX_OUT = 8

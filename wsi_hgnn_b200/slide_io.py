@@ -273,7 +273,8 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
 
     fast = hasattr(model, "forward_planned")                        # plan + forward without a HeteroGraph per slide
 
-    def plan(staged):
+    def plan_begin(staged):
+        """CSR build and the counting half of the work list: kernels only, no host wait"""
         s, k, uploaded = staged
         with torch.cuda.stream(plan_stream), torch.no_grad():
             plan_stream.wait_event(uploaded)
@@ -284,11 +285,22 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
             else:
                 G = s.graph_on(blob)
                 p = G.plan()
+            if hasattr(model, "prepare_plan_begin"):
+                model.prepare_plan_begin(p)
+        return G, k, p
+
+    def plan_finish(begun):
+        """everything of the plan that needs a host read (by now the counting kernels had a forward's worth of head start)"""
+        G, k, p = begun
+        with torch.cuda.stream(plan_stream), torch.no_grad():
             if hasattr(model, "prepare_plan"):
-                model.prepare_plan(p)                               # work list etc.: everything with a host read
+                model.prepare_plan(p)
             ev = torch.cuda.Event()
             ev.record(plan_stream)
         return G, k, ev
+
+    def plan(staged):
+        return plan_finish(plan_begin(staged))
 
     def forward(planned):
         G, k, ready = planned
@@ -374,8 +386,9 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
                 if s is not None:                                   # stage 1: slide i+2
                     up.append(upload(n_up % nbuf, s, free_ev[n_up % nbuf]))
                     n_up += 1
-                nxt = plan(up.pop(0)) if up else None               # stage 2: slide i+1
+                begun = plan_begin(up.pop(0)) if up else None       # stage 2a: slide i+1, kernels only
                 host, done, G = forward(planned)                    # stage 3: slide i
+                nxt = plan_finish(begun) if begun is not None else None    # stage 2b: the host reads of slide i+1's plan
                 free_ev[planned[1]] = done
                 pending.append((host, done, G))
                 if len(pending) >= nbuf:
