@@ -57,9 +57,17 @@ def readout_scale(plan: GraphPlan, independent: bool) -> torch.Tensor:
     for pack()ed graphs, per batch for dgl.batch semantics."""
     key = ("readout_scale", independent)
     if key not in plan.cache:
-        ne = plan.seg_nonempty
-        m = ne if independent else ne.any(dim=1, keepdim=True).expand_as(ne)
-        plan.cache[key] = m.to(torch.float32).reshape(-1).contiguous().to(plan.device)
+        if plan.device.type == "cuda":
+            # from the device copy of the segment pointers: a pageable host -> device copy here is host-synchronous
+            # and queues behind the next slide's 34 MB upload on the copy engine (it serialised the streamed path)
+            T = len(plan.ntypes)
+            ne = (plan.seg_ptr[1:] > plan.seg_ptr[:-1]).view(T, plan.B)
+            m = ne if independent else ne.any(dim=1, keepdim=True).expand(T, plan.B)
+            plan.cache[key] = m.to(torch.float32).reshape(-1).contiguous()
+        else:
+            ne = plan.seg_nonempty
+            m = ne if independent else ne.any(dim=1, keepdim=True).expand_as(ne)
+            plan.cache[key] = m.to(torch.float32).reshape(-1).contiguous().to(plan.device)
     return plan.cache[key]
 
 

@@ -16,6 +16,7 @@ flat slides with the copy of slide i+1 (copy engine, its own stream) overlapping
 logits of slide i-1 read back asynchronously: the per-epoch evaluation loop without a host sync per slide.
 """
 import json
+import os
 import queue
 import struct
 import threading
@@ -271,7 +272,8 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
             ev.record(copy_stream)
         return s, k, ev
 
-    fast = hasattr(model, "forward_planned")                        # plan + forward without a HeteroGraph per slide
+    # plan + forward without a HeteroGraph per slide (WSI_STREAM_NO_FAST: development knob for A/B timing)
+    fast = hasattr(model, "forward_planned") and not os.environ.get("WSI_STREAM_NO_FAST")
 
     def plan_begin(staged):
         """CSR build and the counting half of the work list: kernels only, no host wait"""
