@@ -138,3 +138,25 @@ def test_plan_on_equals_graph_plan():
             wa, wb = p.attn_work(), q.attn_work()
             assert wa["n_items"] == wb["n_items"] and wa["n_part"] == wb["n_part"] and wa["n_split"] == wb["n_split"]
             assert torch.equal(wa["split_ptr"], wb["split_ptr"]) and torch.equal(wa["part_rel"][:wa["n_part"]], wb["part_rel"][:wb["n_part"]])
+
+
+def test_plan_head_matches_host_plan():
+    """host half of the header-driven planner (FlatSlide._plan_head) against HeteroGraph.plan() on the CPU"""
+    for G in (synthetic.random_hetero_graph([40, 0, 25], 300, 12, seed=3), synthetic.random_hetero_graph([7, 9], 0, 4, seed=2),
+              synthetic.synth_slide_graph(300, 16, 3, 4, seed=5, noise_edges=0.3)):
+        s = FlatSlide.from_graph(G)
+        hd, q = s._plan_head(), G.plan()
+        assert (hd["ntypes"], hd["rel_list"], hd["type_ptr"], hd["N"], hd["E"]) == (q.ntypes, q.rel_list, q.type_ptr, q.N, q.E)
+        assert (hd["src_t"], hd["dst_t"], hd["r_count"]) == (q.rel_src_type, q.rel_dst_type, q.r_count)
+        assert torch.equal(hd["nonempty"], q.seg_nonempty)
+        buf = hd["buf"]
+        assert buf[:hd["n0"]].tolist() == q.seg_ptr.tolist() == q.type_ptr
+        table = buf[hd["n0"]:hd["n1"]].view(3, hd["R"] + 1)
+        eptr = [0]
+        for ce in q.rel_list:
+            eptr.append(eptr[-1] + G.num_edges(ce))
+        assert table[0].tolist() == eptr
+        assert table[1, :-1].tolist() == [q.type_ptr[t] for t in q.rel_src_type]
+        assert table[2, :-1].tolist() == [q.type_ptr[t] for t in q.rel_dst_type]
+        assert torch.equal(buf[hd["n1p"]:].view(torch.float32), q.node_inv_r)
+        assert s._plan_head() is hd                                  # computed once per slide
