@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 13
+#define WSI_ABI_VERSION 14
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -302,6 +302,38 @@ int64_t wsi_heat_forward_workspace_bytes(int64_t n_rows, int F, int D, int64_t n
  * x: embeddings are in natural order) or NULL; logits [B, ldl]. */
 int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_graph* g, const wsi_heat_params* p, float* x_out,
                      int64_t ldx, float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One slide, blob to logits, in ONE host call: the per-slide body of the streaming evaluator
+ * (evaluator/eval_homo_graph.py:61-95 drives `gnn(g.to(device))` slide by slide).  For a flat slide already resident
+ * on the device (features | src | dst | sim, wsi_hgnn_b200/slide_io.py) it enqueues
+ *     plan_stream:  wsi_plan_build_csr -> wsi_plan_attn_work_count -> [host read of the 4 totals] -> wsi_plan_attn_work_fill
+ *     stream     :  waits for the plan (event), then wsi_heat_forward
+ * EXCEPTION to the conventions at the top of this header: it synchronises `plan_stream` once (the totals size the work
+ * list) - `plan_stream` must therefore carry nothing but this slide's upload dependency and plan.
+ * workspace: wsi_slide_forward_workspace_bytes(); it is still in use by `stream` when the call returns (the caller
+ * recycles it only after the slide's forward has completed).  max_part = capacity for hub-row chunk partials
+ * (n_edges always suffices); a slide that needs more fails with WSI_ERR_ARG.
+ */
+typedef struct wsi_slide_desc {
+  const float* feat;              /* [N, ldf] packed features */
+  int64_t ldf;
+  const int64_t* src;             /* [E] local ids, relation-major */
+  const int64_t* dst;
+  const float* sim;               /* [E] or NULL */
+  const int32_t* rel_table;       /* DEVICE int32 [3, R + 1] (wsi_plan_build_csr) */
+  const int32_t* seg_ptr;         /* DEVICE int32 [T + 1] readout segments of the one graph (= type_ptr) */
+  const float* node_inv_r;        /* DEVICE [N] */
+  const int32_t* type_ptr_host;   /* HOST int32 [T + 1] */
+  int64_t n_nodes, n_edges;
+  int32_t T, R, chunk;
+} wsi_slide_desc;
+
+int64_t wsi_slide_forward_workspace_bytes(int64_t n_nodes, int64_t n_edges, int F, int D, int T, int64_t max_part);
+/* totals_host: PINNED host int32 [4] scratch (n_part, n_split, max in-degree, bad-edge flag on return) */
+int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
+                      float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -160,3 +160,27 @@ def test_plan_head_matches_host_plan():
         assert table[2, :-1].tolist() == [q.type_ptr[t] for t in q.rel_dst_type]
         assert torch.equal(buf[hd["n1p"]:].view(torch.float32), q.node_inv_r)
         assert s._plan_head() is hd                                  # computed once per slide
+
+
+@pytest.mark.gpu
+def test_stream_forward_native_slide_call(monkeypatch):
+    """WSI_STREAM_NATIVE=1: planner + forward of a slide issued by ONE C call (wsi_slide_forward) - same logits, bit for bit,
+    as the slide-at-a-time forward; slides the driver does not take (tiny / empty relation set) go through the generic path"""
+    dev = torch.device("cuda", 0)
+    T = 3
+    kw = dict(in_dim=64, hidden_dim=128, out_dim=3, n_layers=2, n_heads=4, dropuout=0.0)
+    ours = helpers.build_ours("HEATNet4", T, kw)
+    golden_util.fill_params(ours, 31)
+    ours = ours.to(dev).eval()
+    graphs = [synthetic.synth_slide_graph(600 + 173 * i, 64, T, 5, seed=60 + i, noise_edges=0.1) for i in range(6)]
+    graphs.append(synthetic.random_hetero_graph([900, 300, 200], 9000, 64, seed=4, hub=150))      # hub rows: chunk partials
+    graphs.append(synthetic.synth_slide_graph(200, 64, T, 5, seed=9))                               # below the tcgen05 row minimum
+    slides = [FlatSlide.from_graph(g, pin=True) for g in graphs]
+    with torch.no_grad():
+        ref = [ours(g.to(dev)).cpu() for g in graphs]
+    monkeypatch.setenv("WSI_STREAM_NATIVE", "1")
+    for _ in range(2):                                                # second pass reuses the per-slot workspaces
+        outs = list(stream_forward(ours, slides, dev))
+        assert len(outs) == len(ref)
+        for i, (o, r) in enumerate(zip(outs, ref)):
+            assert torch.equal(o, r), i

@@ -6,7 +6,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -28,6 +28,13 @@ class HeatParams(Structure):
                 ("w_a_split", POINTER(c_void_p)), ("b_a", POINTER(c_void_p)), ("skip", POINTER(c_void_p)),
                 ("e_w", POINTER(c_void_p)), ("e_b", POINTER(c_void_p)), ("pool_op", c_int32), ("n_out", c_int32),
                 ("M", c_void_p), ("c", c_void_p), ("b_total", c_void_p), ("seg_scale", c_void_p)]
+
+
+class SlideDesc(Structure):
+    """struct wsi_slide_desc (include/wsi_hgnn.h)."""
+    _fields_ = [("feat", c_void_p), ("ldf", c_int64), ("src", c_void_p), ("dst", c_void_p), ("sim", c_void_p),
+                ("rel_table", c_void_p), ("seg_ptr", c_void_p), ("node_inv_r", c_void_p), ("type_ptr_host", c_void_p),
+                ("n_nodes", c_int64), ("n_edges", c_int64), ("T", c_int32), ("R", c_int32), ("chunk", c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/wsi_hgnn.h declares (checked by tests)
@@ -65,6 +72,8 @@ PROTOTYPES = {
     "wsi_edge_pearson": (_I, [_P, _L, _I, _P, _P, _L, _P, _P, _P]),
     "wsi_heat_forward_workspace_bytes": (_L, [_L, _I, _I, _L, _I, _I]),
     "wsi_heat_forward": (_I, [_P, _L, POINTER(HeatGraph), POINTER(HeatParams), _P, _L, _P, _L, _P, _L, _P]),
+    "wsi_slide_forward_workspace_bytes": (_L, [_L, _L, _I, _I, _I, _L]),
+    "wsi_slide_forward": (_I, [POINTER(SlideDesc), POINTER(HeatParams), _L, _P, _P, _L, _P, _L, _P, _P]),
 }
 
 _lib = None

@@ -95,3 +95,89 @@ extern "C" int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_g
   return wsi_segment_pool_affine_fwd(x, ld, g->seg_ptr, T, B, N, D, p->pool_op, p->M, p->c, p->b_total, p->seg_scale,
                                      p->n_out, 0, logits, ldl, pool_ws, pool_bytes, stream);
 }
+
+// ------------------------------------------------------------------------------------------------ blob -> logits
+namespace {
+struct SlideLayout {
+  int64_t rowptr, e_src, e_sim, e_rel, stats, plan_ws, chunk_base, split_idx, hist, items, split_row, split_ptr, part_rel,
+      part_split, zeroed, fwd, total;
+};
+SlideLayout slide_layout(int64_t N, int64_t E, int F, int D, int T, int chunk, int64_t max_part) {
+  SlideLayout L{};
+  int64_t o = 1024;
+  auto take = [&](int64_t bytes) { int64_t r = o; o += al(bytes); return r; };
+  L.rowptr = take((N + 1) * 4); L.e_src = take(E * 4); L.e_sim = take(E * 4); L.e_rel = take(E); L.stats = take(16);
+  L.plan_ws = take(wsi_plan_workspace_bytes(N, E));
+  L.chunk_base = take((N + 1) * 4); L.split_idx = take((N + 1) * 4); L.hist = take(2 * (chunk + 1) * 4);
+  L.items = take((max_part + N + 1) * 16); L.split_row = take((N + 1) * 4); L.split_ptr = take((N + 2) * 4);
+  L.part_rel = take((max_part + 1) * 4); L.part_split = take((max_part + 1) * 4); L.zeroed = take((N + 64) * 4);
+  L.fwd = take(wsi_heat_forward_workspace_bytes(N, F, D, max_part, T, 1));
+  L.total = o;
+  return L;
+}
+}  // namespace
+
+extern "C" int64_t wsi_slide_forward_workspace_bytes(int64_t n_nodes, int64_t n_edges, int F, int D, int T, int64_t max_part) {
+  return slide_layout(n_nodes, n_edges, F, D, T, 16, max_part).total + 1024;
+}
+
+extern "C" int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
+                                 float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream,
+                                 void* stream) {
+  WSI_CHECK_ARG(s && p && totals_host && logits && workspace, "slide_forward: null pointer");
+  const int64_t N = s->n_nodes, E = s->n_edges;
+  WSI_CHECK_ARG(N > 0 && E > 0 && N < (1ll << 31) && E < (1ll << 31) && s->chunk == 16 && max_part >= 1,
+                "slide_forward: needs a non-empty slide, chunk 16 (N=%lld E=%lld chunk=%d)", (long long)N, (long long)E, s->chunk);
+  WSI_CHECK_ARG(plan_stream != stream, "slide_forward: plan_stream and stream must differ (the call synchronises plan_stream)");
+  const SlideLayout L = slide_layout(N, E, p->F, p->D, s->T, s->chunk, max_part);
+  WSI_CHECK_ARG(workspace_bytes >= L.total + 1024, "slide_forward: workspace of %lld bytes needed", (long long)(L.total + 1024));
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  auto at = [&](int64_t off) { return base + off; };
+  int32_t* rowptr = reinterpret_cast<int32_t*>(at(L.rowptr));
+  int32_t* e_src = reinterpret_cast<int32_t*>(at(L.e_src));
+  float* e_sim = reinterpret_cast<float*>(at(L.e_sim));
+  uint8_t* e_rel = at(L.e_rel);
+  int32_t* stats = reinterpret_cast<int32_t*>(at(L.stats));
+  int32_t* chunk_base = reinterpret_cast<int32_t*>(at(L.chunk_base));
+  int32_t* split_idx = reinterpret_cast<int32_t*>(at(L.split_idx));
+  int32_t* hist = reinterpret_cast<int32_t*>(at(L.hist));
+  cudaStream_t ps = wsi_stream(plan_stream), ms = wsi_stream(stream);
+
+  int rc = wsi_plan_build_csr(s->src, s->dst, s->sim, nullptr, s->rel_table, s->R, N, E, rowptr, e_src, e_sim, e_rel, nullptr,
+                              stats, at(L.plan_ws), wsi_plan_workspace_bytes(N, E), plan_stream);
+  if (rc) return rc;
+  rc = wsi_plan_attn_work_count(rowptr, e_rel, N, s->chunk, chunk_base, split_idx, hist, at(L.plan_ws),
+                                wsi_plan_workspace_bytes(N, 0), plan_stream);
+  if (rc) return rc;
+  WSI_CHECK_CUDA(cudaMemcpyAsync(totals_host, chunk_base + N, 4, cudaMemcpyDeviceToHost, ps));
+  WSI_CHECK_CUDA(cudaMemcpyAsync(totals_host + 1, split_idx + N, 4, cudaMemcpyDeviceToHost, ps));
+  WSI_CHECK_CUDA(cudaMemcpyAsync(totals_host + 2, stats, 8, cudaMemcpyDeviceToHost, ps));
+  WSI_CHECK_CUDA(cudaStreamSynchronize(ps));                          // the one host read of the planner
+  const int64_t n_part = totals_host[0], n_split = totals_host[1];
+  if (totals_host[3] != 0) { wsi_set_error("slide_forward: edge endpoint out of range"); return WSI_ERR_ARG; }
+  WSI_CHECK_ARG(n_part >= 0 && n_split >= 0 && n_split <= N && n_part <= max_part,
+                "slide_forward: %lld chunk partials exceed the workspace capacity %lld", (long long)n_part, (long long)max_part);
+  int32_t* items = reinterpret_cast<int32_t*>(at(L.items));
+  int32_t* zeroed = reinterpret_cast<int32_t*>(at(L.zeroed));
+  rc = wsi_plan_attn_work_fill(rowptr, e_rel, N, s->chunk, chunk_base, split_idx, n_part, n_split, hist, items,
+                               reinterpret_cast<int32_t*>(at(L.split_row)), reinterpret_cast<int32_t*>(at(L.split_ptr)),
+                               reinterpret_cast<int32_t*>(at(L.part_rel)), reinterpret_cast<int32_t*>(at(L.part_split)),
+                               plan_stream);
+  if (rc) return rc;
+  WSI_CHECK_CUDA(cudaMemsetAsync(zeroed, 0, (size_t)(N + 64) * 4, ps));   // arrival counters of the fused merge, queue words
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev) WSI_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  WSI_CHECK_CUDA(cudaEventRecord(ev, ps));
+  WSI_CHECK_CUDA(cudaStreamWaitEvent(ms, ev, 0));
+
+  wsi_heat_graph g{};
+  g.n_rows = N; g.T = s->T; g.B = 1; g.type_ptr_host = s->type_ptr_host; g.seg_ptr = s->seg_ptr;
+  g.e_src = e_src; g.e_sim = e_sim; g.e_rel = e_rel; g.node_inv_r = s->node_inv_r;
+  g.items = items; g.n_items = n_part + N - n_split;
+  g.split_row = reinterpret_cast<int32_t*>(at(L.split_row)); g.split_ptr = reinterpret_cast<int32_t*>(at(L.split_ptr));
+  g.part_rel = reinterpret_cast<int32_t*>(at(L.part_rel)); g.part_split = reinterpret_cast<int32_t*>(at(L.part_split));
+  g.split_cnt = zeroed; g.sched = zeroed + N + 62;
+  g.n_split = n_split; g.n_part = n_part;
+  return wsi_heat_forward(s->feat, s->ldf, &g, p, nullptr, 0, logits, ldl, at(L.fwd),
+                          wsi_heat_forward_workspace_bytes(N, p->F, p->D, max_part, s->T, 1), stream);
+}

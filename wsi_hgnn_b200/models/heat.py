@@ -274,6 +274,52 @@ class _HEATBase(nn.Module):
             return None
         return self._forward_native_core(plan, feat, independent, hasattr(self, "head"), False)
 
+    def slide_forward_native(self, slide, blob: torch.Tensor, head: torch.Tensor, slot: Dict, plan_stream, main_stream):
+        """Blob -> logits of ONE flat slide through wsi_slide_forward (planner + forward in one host call).  `head` = the
+        slide's plan head (FlatSlide._plan_head) on the device, `slot` = per-buffer scratch ({'ws', 'totals'}) recycled by
+        the caller once the slide's forward has finished.  -> logits [1, out] (on `main_stream`), or None when the shapes
+        are not the driver's (the caller then takes the generic path)."""
+        import ctypes
+        from types import SimpleNamespace
+        from .. import _lib
+        lib = _lib.load()
+        hd, hdr = slide._plan_head(), slide.header
+        N, E, T, R, F = hd["N"], hd["E"], hd["T"], hd["R"], hdr["feat_dim"]
+        n_out = self.head.out_features if hasattr(self, "head") else next(iter(self.linears_prediction.values())).out_features
+        shape = SimpleNamespace(N=N)
+        if (not self.native_forward or N == 0 or E == 0 or not self._native_ok(None, shape, None, n_out)
+                or F != self.adapt_ws[0].in_features or hdr["feat_name"] != "feat"):
+            return None
+        names = list(hd["ntypes"])
+        order = [self.node_dict[nt] for nt in names]
+        P, _keep = self._native_params(None, order, names, hasattr(self, "head"))
+        D = P.D
+        key = (N, E, F, D, T)
+        if slot.get("key") != key:
+            ws_bytes = lib.wsi_slide_forward_workspace_bytes(N, E, F, D, T, E)
+            slot["ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=blob.device)
+            slot["ws_bytes"], slot["key"] = ws_bytes, key
+            slot["totals"] = torch.zeros(4, dtype=torch.int32).pin_memory()
+            slot["tpc"] = None
+        off, base = hdr["off"], blob.data_ptr()
+        hp = head.data_ptr()
+        d = _lib.SlideDesc()
+        d.feat, d.ldf = base + off["feat"], F
+        d.src, d.dst, d.sim = base + off["src"], base + off["dst"], base + off["sim"]
+        d.seg_ptr = hp
+        d.rel_table = hp + 4 * hd["n0"]
+        d.node_inv_r = hp + 4 * hd["n1p"]
+        tpc = ops.host_i32(hd["type_ptr"])
+        d.type_ptr_host = ctypes.cast(tpc, ctypes.c_void_p)
+        d.n_nodes, d.n_edges, d.T, d.R, d.chunk = N, E, T, R, 16
+        P.seg_scale = hp + 4 * hd["n1"]
+        ops._prep(blob)
+        logits = torch.empty((1, P.n_out), dtype=torch.float32, device=blob.device)
+        rc = lib.wsi_slide_forward(ctypes.byref(d), ctypes.byref(P), E, slot["totals"].data_ptr(), logits.data_ptr(), P.n_out,
+                                   slot["ws"].data_ptr(), slot["ws_bytes"], plan_stream.cuda_stream, main_stream.cuda_stream)
+        _lib.check(rc, "wsi_slide_forward")
+        return logits
+
     def _forward_native_core(self, plan: GraphPlan, feat: torch.Tensor, independent: bool, collapse_heads: bool,
                              return_embeddings: bool):
         import ctypes

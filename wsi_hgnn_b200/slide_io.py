@@ -159,10 +159,11 @@ class FlatSlide:
             inv = np.repeat(np.array([1.0 / r if r > 0 else 0.0 for r in r_count], dtype=np.float32), n_per)
             n0 = T + 1
             n1 = n0 + len(table)
-            n1p = (n1 + 3) // 4 * 4                                  # node_inv_r starts 16 B aligned
+            n1p = (n1 + T + 3) // 4 * 4                              # node_inv_r starts 16 B aligned
             buf = torch.zeros(n1p + N, dtype=torch.int32)
             buf[:n0] = torch.tensor(type_ptr, dtype=torch.int32)
             buf[n0:n1] = torch.tensor(table, dtype=torch.int32)
+            buf[n1:n1 + T] = torch.tensor([1.0 if n > 0 else 0.0 for n in n_per], dtype=torch.float32).view(torch.int32)
             if N:
                 buf[n1p:] = torch.from_numpy(inv).view(torch.int32)
             if torch.cuda.is_available():
@@ -328,8 +329,45 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
     pending: List[Tuple[torch.Tensor, torch.cuda.Event, HeteroGraph]] = []
     stop = threading.Event()
     worker = None
+    # blob -> logits in ONE host call per slide (wsi_slide_forward: planner + forward issued from C).  Opt-in for now
+    # (WSI_STREAM_NATIVE=1): see DESIGN.md section 7.
+    native = hasattr(model, "slide_forward_native") and bool(os.environ.get("WSI_STREAM_NATIVE"))
     try:
-        if threaded:
+        if native:
+            slots = ctx.setdefault("slots", [dict() for _ in range(nbuf)])
+            free_ev: List[Optional[torch.cuda.Event]] = [None] * nbuf
+            it = iter(slides)
+            nxt_s = next(it, None)
+            staged = upload(0, nxt_s, None) if nxt_s is not None else None
+            i = 0
+            while staged is not None:
+                s, k, uploaded = staged
+                nxt_s = next(it, None)
+                staged = upload((i + 1) % nbuf, nxt_s, free_ev[(i + 1) % nbuf]) if nxt_s is not None else None
+                blob = bufs[k][:s.header["nbytes"]]
+                with torch.no_grad():
+                    out = None
+                    if s.num_nodes() > 0:
+                        with torch.cuda.stream(plan_stream):
+                            plan_stream.wait_event(uploaded)
+                            head = s._plan_head()["buf"].to(dev, non_blocking=True)
+                        out = model.slide_forward_native(s, blob, head, slots[k], plan_stream, main)
+                    keep = (s, blob, head if s.num_nodes() > 0 else None)
+                    if out is None:                                 # not the driver's shapes: generic path
+                        host, done, keep = forward(plan((s, k, uploaded)))
+                    else:
+                        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                        host.copy_(out, non_blocking=True)
+                        done = torch.cuda.Event()
+                        done.record(main)
+                free_ev[k] = done
+                pending.append((host, done, keep))
+                if len(pending) >= nbuf:
+                    h, ev, _ = pending.pop(0)
+                    ev.synchronize()
+                    yield h
+                i += 1
+        elif threaded:
             ready_q: "queue.Queue" = queue.Queue(maxsize=max(1, nbuf - 2))
             free_q = [queue.Queue() for _ in range(nbuf)]           # per buffer: `done` event of the forward that read it
 
