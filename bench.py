@@ -367,8 +367,9 @@ def main():
                     "ms_per_step": float(t_e2e) / n_e2e * 1e3, "steps": n_e2e,
                     "sync_ms_per_step": e2e_sync_ms,
                     "note": "slide_io.stream_forward over pinned FlatSlide blobs: per slide ONE H2D copy (features + edges + "
-                            "sim), CSR + work-list build, forward, logits D2H; the copy of slide i+1 overlaps the forward of "
-                            "slide i.  sync_ms_per_step = the same slides one at a time with a host sync per slide"},
+                            "sim), CSR + work-list build and forward issued by one C call (wsi_slide_forward), logits D2H; the "
+                            "copy of slide i+1 overlaps the forward of slide i.  sync_ms_per_step = the same slides one at a "
+                            "time through model(G) with a host sync per slide"},
             "gpu_launches": gf.kernels_per_replay * args.steps,
             "roofline": {"kernel": "edge attention of one layer (wsi_hetero_attn_work_fwd: TMA bulk-copy gather of K|V by "
                                    "source, per-relation softmax, merge of hub-row chunks, write to dst)", "bound": "hbm",

@@ -62,7 +62,9 @@ def test_flat_rejects_batched_and_short_blob():
 
 
 @pytest.mark.gpu
-def test_stream_forward_matches_per_slide_forward():
+@pytest.mark.parametrize("native", ["1", "0"])
+def test_stream_forward_matches_per_slide_forward(native, monkeypatch):
+    monkeypatch.setenv("WSI_STREAM_NATIVE", native)
     dev = torch.device("cuda", 0)
     T = 3
     kw = dict(in_dim=64, hidden_dim=128, out_dim=3, n_layers=2, n_heads=4, dropuout=0.0)

@@ -239,9 +239,11 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
 
     Three stages run concurrently on three streams, each ahead of the next:
         copy stream   ONE host -> device copy of the slide's blob (copy engine)
-        plan stream   CSR + work-list build on the device blob (the two small host reads of the planner wait only for
-                      this stream, i.e. for a copy that was queued a whole slide earlier)
+        plan stream   CSR + work-list build on the device blob (the one host read of the planner waits only for this
+                      stream, i.e. for a copy that was queued a whole slide earlier)
         main stream   forward (wsi_heat_forward), logits -> pinned host memory (asynchronous)
+    For HEATNet2 / HEATNet4 on shapes the tensor-core chain takes, the last two stages of a slide are issued by ONE C call
+    (wsi_slide_forward); other models / shapes go through the Python-issued planner and forward (same kernels).
     The caller's thread interleaves the stages one slide apart; with `threaded` the first two stages are issued by a
     worker thread instead (planning is the larger part of the host cost per slide, but most of it holds the GIL: on
     config-2 slides it measured no faster - 0.97 vs 0.93 ms / slide - so it is not the default).  The host never waits for the main stream except on a
@@ -329,9 +331,10 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
     pending: List[Tuple[torch.Tensor, torch.cuda.Event, HeteroGraph]] = []
     stop = threading.Event()
     worker = None
-    # blob -> logits in ONE host call per slide (wsi_slide_forward: planner + forward issued from C).  Opt-in for now
-    # (WSI_STREAM_NATIVE=1): see DESIGN.md section 7.
-    native = hasattr(model, "slide_forward_native") and bool(os.environ.get("WSI_STREAM_NATIVE"))
+    # blob -> logits in ONE host call per slide (wsi_slide_forward: planner + forward issued from C; measured 0.89-0.95
+    # against 1.13-1.15 ms / slide for the Python-issued stages on the same box).  WSI_STREAM_NATIVE=0 (development knob)
+    # or `threaded` select the Python-issued stages.
+    native = (hasattr(model, "slide_forward_native") and os.environ.get("WSI_STREAM_NATIVE", "1") != "0" and not threaded)
     try:
         if native:
             slots = ctx.setdefault("slots", [dict() for _ in range(nbuf)])
