@@ -80,3 +80,29 @@ def test_unknown_pooling_raises():
     from wsi_hgnn_b200.models import HEATNet4
     with pytest.raises(NotImplementedError):
         HEATNet4(8, 16, 2, 1, 4, {"0": 0}, 0.1, graph_pooling_type="att")
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """the ctypes mirrors of the header's structs (wsi_heat_graph / wsi_heat_params / wsi_slide_desc) have the C layout:
+    a C program compiled against include/wsi_hgnn.h prints sizeof / offsetof, compared with ctypes"""
+    import shutil
+    import subprocess
+    from wsi_hgnn_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"wsi_heat_graph": _lib.HeatGraph, "wsi_heat_params": _lib.HeatParams, "wsi_slide_desc": _lib.SlideDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = os.path.join(tmp_path, "layout.c")
+    open(src, "w").write("\n".join(lines))
+    exe = os.path.join(tmp_path, "layout")
+    subprocess.run(["gcc", "-std=c11", "-o", exe, src], check=True)
+    got = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
