@@ -81,6 +81,14 @@ CASES = [
                         synthetic.random_hetero_graph([10, 0, 12], 25, 16, seed=32),
                         synthetic.random_hetero_graph([6, 7, 5], 12, 16, seed=33)],
          kw=dict(in_dim=16, hidden_dim=32, out_dim=2, n_layers=2, n_heads=4, dropuout=0.2, graph_pooling_type="mean")),
+    # BASELINE.json configs[0], literally: 2 node types, 1k nodes, k=5 -> 5k edges, F = D = 64, H = 4, 1 layer
+    dict(name="heat4_config1_T2", model="HEATNet4",
+         graph=lambda: synthetic.synth_slide_graph(1000, 64, 2, 5, seed=0),
+         kw=dict(in_dim=64, hidden_dim=64, out_dim=2, n_layers=1, n_heads=4, dropuout=0.2, graph_pooling_type="mean")),
+    dict(name="heat2_pack2_T3_max", model="HEATNet2", independent=True,
+         graph=lambda: [synthetic.random_hetero_graph([15, 0, 9], 70, 16, seed=41),
+                        synthetic.random_hetero_graph([7, 12, 5], 40, 16, seed=42)],
+         kw=dict(in_dim=16, hidden_dim=32, out_dim=3, n_layers=2, n_heads=4, dropuout=0.2, graph_pooling_type="max")),
     dict(name="hgt_pack2_T2", model="HGT", independent=True,
          graph=lambda: [synthetic.random_hetero_graph([12, 9], 50, 16, seed=34),
                         synthetic.random_hetero_graph([8, 11], 9, 16, seed=35)],
