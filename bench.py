@@ -211,9 +211,25 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL printf()s its version banner to stdout when NCCL_DEBUG is VERSION / WARN; stdout must carry ONE JSON line:
+        # send NCCL's log to stderr and keep fd 1 pointed at stderr while the communicator is created
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        import ctypes
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            try:
+                ctypes.CDLL(None).fflush(None)
+            except Exception:
+                pass
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.load()
     hbm_peak, tc_peak, peak_src = peaks()
 
