@@ -11,6 +11,15 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C-ABI library is a build artefact (git-ignored): build it once if this checkout has none yet
+    # (nvcc cross-compiles without a GPU; ~45 s).  A failing build surfaces in test_abi.py, not here.
+    from wsi_hgnn_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        try:
+            from wsi_hgnn_b200 import build
+            build.build(verbose=False)
+        except Exception as e:                       # noqa: BLE001
+            sys.stderr.write(f"[conftest] building libwsi_hgnn.so failed: {e}\n")
 
 
 def pytest_collection_modifyitems(config, items):
