@@ -328,8 +328,8 @@ def main():
         order = [ours.node_dict[nt] for nt in plan.ntypes]
         w_kvq, b_kvq, wa, ba, skip, use_perm = layer._packed(order)
         w_kvq_s, wa_s = layer._packed_split(order)
-        xs = ops.split_bf16(x)
-        kvq, _ = ops.typed_linear_split(xs, w_kvq_s, b_kvq, plan.type_ptr, 3 * D)
+        xs = ops.to_operand(x)
+        kvq, _ = ops.typed_linear_op(xs, w_kvq_s, b_kvq, plan.type_ptr, 3 * D)
         work = plan.attn_work()
         attn_args = (kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, plan.e_src, plan.e_sim, plan.e_rel,
                      plan.node_inv_r, layer.e_linear.weight, layer.e_linear.bias, D, CFG["heads"])
@@ -357,7 +357,7 @@ def main():
         torch.cuda.synchronize()
         attn_ms = sorted(a.elapsed_time(b) for a, b in kev)[reps // 2]
         # dense: fused K|V|Q typed GEMM on pre-split operands (as inside the forward)
-        g_gemm = graphed(lambda: ops.typed_linear_split(xs, w_kvq_s, b_kvq, plan.type_ptr, 3 * D))
+        g_gemm = graphed(lambda: ops.typed_linear_op(xs, w_kvq_s, b_kvq, plan.type_ptr, 3 * D))
         gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for a, b in gev:
             flush.zero_()

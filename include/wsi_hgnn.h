@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 14
+#define WSI_ABI_VERSION 15
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -38,6 +38,18 @@ extern "C" {
 #define WSI_POOL_MEAN 1
 #define WSI_POOL_MAX 2
 
+/* Operand formats of the tensor-core typed linear (kernel K1) and of the buffers that feed it.
+ *   WSI_OPF_BF16X3  bf16 [2 * rows, K]: rows [0, rows) = hi = bf16(x), rows [rows, 2 rows) = lo = bf16(x - hi); the
+ *                   product is hi*hi + hi*lo + lo*hi (3 MMAs, ~2^-17 relative): "exact" mode, used for gradients
+ *   WSI_OPF_F16     fp16 [rows, K], round to nearest, clamped to +-65504: ONE MMA per k-slice; 11-bit significand
+ *                   (TF32's).  Default of the fp32 models: the whole forward stays 3.6x inside the 1e-3 parity bar on
+ *                   the 16 reference-generated goldens and config 2 (profiles/r2_precision_study.json)
+ *   WSI_OPF_BF16    bf16 [rows, K]: one MMA; the bf16-storage configuration (BASELINE config 3)
+ */
+#define WSI_OPF_BF16X3 0
+#define WSI_OPF_F16 1
+#define WSI_OPF_BF16 2
+
 /* attention scoring modes */
 #define WSI_SCORE_HEAT 0 /* score = <q,k> * (w*sim+b) / sqrt(d_k)        models/HEATNet4.py:103,111 */
 #define WSI_SCORE_HGT 1  /* score = <q',k> * relation_pri[r,h] / sqrt(d_k) models/HGT.py:100         */
@@ -50,6 +62,9 @@ int wsi_num_sms(void);
 int wsi_set_device(int device);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
 int64_t wsi_launch_count(void);
+/* DEVELOPMENT hook, not product API: sets one of the process-wide kernel debug / variant knobs the library otherwise
+ * reads once from the environment at load time (tools/sweep_dev.py); unknown key -> WSI_ERR_ARG. */
+int wsi_dev_set(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * Typed linear:  Y[rows of type t] = epilogue( X[rows of type t] . W[t]^T )        (kernel K1)
@@ -63,29 +78,29 @@ int64_t wsi_launch_count(void);
  *   v *= row_scale[row]
  * y [N, ldy] fp32.  `impl`: 0 = auto (tcgen05 tensor-core path when the shape is tile aligned,
  * else the fp32 SIMT path), 1 = force SIMT, 2 = force tcgen05 (error if the shape does not fit).
- * The tcgen05 path computes a 3-term bf16 split product (hi*hi + hi*lo + lo*hi, fp32 accumulate in
- * TMEM; ~2^-16 relative) and needs `workspace` of wsi_typed_linear_workspace_bytes() bytes.
+ * The tcgen05 path converts x and w to the operand format `opf` (WSI_OPF_*) in a pre-pass, accumulates in fp32 in
+ * TMEM, and needs `workspace` of wsi_typed_linear_workspace_bytes() bytes.
  */
-int64_t wsi_typed_linear_workspace_bytes(int64_t n_rows, int K, int n_out, int T, int impl);
+int64_t wsi_typed_linear_workspace_bytes(int64_t n_rows, int K, int n_out, int T, int impl, int opf);
 int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w, const float* bias, int K, int n_out,
                          const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
                          int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,
-                         const float* row_scale, float* y, int64_t ldy, int impl, void* workspace,
+                         const float* row_scale, float* y, int64_t ldy, int impl, int opf, void* workspace,
                          int64_t workspace_bytes, void* stream);
 
-/* Pre-split operands for chains of tensor-core GEMMs (no per-call conversion pass):
- * wsi_split_bf16: fp32 [rows, K] (row stride ld_src) -> dst bf16 [2 * rows, K]: rows [0, rows) = hi = bf16(x),
- *   rows [rows, 2 rows) = lo = bf16(x - hi).  K % 8 == 0.  Weights [T, n_out, K] are split as rows = T * n_out.
- * wsi_typed_linear_split: the typed linear of wsi_typed_linear_f32 on the tcgen05 path with x and w given in that
- *   split form (x_split [2N, K], w_split [2 T n_out, K], both 128 B aligned); y_split != NULL additionally emits
- *   the epilogue result in split form [2N, n_out] (n_out % 8 == 0) for the next GEMM; y may be NULL then.
+/* Operands kept in operand form for chains of tensor-core GEMMs (no per-call conversion pass):
+ * wsi_to_operand: fp32 [rows, K] (row stride ld_src) -> dst in format `opf` (16-bit [2 * rows, K] for WSI_OPF_BF16X3,
+ *   [rows, K] otherwise).  K % 8 == 0.  Weights [T, n_out, K] are converted as rows = T * n_out.
+ * wsi_typed_linear_op: the typed linear of wsi_typed_linear_f32 on the tcgen05 path with x and w given in operand
+ *   form (both 128 B aligned); y_op != NULL additionally emits the epilogue result in operand form ([2N, n_out] or
+ *   [N, n_out], n_out % 8 == 0) for the next GEMM; y may be NULL then.
  *   Returns WSI_ERR_UNSUPPORTED when wsi_typed_linear_tc_ok(N, K, n_out) == 0. */
 int wsi_typed_linear_tc_ok(int64_t n_rows, int K, int n_out);
-int wsi_split_bf16(const float* src, int64_t ld_src, int64_t rows, int K, void* dst, void* stream);
-int wsi_typed_linear_split(const void* x_split, const void* w_split, const float* bias, int K, int n_out,
-                           const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
-                           int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,
-                           const float* row_scale, float* y, int64_t ldy, void* y_split, void* stream);
+int wsi_to_operand(const float* src, int64_t ld_src, int64_t rows, int K, int opf, void* dst, void* stream);
+int wsi_typed_linear_op(const void* x_op, const void* w_op, const float* bias, int K, int n_out,
+                        const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
+                        int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,
+                        const float* row_scale, float* y, int64_t ldy, void* y_op, int opf, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Heterogeneous edge attention forward, ONE launch for all relations of a layer        (kernel K2)
@@ -118,15 +133,15 @@ int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   sched int32 [2] (optional, ZERO before the first launch, left zero): device-side work queue - warps pull items in
  *   list order (largest first = LPT) instead of a static round-robin.
  * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work().
- *   agg_split != NULL: the result is (also) written as bf16 [2 * n_rows, D] (hi rows, then lo rows: x = hi + lo),
- *   the A operand layout of wsi_typed_linear_split; agg may then be NULL. */
+ *   agg_op != NULL: the result is (also) written in operand format `opf` (WSI_OPF_*: 16-bit [2 * n_rows, D] hi rows then
+ *   lo rows, or [n_rows, D]), the A operand of wsi_typed_linear_op; agg may then be NULL. */
 int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
                              const int32_t* e_src, const float* e_sim, const uint8_t* e_rel, const float* node_inv_r,
                              const float* e_w, const float* e_b, int64_t n_rows, int D, int H, const int32_t* items,
                              int64_t n_items, const int32_t* split_row, const int32_t* split_ptr,
                              const int32_t* part_rel, const int32_t* part_split, int32_t* split_cnt, int32_t* sched,
                              int64_t n_split, int64_t n_part, float* part_ms,
-                             float* part_acc, float* agg, int64_t ldo, void* agg_split, void* stream);
+                             float* part_acc, float* agg, int64_t ldo, void* agg_op, int opf, void* stream);
 
 /* Backward of wsi_hetero_attn_fwd (kernel K3; HEAT scoring, lane-grouped column order): what DGL's GSDDMM / EdgeSoftmax /
  * GSpMM backward compute under loss.backward() (trainer/train_gnn.py:68-71 through models/HEATNet4.py:103-119).
@@ -256,8 +271,8 @@ int wsi_edge_pearson(const float* feat, int64_t n, int F, const int64_t* src, co
  * (the same launches the Python modules issue one by one; here the host cost per slide is a few microseconds per
  * kernel, which is what bounds the streamed end-to-end path).  Preconditions = those of the tcgen05 chain:
  * wsi_typed_linear_tc_ok(n_rows, F, D), (n_rows, D, 3D), (n_rows, D, D); wsi_head_perm(D, H) exists; n_out <= 8.
- * All weights are in the forms the kernels consume: bf16 [hi; lo] stacks in the GRAPH's node-type order
- * (wsi_split_bf16), K|V|Q fused along the output dimension, K/V/Q rows and a_linear columns in head_perm order.
+ * All weights are in the forms the kernels consume: operand-format stacks (`opf`, wsi_to_operand) in the GRAPH's
+ * node-type order, K|V|Q fused along the output dimension, K/V/Q rows and a_linear columns in head_perm order.
  */
 typedef struct wsi_heat_graph {
   int64_t n_rows;                 /* N packed nodes */
@@ -281,11 +296,12 @@ typedef struct wsi_heat_graph {
 
 typedef struct wsi_heat_params {
   int32_t F, D, H, L;             /* input / hidden width, heads, layers */
-  const void* w_in_split;         /* bf16 [2*T*D, F] */
+  int32_t opf;                    /* WSI_OPF_*: format of the w_*_op stacks and of the chain's internal operands */
+  const void* w_in_split;         /* operand form of [T*D, F] */
   const float* b_in;              /* [T, D] */
-  const void* const* w_kvq_split; /* HOST array [L] of bf16 [2*T*3D, D] */
+  const void* const* w_kvq_split; /* HOST array [L] of the operand form of [T*3D, D] */
   const float* const* b_kvq;      /* HOST array [L] of [T, 3D] */
-  const void* const* w_a_split;   /* HOST array [L] of bf16 [2*T*D, D] */
+  const void* const* w_a_split;   /* HOST array [L] of the operand form of [T*D, D] */
   const float* const* b_a;        /* HOST array [L] of [T, D] */
   const float* const* skip;       /* HOST array [L] of [T] */
   const float* const* e_w;        /* HOST array [L] of device scalars (e_linear.weight) */
@@ -298,10 +314,12 @@ typedef struct wsi_heat_params {
 } wsi_heat_params;
 
 int64_t wsi_heat_forward_workspace_bytes(int64_t n_rows, int F, int D, int64_t n_part, int T, int B);
-/* feat fp32 [N, ldf] type-major packed; x_out [N, ldx] final node embeddings (head_perm column order is NOT applied to
- * x: embeddings are in natural order) or NULL; logits [B, ldl]. */
-int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_graph* g, const wsi_heat_params* p, float* x_out,
-                     int64_t ldx, float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* stream);
+/* feat [N, ldf] type-major packed: fp32 when feat_is_op == 0; already in operand form p->opf (dense, ldf == F, 128 B
+ * aligned - a flat slide that stores its features in fp16) when feat_is_op != 0.  x_out [N, ldx] final node embeddings
+ * (head_perm column order is NOT applied to x: embeddings are in natural order) or NULL; logits [B, ldl]. */
+int wsi_heat_forward(const void* feat, int64_t ldf, int feat_is_op, const wsi_heat_graph* g, const wsi_heat_params* p,
+                     float* x_out, int64_t ldx, float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One slide, blob to logits, in ONE host call: the per-slide body of the streaming evaluator
@@ -316,8 +334,9 @@ int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_graph* g, co
  * (n_edges always suffices); a slide that needs more fails with WSI_ERR_ARG.
  */
 typedef struct wsi_slide_desc {
-  const float* feat;              /* [N, ldf] packed features */
+  const void* feat;               /* [N, ldf] packed features: fp32, or (feat_is_op != 0) operand form p->opf, ldf == F */
   int64_t ldf;
+  int32_t feat_is_op;
   const int64_t* src;             /* [E] local ids, relation-major */
   const int64_t* dst;
   const float* sim;               /* [E] or NULL */

@@ -17,16 +17,31 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+# relative L2 tolerance of ONE tensor-core GEMM per operand format (fp64 reference): the 3-term bf16 split is fp32-grade;
+# one fp16 / bf16 pass carries the operand rounding 2^-11 / 2^-8 (x sqrt(2)/sqrt(3) in the L2 norm of a random product)
+PREC_TOL = {"bf16x3": 2e-5, "fp16": 6e-4, "bf16": 5e-3}
+
 TC_SHAPES = [([600, 0, 700], 512, 1536), ([128, 256, 300], 200, 200), ([1000], 1024, 512), ([513], 64, 64),
              ([130, 1, 127, 500, 0, 3], 256, 520), ([2731, 2731, 2730], 512, 512)]
 
 
+@pytest.fixture
+def precision(request):
+    prev = ops.set_matmul_precision(request.param)
+    yield request.param
+    ops.set_matmul_precision(prev)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16", "bf16"], indirect=True)
 @pytest.mark.parametrize("counts,K,n_out,impl",
                          [(c, k, n, i) for c, k, n in [([70, 0, 133], 48, 96), ([1, 2, 3], 7, 5), ([300], 200, 200),
                                                        ([128, 256], 512, 1536), ([0, 0, 5], 16, 256)]
                           for i in (ops.IMPL_SIMT, ops.IMPL_AUTO)] +
                          [(c, k, n, ops.IMPL_TC) for c, k, n in TC_SHAPES])
-def test_typed_linear_epilogues(counts, K, n_out, impl):
+def test_typed_linear_epilogues(counts, K, n_out, impl, precision):
+    if impl == ops.IMPL_SIMT and precision != "bf16x3":
+        pytest.skip("the SIMT path is fp32 whatever the operand format")
+    TOL = 2e-5 if impl == ops.IMPL_SIMT else PREC_TOL[precision]
     g = torch.Generator().manual_seed(sum(counts) + K)
     T = len(counts)
     ptr = [0]
@@ -62,22 +77,25 @@ def test_typed_linear_epilogues(counts, K, n_out, impl):
 
     c = lambda t: t.cuda()
     y = ops.typed_linear(c(x), c(w), c(b), ptr, impl=impl)
-    assert rel(y, ref()) < 2e-5
+    assert rel(y, ref()) < TOL
     y = ops.typed_linear(c(x), c(w), c(b), ptr, act=ops.ACT_GELU, impl=impl)
-    assert rel(y, ref(act=True)) < 2e-5
+    assert rel(y, ref(act=True)) < TOL
     y = ops.typed_linear(c(x), c(w), c(b), ptr, skip=c(skip), res=c(res), drop_mask=c(mask), row_gate=c(gate),
                          row_scale=c(scale), impl=impl)
-    assert rel(y, ref(use_skip=True, use_mask=True, use_gate=True, use_scale=True)) < 2e-5
+    assert rel(y, ref(use_skip=True, use_mask=True, use_gate=True, use_scale=True)) < TOL
     # strided input / output views (the K|V|Q fused buffer is sliced by column)
     big = torch.zeros(N, n_out + 8, device="cuda")
     ops.typed_linear(c(x), c(w), None, ptr, out=big[:, 8:], impl=impl)
-    assert rel(big[:, 8:], ref() - torch.cat([b[t].double().expand(counts[t], n_out) for t in range(T)])) < 2e-5
+    assert rel(big[:, 8:], ref() - torch.cat([b[t].double().expand(counts[t], n_out) for t in range(T)])) < TOL
     assert float(big[:, :8].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16", "bf16"], indirect=True)
 @pytest.mark.parametrize("counts,K,n_out", [([600, 0, 700], 512, 512), ([513], 64, 136), ([300, 300, 424], 1024, 256)])
-def test_typed_linear_split_chain(counts, K, n_out):
-    """Pre-split bf16 [hi; lo] operands in, fp32 + split result out (the operand of the next GEMM)."""
+def test_typed_linear_op_chain(counts, K, n_out, precision):
+    """Operands already in operand form in, fp32 + operand-form result out (the operand of the next GEMM)."""
+    TOL = PREC_TOL[precision]
+    split = precision == "bf16x3"
     g = torch.Generator().manual_seed(K + n_out)
     T = len(counts)
     ptr = [0]
@@ -90,25 +108,28 @@ def test_typed_linear_split_chain(counts, K, n_out):
     skip = torch.randn(T, generator=g)
     res = torch.randn(N, n_out, generator=g)
     gate = (torch.rand(N, generator=g) > 0.25).float()
-    xs = ops.split_bf16(x.cuda())
-    assert xs.shape == (2 * N, K) and xs.dtype == torch.bfloat16
-    back = xs[:N].float() + xs[N:].float()
-    assert float((back.cpu() - x).abs().max() / x.abs().max()) < 2 ** -15
-    ws = ops.split_bf16(w.cuda())
+    xs = ops.to_operand(x.cuda())
+    assert xs.shape == ((2 * N if split else N), K) and xs.dtype == (torch.float16 if precision == "fp16" else torch.bfloat16)
+    back = (xs[:N].float() + xs[N:].float()) if split else xs.float()
+    assert float((back.cpu() - x).abs().max() / x.abs().max()) < {"bf16x3": 2 ** -15, "fp16": 2 ** -10, "bf16": 2 ** -7}[precision]
+    if precision == "fp16":                                  # values beyond the fp16 range are clamped, never inf
+        big = ops.to_operand(torch.tensor([[1e6, -1e6, 3.0, 1e-9] * 2], device="cuda"))
+        assert torch.isfinite(big.float()).all() and float(big[0, 0]) == 65504.0 and float(big[0, 1]) == -65504.0
+    ws = ops.to_operand(w.cuda())
     ref = torch.empty(N, n_out, dtype=torch.float64)
     for t in range(T):
         a, z = ptr[t], ptr[t + 1]
         v = x[a:z].double() @ w[t].double().T + b[t].double()
         al = torch.sigmoid(skip[t].double())
         ref[a:z] = torch.where(gate[a:z, None] != 0, v * al + res[a:z].double() * (1 - al), res[a:z].double())
-    y, ys = ops.typed_linear_split(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(), row_gate=gate.cuda(),
-                                   want_split=True)
-    assert rel(y, ref) < 2e-5
-    assert rel(ys[:N].float() + ys[N:].float(), ref) < 2e-5
-    y2, none = ops.typed_linear_split(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(), row_gate=gate.cuda())
+    y, ys = ops.typed_linear_op(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(), row_gate=gate.cuda(),
+                                   want_op=True)
+    assert rel(y, ref) < TOL
+    assert rel((ys[:N].float() + ys[N:].float()) if split else ys.float(), ref) < max(TOL, {"bf16x3": 0, "fp16": 8e-4, "bf16": 6e-3}[precision])
+    y2, none = ops.typed_linear_op(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(), row_gate=gate.cuda())
     assert none is None and torch.equal(y2, y)
-    only, ys2 = ops.typed_linear_split(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(),
-                                       row_gate=gate.cuda(), want_y=False, want_split=True)
+    only, ys2 = ops.typed_linear_op(xs, ws, b.cuda(), ptr, n_out, skip=skip.cuda(), res=res.cuda(),
+                                       row_gate=gate.cuda(), want_y=False, want_op=True)
     assert only is None and torch.equal(ys2, ys)
 
 
@@ -225,13 +246,15 @@ def test_hetero_attn_work_list(D, H, chunk):
     un[:, p] = agg
     assert rel_ok(un, ref, 2e-5)
     assert float(un[inv_r == 0].abs().sum()) == 0.0
-    # split-form output: bf16 [hi; lo] of the same result
-    sp = ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, src.to(torch.int32).cuda(),
-                              sim.float().cuda(), plan.e_rel, inv_r.cuda(), torch.tensor([[ew]]).cuda(),
-                              torch.tensor([eb]).cuda(), D, H, split_out=True)
-    assert sp.dtype == torch.bfloat16 and sp.shape == (2 * n_dst, D)
-    back = (sp[:n_dst].float() + sp[n_dst:].float()).cpu()
-    assert float((back - agg).abs().max()) <= 2 ** -15 * float(agg.abs().max())
+    # operand-form outputs of the same result: bf16 [hi; lo], fp16, bf16
+    for opf, dt, rows, eps in ((ops.OPF_BF16X3, torch.bfloat16, 2 * n_dst, 2 ** -15), (ops.OPF_F16, torch.float16, n_dst, 2 ** -10),
+                               (ops.OPF_BF16, torch.bfloat16, n_dst, 2 ** -7)):
+        sp = ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, src.to(torch.int32).cuda(),
+                                  sim.float().cuda(), plan.e_rel, inv_r.cuda(), torch.tensor([[ew]]).cuda(),
+                                  torch.tensor([eb]).cuda(), D, H, op_out=True, opf=opf)
+        assert sp.dtype == dt and sp.shape == (rows, D)
+        back = ((sp[:n_dst].float() + sp[n_dst:].float()) if opf == ops.OPF_BF16X3 else sp.float()).cpu()
+        assert float((back - agg).abs().max()) <= eps * float(agg.abs().max())
 
 
 def rel_ok(a, b, tol):

@@ -54,21 +54,49 @@ def main():
         if epi.get("skip"):
             kw = dict(skip=torch.ones(T, device=dev), res=torch.randn(N, n_out, device=dev),
                       row_gate=torch.ones(N, device=dev))
-        ref = None
-        for impl, tag in ((ops.IMPL_TC, "tcgen05"), (ops.IMPL_SIMT, "simt")):
-            ms = timeit(lambda: ops.typed_linear(x, w, b, ptr, impl=impl, out=out, **kw), args.reps, flush)
-            tf = 2.0 * N * K * n_out / (ms * 1e-3) / 1e12
-            y = out.clone()
-            err = None
-            if ref is None:
-                ref = y
-            else:
-                err = float((ref.double() - y.double()).norm() / y.double().norm())
-            print(json.dumps({"kernel": f"typed_linear[{name}] {tag}", "N": N, "K": K, "n_out": n_out, "ms": ms,
-                              "tflops": tf, "frac_bf16_peak": tf / peaks["bf16_tflops"], "rel_diff_vs_tc": err}), flush=True)
-        ms = timeit(lambda: torch.matmul(x, w[0].T), args.reps, flush)
-        print(json.dumps({"kernel": f"torch.matmul fp32 (cuBLAS, allow_tf32={torch.backends.cuda.matmul.allow_tf32}) [{name}]",
-                          "ms": ms, "tflops": 2.0 * N * K * n_out / (ms * 1e-3) / 1e12}), flush=True)
+        ref64 = torch.cat([x[ptr[t]:ptr[t + 1]].double() @ w[t].double().T + b[t].double() for t in range(T)]) if not kw else None
+        flops = 2.0 * N * K * n_out
+        for prec in ("fp16", "bf16x3", "bf16"):
+            with ops.matmul_precision(prec):
+                xs, ws = ops.to_operand(x), ops.to_operand(w)
+                # the GEMM alone on operands already in operand form (what the forward chain launches) ...
+                ms = timeit(lambda: ops.typed_linear_op(xs, ws, b, ptr, n_out, **kw), args.reps, flush)
+                y, _ = ops.typed_linear_op(xs, ws, b, ptr, n_out, **kw)
+                err = float((ref64 - y.double()).norm() / ref64.norm()) if ref64 is not None else None
+                issued = {"fp16": 1, "bf16": 1, "bf16x3": 3}[prec]
+                tf = flops / (ms * 1e-3) / 1e12
+                print(json.dumps({"kernel": f"typed_linear_op[{name}] tcgen05 {prec}", "N": N, "K": K, "n_out": n_out, "ms": ms,
+                                  "tflops": tf, "frac_bf16_peak": tf / peaks["bf16_tflops"],
+                                  "frac_issued": issued * tf / peaks["bf16_tflops"], "rel_err_vs_fp64": err}), flush=True)
+                # ... and through the fp32 API (conversion pre-pass of x and w inside the timed region)
+                ms = timeit(lambda: ops.typed_linear(x, w, b, ptr, impl=ops.IMPL_TC, out=out, **kw), args.reps, flush)
+                print(json.dumps({"kernel": f"typed_linear[{name}] tcgen05 {prec} incl. fp32 -> operand pre-pass", "ms": ms,
+                                  "tflops": flops / (ms * 1e-3) / 1e12}), flush=True)
+        ms = timeit(lambda: ops.typed_linear(x, w, b, ptr, impl=ops.IMPL_SIMT, out=out, **kw), args.reps, flush)
+        print(json.dumps({"kernel": f"typed_linear[{name}] simt fp32", "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12}), flush=True)
+        # library bars on the same box (one dense [N, K] x [K, n_out] product, no epilogue, no type grouping)
+        wt = w[0].T.contiguous()
+        for tag, setup in (("cuBLAS fp32 (allow_tf32=False)", lambda: setattr(torch.backends.cuda.matmul, "allow_tf32", False)),
+                           ("cuBLASLt TF32 (allow_tf32=True)", lambda: setattr(torch.backends.cuda.matmul, "allow_tf32", True))):
+            setup()
+            ms = timeit(lambda: torch.matmul(x, wt), args.reps, flush)
+            err = float(((x.double() @ wt.double()) - torch.matmul(x, wt).double()).norm() / (x.double() @ wt.double()).norm())
+            print(json.dumps({"kernel": f"torch.matmul {tag} [{name}]", "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+                              "rel_err_vs_fp64": err}), flush=True)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        # 3xTF32-class: torch's "high" float32 matmul precision (cuBLASLt picks its own split scheme when it has one)
+        try:
+            torch.set_float32_matmul_precision("high")
+            ms = timeit(lambda: torch.matmul(x, wt), args.reps, flush)
+            print(json.dumps({"kernel": f"torch.matmul float32_matmul_precision=high [{name}]", "ms": ms,
+                              "tflops": flops / (ms * 1e-3) / 1e12}), flush=True)
+        finally:
+            torch.set_float32_matmul_precision("highest")
+        for dt, tag in ((torch.float16, "fp16"), (torch.bfloat16, "bf16")):
+            xa, wa = x.to(dt), wt.to(dt)
+            ms = timeit(lambda: torch.matmul(xa, wa), args.reps, flush)
+            print(json.dumps({"kernel": f"torch.matmul cuBLASLt {tag} in / {tag} out [{name}]", "ms": ms,
+                              "tflops": flops / (ms * 1e-3) / 1e12}), flush=True)
 
     gemm_case("K|V|Q", 512, 1536)
     gemm_case("a_linear+skip", 512, 512, skip=True)

@@ -6,7 +6,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -23,7 +23,7 @@ class HeatGraph(Structure):
 
 class HeatParams(Structure):
     """struct wsi_heat_params (include/wsi_hgnn.h)."""
-    _fields_ = [("F", c_int32), ("D", c_int32), ("H", c_int32), ("L", c_int32), ("w_in_split", c_void_p),
+    _fields_ = [("F", c_int32), ("D", c_int32), ("H", c_int32), ("L", c_int32), ("opf", c_int32), ("w_in_split", c_void_p),
                 ("b_in", c_void_p), ("w_kvq_split", POINTER(c_void_p)), ("b_kvq", POINTER(c_void_p)),
                 ("w_a_split", POINTER(c_void_p)), ("b_a", POINTER(c_void_p)), ("skip", POINTER(c_void_p)),
                 ("e_w", POINTER(c_void_p)), ("e_b", POINTER(c_void_p)), ("pool_op", c_int32), ("n_out", c_int32),
@@ -32,7 +32,7 @@ class HeatParams(Structure):
 
 class SlideDesc(Structure):
     """struct wsi_slide_desc (include/wsi_hgnn.h)."""
-    _fields_ = [("feat", c_void_p), ("ldf", c_int64), ("src", c_void_p), ("dst", c_void_p), ("sim", c_void_p),
+    _fields_ = [("feat", c_void_p), ("ldf", c_int64), ("feat_is_op", c_int32), ("src", c_void_p), ("dst", c_void_p), ("sim", c_void_p),
                 ("rel_table", c_void_p), ("seg_ptr", c_void_p), ("node_inv_r", c_void_p), ("type_ptr_host", c_void_p),
                 ("n_nodes", c_int64), ("n_edges", c_int64), ("T", c_int32), ("R", c_int32), ("chunk", c_int32)]
 
@@ -44,14 +44,15 @@ PROTOTYPES = {
     "wsi_num_sms": (_I, []),
     "wsi_set_device": (_I, [_I]),
     "wsi_launch_count": (_L, []),
-    "wsi_typed_linear_workspace_bytes": (_L, [_L, _I, _I, _I, _I]),
-    "wsi_typed_linear_f32": (_I, [_P, _L, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _I, _P, _L, _P]),
+    "wsi_dev_set": (_I, [c_char_p, _I]),
+    "wsi_typed_linear_workspace_bytes": (_L, [_L, _I, _I, _I, _I, _I]),
+    "wsi_typed_linear_f32": (_I, [_P, _L, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _P, _L, _P]),
     "wsi_hetero_attn_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P, _P]),
     "wsi_hetero_attn_work_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _P, _P, _P, _P,
-                                      _P, _L, _L, _P, _P, _P, _L, _P, _P]),
+                                      _P, _L, _L, _P, _P, _P, _L, _P, _I, _P]),
     "wsi_typed_linear_tc_ok": (_I, [_L, _I, _I]),
-    "wsi_split_bf16": (_I, [_P, _L, _L, _I, _P, _P]),
-    "wsi_typed_linear_split": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _P]),
+    "wsi_to_operand": (_I, [_P, _L, _L, _I, _I, _P, _P]),
+    "wsi_typed_linear_op": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _I, _P]),
     "wsi_hetero_attn_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _L,
                                  _P, _P, _P]),
     "wsi_hetero_attn_seg_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P]),
@@ -71,7 +72,7 @@ PROTOTYPES = {
     "wsi_knn_topk": (_I, [_P, _L, _I, _I, _L, _L, _P, _P, _P, _L, _P]),
     "wsi_edge_pearson": (_I, [_P, _L, _I, _P, _P, _L, _P, _P, _P]),
     "wsi_heat_forward_workspace_bytes": (_L, [_L, _I, _I, _L, _I, _I]),
-    "wsi_heat_forward": (_I, [_P, _L, POINTER(HeatGraph), POINTER(HeatParams), _P, _L, _P, _L, _P, _L, _P]),
+    "wsi_heat_forward": (_I, [_P, _L, _I, POINTER(HeatGraph), POINTER(HeatParams), _P, _L, _P, _L, _P, _L, _P]),
     "wsi_slide_forward_workspace_bytes": (_L, [_L, _L, _I, _I, _I, _L]),
     "wsi_slide_forward": (_I, [POINTER(SlideDesc), POINTER(HeatParams), _L, _P, _P, _L, _P, _L, _P, _P]),
 }

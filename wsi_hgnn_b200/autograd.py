@@ -21,7 +21,7 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor, tp: Sequence[int]) -> torch.Tensor
     N = int(tp[-1])
     if _MM_OUT_DTYPE[0] is not False and N > 0 and x.shape[1] % 8 == 0 and dy.shape[1] % 8 == 0:
         try:
-            xs, ds = ops.split_bf16(x), ops.split_bf16(dy)
+            xs, ds = ops.to_operand(x, ops.OPF_BF16X3), ops.to_operand(dy, ops.OPF_BF16X3)
             out = []
             for t in range(T):
                 a, z = tp[t], tp[t + 1]
@@ -57,7 +57,8 @@ class TypedLinearFn(torch.autograd.Function):
         tp = ctx.type_ptr
         dx = dw = db = None
         if ctx.needs_input_grad[0]:                      # dgrad: the same typed GEMM with W^T
-            dx = ops.typed_linear(dy, w.transpose(1, 2).contiguous(), None, tp, type_ptr_c=ctx.type_ptr_c)
+            # gradients keep the 3-term split (fp32 range and ~2^-17 accuracy): a single fp16 pass would need loss scaling
+            dx = ops.typed_linear(dy, w.transpose(1, 2).contiguous(), None, tp, type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
         if ctx.needs_input_grad[1]:                      # wgrad: plain dense GEMM per node type (cuBLAS)
             dw = _wgrad(dy, x, tp)
         if ctx.has_bias and ctx.needs_input_grad[2]:

@@ -94,7 +94,22 @@ static inline cudaStream_t wsi_stream(void* s) { return reinterpret_cast<cudaStr
 __device__ __forceinline__ void wsi_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void wsi_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-bool wsi_pdl_enabled();      // error.cu: false when the environment has WSI_NO_PDL (development knob)
+// Development knobs (error.cu): process-wide, read ONCE from the environment when the library is loaded (WSI_TC_DEBUG,
+// WSI_ATTN_DEBUG, WSI_ATTN_KERNEL=ring|pipe, WSI_ATTN_RING, WSI_ATTN_BLOCKS, WSI_ATTN_CAP, WSI_ATTN_SEPARATE_MERGE,
+// WSI_ATTN_STATIC, WSI_NO_PDL) and settable through wsi_dev_set(); no launch path calls getenv().  Not product API.
+struct WsiDev {
+  int tc_debug;            // typed_linear_tc_kernel: see TcArgs::dbg
+  int attn_debug;          // attention kernels: see AttnArgs::dbg
+  int attn_kernel;         // 0 = chosen per launch (default), 1 = register path, 2 = TMA ring, 3 = TMA pipe
+  int attn_ring;           // ring depth of the TMA kernels (0 = default)
+  int attn_blocks;         // blocks-per-SM cap of the TMA kernels (0 = none)
+  int attn_cap;            // blocks-per-SM cap of the grid (0 = none)
+  int attn_separate_merge; // merge the hub rows in a second launch
+  int attn_static;         // static round-robin instead of the device work queue
+  int no_pdl;              // launch without programmatic stream serialization
+};
+WsiDev* wsi_dev();
+static inline bool wsi_pdl_enabled() { return wsi_dev()->no_pdl == 0; }
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t wsi_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

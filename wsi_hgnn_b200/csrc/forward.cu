@@ -30,9 +30,9 @@ extern "C" int64_t wsi_heat_forward_workspace_bytes(int64_t n_rows, int F, int D
   return b;
 }
 
-extern "C" int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_graph* g, const wsi_heat_params* p,
-                                float* x_out, int64_t ldx, float* logits, int64_t ldl, void* workspace,
-                                int64_t workspace_bytes, void* stream) {
+extern "C" int wsi_heat_forward(const void* feat, int64_t ldf, int feat_is_op, const wsi_heat_graph* g,
+                                const wsi_heat_params* p, float* x_out, int64_t ldx, float* logits, int64_t ldl,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
   WSI_CHECK_ARG(g && p && feat && logits, "heat_forward: null pointer");
   const int64_t N = g->n_rows;
   const int T = g->T, B = g->B, F = p->F, D = p->D, H = p->H, L = p->L;
@@ -43,6 +43,11 @@ extern "C" int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_g
   WSI_CHECK_ARG(p->n_out >= 1 && p->n_out <= 8 && p->M, "heat_forward: n_out=%d must be in [1, 8]", p->n_out);
   WSI_CHECK_ARG(!x_out || ldx >= D, "heat_forward: x_out row stride smaller than D");
   WSI_CHECK_ARG(ldf >= F && ldl >= p->n_out, "heat_forward: feat / logits row stride smaller than the row");
+  const int opf = p->opf;
+  WSI_CHECK_ARG(opf == WSI_OPF_BF16X3 || opf == WSI_OPF_F16 || opf == WSI_OPF_BF16, "heat_forward: unknown operand format %d", opf);
+  WSI_CHECK_ARG(!feat_is_op || (ldf == F && (reinterpret_cast<uintptr_t>(feat) & 127) == 0),
+                "heat_forward: operand-form features must be dense (ldf == F) and 128 B aligned");
+  const int64_t m = opf == WSI_OPF_BF16X3 ? 2 : 1;       // 16-bit matrices per operand
   WSI_CHECK_ARG(p->w_in_split && g->seg_ptr && g->node_inv_r && g->e_src && g->e_sim && g->e_rel && g->items &&
                     (L == 0 || (p->w_kvq_split && p->b_kvq && p->w_a_split && p->b_a && p->skip && p->e_w && p->e_b)),
                 "heat_forward: null pointer in the graph / parameter structs");
@@ -53,9 +58,10 @@ extern "C" int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_g
   WSI_CHECK_ARG(workspace && workspace_bytes >= need, "heat_forward: workspace of %lld bytes needed", (long long)need);
 
   Carve cv{reinterpret_cast<uintptr_t>(workspace), reinterpret_cast<uintptr_t>(workspace) + (uintptr_t)workspace_bytes};
-  void* feat_s = cv.take(2 * N * F * 2);
-  void* xs = cv.take(2 * N * D * 2);
-  void* aggs = cv.take(2 * N * D * 2);
+  const void* feat_s = feat;
+  if (!feat_is_op) feat_s = cv.take(m * N * F * 2);
+  void* xs = cv.take(m * N * D * 2);
+  void* aggs = cv.take(m * N * D * 2);
   float* kvq = static_cast<float*>(cv.take(N * 3 * D * 4));
   float* xa = static_cast<float*>(cv.take(N * D * 4));
   float* xb = static_cast<float*>(cv.take(N * D * 4));
@@ -65,28 +71,29 @@ extern "C" int wsi_heat_forward(const float* feat, int64_t ldf, const wsi_heat_g
   void* pool_ws = cv.take(pool_bytes);
   const int32_t* tp = g->type_ptr_host;
 
-  int rc = wsi_split_bf16(feat, ldf, N, F, feat_s, stream);
+  int rc = WSI_OK;
+  if (!feat_is_op) rc = wsi_to_operand(static_cast<const float*>(feat), ldf, N, F, opf, const_cast<void*>(feat_s), stream);
   if (rc) return rc;
   // x = adapt_ws[type](feat)                                                   models/HEATNet4.py:198-206
   float* x = (L == 0 && x_out) ? x_out : xa;
   int64_t ld = (L == 0 && x_out) ? ldx : D;
-  rc = wsi_typed_linear_split(feat_s, p->w_in_split, p->b_in, F, D, tp, T, WSI_ACT_NONE, nullptr, nullptr, 0, nullptr, 0,
-                              nullptr, nullptr, x, ld, L > 0 ? xs : nullptr, stream);
+  rc = wsi_typed_linear_op(feat_s, p->w_in_split, p->b_in, F, D, tp, T, WSI_ACT_NONE, nullptr, nullptr, 0, nullptr, 0,
+                           nullptr, nullptr, x, ld, L > 0 ? xs : nullptr, opf, stream);
   if (rc) return rc;
   for (int l = 0; l < L; ++l) {                                                // models/HEATNet4.py:213-214
-    rc = wsi_typed_linear_split(xs, p->w_kvq_split[l], p->b_kvq[l], D, 3 * D, tp, T, WSI_ACT_NONE, nullptr, nullptr, 0,
-                                nullptr, 0, nullptr, nullptr, kvq, 3 * D, nullptr, stream);     // :91-102, once per type
+    rc = wsi_typed_linear_op(xs, p->w_kvq_split[l], p->b_kvq[l], D, 3 * D, tp, T, WSI_ACT_NONE, nullptr, nullptr, 0,
+                             nullptr, 0, nullptr, nullptr, kvq, 3 * D, nullptr, opf, stream);   // :91-102, once per type
     if (rc) return rc;
     rc = wsi_hetero_attn_work_fwd(kvq, 3 * D, kvq + D, 3 * D, kvq + 2 * D, 3 * D, g->e_src, g->e_sim, g->e_rel,
                                   g->node_inv_r, p->e_w[l], p->e_b[l], N, D, H, g->items, g->n_items, g->split_row,
                                   g->split_ptr, g->part_rel, g->part_split, g->split_cnt, g->sched, g->n_split, g->n_part,
-                                  part_ms, part_acc, nullptr, D, aggs, stream);                    // :103-119
+                                  part_ms, part_acc, nullptr, D, aggs, opf, stream);               // :103-119
     if (rc) return rc;
     const bool last = l + 1 == L;
     float* y = (last && x_out) ? x_out : (x == xa ? xb : xa);
     const int64_t ldy = (last && x_out) ? ldx : D;
-    rc = wsi_typed_linear_split(aggs, p->w_a_split[l], p->b_a[l], D, D, tp, T, WSI_ACT_NONE, p->skip[l], x, ld, nullptr, 0,
-                                g->node_inv_r, nullptr, y, ldy, last ? nullptr : xs, stream);      // :121-136
+    rc = wsi_typed_linear_op(aggs, p->w_a_split[l], p->b_a[l], D, D, tp, T, WSI_ACT_NONE, p->skip[l], x, ld, nullptr, 0,
+                             g->node_inv_r, nullptr, y, ldy, last ? nullptr : xs, opf, stream);    // :121-136
     if (rc) return rc;
     x = y;
     ld = ldy;
@@ -178,6 +185,6 @@ extern "C" int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params*
   g.part_rel = reinterpret_cast<int32_t*>(at(L.part_rel)); g.part_split = reinterpret_cast<int32_t*>(at(L.part_split));
   g.split_cnt = zeroed; g.sched = zeroed + N + 62;
   g.n_split = n_split; g.n_part = n_part;
-  return wsi_heat_forward(s->feat, s->ldf, &g, p, nullptr, 0, logits, ldl, at(L.fwd),
+  return wsi_heat_forward(s->feat, s->ldf, s->feat_is_op, &g, p, nullptr, 0, logits, ldl, at(L.fwd),
                           wsi_heat_forward_workspace_bytes(N, p->F, p->D, max_part, s->T, 1), stream);
 }

@@ -19,6 +19,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -48,8 +52,8 @@ struct AttnArgs {
   const int4* items;          // optional work list [n_items]: (row, e_beg, e_end, slot); slot < 0: the whole row
   float* part_ms;             // [P, 2, 32] per-lane (max, sum) of partial slot p
   float* part_acc;            // [P, D] unnormalised accumulator of partial slot p (physical column order)
-  __nv_bfloat16* out_split;   // optional [2 * n_rows, D] bf16 (hi; lo) form of `out`: A operand of the a_linear GEMM
-  int64_t split_lo;           // element offset of the lo half (n_rows * D)
+  __nv_bfloat16* out_split;   // optional operand-form copy of `out` (16-bit elements): A operand of the a_linear GEMM
+  int64_t split_lo;           // > 0: WSI_OPF_BF16X3, element offset of the lo half (n_rows * D); 0: WSI_OPF_F16; < 0: WSI_OPF_BF16
   // fused merge of the split rows (TMA kernel): split index of every partial, per-split-row arrival counter
   const int* part_split; int* split_cnt;
   int dbg;                    // development only (env WSI_ATTN_DEBUG): 1 = gather only 64 distinct rows, 2 = no bulk copies, 3 = no math
@@ -58,6 +62,22 @@ struct AttnArgs {
 };
 
 __device__ __forceinline__ void st_split4(__nv_bfloat16* dst, int64_t lo_off, float4 v) {
+  if (lo_off == 0) {                                     // single fp16 operand, clamped to the finite range
+    const float lim = 65504.f;
+    __half2 a = __floats2half2_rn(fminf(fmaxf(v.x, -lim), lim), fminf(fmaxf(v.y, -lim), lim));
+    __half2 b = __floats2half2_rn(fminf(fmaxf(v.z, -lim), lim), fminf(fmaxf(v.w, -lim), lim));
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst) = r;
+    return;
+  }
+  if (lo_off < 0) {                                      // single bf16 operand
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst) = r;
+    return;
+  }
   __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
   wsi_split_bf16(v.x, h0, l0); wsi_split_bf16(v.y, h1, l1); wsi_split_bf16(v.z, h2, l2); wsi_split_bf16(v.w, h3, l3);
   __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
@@ -1038,35 +1058,37 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
   int blocks = (a.n_items + WARPS - 1) / WARPS;
   // one work item per warp: the hardware block scheduler deals the (largest-first) items out as blocks retire, which
   // balances better than a persistent grid-stride loop; WSI_ATTN_CAP (development knob) = blocks per SM of a persistent grid
-  if (const char* c = getenv("WSI_ATTN_CAP")) { const int cap = sms * atoi(c); if (cap > 0 && blocks > cap) blocks = cap; }
+  const WsiDev& dev = *wsi_dev();
+  if (dev.attn_cap > 0 && blocks > sms * dev.attn_cap) blocks = sms * dev.attn_cap;
   if (head_perm) {
     if (!vec_ok(a.D, a.H)) {
       wsi_set_error("hetero_attn: head_perm layout needs D %% 128 == 0, D <= 1024, H a power of two <= 32 (D=%d H=%d)", a.D, a.H);
       return WSI_ERR_UNSUPPORTED;
     }
-    const char* kern = getenv("WSI_ATTN_KERNEL");       // development knob: "ring" / "pipe" = the TMA bulk-copy kernels
-    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && kern && (kern[0] == 'r' || kern[0] == 'p')) {
+    // development knob attn_kernel: 2 / 3 = the TMA bulk-copy kernels (ring / item-pipelined)
+    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && dev.attn_kernel >= 2) {
       const int slot_bytes = 2 * a.D * 4;
-      const bool pipe = kern[0] == 'p';
+      const bool pipe = dev.attn_kernel == 3;
       // ring kernel: ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM;
       // item-pipelined kernel: ~24 KB per warp (the ring spans item boundaries), 2 blocks of 4 warps per SM, no spills
       int ring = (pipe ? 24576 : 12288) / slot_bytes;
       ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
-      if (const char* r = getenv("WSI_ATTN_RING")) ring = atoi(r);          // development knob
+      if (dev.attn_ring > 0) ring = dev.attn_ring;                          // development knob
       if (ring < 1) ring = 1;
       const int smem = TMA_WARPS * ring * slot_bytes + TMA_WARPS * ring * 8;
       int tb = (a.n_items + TMA_WARPS - 1) / TMA_WARPS;
       const int per_sm = 200 * 1024 / (smem + 1024) < 1 ? 1 : 200 * 1024 / (smem + 1024);
       if (tb > sms * per_sm) tb = sms * per_sm;
-      if (const char* b = getenv("WSI_ATTN_BLOCKS")) { const int cap = sms * atoi(b); if (cap > 0 && tb > cap) tb = cap; }   // development knob
+      if (dev.attn_blocks > 0 && tb > sms * dev.attn_blocks) tb = sms * dev.attn_blocks;   // development knob
       switch (a.D / 128) {
 #define CASE(NV) case NV: { \
-        static bool attr_set = false; \
-        if (!attr_set) { \
-          WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-          WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-          WSI_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-          attr_set = true; } \
+        static std::once_flag once; \
+        static cudaError_t aerr = cudaSuccess; \
+        std::call_once(once, [] { \
+          aerr = cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+          if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+          if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }); \
+        WSI_CHECK_CUDA(aerr); \
         if (pipe && per_sm >= 3) attn_fwd_pipe_kernel<NV, MODE, 3><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); \
         else if (pipe) attn_fwd_pipe_kernel<NV, MODE, 2><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); \
         else attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
@@ -1080,25 +1102,15 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
     // register-path kernel (default): one work item per warp, the block scheduler is the work queue; rows are gathered
     // with 16-byte loads straight into registers, GROUP edges in flight; split rows merged through arrival counters
     a.sched = nullptr;
-    if (getenv("WSI_ATTN_SEPARATE_MERGE")) a.split_cnt = nullptr;      // development knob: merge as its own launch
+    if (dev.attn_separate_merge) a.split_cnt = nullptr;                // development knob: merge as its own launch
     // GROUP edges in flight per warp x MINB resident blocks per SM: measured on config 2 (D = 512) the kernel is bound
     // by latency per warp, not by bytes in flight, so more (lighter) warps win: GROUP 2 at 4 blocks / SM (128
-    // registers) beats GROUP 4 at 3.  WSI_ATTN_VARIANT (development knob, D = 512 only): "g4b3" | "g1b5" | "g1b6" | "g2b5"
-    const char* var = getenv("WSI_ATTN_VARIANT");
-    if (var && a.D == 512) {
-      const dim3 g_(blocks), b_(WARPS * 32);
-      if (!strcmp(var, "g4b3")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 4, 3>, g_, b_, 0, stream, a));
-      else if (!strcmp(var, "g1b5")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 1, 5>, g_, b_, 0, stream, a));
-      else if (!strcmp(var, "g1b6")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 1, 6>, g_, b_, 0, stream, a));
-      else if (!strcmp(var, "g2b5")) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 2, 5>, g_, b_, 0, stream, a));
-      else WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<4, MODE, 2, 4>, g_, b_, 0, stream, a));
-    } else {
-      switch (a.D / 128) {
+    // registers) beats GROUP 4 at 3, GROUP 1 at 5-6 and GROUP 2 at 5 (round-1 sweep; those variants no longer ship).
+    switch (a.D / 128) {
 #define CASE(NV, GRP, MINB) case NV: \
-        WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<NV, MODE, GRP, MINB>, dim3(blocks), dim3(WARPS * 32), 0, stream, a)); break;
-        CASE(1, 4, 4) CASE(2, 4, 4) CASE(3, 2, 4) CASE(4, 2, 4) CASE(5, 2, 2) CASE(6, 2, 2) CASE(7, 2, 2) CASE(8, 2, 2)
+      WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<NV, MODE, GRP, MINB>, dim3(blocks), dim3(WARPS * 32), 0, stream, a)); break;
+      CASE(1, 4, 4) CASE(2, 4, 4) CASE(3, 2, 4) CASE(4, 2, 4) CASE(5, 2, 2) CASE(6, 2, 2) CASE(7, 2, 2) CASE(8, 2, 2)
 #undef CASE
-      }
     }
     WSI_CHECK_LAUNCH();
     if (fused_merge) *fused_merge = a.split_cnt != nullptr;
@@ -1176,7 +1188,7 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
                                         const int32_t* split_row, const int32_t* split_ptr, const int32_t* part_rel,
                                         const int32_t* part_split, int32_t* split_cnt, int32_t* sched, int64_t n_split,
                                         int64_t n_part, float* part_ms, float* part_acc, float* agg, int64_t ldo,
-                                        void* agg_split, void* stream) {
+                                        void* agg_split, int opf, void* stream) {
   WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && n_items >= 0 && n_items < (1ll << 31), "hetero_attn_work_fwd: bad sizes");
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(k && v && q && node_inv_r && e_w && e_b && (agg || agg_split) && items, "hetero_attn_work_fwd: null pointer");
@@ -1195,13 +1207,15 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.out = agg; a.ldo = ldo; a.attn = nullptr;
   a.items = reinterpret_cast<const int4*>(items); a.part_ms = part_ms; a.part_acc = part_acc;
-  a.out_split = reinterpret_cast<__nv_bfloat16*>(agg_split); a.split_lo = n_rows * D;
+  WSI_CHECK_ARG(opf == WSI_OPF_BF16X3 || opf == WSI_OPF_F16 || opf == WSI_OPF_BF16, "hetero_attn_work_fwd: unknown operand format %d", opf);
+  a.out_split = reinterpret_cast<__nv_bfloat16*>(agg_split);
+  a.split_lo = opf == WSI_OPF_BF16X3 ? n_rows * D : (opf == WSI_OPF_F16 ? 0 : -1);
   if (n_split > 0 && split_cnt) {
     a.part_split = part_split; a.split_cnt = split_cnt;
     a.split_row = split_row; a.split_ptr = split_ptr; a.part_rel = part_rel;
   }
-  a.sched = getenv("WSI_ATTN_STATIC") ? nullptr : sched;                    // development knob: static round-robin
-  { const char* d = getenv("WSI_ATTN_DEBUG"); a.dbg = d ? atoi(d) : 0; }
+  a.sched = wsi_dev()->attn_static ? nullptr : sched;                       // development knob: static round-robin
+  a.dbg = wsi_dev()->attn_debug;
   bool fused = false;
   int rc = launch<MODE_HEAT>(a, 1, wsi_stream(stream), &fused);
   if (rc != WSI_OK || fused) return rc;

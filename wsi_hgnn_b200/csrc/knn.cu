@@ -138,7 +138,7 @@ extern "C" int64_t wsi_knn_workspace_bytes(int64_t n, int F, int topn, int64_t q
   if (n <= 0 || q_end <= q_begin) return 0;
   const int64_t qc = query_chunk(n, q_end - q_begin);
   const int64_t n4 = (n + 3) & ~(int64_t)3;       // row pitch of the dot-product matrix (16 B rows for the tcgen05 epilogue)
-  return align256(n * 4) + align256(qc * n4 * 4) + align256(wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0));
+  return align256(n * 4) + align256(qc * n4 * 4) + align256(wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0, WSI_OPF_BF16X3));
 }
 
 extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64_t q_begin, int64_t q_end,
@@ -159,17 +159,20 @@ extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64
   const int64_t n4 = (n + 3) & ~(int64_t)3;
   float* dot = (float*)(ws + align256(n * 4));
   void* lin_ws = ws + align256(n * 4) + align256(qc * n4 * 4);
-  const int64_t lin_ws_bytes = wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0);
-  int blocks = (int)((n + 7) / 8 < 148 * 16 ? (n + 7) / 8 : 148 * 16);
+  const int64_t lin_ws_bytes = wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0, WSI_OPF_BF16X3);
+  const int sms = wsi_num_sms();
+  if (sms <= 0) return WSI_ERR_CUDA;
+  const int64_t grid_cap = (int64_t)sms * 16;
+  int blocks = (int)((n + 7) / 8 < grid_cap ? (n + 7) / 8 : grid_cap);
   row_sqnorm_kernel<<<blocks, 256, 0, st>>>(feat, n, F, sqn);
   WSI_CHECK_LAUNCH();
   for (int64_t q0 = q_begin; q0 < q_end; q0 += qc) {
     const int n_q = (int)((q_end - q0) < qc ? (q_end - q0) : qc);
     int32_t tp[2] = {0, n_q};
     int rc = wsi_typed_linear_f32(feat + q0 * F, F, feat, nullptr, F, (int)n, tp, 1, WSI_ACT_NONE, nullptr, nullptr, 0,
-                                  nullptr, 0, nullptr, nullptr, dot, n4, 0, lin_ws, lin_ws_bytes, stream);
+                                  nullptr, 0, nullptr, nullptr, dot, n4, 0, WSI_OPF_BF16X3, lin_ws, lin_ws_bytes, stream);
     if (rc != WSI_OK) return rc;
-    int sb = (n_q + 7) / 8 < 148 * 16 ? (n_q + 7) / 8 : 148 * 16;
+    int sb = (int)((n_q + 7) / 8 < grid_cap ? (n_q + 7) / 8 : grid_cap);
     knn_select_kernel<<<sb, 256, 0, st>>>(feat, sqn, dot, n4, n, F, topn, q0, n_q, nbr + (q0 - q_begin) * topn,
                                           nbr_dist ? nbr_dist + (q0 - q_begin) * topn : nullptr);
     WSI_CHECK_LAUNCH();
@@ -182,8 +185,10 @@ extern "C" int wsi_edge_pearson(const float* feat, int64_t n, int F, const int64
   WSI_CHECK_ARG(n_edges >= 0 && F >= 1 && n >= 0, "edge_pearson: bad sizes");
   if (n_edges == 0) return WSI_OK;
   WSI_CHECK_ARG(feat && src && dst && sim, "edge_pearson: null pointer");
+  const int sms = wsi_num_sms();
+  if (sms <= 0) return WSI_ERR_CUDA;
   int64_t want = (n_edges + 7) / 8;
-  int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  int blocks = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
   edge_pearson_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(feat, F, src, dst, n_edges, sim, etype);
   WSI_CHECK_LAUNCH();
   return WSI_OK;

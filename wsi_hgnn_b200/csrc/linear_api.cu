@@ -6,41 +6,42 @@ int wsi_typed_linear_simt_launch(const float* x, int64_t ldx, const float* w, in
                                  int T, const LinearEpilogue& ep, cudaStream_t stream);
 // linear_tc.cu
 bool wsi_typed_linear_tc_supported(int64_t n_rows, int K, int n_out, int64_t ldx);
-int64_t wsi_typed_linear_tc_workspace(int64_t n_rows, int K, int n_out, int T);
+bool wsi_opf_valid(int opf);
+int64_t wsi_typed_linear_tc_workspace(int64_t n_rows, int K, int n_out, int T, int opf);
 int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int K, const int32_t* type_ptr_host,
-                               int T, const LinearEpilogue& ep, void* workspace, int64_t workspace_bytes,
+                               int T, const LinearEpilogue& ep, int opf, void* workspace, int64_t workspace_bytes,
                                cudaStream_t stream);
 
 int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const int32_t* type_ptr_host, int T,
-                             const LinearEpilogue& ep, void* y_split, cudaStream_t stream);
+                             const LinearEpilogue& ep, void* y_op, int opf, cudaStream_t stream);
 int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_dst, const float* b_src, int64_t b_ld,
-                     int64_t b_rows, void* b_dst, int K, cudaStream_t stream);
+                     int64_t b_rows, void* b_dst, int K, int opf, cudaStream_t stream);
 
 extern "C" int wsi_typed_linear_tc_ok(int64_t n_rows, int K, int n_out) {
   return (wsi_typed_linear_tc_supported(n_rows, K, n_out, K) && n_out % 4 == 0) ? 1 : 0;
 }
 
-extern "C" int wsi_split_bf16(const float* src, int64_t ld_src, int64_t rows, int K, void* dst, void* stream) {
-  WSI_CHECK_ARG(rows >= 0 && K >= 8, "split_bf16: bad shape");
+extern "C" int wsi_to_operand(const float* src, int64_t ld_src, int64_t rows, int K, int opf, void* dst, void* stream) {
+  WSI_CHECK_ARG(rows >= 0 && K >= 8, "to_operand: bad shape");
   if (rows == 0) return WSI_OK;
-  WSI_CHECK_ARG(src && dst && ld_src >= K, "split_bf16: null pointer / short row stride");
-  return wsi_split_launch(src, ld_src, rows, dst, nullptr, 4, 0, nullptr, K, wsi_stream(stream));
+  WSI_CHECK_ARG(src && dst && ld_src >= K, "to_operand: null pointer / short row stride");
+  return wsi_split_launch(src, ld_src, rows, dst, nullptr, 4, 0, nullptr, K, opf, wsi_stream(stream));
 }
 
-extern "C" int wsi_typed_linear_split(const void* x_split, const void* w_split, const float* bias, int K, int n_out,
-                                      const int32_t* type_ptr_host, int T, int act, const float* skip,
-                                      const float* res, int64_t ldres, const float* drop_mask, int64_t ldmask,
-                                      const float* row_gate, const float* row_scale, float* y, int64_t ldy,
-                                      void* y_split, void* stream) {
-  WSI_CHECK_ARG(type_ptr_host && T >= 1 && T <= WSI_MAX_TYPES, "typed_linear_split: bad type_ptr / T=%d", T);
-  WSI_CHECK_ARG(act == WSI_ACT_NONE || act == WSI_ACT_GELU, "typed_linear_split: unknown activation %d", act);
-  WSI_CHECK_ARG(!skip || res, "typed_linear_split: skip mix needs a residual");
+extern "C" int wsi_typed_linear_op(const void* x_split, const void* w_split, const float* bias, int K, int n_out,
+                                   const int32_t* type_ptr_host, int T, int act, const float* skip,
+                                   const float* res, int64_t ldres, const float* drop_mask, int64_t ldmask,
+                                   const float* row_gate, const float* row_scale, float* y, int64_t ldy,
+                                   void* y_split, int opf, void* stream) {
+  WSI_CHECK_ARG(type_ptr_host && T >= 1 && T <= WSI_MAX_TYPES, "typed_linear_op: bad type_ptr / T=%d", T);
+  WSI_CHECK_ARG(act == WSI_ACT_NONE || act == WSI_ACT_GELU, "typed_linear_op: unknown activation %d", act);
+  WSI_CHECK_ARG(!skip || res, "typed_linear_op: skip mix needs a residual");
   const int64_t n_rows = type_ptr_host[T];
   if (n_rows == 0) return WSI_OK;
-  WSI_CHECK_ARG(x_split && w_split && (y || y_split), "typed_linear_split: null pointer");
-  WSI_CHECK_ARG(!y || ldy >= n_out, "typed_linear_split: row stride smaller than the row");
+  WSI_CHECK_ARG(x_split && w_split && (y || y_split), "typed_linear_op: null pointer");
+  WSI_CHECK_ARG(!y || ldy >= n_out, "typed_linear_op: row stride smaller than the row");
   if (!wsi_typed_linear_tc_supported(n_rows, K, n_out, K) || n_out % 4 != 0) {
-    wsi_set_error("typed_linear_split: shape (rows=%lld K=%d n_out=%d) does not fit the tcgen05 path",
+    wsi_set_error("typed_linear_op: shape (rows=%lld K=%d n_out=%d) does not fit the tcgen05 path",
                   (long long)n_rows, K, n_out);
     return WSI_ERR_UNSUPPORTED;
   }
@@ -48,25 +49,26 @@ extern "C" int wsi_typed_linear_split(const void* x_split, const void* w_split, 
   ep.bias = bias; ep.act = act; ep.skip = skip; ep.res = res; ep.ldres = ldres;
   ep.drop_mask = drop_mask; ep.ldmask = ldmask; ep.row_gate = row_gate; ep.row_scale = row_scale;
   ep.y = y; ep.ldy = ldy; ep.n_out = n_out;
-  return wsi_typed_linear_tc_gemm(x_split, w_split, K, type_ptr_host, T, ep, y_split, wsi_stream(stream));
+  return wsi_typed_linear_tc_gemm(x_split, w_split, K, type_ptr_host, T, ep, y_split, opf, wsi_stream(stream));
 }
 
-extern "C" int64_t wsi_typed_linear_workspace_bytes(int64_t n_rows, int K, int n_out, int T, int impl) {
-  if (impl == 1) return 0;
+extern "C" int64_t wsi_typed_linear_workspace_bytes(int64_t n_rows, int K, int n_out, int T, int impl, int opf) {
+  if (impl == 1 || !wsi_opf_valid(opf)) return 0;
   if (!wsi_typed_linear_tc_supported(n_rows, K, n_out, K)) return 0;
-  return wsi_typed_linear_tc_workspace(n_rows, K, n_out, T);
+  return wsi_typed_linear_tc_workspace(n_rows, K, n_out, T, opf);
 }
 
 extern "C" int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w, const float* bias, int K, int n_out,
                                     const int32_t* type_ptr_host, int T, int act, const float* skip,
                                     const float* res, int64_t ldres, const float* drop_mask, int64_t ldmask,
                                     const float* row_gate, const float* row_scale, float* y, int64_t ldy, int impl,
-                                    void* workspace, int64_t workspace_bytes, void* stream) {
+                                    int opf, void* workspace, int64_t workspace_bytes, void* stream) {
   WSI_CHECK_ARG(type_ptr_host && T >= 1 && T <= WSI_MAX_TYPES, "typed_linear: bad type_ptr / T=%d", T);
   WSI_CHECK_ARG(K >= 1 && n_out >= 1, "typed_linear: bad K=%d n_out=%d", K, n_out);
   WSI_CHECK_ARG(act == WSI_ACT_NONE || act == WSI_ACT_GELU, "typed_linear: unknown activation %d", act);
   WSI_CHECK_ARG(!skip || res, "typed_linear: skip mix needs a residual");
   WSI_CHECK_ARG(impl >= 0 && impl <= 2, "typed_linear: unknown impl %d", impl);
+  WSI_CHECK_ARG(wsi_opf_valid(opf), "typed_linear: unknown operand format %d", opf);
   const int64_t n_rows = type_ptr_host[T];
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(x && w && y, "typed_linear: null pointer");
@@ -89,7 +91,7 @@ extern "C" int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w,
     return WSI_ERR_UNSUPPORTED;
   }
   if (impl == 2 || (impl == 0 && tc_ok))
-    return wsi_typed_linear_tc_launch(x, ldx, w, K, type_ptr_host, T, ep, workspace, workspace_bytes,
+    return wsi_typed_linear_tc_launch(x, ldx, w, K, type_ptr_host, T, ep, opf, workspace, workspace_bytes,
                                       wsi_stream(stream));
   return wsi_typed_linear_simt_launch(x, ldx, w, K, type_ptr_host, T, ep, wsi_stream(stream));
 }

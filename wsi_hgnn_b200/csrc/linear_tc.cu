@@ -18,9 +18,16 @@
 //                    (epilogue.cuh) -> coalesced 16 B global stores; double-buffered TMEM (2 x 256 columns) so the
 //                    epilogue of tile i overlaps the MMAs of tile i+1
 // Tensor-pipe bound: algorithmic flops 2*N*K*n_out (x3 MMAs issued for the split).
+//
+// Operand formats (WSI_OPF_*, include/wsi_hgnn.h).  The kernel is a template on TERMS:
+//   TERMS 3  WSI_OPF_BF16X3: the [hi; lo] scheme above (~2^-17 relative: "exact" mode, gradients)
+//   TERMS 1  WSI_OPF_F16 / WSI_OPF_BF16: ONE 16-bit operand per matrix, one MMA per k-slice, a 6-stage ring of
+//            32 KB stages.  fp16 (11-bit significand = TF32's) is the default of the fp32 models: measured on the 16
+//            reference-generated goldens + config 2 (tools/precision_study.py, profiles/r2_precision_study.json) the
+//            whole forward stays 3.6x inside the 1e-3 parity bar, at 1/3 of the tensor work and 1/2 of the L2 -> smem
+//            operand bytes of the 3-term product; bf16 serves the bf16-storage configuration (BASELINE config 3).
 #include <cuda.h>
-
-#include <stdlib.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 
@@ -29,21 +36,21 @@
 namespace {
 
 constexpr int BM = 128;            // rows per CTA (TMEM lanes)
-// Two tile shapes (template parameter BN = columns per tile = UMMA N; each CTA of the pair stages BN/2 rows of W):
-//   BN 256, 3-stage ring: the fewest L2 -> smem bytes per flop; used when there are several tiles per CTA pair
-//   BN 128, 4-stage ring: twice as many (half-size) tiles, so that with one 256-wide tile per CTA pair the epilogue of
-//                         the first half tile overlaps the MMAs of the second - measured slower (more operand bytes),
-//                         kept behind WSI_TC_BN=128
-constexpr int BK = 64;             // bf16 per k-block = one 128 B swizzle row
+constexpr int BN = 256;            // columns per tile = UMMA N; each CTA of the pair stages BN/2 rows of W
+constexpr int BK = 64;             // 16-bit elements per k-block = one 128 B swizzle row
 constexpr int UMMA_K = 16;
 constexpr int PAIR_M = 2 * BM;     // rows per CTA pair (UMMA M = 256, cta_group::2)
 constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
 constexpr int EPI_LD = 32;                               // staging row pitch in floats; float4 slots XOR-swizzled by row
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
 constexpr int EPI_WARPS = 8;                             // 2 warps per TMEM lane quarter, each takes half of the columns
-constexpr int stages_of(int bn) { return bn == 256 ? 3 : 4; }
-constexpr int stage_bytes_of(int bn) { return 2 * A_TILE_BYTES + 2 * (bn / 2) * BK * 2; }       // per CTA
-constexpr int smem_bytes_of(int bn) { return 1024 + stages_of(bn) * stage_bytes_of(bn) + EPI_WARPS * EPI_WARP_FLOATS * 4 + 256; }
+// Tile shapes that were built, verified bit-identical and measured in round 1 and do NOT ship any more (they lost):
+// 128-wide tiles with a 4-stage ring (more L2 -> smem operand bytes per flop) and a 4-CTA cluster sharing the A operand
+// by TMA multicast (no gain: only 132 of 148 SMs host 4-CTA clusters).  See DESIGN.md section 3.
+constexpr int stages_of(int terms) { return terms == 3 ? 3 : 6; }
+constexpr int stage_bytes_of(int terms) { return (terms == 3 ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES); }       // per CTA
+constexpr int smem_bytes_of(int terms) { return 1024 + stages_of(terms) * stage_bytes_of(terms) + EPI_WARPS * EPI_WARP_FLOATS * 4 + 256; }
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -96,15 +103,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t clu
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
 }
-// same, multicast: the box lands at the same smem offset in every CTA of `mask` (cluster ranks) and each copy posts its
-// bytes on the full barrier of the destination CTA's pair leader (barrier operand with the peer bit clear)
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint32_t cluster_bar, uint32_t dst, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // arrive (once the MMAs issued so far retire) on the barrier at this smem offset in BOTH CTAs of the pair
@@ -112,9 +110,9 @@ __device__ __forceinline__ void tc_commit_mask(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
 }
-// D[tmem, 256 x N over the CTA pair] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
+// D[tmem, 256 x N over the CTA pair] (+)= A[smem] . B[smem]^T, 16-bit x 16-bit -> fp32 (operand type in the descriptor)
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -138,7 +136,7 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B):
+// K-major, 128B-swizzled operand tile (rows of 64 16-bit elements = 128 B, 8-row swizzle atoms of 1024 B):
 // start address >> 4 | LBO 1 (unused for swizzled K-major) | SBO 1024 B >> 4 | version 1 (sm_100) | SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   uint64_t d = 0;
@@ -149,14 +147,56 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::f16 instruction descriptor: fp32 accumulate, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t idesc_of(int bn) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24); }
+// kind::f16 instruction descriptor: fp32 accumulate (bit 4), A / B format at bits 7 / 10 (0 = fp16, 1 = bf16), both
+// K-major, N >> 3 at bit 17, M >> 4 at bit 24
+inline uint32_t idesc_of(bool bf16) {
+  const uint32_t f = bf16 ? 1u : 0u;
+  return (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------ pre-pass
-// fp32 -> [hi; lo] bf16.  src rows have stride ld_src floats; dst is dense [2 * rows, K] (lo half at row `rows`).
-struct SplitJob { const float* src; int64_t ld_src; int64_t rows; __nv_bfloat16* dst; };
+// fp32 -> operand form.  src rows have stride ld_src floats; dst is dense:
+//   WSI_OPF_BF16X3  [2 * rows, K] bf16 (hi rows, then lo rows at row `rows`)
+//   WSI_OPF_F16     [rows, K] fp16, round to nearest, clamped to the finite fp16 range (+-65504)
+//   WSI_OPF_BF16    [rows, K] bf16
+struct SplitJob { const float* src; int64_t ld_src; int64_t rows; void* dst; };
 
-__global__ void __launch_bounds__(256) split_bf16_kernel(SplitJob a, SplitJob b, int K) {
+__device__ __forceinline__ uint2 pack4_f16(float4 x) {
+  const float lim = 65504.f;
+  __half2 a = __floats2half2_rn(fminf(fmaxf(x.x, -lim), lim), fminf(fmaxf(x.y, -lim), lim));
+  __half2 b = __floats2half2_rn(fminf(fmaxf(x.z, -lim), lim), fminf(fmaxf(x.w, -lim), lim));
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  return r;
+}
+__device__ __forceinline__ uint2 pack4_bf16(float4 x) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  return r;
+}
+// the operand-form store shared by this pre-pass, the GEMM epilogue and (hetero_attn.cu has its own copy) the attention
+// kernel: 4 consecutive values of one row at `dst16` (16-bit element pointer)
+template <int OPF>
+__device__ __forceinline__ void store_operand4(void* dst16, int64_t lo_off, float4 x) {
+  if (OPF == WSI_OPF_BF16X3) {
+    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+    wsi_split_bf16(x.x, h0, l0); wsi_split_bf16(x.y, h1, l1); wsi_split_bf16(x.z, h2, l2); wsi_split_bf16(x.w, h3, l3);
+    __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
+    __nv_bfloat162 lv[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
+    *reinterpret_cast<uint2*>(dst16) = *reinterpret_cast<uint2*>(hv);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst16) + lo_off) = *reinterpret_cast<uint2*>(lv);
+  } else if (OPF == WSI_OPF_F16) {
+    *reinterpret_cast<uint2*>(dst16) = pack4_f16(x);
+  } else {
+    *reinterpret_cast<uint2*>(dst16) = pack4_bf16(x);
+  }
+}
+
+template <int OPF>
+__global__ void __launch_bounds__(256) convert_operand_kernel(SplitJob a, SplitJob b, int K) {
   wsi_pdl_trigger();                                      // the GEMM that follows may set itself up while this drains
   const int kv = K >> 2;                                  // float4 groups per row (K % 8 == 0)
   const int64_t na = a.rows * kv, total = na + b.rows * kv;
@@ -166,24 +206,22 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(SplitJob a, SplitJob b,
     const int64_t r = li / kv;
     const int c = (int)(li - r * kv) << 2;
     const float4 x = __ldg(reinterpret_cast<const float4*>(j.src + r * j.ld_src + c));
-    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-    wsi_split_bf16(x.x, h0, l0); wsi_split_bf16(x.y, h1, l1); wsi_split_bf16(x.z, h2, l2); wsi_split_bf16(x.w, h3, l3);
-    __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
-    __nv_bfloat162 lv[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
-    *reinterpret_cast<uint2*>(j.dst + r * K + c) = *reinterpret_cast<uint2*>(hv);
-    *reinterpret_cast<uint2*>(j.dst + (j.rows + r) * K + c) = *reinterpret_cast<uint2*>(lv);
+    store_operand4<OPF>(reinterpret_cast<uint16_t*>(j.dst) + r * K + c, j.rows * K, x);
   }
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
 struct TcArgs {
-  int n_rows;        // N  (row offset of the lo half of the A workspace)
-  int w_rows;        // T * n_out (row offset of the lo half of the W workspace)
+  int n_rows;        // N  (TERMS 3: row offset of the lo half of the A workspace)
+  int w_rows;        // T * n_out (TERMS 3: row offset of the lo half of the W workspace)
   int K, n_out;
   int n_tiles_m, n_tiles_n;   // n_tiles_m counts 256-row PAIR tiles
-  __nv_bfloat16* y_split;   // optional [2 * n_rows, n_out] bf16 (hi; lo) copy of y: the next GEMM's A operand
-  int dbg;           // development only (env WSI_TC_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads, bit 2 = skip the epilogue body,
-                     // bit 3 = no global stores in the epilogue, bit 4 = no TMEM reads in the epilogue
+  void* y_op;        // optional operand-form copy of y (the next GEMM's A operand): TERMS 3 bf16 [2 * n_rows, n_out]
+                     // (hi; lo), TERMS 1 fp16 / bf16 [n_rows, n_out]
+  uint32_t idesc;
+  int op_bf16;       // TERMS 1: 16-bit type of the operands and of y_op (0 = fp16, 1 = bf16)
+  int dbg;           // development only (wsi_dev_set("tc_debug")): bit 0 = skip the MMAs, bit 1 = skip the TMA loads,
+                     // bit 2 = skip the epilogue body, bit 3 = no global stores in the epilogue, bit 4 = no TMEM reads
 };
 
 // FULL = false: v = act(acc + bias).  FULL = true: + dropout mask, sigma(skip) residual mix with row gate, row scale.
@@ -206,19 +244,12 @@ __device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc,
   return make_float4(a[0], a[1], a[2], a[3]);
 }
 
-// CL = CTAs per cluster.  CL 2: one CTA pair per cluster (as described at the top).  CL 4: TWO pairs that work on the two
-// neighbouring column tiles (tn, tn + 1) of the same 256 rows and SHARE the A operand: each CTA loads only half of the
-// A rows it needs (64 of 128, hi and lo) and TMA-multicasts them to the CTA of the other pair that needs the same rows,
-// which cuts the L2 -> smem operand bytes per flop by 25 % - the measured limiter of this kernel.  A ring slot is then
-// written from both pairs, so it is released by the tcgen05.commit of BOTH pairs (empty barriers count 2, commit
-// multicast to all four CTAs).
-template <bool FULL, bool GELU, int BN, int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+template <bool FULL, bool GELU, int TERMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ TypeSegs segs, const __grid_constant__ LinearEpilogue ep, TcArgs a) {
-  constexpr int STAGES = stages_of(BN), STAGE_BYTES = stage_bytes_of(BN), B_TILE_BYTES = (BN / 2) * BK * 2;
-  constexpr uint32_t IDESC = idesc_of(BN);
-  constexpr bool MC = CL == 4;
+  constexpr int STAGES = stages_of(TERMS), STAGE_BYTES = stage_bytes_of(TERMS);
+  constexpr int B_OFF = (TERMS == 3 ? 2 : 1) * A_TILE_BYTES;          // first W tile inside a stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B tiles need 1024 B alignment
@@ -230,14 +261,11 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank & 1;                                   // 0 = leader (issues the MMAs of the pair)
-  const uint32_t pc = crank >> 1;                                    // pair index inside the cluster (0 when CL == 2)
-  const uint32_t leader = crank & ~1u;                               // cluster rank of this pair's leader
-  const uint16_t pair_mask = (uint16_t)(3u << (2 * pc));             // both CTAs of this pair
-  const int pair = blockIdx.x / CL, n_pairs = gridDim.x / CL;        // (cluster index / count: a cluster owns a tile or, CL 4, a tile pair)
+  const uint32_t rank = cluster_ctarank();                           // 0 = leader (issues the MMAs of the pair)
+  const uint16_t pair_mask = 3;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int num_kb = (a.K + BK - 1) / BK;
-  const int n_tn = MC ? a.n_tiles_n / 2 : a.n_tiles_n;              // column (super)tiles
+  const int n_tn = a.n_tiles_n;
   const int total_tiles = a.n_tiles_m * n_tn;
 
   if (warp == 0 && lane == 0) {
@@ -245,7 +273,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     // full: the leader's expect_tx arrive + the peer's plain arrive; empty / tmem_full: one tcgen05.commit;
     // tmem_empty (leader's is the one waited on): the epilogue warps of both CTAs
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, MC ? 2 : 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -267,28 +295,21 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===================================================================== TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint16_t a_mask = (uint16_t)(5u << rank);                // the CTAs (one per pair) that need the same A rows
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const int tm = tile / n_tn, tn = MC ? 2 * (tile - tm * n_tn) + (int)pc : tile - tm * n_tn;
+        const int tm = tile / n_tn, tn = tile - tm * n_tn;
         const int t = wsi_tile_group(segs, tm);
         const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * PAIR_M + (int)rank * BM;
         const int wrow0 = t * a.n_out + tn * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = mapa(full_bar + 8 * stage, leader);
+          const uint32_t fb = mapa(full_bar + 8 * stage, 0);
           const uint32_t s0 = base + stage * STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(full_bar + 8 * stage, (a.dbg & 2) ? 0 : 2 * STAGE_BYTES);
           if (!(a.dbg & 2)) {
-          if (MC) {                                                  // my half (64 rows) of the shared A rows, to both pairs
-            const int half_rows = BM / 2, off = (int)pc * half_rows;
-            tma_load_2d_mc(&tmA, fb, s0 + off * BK * 2, kb * BK, row0 + off, a_mask);
-            tma_load_2d_mc(&tmA, fb, s0 + A_TILE_BYTES + off * BK * 2, kb * BK, a.n_rows + row0 + off, a_mask);
-          } else {
             tma_load_2d(&tmA, fb, s0, kb * BK, row0);
-            tma_load_2d(&tmA, fb, s0 + A_TILE_BYTES, kb * BK, a.n_rows + row0);
-          }
-          tma_load_2d(&tmB, fb, s0 + 2 * A_TILE_BYTES, kb * BK, wrow0);
-          tma_load_2d(&tmB, fb, s0 + 2 * A_TILE_BYTES + B_TILE_BYTES, kb * BK, a.w_rows + wrow0);
+            if (TERMS == 3) tma_load_2d(&tmA, fb, s0 + A_TILE_BYTES, kb * BK, a.n_rows + row0);
+            tma_load_2d(&tmB, fb, s0 + B_OFF, kb * BK, wrow0);
+            if (TERMS == 3) tma_load_2d(&tmB, fb, s0 + B_OFF + B_TILE_BYTES, kb * BK, a.w_rows + wrow0);
           }
           if (rank != 0) mbar_arrive_cluster(fb);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -300,6 +321,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t idesc = a.idesc;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);              // both epilogues have drained this accumulator
         tc_fence_after();
@@ -309,21 +331,19 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc_fence_after();
           if (lane == 0) {
             const uint32_t s0 = base + stage * STAGE_BYTES;
-            const uint64_t a_hi = make_smem_desc(s0), a_lo = make_smem_desc(s0 + A_TILE_BYTES);
-            const uint64_t b_hi = make_smem_desc(s0 + 2 * A_TILE_BYTES),
-                           b_lo = make_smem_desc(s0 + 2 * A_TILE_BYTES + B_TILE_BYTES);
+            const uint64_t a_hi = make_smem_desc(s0), b_hi = make_smem_desc(s0 + B_OFF);
             if (!(a.dbg & 1))
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);   // +32 B per k-slice inside the swizzle atom
-              tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kb | ks) != 0);
-              {
-              tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1);
-              tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
+              tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | ks) != 0);
+              if (TERMS == 3) {
+                const uint64_t a_lo = make_smem_desc(s0 + A_TILE_BYTES), b_lo = make_smem_desc(s0 + B_OFF + B_TILE_BYTES);
+                tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
               }
             }
-            // smem slot free once these retire: in both CTAs of the pair, and - with shared A tiles - in the other pair too
-            tc_commit_mask(empty_bar + 8 * stage, MC ? (uint16_t)0xF : pair_mask);
+            tc_commit_mask(empty_bar + 8 * stage, pair_mask);        // smem slot free once these retire (both CTAs)
             if (kb == num_kb - 1) tc_commit_mask(tfull_bar + 8 * acc, pair_mask);   // accumulator complete (both CTAs)
           }
           __syncwarp();
@@ -342,7 +362,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr int CHUNKS = BN / 32 / 2;                              // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-      const int tm = tile / n_tn, tn = MC ? 2 * (tile - tm * n_tn) + (int)pc : tile - tm * n_tn;
+      const int tm = tile / n_tn, tn = tile - tm * n_tn;
       const int t = wsi_tile_group(segs, tm);
       const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * PAIR_M + (int)rank * BM + q * 32;
       const int rows_left = segs.ptr[t + 1] - (row0 + rsub);         // this lane handles rows row0 + rsub + 4 it
@@ -374,7 +394,6 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       };
       if (FULL) load_res(0, rr[0]);
       // the bias vectors of all chunks too: a load issued inside the chunk loop sat in the dependent chain of every chunk
-      // (the "epilogue only" knob timing was 1.9 us per 32 x 32 chunk, almost all of it this L2 round trip)
       float4 bb_all[CHUNKS];
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c)
@@ -417,14 +436,11 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                   : epi_mix4<false, GELU>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
             if (ep.y && !(a.dbg & 8)) *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
             else if (a.dbg & 8) { if (o.x == 123456.789f) yp[0] = o.y; }       // development: no global stores (keep the math alive)
-            if (a.y_split && !(a.dbg & 8)) {
-              __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-              wsi_split_bf16(o.x, h0, l0); wsi_split_bf16(o.y, h1, l1); wsi_split_bf16(o.z, h2, l2); wsi_split_bf16(o.w, h3, l3);
-              __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
-              __nv_bfloat162 lv[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
-              __nv_bfloat16* ys = a.y_split + (int64_t)(row0 + rsub + it * 4) * a.n_out + n0 + c * 32;
-              *reinterpret_cast<uint2*>(ys) = *reinterpret_cast<uint2*>(hv);
-              *reinterpret_cast<uint2*>(ys + (int64_t)a.n_rows * a.n_out) = *reinterpret_cast<uint2*>(lv);
+            if (a.y_op && !(a.dbg & 8)) {
+              uint16_t* ys = reinterpret_cast<uint16_t*>(a.y_op) + (int64_t)(row0 + rsub + it * 4) * a.n_out + n0 + c * 32;
+              if (TERMS == 3) store_operand4<WSI_OPF_BF16X3>(ys, (int64_t)a.n_rows * a.n_out, o);
+              else if (a.op_bf16) store_operand4<WSI_OPF_BF16>(ys, 0, o);
+              else store_operand4<WSI_OPF_F16>(ys, 0, o);
             }
           }
         }
@@ -432,7 +448,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar + 8 * acc, leader));   // on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar + 8 * acc, 0));   // on the leader's barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -464,27 +480,28 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 [rows, K] row-major, box [box_rows, BK], 128 B swizzle, out-of-bounds elements read as 0
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int K, int box_rows) {
+// 16-bit [rows, K] row-major, box [box_rows, BK], 128 B swizzle, out-of-bounds elements read as 0
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int K, int box_rows, bool bf16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { wsi_set_error("typed_linear(tcgen05): cuTensorMapEncodeTiled is not available"); return WSI_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { wsi_set_error("typed_linear(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r); return WSI_ERR_CUDA; }
   return WSI_OK;
 }
 
 inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int terms_of(int opf) { return opf == WSI_OPF_BF16X3 ? 2 : 1; }   // 16-bit matrices per operand
 
 }  // namespace
 
-// Shapes the tensor-core path takes: K a multiple of 8 (16 B rows for TMA / float4 split), output rows 16 B
+// Shapes the tensor-core path takes: K a multiple of 8 (16 B rows for TMA / float4 conversion), output rows 16 B
 // aligned, and enough work to fill 128-row MMA tiles (small [B, D] readout GEMMs stay on the SIMT path).
 bool wsi_typed_linear_tc_supported(int64_t n_rows, int K, int n_out, int64_t ldx) {
   // (n_out % 4 != 0 is accepted here; the callers then require a padded output pitch and no per-column vectors:
@@ -493,102 +510,73 @@ bool wsi_typed_linear_tc_supported(int64_t n_rows, int K, int n_out, int64_t ldx
          ldx % 4 == 0 && (int64_t)n_out * WSI_MAX_TYPES < (1ll << 30);
 }
 
-int64_t wsi_typed_linear_tc_workspace(int64_t n_rows, int K, int n_out, int T) {
-  return align256(2 * n_rows * K * 2) + align256(2 * (int64_t)T * n_out * K * 2) + 1024;
+bool wsi_opf_valid(int opf) { return opf == WSI_OPF_BF16X3 || opf == WSI_OPF_F16 || opf == WSI_OPF_BF16; }
+
+int64_t wsi_typed_linear_tc_workspace(int64_t n_rows, int K, int n_out, int T, int opf) {
+  const int64_t m = terms_of(opf);
+  return align256(m * n_rows * K * 2) + align256(m * (int64_t)T * n_out * K * 2) + 1024;
 }
 
-// GEMM on pre-split operands: a_ws bf16 [2 * n_rows, K] (hi rows, then lo rows), w_ws bf16 [2 * T * n_out, K].
+// GEMM on operands already in operand form (`opf`): a_ws / w_ws 16-bit [m * n_rows, K] / [m * T * n_out, K], m = 2 for
+// the [hi; lo] split (hi rows, then lo rows), else 1.
 int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const int32_t* type_ptr_host, int T,
-                             const LinearEpilogue& ep, void* y_split, cudaStream_t stream) {
+                             const LinearEpilogue& ep, void* y_op, int opf, cudaStream_t stream) {
   const int64_t n_rows = type_ptr_host[T];
   const int n_out = ep.n_out;
-  WSI_CHECK_ARG((ep.y || y_split) && (!ep.y || (aligned16(ep.y) && ep.ldy % 4 == 0)),
+  WSI_CHECK_ARG(wsi_opf_valid(opf), "typed_linear(tcgen05): unknown operand format %d", opf);
+  WSI_CHECK_ARG((ep.y || y_op) && (!ep.y || (aligned16(ep.y) && ep.ldy % 4 == 0)),
                 "typed_linear(tcgen05): y must be 16 B aligned with a row stride that is a multiple of 4 floats");
   WSI_CHECK_ARG((reinterpret_cast<uintptr_t>(a_ws) & 127) == 0 && (reinterpret_cast<uintptr_t>(w_ws) & 127) == 0 &&
-                    (!y_split || (reinterpret_cast<uintptr_t>(y_split) & 15) == 0),
-                "typed_linear(tcgen05): split operands must be 128 B aligned");
+                    (!y_op || (reinterpret_cast<uintptr_t>(y_op) & 15) == 0),
+                "typed_linear(tcgen05): operands must be 128 B aligned");
   WSI_CHECK_ARG((!ep.bias || aligned16(ep.bias)) && (!ep.drop_mask || (aligned16(ep.drop_mask) && ep.ldmask % 4 == 0)) &&
                     (!ep.res || (aligned16(ep.res) && ep.ldres % 4 == 0)),
                 "typed_linear(tcgen05): bias / drop_mask / res must be 16 B aligned with row strides multiple of 4 floats");
   TypeSegs segs;
   if (wsi_make_segs(&segs, type_ptr_host, T, PAIR_M) != 0) { wsi_set_error("typed_linear: bad type_ptr"); return WSI_ERR_ARG; }
-
-  // tile shape: 256-wide tiles unless they leave every CTA pair with at most one tile (see the top of the file)
   int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
-  // Measured (config 2, tools/sweep_dev.py): the 128-wide tiling loses even for the one-tile-per-pair shapes (a_linear
-  // 32.8 vs 28.7 us, adapt_ws 47.1 vs 34.8 us) - the kernel is bound by L2 -> smem operand bytes, which the narrower
-  // tile raises by 50 %, not by the exposed epilogue.  It stays selectable for experiments only.
-  int BN = 256;
-  if (const char* f = getenv("WSI_TC_BN")) BN = atoi(f) == 128 ? 128 : 256;        // development knob
-  // cluster shape.  The 4-CTA variant (two pairs sharing the A operand by TMA multicast) is bit-identical and was
-  // measured on config 2: K|V|Q 43.0 vs 43.0 us, a_linear 28.7 vs 28.7 us, adapt_ws (K = 1024) 32.8 vs 34.8 us, whole
-  // forward +0.5 % - the L2 evidently already merges the two pairs' concurrent reads of the same A tile, and only 33
-  // four-CTA clusters (132 of 148 SMs) are co-resident.  Default stays one pair per cluster; WSI_TC_CL=4 selects it.
-  int CL = 2;
-  if (const char* f = getenv("WSI_TC_CL")) CL = (atoi(f) == 4 && BN == 256 && ((n_out + BN - 1) / BN) % 2 == 0) ? 4 : 2;   // development knob
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
-  static int max_clusters4 = 0;
   std::call_once(attr_once, [] {
-    const void* fns[12] = {(const void*)typed_linear_tc_kernel<false, false, 256, 2>, (const void*)typed_linear_tc_kernel<true, false, 256, 2>,
-                           (const void*)typed_linear_tc_kernel<false, true, 256, 2>, (const void*)typed_linear_tc_kernel<true, true, 256, 2>,
-                           (const void*)typed_linear_tc_kernel<false, false, 256, 4>, (const void*)typed_linear_tc_kernel<true, false, 256, 4>,
-                           (const void*)typed_linear_tc_kernel<false, true, 256, 4>, (const void*)typed_linear_tc_kernel<true, true, 256, 4>,
-                           (const void*)typed_linear_tc_kernel<false, false, 128, 2>, (const void*)typed_linear_tc_kernel<true, false, 128, 2>,
-                           (const void*)typed_linear_tc_kernel<false, true, 128, 2>, (const void*)typed_linear_tc_kernel<true, true, 128, 2>};
-    for (int i = 0; i < 12 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(i < 8 ? 256 : 128));
-    if (attr_err == cudaSuccess) {                                   // how many 4-CTA clusters (1 CTA / SM) fit on the chip at once
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes_of(256);
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      int n = 0;
-      for (int with_attr = 0; with_attr < 2 && n <= 0; ++with_attr) {      // (the kernel carries __cluster_dims__ itself)
-        cfg.numAttrs = with_attr;
-        if (cudaOccupancyMaxActiveClusters(&n, (const void*)typed_linear_tc_kernel<false, false, 256, 4>, &cfg) != cudaSuccess) {
-          (void)cudaGetLastError();
-          n = 0;
-        }
-      }
-      max_clusters4 = n;
-      if (getenv("WSI_TC_VERBOSE")) fprintf(stderr, "[wsi] typed_linear(tcgen05): %d co-resident 4-CTA clusters\n", n);
-    }
+    const void* fns[8] = {(const void*)typed_linear_tc_kernel<false, false, 3>, (const void*)typed_linear_tc_kernel<true, false, 3>,
+                          (const void*)typed_linear_tc_kernel<false, true, 3>, (const void*)typed_linear_tc_kernel<true, true, 3>,
+                          (const void*)typed_linear_tc_kernel<false, false, 1>, (const void*)typed_linear_tc_kernel<true, false, 1>,
+                          (const void*)typed_linear_tc_kernel<false, true, 1>, (const void*)typed_linear_tc_kernel<true, true, 1>};
+    for (int i = 0; i < 8 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(i < 4 ? 3 : 1));
   });
   WSI_CHECK_CUDA(attr_err);
-  if (CL == 4 && max_clusters4 < 8) CL = 2;                          // (no usable 4-CTA placement on this device)
 
+  const bool bf16 = opf != WSI_OPF_F16;
+  const int m = terms_of(opf);
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, a_ws, 2 * n_rows, K, CL == 4 ? BM / 2 : BM);
+  int rc = make_map(&tmA, a_ws, m * n_rows, K, BM, bf16);
   if (rc != WSI_OK) return rc;
-  rc = make_map(&tmB, w_ws, 2 * (int64_t)T * n_out, K, BN / 2);
+  rc = make_map(&tmB, w_ws, m * (int64_t)T * n_out, K, BN / 2, bf16);
   if (rc != WSI_OK) return rc;
   TcArgs a{};
   a.n_rows = (int)n_rows; a.w_rows = T * n_out; a.K = K; a.n_out = n_out;
   a.n_tiles_m = segs.tile_start[T]; a.n_tiles_n = (n_out + BN - 1) / BN;
-  a.y_split = reinterpret_cast<__nv_bfloat16*>(y_split);
+  a.y_op = y_op;
+  a.idesc = idesc_of(bf16);
+  a.op_bf16 = bf16 ? 1 : 0;
+  a.dbg = wsi_dev()->tc_debug;
   const bool full = ep.skip || ep.drop_mask || ep.row_scale;
-  { const char* d = getenv("WSI_TC_DEBUG"); a.dbg = d ? atoi(d) : 0; }
-  const int total = a.n_tiles_m * (CL == 4 ? a.n_tiles_n / 2 : a.n_tiles_n);       // tiles (CL 2) or tile pairs (CL 4)
+  const int total = a.n_tiles_m * a.n_tiles_n;
   if (total == 0) return WSI_OK;
-  const int max_clusters = CL == 4 ? max_clusters4 : sms / 2;        // persistent: one cluster per CL SMs
+  const int max_clusters = sms / 2;                                  // persistent: one CTA pair per two SMs
   const int clusters = total < max_clusters ? total : max_clusters;
   const bool gelu = ep.act == WSI_ACT_GELU;       // compile-time in the kernel: the erf code must not sit (predicated off) in the plain epilogue
-  const dim3 grid(CL * clusters), block(THREADS);
+  const dim3 grid(2 * clusters), block(THREADS);
   cudaError_t le;
-#define TC_LAUNCH(F, G, B, C) le = wsi_launch_pdl(typed_linear_tc_kernel<F, G, B, C>, grid, block, smem_bytes_of(B), stream, tmA, tmB, segs, ep, a)
-  if (BN == 256 && CL == 4) {
-    if (full && gelu) TC_LAUNCH(true, true, 256, 4); else if (full) TC_LAUNCH(true, false, 256, 4);
-    else if (gelu) TC_LAUNCH(false, true, 256, 4); else TC_LAUNCH(false, false, 256, 4);
-  } else if (BN == 256) {
-    if (full && gelu) TC_LAUNCH(true, true, 256, 2); else if (full) TC_LAUNCH(true, false, 256, 2);
-    else if (gelu) TC_LAUNCH(false, true, 256, 2); else TC_LAUNCH(false, false, 256, 2);
+#define TC_LAUNCH(F, G, TR) le = wsi_launch_pdl(typed_linear_tc_kernel<F, G, TR>, grid, block, smem_bytes_of(TR), stream, tmA, tmB, segs, ep, a)
+  if (m == 2) {
+    if (full && gelu) TC_LAUNCH(true, true, 3); else if (full) TC_LAUNCH(true, false, 3);
+    else if (gelu) TC_LAUNCH(false, true, 3); else TC_LAUNCH(false, false, 3);
   } else {
-    if (full && gelu) TC_LAUNCH(true, true, 128, 2); else if (full) TC_LAUNCH(true, false, 128, 2);
-    else if (gelu) TC_LAUNCH(false, true, 128, 2); else TC_LAUNCH(false, false, 128, 2);
+    if (full && gelu) TC_LAUNCH(true, true, 1); else if (full) TC_LAUNCH(true, false, 1);
+    else if (gelu) TC_LAUNCH(false, true, 1); else TC_LAUNCH(false, false, 1);
   }
 #undef TC_LAUNCH
   WSI_CHECK_CUDA(le);
@@ -596,36 +584,39 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   return WSI_OK;
 }
 
-// fp32 -> [hi; lo] bf16 of up to two row-strided matrices in one launch (b.rows == 0: only a)
+// fp32 -> operand form of up to two row-strided matrices in one launch (b.rows == 0: only a)
 int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_dst, const float* b_src, int64_t b_ld,
-                     int64_t b_rows, void* b_dst, int K, cudaStream_t stream) {
+                     int64_t b_rows, void* b_dst, int K, int opf, cudaStream_t stream) {
+  WSI_CHECK_ARG(wsi_opf_valid(opf), "operand conversion: unknown operand format %d", opf);
   WSI_CHECK_ARG(K % 8 == 0 && a_ld % 4 == 0 && (b_rows == 0 || b_ld % 4 == 0) && aligned16(a_src) && aligned16(b_src) &&
                     (reinterpret_cast<uintptr_t>(a_dst) & 7) == 0 && (reinterpret_cast<uintptr_t>(b_dst) & 7) == 0,
-                "split_bf16: K must be a multiple of 8, rows 16 B aligned");
+                "operand conversion: K must be a multiple of 8, rows 16 B aligned");
   int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
-  SplitJob ja{a_src, a_ld, a_rows, reinterpret_cast<__nv_bfloat16*>(a_dst)};
-  SplitJob jb{b_src, b_ld, b_rows, reinterpret_cast<__nv_bfloat16*>(b_dst)};
+  SplitJob ja{a_src, a_ld, a_rows, a_dst};
+  SplitJob jb{b_src, b_ld, b_rows, b_dst};
   const int64_t groups = (ja.rows + jb.rows) * (K / 4);
   if (groups == 0) return WSI_OK;
   int sblocks = (int)((groups + 255) / 256);
   if (sblocks > sms * 8) sblocks = sms * 8;
-  split_bf16_kernel<<<sblocks, 256, 0, stream>>>(ja, jb, K);
+  if (opf == WSI_OPF_BF16X3) convert_operand_kernel<WSI_OPF_BF16X3><<<sblocks, 256, 0, stream>>>(ja, jb, K);
+  else if (opf == WSI_OPF_F16) convert_operand_kernel<WSI_OPF_F16><<<sblocks, 256, 0, stream>>>(ja, jb, K);
+  else convert_operand_kernel<WSI_OPF_BF16><<<sblocks, 256, 0, stream>>>(ja, jb, K);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }
 
 int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int K, const int32_t* type_ptr_host,
-                               int T, const LinearEpilogue& ep, void* workspace, int64_t workspace_bytes,
+                               int T, const LinearEpilogue& ep, int opf, void* workspace, int64_t workspace_bytes,
                                cudaStream_t stream) {
   const int64_t n_rows = type_ptr_host[T];
   const int n_out = ep.n_out;
-  WSI_CHECK_ARG(workspace && workspace_bytes >= wsi_typed_linear_tc_workspace(n_rows, K, n_out, T),
-                "typed_linear(tcgen05): workspace of %lld bytes needed", (long long)wsi_typed_linear_tc_workspace(n_rows, K, n_out, T));
+  WSI_CHECK_ARG(workspace && workspace_bytes >= wsi_typed_linear_tc_workspace(n_rows, K, n_out, T, opf),
+                "typed_linear(tcgen05): workspace of %lld bytes needed", (long long)wsi_typed_linear_tc_workspace(n_rows, K, n_out, T, opf));
   uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023;
   void* a_ws = reinterpret_cast<void*>(wsp);
-  void* w_ws = reinterpret_cast<void*>(wsp + align256(2 * n_rows * K * 2));
-  int rc = wsi_split_launch(x, ldx, n_rows, a_ws, w, K, (int64_t)T * n_out, w_ws, K, stream);
+  void* w_ws = reinterpret_cast<void*>(wsp + align256(terms_of(opf) * n_rows * K * 2));
+  int rc = wsi_split_launch(x, ldx, n_rows, a_ws, w, K, (int64_t)T * n_out, w_ws, K, opf, stream);
   if (rc != WSI_OK) return rc;
-  return wsi_typed_linear_tc_gemm(a_ws, w_ws, K, type_ptr_host, T, ep, nullptr, stream);
+  return wsi_typed_linear_tc_gemm(a_ws, w_ws, K, type_ptr_host, T, ep, nullptr, opf, stream);
 }

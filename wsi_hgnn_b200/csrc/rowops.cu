@@ -225,7 +225,8 @@ int pool_splits(int64_t n_rows, int64_t n_seg, int D) {
   // enough CTAs to fill the chip even when one (type, graph) segment holds all the rows
   int chunks = (D + 127) / 128;
   int64_t ctas = n_seg * chunks;
-  int64_t want = 148 * 4;
+  const int sms = wsi_num_sms();
+  int64_t want = (int64_t)(sms > 0 ? sms : 148) * 4;
   int s = (int)((want + ctas - 1) / ctas);
   int64_t max_by_rows = (n_rows + 255) / 256;     // at least ~256 rows per slab
   if (s > max_by_rows) s = (int)max_by_rows;
@@ -361,7 +362,7 @@ extern "C" int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gam
   int n_rows = segs.ptr[T];
   if (n_rows == 0) return WSI_OK;
   int blocks = (n_rows + 7) / 8;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  { const int sms = wsi_num_sms(); if (sms <= 0) return WSI_ERR_CUDA; if (blocks > sms * 16) blocks = sms * 16; }
   typed_layernorm_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(x, ldx, gamma, beta, segs, D, eps, y, ldy);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
@@ -373,7 +374,7 @@ extern "C" int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t*
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(row_seg_ptr && node_inv_r && agg, "segment_combine: null pointer");
   int blocks = (int)((n_rows + 7) / 8);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  { const int sms = wsi_num_sms(); if (sms <= 0) return WSI_ERR_CUDA; if (blocks > sms * 16) blocks = sms * 16; }
   segment_combine_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(msg, ldm, row_seg_ptr, node_inv_r, (int)n_rows, D,
                                                                  agg, ldo);
   WSI_CHECK_LAUNCH();

@@ -114,10 +114,11 @@ class HEATLayer(nn.Module):
         return self._packs.get(tuple(order), params, build) + (perm is not None,)
 
     def _packed_split(self, order):
-        """bf16 [hi; lo] forms of the K|V|Q and a_linear weight stacks (operands of the tcgen05 GEMM chain)."""
+        """Operand forms (ops.to_operand, the current matmul precision) of the K|V|Q and a_linear weight stacks."""
         w_kvq, b_kvq, wa, ba, skip, _ = self._packed(order)
         params = param_list(self, "all", self.parameters)
-        return self._packs.get(("split", tuple(order)), params, lambda: (ops.split_bf16(w_kvq), ops.split_bf16(wa)))
+        opf = ops.matmul_opf()
+        return self._packs.get(("split", opf, tuple(order)), params, lambda: (ops.to_operand(w_kvq, opf), ops.to_operand(wa, opf)))
 
     def tc_chain_ok(self, plan: GraphPlan) -> bool:
         """The pre-split tensor-core chain needs tile-friendly shapes and the lane-grouped attention layout."""
@@ -134,15 +135,15 @@ class HEATLayer(nn.Module):
         w_kvq, b_kvq, wa, ba, skip, _ = self._packed(order)
         w_kvq_s, wa_s = self._packed_split(order)
         tpc = plan.type_ptr_c()
-        kvq, _ = ops.typed_linear_split(x_split, w_kvq_s, b_kvq, plan.type_ptr, 3 * D, type_ptr_c=tpc)
+        kvq, _ = ops.typed_linear_op(x_split, w_kvq_s, b_kvq, plan.type_ptr, 3 * D, type_ptr_c=tpc)
         agg_s = ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.attn_work(), plan.e_src,
                                      plan.e_sim, plan.e_rel, plan.node_inv_r, self.e_linear.weight,
-                                     self.e_linear.bias, D, H, split_out=True)
+                                     self.e_linear.bias, D, H, op_out=True)
         mask = None
         if self.training and self.drop.p > 0:
             mask = F.dropout(torch.ones((plan.N, D), dtype=torch.float32, device=x.device), self.drop.p, True)
-        return ops.typed_linear_split(agg_s, wa_s, ba, plan.type_ptr, D, skip=skip, res=x, row_gate=plan.node_inv_r,
-                                      drop_mask=mask, want_split=want_split, type_ptr_c=tpc)
+        return ops.typed_linear_op(agg_s, wa_s, ba, plan.type_ptr, D, skip=skip, res=x, row_gate=plan.node_inv_r,
+                                      drop_mask=mask, want_op=want_split, type_ptr_c=tpc)
 
     def forward_train(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
         """Differentiable layer (autograd.py): the packed weights are built WITH grad tracking so that the gradients
@@ -234,10 +235,11 @@ class _HEATBase(nn.Module):
         import ctypes
         from .. import _lib
         params = param_list(self, "all", self.parameters)
+        opf = ops.matmul_opf()
 
         def build():
             w_in, b_in = stack_linears(self.adapt_ws, order)
-            keep = [ops.split_bf16(w_in), b_in]
+            keep = [ops.to_operand(w_in, opf), b_in]
             L = len(self.gcs)
             arr = lambda: (ctypes.c_void_p * max(L, 1))()
             w_kvq, b_kvq, w_a, b_a, skip, e_w, e_b = arr(), arr(), arr(), arr(), arr(), arr(), arr()
@@ -252,6 +254,7 @@ class _HEATBase(nn.Module):
             keep += [M, c, b_total, w_kvq, b_kvq, w_a, b_a, skip, e_w, e_b]
             P = _lib.HeatParams()
             P.F, P.D, P.H, P.L = w_in.shape[2], w_in.shape[1], self.gcs[0].n_heads, L
+            P.opf = opf
             P.w_in_split, P.b_in = keep[0].data_ptr(), b_in.data_ptr()
             P.w_kvq_split, P.b_kvq, P.w_a_split, P.b_a, P.skip, P.e_w, P.e_b = w_kvq, b_kvq, w_a, b_a, skip, e_w, e_b
             P.pool_op, P.n_out = ops.POOL_OPS[self.graph_pooling_type], M.shape[1]
@@ -259,7 +262,7 @@ class _HEATBase(nn.Module):
             P.b_total = b_total.data_ptr() if b_total is not None else None
             return P, keep
 
-        return self._packs.get(("native", tuple(order), tuple(names), collapse_heads), params, build)
+        return self._packs.get(("native", opf, tuple(order), tuple(names), collapse_heads), params, build)
 
     def _forward_native(self, G: HeteroGraph, plan: GraphPlan, collapse_heads: bool, return_embeddings: bool):
         return self._forward_native_core(plan, packed_features(G, plan, None), G.independent, collapse_heads,
@@ -356,7 +359,7 @@ class _HEATBase(nn.Module):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         logits = torch.empty((plan.B, P.n_out), dtype=torch.float32, device=dev)
         x_out = torch.empty((plan.N, P.D), dtype=torch.float32, device=dev) if return_embeddings else None
-        rc = lib.wsi_heat_forward(feat.data_ptr(), feat.stride(0), ctypes.byref(g), ctypes.byref(P),
+        rc = lib.wsi_heat_forward(feat.data_ptr(), feat.stride(0), 0, ctypes.byref(g), ctypes.byref(P),
                                   x_out.data_ptr() if x_out is not None else None, P.D, logits.data_ptr(), P.n_out,
                                   ws.data_ptr(), ws_bytes, stream)
         _lib.check(rc, "wsi_heat_forward")
@@ -376,13 +379,14 @@ class _HEATBase(nn.Module):
             return plan, x
         F_in, D = int(x.shape[1]), int(w_in.shape[1])
         if len(self.gcs) > 0 and ops.tc_ok(plan.N, F_in, D) and all(l.tc_chain_ok(plan) for l in self.gcs):
-            # tensor-core chain on pre-split bf16 [hi; lo] operands: one conversion pass for the raw features,
-            # every later operand is emitted in split form by the kernel that produces it
-            w_in_s = self._packs.get(("in_split", tuple(order)), params, lambda: ops.split_bf16(w_in))
-            x, xs = ops.typed_linear_split(ops.split_bf16(x), w_in_s, b_in, plan.type_ptr, D, want_split=True,
+            # tensor-core chain on operands kept in operand form (ops.to_operand): one conversion pass for the raw
+            # features, every later operand is emitted in that form by the kernel that produces it
+            opf = ops.matmul_opf()
+            w_in_s = self._packs.get(("in_split", opf, tuple(order)), params, lambda: ops.to_operand(w_in, opf))
+            x, xs = ops.typed_linear_op(ops.to_operand(x), w_in_s, b_in, plan.type_ptr, D, want_op=True,
                                            type_ptr_c=plan.type_ptr_c())                     # HEATNet4.py:198-206
             for i, layer in enumerate(self.gcs):                                             # :213-214
-                x, xs = layer.forward_split(plan, x, xs, want_split=i + 1 < len(self.gcs))
+                x, xs = layer.forward_split(plan, x, xs, want_op=i + 1 < len(self.gcs))
             return plan, x
         x = ops.typed_linear(x, w_in, b_in, plan.type_ptr, type_ptr_c=plan.type_ptr_c())    # HEATNet4.py:198-206
         for layer in self.gcs:                                                               # :213-214

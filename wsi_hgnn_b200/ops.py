@@ -16,6 +16,57 @@ ACT_NONE, ACT_GELU = 0, 1
 POOL_OPS = {"sum": 0, "mean": 1, "max": 2}
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 
+# Operand formats of the tensor-core typed linear (WSI_OPF_*, include/wsi_hgnn.h) and the process-wide default
+# (the analogue of torch.backends.cuda.matmul.allow_tf32 - but measured, see profiles/r2_precision_study.json):
+#   "fp16"    one fp16 pass, fp32 accumulate: 11-bit significand = TF32's; the default of the fp32 models
+#   "bf16x3"  3-term bf16 split, ~2^-17 relative: "exact" mode; always used for gradient GEMMs
+#   "bf16"    one bf16 pass: the bf16-storage configuration (BASELINE config 3)
+OPF_BF16X3, OPF_F16, OPF_BF16 = 0, 1, 2
+_PRECISIONS = {"bf16x3": OPF_BF16X3, "fp16": OPF_F16, "bf16": OPF_BF16}
+_OPF_DTYPE = {OPF_BF16X3: torch.bfloat16, OPF_F16: torch.float16, OPF_BF16: torch.bfloat16}
+_opf_default = [OPF_F16]
+
+
+def set_matmul_precision(name: str) -> str:
+    """Operand precision of the tensor-core GEMMs of every later forward: "fp16" (default) | "bf16x3" | "bf16".
+    Returns the previous setting."""
+    if name not in _PRECISIONS:
+        raise ValueError(f"matmul precision must be one of {sorted(_PRECISIONS)}, got {name!r}")
+    prev = get_matmul_precision()
+    _opf_default[0] = _PRECISIONS[name]
+    return prev
+
+
+def get_matmul_precision() -> str:
+    return next(k for k, v in _PRECISIONS.items() if v == _opf_default[0])
+
+
+class matmul_precision:
+    """with ops.matmul_precision("bf16x3"): ...   (restores the previous setting on exit)"""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        self.prev = set_matmul_precision(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        set_matmul_precision(self.prev)
+
+
+def matmul_opf(opf: Optional[int] = None) -> int:
+    return _opf_default[0] if opf is None else int(opf)
+
+
+def operand_rows(rows: int, opf: int) -> int:
+    return 2 * rows if opf == OPF_BF16X3 else rows
+
+
+def dev_set(key: str, value: int):
+    """Development knob of the library (wsi_dev_set); not product API."""
+    _lib.check(_lib.load().wsi_dev_set(key.encode(), int(value)), "wsi_dev_set")
+
 import threading
 
 _cur_device = threading.local()      # cudaSetDevice is per host thread (the streaming evaluator plans on a worker thread)
@@ -55,7 +106,7 @@ def _vec(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
     return t.data_ptr()
 
 
-_DT_SIZE = {torch.int32: 4, torch.float32: 4, torch.uint8: 1, torch.int64: 8, torch.bfloat16: 2}
+_DT_SIZE = {torch.int32: 4, torch.float32: 4, torch.uint8: 1, torch.int64: 8, torch.bfloat16: 2, torch.float16: 2}
 
 
 def _arena(dev, specs):
@@ -88,9 +139,11 @@ def typed_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
                  act: int = ACT_NONE, skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
                  drop_mask: Optional[torch.Tensor] = None, row_gate: Optional[torch.Tensor] = None,
                  row_scale: Optional[torch.Tensor] = None, impl: int = IMPL_AUTO,
-                 out: Optional[torch.Tensor] = None, type_ptr_c=None) -> torch.Tensor:
-    """y[rows of type t] = epilogue(x[rows of type t] @ w[t].T); see wsi_typed_linear_f32."""
+                 out: Optional[torch.Tensor] = None, type_ptr_c=None, opf: Optional[int] = None) -> torch.Tensor:
+    """y[rows of type t] = epilogue(x[rows of type t] @ w[t].T); see wsi_typed_linear_f32.
+    opf: operand format of the tensor-core path (None = the process default, set_matmul_precision)."""
     lib = _lib.load()
+    opf = matmul_opf(opf)
     stream = _prep(x)
     T = len(type_ptr) - 1
     if w.dim() != 3 or w.shape[0] != T:
@@ -109,11 +162,11 @@ def typed_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
     yp, ldy = _rows(out, "out")
     rp, ldres = _rows(res, "res")
     mp, ldm = _rows(drop_mask, "drop_mask")
-    ws_bytes = lib.wsi_typed_linear_workspace_bytes(N, K, n_out, T, impl)
+    ws_bytes = lib.wsi_typed_linear_workspace_bytes(N, K, n_out, T, impl, opf)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
     tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
     rc = lib.wsi_typed_linear_f32(xp, ldx, wp, bp, K, n_out, tp, T, act, _vec(skip, "skip"), rp, ldres, mp, ldm,
-                                  _vec(row_gate, "row_gate"), _vec(row_scale, "row_scale"), yp, ldy, impl,
+                                  _vec(row_gate, "row_gate"), _vec(row_scale, "row_scale"), yp, ldy, impl, opf,
                                   ws.data_ptr() if ws is not None else None, ws_bytes, stream)
     _lib.check(rc, "wsi_typed_linear_f32")
     return out
@@ -124,46 +177,50 @@ def tc_ok(n_rows: int, K: int, n_out: int) -> bool:
     return bool(_lib.load().wsi_typed_linear_tc_ok(int(n_rows), int(K), int(n_out)))
 
 
-def split_bf16(x: torch.Tensor) -> torch.Tensor:
-    """fp32 [rows, K] -> bf16 [2 * rows, K] = [hi; lo] with x = hi + lo (wsi_split_bf16): the operand form of
-    typed_linear_split.  A weight stack [T, n_out, K] is split as [T * n_out, K]."""
+def to_operand(x: torch.Tensor, opf: Optional[int] = None) -> torch.Tensor:
+    """fp32 [rows, K] -> the operand form of typed_linear_op (wsi_to_operand): bf16 [2 * rows, K] = [hi; lo] with
+    x = hi + lo (OPF_BF16X3), fp16 [rows, K] (OPF_F16) or bf16 [rows, K] (OPF_BF16).  A weight stack [T, n_out, K] is
+    converted as [T * n_out, K].  opf None = the process default (set_matmul_precision)."""
     lib = _lib.load()
     stream = _prep(x)
+    opf = matmul_opf(opf)
     if x.dim() == 3:
         x = x.reshape(-1, x.shape[-1])
     xp, ld = _rows(x, "x")
     rows, K = int(x.shape[0]), int(x.shape[1])
-    out = torch.empty((2 * rows, K), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.wsi_split_bf16(xp, ld, rows, K, out.data_ptr(), stream), "wsi_split_bf16")
+    out = torch.empty((operand_rows(rows, opf), K), dtype=_OPF_DTYPE[opf], device=x.device)
+    _lib.check(lib.wsi_to_operand(xp, ld, rows, K, opf, out.data_ptr(), stream), "wsi_to_operand")
     return out
 
 
-def typed_linear_split(x_split: torch.Tensor, w_split: torch.Tensor, bias: Optional[torch.Tensor],
-                       type_ptr: Sequence[int], n_out: int, *, act: int = ACT_NONE,
-                       skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
-                       drop_mask: Optional[torch.Tensor] = None, row_gate: Optional[torch.Tensor] = None,
-                       row_scale: Optional[torch.Tensor] = None, want_y: bool = True, want_split: bool = False,
-                       type_ptr_c=None):
-    """tcgen05 typed linear on pre-split bf16 operands; see wsi_typed_linear_split.
-    -> y fp32 [N, n_out] (or None), y_split bf16 [2N, n_out] (or None)."""
+def typed_linear_op(x_op: torch.Tensor, w_op: torch.Tensor, bias: Optional[torch.Tensor],
+                    type_ptr: Sequence[int], n_out: int, *, act: int = ACT_NONE,
+                    skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+                    drop_mask: Optional[torch.Tensor] = None, row_gate: Optional[torch.Tensor] = None,
+                    row_scale: Optional[torch.Tensor] = None, want_y: bool = True, want_op: bool = False,
+                    type_ptr_c=None, opf: Optional[int] = None):
+    """tcgen05 typed linear on operands already in operand form (to_operand); see wsi_typed_linear_op.
+    -> y fp32 [N, n_out] (or None), y in operand form (or None)."""
     lib = _lib.load()
-    stream = _prep(x_split)
+    stream = _prep(x_op)
+    opf = matmul_opf(opf)
     T = len(type_ptr) - 1
-    N, K = int(type_ptr[-1]), int(x_split.shape[1])
-    for name, t, rows in (("x_split", x_split, 2 * N), ("w_split", w_split, 2 * T * n_out)):
-        if t.dtype != torch.bfloat16 or not t.is_contiguous() or tuple(t.shape) != (rows, K):
-            raise ValueError(f"typed_linear_split: {name} must be a contiguous bf16 [{rows}, {K}] tensor, "
+    N, K = int(type_ptr[-1]), int(x_op.shape[1])
+    dt = _OPF_DTYPE[opf]
+    for name, t, rows in (("x_op", x_op, operand_rows(N, opf)), ("w_op", w_op, operand_rows(T * n_out, opf))):
+        if t.dtype != dt or not t.is_contiguous() or tuple(t.shape) != (rows, K):
+            raise ValueError(f"typed_linear_op: {name} must be a contiguous {dt} [{rows}, {K}] tensor, "
                              f"got {t.dtype} {tuple(t.shape)}")
-    y = torch.empty((N, n_out), dtype=torch.float32, device=x_split.device) if want_y else None
-    ys = torch.empty((2 * N, n_out), dtype=torch.bfloat16, device=x_split.device) if want_split else None
+    y = torch.empty((N, n_out), dtype=torch.float32, device=x_op.device) if want_y else None
+    ys = torch.empty((operand_rows(N, opf), n_out), dtype=dt, device=x_op.device) if want_op else None
     rp, ldres = _rows(res, "res")
     mp, ldm = _rows(drop_mask, "drop_mask")
     tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
-    rc = lib.wsi_typed_linear_split(x_split.data_ptr(), w_split.data_ptr(), _vec(bias, "bias"), K, n_out, tp, T, act,
-                                    _vec(skip, "skip"), rp, ldres, mp, ldm, _vec(row_gate, "row_gate"),
-                                    _vec(row_scale, "row_scale"), y.data_ptr() if y is not None else None, n_out,
-                                    ys.data_ptr() if ys is not None else None, stream)
-    _lib.check(rc, "wsi_typed_linear_split")
+    rc = lib.wsi_typed_linear_op(x_op.data_ptr(), w_op.data_ptr(), _vec(bias, "bias"), K, n_out, tp, T, act,
+                                 _vec(skip, "skip"), rp, ldres, mp, ldm, _vec(row_gate, "row_gate"),
+                                 _vec(row_scale, "row_scale"), y.data_ptr() if y is not None else None, n_out,
+                                 ys.data_ptr() if ys is not None else None, opf, stream)
+    _lib.check(rc, "wsi_typed_linear_op")
     return y, ys
 
 
@@ -192,19 +249,20 @@ def hetero_attn(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, rowptr: torch
 def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: dict, e_src: torch.Tensor,
                      e_sim: torch.Tensor, e_rel: torch.Tensor, node_inv_r: torch.Tensor, e_w: torch.Tensor,
                      e_b: torch.Tensor, D: int, H: int, out: Optional[torch.Tensor] = None,
-                     split_out: bool = False) -> torch.Tensor:
+                     op_out: bool = False, opf: Optional[int] = None) -> torch.Tensor:
     """HEAT edge attention driven by the hub-balancing work list of GraphPlan.attn_work();
     see wsi_hetero_attn_work_fwd.  k/v/q/agg columns are in the head_perm(D, H) order.
-    split_out: return the result as bf16 [2N, D] = [hi; lo] (operand of typed_linear_split) instead of fp32."""
+    op_out: return the result in operand form (to_operand layout, the A operand of typed_linear_op) instead of fp32."""
     lib = _lib.load()
     stream = _prep(q)
+    opf = matmul_opf(opf)
     N = int(q.shape[0])
     kp, ldk = _rows(k, "k")
     vp, ldv = _rows(v, "v")
     qp, ldq = _rows(q, "q")
     agg = agg_split = None
-    if split_out:
-        agg_split = torch.empty((2 * N, D), dtype=torch.bfloat16, device=q.device)
+    if op_out:
+        agg_split = torch.empty((operand_rows(N, opf), D), dtype=_OPF_DTYPE[opf], device=q.device)
         ap, ldo = None, D
     else:
         agg = out if out is not None else torch.empty((N, D), dtype=torch.float32, device=q.device)
@@ -226,9 +284,9 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
                                       _vec(work.get("sched"), "sched", torch.int32), n_split, n_part,
                                       part_ms.data_ptr() if part_ms is not None else None,
                                       part_acc.data_ptr() if part_acc is not None else None, ap, ldo,
-                                      agg_split.data_ptr() if agg_split is not None else None, stream)
+                                      agg_split.data_ptr() if agg_split is not None else None, opf, stream)
     _lib.check(rc, "wsi_hetero_attn_work_fwd")
-    return agg_split if split_out else agg
+    return agg_split if op_out else agg
 
 
 def hetero_attn_bwd(k, v, q, rowptr, e_src, e_sim, e_rel, node_inv_r, e_w, e_b, D: int, H: int, d_agg: torch.Tensor,
