@@ -48,7 +48,8 @@ class TypedLinearFn(torch.autograd.Function):
         w = w.contiguous()
         ctx.save_for_backward(x, w)
         ctx.type_ptr, ctx.type_ptr_c, ctx.has_bias = list(type_ptr), type_ptr_c, b is not None
-        return ops.typed_linear(x, w, b.contiguous() if b is not None else None, type_ptr, type_ptr_c=type_ptr_c)
+        return ops.typed_linear(x, w, b.contiguous() if b is not None else None, type_ptr, type_ptr_c=type_ptr_c,
+                                opf=ops.train_opf())
 
     @staticmethod
     def backward(ctx, dy):

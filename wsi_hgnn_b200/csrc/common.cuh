@@ -99,6 +99,7 @@ __device__ __forceinline__ void wsi_pdl_trigger() { asm volatile("griddepcontrol
 // WSI_ATTN_STATIC, WSI_NO_PDL) and settable through wsi_dev_set(); no launch path calls getenv().  Not product API.
 struct WsiDev {
   int tc_debug;            // typed_linear_tc_kernel: see TcArgs::dbg
+  int tc_no_tma_store;     // typed_linear_tc_kernel: plain epilogue through per-lane global stores instead of TMA stores
   int attn_debug;          // attention kernels: see AttnArgs::dbg
   int attn_kernel;         // 0 = chosen per launch (default), 1 = register path, 2 = TMA ring, 3 = TMA pipe
   int attn_ring;           // ring depth of the TMA kernels (0 = default)

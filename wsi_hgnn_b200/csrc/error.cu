@@ -53,7 +53,7 @@ WsiDev* wsi_dev() { return &g_dev; }
 extern "C" int wsi_dev_set(const char* key, int value) {
   WSI_CHECK_ARG(key, "dev_set: null key");
   struct { const char* k; int* p; } tab[] = {
-      {"tc_debug", &g_dev.tc_debug}, {"attn_debug", &g_dev.attn_debug}, {"attn_kernel", &g_dev.attn_kernel},
+      {"tc_debug", &g_dev.tc_debug}, {"tc_no_tma_store", &g_dev.tc_no_tma_store}, {"attn_debug", &g_dev.attn_debug}, {"attn_kernel", &g_dev.attn_kernel},
       {"attn_ring", &g_dev.attn_ring}, {"attn_blocks", &g_dev.attn_blocks}, {"attn_cap", &g_dev.attn_cap},
       {"attn_separate_merge", &g_dev.attn_separate_merge}, {"attn_static", &g_dev.attn_static}, {"no_pdl", &g_dev.no_pdl}};
   for (auto& e : tab)

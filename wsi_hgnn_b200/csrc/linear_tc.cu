@@ -48,9 +48,12 @@ constexpr int EPI_WARPS = 8;                             // 2 warps per TMEM lan
 // Tile shapes that were built, verified bit-identical and measured in round 1 and do NOT ship any more (they lost):
 // 128-wide tiles with a 4-stage ring (more L2 -> smem operand bytes per flop) and a 4-CTA cluster sharing the A operand
 // by TMA multicast (no gain: only 132 of 148 SMs host 4-CTA clusters).  See DESIGN.md section 3.
-constexpr int stages_of(int terms) { return terms == 3 ? 3 : 6; }
+constexpr int stages_of(int terms) { return terms == 3 ? 3 : 5; }
 constexpr int stage_bytes_of(int terms) { return (terms == 3 ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES); }       // per CTA
-constexpr int smem_bytes_of(int terms) { return 1024 + stages_of(terms) * stage_bytes_of(terms) + EPI_WARPS * EPI_WARP_FLOATS * 4 + 256; }
+// epilogue staging: 4 KB (32 rows x 128 B) buffers per warp; the single-operand kernel has room for two (the TMA store
+// of chunk c drains while chunk c+1 is staged; the second one doubles as the 16-bit staging when y_op is written)
+constexpr int epi_bufs_of(int terms) { return terms == 3 ? 1 : 2; }
+constexpr int smem_bytes_of(int terms) { return 1024 + stages_of(terms) * stage_bytes_of(terms) + EPI_WARPS * epi_bufs_of(terms) * EPI_WARP_FLOATS * 4 + 256; }
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -103,6 +106,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t clu
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
 }
+// TMA tile store smem -> global (bulk async group of the issuing thread); the box is clipped at the tensor bounds
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (TMA) that reads them next
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // arrive (once the MMAs issued so far retire) on the barrier at this smem offset in BOTH CTAs of the pair
@@ -219,6 +233,7 @@ struct TcArgs {
   void* y_op;        // optional operand-form copy of y (the next GEMM's A operand): TERMS 3 bf16 [2 * n_rows, n_out]
                      // (hi; lo), TERMS 1 fp16 / bf16 [n_rows, n_out]
   uint32_t idesc;
+  int tma_store;     // y (and, TERMS 1, y_op) described by tmY / tmY16: the plain epilogue may use TMA stores
   int op_bf16;       // TERMS 1: 16-bit type of the operands and of y_op (0 = fp16, 1 = bf16)
   int dbg;           // development only (wsi_dev_set("tc_debug")): bit 0 = skip the MMAs, bit 1 = skip the TMA loads,
                      // bit 2 = skip the epilogue body, bit 3 = no global stores in the epilogue, bit 4 = no TMEM reads
@@ -247,15 +262,16 @@ __device__ __forceinline__ float4 epi_mix4(const LinearEpilogue& ep, float4 acc,
 template <bool FULL, bool GELU, int TERMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY16,
                        const __grid_constant__ TypeSegs segs, const __grid_constant__ LinearEpilogue ep, TcArgs a) {
-  constexpr int STAGES = stages_of(TERMS), STAGE_BYTES = stage_bytes_of(TERMS);
+  constexpr int STAGES = stages_of(TERMS), STAGE_BYTES = stage_bytes_of(TERMS), EPI_BUFS = epi_bufs_of(TERMS);
   constexpr int B_OFF = (TERMS == 3 ? 2 : 1) * A_TILE_BYTES;          // first W tile inside a stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* gen = smem_raw + (base - raw);
   float* epi_stage = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
-  const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_WARPS * EPI_WARP_FLOATS * 4;
+  const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUFS * EPI_WARP_FLOATS * 4;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES,
                  tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16;
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
@@ -271,9 +287,17 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    // full: the leader's expect_tx arrive + the peer's plain arrive; empty / tmem_full: one tcgen05.commit;
-    // tmem_empty (leader's is the one waited on): the epilogue warps of both CTAs
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+    if (a.tma_store) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+      if (a.y_op) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY16) : "memory");
+    }
+    // full (the leader's is the one used): ONE arrival, the leader's expect_tx for the bytes of BOTH CTAs - the peer's
+    // loads post their bytes on it and need no arrival of their own (a phase completes only when the pending arrival
+    // AND the byte count reach zero, whichever CTA is ahead).  The peer used to add a release.cluster arrive per
+    // k-block: a MEMBAR + ERRBAR that drained its just-issued bulk loads, i.e. one full L2 round trip per k-block
+    // (measured round 2: "loads only" 28.7 us for 99 MB and 32.8 us for 198 MB - latency, not bytes).
+    // empty / tmem_full: one tcgen05.commit; tmem_empty (leader's is the one waited on): the epilogue warps of both CTAs
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -311,7 +335,6 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tma_load_2d(&tmB, fb, s0 + B_OFF, kb * BK, wrow0);
             if (TERMS == 3) tma_load_2d(&tmB, fb, s0 + B_OFF + B_TILE_BYTES, kb * BK, a.w_rows + wrow0);
           }
-          if (rank != 0) mbar_arrive_cluster(fb);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -356,7 +379,9 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===================================================================== epilogue warps
     // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the BN columns in halves.
     const int q = warp & 3, half = (warp - 2) >> 2;
-    float* stg = epi_stage + (warp - 2) * EPI_WARP_FLOATS;
+    float* stg = epi_stage + (warp - 2) * EPI_BUFS * EPI_WARP_FLOATS;
+    const uint32_t stg_u32 = smem_u32(stg);
+    uint32_t store_buf = 0;                                          // staging buffer of the next TMA store (EPI_BUFS == 2)
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
     const int rsub = lane >> 3, c4 = (lane & 7) << 2;
     constexpr int CHUNKS = BN / 32 / 2;                              // 32-column chunks per warp
@@ -366,6 +391,76 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int t = wsi_tile_group(segs, tm);
       const int row0 = segs.ptr[t] + (tm - segs.tile_start[t]) * PAIR_M + (int)rank * BM + q * 32;
       const int rows_left = segs.ptr[t + 1] - (row0 + rsub);         // this lane handles rows row0 + rsub + 4 it
+      // ---- plain epilogue through TMA stores (SASS UTMASTG): thread = accumulator row straight out of TMEM, + bias
+      // (+ GELU), one swizzled 16 B store per 4 columns into the warp's 4 KB staging buffer, then ONE bulk tensor store of
+      // the 32 x 32 chunk - no smem read-back, no per-lane global stores.  Warps whose 32 rows straddle the end of the
+      // node type (the next rows belong to another tile) and the FULL epilogue take the generic path below.
+      if (!FULL && a.tma_store && (TERMS == 1 || !a.y_op) && segs.ptr[t + 1] - row0 >= 32) {
+        const int col_w = tn * BN + half * (BN / 2);                 // first column of this warp
+        const float* bias_w = ep.bias ? ep.bias + (int64_t)t * ep.n_out : nullptr;
+        const bool two = EPI_BUFS == 2 && !a.y_op;                   // y double-buffered (else buffer 1 stages y_op)
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+        const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int col0 = col_w + c * 32;
+          if (col0 >= a.n_out) break;                                // warp-uniform
+          float v[32];
+          tc_ld_32x32(taddr + c * 32, v);
+          float4 bb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            bb[j] = (bias_w && col0 + 4 * j < a.n_out) ? __ldg(reinterpret_cast<const float4*>(bias_w + col0 + 4 * j)) : zero4;
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w;
+            if (GELU) { v[4 * j] = wsi_gelu(v[4 * j]); v[4 * j + 1] = wsi_gelu(v[4 * j + 1]); v[4 * j + 2] = wsi_gelu(v[4 * j + 2]); v[4 * j + 3] = wsi_gelu(v[4 * j + 3]); }
+          }
+          // the staging buffer is free once the bulk store that last read it has finished READING smem
+          if (lane == 0) { if (two) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+          __syncwarp();
+          if (ep.y) {
+            const uint32_t sb = stg_u32 + (two ? store_buf * (EPI_WARP_FLOATS * 4) : 0) + (uint32_t)lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((((uint32_t)j) ^ sw) << 4)), "f"(v[4 * j]),
+                           "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+          }
+          if (TERMS == 1 && a.y_op) {                                // 16-bit copy: two chunks fill one 128 B staging row
+            const uint32_t sb = stg_u32 + EPI_WARP_FLOATS * 4 + (uint32_t)lane * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint2 lo = a.op_bf16 ? pack4_bf16(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]))
+                                   : pack4_f16(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]));
+              uint2 hi = a.op_bf16 ? pack4_bf16(make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]))
+                                   : pack4_f16(make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((((uint32_t)((c & 1) * 4 + j)) ^ sw) << 4)),
+                           "r"(lo.x), "r"(lo.y), "r"(hi.x), "r"(hi.y) : "memory");
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (ep.y) tma_store_2d(&tmY, stg_u32 + (two ? store_buf * (EPI_WARP_FLOATS * 4) : 0), col0, row0);
+            if (TERMS == 1 && a.y_op && ((c & 1) || col0 + 32 >= a.n_out))
+              tma_store_2d(&tmY16, stg_u32 + EPI_WARP_FLOATS * 4, col0 & ~63, row0);
+            bulk_commit();
+          }
+          store_buf ^= 1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar + 8 * acc, 0));   // on the leader's barrier
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      if (a.tma_store) {                                             // the generic path reuses the staging buffer: drain first
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+      }
       const int n0 = tn * BN + half * (BN / 2) + c4;                 // this lane's first column
       const float alpha = (FULL && ep.skip) ? wsi_sigmoid(__ldg(ep.skip + t)) : 1.0f;
       float* yp = ep.y ? ep.y + (int64_t)(row0 + rsub) * ep.ldy + n0 : nullptr;
@@ -414,15 +509,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const bool n_ok = n0 + c * 32 < a.n_out;
         // issue every global load of this chunk before waiting on TMEM
         const float4 bb = bb_all[c];
-        float4 mm[8];
-        if (FULL) {
-          if (c + 1 < CHUNKS) load_res(c + 1, rr[(c + 1) & 1]);
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const bool ok = n_ok && it * 4 < rows_left;
-            mm[it] = (mask_p && ok) ? __ldg(reinterpret_cast<const float4*>(mask_p + (int64_t)it * 4 * ep.ldmask + c * 32)) : one4;
-          }
-        }
+        if (FULL && c + 1 < CHUNKS) load_res(c + 1, rr[(c + 1) & 1]);
         tc_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -432,7 +519,10 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int it = 0; it < 8; ++it) {
           if (n_ok && it * 4 < rows_left ) {
             const float4 accv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * EPI_LD + ((((lane & 7) ^ ((it * 4 + rsub) & 7))) << 2));
-            const float4 o = FULL ? epi_mix4<true, GELU>(ep, accv, bb, mm[it], rr[c & 1][it], alpha, gate[it] != 0.f, rscl[it])
+            // (the dropout mask - training only - is read where it is used: prefetching it next to the residual cost 32
+            //  registers and pushed the FULL epilogue into local-memory spills)
+            const float4 mk = (FULL && mask_p) ? __ldg(reinterpret_cast<const float4*>(mask_p + (int64_t)it * 4 * ep.ldmask + c * 32)) : one4;
+            const float4 o = FULL ? epi_mix4<true, GELU>(ep, accv, bb, mk, rr[c & 1][it], alpha, gate[it] != 0.f, rscl[it])
                                   : epi_mix4<false, GELU>(ep, accv, bb, one4, zero4, 1.f, true, 1.f);
             if (ep.y && !(a.dbg & 8)) *reinterpret_cast<float4*>(yp + (int64_t)it * 4 * ep.ldy + c * 32) = o;
             else if (a.dbg & 8) { if (o.x == 123456.789f) yp[0] = o.y; }       // development: no global stores (keep the math alive)
@@ -453,6 +543,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait_all();                       // this thread's TMA stores have landed
   tc_fence_before();
   __syncthreads();
   cluster_sync();                                                    // nobody touches the peer's smem / TMEM after this
@@ -480,15 +571,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 16-bit [rows, K] row-major, box [box_rows, BK], 128 B swizzle, out-of-bounds elements read as 0
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int K, int box_rows, bool bf16) {
+// [rows, cols] row-major (row pitch `pitch_bytes`), box [box_rows, box_cols] with box_cols * element size == 128 B,
+// 128 B swizzle, out-of-bounds elements read as 0 / not written
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch_bytes, int box_rows, int box_cols,
+             CUtensorMapDataType dt) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { wsi_set_error("typed_linear(tcgen05): cuTensorMapEncodeTiled is not available"); return WSI_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr),
                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { wsi_set_error("typed_linear(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r); return WSI_ERR_CUDA; }
@@ -550,19 +643,35 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
 
   const bool bf16 = opf != WSI_OPF_F16;
   const int m = terms_of(opf);
-  CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, a_ws, m * n_rows, K, BM, bf16);
+  const CUtensorMapDataType dt16 = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmA, tmB, tmY, tmY16;
+  int rc = make_map(&tmA, a_ws, m * n_rows, K, (int64_t)K * 2, BM, BK, dt16);
   if (rc != WSI_OK) return rc;
-  rc = make_map(&tmB, w_ws, m * (int64_t)T * n_out, K, BN / 2, bf16);
+  rc = make_map(&tmB, w_ws, m * (int64_t)T * n_out, K, (int64_t)K * 2, BN / 2, BK, dt16);
   if (rc != WSI_OK) return rc;
+  const bool full = ep.skip || ep.drop_mask || ep.row_scale;
+  // output maps of the TMA-store epilogue (plain epilogue only; column counts that are not a multiple of 4 - the padded
+  // k-NN dot-product matrix - keep the generic stores, whose last float4 may spill into the row padding)
+  const bool tma_store = !full && n_out % 4 == 0 && !wsi_dev()->tc_no_tma_store && (m == 1 || !y_op) && (!y_op || n_out % 8 == 0);
+  tmY = tmA; tmY16 = tmA;
+  if (tma_store) {
+    if (ep.y) {
+      rc = make_map(&tmY, ep.y, n_rows, n_out, ep.ldy * 4, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+      if (rc != WSI_OK) return rc;
+    }
+    if (y_op) {
+      rc = make_map(&tmY16, y_op, n_rows, n_out, (int64_t)n_out * 2, 32, 64, dt16);
+      if (rc != WSI_OK) return rc;
+    }
+  }
   TcArgs a{};
+  a.tma_store = tma_store ? 1 : 0;
   a.n_rows = (int)n_rows; a.w_rows = T * n_out; a.K = K; a.n_out = n_out;
   a.n_tiles_m = segs.tile_start[T]; a.n_tiles_n = (n_out + BN - 1) / BN;
   a.y_op = y_op;
   a.idesc = idesc_of(bf16);
   a.op_bf16 = bf16 ? 1 : 0;
   a.dbg = wsi_dev()->tc_debug;
-  const bool full = ep.skip || ep.drop_mask || ep.row_scale;
   const int total = a.n_tiles_m * a.n_tiles_n;
   if (total == 0) return WSI_OK;
   const int max_clusters = sms / 2;                                  // persistent: one CTA pair per two SMs
@@ -570,7 +679,7 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   const bool gelu = ep.act == WSI_ACT_GELU;       // compile-time in the kernel: the erf code must not sit (predicated off) in the plain epilogue
   const dim3 grid(2 * clusters), block(THREADS);
   cudaError_t le;
-#define TC_LAUNCH(F, G, TR) le = wsi_launch_pdl(typed_linear_tc_kernel<F, G, TR>, grid, block, smem_bytes_of(TR), stream, tmA, tmB, segs, ep, a)
+#define TC_LAUNCH(F, G, TR) le = wsi_launch_pdl(typed_linear_tc_kernel<F, G, TR>, grid, block, smem_bytes_of(TR), stream, tmA, tmB, tmY, tmY16, segs, ep, a)
   if (m == 2) {
     if (full && gelu) TC_LAUNCH(true, true, 3); else if (full) TC_LAUNCH(true, false, 3);
     else if (gelu) TC_LAUNCH(false, true, 3); else TC_LAUNCH(false, false, 3);

@@ -126,9 +126,9 @@ class HEATLayer(nn.Module):
         return (self.in_size == D and ops.head_perm(D, self.n_heads) is not None and
                 ops.tc_ok(plan.N, D, 3 * D) and ops.tc_ok(plan.N, D, D))
 
-    def forward_split(self, plan: GraphPlan, x: torch.Tensor, x_split: torch.Tensor, want_split: bool):
+    def forward_split(self, plan: GraphPlan, x: torch.Tensor, x_split: torch.Tensor, want_op: bool):
         """One layer on the pre-split chain: x fp32 [N, D] (residual) and its bf16 [hi; lo] form in, the same two
-        out (x_split only if `want_split`, i.e. another layer follows).  No fp32 -> bf16 conversion pass: the
+        out (x_split only if `want_op`, i.e. another layer follows).  No fp32 -> bf16 conversion pass: the
         attention kernel and the a_linear epilogue emit the split form directly."""
         D, H = self.out_size, self.n_heads
         order = _graph_type_order(plan, self.node_dict)
@@ -143,7 +143,7 @@ class HEATLayer(nn.Module):
         if self.training and self.drop.p > 0:
             mask = F.dropout(torch.ones((plan.N, D), dtype=torch.float32, device=x.device), self.drop.p, True)
         return ops.typed_linear_op(agg_s, wa_s, ba, plan.type_ptr, D, skip=skip, res=x, row_gate=plan.node_inv_r,
-                                      drop_mask=mask, want_op=want_split, type_ptr_c=tpc)
+                                      drop_mask=mask, want_op=want_op, type_ptr_c=tpc)
 
     def forward_train(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
         """Differentiable layer (autograd.py): the packed weights are built WITH grad tracking so that the gradients

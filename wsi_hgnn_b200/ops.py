@@ -59,6 +59,25 @@ def matmul_opf(opf: Optional[int] = None) -> int:
     return _opf_default[0] if opf is None else int(opf)
 
 
+# The differentiable (training) path keeps the 3-term split for its forward GEMMs too: with an fp16-rounded forward the
+# gradients of ill-conditioned parameters (e_linear.weight: a sum over all edges with heavy cancellation) moved by
+# 2e-2 relative against the fp64 oracle, outside the 2e-3 gradient-parity bar; set_train_matmul_precision("fp16")
+# trades that for speed.  Gradient GEMMs (dgrad / wgrad) always use the split.
+_train_opf = [OPF_BF16X3]
+
+
+def set_train_matmul_precision(name: str) -> str:
+    if name not in _PRECISIONS:
+        raise ValueError(f"matmul precision must be one of {sorted(_PRECISIONS)}, got {name!r}")
+    prev = next(k for k, v in _PRECISIONS.items() if v == _train_opf[0])
+    _train_opf[0] = _PRECISIONS[name]
+    return prev
+
+
+def train_opf() -> int:
+    return _train_opf[0]
+
+
 def operand_rows(rows: int, opf: int) -> int:
     return 2 * rows if opf == OPF_BF16X3 else rows
 
