@@ -189,8 +189,11 @@ int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_pt
                         int64_t n_rows, int D, float* agg, int64_t ldo, void* stream);
 
 /* Typed LayerNorm  models/HGT.py:123-124 (nn.LayerNorm(out_dim) per node type, eps 1e-5), in place allowed.
- *   gamma/beta [T, D]; rows of type t = [type_ptr_host[t], type_ptr_host[t+1]). */
-int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta,
+ *   gamma/beta [T, D]; rows of type t = [type_ptr_host[t], type_ptr_host[t+1]).
+ *   row_gate [N] or NULL: rows with gate == 0 are copied through un-normalised - the reference `continue`s before the
+ *   norm for a node type without incoming relation (models/HGT.py:118-120); per ROW because in a pack()ed batch that is
+ *   a per-(type, graph) property (pass node_inv_r). */
+int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, const float* row_gate,
                         const int32_t* type_ptr_host, int T, int D, float eps, float* y, int64_t ldy,
                         void* stream);
 
@@ -353,6 +356,24 @@ int64_t wsi_slide_forward_workspace_bytes(int64_t n_nodes, int64_t n_edges, int 
 int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
                       float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream,
                       void* stream);
+/* The same in two phases WITHOUT any host synchronisation inside the library, for a software-pipelined caller:
+ *   wsi_slide_plan : CSR build + work-list counting on plan_stream; the 4 totals are copied asynchronously to totals_host
+ *   wsi_slide_run  : after the caller has made sure plan_stream passed those copies (an event it recorded after
+ *                    wsi_slide_plan - in the streaming evaluator that event is a whole slide old): work-list fill on
+ *                    plan_stream, forward on `stream` behind an event.  Same desc / params / workspace in both calls. */
+int wsi_slide_plan(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
+                   void* workspace, int64_t workspace_bytes, void* plan_stream);
+int wsi_slide_run(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, const int32_t* totals_host,
+                  float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step of the data-parallel training path (BASELINE config 5): torch.optim.Adam(lr, weight_decay) as the
+ * reference builds it (parser.py:35-40; stepped by trainer/train_gnn.py:71) over ONE flat fp32 buffer of all
+ * parameters (wsi_hgnn_b200/parallel.py keeps parameters, gradients and both moments flat).
+ *   g' = grad * grad_scale + weight_decay * param;  exp_avg, exp_avg_sq updated in place;  step = 1, 2, ...;
+ *   zero_grad != 0 also clears grad (the next step's zero_grad()).  All buffers 16 B aligned, n elements. */
+int wsi_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,7 +59,7 @@ PROTOTYPES = {
     "wsi_head_perm": (_I, [_I, _I, _P]),
     "wsi_rel_transform": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _L, _P]),
     "wsi_segment_combine": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _P]),
-    "wsi_typed_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _F, _P, _L, _P]),
+    "wsi_typed_layernorm": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _F, _P, _L, _P]),
     "wsi_plan_workspace_bytes": (_L, [_L, _L]),
     "wsi_plan_build_csr": (_I, [_P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "wsi_plan_attn_work_count": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),
@@ -73,8 +73,11 @@ PROTOTYPES = {
     "wsi_edge_pearson": (_I, [_P, _L, _I, _P, _P, _L, _P, _P, _P]),
     "wsi_heat_forward_workspace_bytes": (_L, [_L, _I, _I, _L, _I, _I]),
     "wsi_heat_forward": (_I, [_P, _L, _I, POINTER(HeatGraph), POINTER(HeatParams), _P, _L, _P, _L, _P, _L, _P]),
+    "wsi_adam_step": (_I, [_P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _F, _I, _P]),
     "wsi_slide_forward_workspace_bytes": (_L, [_L, _L, _I, _I, _I, _L]),
     "wsi_slide_forward": (_I, [POINTER(SlideDesc), POINTER(HeatParams), _L, _P, _P, _L, _P, _L, _P, _P]),
+    "wsi_slide_plan": (_I, [POINTER(SlideDesc), POINTER(HeatParams), _L, _P, _P, _L, _P]),
+    "wsi_slide_run": (_I, [POINTER(SlideDesc), POINTER(HeatParams), _L, _P, _P, _L, _P, _L, _P, _P]),
 }
 
 _lib = None

@@ -128,16 +128,17 @@ extern "C" int64_t wsi_slide_forward_workspace_bytes(int64_t n_nodes, int64_t n_
   return slide_layout(n_nodes, n_edges, F, D, T, 16, max_part).total + 1024;
 }
 
-extern "C" int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
-                                 float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream,
-                                 void* stream) {
-  WSI_CHECK_ARG(s && p && totals_host && logits && workspace, "slide_forward: null pointer");
+// Phase 1 of a slide: CSR build + work-list counting on `plan_stream`, totals copied (asynchronously) into the caller's
+// pinned totals_host.  No host synchronisation: the caller waits for plan_stream (an event recorded after this call)
+// before phase 2 - in the streaming evaluator that wait is a whole slide old and never blocks.
+extern "C" int wsi_slide_plan(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
+                              void* workspace, int64_t workspace_bytes, void* plan_stream) {
+  WSI_CHECK_ARG(s && p && totals_host && workspace, "slide_plan: null pointer");
   const int64_t N = s->n_nodes, E = s->n_edges;
   WSI_CHECK_ARG(N > 0 && E > 0 && N < (1ll << 31) && E < (1ll << 31) && s->chunk == 16 && max_part >= 1,
-                "slide_forward: needs a non-empty slide, chunk 16 (N=%lld E=%lld chunk=%d)", (long long)N, (long long)E, s->chunk);
-  WSI_CHECK_ARG(plan_stream != stream, "slide_forward: plan_stream and stream must differ (the call synchronises plan_stream)");
+                "slide_plan: needs a non-empty slide, chunk 16 (N=%lld E=%lld chunk=%d)", (long long)N, (long long)E, s->chunk);
   const SlideLayout L = slide_layout(N, E, p->F, p->D, s->T, s->chunk, max_part);
-  WSI_CHECK_ARG(workspace_bytes >= L.total + 1024, "slide_forward: workspace of %lld bytes needed", (long long)(L.total + 1024));
+  WSI_CHECK_ARG(workspace_bytes >= L.total + 1024, "slide_plan: workspace of %lld bytes needed", (long long)(L.total + 1024));
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   auto at = [&](int64_t off) { return base + off; };
   int32_t* rowptr = reinterpret_cast<int32_t*>(at(L.rowptr));
@@ -148,8 +149,7 @@ extern "C" int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params*
   int32_t* chunk_base = reinterpret_cast<int32_t*>(at(L.chunk_base));
   int32_t* split_idx = reinterpret_cast<int32_t*>(at(L.split_idx));
   int32_t* hist = reinterpret_cast<int32_t*>(at(L.hist));
-  cudaStream_t ps = wsi_stream(plan_stream), ms = wsi_stream(stream);
-
+  cudaStream_t ps = wsi_stream(plan_stream);
   int rc = wsi_plan_build_csr(s->src, s->dst, s->sim, nullptr, s->rel_table, s->R, N, E, rowptr, e_src, e_sim, e_rel, nullptr,
                               stats, at(L.plan_ws), wsi_plan_workspace_bytes(N, E), plan_stream);
   if (rc) return rc;
@@ -159,23 +159,49 @@ extern "C" int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params*
   WSI_CHECK_CUDA(cudaMemcpyAsync(totals_host, chunk_base + N, 4, cudaMemcpyDeviceToHost, ps));
   WSI_CHECK_CUDA(cudaMemcpyAsync(totals_host + 1, split_idx + N, 4, cudaMemcpyDeviceToHost, ps));
   WSI_CHECK_CUDA(cudaMemcpyAsync(totals_host + 2, stats, 8, cudaMemcpyDeviceToHost, ps));
-  WSI_CHECK_CUDA(cudaStreamSynchronize(ps));                          // the one host read of the planner
+  return WSI_OK;
+}
+
+// Phase 2: totals_host is valid (plan_stream has passed the copies of phase 1): work-list fill on plan_stream, forward on
+// `stream` behind an event.
+extern "C" int wsi_slide_run(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, const int32_t* totals_host,
+                             float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream,
+                             void* stream) {
+  WSI_CHECK_ARG(s && p && totals_host && logits && workspace, "slide_run: null pointer");
+  const int64_t N = s->n_nodes, E = s->n_edges;
+  WSI_CHECK_ARG(plan_stream != stream, "slide_run: plan_stream and stream must differ");
+  const SlideLayout L = slide_layout(N, E, p->F, p->D, s->T, s->chunk, max_part);
+  WSI_CHECK_ARG(workspace_bytes >= L.total + 1024, "slide_run: workspace of %lld bytes needed", (long long)(L.total + 1024));
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  auto at = [&](int64_t off) { return base + off; };
+  int32_t* rowptr = reinterpret_cast<int32_t*>(at(L.rowptr));
+  int32_t* e_src = reinterpret_cast<int32_t*>(at(L.e_src));
+  float* e_sim = reinterpret_cast<float*>(at(L.e_sim));
+  uint8_t* e_rel = at(L.e_rel);
+  int32_t* chunk_base = reinterpret_cast<int32_t*>(at(L.chunk_base));
+  int32_t* split_idx = reinterpret_cast<int32_t*>(at(L.split_idx));
+  int32_t* hist = reinterpret_cast<int32_t*>(at(L.hist));
+  cudaStream_t ps = wsi_stream(plan_stream), ms = wsi_stream(stream);
   const int64_t n_part = totals_host[0], n_split = totals_host[1];
   if (totals_host[3] != 0) { wsi_set_error("slide_forward: edge endpoint out of range"); return WSI_ERR_ARG; }
   WSI_CHECK_ARG(n_part >= 0 && n_split >= 0 && n_split <= N && n_part <= max_part,
                 "slide_forward: %lld chunk partials exceed the workspace capacity %lld", (long long)n_part, (long long)max_part);
   int32_t* items = reinterpret_cast<int32_t*>(at(L.items));
   int32_t* zeroed = reinterpret_cast<int32_t*>(at(L.zeroed));
-  rc = wsi_plan_attn_work_fill(rowptr, e_rel, N, s->chunk, chunk_base, split_idx, n_part, n_split, hist, items,
-                               reinterpret_cast<int32_t*>(at(L.split_row)), reinterpret_cast<int32_t*>(at(L.split_ptr)),
-                               reinterpret_cast<int32_t*>(at(L.part_rel)), reinterpret_cast<int32_t*>(at(L.part_split)),
-                               plan_stream);
+  int rc = wsi_plan_attn_work_fill(rowptr, e_rel, N, s->chunk, chunk_base, split_idx, n_part, n_split, hist, items,
+                                   reinterpret_cast<int32_t*>(at(L.split_row)), reinterpret_cast<int32_t*>(at(L.split_ptr)),
+                                   reinterpret_cast<int32_t*>(at(L.part_rel)), reinterpret_cast<int32_t*>(at(L.part_split)),
+                                   plan_stream);
   if (rc) return rc;
   WSI_CHECK_CUDA(cudaMemsetAsync(zeroed, 0, (size_t)(N + 64) * 4, ps));   // arrival counters of the fused merge, queue words
-  static thread_local cudaEvent_t ev = nullptr;
-  if (!ev) WSI_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  WSI_CHECK_CUDA(cudaEventRecord(ev, ps));
-  WSI_CHECK_CUDA(cudaStreamWaitEvent(ms, ev, 0));
+  // one event per (thread, device): an event may only be recorded on a stream of the device it was created on
+  static thread_local cudaEvent_t evs[64] = {};
+  int dev = 0;
+  WSI_CHECK_CUDA(cudaGetDevice(&dev));
+  WSI_CHECK_ARG(dev >= 0 && dev < 64, "slide_run: device index %d out of range", dev);
+  if (!evs[dev]) WSI_CHECK_CUDA(cudaEventCreateWithFlags(&evs[dev], cudaEventDisableTiming));
+  WSI_CHECK_CUDA(cudaEventRecord(evs[dev], ps));
+  WSI_CHECK_CUDA(cudaStreamWaitEvent(ms, evs[dev], 0));
 
   wsi_heat_graph g{};
   g.n_rows = N; g.T = s->T; g.B = 1; g.type_ptr_host = s->type_ptr_host; g.seg_ptr = s->seg_ptr;
@@ -187,4 +213,15 @@ extern "C" int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params*
   g.n_split = n_split; g.n_part = n_part;
   return wsi_heat_forward(s->feat, s->ldf, s->feat_is_op, &g, p, nullptr, 0, logits, ldl, at(L.fwd),
                           wsi_heat_forward_workspace_bytes(N, p->F, p->D, max_part, s->T, 1), stream);
+}
+
+// Both phases in one call, with the one host synchronisation of plan_stream in between.
+extern "C" int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
+                                 float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream,
+                                 void* stream) {
+  WSI_CHECK_ARG(logits && plan_stream != stream, "slide_forward: plan_stream and stream must differ (the call synchronises plan_stream)");
+  int rc = wsi_slide_plan(s, p, max_part, totals_host, workspace, workspace_bytes, plan_stream);
+  if (rc) return rc;
+  WSI_CHECK_CUDA(cudaStreamSynchronize(wsi_stream(plan_stream)));       // the one host read of the planner
+  return wsi_slide_run(s, p, max_part, totals_host, logits, ldl, workspace, workspace_bytes, plan_stream, stream);
 }

@@ -239,14 +239,21 @@ int pool_splits(int64_t n_rows, int64_t n_seg, int D) {
 // Typed LayerNorm (reference models/HGT.py:123-124): one warp per row, two-pass mean / variance.
 __global__ void __launch_bounds__(256)
 typed_layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, TypeSegs segs, int D, float eps, float* __restrict__ y,
-                       int64_t ldy) {
+                       const float* __restrict__ beta, const float* __restrict__ row_gate, TypeSegs segs, int D, float eps,
+                       float* __restrict__ y, int64_t ldy) {
   const int lane = threadIdx.x & 31;
   const int n_rows = segs.ptr[segs.T];
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 8) {
     int t = 0;
     while (t + 1 < segs.T && row >= segs.ptr[t + 1]) ++t;
     const float* xr = x + (int64_t)row * ldx;
+    if (row_gate && __ldg(row_gate + row) == 0.f) {       // passthrough row (no incoming relation): not normalised
+      if (y != x || ldy != ldx) {
+        float* yr = y + (int64_t)row * ldy;
+        for (int c = lane; c < D; c += 32) yr[c] = xr[c];
+      }
+      continue;
+    }
     float s = 0.f;
     for (int c = lane; c < D; c += 32) s += xr[c];
 #pragma unroll
@@ -354,8 +361,8 @@ extern "C" int wsi_segment_pool_affine_fwd(const float* x, int64_t ldx, const in
 }
 
 extern "C" int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta,
-                                   const int32_t* type_ptr_host, int T, int D, float eps, float* y, int64_t ldy,
-                                   void* stream) {
+                                   const float* row_gate, const int32_t* type_ptr_host, int T, int D, float eps, float* y,
+                                   int64_t ldy, void* stream) {
   WSI_CHECK_ARG(x && gamma && beta && y && type_ptr_host, "typed_layernorm: null pointer");
   TypeSegs segs;
   WSI_CHECK_ARG(wsi_make_segs(&segs, type_ptr_host, T, 1) == 0, "typed_layernorm: bad type_ptr (T=%d)", T);
@@ -363,7 +370,7 @@ extern "C" int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gam
   if (n_rows == 0) return WSI_OK;
   int blocks = (n_rows + 7) / 8;
   { const int sms = wsi_num_sms(); if (sms <= 0) return WSI_ERR_CUDA; if (blocks > sms * 16) blocks = sms * 16; }
-  typed_layernorm_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(x, ldx, gamma, beta, segs, D, eps, y, ldy);
+  typed_layernorm_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(x, ldx, gamma, beta, row_gate, segs, D, eps, y, ldy);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }

@@ -616,6 +616,16 @@ class HeteroGraph:
     def invalidate_plan(self):
         self._plan = None
 
+    def _edata_signature(self, name: str):
+        flat = getattr(self, "_flat_edges", None)
+        if flat is not None:                            # flat-format graph: one tensor behind every relation's view
+            return (flat[2].data_ptr(), flat[2]._version, len(self._edata))
+        return tuple((fr[name].data_ptr(), fr[name]._version) if name in fr else None for fr in self._edata.values())
+
+    def ndata_signature(self, name: str):
+        """(data_ptr, version) of every node type's `name` tensor: changes when a feature is replaced or written in place."""
+        return tuple((fr[name].data_ptr(), fr[name]._version) if name in fr else None for fr in self._ndata.values())
+
     def plan(self, sim_name: str = "sim") -> GraphPlan:
         """Build (once) the device layout the kernels consume; see :class:`GraphPlan`.
 
@@ -623,10 +633,16 @@ class HeteroGraph:
         reference (construct_graph/graph_constructor.py:285-297; [DGL-mem] HeteroGraph::GetCSCMatrix).
         """
         if self._plan is not None:
-            return self._plan
+            # the plan bakes the edge attribute into the CSR: a write to G.edata[sim_name] since then (a new tensor or an
+            # in-place update - both visible as (data_ptr, _version)) makes it stale; the reference re-reads
+            # G.edata['sim'] on every forward (models/HEATNet4.py:209-210)
+            if getattr(self._plan, "_sim_sig", None) == self._edata_signature(sim_name):
+                return self._plan
+            self._plan = None
         dev = self.device
         p = GraphPlan()
         p.device = dev
+        p._sim_sig = self._edata_signature(sim_name)
         p.ntypes = list(self.ntypes)
         p.rel_list = list(self.canonical_etypes)
         if len(p.rel_list) > 255:

@@ -40,9 +40,15 @@ def _graph_type_order(plan: GraphPlan, node_dict: Dict[str, int]):
 def packed_features(G: HeteroGraph, plan: GraphPlan, h: Optional[Dict[str, torch.Tensor]], name: str = "feat"):
     """[N, F] type-major packed input features (G.nodes[nt].data['feat'] or the caller's dict)."""
     if h is None:
-        if name not in plan.cache:
-            plan.cache[name] = G.packed_ndata(name, torch.float32)
-        return plan.cache[name]
+        # cached per plan, keyed by the identity + version of the per-type tensors: a later write to
+        # G.nodes[nt].data['feat'] (feature masking, in-place normalisation) must be seen, as in the reference, which
+        # re-reads the features on every forward (models/HEATNet4.py:198-206)
+        sig = G.ndata_signature(name)
+        hit = plan.cache.get(name)
+        if hit is None or hit[0] != sig:
+            hit = (sig, G.packed_ndata(name, torch.float32))
+            plan.cache[name] = hit
+        return hit[1]
     parts = [h[nt].to(torch.float32) for nt in plan.ntypes if G.num_nodes(nt) > 0]
     return torch.cat(parts, 0).contiguous()
 
@@ -277,11 +283,12 @@ class _HEATBase(nn.Module):
             return None
         return self._forward_native_core(plan, feat, independent, hasattr(self, "head"), False)
 
-    def slide_forward_native(self, slide, blob: torch.Tensor, head: torch.Tensor, slot: Dict, plan_stream, main_stream):
-        """Blob -> logits of ONE flat slide through wsi_slide_forward (planner + forward in one host call).  `head` = the
-        slide's plan head (FlatSlide._plan_head) on the device, `slot` = per-buffer scratch ({'ws', 'totals'}) recycled by
-        the caller once the slide's forward has finished.  -> logits [1, out] (on `main_stream`), or None when the shapes
-        are not the driver's (the caller then takes the generic path)."""
+    def slide_plan_native(self, slide, blob: torch.Tensor, head: torch.Tensor, slot: Dict, plan_stream):
+        """Phase 1 of blob -> logits of ONE flat slide (wsi_slide_plan: CSR + work-list counting enqueued on `plan_stream`,
+        totals on their way to pinned host memory; nothing waits).  `head` = the slide's plan head (FlatSlide._plan_head)
+        on the device, `slot` = per-buffer scratch ({'ws', 'totals'}) recycled by the caller once the slide's forward has
+        finished.  -> an opaque state for slide_run_native, or None when the shapes are not the driver's (the caller then
+        takes the generic path)."""
         import ctypes
         from types import SimpleNamespace
         from .. import _lib
@@ -295,7 +302,10 @@ class _HEATBase(nn.Module):
             return None
         names = list(hd["ntypes"])
         order = [self.node_dict[nt] for nt in names]
-        P, _keep = self._native_params(None, order, names, hasattr(self, "head"))
+        P0, _keep = self._native_params(None, order, names, hasattr(self, "head"))
+        if slide.feat_is_fp16() and P0.opf != ops.OPF_F16:
+            return None                                         # fp16 features + another operand format: generic path
+        P = _lib.HeatParams.from_buffer_copy(P0)                # per-slide copy: seg_scale points into this slide's head
         D = P.D
         key = (N, E, F, D, T)
         if slot.get("key") != key:
@@ -303,11 +313,11 @@ class _HEATBase(nn.Module):
             slot["ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=blob.device)
             slot["ws_bytes"], slot["key"] = ws_bytes, key
             slot["totals"] = torch.zeros(4, dtype=torch.int32).pin_memory()
-            slot["tpc"] = None
         off, base = hdr["off"], blob.data_ptr()
         hp = head.data_ptr()
         d = _lib.SlideDesc()
         d.feat, d.ldf = base + off["feat"], F
+        d.feat_is_op = 1 if slide.feat_is_fp16() else 0
         d.src, d.dst, d.sim = base + off["src"], base + off["dst"], base + off["sim"]
         d.seg_ptr = hp
         d.rel_table = hp + 4 * hd["n0"]
@@ -317,11 +327,32 @@ class _HEATBase(nn.Module):
         d.n_nodes, d.n_edges, d.T, d.R, d.chunk = N, E, T, R, 16
         P.seg_scale = hp + 4 * hd["n1"]
         ops._prep(blob)
+        rc = lib.wsi_slide_plan(ctypes.byref(d), ctypes.byref(P), E, slot["totals"].data_ptr(), slot["ws"].data_ptr(),
+                                slot["ws_bytes"], plan_stream.cuda_stream)
+        _lib.check(rc, "wsi_slide_plan")
+        return (d, P, tpc, _keep, E, blob, head)
+
+    def slide_run_native(self, state, slot: Dict, plan_stream, main_stream) -> torch.Tensor:
+        """Phase 2 (wsi_slide_run): the caller has waited for the event it recorded on `plan_stream` after phase 1, so the
+        totals are on the host; work-list fill + the whole forward are enqueued.  -> logits [1, out] (on `main_stream`)."""
+        import ctypes
+        from .. import _lib
+        lib = _lib.load()
+        d, P, _tpc, _keep, E, blob, _head = state
+        ops._prep(blob)
         logits = torch.empty((1, P.n_out), dtype=torch.float32, device=blob.device)
-        rc = lib.wsi_slide_forward(ctypes.byref(d), ctypes.byref(P), E, slot["totals"].data_ptr(), logits.data_ptr(), P.n_out,
-                                   slot["ws"].data_ptr(), slot["ws_bytes"], plan_stream.cuda_stream, main_stream.cuda_stream)
-        _lib.check(rc, "wsi_slide_forward")
+        rc = lib.wsi_slide_run(ctypes.byref(d), ctypes.byref(P), E, slot["totals"].data_ptr(), logits.data_ptr(), P.n_out,
+                               slot["ws"].data_ptr(), slot["ws_bytes"], plan_stream.cuda_stream, main_stream.cuda_stream)
+        _lib.check(rc, "wsi_slide_run")
         return logits
+
+    def slide_forward_native(self, slide, blob: torch.Tensor, head: torch.Tensor, slot: Dict, plan_stream, main_stream):
+        """Both phases back to back with one host wait on `plan_stream` in between (un-pipelined callers)."""
+        state = self.slide_plan_native(slide, blob, head, slot, plan_stream)
+        if state is None:
+            return None
+        plan_stream.synchronize()
+        return self.slide_run_native(state, slot, plan_stream, main_stream)
 
     def _forward_native_core(self, plan: GraphPlan, feat: torch.Tensor, independent: bool, collapse_heads: bool,
                              return_embeddings: bool):
@@ -351,7 +382,10 @@ class _HEATBase(nn.Module):
             ws_bytes = lib.wsi_heat_forward_workspace_bytes(plan.N, P.F, P.D, w["n_part"], len(names), plan.B)
             plan.cache[key] = (g, scale, ws_bytes, tpc, w)
         g, scale, ws_bytes, _, _ = plan.cache[key]
-        if feat.dtype != torch.float32 or feat.stride(1) != 1:
+        feat_is_op = 0
+        if feat.dtype == torch.float16 and P.opf == ops.OPF_F16 and feat.is_contiguous() and feat.data_ptr() % 128 == 0:
+            feat_is_op = 1                                      # fp16 features of a flat slide: already the GEMM's operand
+        elif feat.dtype != torch.float32 or feat.stride(1) != 1:
             feat = feat.float().contiguous()
         stream = ops._prep(feat)
         P.seg_scale = scale.data_ptr()
@@ -359,7 +393,7 @@ class _HEATBase(nn.Module):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         logits = torch.empty((plan.B, P.n_out), dtype=torch.float32, device=dev)
         x_out = torch.empty((plan.N, P.D), dtype=torch.float32, device=dev) if return_embeddings else None
-        rc = lib.wsi_heat_forward(feat.data_ptr(), feat.stride(0), 0, ctypes.byref(g), ctypes.byref(P),
+        rc = lib.wsi_heat_forward(feat.data_ptr(), feat.stride(0), feat_is_op, ctypes.byref(g), ctypes.byref(P),
                                   x_out.data_ptr() if x_out is not None else None, P.D, logits.data_ptr(), P.n_out,
                                   ws.data_ptr(), ws_bytes, stream)
         _lib.check(rc, "wsi_heat_forward")

@@ -130,23 +130,10 @@ class HGTLayer(nn.Module):
 
 
 def _gated_layernorm(x, gamma, beta, plan: GraphPlan, tpc):
-    """LayerNorm on the rows of node types that have an incoming relation; other types pass through
-    (reference models/HGT.py:118-120 `continue`s before the norm)."""
-    if "ln_segments" not in plan.cache:
-        T = len(plan.ntypes)
-        live = []
-        for t in range(T):
-            a, b = plan.type_ptr[t], plan.type_ptr[t + 1]
-            live.append(b > a and bool((plan.node_inv_r[a:b] != 0).all().item()))
-        plan.cache["ln_segments"] = live
-    live = plan.cache["ln_segments"]
-    if all(live[t] or plan.type_ptr[t] == plan.type_ptr[t + 1] for t in range(len(live))):
-        return ops.typed_layernorm(x, gamma, beta, plan.type_ptr, type_ptr_c=tpc, inplace=True)
-    for t, ok in enumerate(live):
-        a, b = plan.type_ptr[t], plan.type_ptr[t + 1]
-        if ok:
-            ops.typed_layernorm(x[a:b], gamma[t:t + 1], beta[t:t + 1], [0, b - a], inplace=True)
-    return x
+    """LayerNorm on the rows that received a message; rows of a node type without incoming relation pass through
+    (reference models/HGT.py:118-120 `continue`s before the norm).  Gated per ROW by 1/R (0 = passthrough): in a
+    pack()ed batch "no incoming relation" is a property of the (type, graph) segment, not of the node type."""
+    return ops.typed_layernorm(x, gamma, beta, plan.type_ptr, type_ptr_c=tpc, inplace=True, row_gate=plan.node_inv_r)
 
 
 class HGT(nn.Module):

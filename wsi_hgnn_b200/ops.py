@@ -377,7 +377,8 @@ def segment_combine(msg, row_seg_ptr, node_inv_r, N: int, D: int):
     return agg
 
 
-def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, type_ptr_c=None, inplace=False):
+def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, type_ptr_c=None, inplace=False,
+                    row_gate: Optional[torch.Tensor] = None):
     lib = _lib.load()
     stream = _prep(x)
     T = len(type_ptr) - 1
@@ -388,8 +389,8 @@ def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, 
     y = x if inplace else torch.empty_like(x)
     yp, ldy = _rows(y, "y")
     tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
-    rc = lib.wsi_typed_layernorm(xp, ldx, _vec(gamma, "gamma"), _vec(beta, "beta"), tp, T, D, float(eps), yp, ldy,
-                                 stream)
+    rc = lib.wsi_typed_layernorm(xp, ldx, _vec(gamma, "gamma"), _vec(beta, "beta"), _vec(row_gate, "row_gate"), tp, T, D,
+                                 float(eps), yp, ldy, stream)
     _lib.check(rc, "wsi_typed_layernorm")
     return y
 

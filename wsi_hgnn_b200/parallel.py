@@ -1,16 +1,31 @@
 """Data-parallel training over the GPUs of one box: slides are sharded over ranks (sharding.py), every rank runs
-forward + backward on its own slides, and the ONE collective of the step is an all-reduce (sum) of a single flat fp32
-gradient buffer over NCCL / NVLink.  The reference has no distributed code at all
-(trainer/trainer.py:32-34 is single-device); this is the config-5 wrapper around its train_one_step
-(trainer/train_gnn.py:55-79)."""
-from typing import Iterable, List, Optional
+forward + backward on its own slides, and the ONE collective of the step is an all-reduce (sum) of the flat fp32
+gradient buffer over NCCL / NVLink, issued bucket by bucket WHILE the backward is still running.
+The reference has no distributed code at all (trainer/trainer.py:32-34 is single-device); this is the config-5
+wrapper around its train_one_step (trainer/train_gnn.py:55-79).
+
+Memory layout: `FlatModel` re-homes every trainable parameter into ONE flat fp32 buffer and gives it a gradient that is
+a view of a second flat buffer, so that
+  * autograd accumulates straight into the communication buffer (no pack / unpack launches),
+  * zero_grad is one memset (or free: fused into the optimizer kernel),
+  * Adam is ONE kernel of libwsi_hgnn.so over the four flat buffers (wsi_adam_step) instead of torch's
+    multi_tensor_apply chain over ~100 tensors,
+  * a bucket = a contiguous slice of the gradient buffer, all-reduced asynchronously as soon as the last gradient of
+    the slice has been accumulated (post-accumulate-grad hooks).
+"""
+from typing import Iterable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
 class FlatGradAllReduce:
-    """Packs the gradients of `params` into one flat buffer, all-reduces it once, unpacks in place."""
+    """Gradients of `params` as views of ONE flat buffer + a single all-reduce of it (the simple, non-overlapped form:
+    CPU / gloo tests, and the fallback of FlatModel for parameters whose gradient arrives out of bucket order)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -18,28 +33,127 @@ class FlatGradAllReduce:
         self.numel = sum(p.numel() for p in self.params)
         self.flat: Optional[torch.Tensor] = None
 
-    def __call__(self):
-        if not self.params:
-            return
-        dev, dt = self.params[0].device, torch.float32
+    def _adopt(self):
+        """(Re)point every p.grad at its slice of the flat buffer, keeping gradients that already exist."""
+        dev = self.params[0].device
         if self.flat is None or self.flat.device != dev:
-            self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
-        off = 0
-        for p in self.params:                           # parameters unused in the forward (HEATLayer.weight, attn.*)
-            n = p.numel()                               # have no grad: they contribute zeros
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
             n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
+            view = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                view.zero_()                            # unused in the forward (HEATLayer.weight, attn.*): zeros
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view                               # every rank ends up with the reduced gradient, used or not
             off += n
+
+    def __call__(self):
+        if not self.params:
+            return
+        self._adopt()
+        if _world(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class FlatModel:
+    """Flat parameter / gradient / Adam-state buffers of `model` with bucketed, overlapped gradient all-reduce."""
+
+    def __init__(self, model: torch.nn.Module, bucket_mb: float = 16.0, group=None):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatModel: the model has no trainable parameter")
+        self.group = group
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4           # 16 B aligned slices
+        self.numel = total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                n = p.numel()
+                self.flat_p[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[o:o + n].view_as(p)
+                p.grad = self.flat_g[o:o + n].view_as(p)
+        # buckets: contiguous slices, filled from the LAST parameter backwards (gradients arrive roughly in reverse
+        # registration order), each >= bucket_mb
+        limit = int(bucket_mb * (1 << 20) / 4)
+        self.buckets = []                               # (start, end, [param indices])
+        end, idx = total, []
+        for i in range(len(self.params) - 1, -1, -1):
+            idx.append(i)
+            if end - offs[i] >= limit or i == 0:
+                self.buckets.append((offs[i], end, list(idx)))
+                end, idx = offs[i], []
+        self.bucket_of = {}
+        for b, (_, _, ids) in enumerate(self.buckets):
+            for i in ids:
+                self.bucket_of[i] = b
+        self.expected = None                            # per bucket: parameters whose gradient arrived last step
+        self._seen = [set() for _ in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+        self.armed = False                              # hooks fire collectives only in the last micro-batch of a step
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i: int):
+        def hook(_p):
+            if not self.armed:
+                return
+            b = self.bucket_of[i]
+            self._seen[b].add(i)
+            if (self.expected is not None and not self._launched[b] and self._seen[b] >= self.expected[b]
+                    and _world(self.group) > 1):
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: int):
+        s, e, _ = self.buckets[b]
+        self._launched[b] = True
+        self._handles.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def arm(self):
+        """Call before the backward of the step's LAST micro-batch."""
+        self.armed = True
+        self._seen = [set() for _ in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+
+    def finish(self):
+        """After the last backward: reduce whatever the hooks did not (first step, parameters without a gradient), then
+        make the compute stream wait for every bucket."""
+        self.armed = False
+        if _world(self.group) > 1:
+            for b in range(len(self.buckets)):
+                if not self._launched[b]:
+                    self._launch(b)
+            for h in self._handles:
+                h.wait()
+        self.expected = [set(s) for s in self._seen]
+        self._handles = []
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def adam_step(self, lr: float, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                  grad_scale: float = 1.0, zero_grad: bool = True):
+        """torch.optim.Adam(lr, weight_decay) semantics (parser.py:35-40) over the flat buffers: one kernel."""
+        from . import _lib, ops
+        stream = ops._prep(self.flat_p)
+        self.step_count += 1
+        rc = _lib.load().wsi_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.numel, self.step_count, float(lr), float(betas[0]),
+                                       float(betas[1]), float(eps), float(weight_decay), float(grad_scale),
+                                       1 if zero_grad else 0, stream)
+        _lib.check(rc, "wsi_adam_step")
 
 
 def train_step(model, graphs, labels: torch.Tensor, global_batch: int, optimizer, reducer: FlatGradAllReduce,
@@ -58,3 +172,43 @@ def train_step(model, graphs, labels: torch.Tensor, global_batch: int, optimizer
     reducer()
     optimizer.step()
     return loss.detach()
+
+
+def flat_train_step(model, flat: FlatModel, micro_batches: Sequence, labels: Sequence[torch.Tensor], global_batch: int,
+                    lr: float, weight_decay: float, loss_fn=torch.nn.functional.cross_entropy, events=None) -> torch.Tensor:
+    """The same step on the flat buffers: `micro_batches` = this rank's slides as a list of packed HeteroGraphs (gradient
+    accumulation bounds the activation memory), bucketed all-reduce overlapped with the last backward, fused Adam.
+    events (optional): dict that receives CUDA events 'fwd' / 'bwd' / 'comm' / 'opt' lists of (start, end) pairs."""
+    total = None
+
+    def mark(kind, a, b):
+        if events is not None:
+            events.setdefault(kind, []).append((a, b))
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+    timed = events is not None and labels[0].is_cuda
+    for i, (G, y) in enumerate(zip(micro_batches, labels)):
+        if i + 1 == len(micro_batches):
+            flat.arm()
+        t0 = ev() if timed else None
+        logits = model(G)
+        loss = loss_fn(logits, y, reduction="sum") / float(global_batch)
+        t1 = ev() if timed else None
+        loss.backward()
+        t2 = ev() if timed else None
+        if timed:
+            mark("fwd", t0, t1)
+            mark("bwd", t1, t2)
+        total = loss.detach() if total is None else total + loss.detach()
+    t3 = ev() if timed else None
+    flat.finish()
+    t4 = ev() if timed else None
+    flat.adam_step(lr, weight_decay)
+    t5 = ev() if timed else None
+    if timed:
+        mark("comm", t3, t4)
+        mark("opt", t4, t5)
+    return total

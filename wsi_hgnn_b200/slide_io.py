@@ -4,7 +4,7 @@ The reference stores every slide as a pickled DGLHeteroGraph (get_graph.py:279-2
 evaluates one graph at a time with a synchronous `.to(device)` + D2H read per slide (evaluator/eval_homo_graph.py:
 61-95).  Here a slide is ONE contiguous byte blob + a small JSON-able header:
 
-    [ features  fp32 [N, F]  type-major packed (the GraphPlan row order) ]
+    [ features  fp32 or fp16 [N, F]  type-major packed (the GraphPlan row order) ]
     [ src       int64 [E]    local ids, relation-major (canonical_etypes order) ]
     [ dst       int64 [E] ]
     [ sim       fp32  [E] ]
@@ -47,7 +47,16 @@ class FlatSlide:
 
     # ------------------------------------------------------------------ construction
     @staticmethod
-    def from_graph(G: HeteroGraph, feat_name: str = "feat", sim_name: str = "sim", pin: bool = False) -> "FlatSlide":
+    def from_graph(G: HeteroGraph, feat_name: str = "feat", sim_name: str = "sim", pin: bool = False,
+                   feat_dtype: str = "fp32") -> "FlatSlide":
+        """feat_dtype "fp16": the features are stored as fp16 (round to nearest, clamped to +-65504) - exactly the operand
+        the default single-pass fp16 GEMM forms from fp32 features, so the logits are bit-identical while the blob (and
+        the host -> device copy that bounds the streamed path) is half the size; the tensor-core chain then reads the
+        features in place (no conversion pass)."""
+        if feat_dtype not in ("fp32", "fp16"):
+            raise ValueError("feat_dtype must be 'fp32' or 'fp16'")
+        fsz = 4 if feat_dtype == "fp32" else 2
+        fdt = torch.float32 if feat_dtype == "fp32" else torch.float16
         if G.batch_size != 1:
             raise ValueError("FlatSlide holds one slide; flatten the graphs before batching / packing them")
         ntypes, cets = list(G.ntypes), list(G.canonical_etypes)
@@ -58,7 +67,7 @@ class FlatSlide:
         e_per = [int(G._edges[ce][0].numel()) for ce in cets]
         E = sum(e_per)
         off_feat = 0
-        off_src = _align(off_feat + N * F * 4)
+        off_src = _align(off_feat + N * F * fsz)
         off_dst = _align(off_src + E * 8)
         off_sim = _align(off_dst + E * 8)
         nbytes = _align(off_sim + E * 4)
@@ -66,8 +75,10 @@ class FlatSlide:
         if pin and torch.cuda.is_available():
             blob = blob.pin_memory()
         if N * F:
-            blob[off_feat:off_feat + N * F * 4].view(torch.float32).view(N, F).copy_(
-                torch.cat([f.detach().to("cpu", torch.float32) for f in feats], 0))
+            allf = torch.cat([f.detach().to("cpu", torch.float32) for f in feats], 0)
+            if fsz == 2:
+                allf = allf.clamp(-65504.0, 65504.0)
+            blob[off_feat:off_feat + N * F * fsz].view(fdt).view(N, F).copy_(allf)
         if E:
             src = torch.cat([G._edges[ce][0].detach().to("cpu", torch.int64) for ce in cets])
             dst = torch.cat([G._edges[ce][1].detach().to("cpu", torch.int64) for ce in cets])
@@ -78,7 +89,7 @@ class FlatSlide:
             blob[off_sim:off_sim + E * 4].view(torch.float32).copy_(sim)
         header = {"format": "wsi_hgnn_b200.FlatSlide/1", "ntypes": ntypes, "num_nodes": n_per,
                   "canonical_etypes": [list(ce) for ce in cets], "num_edges": e_per, "feat_dim": F,
-                  "feat_name": feat_name, "sim_name": sim_name,
+                  "feat_name": feat_name, "sim_name": sim_name, "feat_dtype": feat_dtype,
                   "off": {"feat": off_feat, "src": off_src, "dst": off_dst, "sim": off_sim}, "nbytes": nbytes}
         return FlatSlide(header, blob)
 
@@ -117,7 +128,7 @@ class FlatSlide:
         off, F = h["off"], h["feat_dim"]
         n_per, e_per = h["num_nodes"], h["num_edges"]
         N, E = sum(n_per), sum(e_per)
-        feat = blob[off["feat"]:off["feat"] + N * F * 4].view(torch.float32).view(N, F)
+        feat = self._feat_view(blob)
         src = blob[off["src"]:off["src"] + E * 8].view(torch.int64)
         dst = blob[off["dst"]:off["dst"] + E * 8].view(torch.int64)
         sim = blob[off["sim"]:off["sim"] + E * 4].view(torch.float32)
@@ -135,6 +146,16 @@ class FlatSlide:
         G._packed_feat_view = feat                                # packed_ndata() returns it without a copy
         G._flat_edges = (src, dst, sim)                           # plan() reads them without concatenating
         return G
+
+    def feat_is_fp16(self) -> bool:
+        return self.header.get("feat_dtype", "fp32") == "fp16"
+
+    def _feat_view(self, blob: torch.Tensor) -> torch.Tensor:
+        h = self.header
+        N, F, o = sum(h["num_nodes"]), h["feat_dim"], h["off"]["feat"]
+        if self.feat_is_fp16():
+            return blob[o:o + N * F * 2].view(torch.float16).view(N, F)
+        return blob[o:o + N * F * 4].view(torch.float32).view(N, F)
 
     def _plan_head(self):
         """Host side of the plan of this (single) slide, computed once per FlatSlide: everything GraphPlan needs that
@@ -194,7 +215,7 @@ class FlatSlide:
         p.seg_ptr = p.type_ptr_dev = head[:hd["n0"]]
         p._rel_table = head[hd["n0"]:hd["n1"]].view(3, R + 1)
         p.node_inv_r = head[hd["n1p"]:].view(torch.float32)
-        feat = blob[off["feat"]:off["feat"] + N * F * 4].view(torch.float32).view(N, F)
+        feat = self._feat_view(blob)
         if E == 0:
             p.e_src = torch.zeros(0, dtype=torch.int32, device=dev)
             p.e_sim = torch.zeros(0, dtype=torch.float32, device=dev)
@@ -252,7 +273,7 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("stream_forward needs a CUDA device (there is no CPU fallback)")
-    nbuf = max(3, int(depth))
+    nbuf = max(4, int(depth))
     main = torch.cuda.current_stream(dev)
     # streams and device blob buffers persist across calls (per device): a new stream per call would make the caching
     # allocator cudaMalloc fresh buffers every time, and cudaMalloc stalls for tens of ms once CUDA graphs exist
@@ -334,42 +355,65 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
     # blob -> logits in ONE host call per slide (wsi_slide_forward: planner + forward issued from C; measured 0.89-0.95
     # against 1.13-1.15 ms / slide for the Python-issued stages on the same box).  WSI_STREAM_NATIVE=0 (development knob)
     # or `threaded` select the Python-issued stages.
-    native = (hasattr(model, "slide_forward_native") and os.environ.get("WSI_STREAM_NATIVE", "1") != "0" and not threaded)
+    native = (hasattr(model, "slide_plan_native") and os.environ.get("WSI_STREAM_NATIVE", "1") != "0" and not threaded)
     try:
         if native:
+            # software pipeline, one slide apart per stage, no host wait on anything younger than a whole slide:
+            #   upload(i + 2)  ->  plan(i + 1): wsi_slide_plan (CSR + counting, totals -> pinned host, event)  ->
+            #   run(i): wait for slide i's plan event (recorded one iteration ago), wsi_slide_run (fill + forward), logits D2H
             slots = ctx.setdefault("slots", [dict() for _ in range(nbuf)])
             free_ev: List[Optional[torch.cuda.Event]] = [None] * nbuf
             it = iter(slides)
-            nxt_s = next(it, None)
-            staged = upload(0, nxt_s, None) if nxt_s is not None else None
-            i = 0
-            while staged is not None:
-                s, k, uploaded = staged
-                nxt_s = next(it, None)
-                staged = upload((i + 1) % nbuf, nxt_s, free_ev[(i + 1) % nbuf]) if nxt_s is not None else None
-                blob = bufs[k][:s.header["nbytes"]]
+            n_up = 0
+
+            def next_upload():
+                nonlocal n_up
+                s_ = next(it, None)
+                if s_ is None:
+                    return None
+                k_ = n_up % nbuf
+                n_up += 1
+                return upload(k_, s_, free_ev[k_])
+
+            def plan_native(staged_):
+                s_, k_, uploaded_ = staged_
+                blob_ = bufs[k_][:s_.header["nbytes"]]
+                state_ = head_ = None
+                if s_.num_nodes() > 0:
+                    with torch.cuda.stream(plan_stream), torch.no_grad():
+                        plan_stream.wait_event(uploaded_)
+                        head_ = s_._plan_head()["buf"].to(dev, non_blocking=True)
+                        state_ = model.slide_plan_native(s_, blob_, head_, slots[k_], plan_stream)
+                ev_ = torch.cuda.Event()
+                ev_.record(plan_stream)
+                return s_, k_, uploaded_, blob_, head_, state_, ev_
+
+            up_q = [u for u in (next_upload(), next_upload()) if u is not None]
+            cur = plan_native(up_q.pop(0)) if up_q else None
+            while cur is not None:
+                u = next_upload()                                   # stage 1: slide i + 2
+                if u is not None:
+                    up_q.append(u)
+                nxt = plan_native(up_q.pop(0)) if up_q else None    # stage 2: slide i + 1 (kernels + async totals)
+                s, k, uploaded, blob, head, state, planned_ev = cur
                 with torch.no_grad():
-                    out = None
-                    if s.num_nodes() > 0:
-                        with torch.cuda.stream(plan_stream):
-                            plan_stream.wait_event(uploaded)
-                            head = s._plan_head()["buf"].to(dev, non_blocking=True)
-                        out = model.slide_forward_native(s, blob, head, slots[k], plan_stream, main)
-                    keep = (s, blob, head if s.num_nodes() > 0 else None)
-                    if out is None:                                 # not the driver's shapes: generic path
-                        host, done, keep = forward(plan((s, k, uploaded)))
-                    else:
+                    if state is not None:
+                        planned_ev.synchronize()                    # a whole slide old: the totals are on the host
+                        out = model.slide_run_native(state, slots[k], plan_stream, main)
                         host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
                         host.copy_(out, non_blocking=True)
                         done = torch.cuda.Event()
                         done.record(main)
+                        keep = (s, blob, head, state)
+                    else:                                           # not the driver's shapes: generic path
+                        host, done, keep = forward(plan((s, k, uploaded)))
                 free_ev[k] = done
                 pending.append((host, done, keep))
                 if len(pending) >= nbuf:
                     h, ev, _ = pending.pop(0)
                     ev.synchronize()
                     yield h
-                i += 1
+                cur = nxt
         elif threaded:
             ready_q: "queue.Queue" = queue.Queue(maxsize=max(1, nbuf - 2))
             free_q = [queue.Queue() for _ in range(nbuf)]           # per buffer: `done` event of the forward that read it

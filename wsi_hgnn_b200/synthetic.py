@@ -91,3 +91,24 @@ def random_hetero_graph(num_nodes: Sequence[int], n_edges: int, f: int, seed: in
     feats = torch.randn(n, f, generator=g)
     return to_heterogeneous(src, dst, ntype, et, [str(t) for t in range(T)], list(etypes),
                             ndata={"feat": feats}, edata={"sim": sim})
+
+
+def device_slide_graph(n: int, f: int, n_types: int, k: int, seed: int, device, skew: bool = False) -> HeteroGraph:
+    """The same recipe built ON THE GPU (device RNG; the product's own k-NN + Pearson kernels as the edge builder): the
+    generator of the large benchmark batches (256 slides of 2k-20k nodes), where the exact fp64 host k-NN of
+    synth_slide_graph would take minutes per slide.  Different random stream than the host generator."""
+    from .construct_graph.graph_constructor import construct_graph_arrays
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    n_clusters = 8 * n_types
+    centres = torch.randn(n_clusters, f, generator=g, device=dev)
+    if skew and n_types == 6:
+        probs = torch.tensor(TYPE_SKEW6, device=dev).repeat(8) / 8.0
+        cid = torch.multinomial(probs, n, replacement=True, generator=g)
+    else:
+        cid = torch.randint(0, n_clusters, (n,), generator=g, device=dev)
+    feats = centres[cid] + 0.5 * torch.randn(n, f, generator=g, device=dev)
+    ntype = cid % n_types
+    ei, et, sim = construct_graph_arrays(feats, k + 1)
+    return to_heterogeneous(ei[0], ei[1], ntype, et.to(torch.int64), [str(t) for t in range(n_types)], ["neg", "pos"],
+                            ndata={"feat": feats}, edata={"sim": sim})
