@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--nodes", type=int, default=8192)
     ap.add_argument("--gemm-dbg", action="store_true", help="also time the tc_debug variants of the GEMM")
     ap.add_argument("--precisions", default="bf16x3,fp16")
+    ap.add_argument("--attn-only", action="store_true")
+    ap.add_argument("--k", type=int, default=5, help="out-degree of the synthetic k-NN graph of the attention sweep")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -55,7 +57,7 @@ def main():
     ptr = [0, N // 3, 2 * (N // 3), N]
     g = torch.Generator().manual_seed(0)
 
-    for name, K, n_out, full in (("K|V|Q", 512, 1536, False), ("a_linear+skip", 512, 512, True), ("adapt_ws", 1024, 512, False)):
+    for name, K, n_out, full in (() if args.attn_only else (("K|V|Q", 512, 1536, False), ("a_linear+skip", 512, 512, True), ("adapt_ws", 1024, 512, False))):
         x = torch.randn(N, K, generator=g).to(dev)
         w = (torch.randn(T, n_out, K, generator=g) / K ** 0.5).to(dev)
         b = torch.randn(T, n_out, generator=g).to(dev)
@@ -80,7 +82,7 @@ def main():
     print(json.dumps({"kernel": "floor: z.add_(1) on 32 floats", "ms": timeit(lambda: z.add_(1.0), args.reps, flush)}), flush=True)
 
     D, H = 512, 4
-    G = synthetic.synth_slide_graph(N, 64, T, 5, seed=1).to(dev)
+    G = synthetic.device_slide_graph(N, 64, T, args.k, seed=1, device=dev)
     plan = G.plan()
     E = G.num_edges()
     kvq = torch.randn(N, 3 * D, device=dev)
@@ -91,12 +93,12 @@ def main():
     def warm():
         kvq.add_(0.0)
 
-    variants = [dict(), dict(no_pdl=1), dict(attn_kernel=2), dict(attn_kernel=3)]
+    variants = [dict(attn_kernel=1), dict(attn_kernel=2), dict(attn_kernel=3)]
     keys = sorted({k for v in variants for k in v})
     for var in variants:
         for k in keys:
             ops.dev_set(k, var.get(k, 0))
-        for op_out in (False, True):
+        for op_out in (True,):
             try:
                 fn = lambda: ops.hetero_attn_work(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], work, plan.e_src, plan.e_sim,
                                                   plan.e_rel, plan.node_inv_r, ew, eb, D, H, op_out=op_out)

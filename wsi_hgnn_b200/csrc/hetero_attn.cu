@@ -59,6 +59,7 @@ struct AttnArgs {
   int dbg;                    // development only (env WSI_ATTN_DEBUG): 1 = gather only 64 distinct rows, 2 = no bulk copies, 3 = no math
   int* sched;                 // optional int32 [2], zero before the first launch: dynamic work queue (next item | warps done)
   const int* split_row; const int* split_ptr; const int* part_rel;
+  int64_t n_src_rows;         // rows of K / V that can be gathered (the footprint that decides register vs TMA-ring kernel); 0 = unknown
 };
 
 __device__ __forceinline__ void st_split4(__nv_bfloat16* dst, int64_t lo_off, float4 v) {
@@ -662,294 +663,6 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Item-pipelined TMA kernel (the one the forward uses).  The ring kernel above hides the K/V latency INSIDE an item,
-// but a work item is only ~5 edges and the dependent chain  queue index -> item descriptor -> edge ids -> K|V rows
-// is four serial memory round trips per item (ncu: the warps sit on the SHFL of the freshly loaded edge ids and on
-// the descriptor load).  Here every warp runs that chain as a software pipeline over its items:
-//     iteration i:  queue index of item i+4 | descriptor of i+3 | edge ids, sim, relation, 1/R of i+2 | q row of i+1
-//                   | K|V bulk copies of item i+1 go out as soon as item i's last copies are issued | math of item i
-// so each load was requested one whole item earlier than it is consumed and the per-warp ring of K|V slots stays full
-// across item boundaries (slots are consumed in FIFO order: item i's edges, then item i+1's).
-struct ItemDesc { int row, beg, end, slot; };
-struct ItemMeta { int src; float scale; int rel; float invr; float seg_scale; };
-
-template <int MODE>
-__device__ __forceinline__ ItemDesc pipe_load_desc(const AttnArgs& a, int idx) {
-  ItemDesc d; d.row = 0; d.beg = 0; d.end = 0; d.slot = -1;
-  if (idx < a.n_items) {
-    if (a.items) { const int4 it = __ldg(a.items + idx); d.row = it.x; d.beg = it.y; d.end = it.z; d.slot = it.w; }
-    else { d.row = idx; d.beg = __ldg(a.rowptr + idx); d.end = __ldg(a.rowptr + idx + 1); }
-  }
-  return d;
-}
-
-// edge window [beg, beg + 32) of an item: lane l holds edge beg + l
-template <int MODE>
-__device__ __forceinline__ ItemMeta pipe_load_meta(const AttnArgs& a, const ItemDesc& d, int beg, int lane, int head,
-                                                   float ew, float eb) {
-  ItemMeta m; m.src = 0; m.scale = 0.f; m.rel = 0; m.invr = 1.f; m.seg_scale = 0.f;
-  if (beg + lane < d.end) {
-    m.src = __ldg(a.e_src + beg + lane);
-    if (a.dbg == 1) m.src &= 63;
-    if (MODE == MODE_HEAT) {
-      m.scale = fmaf(ew, __ldg(a.e_sim + beg + lane), eb) * a.inv_sqrt_dk;
-      m.rel = __ldg(a.e_rel + beg + lane);
-    }
-  }
-  if (d.end > d.beg) {
-    if (MODE == MODE_HEAT) m.invr = __ldg(a.inv_r + d.row);
-    else m.seg_scale = __ldg(a.rel_pri + (int64_t)__ldg(a.seg_rel + d.row) * a.H + head) * a.inv_sqrt_dk;
-  }
-  return m;
-}
-
-template <int NV, int MODE, int MINB>
-__global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? MINB : 1) attn_fwd_pipe_kernel(AttnArgs a, int ring) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int ROW_BYTES = NV * 512, SLOT_BYTES = 2 * ROW_BYTES;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int G = 32 / a.H;
-  const int head = lane / G;
-  const int n_warps = gridDim.x * TMA_WARPS;
-  uint8_t* my_slots = smem + (size_t)warp * ring * SLOT_BYTES;
-  const uint32_t slots_u32 = smem_u32(my_slots);
-  const uint32_t bars_u32 = smem_u32(smem + (size_t)TMA_WARPS * ring * SLOT_BYTES) + warp * ring * 8;
-  if (lane == 0) {
-    for (int s = 0; s < ring; ++s) mbar_init(bars_u32 + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  float ew = 0.f, eb = 0.f;
-  if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
-  const bool kv_adjacent = a.V == a.K + a.D && a.ldk == a.ldv;
-  const int bmax = min(BMAX, ring);
-
-  int rs = 0; uint32_t rpar = 0;          // consumer side of the ring: next slot to read, its phase parity
-  int ws = 0;                             // producer side: next slot to fill
-  int inflight = 0;                       // slots filled or being filled
-
-  // issue the K|V copy of one edge into ring slot ws (all lanes call; lane 0 issues)
-  auto issue = [&](int src) {
-    if (lane == 0 && a.dbg != 2) {
-      const uint32_t bar = bars_u32 + 8 * ws, dst = slots_u32 + ws * SLOT_BYTES;
-      mbar_expect_tx(bar, SLOT_BYTES);
-      if (kv_adjacent) {
-        bulk_g2s(dst, a.K + (int64_t)src * a.ldk, SLOT_BYTES, bar);
-      } else {
-        bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
-        bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
-      }
-    }
-    if (++ws == ring) ws = 0;
-    ++inflight;
-  };
-  // Queue index of a later item.  Dynamic queue: lane 0's atomicAdd result is NOT broadcast here - the shuffle would
-  // wait for the atomic's round trip; it is broadcast one iteration later, when the value is first needed.
-  auto next_index_raw = [&](int prev) -> int {
-    int v = prev + n_warps;
-    if (a.sched) { v = 0; if (lane == 0) v = atomicAdd(a.sched, 1); }
-    return v;
-  };
-  auto bcast = [&](int raw) -> int { return a.sched ? __shfl_sync(FULL, raw, 0) : raw; };
-
-  // ---- prologue: fill the pipeline (items 0..3 of this warp)
-  int idx0 = blockIdx.x * TMA_WARPS + warp;
-  if (a.sched) idx0 = bcast(next_index_raw(0));
-  int idx1 = bcast(next_index_raw(idx0)), idx2 = bcast(next_index_raw(idx1));
-  int idx3_raw = next_index_raw(idx2);
-  ItemDesc d0 = pipe_load_desc<MODE>(a, idx0), d1 = pipe_load_desc<MODE>(a, idx1), d2 = pipe_load_desc<MODE>(a, idx2);
-  ItemMeta m0 = pipe_load_meta<MODE>(a, d0, d0.beg, lane, head, ew, eb);
-  ItemMeta m1 = pipe_load_meta<MODE>(a, d1, d1.beg, lane, head, ew, eb);
-  int cur_issued = 0;                     // copies of the current item's window already issued
-
-  while (idx0 < a.n_items) {
-    // ---- prefetch stages for the following items (each consumed one iteration after it is requested)
-    const int idx3 = bcast(idx3_raw);
-    const int idx4_raw = next_index_raw(idx3);
-    const ItemDesc d3 = pipe_load_desc<MODE>(a, idx3);
-    const ItemMeta m2 = pipe_load_meta<MODE>(a, d2, d2.beg, lane, head, ew, eb);
-    if (d1.end > d1.beg && lane < NV * 4)              // next item's q row: pull its 128 B lines into L2 / L1
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Q + (int64_t)d1.row * a.ldq + lane * 32));
-    const int n1 = (m1.invr != 0.f) ? min(32, d1.end - d1.beg) : 0;     // first window of the next item
-    int nxt_issued = 0;
-    float4 q0[NV];
-    if (m0.invr != 0.f && d0.end > d0.beg) {
-      const float* qr = a.Q + (int64_t)d0.row * a.ldq;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) q0[i] = ld4(qr + (i * 32 + lane) * 4);
-    }
-
-    // ---- item i
-    const int row = d0.row, slot = d0.slot;
-    float4 out[NV], acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc[i] = out[i]; }
-    const float invr = m0.invr;
-    float m = -INFINITY, ssum = 0.f;
-    const bool live = invr != 0.f && d0.end > d0.beg;
-    int cur_rel = -1;
-    for (int base = d0.beg; base < d0.end || base == d0.beg; base += 32) {
-      const int n = live ? min(32, d0.end - base) : 0;
-      const bool last_window = base + 32 >= d0.end;
-      if (base != d0.beg) {               // rows with more than 32 edges per item: the later windows are not prefetched
-        m0 = pipe_load_meta<MODE>(a, d0, base, lane, head, ew, eb);
-        cur_issued = 0;
-      }
-      int j = 0;
-      while (true) {
-        // refill the ring: this window's edges first, then (last window only) the next item's
-        if (inflight < ring && (cur_issued < n || (last_window && nxt_issued < n1))) {
-          // the freed slots were read through the generic proxy; order those reads before the async-proxy writes
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          while (inflight < ring) {
-            if (cur_issued < n) { issue(__shfl_sync(FULL, m0.src, cur_issued)); ++cur_issued; }
-            else if (last_window && nxt_issued < n1) { issue(__shfl_sync(FULL, m1.src, nxt_issued)); ++nxt_issued; }
-            else break;
-          }
-        }
-        if (j >= n) break;
-        int g = min(bmax, n - j);
-        if (MODE == MODE_HEAT) {
-          const int rel = __shfl_sync(FULL, m0.rel, j);
-          const unsigned same = __ballot_sync(FULL, lane >= j && lane < n && m0.rel == rel) >> j;
-          g = min(g, same == FULL ? 32 : __ffs(~same) - 1);        // (__ffs(0) == 0)
-          if (rel != cur_rel) {                       // warp-uniform: close the running segment
-            if (cur_rel >= 0) {
-              const float inv = 1.f / ssum;
-#pragma unroll
-              for (int i = 0; i < NV; ++i) {
-                out[i].x = fmaf(acc[i].x, inv, out[i].x); out[i].y = fmaf(acc[i].y, inv, out[i].y);
-                out[i].z = fmaf(acc[i].z, inv, out[i].z); out[i].w = fmaf(acc[i].w, inv, out[i].w);
-                acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
-            m = -INFINITY; ssum = 0.f; cur_rel = rel;
-          }
-        }
-        float sc[BMAX];
-        const float* slot_ptr[BMAX];
-#pragma unroll
-        for (int u = 0; u < BMAX; ++u) {
-          sc[u] = -INFINITY;
-          slot_ptr[u] = nullptr;
-          if (u < g) {
-            int su = rs + u;
-            uint32_t pu = rpar;
-            if (su >= ring) { su -= ring; pu ^= 1; }
-            if (a.dbg != 2) mbar_wait(bars_u32 + 8 * su, pu);
-            const float* ks = reinterpret_cast<const float*>(my_slots + (size_t)su * SLOT_BYTES);
-            slot_ptr[u] = ks;
-            float d0_ = 0.f, d1_ = 0.f;
-            if (a.dbg != 3)
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-              const float4 kk = *reinterpret_cast<const float4*>(ks + (i * 32 + lane) * 4);
-              d0_ = fmaf(q0[i].x, kk.x, d0_); d1_ = fmaf(q0[i].y, kk.y, d1_);
-              d0_ = fmaf(q0[i].z, kk.z, d0_); d1_ = fmaf(q0[i].w, kk.w, d1_);
-            }
-            sc[u] = d0_ + d1_;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < BMAX; ++u) {
-          if (u < g) {
-            float d = sc[u];
-            for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
-            float scale = m0.seg_scale;
-            if (MODE == MODE_HEAT) scale = __shfl_sync(FULL, m0.scale, j + u);
-            sc[u] = d * scale;
-          }
-        }
-        float mn = m;
-#pragma unroll
-        for (int u = 0; u < BMAX; ++u) mn = fmaxf(mn, sc[u]);
-        const float corr = __expf(m - mn);            // m = -inf on the first batch -> 0
-        float p[BMAX], psum = 0.f;
-#pragma unroll
-        for (int u = 0; u < BMAX; ++u) { p[u] = __expf(sc[u] - mn); psum += p[u]; }   // exp(-inf) = 0 for u >= g
-        ssum = fmaf(ssum, corr, psum);
-        m = mn;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) { acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr; }
-#pragma unroll
-        for (int u = 0; u < BMAX; ++u) {
-          if (u < g && a.dbg != 3) {
-            const float* vs = slot_ptr[u] + NV * 128;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-              const float4 vv = *reinterpret_cast<const float4*>(vs + (i * 32 + lane) * 4);
-              acc[i].x = fmaf(p[u], vv.x, acc[i].x); acc[i].y = fmaf(p[u], vv.y, acc[i].y);
-              acc[i].z = fmaf(p[u], vv.z, acc[i].z); acc[i].w = fmaf(p[u], vv.w, acc[i].w);
-            }
-          }
-        }
-        __syncwarp();                                 // every lane is done with these g slots
-        rs += g;
-        if (rs >= ring) { rs -= ring; rpar ^= 1; }
-        inflight -= g;
-        j += g;
-      }
-      if (!live) break;
-    }
-    if (live && slot < 0) {                           // close the last segment
-      const float inv = 1.f / ssum;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        out[i].x = fmaf(acc[i].x, inv, out[i].x) * invr; out[i].y = fmaf(acc[i].y, inv, out[i].y) * invr;
-        out[i].z = fmaf(acc[i].z, inv, out[i].z) * invr; out[i].w = fmaf(acc[i].w, inv, out[i].w) * invr;
-      }
-    }
-    if (slot < 0) {
-      if (a.out) {
-        float* o = a.out + (int64_t)row * a.ldo;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = out[i];
-      }
-      if (a.out_split) {
-        __nv_bfloat16* o = a.out_split + (int64_t)row * a.D;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) st_split4(o + (i * 32 + lane) * 4, a.split_lo, out[i]);
-      }
-    } else {                                          // partial of one segment chunk: (m, sum, unnormalised acc)
-      a.part_ms[(int64_t)slot * 64 + lane] = m;
-      a.part_ms[(int64_t)slot * 64 + 32 + lane] = ssum;
-      float* o = a.part_acc + (int64_t)slot * a.D;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = acc[i];
-      if (a.split_cnt) {                              // the warp that completes the row's last chunk merges it
-        const int h = __ldg(a.part_split + slot);
-        __threadfence();
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-          const int n_chunks = __ldg(a.split_ptr + h + 1) - __ldg(a.split_ptr + h);
-          last = atomicAdd(a.split_cnt + h, 1) == n_chunks - 1;
-          if (last) a.split_cnt[h] = 0;               // self-resetting: ready for the next launch
-        }
-        last = __shfl_sync(FULL, last, 0);
-        if (last) {
-          __threadfence();
-          MergeArgs mg;
-          mg.split_row = a.split_row; mg.split_ptr = a.split_ptr; mg.part_rel = a.part_rel;
-          mg.part_ms = a.part_ms; mg.part_acc = a.part_acc; mg.inv_r = a.inv_r; mg.n_split = 0; mg.D = a.D;
-          mg.out = a.out; mg.ldo = a.ldo; mg.out_split = a.out_split; mg.split_lo = a.split_lo;
-          merge_row<NV>(mg, h, lane);
-        }
-      }
-    }
-    // ---- rotate the pipeline
-    idx0 = idx1; idx1 = idx2; idx2 = idx3; idx3_raw = idx4_raw;
-    d0 = d1; d1 = d2; d2 = d3;
-    m0 = m1; m1 = m2;
-    cur_issued = nxt_issued;
-  }
-  if (a.sched && lane == 0) {                         // the last warp to leave re-arms the queue for the next launch
-    __threadfence();
-    if (atomicAdd(a.sched + 1, 1) == n_warps - 1) { a.sched[0] = 0; a.sched[1] = 0; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Generic path: any D, H (natural column order).  One warp per work item, heads processed one after the
 // other; lane l owns columns {l + 32 j} of the current head (MAXJ >= ceil(d_k / 32)).
 template <int MAXJ, int MODE>
@@ -1065,13 +778,18 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       wsi_set_error("hetero_attn: head_perm layout needs D %% 128 == 0, D <= 1024, H a power of two <= 32 (D=%d H=%d)", a.D, a.H);
       return WSI_ERR_UNSUPPORTED;
     }
-    // development knob attn_kernel: 2 / 3 = the TMA bulk-copy kernels (ring / item-pipelined)
-    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && dev.attn_kernel >= 2) {
+    // Kernel choice per launch (round-2 sweep, profiles/r2_attn_crossover.txt): while K|V fit in L2 (config 2: 33 MB)
+    // the register-path kernel wins (30.7 vs 43.2 us) - the gathers are L2 hits and many light warps hide their latency
+    // best; once the gathered rows come from DRAM (>= ~16-20k rows at D = 512; config 4: 410 MB, the packed training
+    // batches: 655 MB) the TMA bulk-copy ring wins by 1.2-1.3x (100k nodes, k = 8: 0.537 vs 0.707 ms = 6.9 TB/s on the
+    // SURVEY 8(d) byte model) because it keeps ~12 KB per warp in flight without spending registers on them.  The
+    // item-pipelined variant of round 1 lost at every size and no longer ships.  Knob attn_kernel: 1 / 2 force one.
+    const int64_t kv_bytes = a.n_src_rows * 2 * (int64_t)a.D * 4;
+    const bool want_ring = dev.attn_kernel == 2 || (dev.attn_kernel == 0 && kv_bytes >= (80ll << 20));
+    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && want_ring) {
       const int slot_bytes = 2 * a.D * 4;
-      const bool pipe = dev.attn_kernel == 3;
-      // ring kernel: ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM;
-      // item-pipelined kernel: ~24 KB per warp (the ring spans item boundaries), 2 blocks of 4 warps per SM, no spills
-      int ring = (pipe ? 24576 : 12288) / slot_bytes;
+      // ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM
+      int ring = 12288 / slot_bytes;
       ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
       if (dev.attn_ring > 0) ring = dev.attn_ring;                          // development knob
       if (ring < 1) ring = 1;
@@ -1085,13 +803,9 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
         static std::once_flag once; \
         static cudaError_t aerr = cudaSuccess; \
         std::call_once(once, [] { \
-          aerr = cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-          if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-          if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(attn_fwd_pipe_kernel<NV, MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }); \
+          aerr = cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }); \
         WSI_CHECK_CUDA(aerr); \
-        if (pipe && per_sm >= 3) attn_fwd_pipe_kernel<NV, MODE, 3><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); \
-        else if (pipe) attn_fwd_pipe_kernel<NV, MODE, 2><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); \
-        else attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
+        attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
       }
@@ -1178,6 +892,7 @@ extern "C" int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, 
   a.e_w = e_w; a.e_b = e_b; a.n_items = (int)n_rows; a.D = D; a.H = H; a.dk = D / H;
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.out = agg; a.ldo = ldo; a.attn = attn_out;
+  a.n_src_rows = n_rows;
   return launch<MODE_HEAT>(a, head_perm, wsi_stream(stream));
 }
 
@@ -1206,6 +921,7 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
   a.e_w = e_w; a.e_b = e_b; a.n_items = (int)n_items; a.D = D; a.H = H; a.dk = D / H;
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.out = agg; a.ldo = ldo; a.attn = nullptr;
+  a.n_src_rows = n_rows;
   a.items = reinterpret_cast<const int4*>(items); a.part_ms = part_ms; a.part_acc = part_acc;
   WSI_CHECK_ARG(opf == WSI_OPF_BF16X3 || opf == WSI_OPF_F16 || opf == WSI_OPF_BF16, "hetero_attn_work_fwd: unknown operand format %d", opf);
   a.out_split = reinterpret_cast<__nv_bfloat16*>(agg_split);
