@@ -27,6 +27,9 @@ def _grads(model, G, labels, device):
     ("HEATNet4", dict(in_dim=64, hidden_dim=128, out_dim=3, n_layers=2, n_heads=4, dropuout=0.0), 700),
     ("HEATNet2", dict(in_dim=32, hidden_dim=256, out_dim=2, n_layers=1, n_heads=8, dropuout=0.0), 300),
     ("HEATNet4", dict(in_dim=64, hidden_dim=512, out_dim=2, n_layers=2, n_heads=4, dropuout=0.0), 1500),
+    ("HEATNet2", dict(in_dim=32, hidden_dim=128, out_dim=2, n_layers=2, n_heads=4, dropuout=0.0, graph_pooling_type="max"), 400),
+    ("HGT", dict(in_dim=48, hidden_dim=128, out_dim=2, n_layers=3, n_heads=4, use_norm=True), 600),
+    ("HGT", dict(in_dim=32, hidden_dim=256, out_dim=3, n_layers=2, n_heads=8, use_norm=False, graph_pooling_type="sum"), 300),
 ])
 def test_gradients_match_oracle_autograd(model, kw, n):
     gs = [synthetic.synth_slide_graph(n + 50 * i, kw["in_dim"], 3, 5, seed=20 + i, noise_edges=0.3) for i in range(2)]
@@ -39,6 +42,10 @@ def test_gradients_match_oracle_autograd(model, kw, n):
     orc.load_state_dict(ours.state_dict(), strict=True)
     ours = ours.cuda().train()
     orc = orc.double().train()
+    for m_ in (ours, orc):                                  # HGTLayer hard-codes nn.Dropout(0.2) (models/HGT.py:34): off for parity
+        for mod in m_.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
     for nt in G.ntypes:
         pass
     G64 = pack(gs)

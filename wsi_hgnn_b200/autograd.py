@@ -95,9 +95,10 @@ class SegmentPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, plan, n_seg: int, op: str):
         ctx.plan, ctx.op, ctx.n_seg = plan, op, n_seg
+        pooled = ops.segment_pool(x, plan.seg_ptr, n_seg, op)
         if op == "max":
-            raise NotImplementedError("max pooling has no backward yet: train with graph_pooling_type 'mean' or 'sum'")
-        return ops.segment_pool(x, plan.seg_ptr, n_seg, op)
+            ctx.save_for_backward(x, pooled)
+        return pooled
 
     @staticmethod
     def backward(ctx, d_pooled):
@@ -106,6 +107,18 @@ class SegmentPoolFn(torch.autograd.Function):
         d = d_pooled.index_select(0, seg_of_row)
         if ctx.op == "mean":
             d = d * inv_n.unsqueeze(1)
+        elif ctx.op == "max":
+            # dgl.readout.max_nodes / torch.max(dim=0): the gradient goes to ONE row per (segment, column), the first that
+            # attains the maximum (ties have measure zero for real features; resolved like torch's max(0).indices)
+            x, pooled = ctx.saved_tensors
+            eq = x == pooled.index_select(0, seg_of_row)
+            c = eq.to(torch.int64).cumsum(0)
+            seg_first = plan.seg_ptr[:-1].to(torch.int64)                      # first row of every segment
+            base = torch.zeros((ctx.n_seg, x.shape[1]), dtype=torch.int64, device=x.device)
+            has_prev = seg_first > 0
+            base[has_prev] = c.index_select(0, (seg_first[has_prev] - 1).clamp_max(max(x.shape[0] - 1, 0)))
+            first = eq & ((c - base.index_select(0, seg_of_row)) == 1)
+            d = d * first
         return d, None, None, None
 
 
@@ -133,3 +146,100 @@ class SkipMixFn(torch.autograd.Function):
         s_row = (dout * (lin - x)).sum(1) * (a_row.squeeze(1) != 0)
         d_alpha = torch.stack([s_row[tp[t]:tp[t + 1]].sum() for t in range(len(tp) - 1)])
         return d_lin, d_x, d_alpha * alpha_t * (1 - alpha_t), None, None
+
+
+# ------------------------------------------------------------------------------------------------------------ HGT
+class RelTransformFn(torch.autograd.Function):
+    """y[y_idx[i]] = W[r(i), h] (.) x[x_idx[i]] for the relation-grouped (dst, relation) segments i (models/HGT.py:88-93 moved
+    to the segments, see models/hgt.py).  x_idx may repeat (the q side gathers the dst row of every segment), y_idx and
+    `order` are permutations of the segments.  Backward: the transposed maps through the same kernel; the weight gradient
+    is a per-relation batched outer-product reduction (cuBLAS bmm, like the typed wgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, w, x_idx, y_idx, rel_ptr_c, rel_ptr, R: int, H: int, d_k: int, w_kn: bool, n_out_rows: int,
+                row_seg_ptr):
+        x = x.contiguous()
+        ctx.save_for_backward(x, w, x_idx, y_idx, row_seg_ptr if row_seg_ptr is not None else x_idx)
+        ctx.meta = (rel_ptr_c, rel_ptr, R, H, d_k, w_kn, row_seg_ptr is not None)
+        return ops.rel_transform(x, x_idx, y_idx, w.detach().contiguous(), rel_ptr_c, R, H, d_k, w_kn, n_out_rows)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, x_idx, y_idx, row_seg_ptr = ctx.saved_tensors
+        rel_ptr_c, rel_ptr, R, H, d_k, w_kn, reduce_rows = ctx.meta
+        dy = dy.contiguous()
+        S = int(y_idx.numel())
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            # d x_i = W^T-side map of d y_i, written in natural segment order, then summed over the segments that share
+            # an input row (q side) or scattered back through the permutation (message side)
+            dseg = ops.rel_transform(dy, y_idx, y_idx, w.detach().contiguous(), rel_ptr_c, R, H, d_k, not w_kn, S)
+            if reduce_rows:
+                ones = torch.ones(x.shape[0], dtype=torch.float32, device=x.device)
+                dx = ops.segment_combine(dseg, row_seg_ptr, ones, x.shape[0], H * d_k)
+            else:
+                dx = torch.zeros_like(x)
+                dx.index_copy_(0, x_idx.to(torch.int64), dseg.index_select(0, y_idx.to(torch.int64)))
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            xi, yi = x_idx.to(torch.int64), y_idx.to(torch.int64)
+            for r in range(R):
+                a, b = rel_ptr[r], rel_ptr[r + 1]
+                if b <= a:
+                    continue
+                xr = x.index_select(0, xi[a:b]).view(b - a, H, d_k).permute(1, 0, 2)          # [H, n, dk]
+                gr = dy.index_select(0, yi[a:b]).view(b - a, H, d_k).permute(1, 0, 2)
+                # w_kn: y_n = sum_k x_k W[k, n] -> dW[k, n] = sum_i x_k g_n;   else y_n = sum_k W[n, k] x_k -> dW[n, k] = g_n x_k
+                dw[r] = torch.bmm(xr.transpose(1, 2), gr) if w_kn else torch.bmm(gr.transpose(1, 2), xr)
+        return dx, dw, None, None, None, None, None, None, None, None, None, None
+
+
+class SegAttnFn(torch.autograd.Function):
+    """Edge attention over the (dst, relation) segments of HGT (models/HGT.py:95-106 before the cross-relation mean):
+    out[s] = softmax_{e in s}(<q_s, k[src e]> / sqrt(d_k)) . v[src e]  - the HEAT kernels (forward K2, backward K3) run on
+    the SEGMENT graph: one "row" per segment, one relation run per row, unit edge attribute; relation_pri is folded into
+    q_s by the caller.  k, v, q_s in the lane-grouped column order."""
+
+    @staticmethod
+    def forward(ctx, k, v, qseg, plan, D: int, H: int):
+        segs = plan.segments()
+        aux = plan.cache.get("hgt_seg_graph")
+        if aux is None:
+            dev = qseg.device
+            aux = dict(sim=torch.ones(plan.E, dtype=torch.float32, device=dev),
+                       rel=torch.zeros(plan.E, dtype=torch.uint8, device=dev),
+                       inv=torch.ones(segs["S"], dtype=torch.float32, device=dev),
+                       ew=torch.ones(1, dtype=torch.float32, device=dev), eb=torch.zeros(1, dtype=torch.float32, device=dev))
+            plan.cache["hgt_seg_graph"] = aux
+        ctx.save_for_backward(k, v, qseg)
+        ctx.plan, ctx.D, ctx.H, ctx.aux = plan, D, H, aux
+        return ops.hetero_attn(k, v, qseg, segs["seg_ptr"], plan.e_src, aux["sim"], aux["rel"], aux["inv"], aux["ew"],
+                               aux["eb"], D, H, True)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        k, v, qseg = ctx.saved_tensors
+        plan, D, H, aux = ctx.plan, ctx.D, ctx.H, ctx.aux
+        segs = plan.segments()
+        dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+        dq = torch.empty_like(qseg)
+        ops.hetero_attn_bwd(k, v, qseg, segs["seg_ptr"], plan.e_src, aux["sim"], aux["rel"], aux["inv"], aux["ew"], aux["eb"],
+                            D, H, d_out.contiguous(), dk, dv, dq)
+        return dk, dv, dq, None, None, None
+
+
+class SegmentCombineFn(torch.autograd.Function):
+    """agg[v] = inv_r[v] * sum of the messages of row v's segments (the stack -> mean of models/HGT.py:105-106)."""
+
+    @staticmethod
+    def forward(ctx, msg, plan, D: int):
+        segs = plan.segments()
+        ctx.plan = plan
+        return ops.segment_combine(msg.contiguous(), segs["row_seg_ptr"], plan.node_inv_r, plan.N, D)
+
+    @staticmethod
+    def backward(ctx, d_agg):
+        plan = ctx.plan
+        segs = plan.segments()
+        dst = segs["seg_dst"].to(torch.int64)
+        return d_agg.index_select(0, dst) * plan.node_inv_r.index_select(0, dst).unsqueeze(1), None, None

@@ -15,8 +15,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from ..autograd import (RelTransformFn, SegAttnFn, SegmentCombineFn, SegmentPoolFn, SkipMixFn, TypedLinearFn)
 from ..hetero_graph import GraphPlan, HeteroGraph
-from ._packing import PackCache, param_list, stack_linears
+from ._packing import PackCache, _Permute, param_list, stack_linears
 from .heat import _check_pool, _graph_type_order, packed_features, readout_scale, unpack_rows
 
 
@@ -36,7 +37,7 @@ def _relation_groups(plan: GraphPlan, edge_dict: Dict, tag):
             seg_rel=seg_rel.to(torch.int32).contiguous(),
             order=order.to(torch.int32).contiguous(),
             dst_of_order=segs["seg_dst"][order].contiguous(),
-            rel_ptr_c=ops.host_i32(rel_ptr), R=R)
+            rel_ptr_c=ops.host_i32(rel_ptr), rel_ptr=rel_ptr, R=R)
     return plan.cache[key]
 
 
@@ -123,6 +124,55 @@ class HGTLayer(nn.Module):
             out = _gated_layernorm(out, gamma, beta, plan, tpc)
         return out
 
+    def forward_train(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
+        """Differentiable layer (autograd.py): what `loss.backward()` of the reference's train_one_step needs
+        (trainer/train_gnn.py:68-71).  Same schedule as forward_packed; the edge attention runs in the lane-grouped
+        column order (the backward kernel's layout), so K / V are projected with row-permuted weights and the transformed
+        queries / aggregated segments are permuted on the way in / out."""
+        D, H, dk = self.out_dim, self.n_heads, self.d_k
+        perm = ops.head_perm(D, H)
+        if perm is None:
+            raise NotImplementedError(f"training needs the lane-grouped attention layout (D % 128 == 0, H a power of two "
+                                      f"<= 32); got D={D}, H={H}")
+        order = _graph_type_order(plan, self.node_dict)
+        pm = perm.to(x.device)
+        inv_pm = torch.empty_like(pm)
+        inv_pm[pm] = torch.arange(D, device=x.device)
+        tpc = plan.type_ptr_c()
+        segs = plan.segments()
+        grp = _relation_groups(plan, self.edge_dict, id(self.edge_dict))
+        S = segs["S"]
+        wk, bk = stack_linears(self.k_linears, order, row_perm=pm)
+        wv, bv = stack_linears(self.v_linears, order, row_perm=pm)
+        wq, bq = stack_linears(self.q_linears, order)
+        wa, ba = stack_linears(self.a_linears, order)
+        kvq = TypedLinearFn.apply(x, torch.cat([wk, wv, wq], 1), torch.cat([bk, bv, bq], 1), plan.type_ptr, tpc)
+        k, v, q = kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:]
+        if S == 0:
+            agg = torch.zeros_like(x)
+        else:
+            qseg = RelTransformFn.apply(q, self.relation_att, grp["dst_of_order"], grp["order"], grp["rel_ptr_c"],
+                                        grp["rel_ptr"], grp["R"], H, dk, False, S, segs["row_seg_ptr"])      # :88-92
+            pri = self.relation_pri.index_select(0, grp["seg_rel"].to(torch.int64))                           # [S, H]  :100
+            qseg = (qseg.view(S, H, dk) * pri.unsqueeze(-1)).view(S, D)
+            aggseg = SegAttnFn.apply(k, v, _Permute.apply(qseg, pm, 1).contiguous(), plan, D, H)              # :95-104
+            aggseg = _Permute.apply(aggseg, inv_pm, 1).contiguous()
+            msgseg = RelTransformFn.apply(aggseg, self.relation_msg, grp["order"], grp["order"], grp["rel_ptr_c"],
+                                          grp["rel_ptr"], grp["R"], H, dk, True, S, None)                      # :93
+            agg = SegmentCombineFn.apply(msgseg, plan, D)                                                      # :105-106
+        lin = self.drop(TypedLinearFn.apply(agg, wa, ba, plan.type_ptr, tpc))                                  # :121
+        skip_t = self.skip[torch.tensor(order, device=x.device)]
+        out = SkipMixFn.apply(lin, x, skip_t, plan.type_ptr, plan.node_inv_r)                                  # :122, passthrough :118-120
+        if self.use_norm:                                                                                      # :123-124
+            parts = []
+            for t, i in enumerate(order):
+                a, b = plan.type_ptr[t], plan.type_ptr[t + 1]
+                if b > a:
+                    ln = F.layer_norm(out[a:b], (D,), self.norms[i].weight, self.norms[i].bias, self.norms[i].eps)
+                    parts.append(torch.where(plan.node_inv_r[a:b].unsqueeze(1) != 0, ln, out[a:b]))
+            out = torch.cat(parts, 0) if parts else out
+        return out
+
     def forward(self, G: HeteroGraph, h: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         plan = G.plan()
         x = packed_features(G, plan, h)
@@ -170,6 +220,8 @@ class HGT(nn.Module):
         order = _graph_type_order(plan, self.node_dict)
         names = list(plan.ntypes)
         x = packed_features(G, plan, h)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in param_list(self, "all", self.parameters)):
+            return self._forward_train(G, plan, x, order, names, return_embeddings)
         params = param_list(self, "in", lambda: (p for m in self.adapt_ws for p in m.parameters()))
         w_in, b_in = self._packs.get(("in", tuple(order)), params, lambda: stack_linears(self.adapt_ws, order))
         x = ops.typed_linear(x, w_in, b_in, plan.type_ptr, act=ops.ACT_GELU, type_ptr_c=plan.type_ptr_c())  # :176-184
@@ -192,6 +244,26 @@ class HGT(nn.Module):
             # it is computed only when the caller asks for the embeddings
             if i + 1 < self.n_layers or return_embeddings:
                 x = self.gcs[i].forward_packed(plan, x)
+        if hg is None:
+            hg = torch.zeros(B, self.out_dim, device=x.device)
+        return (hg, unpack_rows(plan, x)) if return_embeddings else hg
+
+    def _forward_train(self, G: HeteroGraph, plan: GraphPlan, x, order, names, return_embeddings: bool):
+        """The differentiable chain (training): the same reads of the reference - logits = sum over layers i < L and node
+        types of linears_prediction[type][i](pool(h^(i))) (models/HGT.py:189-199) - through autograd Functions."""
+        T, B = len(plan.ntypes), plan.B
+        w_in, b_in = stack_linears(self.adapt_ws, order)
+        x = F.gelu(TypedLinearFn.apply(x, w_in, b_in, plan.type_ptr, plan.type_ptr_c()))                    # :176-184
+        scale = readout_scale(plan, G.independent).unsqueeze(1)
+        hg = None
+        for i in range(self.n_layers):
+            pooled = SegmentPoolFn.apply(x, plan, T * B, self.graph_pooling_type)
+            w_p = torch.stack([self.linears_prediction[nt][i].weight for nt in names])
+            b_p = torch.stack([self.linears_prediction[nt][i].bias for nt in names])
+            o = (TypedLinearFn.apply(pooled, w_p, b_p, plan.readout_ptr(), None) * scale).view(T, B, -1).sum(0)
+            hg = o if hg is None else hg + o
+            if i + 1 < self.n_layers or return_embeddings:
+                x = self.gcs[i].forward_train(plan, x)
         if hg is None:
             hg = torch.zeros(B, self.out_dim, device=x.device)
         return (hg, unpack_rows(plan, x)) if return_embeddings else hg
