@@ -160,8 +160,11 @@ int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   qseg [S, ldq] = transformed query of the segment (Q[dst] . relation_att[r]^T per head,
  *   models/HGT.py:88-92 moved to the dst side), rel_pri [R_model, H] (models/HGT.py:59,100).
  *   out [S, ldo] = softmax-weighted sum of V[src] over the segment (before relation_msg).
+ *   kv_dtype: storage type of k / v - 0 fp32, 1 fp16, 2 bf16 (ldk / ldv in elements).  The 16-bit forms are the
+ *   bf16-storage configuration (BASELINE config 3): gathered bytes halve, scores / softmax / accumulation stay fp32;
+ *   they need head_perm == 0.
  */
-int wsi_hetero_attn_seg_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qseg,
+int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* qseg,
                             int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel, const int32_t* e_src,
                             const float* rel_pri, int64_t n_segs, int D, int H, int head_perm, float* out,
                             int64_t ldo, void* stream);

@@ -1,8 +1,10 @@
 """Shared test helpers.  TEST INFRASTRUCTURE ONLY."""
+import contextlib
 import glob
 import os
 
 import torch
+import torch.nn.functional as F
 
 import golden_util
 from wsi_hgnn_b200.hetero_graph import HeteroGraph, unbatch
@@ -69,3 +71,34 @@ def run_oracle(m, G, fx=None, independent=None):
         if independent:
             return torch.cat([m(g) for g in unbatch(G)], 0)
         return m(G)
+
+
+@contextlib.contextmanager
+def oracle_rounding(model, dtype=torch.bfloat16, store_kv: bool = True, min_k: int = 64, min_out: int = 64):
+    """Run the CPU oracle with the product's 16-bit rounding at the product's storage points (set_matmul_precision("bf16") /
+    ("fp16")): every nn.Linear the tensor-core path takes (in_features >= 64 and % 8 == 0, out_features >= 64 - the
+    [B, *] readout heads stay fp32) sees its input and its weight rounded to `dtype`, accumulates in fp32, adds the fp32
+    bias; with `store_kv` the outputs of the k_linears / v_linears are additionally stored in `dtype` (the bf16-storage
+    configuration of BASELINE config 3).  TEST INFRASTRUCTURE ONLY."""
+    kv = set()
+    if store_kv:
+        for layer in getattr(model, "gcs", []):
+            for tag in ("k_linears", "v_linears"):
+                for lin in getattr(layer, tag, []):
+                    kv.add(id(lin.weight))
+    orig = F.linear
+
+    def lin(x, w, b=None):
+        if x.dim() != 2 or w.shape[1] < min_k or w.shape[1] % 8 != 0 or w.shape[0] < min_out:
+            return orig(x, w, b)
+        y = torch.mm(x.float().to(dtype).float(), w.float().to(dtype).float().t())
+        if b is not None:
+            y = y + b.float()
+        if id(w) in kv:
+            y = y.to(dtype).float()
+        return y.to(x.dtype)
+    F.linear = torch.nn.functional.linear = lin
+    try:
+        yield
+    finally:
+        F.linear = torch.nn.functional.linear = orig

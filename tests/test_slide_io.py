@@ -98,6 +98,52 @@ def test_stream_forward_matches_per_slide_forward(native, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("feat_dtype", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["heat4_vec_D512_T3_knn", "heat4_config1_T2", "heat4_vec_D128_T3", "heat2_vec_D256_H8_T2"])
+def test_stream_forward_matches_reference_goldens(name, feat_dtype):
+    """The end-to-end path the bench's headline rests on (flat blob -> wsi_slide_plan / wsi_slide_run -> logits) checked
+    DIRECTLY against the reference-generated golden fixtures (outputs of the reference's own model files) and the CPU
+    oracle - with fp32 and with fp16 feature blobs (bit-identical by construction under the fp16 GEMM precision)."""
+    dev = torch.device("cuda", 0)
+    fx, G, m = helpers.golden_setup(name, helpers.build_ours)
+    m = m.to(dev).eval()
+    slide = FlatSlide.from_graph(G, pin=True, feat_dtype=feat_dtype)
+    outs = list(stream_forward(m, [slide, slide, slide], dev))
+    for o in outs:
+        assert helpers.rel_err(o, fx["logits_fp64"]) < 1e-3, f"{name}: rel err {helpers.rel_err(o, fx['logits_fp64']):.3e}"
+    with torch.no_grad():
+        direct = m(G.to(dev)).cpu()
+    assert torch.equal(outs[1], outs[0]) and torch.equal(outs[2], outs[0])
+    # fp32 blobs: the same kernels on the same bits.  fp16 blobs: identical whenever the tensor-core chain runs (it forms the
+    # same fp16 operand itself); graphs too small for it (< 512 nodes: fp32 SIMT GEMMs) see the 2^-11 feature rounding
+    from wsi_hgnn_b200 import ops
+    if feat_dtype == "fp32" or ops.tc_ok(G.num_nodes(), fx["kwargs"]["in_dim"], fx["kwargs"]["hidden_dim"]):
+        assert torch.equal(outs[0], direct)
+    else:
+        assert helpers.rel_err(outs[0], direct) < 1e-3
+
+
+@pytest.mark.gpu
+def test_stream_forward_matches_oracle_distinct_slides():
+    """distinct slides of different sizes through the pipelined native path vs the CPU oracle on every one of them"""
+    dev = torch.device("cuda", 0)
+    T = 3
+    kw = dict(in_dim=64, hidden_dim=128, out_dim=3, n_layers=2, n_heads=4, dropuout=0.0)
+    ours = helpers.build_ours("HEATNet4", T, kw)
+    orc = helpers.build_oracle("HEATNet4", T, kw)
+    golden_util.fill_params(ours, 31)
+    orc.load_state_dict(ours.state_dict(), strict=True)
+    ours, orc = ours.to(dev).eval(), orc.eval()
+    graphs = [synthetic.synth_slide_graph(600 + 211 * i, 64, T, 5, seed=160 + i, noise_edges=0.15) for i in range(6)]
+    for feat_dtype in ("fp32", "fp16"):
+        slides = [FlatSlide.from_graph(g, pin=True, feat_dtype=feat_dtype) for g in graphs]
+        outs = list(stream_forward(ours, slides, dev))
+        with torch.no_grad():
+            for o, g in zip(outs, graphs):
+                assert helpers.rel_err(o, orc(g)) < 1e-3
+
+
+@pytest.mark.gpu
 def test_stream_forward_hgt_and_heatnet2():
     """the streaming evaluator is model-agnostic: HGT (segment planner structures) and HEATNet2 (per-op path at a width
     the one-call driver does not take) give the same logits as slide-at-a-time forwards"""

@@ -26,12 +26,14 @@ def main():
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", type=int, default=0)
+    ap.add_argument("--precision", default="bf16", help="bf16 (config 3 as stated: bf16 storage) | fp16 | bf16x3 (fp32-grade)")
     args = ap.parse_args()
     import golden_util
     import helpers
-    from wsi_hgnn_b200 import synthetic
+    from wsi_hgnn_b200 import ops, synthetic
     from wsi_hgnn_b200.construct_graph import GraphConstructor
     from wsi_hgnn_b200.hetero_graph import pack
+    ops.set_matmul_precision(args.precision)
 
     dev = torch.device("cuda", 0)
     T, k = 6, 6
@@ -72,7 +74,12 @@ def main():
             ref = helpers.run_oracle(orc, sub.to("cpu"), independent=True)
             got = model(sub)
         err = helpers.rel_err(got, ref)
+    E, N, D = G.num_edges(), G.num_nodes(), args.hidden
+    s_kv = 2 if args.precision == "bf16" else 4
+    edge_bytes = (E * (2 * D * s_kv + 8) + N * (2 * D * 4 + 4)) * args.layers          # SURVEY 8(d) edge-phase bytes per layer
     print(json.dumps({"bench": "config3: HGT forward on a batch of ESCA-shape graphs", "graphs": args.graphs,
+                      "precision": args.precision, "edge_phase_bytes_model": edge_bytes,
+                      "edge_phase_model_share_of_forward_at_hbm_peak": edge_bytes / 6545.9e9 / (ms * 1e-3),
                       "nodes": G.num_nodes(), "edges": G.num_edges(), "hidden": args.hidden, "layers": args.layers,
                       "fwd_ms": ms, "edges_per_s": G.num_edges() / (ms * 1e-3), "graph_build_s": t_build,
                       "rel_err_vs_oracle_first_graphs": err, "logits0": out[0].cpu().tolist()}), flush=True)

@@ -93,7 +93,28 @@ CASES = [
          graph=lambda: [synthetic.random_hetero_graph([12, 9], 50, 16, seed=34),
                         synthetic.random_hetero_graph([8, 11], 9, 16, seed=35)],
          kw=dict(in_dim=16, hidden_dim=32, out_dim=3, n_layers=2, n_heads=4, use_norm=True, graph_pooling_type="mean")),
+    # round 2: the ESCA / COAD type count (T = 6: up to 72 relations, most of them a handful of edges)
+    dict(name="hgt_T6_norm", model="HGT",
+         graph=lambda: synthetic.random_hetero_graph([20, 15, 10, 8, 6, 4], 420, 24, seed=61, hub=30),
+         kw=dict(in_dim=24, hidden_dim=64, out_dim=2, n_layers=3, n_heads=4, use_norm=True, graph_pooling_type="mean")),
+    # a relation that EXISTS with zero edges (what DropEdge / dgl.batch of sparse slides produce): it still counts in the
+    # denominator of the cross-relation mean (multi_update_all(..., 'mean')), here in a dgl.batch-style batch of two
+    dict(name="heat4_batch2_zero_edge_rel", model="HEATNet4",
+         graph=lambda: _batched([_drop_relation(synthetic.random_hetero_graph([12, 10], 60, 16, seed=51), 1),
+                                 _drop_relation(synthetic.random_hetero_graph([9, 14], 50, 16, seed=52), 1)]),
+         kw=dict(in_dim=16, hidden_dim=32, out_dim=2, n_layers=2, n_heads=4, dropuout=0.2, graph_pooling_type="mean")),
 ]
+
+
+def _drop_relation(g, index):
+    """The same graph with every edge of its `index`-th canonical etype removed; the (now empty) relation stays."""
+    from wsi_hgnn_b200.hetero_graph import HeteroGraph
+    ce = g.canonical_etypes[index]
+    edges = {c: (g._edges[c][0].clone(), g._edges[c][1].clone()) for c in g.canonical_etypes}
+    edata = {c: {k: v.clone() for k, v in g._edata[c].items()} for c in g.canonical_etypes}
+    edges[ce] = (edges[ce][0][:0], edges[ce][1][:0])
+    edata[ce] = {k: v[:0] for k, v in edata[ce].items()}
+    return HeteroGraph({nt: g.num_nodes(nt) for nt in g.ntypes}, edges, {nt: dict(g._ndata[nt]) for nt in g.ntypes}, edata)
 
 
 def _batched(gs):
@@ -105,7 +126,10 @@ def main():
     mods = dgl_shim.load_reference_models("/root/reference")
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         G = case["graph"]()
         graphs = [G]
         if case.get("independent"):

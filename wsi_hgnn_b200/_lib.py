@@ -55,7 +55,7 @@ PROTOTYPES = {
     "wsi_typed_linear_op": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _I, _P]),
     "wsi_hetero_attn_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _L,
                                  _P, _P, _P]),
-    "wsi_hetero_attn_seg_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P]),
+    "wsi_hetero_attn_seg_fwd": (_I, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P]),
     "wsi_head_perm": (_I, [_I, _I, _P]),
     "wsi_rel_transform": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _L, _P]),
     "wsi_segment_combine": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _P]),

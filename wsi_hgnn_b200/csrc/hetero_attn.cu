@@ -59,6 +59,7 @@ struct AttnArgs {
   int dbg;                    // development only (env WSI_ATTN_DEBUG): 1 = gather only 64 distinct rows, 2 = no bulk copies, 3 = no math
   int* sched;                 // optional int32 [2], zero before the first launch: dynamic work queue (next item | warps done)
   const int* split_row; const int* split_ptr; const int* part_rel;
+  int kv_dtype;               // storage of K / V: 0 = fp32 (every kernel), 1 = fp16, 2 = bf16 (natural-order kernel only)
   int64_t n_src_rows;         // rows of K / V that can be gathered (the footprint that decides register vs TMA-ring kernel); 0 = unknown
 };
 
@@ -665,7 +666,13 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
 // ------------------------------------------------------------------------------------------------
 // Generic path: any D, H (natural column order).  One warp per work item, heads processed one after the
 // other; lane l owns columns {l + 32 j} of the current head (MAXJ >= ceil(d_k / 32)).
-template <int MAXJ, int MODE>
+// KVT = storage type of K / V (float, __half, __nv_bfloat16: the 16-bit forms are the bf16-storage configuration,
+// BASELINE config 3 - gathered bytes halve, the arithmetic stays fp32); ldk / ldv count elements.
+__device__ __forceinline__ float kv_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float kv_ld(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ float kv_ld(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+
+template <int MAXJ, int MODE, typename KVT>
 __global__ void __launch_bounds__(WARPS * 32) attn_fwd_generic_kernel(AttnArgs a) {
   const int lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * WARPS;
@@ -716,15 +723,15 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_generic_kernel(AttnArgs a
             }
             scale = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
           }
-          const float* kr = a.K + (int64_t)src * a.ldk + h * dk;
-          const float* vr = a.V + (int64_t)src * a.ldv + h * dk;
+          const KVT* kr = reinterpret_cast<const KVT*>(a.K) + (int64_t)src * a.ldk + h * dk;
+          const KVT* vr = reinterpret_cast<const KVT*>(a.V) + (int64_t)src * a.ldv + h * dk;
           float vv[MAXJ];
           float d = 0.f;
 #pragma unroll
           for (int j = 0; j < MAXJ; ++j) {
             int c = lane + 32 * j;
-            float kk = c < dk ? __ldg(kr + c) : 0.f;
-            vv[j] = c < dk ? __ldg(vr + c) : 0.f;
+            float kk = c < dk ? kv_ld(kr + c) : 0.f;
+            vv[j] = c < dk ? kv_ld(vr + c) : 0.f;
             d = fmaf(q[j], kk, d);
           }
 #pragma unroll
@@ -774,6 +781,10 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
   const WsiDev& dev = *wsi_dev();
   if (dev.attn_cap > 0 && blocks > sms * dev.attn_cap) blocks = sms * dev.attn_cap;
   if (head_perm) {
+    if (a.kv_dtype != 0) {
+      wsi_set_error("hetero_attn: 16-bit K / V storage is implemented for the natural column order only");
+      return WSI_ERR_UNSUPPORTED;
+    }
     if (!vec_ok(a.D, a.H)) {
       wsi_set_error("hetero_attn: head_perm layout needs D %% 128 == 0, D <= 1024, H a power of two <= 32 (D=%d H=%d)", a.D, a.H);
       return WSI_ERR_UNSUPPORTED;
@@ -831,14 +842,17 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
     return WSI_OK;
   } else {
     int mj = (a.dk + 31) / 32;
-    if (mj <= 1) attn_fwd_generic_kernel<1, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
-    else if (mj <= 2) attn_fwd_generic_kernel<2, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
-    else if (mj <= 4) attn_fwd_generic_kernel<4, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
-    else if (mj <= 8) attn_fwd_generic_kernel<8, MODE><<<blocks, WARPS * 32, 0, stream>>>(a);
-    else {
+    if (mj > 8) {
       wsi_set_error("hetero_attn: d_k=%d > 256 is not supported", a.dk);
       return WSI_ERR_UNSUPPORTED;
     }
+#define GEN(KVT) \
+    if (mj <= 1) attn_fwd_generic_kernel<1, MODE, KVT><<<blocks, WARPS * 32, 0, stream>>>(a); \
+    else if (mj <= 2) attn_fwd_generic_kernel<2, MODE, KVT><<<blocks, WARPS * 32, 0, stream>>>(a); \
+    else if (mj <= 4) attn_fwd_generic_kernel<4, MODE, KVT><<<blocks, WARPS * 32, 0, stream>>>(a); \
+    else attn_fwd_generic_kernel<8, MODE, KVT><<<blocks, WARPS * 32, 0, stream>>>(a);
+    if (a.kv_dtype == 1) { GEN(__half) } else if (a.kv_dtype == 2) { GEN(__nv_bfloat16) } else { GEN(float) }
+#undef GEN
   }
   WSI_CHECK_LAUNCH();
   return WSI_OK;
@@ -942,16 +956,18 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
   return launch_merge(m, wsi_stream(stream));
 }
 
-extern "C" int wsi_hetero_attn_seg_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qseg,
+extern "C" int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* qseg,
                                        int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel,
                                        const int32_t* e_src, const float* rel_pri, int64_t n_segs, int D, int H,
                                        int head_perm, float* out, int64_t ldo, void* stream) {
+  WSI_CHECK_ARG(kv_dtype >= 0 && kv_dtype <= 2, "hetero_attn_seg_fwd: unknown K / V storage type %d", kv_dtype);
   WSI_CHECK_ARG(n_segs >= 0 && n_segs < (1ll << 31), "hetero_attn_seg_fwd: bad n_segs");
   if (n_segs == 0) return WSI_OK;
   WSI_CHECK_ARG(k && v && qseg && seg_ptr && seg_rel && e_src && rel_pri && out, "hetero_attn_seg_fwd: null pointer");
   WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0, "hetero_attn_seg_fwd: D=%d is not a multiple of H=%d", D, H);
   AttnArgs a{};
-  a.K = k; a.ldk = ldk; a.V = v; a.ldv = ldv; a.Q = qseg; a.ldq = ldq;
+  a.K = reinterpret_cast<const float*>(k); a.ldk = ldk; a.V = reinterpret_cast<const float*>(v); a.ldv = ldv; a.Q = qseg; a.ldq = ldq;
+  a.kv_dtype = kv_dtype;
   a.rowptr = seg_ptr; a.e_src = e_src; a.seg_rel = seg_rel; a.rel_pri = rel_pri;
   a.n_items = (int)n_segs; a.D = D; a.H = H; a.dk = D / H;
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));

@@ -102,8 +102,22 @@ class HGTLayer(nn.Module):
         segs = plan.segments()
         grp = _relation_groups(plan, self.edge_dict, id(self.edge_dict))
         S = segs["S"]
-        kvq = ops.typed_linear(x, w_kvq, b_kvq, plan.type_ptr, type_ptr_c=tpc)
-        k, v, q = kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:]
+        opf = ops.matmul_opf()
+        if opf == ops.OPF_BF16 and ops.tc_ok(plan.N, self.in_dim, 2 * D) and ops.tc_ok(plan.N, self.in_dim, D):
+            # bf16 storage of K | V (set_matmul_precision("bf16"): BASELINE config 3): the K|V GEMM writes ONLY the bf16
+            # operand-form copy, the edge kernel gathers half the bytes; Q stays fp32 for the relation transform.
+            # Accumulation is fp32 everywhere.
+            params = param_list(self, "all", self.parameters)
+            w_kv_op, w_q_op = self._packs.get(("kv16", opf, tuple(order)), params, lambda: (
+                ops.to_operand(w_kvq[:, :2 * D].contiguous(), opf), ops.to_operand(w_kvq[:, 2 * D:].contiguous(), opf)))
+            xs = ops.to_operand(x, opf)
+            _, kv = ops.typed_linear_op(xs, w_kv_op, b_kvq[:, :2 * D].contiguous(), plan.type_ptr, 2 * D, want_y=False,
+                                        want_op=True, type_ptr_c=tpc, opf=opf)
+            q, _ = ops.typed_linear_op(xs, w_q_op, b_kvq[:, 2 * D:].contiguous(), plan.type_ptr, D, type_ptr_c=tpc, opf=opf)
+            k, v = kv[:, :D], kv[:, D:]
+        else:
+            kvq = ops.typed_linear(x, w_kvq, b_kvq, plan.type_ptr, type_ptr_c=tpc)
+            k, v, q = kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:]
         # q'_seg = relation_att[r,h] . q[dst,h]   (w_kn=0: y_n = sum_k W[n,k] x_k)
         qseg = ops.rel_transform(q, grp["dst_of_order"], grp["order"], self.relation_att, grp["rel_ptr_c"], grp["R"],
                                  H, dk, False, S)

@@ -125,6 +125,7 @@ def _vec(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
     return t.data_ptr()
 
 
+_KV_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _DT_SIZE = {torch.int32: 4, torch.float32: 4, torch.uint8: 1, torch.int64: 8, torch.bfloat16: 2, torch.float16: 2}
 
 
@@ -339,11 +340,13 @@ def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int
     lib = _lib.load()
     stream = _prep(qseg)
     S = int(qseg.shape[0])
-    kp, ldk = _rows(k, "k")
-    vp, ldv = _rows(v, "v")
+    if k.dtype != v.dtype or k.dtype not in _KV_DTYPE:
+        raise TypeError(f"hetero_attn_seg: k / v must both be fp32, fp16 or bf16, got {k.dtype} / {v.dtype}")
+    kp, ldk = _rows(k, "k", k.dtype)
+    vp, ldv = _rows(v, "v", v.dtype)
     qp, ldq = _rows(qseg, "qseg")
     out = torch.empty((S, D), dtype=torch.float32, device=qseg.device)
-    rc = lib.wsi_hetero_attn_seg_fwd(kp, ldk, vp, ldv, qp, ldq, _vec(seg_ptr, "seg_ptr", torch.int32),
+    rc = lib.wsi_hetero_attn_seg_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, ldq, _vec(seg_ptr, "seg_ptr", torch.int32),
                                      _vec(seg_rel, "seg_rel", torch.int32), _vec(e_src, "e_src", torch.int32),
                                      _vec(rel_pri, "rel_pri"), S, D, H, 1 if use_head_perm else 0,
                                      out.data_ptr(), D, stream)
