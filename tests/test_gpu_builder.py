@@ -30,6 +30,44 @@ def test_knn_small_matches_literal_bruteforce_and_duplicates():
     assert np.array_equal(ei.cpu().numpy(), ref)
 
 
+def test_knn_exact_under_adversarial_geometry():
+    """The cases where a 32-candidate shortlist ranked by the fp32 expanded form ||b||^2 - 2 a.b cannot be trusted: tight
+    clusters of near-duplicate patches (more than 32 points within the rounding error of the form) and features with a
+    large common offset (catastrophic cancellation).  The margin check must send those rows to the exact fallback: the
+    edge list still equals the literal fp64 brute force, bit for bit."""
+    g = torch.Generator().manual_seed(11)
+    base, _ = synthetic.synth_features(700, 64, 2, seed=9)
+    # 60 near-duplicates of one patch (relative perturbation 1e-7 .. 1e-6), scattered over the index range
+    dup = base[5].repeat(60, 1) * (1.0 + 1e-6 * torch.rand(60, 64, generator=g))
+    pos = torch.randperm(700, generator=g)[:60]
+    feats = base.clone()
+    feats[pos] = dup
+    ref = O.exact_knn_edges_bruteforce(feats.numpy(), 9)
+    ei, _, _ = construct_graph_arrays(feats.cuda(), 9)
+    assert np.array_equal(ei.cpu().numpy(), ref)
+    # common offset of 300 per coordinate: ||f||^2 ~ 6e6 while neighbour distances^2 are ~ 50
+    off = base + 300.0
+    ref = O.exact_knn_edges_bruteforce(off.numpy(), 7)
+    ei, _, _ = construct_graph_arrays(off.cuda(), 7)
+    assert np.array_equal(ei.cpu().numpy(), ref)
+
+
+def test_pearson_constant_row_is_nan_like_scipy():
+    """scipy.stats.pearsonr of a constant row is NaN; the reference stores it and types the edge 'neg' (NaN > 0 is False,
+    construct_graph/graph_constructor.py:278-281)."""
+    feats, _ = synthetic.synth_features(40, 32, 2, seed=3)
+    feats[7] = 1.5
+    src = torch.tensor([7, 3, 7], dtype=torch.int64)
+    dst = torch.tensor([2, 7, 7], dtype=torch.int64)
+    sim, et = ops.edge_pearson(feats.cuda(), src.cuda(), dst.cuda())
+    assert torch.isnan(sim).all() and int(et.sum()) == 0
+    import warnings
+    from scipy.stats import pearsonr
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert np.isnan(pearsonr(feats[7].numpy(), feats[2].numpy())[0])
+
+
 def test_knn_too_few_nodes_raises():
     feats, _ = synthetic.synth_features(5, 8, 2, seed=1)
     with pytest.raises(ValueError):

@@ -5,7 +5,11 @@
 // k-NN = (1) dot products of a chunk of query rows with ALL rows by the typed-linear GEMM (tensor cores when the
 // shape allows), (2) a streaming per-row selection of the 32 best candidates by the expanded form
 // ||b||^2 - 2 a.b (warp-resident sorted list, one slot per lane), (3) an exact fp64 direct-form re-rank of those
-// candidates ordered by (distance, index) - so the emitted neighbour lists equal the brute-force answer.
+// candidates ordered by (distance, index), (4) a MARGIN CHECK that makes the result exact by construction, not by
+// luck: every node outside the shortlist has an approximate score >= the worst kept one, so its true score is
+// >= worst_kept - eps (eps bounds the fp32 / split-product error of the expanded form); unless that still exceeds the
+// exact topn-th score, the row is recomputed by exact fp64 brute force over all nodes (near-duplicate patches, features
+// with a large common offset).  The emitted neighbour lists therefore always equal the brute-force answer.
 #include "common.cuh"
 
 namespace {
@@ -64,6 +68,11 @@ knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn,
         thresh_i = __shfl_sync(FULL, best_i, CAND - 1);
       }
     }
+    // largest ||b||^2 seen (error bound of the expanded form)
+    float max_sq = 0.f;
+    for (int64_t c = lane; c < n; c += 32) max_sq = fmaxf(max_sq, __ldg(sqn + c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_sq = fmaxf(max_sq, __shfl_xor_sync(FULL, max_sq, o));
     // exact re-rank: candidate j (held by lane j) gets its fp64 direct-form distance, computed by the whole warp
     const float* a = feat + (q0 + qi) * F;
     double my_d = INFINITY;
@@ -83,9 +92,48 @@ knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn,
       const int ij = __shfl_sync(FULL, best_i, j);
       if (dj < my_d || (dj == my_d && ij < best_i)) ++rank;
     }
-    if (lane < n_cand && rank < topn) {
-      nbr[(int64_t)qi * topn + rank] = best_i;
-      if (nbr_dist) nbr_dist[(int64_t)qi * topn + rank] = (float)sqrt(my_d);
+    // margin check (only when nodes were left out of the shortlist)
+    bool exact_ok = true;
+    if (n > CAND) {
+      double aa = 0.0;
+      for (int c = lane; c < F; c += 32) { const double v = (double)__ldg(a + c); aa = fma(v, v, aa); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) aa += __shfl_xor_sync(FULL, aa, o);
+      // exact topn-th squared distance among the shortlist, as a score ||b||^2 - 2 a.b = ||a - b||^2 - ||a||^2
+      const unsigned who = __ballot_sync(FULL, lane < n_cand && rank == topn - 1);
+      const double dn = __shfl_sync(FULL, my_d, who ? __ffs(who) - 1 : 0);
+      const double eps = ldexp(aa + (double)max_sq, -13);       // >= |fp32 expanded form - true score| for every node
+      exact_ok = who != 0 && (double)thresh - eps > dn - aa + eps;
+    }
+    if (exact_ok) {
+      if (lane < n_cand && rank < topn) {
+        nbr[(int64_t)qi * topn + rank] = best_i;
+        if (nbr_dist) nbr_dist[(int64_t)qi * topn + rank] = (float)sqrt(my_d);
+      }
+      continue;
+    }
+    // fallback: exact fp64 brute force of this row over ALL nodes, (distance, index) order; lane i holds the i-th best
+    double bd = INFINITY;
+    int bi = 0x7fffffff;
+    for (int64_t c = 0; c < n; ++c) {
+      const float* b = feat + c * F;
+      double sdist = 0.0;
+      for (int k = lane; k < F; k += 32) { const double df = (double)__ldg(a + k) - (double)__ldg(b + k); sdist = fma(df, df, sdist); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sdist += __shfl_xor_sync(FULL, sdist, o);
+      const double last_d = __shfl_sync(FULL, bd, topn - 1);
+      const int last_i = __shfl_sync(FULL, bi, topn - 1);
+      if (!(sdist < last_d || (sdist == last_d && (int)c < last_i))) continue;      // warp-uniform
+      const unsigned smaller = __ballot_sync(FULL, bd < sdist || (bd == sdist && bi < (int)c));
+      const int pos = __popc(smaller);
+      const double up_d = __shfl_up_sync(FULL, bd, 1);
+      const int up_i = __shfl_up_sync(FULL, bi, 1);
+      if (lane > pos) { bd = up_d; bi = up_i; }
+      else if (lane == pos) { bd = sdist; bi = (int)c; }
+    }
+    if (lane < topn) {
+      nbr[(int64_t)qi * topn + lane] = bi;
+      if (nbr_dist) nbr_dist[(int64_t)qi * topn + lane] = (float)sqrt(bd);
     }
   }
 }
@@ -115,7 +163,10 @@ edge_pearson_kernel(const float* __restrict__ feat, int F, const int64_t* __rest
     }
     if (lane == 0) {
       double r = ab / (sqrt(aa) * sqrt(bb));
-      r = fmin(1.0, fmax(-1.0, r));
+      // a constant feature row has no correlation: scipy.stats.pearsonr returns NaN (ConstantInputWarning) and the
+      // reference stores it, typing the edge 'neg' because `NaN > 0` is False (graph_constructor.py:278-281) - keep NaN
+      // (fmin / fmax would silently turn it into -1); finite values are clipped to [-1, 1] as scipy does
+      if (r == r) r = fmin(1.0, fmax(-1.0, r));
       sim[e] = (float)r;
       if (etype) etype[e] = r > 0.0 ? 1 : 0;        // 'pos' = 1, 'neg' = 0 (graph_constructor.py:281,296)
     }

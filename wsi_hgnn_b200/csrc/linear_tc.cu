@@ -70,9 +70,14 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Execution barrier over the CTA pair WITHOUT memory ordering: the release / acquire form compiles to MEMBAR.ALL.GPU +
+// ERRBAR on every warp (13 % of the stall samples of the fp16 K|V|Q launch, profiles/r2_typed_linear_tc.txt) and, at the
+// end of the kernel, waits for every outstanding global store to drain.  What the two syncs order is covered otherwise:
+// the mbarrier initialisation by fence.mbarrier_init.release.cluster, TMEM / smem hand-over by the tcgen05 fences and
+// the mbarrier protocol; no global data is exchanged between the CTAs.
 __device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -214,13 +219,32 @@ __global__ void __launch_bounds__(256) convert_operand_kernel(SplitJob a, SplitJ
   wsi_pdl_trigger();                                      // the GEMM that follows may set itself up while this drains
   const int kv = K >> 2;                                  // float4 groups per row (K % 8 == 0)
   const int64_t na = a.rows * kv, total = na + b.rows * kv;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const SplitJob& j = i < na ? a : b;
-    const int64_t li = i < na ? i : i - na;
-    const int64_t r = li / kv;
-    const int c = (int)(li - r * kv) << 2;
-    const float4 x = __ldg(reinterpret_cast<const float4*>(j.src + r * j.ld_src + c));
-    store_operand4<OPF>(reinterpret_cast<uint16_t*>(j.dst) + r * K + c, j.rows * K, x);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // four independent 16 B loads in flight per thread (HBM-bound: 4 B in, 2-4 B out per element)
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 x[4];
+    int64_t idx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      idx[u] = i0 + u * stride;
+      if (idx[u] < total) {
+        const SplitJob& j = idx[u] < na ? a : b;
+        const int64_t li = idx[u] < na ? idx[u] : idx[u] - na;
+        const int64_t r = li / kv;
+        const int c = (int)(li - r * kv) << 2;
+        x[u] = __ldg(reinterpret_cast<const float4*>(j.src + r * j.ld_src + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (idx[u] < total) {
+        const SplitJob& j = idx[u] < na ? a : b;
+        const int64_t li = idx[u] < na ? idx[u] : idx[u] - na;
+        const int64_t r = li / kv;
+        const int c = (int)(li - r * kv) << 2;
+        store_operand4<OPF>(reinterpret_cast<uint16_t*>(j.dst) + r * K + c, j.rows * K, x[u]);
+      }
+    }
   }
 }
 
@@ -706,8 +730,9 @@ int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_d
   SplitJob jb{b_src, b_ld, b_rows, b_dst};
   const int64_t groups = (ja.rows + jb.rows) * (K / 4);
   if (groups == 0) return WSI_OK;
-  int sblocks = (int)((groups + 255) / 256);
+  int sblocks = (int)((groups + 1023) / 1024);
   if (sblocks > sms * 8) sblocks = sms * 8;
+  if (sblocks < 1) sblocks = 1;
   if (opf == WSI_OPF_BF16X3) convert_operand_kernel<WSI_OPF_BF16X3><<<sblocks, 256, 0, stream>>>(ja, jb, K);
   else if (opf == WSI_OPF_F16) convert_operand_kernel<WSI_OPF_F16><<<sblocks, 256, 0, stream>>>(ja, jb, K);
   else convert_operand_kernel<WSI_OPF_BF16><<<sblocks, 256, 0, stream>>>(ja, jb, K);
