@@ -424,6 +424,19 @@ def main():
     cb.record()
     torch.cuda.synchronize()
     h2d_ms = ca.elapsed_time(cb) / 8
+    # the same copies issued by ALL ranks at once: the aggregate host -> device bandwidth of the box bounds e2e at N > 1
+    h2d_all_ms = h2d_ms
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        ca.record()
+        for s_ in slides16[:8]:
+            dbuf.copy_(s_.blob[:dbuf.numel()], non_blocking=True)
+        cb.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([ca.elapsed_time(cb) / 8], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d_all_ms = float(tt)
     # the same with fp32 feature blobs (twice the copy), fewer slides
     slides32 = make_slides("fp32", 8)
     e2e32_value, e2e32_ms, _ = time_stream(slides32)
@@ -516,6 +529,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": n_e2e, "distinct_slides": n_e2e,
                     "h2d_alone_ms": h2d_ms, "h2d_gb_s": h2d / (h2d_ms * 1e-3) / 1e9, "device_forward_ms": t_max / args.steps * 1e3,
+                    "h2d_all_ranks_concurrent_ms": h2d_all_ms,
+                    "h2d_all_ranks_aggregate_gb_s": world * h2d / (h2d_all_ms * 1e-3) / 1e9,
                     "fp32_feature_blobs": {"value": e2e32_value, "ms_per_step": e2e32_ms, "h2d_bytes_per_step": h2d32, "steps": 8},
                     "sync_ms_per_step": e2e_sync_ms,
                     "note": "slide_io.stream_forward over pinned FlatSlide blobs, every slide distinct and never seen before: per "

@@ -148,12 +148,17 @@ int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_
  *   d_agg [N, ldg] = gradient of agg.  dk, dv [N, ld*]: ACCUMULATED into (zero them first; rows are shared between
  *   destinations -> vector atomics); dq [N, lddq]: written; d_e [2] = (d e_linear.weight, d e_linear.bias): accumulated.
  *   Nothing is saved by the forward: the segment softmax is recomputed from k, v, q.
- *   row_order int32 [N] or NULL: processing order of the dst rows (largest in-degree first balances the k-NN hubs). */
+ *   row_order int32 [N] or NULL: processing order of the dst rows (largest in-degree first balances the k-NN hubs).
+ *   Two-pass mode (t_ptr != NULL; no atomics, deterministic): the transposed (SOURCE-major) edge list of the same graph
+ *   - t_ptr int32 [n_src + 1], t_eid int32 [E] (position of the edge in the dst-major arrays), t_dst int32 [E] (its dst
+ *   row) - and coef_ws fp32 [E, 2, H].  The dst-major pass writes dq and the per-(edge, head) coefficients, a second
+ *   kernel walks the source rows and WRITES dk / dv (all n_src rows; no zero fill needed). */
 int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
                         const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
                         const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D, int H,
                         const float* d_agg, int64_t ldg, float* dk, int64_t lddk, float* dv, int64_t lddv, float* dq,
-                        int64_t lddq, float* d_e, const int32_t* row_order, void* stream);
+                        int64_t lddq, float* d_e, const int32_t* row_order, const int32_t* t_ptr, const int32_t* t_eid,
+                        const int32_t* t_dst, int64_t n_src, float* coef_ws, void* stream);
 
 /* Segment form used by HGT (WSI_SCORE_HGT): one work item per (dst,relation) segment.
  *   seg_ptr int32 [S+1] edge range of segment s (dst-major order), seg_rel int32 [S] MODEL relation id,
@@ -368,6 +373,16 @@ int wsi_slide_plan(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t ma
                    void* workspace, int64_t workspace_bytes, void* plan_stream);
 int wsi_slide_run(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, const int32_t* totals_host,
                   float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream, void* stream);
+
+/* Backward of the fused a_linear epilogue (sigma(skip) mix + dropout mask + KeyError passthrough of
+ * models/HEATNet4.py:122-136; forward = the epilogue of wsi_typed_linear_op) in one pass over the rows:
+ *   d_lin = dout * a * mask;  d_x = dout * (1 - a);  d_alpha[t] = sum_{live rows of t} <dout, out - x> / a
+ * with a = sigmoid(skip[t]) on rows whose row_gate != 0, 0 (passthrough) otherwise.  out = the forward's result, x = its
+ * residual input, drop_mask [N, ldm] or NULL, d_alpha [T] is overwritten (d skip[t] = d_alpha[t] * a_t * (1 - a_t)). */
+int wsi_skip_mix_bwd(const float* dout, int64_t ldd, const float* out, int64_t ldo, const float* x, int64_t ldx,
+                     const float* drop_mask, int64_t ldm, const float* skip, const float* row_gate,
+                     const int32_t* type_ptr_host, int T, int D, float* d_lin, int64_t ldl, float* d_x, int64_t lddx,
+                     float* d_alpha, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimizer step of the data-parallel training path (BASELINE config 5): torch.optim.Adam(lr, weight_decay) as the

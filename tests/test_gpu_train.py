@@ -90,3 +90,27 @@ def test_train_step_reduces_loss():
         m.train()
         b = m(G).detach()
     assert helpers.rel_err(a, b) < 1e-4
+
+
+def test_attn_bwd_two_pass_equals_atomic_mode():
+    """wsi_hetero_attn_bwd: the two-pass mode (coefficients + source-major second kernel, no atomics) and the one-pass
+    vector-atomic mode produce the same dK / dV / dQ / d e_linear (up to the atomics' summation order)."""
+    from wsi_hgnn_b200 import ops
+    D, H = 256, 4
+    G = synthetic.synth_slide_graph(900, 32, 3, 6, seed=4, noise_edges=0.3).to("cuda")
+    plan = G.plan()
+    g = torch.Generator().manual_seed(0)
+    kvq = torch.randn(plan.N, 3 * D, generator=g).cuda()
+    d_agg = torch.randn(plan.N, D, generator=g).cuda()
+    ew, eb = torch.tensor([0.7]).cuda(), torch.tensor([-0.1]).cuda()
+    outs = []
+    for transposed in (None, ops.transposed_edges(plan.rowptr, plan.e_src, plan.N)):
+        dk, dv = torch.zeros(plan.N, D, device="cuda"), torch.zeros(plan.N, D, device="cuda")
+        dq = torch.empty(plan.N, D, device="cuda")
+        d_e = ops.hetero_attn_bwd(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim, plan.e_rel,
+                                  plan.node_inv_r, ew, eb, D, H, d_agg, dk, dv, dq, row_order=plan.rows_by_degree(),
+                                  transposed=transposed)
+        outs.append((dk, dv, dq, d_e))
+    for a, b in zip(*outs):
+        assert helpers.rel_err(a, b) < 1e-5
+    assert torch.equal(outs[0][2], outs[1][2])            # dQ does not depend on the mode

@@ -33,7 +33,7 @@ def main():
     from wsi_hgnn_b200.construct_graph import GraphConstructor
     from wsi_hgnn_b200.hetero_graph import pack
     from wsi_hgnn_b200.models import HEATNet4
-    from wsi_hgnn_b200.parallel import FlatGradAllReduce, train_step
+    from wsi_hgnn_b200.parallel import FlatModel, flat_train_step
     from wsi_hgnn_b200.sharding import lpt_assign
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -59,17 +59,17 @@ def main():
                      dropuout=0.2)
     golden_util.fill_params(model, 611)
     model = model.to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=5e-3)
-    red = FlatGradAllReduce(model.parameters())
+    red = FlatModel(model)
+    G.plan().attn_work()
     for _ in range(args.warmup):
-        train_step(model, G, labels, args.batch, opt, red)
+        flat_train_step(model, red, [G], [labels], args.batch, 1e-5, 5e-3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
-        loss = train_step(model, G, labels, args.batch, opt, red)
+        loss = flat_train_step(model, red, [G], [labels], args.batch, 1e-5, 5e-3)
     b.record()
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b) * 1e-3], device=dev, dtype=torch.float64)

@@ -54,7 +54,7 @@ PROTOTYPES = {
     "wsi_to_operand": (_I, [_P, _L, _L, _I, _I, _P, _P]),
     "wsi_typed_linear_op": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _I, _P]),
     "wsi_hetero_attn_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _L,
-                                 _P, _P, _P]),
+                                 _P, _P, _P, _P, _P, _L, _P, _P]),
     "wsi_hetero_attn_seg_fwd": (_I, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P]),
     "wsi_head_perm": (_I, [_I, _I, _P]),
     "wsi_rel_transform": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _L, _P]),
@@ -73,6 +73,7 @@ PROTOTYPES = {
     "wsi_edge_pearson": (_I, [_P, _L, _I, _P, _P, _L, _P, _P, _P]),
     "wsi_heat_forward_workspace_bytes": (_L, [_L, _I, _I, _L, _I, _I]),
     "wsi_heat_forward": (_I, [_P, _L, _I, POINTER(HeatGraph), POINTER(HeatParams), _P, _L, _P, _L, _P, _L, _P]),
+    "wsi_skip_mix_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _L, _P, _P]),
     "wsi_adam_step": (_I, [_P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _F, _I, _P]),
     "wsi_slide_forward_workspace_bytes": (_L, [_L, _L, _I, _I, _I, _L]),
     "wsi_slide_forward": (_I, [POINTER(SlideDesc), POINTER(HeatParams), _L, _P, _P, _L, _P, _L, _P, _P]),

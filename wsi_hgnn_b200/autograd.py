@@ -39,15 +39,47 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor, tp: Sequence[int]) -> torch.Tensor
     return torch.stack([dy[tp[t]:tp[t + 1]].t() @ x[tp[t]:tp[t + 1]] for t in range(T)])
 
 
+def _wgrad_ops(ds: torch.Tensor, xs: torch.Tensor, tp: Sequence[int]) -> torch.Tensor:
+    """dW[t] = dY_t^T X_t from operands ALREADY in the [hi; lo] split form (no re-conversion): hi.hi + hi.lo + lo.hi,
+    fp32 accumulate (cuBLAS bf16 GEMMs with fp32 output)."""
+    T = len(tp) - 1
+    N = int(tp[-1])
+    out = []
+    for t in range(T):
+        a, z = tp[t], tp[t + 1]
+        dh, dl, xh, xl = ds[a:z].t(), ds[N + a:N + z].t(), xs[a:z], xs[N + a:N + z]
+        w = torch.mm(dh, xh, out_dtype=torch.float32)
+        w += torch.mm(dh, xl, out_dtype=torch.float32)
+        w += torch.mm(dl, xh, out_dtype=torch.float32)
+        out.append(w)
+    return torch.stack(out)
+
+
+def _tc_chain(N: int, K: int, n_out: int) -> bool:
+    return (N > 0 and ops.train_opf() == ops.OPF_BF16X3 and _MM_OUT_DTYPE[0] is not False and ops.tc_ok(N, K, n_out)
+            and ops.tc_ok(N, n_out, K))
+
+
 class TypedLinearFn(torch.autograd.Function):
-    """y[rows of type t] = x[rows of type t] @ w[t].T + b[t]   (reference: the per-node-type nn.Linear calls)."""
+    """y[rows of type t] = x[rows of type t] @ w[t].T + b[t]   (reference: the per-node-type nn.Linear calls).
+    On tensor-core shapes every operand is converted to the [hi; lo] split form ONCE: x for the forward GEMM and the
+    weight gradient, dy for the data gradient and the weight gradient."""
 
     @staticmethod
     def forward(ctx, x, w, b, type_ptr: Sequence[int], type_ptr_c):
         x = x.contiguous()
         w = w.contiguous()
+        tp = list(type_ptr)
+        N, K, n_out = int(tp[-1]), int(w.shape[2]), int(w.shape[1])
+        ctx.type_ptr, ctx.type_ptr_c, ctx.has_bias = tp, type_ptr_c, b is not None
+        ctx.chain = _tc_chain(N, K, n_out)
+        if ctx.chain:
+            xs = ops.to_operand(x, ops.OPF_BF16X3)
+            ctx.save_for_backward(xs, w)
+            y, _ = ops.typed_linear_op(xs, ops.to_operand(w, ops.OPF_BF16X3), b.contiguous() if b is not None else None, tp,
+                                       n_out, type_ptr_c=type_ptr_c, opf=ops.OPF_BF16X3)
+            return y
         ctx.save_for_backward(x, w)
-        ctx.type_ptr, ctx.type_ptr_c, ctx.has_bias = list(type_ptr), type_ptr_c, b is not None
         return ops.typed_linear(x, w, b.contiguous() if b is not None else None, type_ptr, type_ptr_c=type_ptr_c,
                                 opf=ops.train_opf())
 
@@ -57,14 +89,66 @@ class TypedLinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         tp = ctx.type_ptr
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:                      # dgrad: the same typed GEMM with W^T
-            # gradients keep the 3-term split (fp32 range and ~2^-17 accuracy): a single fp16 pass would need loss scaling
-            dx = ops.typed_linear(dy, w.transpose(1, 2).contiguous(), None, tp, type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
-        if ctx.needs_input_grad[1]:                      # wgrad: plain dense GEMM per node type (cuBLAS)
-            dw = _wgrad(dy, x, tp)
+        if ctx.chain:
+            ds = ops.to_operand(dy, ops.OPF_BF16X3)
+            if ctx.needs_input_grad[0]:                  # dgrad: the same typed GEMM with W^T
+                wt = ops.to_operand(w.transpose(1, 2).contiguous(), ops.OPF_BF16X3)
+                dx, _ = ops.typed_linear_op(ds, wt, None, tp, int(w.shape[2]), type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
+            if ctx.needs_input_grad[1]:
+                try:
+                    dw = _wgrad_ops(ds, x, tp)
+                    _MM_OUT_DTYPE[0] = True
+                except (TypeError, NotImplementedError, RuntimeError):
+                    if _MM_OUT_DTYPE[0] is True:
+                        raise
+                    _MM_OUT_DTYPE[0] = False             # this torch has no mm(out_dtype=): fp32 cuBLAS on the recombined x
+                    N = int(tp[-1])
+                    xf = x[:N].float() + x[N:].float()
+                    dw = torch.stack([dy[tp[t]:tp[t + 1]].t() @ xf[tp[t]:tp[t + 1]] for t in range(len(tp) - 1)])
+        else:
+            if ctx.needs_input_grad[0]:
+                # gradients keep the 3-term split (fp32 range and ~2^-17 accuracy): a single fp16 pass would need loss scaling
+                dx = ops.typed_linear(dy, w.transpose(1, 2).contiguous(), None, tp, type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
+            if ctx.needs_input_grad[1]:                  # wgrad: plain dense GEMM per node type (cuBLAS)
+                dw = _wgrad(dy, x, tp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.stack([dy[tp[t]:tp[t + 1]].sum(0) for t in range(len(tp) - 1)])
+            db = ops.typed_colsum(dy, tp) if dy.shape[1] % 4 == 0 and dy.shape[0] > 0 else \
+                torch.stack([dy[tp[t]:tp[t + 1]].sum(0) for t in range(len(tp) - 1)])
         return dx, dw, db, None, None
+
+
+class ALinearSkipFn(torch.autograd.Function):
+    """out = drop(agg W_a^T + b_a) * sigma(skip_t) + x * (1 - sigma(skip_t)), passthrough rows keep x
+    (models/HEATNet4.py:121-136) as ONE fused GEMM (the inference epilogue, with the dropout mask) in the forward and ONE
+    row kernel (wsi_skip_mix_bwd) + dgrad / wgrad in the backward.  `lin` is never materialised: d out / d sigma(skip) =
+    drop(lin) - x = (out - x) / sigma(skip)."""
+
+    @staticmethod
+    def forward(ctx, agg, w, b, x, skip_t, mask, gate, type_ptr: Sequence[int], type_ptr_c):
+        tp = list(type_ptr)
+        agg, w, x = agg.contiguous(), w.contiguous(), x.contiguous()
+        ags = ops.to_operand(agg, ops.OPF_BF16X3)
+        out, _ = ops.typed_linear_op(ags, ops.to_operand(w, ops.OPF_BF16X3), b.contiguous(), tp, int(w.shape[1]),
+                                     skip=skip_t.contiguous(), res=x, drop_mask=mask, row_gate=gate, type_ptr_c=type_ptr_c,
+                                     opf=ops.OPF_BF16X3)
+        ctx.save_for_backward(ags, w, x, out, skip_t, mask if mask is not None else out.new_zeros(0), gate)
+        ctx.type_ptr, ctx.type_ptr_c, ctx.has_mask = tp, type_ptr_c, mask is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ags, w, x, out, skip_t, mask, gate = ctx.saved_tensors
+        tp = ctx.type_ptr
+        d_lin, d_x, d_alpha = ops.skip_mix_bwd(dout.contiguous(), out, x, mask if ctx.has_mask else None, skip_t.contiguous(),
+                                               gate, tp, ctx.type_ptr_c)
+        alpha = torch.sigmoid(skip_t)
+        d_skip = d_alpha * alpha * (1 - alpha)
+        ds = ops.to_operand(d_lin, ops.OPF_BF16X3)
+        wt = ops.to_operand(w.transpose(1, 2).contiguous(), ops.OPF_BF16X3)
+        d_agg, _ = ops.typed_linear_op(ds, wt, None, tp, int(w.shape[2]), type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
+        dw = _wgrad_ops(ds, ags, tp)
+        db = ops.typed_colsum(d_lin, tp)
+        return d_agg, dw, db, d_x, d_skip, None, None, None, None
 
 
 class HeteroAttnFn(torch.autograd.Function):
@@ -82,10 +166,15 @@ class HeteroAttnFn(torch.autograd.Function):
     def backward(ctx, d_agg):
         kvq, e_w, e_b = ctx.saved_tensors
         plan, D, H = ctx.plan, ctx.D, ctx.H
-        d_kvq = torch.zeros_like(kvq)
+        # two-pass backward on the transposed edge list (built once per plan): dK / dV rows are written once by their
+        # source row's warp - no atomics, no zero fill of the [N, 3D] gradient
+        if "transposed" not in plan.cache:
+            plan.cache["transposed"] = ops.transposed_edges(plan.rowptr, plan.e_src, plan.N)
+        d_kvq = torch.empty_like(kvq)
         d_e = ops.hetero_attn_bwd(kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:], plan.rowptr, plan.e_src, plan.e_sim,
                                   plan.e_rel, plan.node_inv_r, e_w, e_b, D, H, d_agg.contiguous(), d_kvq[:, :D],
-                                  d_kvq[:, D:2 * D], d_kvq[:, 2 * D:], row_order=plan.rows_by_degree())
+                                  d_kvq[:, D:2 * D], d_kvq[:, 2 * D:], row_order=plan.rows_by_degree(),
+                                  transposed=plan.cache["transposed"])
         return d_kvq, d_e[0].reshape(e_w.shape), d_e[1].reshape(e_b.shape), None, None, None
 
 
@@ -221,10 +310,12 @@ class SegAttnFn(torch.autograd.Function):
         k, v, qseg = ctx.saved_tensors
         plan, D, H, aux = ctx.plan, ctx.D, ctx.H, ctx.aux
         segs = plan.segments()
-        dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+        if "transposed" not in aux:
+            aux["transposed"] = ops.transposed_edges(segs["seg_ptr"], plan.e_src, plan.N)
+        dk, dv = torch.empty((plan.N, D), dtype=torch.float32, device=k.device), torch.empty((plan.N, D), dtype=torch.float32, device=k.device)
         dq = torch.empty_like(qseg)
         ops.hetero_attn_bwd(k, v, qseg, segs["seg_ptr"], plan.e_src, aux["sim"], aux["rel"], aux["inv"], aux["ew"], aux["eb"],
-                            D, H, d_out.contiguous(), dk, dv, dq)
+                            D, H, d_out.contiguous(), dk, dv, dq, transposed=aux["transposed"])
         return dk, dv, dq, None, None, None
 
 

@@ -9,8 +9,12 @@
 //      dQ[row] += ds_e c_e K[src];  dK[src] += ds_e c_e q;  dV[src] += a_e g;   d c_e = ds_e <q, K[src]>
 // (segments of one or two edges, the common case, keep their rows in registers and read them once)
 // with g = dAgg[row] / R_t and c_e = (w sim_e + b) / sqrt(d_k).  dQ rows are owned by their warp; dK / dV rows are
-// shared between destinations and accumulated with 16-byte vector atomics (fp32 red.add: the summation order, not the
-// set of terms, depends on scheduling).  HBM/L2 bound: per edge 3 K + 2 V row reads and 2 row atomics.
+// shared between destinations.  Two ways to accumulate them:
+//   * TWO PASSES, no atomics (given the transposed graph): this kernel writes only the per-(edge, head) coefficients
+//     cK[e,h] = ds_e c_e and cV[e,h] = a_e / R_t; attn_bwd_src_kernel then walks the SOURCE-major edge list - every
+//     source row u owns dK[u] = sum_e cK[e] q[dst e], dV[u] = sum_e cV[e] dAgg[dst e]: the forward's gather pattern
+//     (k-NN out-degree is constant, so it is perfectly balanced), deterministic, rows written once;
+//   * one pass with 16-byte vector atomics (fp32 red.add; measured 3.4x the forward: bound by L2 atomic throughput).
 #include "common.cuh"
 
 namespace {
@@ -32,6 +36,9 @@ struct BwdArgs {
   const int* order;           // optional [n_rows]: processing order of the rows (largest in-degree first)
   int n_rows, D, H;
   float inv_sqrt_dk;
+  float* coef;                // two-pass mode: [E, 2, H] per-edge (cK | cV); nullptr = atomics
+  // second pass (source-major edge list)
+  const int* t_ptr; const int* t_eid; const int* t_dst; int n_src;
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -59,8 +66,22 @@ __device__ __forceinline__ float head_dot(const float4* a, const float4* b, int 
 
 // per-edge gradient contributions of one edge whose K / V rows are in registers
 template <int NV>
-__device__ __forceinline__ void bwd_edge(const BwdArgs& a, int lane, int src, float dsc, float at, const float4* kk,
-                                         const float4* q, const float4* g, float4* dq) {
+__device__ __forceinline__ void bwd_edge(const BwdArgs& a, int lane, int e, int src, float dsc, float at, float invr,
+                                         const float4* kk, const float4* q, const float4* g, float4* dq) {
+  if (a.coef) {                                            // two-pass mode: only the coefficients leave this kernel
+    const int G = 32 / a.H;
+    if (lane % G == 0) {
+      float* c = a.coef + (int64_t)e * 2 * a.H + lane / G;
+      c[0] = dsc;
+      c[a.H] = at * invr;                                  // (g already carries 1 / R_t; the second pass reads raw dAgg)
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      dq[i].x = fmaf(dsc, kk[i].x, dq[i].x); dq[i].y = fmaf(dsc, kk[i].y, dq[i].y);
+      dq[i].z = fmaf(dsc, kk[i].z, dq[i].z); dq[i].w = fmaf(dsc, kk[i].w, dq[i].w);
+    }
+    return;
+  }
   float* dkr = a.dK + (int64_t)src * a.lddk;
   float* dvr = a.dV + (int64_t)src * a.lddv;
 #pragma unroll
@@ -69,6 +90,49 @@ __device__ __forceinline__ void bwd_edge(const BwdArgs& a, int lane, int src, fl
     dq[i].z = fmaf(dsc, kk[i].z, dq[i].z); dq[i].w = fmaf(dsc, kk[i].w, dq[i].w);
     red_add4(dkr + (i * 32 + lane) * 4, make_float4(dsc * q[i].x, dsc * q[i].y, dsc * q[i].z, dsc * q[i].w));
     red_add4(dvr + (i * 32 + lane) * 4, make_float4(at * g[i].x, at * g[i].y, at * g[i].z, at * g[i].w));
+  }
+}
+
+// Second pass of the two-pass mode: one warp per SOURCE row, two out-edges in flight.
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32) attn_bwd_src_kernel(BwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int head = lane / (32 / a.H);
+  const int u = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (u >= a.n_src) return;
+  const int beg = __ldg(a.t_ptr + u), end = __ldg(a.t_ptr + u + 1);
+  float4 ak[NV], av[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { ak[i] = make_float4(0.f, 0.f, 0.f, 0.f); av[i] = ak[i]; }
+  for (int j = beg; j < end; j += 2) {
+    const bool two = j + 1 < end;
+    const int e0 = __ldg(a.t_eid + j), e1 = two ? __ldg(a.t_eid + j + 1) : e0;
+    const int v0 = __ldg(a.t_dst + j), v1 = two ? __ldg(a.t_dst + j + 1) : v0;
+    const float ck0 = __ldg(a.coef + (int64_t)e0 * 2 * a.H + head), cv0 = __ldg(a.coef + (int64_t)e0 * 2 * a.H + a.H + head);
+    const float ck1 = two ? __ldg(a.coef + (int64_t)e1 * 2 * a.H + head) : 0.f;
+    const float cv1 = two ? __ldg(a.coef + (int64_t)e1 * 2 * a.H + a.H + head) : 0.f;
+    float4 q0[NV], q1[NV], g0[NV], g1[NV];
+    const float* qr0 = a.Q + (int64_t)v0 * a.ldq; const float* qr1 = a.Q + (int64_t)v1 * a.ldq;
+    const float* gr0 = a.dAgg + (int64_t)v0 * a.ldg; const float* gr1 = a.dAgg + (int64_t)v1 * a.ldg;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      q0[i] = ld4(qr0 + (i * 32 + lane) * 4); q1[i] = ld4(qr1 + (i * 32 + lane) * 4);
+      g0[i] = ld4(gr0 + (i * 32 + lane) * 4); g1[i] = ld4(gr1 + (i * 32 + lane) * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      ak[i].x = fmaf(ck0, q0[i].x, fmaf(ck1, q1[i].x, ak[i].x)); ak[i].y = fmaf(ck0, q0[i].y, fmaf(ck1, q1[i].y, ak[i].y));
+      ak[i].z = fmaf(ck0, q0[i].z, fmaf(ck1, q1[i].z, ak[i].z)); ak[i].w = fmaf(ck0, q0[i].w, fmaf(ck1, q1[i].w, ak[i].w));
+      av[i].x = fmaf(cv0, g0[i].x, fmaf(cv1, g1[i].x, av[i].x)); av[i].y = fmaf(cv0, g0[i].y, fmaf(cv1, g1[i].y, av[i].y));
+      av[i].z = fmaf(cv0, g0[i].z, fmaf(cv1, g1[i].z, av[i].z)); av[i].w = fmaf(cv0, g0[i].w, fmaf(cv1, g1[i].w, av[i].w));
+    }
+  }
+  float* dkr = a.dK + (int64_t)u * a.lddk;
+  float* dvr = a.dV + (int64_t)u * a.lddv;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    *reinterpret_cast<float4*>(dkr + (i * 32 + lane) * 4) = ak[i];
+    *reinterpret_cast<float4*>(dvr + (i * 32 + lane) * 4) = av[i];
   }
 }
 
@@ -137,8 +201,8 @@ __global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 1) attn_bwd_kernel(B
           const float t0 = head_dot<NV>(g, v0, G), t1 = head_dot<NV>(g, v1, G);
           const float delta = a0 * t0 + a1 * t1;
           const float ds0 = a0 * (t0 - delta), ds1 = a1 * (t1 - delta);
-          bwd_edge<NV>(a, lane, s0, ds0 * c0, a0, k0, q, g, dq);
-          if (n > 1) bwd_edge<NV>(a, lane, s1, ds1 * c1, a1, k1, q, g, dq);
+          bwd_edge<NV>(a, lane, seg_beg, s0, ds0 * c0, a0, invr, k0, q, g, dq);
+          if (n > 1) bwd_edge<NV>(a, lane, seg_beg + 1, s1, ds1 * c1, a1, invr, k1, q, g, dq);
           if (lane % G == 0) {                            // one lane per head carries the head's d c_e
             const float dc0 = ds0 * d0 * a.inv_sqrt_dk, dc1 = n > 1 ? ds1 * d1 * a.inv_sqrt_dk : 0.f;
             dw_acc = fmaf(dc0, sim0, fmaf(dc1, sim1, dw_acc));
@@ -187,8 +251,8 @@ __global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 1) attn_bwd_kernel(B
             const float d0 = head_dot<NV>(q, k0, G), d1 = head_dot<NV>(q, k1, G);
             const float a0 = __expf(d0 * c0 - m) * inv_z, a1 = two ? __expf(d1 * c1 - m) * inv_z : 0.f;
             const float ds0 = a0 * (head_dot<NV>(g, v0, G) - delta), ds1 = a1 * (head_dot<NV>(g, v1, G) - delta);
-            bwd_edge<NV>(a, lane, s0, ds0 * c0, a0, k0, q, g, dq);
-            if (two) bwd_edge<NV>(a, lane, s1, ds1 * c1, a1, k1, q, g, dq);
+            bwd_edge<NV>(a, lane, e, s0, ds0 * c0, a0, invr, k0, q, g, dq);
+            if (two) bwd_edge<NV>(a, lane, e + 1, s1, ds1 * c1, a1, invr, k1, q, g, dq);
             if (lane % G == 0) {
               const float dc0 = ds0 * d0 * a.inv_sqrt_dk, dc1 = two ? ds1 * d1 * a.inv_sqrt_dk : 0.f;
               dw_acc = fmaf(dc0, sim0, fmaf(dc1, sim1, dw_acc));
@@ -213,13 +277,15 @@ __global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 1) attn_bwd_kernel(B
 
 }  // namespace
 
-// dK, dV: ACCUMULATED into (zero them first); dQ: written; d_e [2]: accumulated.
+// dK, dV: ACCUMULATED into (zero them first) in the one-pass mode, WRITTEN (all n_src rows) in the two-pass mode;
+// dQ: written; d_e [2]: accumulated.
 extern "C" int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
                                    const int32_t* rowptr, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
                                    const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows, int D,
                                    int H, const float* d_agg, int64_t ldg, float* dk, int64_t lddk, float* dv,
                                    int64_t lddv, float* dq, int64_t lddq, float* d_e, const int32_t* row_order,
-                                   void* stream) {
+                                   const int32_t* t_ptr, const int32_t* t_eid, const int32_t* t_dst, int64_t n_src,
+                                   float* coef_ws, void* stream) {
   WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hetero_attn_bwd: bad n_rows");
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(k && v && q && rowptr && node_inv_r && e_w && e_b && d_agg && dk && dv && dq && d_e,
@@ -236,6 +302,11 @@ extern "C" int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, 
   a.dAgg = d_agg; a.ldg = ldg; a.dK = dk; a.lddk = lddk; a.dV = dv; a.lddv = lddv; a.dQ = dq; a.lddq = lddq; a.d_e = d_e;
   a.n_rows = (int)n_rows; a.D = D; a.H = H; a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.order = row_order;
+  const bool two_pass = t_ptr != nullptr;
+  WSI_CHECK_ARG(!two_pass || (t_eid && t_dst && coef_ws && n_src >= 0 && n_src < (1ll << 31)),
+                "hetero_attn_bwd: the two-pass mode needs t_ptr, t_eid, t_dst, coef_ws and n_src");
+  a.coef = two_pass ? coef_ws : nullptr;
+  a.t_ptr = t_ptr; a.t_eid = t_eid; a.t_dst = t_dst; a.n_src = (int)n_src;
   const int blocks = (int)((n_rows + WARPS - 1) / WARPS);     // one row per warp: the block scheduler is the queue
   cudaStream_t st = wsi_stream(stream);
   switch (D / 128) {
@@ -244,5 +315,14 @@ extern "C" int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, 
 #undef CASE
   }
   WSI_CHECK_LAUNCH();
+  if (two_pass && n_src > 0) {
+    const int sb = (int)((n_src + WARPS - 1) / WARPS);
+    switch (D / 128) {
+#define CASE(NV) case NV: attn_bwd_src_kernel<NV><<<sb, WARPS * 32, 0, st>>>(a); break;
+      CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+    WSI_CHECK_LAUNCH();
+  }
   return WSI_OK;
 }

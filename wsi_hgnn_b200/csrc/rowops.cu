@@ -387,3 +387,88 @@ extern "C" int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t*
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the fused a_linear epilogue  out = drop(lin) * a + x * (1 - a),  a = sigmoid(skip[t]) on rows with an
+// incoming relation, passthrough (out = x) on the others (models/HEATNet4.py:122-136), in ONE pass over the rows:
+//   d_lin = dout * a * mask        (input of the a_linear dgrad / wgrad)
+//   d_x   = dout * (1 - a)         (dout itself on passthrough rows)
+//   d_alpha[t] += sum over live rows of type t of <dout, out - x> / a      (d out / d a = drop(lin) - x = (out - x) / a)
+// `lin` is not needed (and never materialised by the forward).  One warp per row; d_alpha through one atomic per block.
+namespace {
+__global__ void __launch_bounds__(256)
+skip_mix_bwd_kernel(const float* __restrict__ dout, int64_t ldd, const float* __restrict__ out, int64_t ldo,
+                    const float* __restrict__ x, int64_t ldx, const float* __restrict__ mask, int64_t ldm,
+                    const float* __restrict__ skip, const float* __restrict__ gate, TypeSegs segs, int D,
+                    float* __restrict__ d_lin, int64_t ldl, float* __restrict__ d_x, int64_t lddx, float* __restrict__ d_alpha) {
+  __shared__ float s_part[8];
+  __shared__ int s_type[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_rows = segs.ptr[segs.T];
+  for (int row0 = blockIdx.x * 8; row0 < n_rows; row0 += gridDim.x * 8) {
+    const int row = row0 + warp;
+    float part = 0.f;
+    int t = -1;
+    if (row < n_rows) {
+      t = 0;
+      while (t + 1 < segs.T && row >= segs.ptr[t + 1]) ++t;
+      const bool live = gate == nullptr || __ldg(gate + row) != 0.f;
+      const float a = live ? 1.f / (1.f + expf(-__ldg(skip + t))) : 0.f;
+      const float* dr = dout + (int64_t)row * ldd;
+      const float* orow = out + (int64_t)row * ldo;
+      const float* xr = x + (int64_t)row * ldx;
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dr + c));
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (mask) m = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)row * ldm + c));
+        *reinterpret_cast<float4*>(d_lin + (int64_t)row * ldl + c) = make_float4(g.x * a * m.x, g.y * a * m.y, g.z * a * m.z, g.w * a * m.w);
+        *reinterpret_cast<float4*>(d_x + (int64_t)row * lddx + c) = make_float4(g.x * (1.f - a), g.y * (1.f - a), g.z * (1.f - a), g.w * (1.f - a));
+        if (live) {
+          const float4 o = __ldg(reinterpret_cast<const float4*>(orow + c));
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + c));
+          part = fmaf(g.x, o.x - xv.x, fmaf(g.y, o.y - xv.y, fmaf(g.z, o.z - xv.z, fmaf(g.w, o.w - xv.w, part))));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+      part = live ? part / a : 0.f;
+    }
+    if (lane == 0) { s_part[warp] = part; s_type[warp] = t; }
+    __syncthreads();
+    if (threadIdx.x == 0) {                               // rows of a block are consecutive: at most a few types per block
+      int cur = -1;
+      float acc = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        if (s_type[w] < 0) continue;
+        if (s_type[w] != cur) {
+          if (cur >= 0 && acc != 0.f) atomicAdd(d_alpha + cur, acc);
+          cur = s_type[w]; acc = 0.f;
+        }
+        acc += s_part[w];
+      }
+      if (cur >= 0 && acc != 0.f) atomicAdd(d_alpha + cur, acc);
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+
+extern "C" int wsi_skip_mix_bwd(const float* dout, int64_t ldd, const float* out, int64_t ldo, const float* x, int64_t ldx,
+                                const float* drop_mask, int64_t ldm, const float* skip, const float* row_gate,
+                                const int32_t* type_ptr_host, int T, int D, float* d_lin, int64_t ldl, float* d_x, int64_t lddx,
+                                float* d_alpha, void* stream) {
+  WSI_CHECK_ARG(dout && out && x && skip && type_ptr_host && d_lin && d_x && d_alpha, "skip_mix_bwd: null pointer");
+  TypeSegs segs;
+  WSI_CHECK_ARG(wsi_make_segs(&segs, type_ptr_host, T, 1) == 0, "skip_mix_bwd: bad type_ptr (T=%d)", T);
+  WSI_CHECK_ARG(D >= 4 && D % 4 == 0 && ldd % 4 == 0 && ldo % 4 == 0 && ldx % 4 == 0 && ldl % 4 == 0 && lddx % 4 == 0 &&
+                    (!drop_mask || ldm % 4 == 0), "skip_mix_bwd: D and the row strides must be multiples of 4 floats");
+  const int n_rows = segs.ptr[T];
+  if (n_rows == 0) return WSI_OK;
+  WSI_CHECK_CUDA(cudaMemsetAsync(d_alpha, 0, (size_t)T * sizeof(float), wsi_stream(stream)));
+  int blocks = (n_rows + 7) / 8;
+  { const int sms = wsi_num_sms(); if (sms <= 0) return WSI_ERR_CUDA; if (blocks > sms * 16) blocks = sms * 16; }
+  skip_mix_bwd_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(dout, ldd, out, ldo, x, ldx, drop_mask, ldm, skip, row_gate, segs, D,
+                                                             d_lin, ldl, d_x, lddx, d_alpha);
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}

@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..autograd import HeteroAttnFn, SegmentPoolFn, SkipMixFn, TypedLinearFn
+from ..autograd import ALinearSkipFn, HeteroAttnFn, SegmentPoolFn, SkipMixFn, TypedLinearFn, _tc_chain
 from ..hetero_graph import GraphPlan, HeteroGraph
 from ._packing import PackCache, param_list, stack_linears
 
@@ -168,8 +168,14 @@ class HEATLayer(nn.Module):
         tpc = plan.type_ptr_c()
         kvq = TypedLinearFn.apply(x, torch.cat([wk, wv, wq], 1), torch.cat([bk, bv, bq], 1), plan.type_ptr, tpc)
         agg = HeteroAttnFn.apply(kvq, self.e_linear.weight, self.e_linear.bias, plan, D, H)        # HEATNet4.py:103-119
-        lin = self.drop(TypedLinearFn.apply(agg, wa, ba, plan.type_ptr, tpc))                      # :134
         skip_t = self.skip[torch.tensor(order, device=x.device)]
+        if _tc_chain(plan.N, D, D):
+            # a_linear + dropout + sigma(skip) mix + passthrough as ONE fused GEMM forward / one row kernel backward
+            mask = None
+            if self.training and self.drop.p > 0:
+                mask = F.dropout(torch.ones((plan.N, D), dtype=torch.float32, device=x.device), self.drop.p, True)
+            return ALinearSkipFn.apply(agg, wa, ba, x, skip_t, mask, plan.node_inv_r, plan.type_ptr, tpc)    # :134-135, :129-133
+        lin = self.drop(TypedLinearFn.apply(agg, wa, ba, plan.type_ptr, tpc))                      # :134
         return SkipMixFn.apply(lin, x, skip_t, plan.type_ptr, plan.node_inv_r)                     # :135, passthrough :129-133
 
     def forward_packed(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:

@@ -309,11 +309,28 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
     return agg_split if op_out else agg
 
 
+def transposed_edges(rowptr: torch.Tensor, e_src: torch.Tensor, n_src: int):
+    """Source-major view of a dst-major CSR: (t_ptr int32 [n_src + 1], t_eid int32 [E] = position of the edge in the
+    dst-major arrays, t_dst int32 [E] = its dst row), out-edges of a source in dst-major order (deterministic)."""
+    dev = rowptr.device
+    n_rows = int(rowptr.numel()) - 1
+    deg = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+    e_dst = torch.repeat_interleave(torch.arange(n_rows, device=dev, dtype=torch.int64), deg)
+    src64 = e_src.to(torch.int64)
+    order = torch.argsort(src64, stable=True)
+    t_ptr = torch.zeros(n_src + 1, dtype=torch.int32, device=dev)
+    if src64.numel():
+        t_ptr[1:] = torch.cumsum(torch.bincount(src64, minlength=n_src), 0).to(torch.int32)
+    return t_ptr, order.to(torch.int32).contiguous(), e_dst[order].to(torch.int32).contiguous()
+
+
 def hetero_attn_bwd(k, v, q, rowptr, e_src, e_sim, e_rel, node_inv_r, e_w, e_b, D: int, H: int, d_agg: torch.Tensor,
                     dk: torch.Tensor, dv: torch.Tensor, dq: torch.Tensor,
-                    row_order: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Backward of the HEAT edge attention; see wsi_hetero_attn_bwd.  dk / dv must be zero-filled (accumulated into),
-    dq is written.  row_order: int32 [N] processing order of the rows (GraphPlan.rows_by_degree()).
+                    row_order: Optional[torch.Tensor] = None, transposed=None) -> torch.Tensor:
+    """Backward of the HEAT edge attention; see wsi_hetero_attn_bwd.  dq is written.  Without `transposed`: dk / dv must
+    be zero-filled (vector atomics accumulate into them).  With transposed = transposed_edges(rowptr, e_src, n_src):
+    the two-pass mode without atomics, dk / dv (all n_src rows) are written.
+    row_order: int32 [N] processing order of the rows (GraphPlan.rows_by_degree()).
     -> d_e fp32 [2] = (d e_linear.weight, d e_linear.bias)."""
     lib = _lib.load()
     stream = _prep(q)
@@ -326,11 +343,22 @@ def hetero_attn_bwd(k, v, q, rowptr, e_src, e_sim, e_rel, node_inv_r, e_w, e_b, 
     dvp, lddv = _rows(dv, "dv")
     dqp, lddq = _rows(dq, "dq")
     d_e = torch.zeros(2, dtype=torch.float32, device=q.device)
+    t_ptr = t_eid = t_dst = coef = None
+    n_src = 0
+    if transposed is not None:
+        t_ptr, t_eid, t_dst = transposed
+        n_src = int(t_ptr.numel()) - 1
+        if dk.shape[0] != n_src or dv.shape[0] != n_src:
+            raise ValueError("hetero_attn_bwd: dk / dv must have one row per source row of the transposed edge list")
+        coef = torch.zeros((int(e_src.numel()), 2 * H), dtype=torch.float32, device=q.device)
     rc = lib.wsi_hetero_attn_bwd(kp, ldk, vp, ldv, qp, ldq, _vec(rowptr, "rowptr", torch.int32),
                                  _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
                                  _vec(e_rel, "e_rel", torch.uint8), _vec(node_inv_r, "node_inv_r"),
                                  _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, D, H, gp, ldg, dkp, lddk,
-                                 dvp, lddv, dqp, lddq, d_e.data_ptr(), _vec(row_order, "row_order", torch.int32), stream)
+                                 dvp, lddv, dqp, lddq, d_e.data_ptr(), _vec(row_order, "row_order", torch.int32),
+                                 _vec(t_ptr, "t_ptr", torch.int32), _vec(t_eid, "t_eid", torch.int32),
+                                 _vec(t_dst, "t_dst", torch.int32), n_src, coef.data_ptr() if coef is not None else None,
+                                 stream)
     _lib.check(rc, "wsi_hetero_attn_bwd")
     return d_e
 
@@ -396,6 +424,47 @@ def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, 
                                  float(eps), yp, ldy, stream)
     _lib.check(rc, "wsi_typed_layernorm")
     return y
+
+
+def skip_mix_bwd(dout, out, x, drop_mask, skip, row_gate, type_ptr: Sequence[int], type_ptr_c=None):
+    """Backward of the fused a_linear epilogue; see wsi_skip_mix_bwd.  -> d_lin [N, D], d_x [N, D], d_alpha [T]."""
+    lib = _lib.load()
+    stream = _prep(dout)
+    T = len(type_ptr) - 1
+    N, D = int(dout.shape[0]), int(dout.shape[1])
+    gp, ldd = _rows(dout, "dout")
+    op, ldo = _rows(out, "out")
+    xp, ldx = _rows(x, "x")
+    mp, ldm = _rows(drop_mask, "drop_mask")
+    d_lin = torch.empty((N, D), dtype=torch.float32, device=dout.device)
+    d_x = torch.empty((N, D), dtype=torch.float32, device=dout.device)
+    d_alpha = torch.empty(T, dtype=torch.float32, device=dout.device)
+    tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
+    rc = lib.wsi_skip_mix_bwd(gp, ldd, op, ldo, xp, ldx, mp, ldm, _vec(skip, "skip"), _vec(row_gate, "row_gate"), tp, T, D,
+                              d_lin.data_ptr(), D, d_x.data_ptr(), D, d_alpha.data_ptr(), stream)
+    _lib.check(rc, "wsi_skip_mix_bwd")
+    return d_lin, d_x, d_alpha
+
+
+_TYPE_PTR_DEV = {}
+
+
+def type_ptr_dev(type_ptr: Sequence[int], device) -> torch.Tensor:
+    """int32 device copy of a type_ptr list (cached: a pageable host -> device copy per call would synchronise)."""
+    key = (tuple(int(v) for v in type_ptr), str(device))
+    t = _TYPE_PTR_DEV.get(key)
+    if t is None:
+        if len(_TYPE_PTR_DEV) > 256:
+            _TYPE_PTR_DEV.clear()
+        t = torch.tensor(list(key[0]), dtype=torch.int32).to(device)
+        _TYPE_PTR_DEV[key] = t
+    return t
+
+
+def typed_colsum(dy: torch.Tensor, type_ptr: Sequence[int]) -> torch.Tensor:
+    """[T, n_out] column sums of dy over the rows of every type (the bias gradient of a typed linear): the typed readout
+    kernel with the types as segments."""
+    return segment_pool(dy, type_ptr_dev(type_ptr, dy.device), len(type_ptr) - 1, "sum")
 
 
 def segment_pool(x: torch.Tensor, seg_ptr: torch.Tensor, n_seg: int, op: str) -> torch.Tensor:
