@@ -133,9 +133,11 @@ int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   sched int32 [2] (optional, ZERO before the first launch, left zero): device-side work queue - warps pull items in
  *   list order (largest first = LPT) instead of a static round-robin.
  * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work().
+ *   kv_dtype: storage type of k / v - 0 fp32, 1 fp16, 2 bf16 (ldk / ldv in elements; same lane-grouped order): half the
+ *   gathered bytes (and half the exchange of the node-sharded layer), fp32 scores / softmax / accumulation.
  *   agg_op != NULL: the result is (also) written in operand format `opf` (WSI_OPF_*: 16-bit [2 * n_rows, D] hi rows then
  *   lo rows, or [n_rows, D]), the A operand of wsi_typed_linear_op; agg may then be NULL. */
-int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q, int64_t ldq,
+int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* q, int64_t ldq,
                              const int32_t* e_src, const float* e_sim, const uint8_t* e_rel, const float* node_inv_r,
                              const float* e_w, const float* e_b, int64_t n_rows, int D, int H, const int32_t* items,
                              int64_t n_items, const int32_t* split_row, const int32_t* split_ptr,

@@ -137,7 +137,8 @@ def _model_and_graph(cls_name, pooling, n=3000, T=3, D=128, F=96, L=2, seed=4):
 @pytest.mark.gpu
 @pytest.mark.parametrize("cls_name,pooling", [("HEATNet4", "mean"), ("HEATNet4", "max"), ("HEATNet2", "sum")])
 @pytest.mark.parametrize("world", [1, 2, 4])
-def test_virtual_ranks_match_unsharded_and_oracle(cls_name, pooling, world):
+@pytest.mark.parametrize("kv_wire", ["fp32", "auto"])
+def test_virtual_ranks_match_unsharded_and_oracle(cls_name, pooling, world, kv_wire):
     from wsi_hgnn_b200.node_sharded import run_virtual_ranks
     ours, orc, G = _model_and_graph(cls_name, pooling)
     dev = torch.device("cuda", 0)
@@ -146,15 +147,19 @@ def test_virtual_ranks_match_unsharded_and_oracle(cls_name, pooling, world):
     with torch.no_grad():
         ref_logits, ref_emb = ours(Gd, return_embeddings=True)
         orc_logits = orc(G)
-    logits, per_rank, embs, ranks = run_virtual_ranks(ours, Gd, world)
+    logits, per_rank, embs, ranks = run_virtual_ranks(ours, Gd, world, kv_wire=kv_wire)
     for o in per_rank:                                                   # identical on every rank
         assert torch.equal(o, logits)
+    # fp32 wire: the same arithmetic as the unsharded forward.  "auto": K|V travel (and are gathered) as fp16 - one more
+    # 2^-11 rounding of K and V, inside the 1e-3 bar against the oracle (profiles/r2_precision_study.json)
+    tight = 2e-5 if ranks[0].kv_dtype == torch.float32 else 6e-4
+    assert (ranks[0].kv_dtype == torch.float32) == (kv_wire == "fp32")
     plan = Gd.plan()
     full = torch.cat([ref_emb[nt] for nt in plan.ntypes if ref_emb[nt].shape[0] > 0], 0)
     got = torch.cat(embs, 0)
     assert got.shape == full.shape
-    assert helpers.rel_err(got, full) < 2e-5                             # same kernels, different row grouping
-    assert helpers.rel_err(logits, ref_logits) < 2e-5
+    assert helpers.rel_err(got, full) < tight                            # same kernels, different row grouping
+    assert helpers.rel_err(logits, ref_logits) < tight
     assert helpers.rel_err(logits, orc_logits) < 1e-3                    # north_star tolerance
     assert sum(s.n_loc for s in ranks) == plan.N
 
@@ -169,7 +174,7 @@ def test_virtual_ranks_uneven_and_empty_rank():
     with torch.no_grad():
         ref = ours(Gd)
     N = Gd.plan().N
-    logits, _, _, _ = run_virtual_ranks(ours, Gd, 3, bounds=[0, 700, 700, N])     # rank 1 owns no rows
+    logits, _, _, _ = run_virtual_ranks(ours, Gd, 3, bounds=[0, 700, 700, N], kv_wire="fp32")     # rank 1 owns no rows
     assert helpers.rel_err(logits, ref) < 2e-5
 
 

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--hidden", type=int, default=512)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--kv-wire", default="auto", choices=["auto", "fp32", "16"])
     args = ap.parse_args()
     import torch.distributed as dist
     import golden_util
@@ -83,7 +84,7 @@ def main():
     model = model.to(dev).eval()
 
     t0 = sync_time()
-    sh = NodeShardedHEAT(model, G, comm)
+    sh = NodeShardedHEAT(model, G, comm, kv_wire=args.kv_wire)
     t_plan = sync_time() - t0
     for _ in range(3):
         logits = sh.forward()
@@ -121,7 +122,7 @@ def main():
                           "nodes": args.nodes, "edges": E, "feat": args.feat, "hidden": args.hidden, "layers": args.layers,
                           "knn_pearson_s": t_knn, "plan_s": t_plan, "fwd_ms": float(t_fwd),
                           "fwd_edges_per_s": E / (float(t_fwd) * 1e-3), "rows_per_rank": [sh.bounds[p + 1] - sh.bounds[p] for p in range(world)],
-                          "halo_mb_per_layer_per_rank": sh.halo_bytes_per_layer / 1e6, "logits_identical_on_all_ranks": same,
+                          "halo_mb_per_layer_per_rank": sh.halo_bytes_per_layer / 1e6, "kv_wire": str(sh.kv_dtype), "logits_identical_on_all_ranks": same,
                           "edge_index_bit_exact_vs_single": edges_ok, "rel_err_vs_unsharded": err,
                           "unsharded_fwd_ms_rank0": t_single, "logits": logits.cpu().tolist()}), flush=True)
     if world > 1:

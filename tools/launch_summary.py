@@ -8,7 +8,7 @@ import collections
 import csv
 import sys
 
-OURS = ("typed_linear", "attn_", "segment_pool", "split_bf16", "csr_", "scan_", "work_", "knn_", "edge_pearson",
+OURS = ("typed_linear", "attn_", "segment_pool", "split_bf16", "convert_operand", "row_sqnorm", "skip_mix_bwd", "adam_flat", "csr_", "scan_", "work_", "knn_", "edge_pearson",
         "rel_transform", "layernorm", "segment_combine", "skip_mix", "wgrad", "colsum", "adam", "halo", "gather_rows")
 
 

@@ -48,7 +48,7 @@ PROTOTYPES = {
     "wsi_typed_linear_workspace_bytes": (_L, [_L, _I, _I, _I, _I, _I]),
     "wsi_typed_linear_f32": (_I, [_P, _L, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _P, _L, _P]),
     "wsi_hetero_attn_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _L, _P, _P]),
-    "wsi_hetero_attn_work_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _P, _P, _P, _P,
+    "wsi_hetero_attn_work_fwd": (_I, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _P, _P, _P, _P,
                                       _P, _L, _L, _P, _P, _P, _L, _P, _I, _P]),
     "wsi_typed_linear_tc_ok": (_I, [_L, _I, _I]),
     "wsi_to_operand": (_I, [_P, _L, _L, _I, _I, _P, _P]),

@@ -89,6 +89,23 @@ __device__ __forceinline__ void st_split4(__nv_bfloat16* dst, int64_t lo_off, fl
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 4 consecutive K / V elements of a storage type (fp32: 16 B, fp16 / bf16: 8 B) -> fp32
+__device__ __forceinline__ float4 cvt4(uint2 r, const __half*) {
+  const __half2 a = *reinterpret_cast<const __half2*>(&r.x), b = *reinterpret_cast<const __half2*>(&r.y);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ float4 cvt4(uint2 r, const __nv_bfloat16*) {
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x), b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ float4 ldkv4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldkv4(const __half* p) { return cvt4(__ldg(reinterpret_cast<const uint2*>(p)), p); }
+__device__ __forceinline__ float4 ldkv4(const __nv_bfloat16* p) { return cvt4(__ldg(reinterpret_cast<const uint2*>(p)), p); }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 lds4(const __half* p) { return cvt4(*reinterpret_cast<const uint2*>(p), p); }
+__device__ __forceinline__ float4 lds4(const __nv_bfloat16* p) { return cvt4(*reinterpret_cast<const uint2*>(p), p); }
 
 struct MergeArgs;
 template <int NV> __device__ __noinline__ void merge_row(const MergeArgs& a, int h, int lane);
@@ -98,7 +115,9 @@ template <int NV> __device__ __forceinline__ void vec_fused_merge(const AttnArgs
 // Lane-grouped fast path: D = 128*NV, H | 32.  Lane l owns float4 slots {i*32 + l}, all of head l / G
 // (G = 32/H lanes per head) thanks to the head_perm column order (wsi_head_perm).
 // GROUP = edges whose K (then V) rows are in flight together (bounded by the register file: GROUP * NV float4)
-template <int NV, int MODE, int GROUP, int MINB>
+// KVT = storage type of K / V (float, or __half / __nv_bfloat16: half the gathered bytes, fp32 arithmetic; same
+// lane-grouped column order, a lane's 4-element slot is then an 8-byte load); ldk / ldv count elements.
+template <int NV, int MODE, int GROUP, int MINB, typename KVT>
 __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs a) {
   const int lane = threadIdx.x & 31;
   const int G = 32 / a.H;
@@ -178,9 +197,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs
           for (int u = 0; u < GROUP; ++u) {
             if (u < g) {
               const int src = __shfl_sync(FULL, my_src, j + u);
-              const float* kr = a.K + (int64_t)src * a.ldk;
+              const KVT* kr = reinterpret_cast<const KVT*>(a.K) + (int64_t)src * a.ldk;
 #pragma unroll
-              for (int i = 0; i < NV; ++i) buf[u][i] = ld4(kr + (i * 32 + lane) * 4);
+              for (int i = 0; i < NV; ++i) buf[u][i] = ldkv4(kr + (i * 32 + lane) * 4);
             }
           }
 #pragma unroll
@@ -205,9 +224,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs
           for (int u = 0; u < GROUP; ++u) {
             if (u < g) {
               const int src = __shfl_sync(FULL, my_src, j + u);
-              const float* vr = a.V + (int64_t)src * a.ldv;
+              const KVT* vr = reinterpret_cast<const KVT*>(a.V) + (int64_t)src * a.ldv;
 #pragma unroll
-              for (int i = 0; i < NV; ++i) buf[u][i] = ld4(vr + (i * 32 + lane) * 4);
+              for (int i = 0; i < NV; ++i) buf[u][i] = ldkv4(vr + (i * 32 + lane) * 4);
             }
           }
           float mn = m;
@@ -422,10 +441,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 constexpr int TMA_WARPS = 4;
 constexpr int BMAX = 4;      // edges per batch of the TMA kernel
 
-template <int NV, int MODE>
+template <int NV, int MODE, typename KVT>
 __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_kernel(AttnArgs a, int ring) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int ROW_BYTES = NV * 512, SLOT_BYTES = 2 * ROW_BYTES;
+  constexpr int ROW_BYTES = NV * 128 * (int)sizeof(KVT), SLOT_BYTES = 2 * ROW_BYTES;
+  const KVT* const Kp = reinterpret_cast<const KVT*>(a.K);
+  const KVT* const Vp = reinterpret_cast<const KVT*>(a.V);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = 32 / a.H;
   const int head = lane / G;
@@ -440,7 +461,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
   __syncthreads();
   float ew = 0.f, eb = 0.f;
   if (MODE == MODE_HEAT) { ew = __ldg(a.e_w); eb = __ldg(a.e_b); }
-  const bool kv_adjacent = a.V == a.K + a.D && a.ldk == a.ldv;
+  const bool kv_adjacent = Vp == Kp + a.D && a.ldk == a.ldv;
   int rs = 0;                 // ring slot of the next edge to consume
   uint32_t rpar = 0;          // its mbarrier phase parity
 
@@ -494,10 +515,10 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
               const uint32_t bar = bars_u32 + 8 * s, dst = slots_u32 + s * SLOT_BYTES;
               mbar_expect_tx(bar, SLOT_BYTES);
               if (kv_adjacent) {                        // K|V of a node are one contiguous 2 * D * 4 byte run
-                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, SLOT_BYTES, bar);
+                bulk_g2s(dst, Kp + (int64_t)src * a.ldk, SLOT_BYTES, bar);
               } else {
-                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
-                bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+                bulk_g2s(dst, Kp + (int64_t)src * a.ldk, ROW_BYTES, bar);
+                bulk_g2s(dst + ROW_BYTES, Vp + (int64_t)src * a.ldv, ROW_BYTES, bar);
               }
             }
             if (++s == ring) s = 0;
@@ -532,7 +553,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
             }
           }
           float sc[BMAX];
-          const float* slot_ptr[BMAX];
+          const KVT* slot_ptr[BMAX];
 #pragma unroll
           for (int u = 0; u < BMAX; ++u) {
             sc[u] = -INFINITY;
@@ -542,13 +563,13 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
               uint32_t pu = rpar;
               if (su >= ring) { su -= ring; pu ^= 1; }
               if (a.dbg != 2) mbar_wait(bars_u32 + 8 * su, pu);
-              const float* ks = reinterpret_cast<const float*>(my_slots + (size_t)su * SLOT_BYTES);
+              const KVT* ks = reinterpret_cast<const KVT*>(my_slots + (size_t)su * SLOT_BYTES);
               slot_ptr[u] = ks;
               float d0 = 0.f, d1 = 0.f;
               if (a.dbg != 3)
 #pragma unroll
               for (int i = 0; i < NV; ++i) {
-                const float4 kk = *reinterpret_cast<const float4*>(ks + (i * 32 + lane) * 4);
+                const float4 kk = lds4(ks + (i * 32 + lane) * 4);
                 d0 = fmaf(q[i].x, kk.x, d0); d1 = fmaf(q[i].y, kk.y, d1);
                 d0 = fmaf(q[i].z, kk.z, d0); d1 = fmaf(q[i].w, kk.w, d1);
               }
@@ -579,10 +600,10 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
 #pragma unroll
           for (int u = 0; u < BMAX; ++u) {
             if (u < g && a.dbg != 3) {
-              const float* vs = slot_ptr[u] + NV * 128;
+              const KVT* vs = slot_ptr[u] + NV * 128;
 #pragma unroll
               for (int i = 0; i < NV; ++i) {
-                const float4 vv = *reinterpret_cast<const float4*>(vs + (i * 32 + lane) * 4);
+                const float4 vv = lds4(vs + (i * 32 + lane) * 4);
                 acc[i].x = fmaf(p[u], vv.x, acc[i].x); acc[i].y = fmaf(p[u], vv.y, acc[i].y);
                 acc[i].z = fmaf(p[u], vv.z, acc[i].z); acc[i].w = fmaf(p[u], vv.w, acc[i].w);
               }
@@ -597,10 +618,10 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
               const uint32_t bar = bars_u32 + 8 * rs, dst = slots_u32 + rs * SLOT_BYTES;
               mbar_expect_tx(bar, SLOT_BYTES);
               if (kv_adjacent) {                        // K|V of a node are one contiguous 2 * D * 4 byte run
-                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, SLOT_BYTES, bar);
+                bulk_g2s(dst, Kp + (int64_t)src * a.ldk, SLOT_BYTES, bar);
               } else {
-                bulk_g2s(dst, a.K + (int64_t)src * a.ldk, ROW_BYTES, bar);
-                bulk_g2s(dst + ROW_BYTES, a.V + (int64_t)src * a.ldv, ROW_BYTES, bar);
+                bulk_g2s(dst, Kp + (int64_t)src * a.ldk, ROW_BYTES, bar);
+                bulk_g2s(dst + ROW_BYTES, Vp + (int64_t)src * a.ldv, ROW_BYTES, bar);
               }
             }
             if (++rs == ring) { rs = 0; rpar ^= 1; }
@@ -781,8 +802,8 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
   const WsiDev& dev = *wsi_dev();
   if (dev.attn_cap > 0 && blocks > sms * dev.attn_cap) blocks = sms * dev.attn_cap;
   if (head_perm) {
-    if (a.kv_dtype != 0) {
-      wsi_set_error("hetero_attn: 16-bit K / V storage is implemented for the natural column order only");
+    if (a.kv_dtype != 0 && MODE != MODE_HEAT) {
+      wsi_set_error("hetero_attn: 16-bit K / V storage in the lane-grouped order is implemented for the HEAT scoring only");
       return WSI_ERR_UNSUPPORTED;
     }
     if (!vec_ok(a.D, a.H)) {
@@ -795,10 +816,11 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
     // batches: 655 MB) the TMA bulk-copy ring wins by 1.2-1.3x (100k nodes, k = 8: 0.537 vs 0.707 ms = 6.9 TB/s on the
     // SURVEY 8(d) byte model) because it keeps ~12 KB per warp in flight without spending registers on them.  The
     // item-pipelined variant of round 1 lost at every size and no longer ships.  Knob attn_kernel: 1 / 2 force one.
-    const int64_t kv_bytes = a.n_src_rows * 2 * (int64_t)a.D * 4;
+    const int es = a.kv_dtype == 0 ? 4 : 2;                     // bytes per stored K / V element
+    const int64_t kv_bytes = a.n_src_rows * 2 * (int64_t)a.D * es;
     const bool want_ring = dev.attn_kernel == 2 || (dev.attn_kernel == 0 && kv_bytes >= (80ll << 20));
-    if (!a.attn && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && want_ring) {
-      const int slot_bytes = 2 * a.D * 4;
+    if (!a.attn && (a.ldk % 8 == 0) && (a.ldv % 8 == 0) && want_ring) {      // (bulk copies need 16 B aligned rows)
+      const int slot_bytes = 2 * a.D * es;
       // ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM
       int ring = 12288 / slot_bytes;
       ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
@@ -809,17 +831,23 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       const int per_sm = 200 * 1024 / (smem + 1024) < 1 ? 1 : 200 * 1024 / (smem + 1024);
       if (tb > sms * per_sm) tb = sms * per_sm;
       if (dev.attn_blocks > 0 && tb > sms * dev.attn_blocks) tb = sms * dev.attn_blocks;   // development knob
-      switch (a.D / 128) {
-#define CASE(NV) case NV: { \
+#define RING(NV, KVT) { \
         static std::once_flag once; \
         static cudaError_t aerr = cudaSuccess; \
         std::call_once(once, [] { \
-          aerr = cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }); \
+          aerr = cudaFuncSetAttribute(attn_fwd_tma_kernel<NV, MODE, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }); \
         WSI_CHECK_CUDA(aerr); \
-        attn_fwd_tma_kernel<NV, MODE><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); } break;
+        attn_fwd_tma_kernel<NV, MODE, KVT><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); }
+#define CASE(NV) case NV: \
+        if (MODE == MODE_HEAT && a.kv_dtype == 1) RING(NV, __half) \
+        else if (MODE == MODE_HEAT && a.kv_dtype == 2) RING(NV, __nv_bfloat16) \
+        else RING(NV, float) \
+        break;
+      switch (a.D / 128) {
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
-#undef CASE
       }
+#undef CASE
+#undef RING
       WSI_CHECK_LAUNCH();
       if (fused_merge) *fused_merge = a.split_cnt != nullptr;
       return WSI_OK;
@@ -832,10 +860,15 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
     // by latency per warp, not by bytes in flight, so more (lighter) warps win: GROUP 2 at 4 blocks / SM (128
     // registers) beats GROUP 4 at 3, GROUP 1 at 5-6 and GROUP 2 at 5 (round-1 sweep; those variants no longer ship).
     switch (a.D / 128) {
+#define VEC(NV, GRP, MINB, KVT) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<NV, MODE, GRP, MINB, KVT>, dim3(blocks), dim3(WARPS * 32), 0, stream, a))
 #define CASE(NV, GRP, MINB) case NV: \
-      WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<NV, MODE, GRP, MINB>, dim3(blocks), dim3(WARPS * 32), 0, stream, a)); break;
+      if (MODE == MODE_HEAT && a.kv_dtype == 1) VEC(NV, GRP, MINB, __half); \
+      else if (MODE == MODE_HEAT && a.kv_dtype == 2) VEC(NV, GRP, MINB, __nv_bfloat16); \
+      else VEC(NV, GRP, MINB, float); \
+      break;
       CASE(1, 4, 4) CASE(2, 4, 4) CASE(3, 2, 4) CASE(4, 2, 4) CASE(5, 2, 2) CASE(6, 2, 2) CASE(7, 2, 2) CASE(8, 2, 2)
 #undef CASE
+#undef VEC
     }
     WSI_CHECK_LAUNCH();
     if (fused_merge) *fused_merge = a.split_cnt != nullptr;
@@ -910,7 +943,7 @@ extern "C" int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, 
   return launch<MODE_HEAT>(a, head_perm, wsi_stream(stream));
 }
 
-extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv, const float* q,
+extern "C" int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* q,
                                         int64_t ldq, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
                                         const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows,
                                         int D, int H, const int32_t* items, int64_t n_items,
@@ -924,13 +957,16 @@ extern "C" int wsi_hetero_attn_work_fwd(const float* k, int64_t ldk, const float
   WSI_CHECK_ARG((reinterpret_cast<uintptr_t>(agg_split) & 7) == 0, "hetero_attn_work_fwd: agg_split must be 8 B aligned");
   WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0 && vec_ok(D, H),
                 "hetero_attn_work_fwd: needs the lane-grouped layout (D %% 128 == 0, D <= 1024, H a power of two <= 32), got D=%d H=%d", D, H);
-  WSI_CHECK_ARG(ldk % 4 == 0 && ldv % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0,
-                "hetero_attn_work_fwd: row strides must be multiples of 4 floats");
+  WSI_CHECK_ARG(kv_dtype >= 0 && kv_dtype <= 2, "hetero_attn_work_fwd: unknown K / V storage type %d", kv_dtype);
+  WSI_CHECK_ARG(ldk % 4 == 0 && ldv % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(k) & 7) == 0 && (reinterpret_cast<uintptr_t>(v) & 7) == 0,
+                "hetero_attn_work_fwd: row strides must be multiples of 4 elements, K / V 8 B aligned");
   WSI_CHECK_ARG(n_split == 0 || (split_row && split_ptr && part_rel && part_ms && part_acc && n_part > 0),
                 "hetero_attn_work_fwd: split rows need the partial buffers");
   WSI_CHECK_ARG(!split_cnt || part_split, "hetero_attn_work_fwd: split_cnt needs part_split");
   AttnArgs a{};
-  a.K = k; a.ldk = ldk; a.V = v; a.ldv = ldv; a.Q = q; a.ldq = ldq;
+  a.K = reinterpret_cast<const float*>(k); a.ldk = ldk; a.V = reinterpret_cast<const float*>(v); a.ldv = ldv; a.Q = q; a.ldq = ldq;
+  a.kv_dtype = kv_dtype;
   a.e_src = e_src; a.e_sim = e_sim; a.e_rel = e_rel; a.inv_r = node_inv_r;
   a.e_w = e_w; a.e_b = e_b; a.n_items = (int)n_items; a.D = D; a.H = H; a.dk = D / H;
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));

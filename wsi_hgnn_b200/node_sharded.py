@@ -160,7 +160,12 @@ class NodeShardedHEAT:
         all-reduce) -> finish.
     """
 
-    def __init__(self, model, G: HeteroGraph, comm, row_cost: float = 8.0, bounds: Optional[Sequence[int]] = None):
+    def __init__(self, model, G: HeteroGraph, comm, row_cost: float = 8.0, bounds: Optional[Sequence[int]] = None,
+                 kv_wire: str = "auto"):
+        """kv_wire: storage of the exchanged K|V rows - "fp32", or "16" = the 16-bit type of the current matmul precision
+        (fp16 under the default "fp16" precision, bf16 under "bf16"): the K|V GEMM writes the 16-bit rows straight into
+        this rank's block of the gather buffer, the all-gather moves half the bytes and the edge kernel gathers half the
+        bytes (fp32 scores / softmax / accumulation).  "auto" = "16" whenever the precision has a 16-bit operand type."""
         from .models.heat import _graph_type_order
         if model.training:
             raise NotImplementedError("NodeShardedHEAT is the inference path (model.eval())")
@@ -189,12 +194,29 @@ class NodeShardedHEAT:
         self.work = ops.plan_attn_work(self.rowptr, self.e_rel, self.n_loc, 16) if self.n_loc > 0 else None
         D = model.gcs[0].out_size if len(model.gcs) else model.adapt_ws[0].out_features
         self.D = D
-        self.kv_all = torch.zeros((self.world, self.n_max, 2 * D), dtype=torch.float32, device=dev)
+        if kv_wire not in ("auto", "fp32", "16"):
+            raise ValueError("kv_wire must be 'auto', 'fp32' or '16'")
+        self.opf = ops.matmul_opf()
+        F_in = model.adapt_ws[0].in_features
+        # the tensor-core operand chain (operands converted once, 16-bit copies emitted by the producing kernels) needs
+        # tile-friendly local shapes; otherwise the fp32-API GEMMs (per-call conversion) are used
+        # (decided from the row ranges of ALL ranks - every rank knows them - so that the ranks agree on the wire type)
+        def chain_ok(n):
+            return (n >= 512 and ops.tc_ok(n, F_in, D) and ops.tc_ok(n, D, 2 * D) and ops.tc_ok(n, D, D))
+        all_chain = (len(model.gcs) > 0 and ops.head_perm(D, model.gcs[0].n_heads) is not None and
+                     all(chain_ok(self.bounds[p + 1] - self.bounds[p]) for p in range(self.world)))
+        self.chain = all_chain
+        wire16 = kv_wire != "fp32" and self.opf in (ops.OPF_F16, ops.OPF_BF16) and all_chain
+        if kv_wire == "16" and not wire16:
+            raise NotImplementedError("kv_wire='16' needs the fp16 / bf16 matmul precision and tile-friendly shards on every rank")
+        self.kv_dtype = (torch.float16 if self.opf == ops.OPF_F16 else torch.bfloat16) if wire16 else torch.float32
+        self.kv_all = torch.zeros((self.world, self.n_max, 2 * D), dtype=self.kv_dtype, device=dev)
         self.x: Optional[torch.Tensor] = None
+        self.x_op: Optional[torch.Tensor] = None
         self.q: Optional[torch.Tensor] = None
         self._gather = None
         self.pool_buf: Optional[torch.Tensor] = None
-        self.halo_bytes_per_layer = (self.world - 1) * self.n_max * 2 * D * 4      # received per rank per layer
+        self.halo_bytes_per_layer = (self.world - 1) * self.n_max * 2 * D * self.kv_all.element_size()   # received per rank per layer
 
     # -- phases ----------------------------------------------------------------------------------
     def input_projection(self, feat_local: Optional[torch.Tensor] = None):
@@ -205,6 +227,12 @@ class NodeShardedHEAT:
         if feat_local is None:
             feat_local = packed_features(self.G, self.plan, None)[self.r0:self.r1]
         w_in, b_in = stack_linears(m.adapt_ws, self.order)
+        if self.chain:
+            w_in_op = m._packs.get(("ns_in_op", self.opf, tuple(self.order)), list(m.adapt_ws.parameters()),
+                                   lambda: ops.to_operand(w_in.detach(), self.opf))
+            self.x, self.x_op = ops.typed_linear_op(ops.to_operand(feat_local.contiguous().float(), self.opf), w_in_op,
+                                                    b_in.detach(), self.type_ptr, int(w_in.shape[1]), want_op=True, opf=self.opf)
+            return
         self.x = (ops.typed_linear(feat_local.contiguous(), w_in.detach(), b_in.detach(), self.type_ptr)
                   if self.n_loc > 0 else feat_local.new_zeros((0, w_in.shape[1])))
 
@@ -220,6 +248,18 @@ class NodeShardedHEAT:
         w_kv, b_kv, w_q, b_q = layer._packs.get(("kv|q", tuple(self.order)), [w_kvq, b_kvq], lambda: (
             w_kvq[:, :2 * D].contiguous(), b_kvq[:, :2 * D].contiguous(), w_kvq[:, 2 * D:].contiguous(),
             b_kvq[:, 2 * D:].contiguous()))
+        if self.chain:
+            w_kv_op, w_q_op = layer._packs.get(("ns_kv|q_op", self.opf, tuple(self.order)), [w_kvq, b_kvq], lambda: (
+                ops.to_operand(w_kv, self.opf), ops.to_operand(w_q, self.opf)))
+            mine = self.kv_all[self.rank, :self.n_loc]
+            if self.kv_dtype == torch.float32:
+                ops.typed_linear_op(self.x_op, w_kv_op, b_kv, self.type_ptr, 2 * D, out=mine, opf=self.opf)
+            else:                                    # the 16-bit rows straight into this rank's block of the gather buffer
+                ops.typed_linear_op(self.x_op, w_kv_op, b_kv, self.type_ptr, 2 * D, want_y=False, want_op=True, out_op=mine,
+                                    opf=self.opf)
+            self._gather = self.comm.all_gather_blocks(self.kv_all, async_op=True)
+            self.q, _ = ops.typed_linear_op(self.x_op, w_q_op, b_q, self.type_ptr, D, opf=self.opf)
+            return
         if self.n_loc > 0:
             ops.typed_linear(self.x, w_kv, b_kv, self.type_ptr, out=self.kv_all[self.rank, :self.n_loc])
         self._gather = self.comm.all_gather_blocks(self.kv_all, async_op=True)
@@ -237,6 +277,14 @@ class NodeShardedHEAT:
         if self.n_loc == 0:
             return
         kv = self.kv_all.view(self.world * self.n_max, 2 * D)
+        if self.chain:
+            wa_op = layer._packs.get(("ns_a_op", self.opf, tuple(self.order)), [wa], lambda: ops.to_operand(wa, self.opf))
+            agg_op = ops.hetero_attn_work(kv[:, :D], kv[:, D:], self.q, self.work, self.e_src, self.e_sim, self.e_rel,
+                                          self.inv_r, layer.e_linear.weight, layer.e_linear.bias, D, H, op_out=True,
+                                          opf=self.opf)
+            self.x, self.x_op = ops.typed_linear_op(agg_op, wa_op, ba, self.type_ptr, D, skip=skip, res=self.x,
+                                                    row_gate=self.inv_r, want_op=l + 1 < len(self.model.gcs), opf=self.opf)
+            return
         agg = ops.hetero_attn_work(kv[:, :D], kv[:, D:], self.q, self.work, self.e_src, self.e_sim,
                                    self.e_rel, self.inv_r, layer.e_linear.weight, layer.e_linear.bias, D, H)
         self.x = ops.typed_linear(agg, wa, ba, self.type_ptr, skip=skip, res=self.x, row_gate=self.inv_r)
@@ -290,11 +338,11 @@ class NodeShardedHEAT:
         return self.x
 
 
-def run_virtual_ranks(model, G: HeteroGraph, world: int, row_cost: float = 8.0, bounds=None):
+def run_virtual_ranks(model, G: HeteroGraph, world: int, row_cost: float = 8.0, bounds=None, kv_wire: str = "auto"):
     """Drive `world` virtual ranks of the node-sharded forward in one process on one device (LocalComm).
     -> (logits of rank 0, [per-rank logits], [per-rank embeddings], ranks)."""
     hub = LocalComm(world)
-    ranks = [NodeShardedHEAT(model, G, hub.view(r), row_cost, bounds) for r in range(world)]
+    ranks = [NodeShardedHEAT(model, G, hub.view(r), row_cost, bounds, kv_wire) for r in range(world)]
     with torch.no_grad():
         for s in ranks:
             s.input_projection()

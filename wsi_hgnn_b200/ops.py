@@ -218,9 +218,11 @@ def typed_linear_op(x_op: torch.Tensor, w_op: torch.Tensor, bias: Optional[torch
                     skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
                     drop_mask: Optional[torch.Tensor] = None, row_gate: Optional[torch.Tensor] = None,
                     row_scale: Optional[torch.Tensor] = None, want_y: bool = True, want_op: bool = False,
-                    type_ptr_c=None, opf: Optional[int] = None):
+                    type_ptr_c=None, opf: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                    out_op: Optional[torch.Tensor] = None):
     """tcgen05 typed linear on operands already in operand form (to_operand); see wsi_typed_linear_op.
-    -> y fp32 [N, n_out] (or None), y in operand form (or None)."""
+    -> y fp32 [N, n_out] (or None), y in operand form (or None).  out / out_op: caller-owned destinations (out_op: a
+    dense, contiguous tensor of the operand form's shape and dtype, e.g. a rank's block of an all-gather buffer)."""
     lib = _lib.load()
     stream = _prep(x_op)
     opf = matmul_opf(opf)
@@ -231,8 +233,12 @@ def typed_linear_op(x_op: torch.Tensor, w_op: torch.Tensor, bias: Optional[torch
         if t.dtype != dt or not t.is_contiguous() or tuple(t.shape) != (rows, K):
             raise ValueError(f"typed_linear_op: {name} must be a contiguous {dt} [{rows}, {K}] tensor, "
                              f"got {t.dtype} {tuple(t.shape)}")
-    y = torch.empty((N, n_out), dtype=torch.float32, device=x_op.device) if want_y else None
-    ys = torch.empty((operand_rows(N, opf), n_out), dtype=dt, device=x_op.device) if want_op else None
+    y = (out if out is not None else torch.empty((N, n_out), dtype=torch.float32, device=x_op.device)) if want_y else None
+    if y is not None and (tuple(y.shape) != (N, n_out) or y.dtype != torch.float32 or not y.is_contiguous()):
+        raise ValueError("typed_linear_op: out must be a contiguous fp32 [N, n_out] tensor")
+    ys = (out_op if out_op is not None else torch.empty((operand_rows(N, opf), n_out), dtype=dt, device=x_op.device)) if want_op else None
+    if ys is not None and (tuple(ys.shape) != (operand_rows(N, opf), n_out) or ys.dtype != dt or not ys.is_contiguous()):
+        raise ValueError(f"typed_linear_op: out_op must be a contiguous {dt} [{operand_rows(N, opf)}, {n_out}] tensor")
     rp, ldres = _rows(res, "res")
     mp, ldm = _rows(drop_mask, "drop_mask")
     tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
@@ -277,8 +283,10 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
     stream = _prep(q)
     opf = matmul_opf(opf)
     N = int(q.shape[0])
-    kp, ldk = _rows(k, "k")
-    vp, ldv = _rows(v, "v")
+    if k.dtype != v.dtype or k.dtype not in _KV_DTYPE:
+        raise TypeError(f"hetero_attn_work: k / v must both be fp32, fp16 or bf16, got {k.dtype} / {v.dtype}")
+    kp, ldk = _rows(k, "k", k.dtype)
+    vp, ldv = _rows(v, "v", v.dtype)
     qp, ldq = _rows(q, "q")
     agg = agg_split = None
     if op_out:
@@ -292,7 +300,7 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
     if n_part > 0:
         part_ms = torch.empty((n_part, 64), dtype=torch.float32, device=q.device)
         part_acc = torch.empty((n_part, D), dtype=torch.float32, device=q.device)
-    rc = lib.wsi_hetero_attn_work_fwd(kp, ldk, vp, ldv, qp, ldq, _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
+    rc = lib.wsi_hetero_attn_work_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, ldq, _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
                                       _vec(e_rel, "e_rel", torch.uint8), _vec(node_inv_r, "node_inv_r"),
                                       _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, D, H,
                                       _vec(work["items"], "items", torch.int32), work["n_items"],
