@@ -368,13 +368,36 @@ int wsi_slide_forward(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t
                       void* stream);
 /* The same in two phases WITHOUT any host synchronisation inside the library, for a software-pipelined caller:
  *   wsi_slide_plan : CSR build + work-list counting on plan_stream; the 4 totals are copied asynchronously to totals_host
- *   wsi_slide_run  : after the caller has made sure plan_stream passed those copies (an event it recorded after
- *                    wsi_slide_plan - in the streaming evaluator that event is a whole slide old): work-list fill on
- *                    plan_stream, forward on `stream` behind an event.  Same desc / params / workspace in both calls. */
+ *   wsi_slide_run  : after the caller has WAITED ON THE HOST until plan_stream passed those copies (an event it
+ *                    recorded after wsi_slide_plan - in the streaming evaluator that event is a whole slide old):
+ *                    work-list fill and forward on `stream`.  Same desc / params / workspace in both calls. */
 int wsi_slide_plan(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, int32_t* totals_host,
                    void* workspace, int64_t workspace_bytes, void* plan_stream);
 int wsi_slide_run(const wsi_slide_desc* s, const wsi_heat_params* p, int64_t max_part, const int32_t* totals_host,
                   float* logits, int64_t ldl, void* workspace, int64_t workspace_bytes, void* plan_stream, void* stream);
+
+/* The whole streaming evaluator natively: a LIST of flat slides in pinned host memory -> their logits, in one host call.
+ * Per slide: ONE host -> device copy of the blob (+ the small plan head the call derives from the header counts),
+ * wsi_slide_plan on a plan stream, wsi_slide_run + logits D2H on `stream`; three slides in flight on three streams
+ * (two of them created and destroyed by the call), `depth` device slots.  Synchronises `stream` before returning.
+ *   dev_ws: depth * wsi_stream_slot_bytes(max blob bytes, max nodes, max edges, F, D, T, max R, n_out) device bytes
+ *   host_ws: depth * wsi_stream_host_slot_bytes(max nodes, T, max R) PINNED host bytes;  logits_host: pinned [n, n_out]
+ *   p->seg_scale is ignored (taken from every slide's own head). */
+typedef struct wsi_stream_slide {
+  const void* blob_host;              /* pinned: features | src | dst | sim (FlatSlide layout) */
+  int64_t nbytes;
+  int64_t off_feat, off_src, off_dst, off_sim;   /* byte offsets inside the blob */
+  int64_t n_nodes, n_edges;
+  int32_t T, R, F, feat_is_op;        /* feat_is_op != 0: features stored in the operand format p->opf (fp16) */
+  const int32_t* nodes_per_type_host; /* [T] */
+  const int32_t* edges_per_rel_host;  /* [R] relation-major edge counts */
+  const int32_t* rel_src_type_host;   /* [R] node-type index of the relation's sources */
+  const int32_t* rel_dst_type_host;   /* [R] ... destinations */
+} wsi_stream_slide;
+int64_t wsi_stream_slot_bytes(int64_t max_nbytes, int64_t max_nodes, int64_t max_edges, int F, int D, int T, int R, int n_out);
+int64_t wsi_stream_host_slot_bytes(int64_t max_nodes, int T, int R);
+int wsi_stream_forward(const wsi_stream_slide* slides, int64_t n_slides, const wsi_heat_params* p, float* logits_host,
+                       int depth, void* dev_ws, int64_t dev_ws_bytes, void* host_ws, int64_t host_ws_bytes, void* stream);
 
 /* Backward of the fused a_linear epilogue (sigma(skip) mix + dropout mask + KeyError passthrough of
  * models/HEATNet4.py:122-136; forward = the epilogue of wsi_typed_linear_op) in one pass over the rows:

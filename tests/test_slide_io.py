@@ -62,9 +62,12 @@ def test_flat_rejects_batched_and_short_blob():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("native", ["1", "0"])
+@pytest.mark.parametrize("native", ["loop", "1", "0"])
 def test_stream_forward_matches_per_slide_forward(native, monkeypatch):
-    monkeypatch.setenv("WSI_STREAM_NATIVE", native)
+    # "loop": the whole pipeline in one C call (wsi_stream_forward, the default); "1": Python-issued pipeline over
+    # wsi_slide_plan / wsi_slide_run; "0": Python-issued planner and forward ops
+    monkeypatch.setenv("WSI_STREAM_LOOP", "native" if native == "loop" else "python")
+    monkeypatch.setenv("WSI_STREAM_NATIVE", "0" if native == "0" else "1")
     dev = torch.device("cuda", 0)
     T = 3
     kw = dict(in_dim=64, hidden_dim=128, out_dim=3, n_layers=2, n_heads=4, dropuout=0.0)
@@ -227,6 +230,7 @@ def test_stream_forward_native_slide_call(monkeypatch):
     with torch.no_grad():
         ref = [ours(g.to(dev)).cpu() for g in graphs]
     monkeypatch.setenv("WSI_STREAM_NATIVE", "1")
+    monkeypatch.setenv("WSI_STREAM_LOOP", "python")
     for _ in range(2):                                                # second pass reuses the per-slot workspaces
         outs = list(stream_forward(ours, slides, dev))
         assert len(outs) == len(ref)

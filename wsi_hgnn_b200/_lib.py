@@ -37,6 +37,14 @@ class SlideDesc(Structure):
                 ("n_nodes", c_int64), ("n_edges", c_int64), ("T", c_int32), ("R", c_int32), ("chunk", c_int32)]
 
 
+class StreamSlide(Structure):
+    """struct wsi_stream_slide (include/wsi_hgnn.h)."""
+    _fields_ = [("blob_host", c_void_p), ("nbytes", c_int64), ("off_feat", c_int64), ("off_src", c_int64), ("off_dst", c_int64),
+                ("off_sim", c_int64), ("n_nodes", c_int64), ("n_edges", c_int64), ("T", c_int32), ("R", c_int32), ("F", c_int32),
+                ("feat_is_op", c_int32), ("nodes_per_type_host", c_void_p), ("edges_per_rel_host", c_void_p),
+                ("rel_src_type_host", c_void_p), ("rel_dst_type_host", c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/wsi_hgnn.h declares (checked by tests)
 PROTOTYPES = {
     "wsi_abi_version": (_I, []),
@@ -73,6 +81,9 @@ PROTOTYPES = {
     "wsi_edge_pearson": (_I, [_P, _L, _I, _P, _P, _L, _P, _P, _P]),
     "wsi_heat_forward_workspace_bytes": (_L, [_L, _I, _I, _L, _I, _I]),
     "wsi_heat_forward": (_I, [_P, _L, _I, POINTER(HeatGraph), POINTER(HeatParams), _P, _L, _P, _L, _P, _L, _P]),
+    "wsi_stream_slot_bytes": (_L, [_L, _L, _L, _I, _I, _I, _I, _I]),
+    "wsi_stream_host_slot_bytes": (_L, [_L, _I, _I]),
+    "wsi_stream_forward": (_I, [POINTER(StreamSlide), _L, POINTER(HeatParams), _P, _I, _P, _L, _P, _L, _P]),
     "wsi_skip_mix_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _L, _P, _P]),
     "wsi_adam_step": (_I, [_P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _F, _I, _P]),
     "wsi_slide_forward_workspace_bytes": (_L, [_L, _L, _I, _I, _I, _L]),

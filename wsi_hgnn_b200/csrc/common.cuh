@@ -108,6 +108,7 @@ struct WsiDev {
   int attn_separate_merge; // merge the hub rows in a second launch
   int attn_static;         // static round-robin instead of the device work queue
   int no_pdl;              // launch without programmatic stream serialization
+  int stream_debug;        // wsi_stream_forward: bit 0 = copy only the first `depth` blobs, bit 1 = no plan / forward
 };
 WsiDev* wsi_dev();
 static inline bool wsi_pdl_enabled() { return wsi_dev()->no_pdl == 0; }

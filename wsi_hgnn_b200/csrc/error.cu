@@ -55,7 +55,7 @@ extern "C" int wsi_dev_set(const char* key, int value) {
   struct { const char* k; int* p; } tab[] = {
       {"tc_debug", &g_dev.tc_debug}, {"tc_no_tma_store", &g_dev.tc_no_tma_store}, {"attn_debug", &g_dev.attn_debug}, {"attn_kernel", &g_dev.attn_kernel},
       {"attn_ring", &g_dev.attn_ring}, {"attn_blocks", &g_dev.attn_blocks}, {"attn_cap", &g_dev.attn_cap},
-      {"attn_separate_merge", &g_dev.attn_separate_merge}, {"attn_static", &g_dev.attn_static}, {"no_pdl", &g_dev.no_pdl}};
+      {"attn_separate_merge", &g_dev.attn_separate_merge}, {"attn_static", &g_dev.attn_static}, {"no_pdl", &g_dev.no_pdl}, {"stream_debug", &g_dev.stream_debug}};
   for (auto& e : tab)
     if (!strcmp(e.k, key)) { __atomic_store_n(e.p, value, __ATOMIC_RELAXED); return WSI_OK; }
   wsi_set_error("dev_set: unknown knob '%s'", key);

@@ -289,6 +289,68 @@ class _HEATBase(nn.Module):
             return None
         return self._forward_native_core(plan, feat, independent, hasattr(self, "head"), False)
 
+    def stream_native(self, slides, dev, depth: int, ctx: Dict):
+        """Logits of a LIST of flat slides through wsi_stream_forward (the whole pipelined loop in one C call).
+        -> list of [1, out] pinned host tensors, or None when a slide is not the one-call driver's shape (the caller
+        then uses the Python-issued pipeline)."""
+        import ctypes
+        from types import SimpleNamespace
+        from .. import _lib
+        lib = _lib.load()
+        n = len(slides)
+        if n == 0 or not self.native_forward:
+            return None
+        names0 = list(slides[0].header["ntypes"])
+        n_out = self.head.out_features if hasattr(self, "head") else next(iter(self.linears_prediction.values())).out_features
+        F_model = self.adapt_ws[0].in_features
+        for s in slides:
+            h = s.header
+            N, E = sum(h["num_nodes"]), sum(h["num_edges"])
+            if (N == 0 or E == 0 or list(h["ntypes"]) != names0 or h["feat_dim"] != F_model or h["feat_name"] != "feat"
+                    or not s.blob.is_pinned() or not self._native_ok(None, SimpleNamespace(N=N), None, n_out)):
+                return None
+        order = [self.node_dict[nt] for nt in names0]
+        P0, _keep = self._native_params(None, order, names0, hasattr(self, "head"))
+        fp16_feat = [s.feat_is_fp16() for s in slides]
+        if any(fp16_feat) and P0.opf != ops.OPF_F16:
+            return None
+        P = _lib.HeatParams.from_buffer_copy(P0)
+        T = len(names0)
+        tix = {nt: i for i, nt in enumerate(names0)}
+        arr = (_lib.StreamSlide * n)()
+        keep = []
+        max_nb = max_n = max_e = max_r = 0
+        for i, s in enumerate(slides):
+            h = s.header
+            N, E, R = sum(h["num_nodes"]), sum(h["num_edges"]), len(h["canonical_etypes"])
+            ints = (ctypes.c_int32 * (T + 3 * R))(*h["num_nodes"], *h["num_edges"],
+                                                 *[tix[ce[0]] for ce in h["canonical_etypes"]],
+                                                 *[tix[ce[2]] for ce in h["canonical_etypes"]])
+            keep.append(ints)
+            base = ctypes.addressof(ints)
+            a = arr[i]
+            a.blob_host, a.nbytes = s.blob.data_ptr(), h["nbytes"]
+            off = h["off"]
+            a.off_feat, a.off_src, a.off_dst, a.off_sim = off["feat"], off["src"], off["dst"], off["sim"]
+            a.n_nodes, a.n_edges, a.T, a.R, a.F, a.feat_is_op = N, E, T, R, F_model, 1 if fp16_feat[i] else 0
+            a.nodes_per_type_host, a.edges_per_rel_host = base, base + 4 * T
+            a.rel_src_type_host, a.rel_dst_type_host = base + 4 * (T + R), base + 4 * (T + 2 * R)
+            max_nb, max_n, max_e, max_r = max(max_nb, h["nbytes"]), max(max_n, N), max(max_e, E), max(max_r, R)
+        depth = max(3, min(int(depth), 16))
+        slot = lib.wsi_stream_slot_bytes(max_nb, max_n, max_e, F_model, P.D, T, max_r, P.n_out)
+        hslot = lib.wsi_stream_host_slot_bytes(max_n, T, max_r)
+        ws = ctx.get("native_ws")
+        if ws is None or ws[0].numel() < depth * slot + 256 or ws[1].numel() < depth * hslot:
+            ws = (torch.empty(int(depth * slot * 1.25) + 256, dtype=torch.uint8, device=dev),
+                  torch.empty(int(depth * hslot * 1.25), dtype=torch.uint8).pin_memory())
+            ctx["native_ws"] = ws
+        logits = torch.empty((n, P.n_out), dtype=torch.float32).pin_memory()
+        stream = ops._prep(ws[0])
+        rc = lib.wsi_stream_forward(arr, n, ctypes.byref(P), logits.data_ptr(), depth, ws[0].data_ptr(), ws[0].numel(),
+                                    ws[1].data_ptr(), ws[1].numel(), stream)
+        _lib.check(rc, "wsi_stream_forward")
+        return [logits[i:i + 1] for i in range(n)]
+
     def slide_plan_native(self, slide, blob: torch.Tensor, head: torch.Tensor, slot: Dict, plan_stream):
         """Phase 1 of blob -> logits of ONE flat slide (wsi_slide_plan: CSR + work-list counting enqueued on `plan_stream`,
         totals on their way to pinned host memory; nothing waits).  `head` = the slide's plan head (FlatSlide._plan_head)

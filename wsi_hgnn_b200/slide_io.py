@@ -357,7 +357,36 @@ def stream_forward(model, slides: Iterable[FlatSlide], device, depth: int = 4, t
     # or `threaded` select the Python-issued stages.
     native = (hasattr(model, "slide_plan_native") and os.environ.get("WSI_STREAM_NATIVE", "1") != "0" and not threaded)
     try:
-        if native:
+        # the whole loop in ONE C call (wsi_stream_forward: copies, planner and forwards issued by native code, three
+        # slides in flight) whenever every slide is the one-call driver's shape; WSI_STREAM_LOOP=python keeps the
+        # Python-issued pipeline below (same kernels, same order)
+        if native and hasattr(model, "stream_native") and os.environ.get("WSI_STREAM_LOOP", "native") == "native":
+            it_all = iter(slides)
+            while True:
+                chunk = []
+                for s_ in it_all:
+                    chunk.append(s_)
+                    if len(chunk) >= 256:
+                        break
+                if not chunk:
+                    break
+                with torch.no_grad():
+                    outs = model.stream_native(chunk, dev, nbuf, ctx)
+                if outs is None:                                    # not all slides fit: Python-issued pipeline for these
+                    ctx["busy"] = False
+                    old = os.environ.get("WSI_STREAM_LOOP")
+                    os.environ["WSI_STREAM_LOOP"] = "python"
+                    try:
+                        outs = list(stream_forward(model, chunk, dev, depth, threaded))
+                    finally:
+                        if old is None:
+                            os.environ.pop("WSI_STREAM_LOOP", None)
+                        else:
+                            os.environ["WSI_STREAM_LOOP"] = old
+                    ctx["busy"] = True
+                for o in outs:
+                    yield o
+        elif native:
             # software pipeline, one slide apart per stage, no host wait on anything younger than a whole slide:
             #   upload(i + 2)  ->  plan(i + 1): wsi_slide_plan (CSR + counting, totals -> pinned host, event)  ->
             #   run(i): wait for slide i's plan event (recorded one iteration ago), wsi_slide_run (fill + forward), logits D2H
