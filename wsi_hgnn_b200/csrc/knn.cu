@@ -18,8 +18,9 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int CAND = 32;          // candidates kept per query row (>= topn + slack)
 
 __global__ void __launch_bounds__(256)
-row_sqnorm_kernel(const float* __restrict__ feat, int64_t n, int F, float* __restrict__ out) {
+row_sqnorm_kernel(const float* __restrict__ feat, int64_t n, int F, float* __restrict__ out, unsigned* __restrict__ max_bits) {
   const int lane = threadIdx.x & 31;
+  float mx = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * 8) {
     const float* p = feat + row * F;
     float s = 0.f;
@@ -27,7 +28,10 @@ row_sqnorm_kernel(const float* __restrict__ feat, int64_t n, int F, float* __res
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     if (lane == 0) out[row] = s;
+    mx = fmaxf(mx, s);
   }
+  // largest ||b||^2 of the matrix (the error bound of the margin check): non-negative floats order like their bit patterns
+  if (lane == 0 && mx > 0.f) atomicMax(max_bits, __float_as_uint(mx));
 }
 
 __device__ __forceinline__ bool pair_less(float d1, int i1, float d2, int i2) {
@@ -39,8 +43,9 @@ __device__ __forceinline__ bool pair_less(float d1, int i1, float d2, int i2) {
 __global__ void __launch_bounds__(256)
 knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn, const float* __restrict__ dot,
                   int64_t ld_dot, int64_t n, int F, int topn, int64_t q0, int n_q, int32_t* __restrict__ nbr,
-                  float* __restrict__ nbr_dist) {
+                  float* __restrict__ nbr_dist, const unsigned* __restrict__ max_bits) {
   const int lane = threadIdx.x & 31;
+  const float max_sq = __uint_as_float(__ldg(max_bits));
   for (int qi = blockIdx.x * 8 + (threadIdx.x >> 5); qi < n_q; qi += gridDim.x * 8) {
     const float* drow = dot + (int64_t)qi * ld_dot;
     float best_d = INFINITY;       // lane i holds the i-th smallest pair so far
@@ -68,11 +73,6 @@ knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn,
         thresh_i = __shfl_sync(FULL, best_i, CAND - 1);
       }
     }
-    // largest ||b||^2 seen (error bound of the expanded form)
-    float max_sq = 0.f;
-    for (int64_t c = lane; c < n; c += 32) max_sq = fmaxf(max_sq, __ldg(sqn + c));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) max_sq = fmaxf(max_sq, __shfl_xor_sync(FULL, max_sq, o));
     // exact re-rank: candidate j (held by lane j) gets its fp64 direct-form distance, computed by the whole warp
     const float* a = feat + (q0 + qi) * F;
     double my_d = INFINITY;
@@ -189,7 +189,7 @@ extern "C" int64_t wsi_knn_workspace_bytes(int64_t n, int F, int topn, int64_t q
   if (n <= 0 || q_end <= q_begin) return 0;
   const int64_t qc = query_chunk(n, q_end - q_begin);
   const int64_t n4 = (n + 3) & ~(int64_t)3;       // row pitch of the dot-product matrix (16 B rows for the tcgen05 epilogue)
-  return align256(n * 4) + align256(qc * n4 * 4) + align256(wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0, WSI_OPF_BF16X3));
+  return align256(n * 4 + 16) + align256(qc * n4 * 4) + align256(wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0, WSI_OPF_BF16X3));
 }
 
 extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64_t q_begin, int64_t q_end,
@@ -208,14 +208,16 @@ extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64
   char* ws = (char*)workspace;
   float* sqn = (float*)ws;
   const int64_t n4 = (n + 3) & ~(int64_t)3;
-  float* dot = (float*)(ws + align256(n * 4));
-  void* lin_ws = ws + align256(n * 4) + align256(qc * n4 * 4);
+  unsigned* max_bits = (unsigned*)(ws + n * 4);              // one word behind the squared norms
+  float* dot = (float*)(ws + align256(n * 4 + 16));
+  void* lin_ws = ws + align256(n * 4 + 16) + align256(qc * n4 * 4);
   const int64_t lin_ws_bytes = wsi_typed_linear_workspace_bytes(qc, F, (int)n, 1, 0, WSI_OPF_BF16X3);
   const int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
   const int64_t grid_cap = (int64_t)sms * 16;
   int blocks = (int)((n + 7) / 8 < grid_cap ? (n + 7) / 8 : grid_cap);
-  row_sqnorm_kernel<<<blocks, 256, 0, st>>>(feat, n, F, sqn);
+  WSI_CHECK_CUDA(cudaMemsetAsync(max_bits, 0, 4, st));
+  row_sqnorm_kernel<<<blocks, 256, 0, st>>>(feat, n, F, sqn, max_bits);
   WSI_CHECK_LAUNCH();
   for (int64_t q0 = q_begin; q0 < q_end; q0 += qc) {
     const int n_q = (int)((q_end - q0) < qc ? (q_end - q0) : qc);
@@ -225,7 +227,7 @@ extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64
     if (rc != WSI_OK) return rc;
     int sb = (int)((n_q + 7) / 8 < grid_cap ? (n_q + 7) / 8 : grid_cap);
     knn_select_kernel<<<sb, 256, 0, st>>>(feat, sqn, dot, n4, n, F, topn, q0, n_q, nbr + (q0 - q_begin) * topn,
-                                          nbr_dist ? nbr_dist + (q0 - q_begin) * topn : nullptr);
+                                          nbr_dist ? nbr_dist + (q0 - q_begin) * topn : nullptr, max_bits);
     WSI_CHECK_LAUNCH();
   }
   return WSI_OK;

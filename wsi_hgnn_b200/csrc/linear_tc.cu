@@ -430,8 +430,12 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
           const int col0 = col_w + c * 32;
-          if (col0 >= a.n_out) break;                                // warp-uniform
+          if (col0 >= a.n_out || (a.dbg & 4)) break;                 // warp-uniform
           float v[32];
+          if (a.dbg & 16) {                                          // development: no TMEM read
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          } else
           tc_ld_32x32(taddr + c * 32, v);
           float4 bb[8];
 #pragma unroll
@@ -467,7 +471,7 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(a.dbg & 8)) {
             if (ep.y) tma_store_2d(&tmY, stg_u32 + (two ? store_buf * (EPI_WARP_FLOATS * 4) : 0), col0, row0);
             if (TERMS == 1 && a.y_op && ((c & 1) || col0 + 32 >= a.n_out))
               tma_store_2d(&tmY16, stg_u32 + EPI_WARP_FLOATS * 4, col0 & ~63, row0);
