@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 15
+#define WSI_ABI_VERSION 16
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -408,6 +408,17 @@ int wsi_skip_mix_bwd(const float* dout, int64_t ldd, const float* out, int64_t l
                      const float* drop_mask, int64_t ldm, const float* skip, const float* row_gate,
                      const int32_t* type_ptr_host, int T, int D, float* d_lin, int64_t ldl, float* d_x, int64_t lddx,
                      float* d_alpha, void* stream);
+
+/* Weight gradient of the typed linear on tcgen05 (wgrad_tc.cu): dw[t] = dY_t^T . X_t, [T, M, Nn] fp32, overwritten.
+ * Replaces autograd's per-type `grad_output.t() @ input` of every per-node-type nn.Linear (trainer/train_gnn.py:68-71
+ * through models/HEATNet4.py:100-102,134,202).  dy_op / x_op are the WSI_OPF_BF16X3 operand forms ([2N, M] / [2N, Nn]
+ * bf16: hi rows, then lo rows) the forward and data-gradient GEMMs already hold - nothing is transposed or re-converted;
+ * product = hi.hi + hi.lo + lo.hi, fp32 accumulate.  M % 32 == 0, Nn % 8 == 0, N >= 512 (wsi_typed_wgrad_supported).
+ * workspace: wsi_typed_wgrad_workspace_bytes(M, Nn, type_ptr_host, T) bytes (the per-chunk partial products). */
+int wsi_typed_wgrad_supported(int64_t n_rows, int M, int Nn, int T);
+int64_t wsi_typed_wgrad_workspace_bytes(int M, int Nn, const int32_t* type_ptr_host, int T);
+int wsi_typed_wgrad(const void* dy_op, const void* x_op, int M, int Nn, const int32_t* type_ptr_host, int T, float* dw,
+                    void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimizer step of the data-parallel training path (BASELINE config 5): torch.optim.Adam(lr, weight_decay) as the

@@ -133,6 +133,41 @@ def test_typed_linear_op_chain(counts, K, n_out, precision):
     assert only is None and torch.equal(ys2, ys)
 
 
+@pytest.mark.parametrize("counts,M,Nn", [([700, 0, 130, 5000, 63, 64, 1], 256, 128), ([4000, 2500, 1200], 1536, 512),
+                                         ([3000, 3001], 512, 1024), ([1000, 900, 300, 80, 50, 20], 96, 72),
+                                         ([20, 30, 600], 64, 64), ([30000, 9000, 1], 512, 512)])
+def test_typed_wgrad(counts, M, Nn):
+    """dW[t] = dY_t^T X_t on tcgen05 (MN-major operands, K-chunked over the rows of a type, SIMT tail) against fp64:
+    ragged and empty types, types below one 64-row block, M / Nn below and across the 256-wide tile."""
+    torch.manual_seed(len(counts) * 1000 + M + Nn)
+    dev = torch.device("cuda", 0)
+    tp = [0]
+    for c in counts:
+        tp.append(tp[-1] + c)
+    N = tp[-1]
+    assert ops.typed_wgrad_ok(N, M, Nn, len(counts))
+    dy = torch.randn(N, M, device=dev) * torch.rand(N, 1, device=dev)
+    x = torch.randn(N, Nn, device=dev)
+    got = ops.typed_wgrad(ops.to_operand(dy, ops.OPF_BF16X3), ops.to_operand(x, ops.OPF_BF16X3), tp)
+    want = torch.stack([dy[tp[t]:tp[t + 1]].double().t() @ x[tp[t]:tp[t + 1]].double() for t in range(len(counts))])
+    assert got.shape == want.shape
+    for t in range(len(counts)):
+        if counts[t] == 0:
+            assert not got[t].any()
+        else:
+            assert rel(got[t], want[t]) < 3e-5, (t, counts[t])
+
+
+def test_typed_wgrad_refuses_unfit_shapes():
+    assert not ops.typed_wgrad_ok(100, 512, 512, 3)          # too few rows
+    assert not ops.typed_wgrad_ok(5000, 200, 512, 3)         # n_out not a multiple of 32
+    assert not ops.typed_wgrad_ok(5000, 512, 100, 3)         # K not a multiple of 8
+    dev = torch.device("cuda", 0)
+    with pytest.raises(Exception):
+        ops.typed_wgrad(torch.zeros(2000, 200, dtype=torch.bfloat16, device=dev),
+                        torch.zeros(2000, 512, dtype=torch.bfloat16, device=dev), [0, 1000])
+
+
 def test_typed_linear_tc_refuses_unfit_shapes():
     """impl=2 (force tcgen05) must fail loudly - never silently take another path."""
     x = torch.randn(8, 7, device="cuda")

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--max-nodes", type=int, default=20000)
+    ap.add_argument("--cuda-profile", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off: steady-state launch list)")
     args = ap.parse_args()
     import torch.distributed as dist
     import golden_util
@@ -67,10 +69,15 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.cuda_profile:
+        torch.cuda.profiler.start()
     a.record()
     for _ in range(args.steps):
         loss = flat_train_step(model, red, [G], [labels], args.batch, 1e-5, 5e-3)
     b.record()
+    if args.cuda_profile:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b) * 1e-3], device=dev, dtype=torch.float64)
     tot = torch.tensor([float(G.num_edges()), float(G.num_nodes()), float(loss)], device=dev, dtype=torch.float64)

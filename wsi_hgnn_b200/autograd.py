@@ -39,25 +39,41 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor, tp: Sequence[int]) -> torch.Tensor
     return torch.stack([dy[tp[t]:tp[t + 1]].t() @ x[tp[t]:tp[t + 1]] for t in range(T)])
 
 
-def _wgrad_ops(ds: torch.Tensor, xs: torch.Tensor, tp: Sequence[int]) -> torch.Tensor:
+def _wgrad_ops(ds: torch.Tensor, xs: torch.Tensor, tp: Sequence[int], type_ptr_c=None) -> torch.Tensor:
     """dW[t] = dY_t^T X_t from operands ALREADY in the [hi; lo] split form (no re-conversion): hi.hi + hi.lo + lo.hi,
-    fp32 accumulate (cuBLAS bf16 GEMMs with fp32 output)."""
+    fp32 accumulate, on tcgen05 (wsi_typed_wgrad: the operands are read MN-major, nothing is transposed in memory)."""
+    if ops.typed_wgrad_ok(int(tp[-1]), int(ds.shape[1]), int(xs.shape[1]), len(tp) - 1):
+        return ops.typed_wgrad(ds, xs, tp, type_ptr_c)
+    return _wgrad_ops_cublas(ds, xs, tp)
+
+
+def _wgrad_ops_cublas(ds: torch.Tensor, xs: torch.Tensor, tp: Sequence[int]) -> torch.Tensor:
+    """The same product for shapes wsi_typed_wgrad does not take (n_out not a multiple of 32): per-type cuBLAS bf16
+    GEMMs with fp32 output on strided views of the operand planes."""
     T = len(tp) - 1
     N = int(tp[-1])
-    out = []
-    for t in range(T):
-        a, z = tp[t], tp[t + 1]
-        dh, dl, xh, xl = ds[a:z].t(), ds[N + a:N + z].t(), xs[a:z], xs[N + a:N + z]
-        w = torch.mm(dh, xh, out_dtype=torch.float32)
-        w += torch.mm(dh, xl, out_dtype=torch.float32)
-        w += torch.mm(dl, xh, out_dtype=torch.float32)
-        out.append(w)
-    return torch.stack(out)
+    if _MM_OUT_DTYPE[0] is not False:
+        try:
+            out = []
+            for t in range(T):
+                a, z = tp[t], tp[t + 1]
+                dh, dl, xh, xl = ds[a:z].t(), ds[N + a:N + z].t(), xs[a:z], xs[N + a:N + z]
+                w = torch.mm(dh, xh, out_dtype=torch.float32)
+                w += torch.mm(dh, xl, out_dtype=torch.float32)
+                w += torch.mm(dl, xh, out_dtype=torch.float32)
+                out.append(w)
+            _MM_OUT_DTYPE[0] = True
+            return torch.stack(out)
+        except (TypeError, NotImplementedError, RuntimeError):
+            if _MM_OUT_DTYPE[0] is True:
+                raise
+            _MM_OUT_DTYPE[0] = False                     # this torch has no mm(out_dtype=): fp32 cuBLAS on the recombined planes
+    df, xf = ds[:N].float() + ds[N:].float(), xs[:N].float() + xs[N:].float()
+    return torch.stack([df[tp[t]:tp[t + 1]].t() @ xf[tp[t]:tp[t + 1]] for t in range(T)])
 
 
 def _tc_chain(N: int, K: int, n_out: int) -> bool:
-    return (N > 0 and ops.train_opf() == ops.OPF_BF16X3 and _MM_OUT_DTYPE[0] is not False and ops.tc_ok(N, K, n_out)
-            and ops.tc_ok(N, n_out, K))
+    return N > 0 and ops.train_opf() == ops.OPF_BF16X3 and ops.tc_ok(N, K, n_out) and ops.tc_ok(N, n_out, K)
 
 
 class TypedLinearFn(torch.autograd.Function):
@@ -95,16 +111,7 @@ class TypedLinearFn(torch.autograd.Function):
                 wt = ops.to_operand(w.transpose(1, 2).contiguous(), ops.OPF_BF16X3)
                 dx, _ = ops.typed_linear_op(ds, wt, None, tp, int(w.shape[2]), type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
             if ctx.needs_input_grad[1]:
-                try:
-                    dw = _wgrad_ops(ds, x, tp)
-                    _MM_OUT_DTYPE[0] = True
-                except (TypeError, NotImplementedError, RuntimeError):
-                    if _MM_OUT_DTYPE[0] is True:
-                        raise
-                    _MM_OUT_DTYPE[0] = False             # this torch has no mm(out_dtype=): fp32 cuBLAS on the recombined x
-                    N = int(tp[-1])
-                    xf = x[:N].float() + x[N:].float()
-                    dw = torch.stack([dy[tp[t]:tp[t + 1]].t() @ xf[tp[t]:tp[t + 1]] for t in range(len(tp) - 1)])
+                dw = _wgrad_ops(ds, x, tp, ctx.type_ptr_c)
         else:
             if ctx.needs_input_grad[0]:
                 # gradients keep the 3-term split (fp32 range and ~2^-17 accuracy): a single fp16 pass would need loss scaling
@@ -146,7 +153,7 @@ class ALinearSkipFn(torch.autograd.Function):
         ds = ops.to_operand(d_lin, ops.OPF_BF16X3)
         wt = ops.to_operand(w.transpose(1, 2).contiguous(), ops.OPF_BF16X3)
         d_agg, _ = ops.typed_linear_op(ds, wt, None, tp, int(w.shape[2]), type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
-        dw = _wgrad_ops(ds, ags, tp)
+        dw = _wgrad_ops(ds, ags, tp, ctx.type_ptr_c)
         db = ops.typed_colsum(d_lin, tp)
         return d_agg, dw, db, d_x, d_skip, None, None, None, None
 

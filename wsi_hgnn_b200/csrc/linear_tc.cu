@@ -32,6 +32,7 @@
 #include <mutex>
 
 #include "epilogue.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -57,115 +58,6 @@ constexpr int smem_bytes_of(int terms) { return 1024 + stages_of(terms) * stage_
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 
-// ------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-// Execution barrier over the CTA pair WITHOUT memory ordering: the release / acquire form compiles to MEMBAR.ALL.GPU +
-// ERRBAR on every warp (13 % of the stall samples of the fp16 K|V|Q launch, profiles/r2_typed_linear_tc.txt) and, at the
-// end of the kernel, waits for every outstanding global store to drain.  What the two syncs order is covered otherwise:
-// the mbarrier initialisation by fence.mbarrier_init.release.cluster, TMEM / smem hand-over by the tcgen05 fences and
-// the mbarrier protocol; no global data is exchanged between the CTAs.
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// arrive on a barrier anywhere in the cluster (address from mapa)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-// same without release semantics: for signals that order nothing in memory (the epilogue's "accumulator drained": the
-// TMEM reads are already complete - tcgen05.wait::ld - and a release would first wait for the warp's global stores)
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-// TMA tile load into THIS CTA's smem; completion bytes are posted on `cluster_bar`, the leader CTA's barrier
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t cluster_bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
-}
-// TMA tile store smem -> global (bulk async group of the issuing thread); the box is clipped at the tensor bounds
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// generic-proxy smem writes -> visible to the async proxy (TMA) that reads them next
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// arrive (once the MMAs issued so far retire) on the barrier at this smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc_commit_mask(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-// D[tmem, 256 x N over the CTA pair] (+)= A[smem] . B[smem]^T, 16-bit x 16-bit -> fp32 (operand type in the descriptor)
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i).  Asynchronous:
-// the registers are valid after tc_ld_wait().
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile (rows of 64 16-bit elements = 128 B, 8-row swizzle atoms of 1024 B):
-// start address >> 4 | LBO 1 (unused for swizzled K-major) | SBO 1024 B >> 4 | version 1 (sm_100) | SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 // kind::f16 instruction descriptor: fp32 accumulate (bit 4), A / B format at bits 7 / 10 (0 = fp16, 1 = bf16), both
 // K-major, N >> 3 at bit 17, M >> 4 at bit 24
 inline uint32_t idesc_of(bool bf16) {
@@ -582,40 +474,6 @@ typed_linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// [rows, cols] row-major (row pitch `pitch_bytes`), box [box_rows, box_cols] with box_cols * element size == 128 B,
-// 128 B swizzle, out-of-bounds elements read as 0 / not written
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch_bytes, int box_rows, int box_cols,
-             CUtensorMapDataType dt) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) { wsi_set_error("typed_linear(tcgen05): cuTensorMapEncodeTiled is not available"); return WSI_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { wsi_set_error("typed_linear(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r); return WSI_ERR_CUDA; }
-  return WSI_OK;
-}
-
 inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline int terms_of(int opf) { return opf == WSI_OPF_BF16X3 ? 2 : 1; }   // 16-bit matrices per operand

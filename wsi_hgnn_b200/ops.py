@@ -469,6 +469,32 @@ def type_ptr_dev(type_ptr: Sequence[int], device) -> torch.Tensor:
     return t
 
 
+def typed_wgrad_ok(N: int, M: int, Nn: int, T: int) -> bool:
+    return bool(_lib.load().wsi_typed_wgrad_supported(int(N), int(M), int(Nn), int(T)))
+
+
+def typed_wgrad(dy_op: torch.Tensor, x_op: torch.Tensor, type_ptr: Sequence[int], type_ptr_c=None) -> torch.Tensor:
+    """dw[t] = dY_t^T X_t  [T, M, Nn] fp32 on tcgen05 from the OPF_BF16X3 operand forms of dy ([2N, M]) and x ([2N, Nn]);
+    see wsi_typed_wgrad."""
+    lib = _lib.load()
+    stream = _prep(dy_op)
+    T = len(type_ptr) - 1
+    N = int(type_ptr[-1])
+    M, Nn = int(dy_op.shape[1]), int(x_op.shape[1])
+    for name, t, cols in (("dy_op", dy_op, M), ("x_op", x_op, Nn)):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or tuple(t.shape) != (2 * N, cols):
+            raise ValueError(f"typed_wgrad: {name} must be a contiguous bf16 [{2 * N}, {cols}] tensor, got {t.dtype} {tuple(t.shape)}")
+    tpc = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
+    dw = torch.empty((T, M, Nn), dtype=torch.float32, device=dy_op.device)
+    ws_bytes = int(lib.wsi_typed_wgrad_workspace_bytes(M, Nn, tpc, T))
+    if ws_bytes < 0:
+        raise ValueError("typed_wgrad: bad type_ptr")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy_op.device)
+    _lib.check(lib.wsi_typed_wgrad(dy_op.data_ptr(), x_op.data_ptr(), M, Nn, tpc, T, dw.data_ptr(), ws.data_ptr(), ws_bytes,
+                                   stream), "wsi_typed_wgrad")
+    return dw
+
+
 def typed_colsum(dy: torch.Tensor, type_ptr: Sequence[int]) -> torch.Tensor:
     """[T, n_out] column sums of dy over the rows of every type (the bias gradient of a typed linear): the typed readout
     kernel with the types as segments."""
