@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 16
+#define WSI_ABI_VERSION 17
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -97,6 +97,10 @@ int wsi_typed_linear_f32(const float* x, int64_t ldx, const float* w, const floa
  *   Returns WSI_ERR_UNSUPPORTED when wsi_typed_linear_tc_ok(N, K, n_out) == 0. */
 int wsi_typed_linear_tc_ok(int64_t n_rows, int K, int n_out);
 int wsi_to_operand(const float* src, int64_t ld_src, int64_t rows, int K, int opf, void* dst, void* stream);
+/* dst row i = operand form of src row row_idx[i] (int32 [rows]): gather + conversion in one pass - the (dst, relation)
+ * segments of HGT pick up their dst node's query (models/HGT.py:88-92 moved to the dst side). */
+int wsi_gather_to_operand(const float* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, int opf, void* dst,
+                          void* stream);
 int wsi_typed_linear_op(const void* x_op, const void* w_op, const float* bias, int K, int n_out,
                         const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
                         int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,
@@ -169,12 +173,17 @@ int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   out [S, ldo] = softmax-weighted sum of V[src] over the segment (before relation_msg).
  *   kv_dtype: storage type of k / v - 0 fp32, 1 fp16, 2 bf16 (ldk / ldv in elements).  The 16-bit forms are the
  *   bf16-storage configuration (BASELINE config 3): gathered bytes halve, scores / softmax / accumulation stay fp32;
- *   they need head_perm == 0.
+ *   both kernels (head_perm 0 / 1) take them.
+ *   items int32 [n_segs, 4] or NULL (head_perm only): work list (row, e_beg, e_end, -1) - work item i reads qseg row
+ *   `row`, seg_rel[row], the edges [e_beg, e_end) and writes out row `row`; this is how the relation-SORTED segment order
+ *   of the tensor-core relation transforms runs over the dst-major edge arrays (seg_ptr may then be NULL).
+ *   out_op (head_perm only) or NULL: operand-form copy of out (wsi_to_operand layout for `opf`, [n_segs, D]) - the A
+ *   operand of the relation_msg GEMM; out may be NULL when only out_op is wanted.
  */
 int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* qseg,
                             int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel, const int32_t* e_src,
-                            const float* rel_pri, int64_t n_segs, int D, int H, int head_perm, float* out,
-                            int64_t ldo, void* stream);
+                            const float* rel_pri, int64_t n_segs, int D, int H, int head_perm, const int32_t* items,
+                            float* out, int64_t ldo, void* out_op, int opf, void* stream);
 
 /* Physical column order used when head_perm != 0: perm_host[p] = logical column stored at physical
  * position p (int32 [D]).  Returns <0 if (D,H) has no lane-grouped layout. */
@@ -194,9 +203,12 @@ int wsi_rel_transform(const float* x, int64_t ldx, const int32_t* x_row_idx, con
 
 /* Sum of the segment messages of each dst row, times 1/R_t:  the stack->mean of
  * multi_update_all(..., cross_reducer='mean')  models/HGT.py:105-106.
- *   row_seg_ptr int32 [N+1] segment range of row v; msg [S, ldm]; agg [N, ldo]. */
-int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_ptr, const float* node_inv_r,
-                        int64_t n_rows, int D, float* agg, int64_t ldo, void* stream);
+ *   row_seg_ptr int32 [N+1] segment range of row v; msg [S, ldm]; agg [N, ldo] (or NULL).
+ *   seg_pos int32 [S] or NULL: msg row of segment s (the relation-sorted order of the tensor-core transforms).
+ *   agg_op or NULL: operand-form copy of agg (wsi_to_operand layout for `opf`), the A operand of the a_linear GEMM. */
+int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_ptr, const int32_t* seg_pos,
+                        const float* node_inv_r, int64_t n_rows, int D, float* agg, int64_t ldo, void* agg_op, int opf,
+                        void* stream);
 
 /* Typed LayerNorm  models/HGT.py:123-124 (nn.LayerNorm(out_dim) per node type, eps 1e-5), in place allowed.
  *   gamma/beta [T, D]; rows of type t = [type_ptr_host[t], type_ptr_host[t+1]).

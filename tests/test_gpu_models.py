@@ -192,6 +192,24 @@ def test_native_driver_matches_per_op_path(model, pooling):
         assert not ours._native_ok(big, big.plan(), None, 3)          # dropout active
 
 
+@pytest.mark.parametrize("precision,hidden,heads", [("fp16", 256, 8), ("bf16x3", 256, 8), ("fp16", 128, 4), ("fp16", 512, 1)])
+def test_hgt_tensor_core_schedule(precision, hidden, heads):
+    """HGT through its tensor-core schedule (block-diagonal relation transforms as grouped tcgen05 GEMMs over the
+    relation-sorted segments, lane-grouped edge kernel, operand-form hand-overs): a pack()ed batch of three slides
+    (independent forwards, their own relation sets), 2 layers + LayerNorm, against the fp32 oracle within the 1e-3 bar;
+    the schedule must actually be taken (>= 512 nodes and segments, D % 128 == 0)."""
+    from wsi_hgnn_b200 import ops
+    T, F_in = 4, 128
+    graphs = [synthetic.synth_slide_graph(n, F_in, T, 6, seed=40 + i, noise_edges=0.3) for i, n in enumerate((700, 900, 600))]
+    kw = dict(in_dim=F_in, hidden_dim=hidden, out_dim=3, n_layers=2, n_heads=heads, use_norm=True, graph_pooling_type="mean")
+    ours, orc = _pair("HGT", T, kw)
+    G = pack(graphs)
+    plan = G.to("cuda").plan()
+    assert ops.head_perm(hidden, heads) is not None and ops.tc_ok(plan.segments()["S"], hidden, hidden)
+    with ops.matmul_precision(precision):
+        _check(ours, orc, G, embeddings=False)
+
+
 @pytest.mark.parametrize("hidden", [512, 200])
 def test_config3_hgt_bf16_storage_full_shape(hidden):
     """BASELINE config 3 at its stated shape: 16 ESCA-shape graphs (4k-12k nodes, k = 6, T = 6), 4-layer HGT with

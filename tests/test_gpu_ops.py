@@ -375,6 +375,69 @@ def test_rel_transform(dk, H):
         assert rel(y, ref) < 2e-5
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16", "bf16"], indirect=True)
+def test_gather_to_operand(precision):
+    """Row gather fused into the fp32 -> operand-form conversion == conversion of the gathered matrix."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(500, 256, generator=g).cuda()
+    idx = torch.randint(0, 500, (1300,), generator=g).to(torch.int32).cuda()
+    got = ops.gather_to_operand(x, idx)
+    want = ops.to_operand(x[idx.long()].contiguous())
+    assert got.dtype == want.dtype and torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
+@pytest.mark.parametrize("kv_dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_hetero_attn_seg_work_list(kv_dtype):
+    """HGT segment attention through the work list (segments visited in another order than the edge order, lane-grouped
+    layout, operand-form output) == the plain segment kernel."""
+    g = torch.Generator().manual_seed(11)
+    D, H, N, S = 256, 8, 400, 900
+    lens = torch.randint(1, 6, (S,), generator=g)
+    lens[5] = 70                                   # one long segment
+    seg_ptr = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(lens, 0)])
+    E = int(seg_ptr[-1])
+    e_src = torch.randint(0, N, (E,), generator=g).to(torch.int32).cuda()
+    R = 5
+    seg_rel = torch.randint(0, R, (S,), generator=g).to(torch.int32)
+    pri = (torch.rand(R, H, generator=g) + 0.5).cuda()
+    k, v = torch.randn(N, D, generator=g).cuda(), torch.randn(N, D, generator=g).cuda()
+    qseg = torch.randn(S, D, generator=g).cuda()
+    ref = ops.hetero_attn_seg(k, v, qseg, seg_ptr.to(torch.int32).cuda(), seg_rel.cuda(), e_src, pri, D, H)   # natural order
+    pm = ops.head_perm(D, H).cuda()
+    order = torch.randperm(S, generator=g)
+    items = torch.stack([torch.arange(S), seg_ptr[:-1][order], seg_ptr[1:][order], torch.full((S,), -1)], 1).to(torch.int32).cuda()
+    kp, vp = k[:, pm].to(kv_dtype).contiguous(), v[:, pm].to(kv_dtype).contiguous()
+    out, out_op = ops.hetero_attn_seg(kp, vp, qseg[order.cuda()][:, pm].contiguous(), None, seg_rel[order].contiguous().cuda(), e_src,
+                                      pri, D, H, True, items=items, want_out=True, op_out=True, opf=ops.OPF_BF16X3)
+    inv = torch.empty_like(pm)
+    inv[pm] = torch.arange(D, device="cuda")
+    got = torch.empty_like(out)
+    got[order.cuda()] = out[:, inv]
+    tol = 2e-5 if kv_dtype == torch.float32 else (3e-3 if kv_dtype == torch.float16 else 2e-2)
+    assert rel(got, ref) < tol
+    assert rel(out_op[:S].float() + out_op[S:].float(), out) < 1e-5
+
+
+def test_segment_combine_indexed():
+    g = torch.Generator().manual_seed(5)
+    N, D = 300, 256
+    cnt = torch.randint(0, 4, (N,), generator=g)
+    rsp = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(cnt, 0)])
+    S = int(rsp[-1])
+    msg = torch.randn(S, D, generator=g)
+    inv_r = torch.where(cnt > 0, 1.0 / cnt.clamp_min(1).float(), torch.zeros(N))
+    pos = torch.randperm(S, generator=g)
+    shuffled = torch.empty_like(msg)
+    shuffled[pos] = msg
+    ref = torch.stack([msg[rsp[i]:rsp[i + 1]].double().sum(0) * float(inv_r[i]) for i in range(N)])
+    agg, agg_op = ops.segment_combine(shuffled.cuda(), rsp.to(torch.int32).cuda(), inv_r.cuda(), N, D,
+                                      seg_pos=pos.to(torch.int32).cuda(), op_out=True, opf=ops.OPF_F16)
+    assert rel(agg, ref) < 1e-6
+    assert rel(agg_op.float(), ref) < 1e-3
+    plain = ops.segment_combine(msg.cuda(), rsp.to(torch.int32).cuda(), inv_r.cuda(), N, D)
+    assert torch.equal(plain, agg)
+
+
 def test_ops_reject_cpu_tensors():
     with pytest.raises(RuntimeError):
         ops.typed_linear(torch.zeros(4, 4), torch.zeros(1, 4, 4), None, [0, 4])

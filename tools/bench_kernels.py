@@ -36,6 +36,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--nodes", type=int, default=8192)
+    ap.add_argument("--scale-nodes", type=int, default=163840,
+                    help="rows of the batch-scale GEMM rows (a packed training micro-batch, T=6 skewed types); 0 = skip")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
@@ -97,6 +99,52 @@ def main():
             ms = timeit(lambda: torch.matmul(xa, wa), args.reps, flush)
             print(json.dumps({"kernel": f"torch.matmul cuBLASLt {tag} in / {tag} out [{name}]", "ms": ms,
                               "tflops": flops / (ms * 1e-3) / 1e12}), flush=True)
+
+    def scale_case(Ns):
+        """The same kernels at the size of a packed training micro-batch (config 5: ~160k nodes, 6 skewed types): the
+        config-2 launches above are 3 tiles per CTA pair - prologue and epilogue of a 25 us kernel - these are ~50."""
+        Ts = 6
+        cnt = [int(Ns * f) for f in synthetic.TYPE_SKEW6]
+        cnt[0] += Ns - sum(cnt)
+        tp = [0]
+        for c in cnt:
+            tp.append(tp[-1] + c)
+        for name, K, n_out in (("K|V|Q", 512, 1536), ("a_linear", 512, 512), ("adapt_ws", 1024, 512)):
+            x = torch.randn(Ns, K, device=dev)
+            w = torch.randn(Ts, n_out, K, device=dev) / K ** 0.5
+            b = torch.randn(Ts, n_out, device=dev)
+            dy = torch.randn(Ns, n_out, device=dev)
+            flops = 2.0 * Ns * K * n_out
+            for prec in ("fp16", "bf16x3"):
+                with ops.matmul_precision(prec):
+                    xs, ws = ops.to_operand(x), ops.to_operand(w)
+                    ms = timeit(lambda: ops.typed_linear_op(xs, ws, b, tp, n_out), args.reps, flush)
+                issued = 3 if prec == "bf16x3" else 1
+                tf = flops / (ms * 1e-3) / 1e12
+                print(json.dumps({"kernel": f"typed_linear_op[{name}] tcgen05 {prec} (batch scale)", "N": Ns, "K": K, "n_out": n_out,
+                                  "ms": ms, "tflops": tf, "frac_bf16_peak": tf / peaks["bf16_tflops"],
+                                  "frac_issued": issued * tf / peaks["bf16_tflops"]}), flush=True)
+            xs, ds = ops.to_operand(x, ops.OPF_BF16X3), ops.to_operand(dy, ops.OPF_BF16X3)
+            ms = timeit(lambda: ops.typed_wgrad(ds, xs, tp), args.reps, flush)
+            tf = flops / (ms * 1e-3) / 1e12
+            print(json.dumps({"kernel": f"typed_wgrad[{name}] tcgen05 bf16x3 MN-major + reduce (batch scale)", "N": Ns, "M": n_out,
+                              "Nn": K, "ms": ms, "tflops": tf, "frac_bf16_peak": tf / peaks["bf16_tflops"],
+                              "frac_issued": 3 * tf / peaks["bf16_tflops"]}), flush=True)
+            xh, dh = xs[:Ns], ds[:Ns]
+
+            def cublas3():
+                for t in range(Ts):
+                    a_, z_ = tp[t], tp[t + 1]
+                    torch.mm(dh[a_:z_].t(), xh[a_:z_], out_dtype=torch.float32)
+            try:
+                ms1 = timeit(cublas3, args.reps, flush)
+                print(json.dumps({"kernel": f"cuBLASLt bf16 -> fp32 dY^T X per type, ONE of the three terms [{name}] (batch scale)",
+                                  "ms": ms1, "tflops_one_term": flops / (ms1 * 1e-3) / 1e12}), flush=True)
+            except Exception as e:       # noqa: BLE001 - library bar only
+                print(json.dumps({"kernel": f"cuBLASLt wgrad bar [{name}]", "error": str(e)[:100]}), flush=True)
+
+    if args.scale_nodes > 0:
+        scale_case(args.scale_nodes)
 
     gemm_case("K|V|Q", 512, 1536)
     gemm_case("a_linear+skip", 512, 512, skip=True)

@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_train.py tests/test_gpu_ops.py -m gpu -q -x 2>&1 | tail -5
-python tools/bench_train.py --batch 16 --steps 5 --warmup 2 2>&1 | tail -1
+python -m pytest tests/test_gpu_models.py tests/test_gpu_golden.py tests/test_gpu_ops.py -m gpu -q -x -k "hgt or HGT or segment or rel_transform or config3" 2>&1 | tail -8
+python tools/bench_hgt.py --precision bf16 2>&1 | tail -1
+python tools/bench_hgt.py --precision fp16 --check 2 2>&1 | tail -1

@@ -802,10 +802,6 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
   const WsiDev& dev = *wsi_dev();
   if (dev.attn_cap > 0 && blocks > sms * dev.attn_cap) blocks = sms * dev.attn_cap;
   if (head_perm) {
-    if (a.kv_dtype != 0 && MODE != MODE_HEAT) {
-      wsi_set_error("hetero_attn: 16-bit K / V storage in the lane-grouped order is implemented for the HEAT scoring only");
-      return WSI_ERR_UNSUPPORTED;
-    }
     if (!vec_ok(a.D, a.H)) {
       wsi_set_error("hetero_attn: head_perm layout needs D %% 128 == 0, D <= 1024, H a power of two <= 32 (D=%d H=%d)", a.D, a.H);
       return WSI_ERR_UNSUPPORTED;
@@ -839,8 +835,8 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
         WSI_CHECK_CUDA(aerr); \
         attn_fwd_tma_kernel<NV, MODE, KVT><<<tb, TMA_WARPS * 32, smem, stream>>>(a, ring); }
 #define CASE(NV) case NV: \
-        if (MODE == MODE_HEAT && a.kv_dtype == 1) RING(NV, __half) \
-        else if (MODE == MODE_HEAT && a.kv_dtype == 2) RING(NV, __nv_bfloat16) \
+        if (a.kv_dtype == 1) RING(NV, __half) \
+        else if (a.kv_dtype == 2) RING(NV, __nv_bfloat16) \
         else RING(NV, float) \
         break;
       switch (a.D / 128) {
@@ -862,8 +858,8 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
     switch (a.D / 128) {
 #define VEC(NV, GRP, MINB, KVT) WSI_CHECK_CUDA(wsi_launch_pdl(attn_fwd_vec_kernel<NV, MODE, GRP, MINB, KVT>, dim3(blocks), dim3(WARPS * 32), 0, stream, a))
 #define CASE(NV, GRP, MINB) case NV: \
-      if (MODE == MODE_HEAT && a.kv_dtype == 1) VEC(NV, GRP, MINB, __half); \
-      else if (MODE == MODE_HEAT && a.kv_dtype == 2) VEC(NV, GRP, MINB, __nv_bfloat16); \
+      if (a.kv_dtype == 1) VEC(NV, GRP, MINB, __half); \
+      else if (a.kv_dtype == 2) VEC(NV, GRP, MINB, __nv_bfloat16); \
       else VEC(NV, GRP, MINB, float); \
       break;
       CASE(1, 4, 4) CASE(2, 4, 4) CASE(3, 2, 4) CASE(4, 2, 4) CASE(5, 2, 2) CASE(6, 2, 2) CASE(7, 2, 2) CASE(8, 2, 2)
@@ -995,18 +991,26 @@ extern "C" int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* 
 extern "C" int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* qseg,
                                        int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel,
                                        const int32_t* e_src, const float* rel_pri, int64_t n_segs, int D, int H,
-                                       int head_perm, float* out, int64_t ldo, void* stream) {
+                                       int head_perm, const int32_t* items, float* out, int64_t ldo, void* out_op, int opf,
+                                       void* stream) {
   WSI_CHECK_ARG(kv_dtype >= 0 && kv_dtype <= 2, "hetero_attn_seg_fwd: unknown K / V storage type %d", kv_dtype);
   WSI_CHECK_ARG(n_segs >= 0 && n_segs < (1ll << 31), "hetero_attn_seg_fwd: bad n_segs");
   if (n_segs == 0) return WSI_OK;
-  WSI_CHECK_ARG(k && v && qseg && seg_ptr && seg_rel && e_src && rel_pri && out, "hetero_attn_seg_fwd: null pointer");
+  WSI_CHECK_ARG(k && v && qseg && (seg_ptr || items) && seg_rel && e_src && rel_pri && (out || out_op),
+                "hetero_attn_seg_fwd: null pointer");
   WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0, "hetero_attn_seg_fwd: D=%d is not a multiple of H=%d", D, H);
+  WSI_CHECK_ARG(head_perm || (!items && !out_op && out),
+                "hetero_attn_seg_fwd: the work list and the operand-form output need the lane-grouped layout (head_perm)");
+  WSI_CHECK_ARG(!out_op || (opf >= 0 && opf <= 2 && D % 8 == 0), "hetero_attn_seg_fwd: bad operand format %d", opf);
   AttnArgs a{};
   a.K = reinterpret_cast<const float*>(k); a.ldk = ldk; a.V = reinterpret_cast<const float*>(v); a.ldv = ldv; a.Q = qseg; a.ldq = ldq;
   a.kv_dtype = kv_dtype;
   a.rowptr = seg_ptr; a.e_src = e_src; a.seg_rel = seg_rel; a.rel_pri = rel_pri;
+  a.items = reinterpret_cast<const int4*>(items);
   a.n_items = (int)n_segs; a.D = D; a.H = H; a.dk = D / H;
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.out = out; a.ldo = ldo;
+  a.out_split = reinterpret_cast<__nv_bfloat16*>(out_op);
+  a.split_lo = opf == WSI_OPF_BF16X3 ? n_segs * (int64_t)D : (opf == WSI_OPF_F16 ? 0 : -1);
   return launch<MODE_HGT_SEG>(a, head_perm, wsi_stream(stream));
 }

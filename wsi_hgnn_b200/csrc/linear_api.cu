@@ -15,7 +15,7 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
 int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const int32_t* type_ptr_host, int T,
                              const LinearEpilogue& ep, void* y_op, int opf, cudaStream_t stream);
 int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_dst, const float* b_src, int64_t b_ld,
-                     int64_t b_rows, void* b_dst, int K, int opf, cudaStream_t stream);
+                     int64_t b_rows, void* b_dst, int K, int opf, cudaStream_t stream, const int32_t* a_row_idx = nullptr);
 
 extern "C" int wsi_typed_linear_tc_ok(int64_t n_rows, int K, int n_out) {
   return (wsi_typed_linear_tc_supported(n_rows, K, n_out, K) && n_out % 4 == 0) ? 1 : 0;
@@ -26,6 +26,16 @@ extern "C" int wsi_to_operand(const float* src, int64_t ld_src, int64_t rows, in
   if (rows == 0) return WSI_OK;
   WSI_CHECK_ARG(src && dst && ld_src >= K, "to_operand: null pointer / short row stride");
   return wsi_split_launch(src, ld_src, rows, dst, nullptr, 4, 0, nullptr, K, opf, wsi_stream(stream));
+}
+
+// dst row i = operand form of src row row_idx[i]: the (dst, relation) segments of HGT gather their dst node's query
+// (models/HGT.py:88-92 moved to the dst side) straight into the A operand of the relation-transform GEMM.
+extern "C" int wsi_gather_to_operand(const float* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, int opf,
+                                     void* dst, void* stream) {
+  WSI_CHECK_ARG(rows >= 0 && K >= 8, "gather_to_operand: bad shape");
+  if (rows == 0) return WSI_OK;
+  WSI_CHECK_ARG(src && dst && row_idx && ld_src >= K, "gather_to_operand: null pointer / short row stride");
+  return wsi_split_launch(src, ld_src, rows, dst, nullptr, 4, 0, nullptr, K, opf, wsi_stream(stream), row_idx);
 }
 
 extern "C" int wsi_typed_linear_op(const void* x_split, const void* w_split, const float* bias, int K, int n_out,

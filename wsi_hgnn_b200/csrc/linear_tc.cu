@@ -32,6 +32,7 @@
 #include <mutex>
 
 #include "epilogue.cuh"
+#include "operand.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -70,41 +71,7 @@ inline uint32_t idesc_of(bool bf16) {
 //   WSI_OPF_BF16X3  [2 * rows, K] bf16 (hi rows, then lo rows at row `rows`)
 //   WSI_OPF_F16     [rows, K] fp16, round to nearest, clamped to the finite fp16 range (+-65504)
 //   WSI_OPF_BF16    [rows, K] bf16
-struct SplitJob { const float* src; int64_t ld_src; int64_t rows; void* dst; };
-
-__device__ __forceinline__ uint2 pack4_f16(float4 x) {
-  const float lim = 65504.f;
-  __half2 a = __floats2half2_rn(fminf(fmaxf(x.x, -lim), lim), fminf(fmaxf(x.y, -lim), lim));
-  __half2 b = __floats2half2_rn(fminf(fmaxf(x.z, -lim), lim), fminf(fmaxf(x.w, -lim), lim));
-  uint2 r;
-  r.x = *reinterpret_cast<uint32_t*>(&a);
-  r.y = *reinterpret_cast<uint32_t*>(&b);
-  return r;
-}
-__device__ __forceinline__ uint2 pack4_bf16(float4 x) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
-  uint2 r;
-  r.x = *reinterpret_cast<uint32_t*>(&a);
-  r.y = *reinterpret_cast<uint32_t*>(&b);
-  return r;
-}
-// the operand-form store shared by this pre-pass, the GEMM epilogue and (hetero_attn.cu has its own copy) the attention
-// kernel: 4 consecutive values of one row at `dst16` (16-bit element pointer)
-template <int OPF>
-__device__ __forceinline__ void store_operand4(void* dst16, int64_t lo_off, float4 x) {
-  if (OPF == WSI_OPF_BF16X3) {
-    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-    wsi_split_bf16(x.x, h0, l0); wsi_split_bf16(x.y, h1, l1); wsi_split_bf16(x.z, h2, l2); wsi_split_bf16(x.w, h3, l3);
-    __nv_bfloat162 hv[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
-    __nv_bfloat162 lv[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
-    *reinterpret_cast<uint2*>(dst16) = *reinterpret_cast<uint2*>(hv);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst16) + lo_off) = *reinterpret_cast<uint2*>(lv);
-  } else if (OPF == WSI_OPF_F16) {
-    *reinterpret_cast<uint2*>(dst16) = pack4_f16(x);
-  } else {
-    *reinterpret_cast<uint2*>(dst16) = pack4_bf16(x);
-  }
-}
+struct SplitJob { const float* src; int64_t ld_src; int64_t rows; void* dst; const int* row_idx; };   // row_idx: optional gather of the source rows
 
 template <int OPF>
 __global__ void __launch_bounds__(256) convert_operand_kernel(SplitJob a, SplitJob b, int K) {
@@ -124,7 +91,8 @@ __global__ void __launch_bounds__(256) convert_operand_kernel(SplitJob a, SplitJ
         const int64_t li = idx[u] < na ? idx[u] : idx[u] - na;
         const int64_t r = li / kv;
         const int c = (int)(li - r * kv) << 2;
-        x[u] = __ldg(reinterpret_cast<const float4*>(j.src + r * j.ld_src + c));
+        const int64_t sr = j.row_idx ? (int64_t)__ldg(j.row_idx + r) : r;
+        x[u] = __ldg(reinterpret_cast<const float4*>(j.src + sr * j.ld_src + c));
       }
     }
 #pragma unroll
@@ -581,15 +549,15 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
 
 // fp32 -> operand form of up to two row-strided matrices in one launch (b.rows == 0: only a)
 int wsi_split_launch(const float* a_src, int64_t a_ld, int64_t a_rows, void* a_dst, const float* b_src, int64_t b_ld,
-                     int64_t b_rows, void* b_dst, int K, int opf, cudaStream_t stream) {
+                     int64_t b_rows, void* b_dst, int K, int opf, cudaStream_t stream, const int32_t* a_row_idx) {
   WSI_CHECK_ARG(wsi_opf_valid(opf), "operand conversion: unknown operand format %d", opf);
   WSI_CHECK_ARG(K % 8 == 0 && a_ld % 4 == 0 && (b_rows == 0 || b_ld % 4 == 0) && aligned16(a_src) && aligned16(b_src) &&
                     (reinterpret_cast<uintptr_t>(a_dst) & 7) == 0 && (reinterpret_cast<uintptr_t>(b_dst) & 7) == 0,
                 "operand conversion: K must be a multiple of 8, rows 16 B aligned");
   int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
-  SplitJob ja{a_src, a_ld, a_rows, a_dst};
-  SplitJob jb{b_src, b_ld, b_rows, b_dst};
+  SplitJob ja{a_src, a_ld, a_rows, a_dst, a_row_idx};
+  SplitJob jb{b_src, b_ld, b_rows, b_dst, nullptr};
   const int64_t groups = (ja.rows + jb.rows) * (K / 4);
   if (groups == 0) return WSI_OK;
   int sblocks = (int)((groups + 1023) / 1024);
@@ -612,7 +580,7 @@ int wsi_typed_linear_tc_launch(const float* x, int64_t ldx, const float* w, int 
   uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023;
   void* a_ws = reinterpret_cast<void*>(wsp);
   void* w_ws = reinterpret_cast<void*>(wsp + align256(terms_of(opf) * n_rows * K * 2));
-  int rc = wsi_split_launch(x, ldx, n_rows, a_ws, w, K, (int64_t)T * n_out, w_ws, K, opf, stream);
+  int rc = wsi_split_launch(x, ldx, n_rows, a_ws, w, K, (int64_t)T * n_out, w_ws, K, opf, stream, nullptr);
   if (rc != WSI_OK) return rc;
   return wsi_typed_linear_tc_gemm(a_ws, w_ws, K, type_ptr_host, T, ep, nullptr, opf, stream);
 }

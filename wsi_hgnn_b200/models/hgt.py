@@ -33,10 +33,21 @@ def _relation_groups(plan: GraphPlan, edge_dict: Dict, tag):
         order = torch.argsort(seg_rel, stable=True)
         counts = torch.bincount(seg_rel, minlength=R)
         rel_ptr = [0] + torch.cumsum(counts, 0).tolist()
+        # relation-sorted view of the segments (the tensor-core relation transforms work on rows grouped by relation):
+        # work item i = segment order[i] -> (row i, its edge range); seg_pos = where segment s sits in that order
+        sp = segs["seg_ptr"].to(torch.int64)
+        S = int(segs["S"])
+        items = torch.stack([torch.arange(S, device=plan.device), sp[:-1][order], sp[1:][order],
+                             torch.full((S,), -1, dtype=torch.int64, device=plan.device)], 1).to(torch.int32).contiguous() \
+            if S else torch.zeros((0, 4), dtype=torch.int32, device=plan.device)
+        seg_pos = torch.empty(S, dtype=torch.int64, device=plan.device)
+        seg_pos[order] = torch.arange(S, device=plan.device)
         plan.cache[key] = dict(
             seg_rel=seg_rel.to(torch.int32).contiguous(),
             order=order.to(torch.int32).contiguous(),
             dst_of_order=segs["seg_dst"][order].contiguous(),
+            items=items, seg_rel_sorted=seg_rel[order].to(torch.int32).contiguous(),
+            seg_pos=seg_pos.to(torch.int32).contiguous(),
             rel_ptr_c=ops.host_i32(rel_ptr), rel_ptr=rel_ptr, R=R)
     return plan.cache[key]
 
@@ -103,6 +114,9 @@ class HGTLayer(nn.Module):
         grp = _relation_groups(plan, self.edge_dict, id(self.edge_dict))
         S = segs["S"]
         opf = ops.matmul_opf()
+        if (ops.head_perm(D, H) is not None and ops.tc_ok(S, D, D) and ops.tc_ok(plan.N, self.in_dim, 2 * D)
+                and ops.tc_ok(plan.N, self.in_dim, D) and ops.tc_ok(plan.N, D, D)):
+            return self._forward_packed_tc(plan, x, order, grp, segs, opf)
         if opf == ops.OPF_BF16 and ops.tc_ok(plan.N, self.in_dim, 2 * D) and ops.tc_ok(plan.N, self.in_dim, D):
             # bf16 storage of K | V (set_matmul_precision("bf16"): BASELINE config 3): the K|V GEMM writes ONLY the bf16
             # operand-form copy, the edge kernel gathers half the bytes; Q stays fp32 for the relation transform.
@@ -136,6 +150,66 @@ class HGTLayer(nn.Module):
             # NB the reference normalises only types that received a message (models/HGT.py:118-126);
             # passthrough types keep h unchanged, so the LayerNorm is applied row-gated below.
             out = _gated_layernorm(out, gamma, beta, plan, tpc)
+        return out
+
+    def _packed_tc(self, order, opf, dev):
+        """Operand-form weights of the tensor-core schedule (cached per type order / operand format / parameter version):
+        K | V projected straight into the lane-grouped column order of the edge kernel (row-permuted weights), the per
+        (relation, head) d_k x d_k maps as ONE block-diagonal [D, D] matrix per relation with the column orders folded in:
+          q'_phys = W_att_big[r] q        W_att_big[r][p, :]  = blockdiag_h(relation_att[r, h])[perm[p], :]
+          msg     = W_msg_big[r] agg_phys  W_msg_big[r][:, p] = blockdiag_h(relation_msg[r, h]^T)[:, perm[p]]
+        (3/4 of the block-diagonal product is zeros - tensor-core time well spent: one plain grouped GEMM per transform,
+        no per-head launches, and the permutations cost nothing)."""
+        params = param_list(self, "all", self.parameters)
+
+        def build():
+            D, H = self.out_dim, self.n_heads
+            w_kvq, b_kvq, wa, ba, skip, gamma, beta = self._packed(order)
+            pm = ops.head_perm(D, H).to(dev)
+            w_kv = torch.cat([w_kvq[:, :D][:, pm], w_kvq[:, D:2 * D][:, pm]], 1).contiguous()
+            b_kv = torch.cat([b_kvq[:, :D][:, pm], b_kvq[:, D:2 * D][:, pm]], 1).contiguous()
+            w_q, b_q = w_kvq[:, 2 * D:].contiguous(), b_kvq[:, 2 * D:].contiguous()
+            att = torch.stack([torch.block_diag(*self.relation_att[r]) for r in range(self.num_relations)])        # [R, D(n), D(k)]
+            msg = torch.stack([torch.block_diag(*self.relation_msg[r]).t() for r in range(self.num_relations)])    # [R, D(n), D(k)]
+            att, msg = att[:, pm, :].contiguous(), msg[:, :, pm].contiguous()
+            return dict(w_kv=ops.to_operand(w_kv, opf), b_kv=b_kv, w_q=ops.to_operand(w_q, opf), b_q=b_q,
+                        w_att=ops.to_operand(att, opf), w_msg=ops.to_operand(msg, opf), wa=ops.to_operand(wa, opf), ba=ba,
+                        skip=skip, gamma=gamma, beta=beta)
+
+        return self._packs.get(("tc", opf, tuple(order)), params, build)
+
+    def _forward_packed_tc(self, plan: GraphPlan, x, order, grp, segs, opf) -> torch.Tensor:
+        """The layer on tensor cores end to end (models/HGT.py:68-127): every dense product is a tcgen05 grouped GEMM on
+        operand-form inputs, every producer writes the operand form its consumer reads (no conversion passes between
+        them), the edge kernel is the lane-grouped one of HEAT running over the relation-sorted (dst, relation) segments."""
+        D, H = self.out_dim, self.n_heads
+        pk = self._packed_tc(order, opf, x.device)
+        tpc = plan.type_ptr_c()
+        S = segs["S"]
+        xs = ops.to_operand(x, opf)
+        if opf == ops.OPF_BF16:        # bf16 storage of K | V (BASELINE config 3): only the 16-bit copy is written
+            _, kv = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, want_y=False, want_op=True,
+                                        type_ptr_c=tpc, opf=opf)
+        else:
+            kv, _ = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, type_ptr_c=tpc, opf=opf)
+        q, _ = ops.typed_linear_op(xs, pk["w_q"], pk["b_q"], plan.type_ptr, D, type_ptr_c=tpc, opf=opf)
+        # q'_seg = relation_att[r, h] . q[dst, h] for the segments in relation order   (:88-92)
+        qg = ops.gather_to_operand(q, grp["dst_of_order"], opf)
+        qseg, _ = ops.typed_linear_op(qg, pk["w_att"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"], opf=opf)
+        _, aggseg = ops.hetero_attn_seg(kv[:, :D], kv[:, D:], qseg, None, grp["seg_rel_sorted"], plan.e_src,
+                                        self.relation_pri, D, H, True, items=grp["items"], want_out=False, op_out=True,
+                                        opf=opf)                                                            # :95-104
+        msgseg, _ = ops.typed_linear_op(aggseg, pk["w_msg"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"],
+                                        opf=opf)                                                            # :93
+        _, aggs = ops.segment_combine(msgseg, segs["row_seg_ptr"], plan.node_inv_r, plan.N, D, seg_pos=grp["seg_pos"],
+                                      want_out=False, op_out=True, opf=opf)                                 # :105-106
+        mask = None
+        if self.training and self.drop.p > 0:
+            mask = F.dropout(torch.ones((plan.N, D), dtype=torch.float32, device=x.device), self.drop.p, True)
+        out, _ = ops.typed_linear_op(aggs, pk["wa"], pk["ba"], plan.type_ptr, D, skip=pk["skip"], res=x,
+                                     row_gate=plan.node_inv_r, drop_mask=mask, type_ptr_c=tpc, opf=opf)     # :121-122
+        if self.use_norm:
+            out = _gated_layernorm(out, pk["gamma"], pk["beta"], plan, tpc)
         return out
 
     def forward_train(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:

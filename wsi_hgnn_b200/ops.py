@@ -213,6 +213,19 @@ def to_operand(x: torch.Tensor, opf: Optional[int] = None) -> torch.Tensor:
     return out
 
 
+def gather_to_operand(x: torch.Tensor, row_idx: torch.Tensor, opf: Optional[int] = None) -> torch.Tensor:
+    """out row i = operand form of x[row_idx[i]] (wsi_gather_to_operand): fp32 [*, K] -> [operand_rows(len(row_idx)), K]."""
+    lib = _lib.load()
+    stream = _prep(x)
+    opf = matmul_opf(opf)
+    xp, ld = _rows(x, "x")
+    rows, K = int(row_idx.numel()), int(x.shape[1])
+    out = torch.empty((operand_rows(rows, opf), K), dtype=_OPF_DTYPE[opf], device=x.device)
+    _lib.check(lib.wsi_gather_to_operand(xp, ld, _vec(row_idx, "row_idx", torch.int32), rows, K, opf, out.data_ptr(), stream),
+               "wsi_gather_to_operand")
+    return out
+
+
 def typed_linear_op(x_op: torch.Tensor, w_op: torch.Tensor, bias: Optional[torch.Tensor],
                     type_ptr: Sequence[int], n_out: int, *, act: int = ACT_NONE,
                     skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
@@ -371,8 +384,12 @@ def hetero_attn_bwd(k, v, q, rowptr, e_src, e_sim, e_rel, node_inv_r, e_w, e_b, 
     return d_e
 
 
-def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int, use_head_perm: bool = False):
-    """HGT edge attention over (dst, relation) segments; see wsi_hetero_attn_seg_fwd."""
+def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int, use_head_perm: bool = False,
+                    items: Optional[torch.Tensor] = None, want_out: bool = True, op_out: bool = False,
+                    opf: Optional[int] = None):
+    """HGT edge attention over (dst, relation) segments; see wsi_hetero_attn_seg_fwd.
+    items int32 [S, 4]: work list (row, e_beg, e_end, -1) for a segment order other than the edge order.
+    -> out fp32 [S, D]; with op_out: (out or None, operand-form copy [operand_rows(S), D])."""
     lib = _lib.load()
     stream = _prep(qseg)
     S = int(qseg.shape[0])
@@ -381,13 +398,20 @@ def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int
     kp, ldk = _rows(k, "k", k.dtype)
     vp, ldv = _rows(v, "v", v.dtype)
     qp, ldq = _rows(qseg, "qseg")
-    out = torch.empty((S, D), dtype=torch.float32, device=qseg.device)
-    rc = lib.wsi_hetero_attn_seg_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, ldq, _vec(seg_ptr, "seg_ptr", torch.int32),
+    opf = matmul_opf(opf)
+    out = torch.empty((S, D), dtype=torch.float32, device=qseg.device) if want_out or not op_out else None
+    out_op = torch.empty((operand_rows(S, opf), D), dtype=_OPF_DTYPE[opf], device=qseg.device) if op_out else None
+    if items is not None and (items.dtype != torch.int32 or tuple(items.shape) != (S, 4) or not items.is_contiguous()):
+        raise ValueError(f"hetero_attn_seg: items must be a contiguous int32 [{S}, 4] tensor")
+    rc = lib.wsi_hetero_attn_seg_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, ldq,
+                                     _vec(seg_ptr, "seg_ptr", torch.int32) if seg_ptr is not None else None,
                                      _vec(seg_rel, "seg_rel", torch.int32), _vec(e_src, "e_src", torch.int32),
                                      _vec(rel_pri, "rel_pri"), S, D, H, 1 if use_head_perm else 0,
-                                     out.data_ptr(), D, stream)
+                                     items.data_ptr() if items is not None else None,
+                                     out.data_ptr() if out is not None else None, D,
+                                     out_op.data_ptr() if out_op is not None else None, opf, stream)
     _lib.check(rc, "wsi_hetero_attn_seg_fwd")
-    return out
+    return (out, out_op) if op_out else out
 
 
 def rel_transform(x, x_row_idx, y_row_idx, w, rel_ptr_c, R: int, H: int, d_k: int, w_kn: bool, n_out_rows: int):
@@ -405,15 +429,22 @@ def rel_transform(x, x_row_idx, y_row_idx, w, rel_ptr_c, R: int, H: int, d_k: in
     return y
 
 
-def segment_combine(msg, row_seg_ptr, node_inv_r, N: int, D: int):
+def segment_combine(msg, row_seg_ptr, node_inv_r, N: int, D: int, seg_pos: Optional[torch.Tensor] = None,
+                    want_out: bool = True, op_out: bool = False, opf: Optional[int] = None):
+    """agg[v] = 1/R_v * sum of the messages of row v's (v, relation) segments; see wsi_segment_combine.
+    seg_pos int32 [S]: msg row of segment s.  With op_out: (agg or None, operand-form copy)."""
     lib = _lib.load()
     stream = _prep(node_inv_r)
     mp, ldm = _rows(msg, "msg")
-    agg = torch.empty((N, D), dtype=torch.float32, device=node_inv_r.device)
+    opf = matmul_opf(opf)
+    agg = torch.empty((N, D), dtype=torch.float32, device=node_inv_r.device) if want_out or not op_out else None
+    agg_op = torch.empty((operand_rows(N, opf), D), dtype=_OPF_DTYPE[opf], device=node_inv_r.device) if op_out else None
     rc = lib.wsi_segment_combine(mp, ldm, _vec(row_seg_ptr, "row_seg_ptr", torch.int32),
-                                 _vec(node_inv_r, "node_inv_r"), N, D, agg.data_ptr(), D, stream)
+                                 _vec(seg_pos, "seg_pos", torch.int32) if seg_pos is not None else None,
+                                 _vec(node_inv_r, "node_inv_r"), N, D, agg.data_ptr() if agg is not None else None, D,
+                                 agg_op.data_ptr() if agg_op is not None else None, opf, stream)
     _lib.check(rc, "wsi_segment_combine")
-    return agg
+    return (agg, agg_op) if op_out else agg
 
 
 def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, type_ptr_c=None, inplace=False,
