@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 17
+#define WSI_ABI_VERSION 18
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -139,11 +139,14 @@ int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  * Requires the lane-grouped column order (head_perm layout of wsi_head_perm).  Built by GraphPlan.attn_work().
  *   kv_dtype: storage type of k / v - 0 fp32, 1 fp16, 2 bf16 (ldk / ldv in elements; same lane-grouped order): half the
  *   gathered bytes (and half the exchange of the node-sharded layer), fp32 scores / softmax / accumulation.
+ *   q_dtype: storage type of q, same codes.  n_src_rows: rows of k / v (0 = n_rows; HGT runs this kernel over its
+ *   (dst, relation) SEGMENTS as rows, whose count is not the node count): the K | V footprint picks the kernel.
  *   agg_op != NULL: the result is (also) written in operand format `opf` (WSI_OPF_*: 16-bit [2 * n_rows, D] hi rows then
  *   lo rows, or [n_rows, D]), the A operand of wsi_typed_linear_op; agg may then be NULL. */
-int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* q, int64_t ldq,
-                             const int32_t* e_src, const float* e_sim, const uint8_t* e_rel, const float* node_inv_r,
-                             const float* e_w, const float* e_b, int64_t n_rows, int D, int H, const int32_t* items,
+int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const void* q, int q_dtype,
+                             int64_t ldq, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
+                             const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows,
+                             int64_t n_src_rows, int D, int H, const int32_t* items,
                              int64_t n_items, const int32_t* split_row, const int32_t* split_ptr,
                              const int32_t* part_rel, const int32_t* part_split, int32_t* split_cnt, int32_t* sched,
                              int64_t n_split, int64_t n_part, float* part_ms,
@@ -173,17 +176,20 @@ int wsi_hetero_attn_bwd(const float* k, int64_t ldk, const float* v, int64_t ldv
  *   out [S, ldo] = softmax-weighted sum of V[src] over the segment (before relation_msg).
  *   kv_dtype: storage type of k / v - 0 fp32, 1 fp16, 2 bf16 (ldk / ldv in elements).  The 16-bit forms are the
  *   bf16-storage configuration (BASELINE config 3): gathered bytes halve, scores / softmax / accumulation stay fp32;
- *   both kernels (head_perm 0 / 1) take them.
+ *   both kernels (head_perm 0 / 1) take them.  q_dtype: storage of qseg, same codes (16-bit: head_perm only) - the
+ *   relation_att GEMM then writes only its 16-bit output.
  *   items int32 [n_segs, 4] or NULL (head_perm only): work list (row, e_beg, e_end, -1) - work item i reads qseg row
  *   `row`, seg_rel[row], the edges [e_beg, e_end) and writes out row `row`; this is how the relation-SORTED segment order
  *   of the tensor-core relation transforms runs over the dst-major edge arrays (seg_ptr may then be NULL).
+ *   n_src_rows: rows of k / v that can be gathered (0 = unknown): the K | V footprint picks the register-path or the
+ *   TMA bulk-copy ring kernel, as in wsi_hetero_attn_work_fwd.
  *   out_op (head_perm only) or NULL: operand-form copy of out (wsi_to_operand layout for `opf`, [n_segs, D]) - the A
  *   operand of the relation_msg GEMM; out may be NULL when only out_op is wanted.
  */
-int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* qseg,
-                            int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel, const int32_t* e_src,
+int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const void* qseg,
+                            int q_dtype, int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel, const int32_t* e_src,
                             const float* rel_pri, int64_t n_segs, int D, int H, int head_perm, const int32_t* items,
-                            float* out, int64_t ldo, void* out_op, int opf, void* stream);
+                            int64_t n_src_rows, float* out, int64_t ldo, void* out_op, int opf, void* stream);
 
 /* Physical column order used when head_perm != 0: perm_host[p] = logical column stored at physical
  * position p (int32 [D]).  Returns <0 if (D,H) has no lane-grouped layout. */
@@ -203,10 +209,11 @@ int wsi_rel_transform(const float* x, int64_t ldx, const int32_t* x_row_idx, con
 
 /* Sum of the segment messages of each dst row, times 1/R_t:  the stack->mean of
  * multi_update_all(..., cross_reducer='mean')  models/HGT.py:105-106.
- *   row_seg_ptr int32 [N+1] segment range of row v; msg [S, ldm]; agg [N, ldo] (or NULL).
+ *   row_seg_ptr int32 [N+1] segment range of row v; msg [S, ldm] of storage type msg_dtype (0 fp32, 1 fp16, 2 bf16: the
+ *   16-bit output of the relation_msg GEMM); agg [N, ldo] (or NULL).
  *   seg_pos int32 [S] or NULL: msg row of segment s (the relation-sorted order of the tensor-core transforms).
  *   agg_op or NULL: operand-form copy of agg (wsi_to_operand layout for `opf`), the A operand of the a_linear GEMM. */
-int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_ptr, const int32_t* seg_pos,
+int wsi_segment_combine(const void* msg, int msg_dtype, int64_t ldm, const int32_t* row_seg_ptr, const int32_t* seg_pos,
                         const float* node_inv_r, int64_t n_rows, int D, float* agg, int64_t ldo, void* agg_op, int opf,
                         void* stream);
 

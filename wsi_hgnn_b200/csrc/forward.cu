@@ -84,8 +84,8 @@ extern "C" int wsi_heat_forward(const void* feat, int64_t ldf, int feat_is_op, c
     rc = wsi_typed_linear_op(xs, p->w_kvq_split[l], p->b_kvq[l], D, 3 * D, tp, T, WSI_ACT_NONE, nullptr, nullptr, 0,
                              nullptr, 0, nullptr, nullptr, kvq, 3 * D, nullptr, opf, stream);   // :91-102, once per type
     if (rc) return rc;
-    rc = wsi_hetero_attn_work_fwd(kvq, 3 * D, kvq + D, 3 * D, 0, kvq + 2 * D, 3 * D, g->e_src, g->e_sim, g->e_rel,
-                                  g->node_inv_r, p->e_w[l], p->e_b[l], N, D, H, g->items, g->n_items, g->split_row,
+    rc = wsi_hetero_attn_work_fwd(kvq, 3 * D, kvq + D, 3 * D, 0, kvq + 2 * D, 0, 3 * D, g->e_src, g->e_sim, g->e_rel,
+                                  g->node_inv_r, p->e_w[l], p->e_b[l], N, N, D, H, g->items, g->n_items, g->split_row,
                                   g->split_ptr, g->part_rel, g->part_split, g->split_cnt, g->sched, g->n_split, g->n_part,
                                   part_ms, part_acc, nullptr, D, aggs, opf, stream);               // :103-119
     if (rc) return rc;

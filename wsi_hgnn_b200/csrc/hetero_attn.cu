@@ -60,6 +60,7 @@ struct AttnArgs {
   int* sched;                 // optional int32 [2], zero before the first launch: dynamic work queue (next item | warps done)
   const int* split_row; const int* split_ptr; const int* part_rel;
   int kv_dtype;               // storage of K / V: 0 = fp32 (every kernel), 1 = fp16, 2 = bf16 (natural-order kernel only)
+  int q_dtype;                // storage of Q: 0 = fp32, 1 = fp16, 2 = bf16 (lane-grouped kernels only; ldq counts elements)
   int64_t n_src_rows;         // rows of K / V that can be gathered (the footprint that decides register vs TMA-ring kernel); 0 = unknown
 };
 
@@ -107,6 +108,13 @@ __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cas
 __device__ __forceinline__ float4 lds4(const __half* p) { return cvt4(*reinterpret_cast<const uint2*>(p), p); }
 __device__ __forceinline__ float4 lds4(const __nv_bfloat16* p) { return cvt4(*reinterpret_cast<const uint2*>(p), p); }
 
+// this lane's i-th 4-element slot of Q row `row` (fp32, or a 16-bit storage form converted on load)
+__device__ __forceinline__ float4 ldq4(const AttnArgs& a, int64_t row, int col) {
+  if (a.q_dtype == 0) return __ldg(reinterpret_cast<const float4*>(a.Q + row * a.ldq + col));
+  if (a.q_dtype == 1) return ldkv4(reinterpret_cast<const __half*>(a.Q) + row * a.ldq + col);
+  return ldkv4(reinterpret_cast<const __nv_bfloat16*>(a.Q) + row * a.ldq + col);
+}
+
 struct MergeArgs;
 template <int NV> __device__ __noinline__ void merge_row(const MergeArgs& a, int h, int lane);
 template <int NV> __device__ __forceinline__ void vec_fused_merge(const AttnArgs& a, int slot, int lane);
@@ -151,9 +159,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs
 
     if (invr != 0.f && end > beg) {
       float4 q[NV];
-      const float* qr = a.Q + (int64_t)row * a.ldq;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) q[i] = ld4(qr + (i * 32 + lane) * 4);
+      for (int i = 0; i < NV; ++i) q[i] = ldq4(a, row, (i * 32 + lane) * 4);
       int cur_rel = -1, seg_beg = beg;
 
       for (int base = beg; base < end; base += 32) {
@@ -442,7 +449,7 @@ constexpr int TMA_WARPS = 4;
 constexpr int BMAX = 4;      // edges per batch of the TMA kernel
 
 template <int NV, int MODE, typename KVT>
-__global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_kernel(AttnArgs a, int ring) {
+__global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 5 : 2) attn_fwd_tma_kernel(AttnArgs a, int ring) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int ROW_BYTES = NV * 128 * (int)sizeof(KVT), SLOT_BYTES = 2 * ROW_BYTES;
   const KVT* const Kp = reinterpret_cast<const KVT*>(a.K);
@@ -525,9 +532,8 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 4 : 2) attn_fwd_tma_
           }
         }
         if (!have_q) {
-          const float* qr = a.Q + (int64_t)row * a.ldq;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) q[i] = ld4(qr + (i * 32 + lane) * 4);
+          for (int i = 0; i < NV; ++i) q[i] = ldq4(a, row, (i * 32 + lane) * 4);
           have_q = true;
         }
         // edges are consumed in batches of up to BMAX (same relation): all scores first (independent dot products),
@@ -817,8 +823,11 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
     const bool want_ring = dev.attn_kernel == 2 || (dev.attn_kernel == 0 && kv_bytes >= (80ll << 20));
     if (!a.attn && (a.ldk % 8 == 0) && (a.ldv % 8 == 0) && want_ring) {      // (bulk copies need 16 B aligned rows)
       const int slot_bytes = 2 * a.D * es;
-      // ~12 KB of K/V rows in flight per warp, 4 blocks of 4 warps per SM
-      int ring = 12288 / slot_bytes;
+      // The kernel is bound by latency per warp, not by bytes in flight (round-2 sweep on the HGT segment graph of
+      // config 3: time ~ 1 / resident blocks from 1 to 4 blocks per SM, flat in the ring depth from 2 to 4 slots), so the
+      // ring is sized for FIVE resident blocks of 4 warps (96 registers, <= 40 KB of shared memory each): ~10 KB of K/V
+      // rows in flight per warp (config 3, bf16 rows: 555 us at 4 blocks -> 462 us at 5; config 4, fp32: 530 -> 514 us)
+      int ring = 9984 / slot_bytes;
       ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
       if (dev.attn_ring > 0) ring = dev.attn_ring;                          // development knob
       if (ring < 1) ring = 1;
@@ -939,10 +948,10 @@ extern "C" int wsi_hetero_attn_fwd(const float* k, int64_t ldk, const float* v, 
   return launch<MODE_HEAT>(a, head_perm, wsi_stream(stream));
 }
 
-extern "C" int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* q,
-                                        int64_t ldq, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
+extern "C" int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const void* q,
+                                        int q_dtype, int64_t ldq, const int32_t* e_src, const float* e_sim, const uint8_t* e_rel,
                                         const float* node_inv_r, const float* e_w, const float* e_b, int64_t n_rows,
-                                        int D, int H, const int32_t* items, int64_t n_items,
+                                        int64_t n_src_rows, int D, int H, const int32_t* items, int64_t n_items,
                                         const int32_t* split_row, const int32_t* split_ptr, const int32_t* part_rel,
                                         const int32_t* part_split, int32_t* split_cnt, int32_t* sched, int64_t n_split,
                                         int64_t n_part, float* part_ms, float* part_acc, float* agg, int64_t ldo,
@@ -953,7 +962,8 @@ extern "C" int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* 
   WSI_CHECK_ARG((reinterpret_cast<uintptr_t>(agg_split) & 7) == 0, "hetero_attn_work_fwd: agg_split must be 8 B aligned");
   WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0 && vec_ok(D, H),
                 "hetero_attn_work_fwd: needs the lane-grouped layout (D %% 128 == 0, D <= 1024, H a power of two <= 32), got D=%d H=%d", D, H);
-  WSI_CHECK_ARG(kv_dtype >= 0 && kv_dtype <= 2, "hetero_attn_work_fwd: unknown K / V storage type %d", kv_dtype);
+  WSI_CHECK_ARG(kv_dtype >= 0 && kv_dtype <= 2 && q_dtype >= 0 && q_dtype <= 2,
+                "hetero_attn_work_fwd: unknown K / V / Q storage type %d / %d", kv_dtype, q_dtype);
   WSI_CHECK_ARG(ldk % 4 == 0 && ldv % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0 &&
                     (reinterpret_cast<uintptr_t>(k) & 7) == 0 && (reinterpret_cast<uintptr_t>(v) & 7) == 0,
                 "hetero_attn_work_fwd: row strides must be multiples of 4 elements, K / V 8 B aligned");
@@ -961,13 +971,14 @@ extern "C" int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* 
                 "hetero_attn_work_fwd: split rows need the partial buffers");
   WSI_CHECK_ARG(!split_cnt || part_split, "hetero_attn_work_fwd: split_cnt needs part_split");
   AttnArgs a{};
-  a.K = reinterpret_cast<const float*>(k); a.ldk = ldk; a.V = reinterpret_cast<const float*>(v); a.ldv = ldv; a.Q = q; a.ldq = ldq;
-  a.kv_dtype = kv_dtype;
+  a.K = reinterpret_cast<const float*>(k); a.ldk = ldk; a.V = reinterpret_cast<const float*>(v); a.ldv = ldv;
+  a.Q = reinterpret_cast<const float*>(q); a.ldq = ldq;
+  a.kv_dtype = kv_dtype; a.q_dtype = q_dtype;
   a.e_src = e_src; a.e_sim = e_sim; a.e_rel = e_rel; a.inv_r = node_inv_r;
   a.e_w = e_w; a.e_b = e_b; a.n_items = (int)n_items; a.D = D; a.H = H; a.dk = D / H;
   a.inv_sqrt_dk = 1.0f / sqrtf((float)(D / H));
   a.out = agg; a.ldo = ldo; a.attn = nullptr;
-  a.n_src_rows = n_rows;
+  a.n_src_rows = n_src_rows > 0 ? n_src_rows : n_rows;
   a.items = reinterpret_cast<const int4*>(items); a.part_ms = part_ms; a.part_acc = part_acc;
   WSI_CHECK_ARG(opf == WSI_OPF_BF16X3 || opf == WSI_OPF_F16 || opf == WSI_OPF_BF16, "hetero_attn_work_fwd: unknown operand format %d", opf);
   a.out_split = reinterpret_cast<__nv_bfloat16*>(agg_split);
@@ -988,23 +999,25 @@ extern "C" int wsi_hetero_attn_work_fwd(const void* k, int64_t ldk, const void* 
   return launch_merge(m, wsi_stream(stream));
 }
 
-extern "C" int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const float* qseg,
-                                       int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel,
+extern "C" int wsi_hetero_attn_seg_fwd(const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_dtype, const void* qseg,
+                                       int q_dtype, int64_t ldq, const int32_t* seg_ptr, const int32_t* seg_rel,
                                        const int32_t* e_src, const float* rel_pri, int64_t n_segs, int D, int H,
-                                       int head_perm, const int32_t* items, float* out, int64_t ldo, void* out_op, int opf,
-                                       void* stream) {
+                                       int head_perm, const int32_t* items, int64_t n_src_rows, float* out, int64_t ldo,
+                                       void* out_op, int opf, void* stream) {
   WSI_CHECK_ARG(kv_dtype >= 0 && kv_dtype <= 2, "hetero_attn_seg_fwd: unknown K / V storage type %d", kv_dtype);
   WSI_CHECK_ARG(n_segs >= 0 && n_segs < (1ll << 31), "hetero_attn_seg_fwd: bad n_segs");
   if (n_segs == 0) return WSI_OK;
   WSI_CHECK_ARG(k && v && qseg && (seg_ptr || items) && seg_rel && e_src && rel_pri && (out || out_op),
                 "hetero_attn_seg_fwd: null pointer");
   WSI_CHECK_ARG(H >= 1 && D >= 1 && D % H == 0, "hetero_attn_seg_fwd: D=%d is not a multiple of H=%d", D, H);
-  WSI_CHECK_ARG(head_perm || (!items && !out_op && out),
-                "hetero_attn_seg_fwd: the work list and the operand-form output need the lane-grouped layout (head_perm)");
+  WSI_CHECK_ARG(head_perm || (!items && !out_op && out && q_dtype == 0),
+                "hetero_attn_seg_fwd: the work list, 16-bit queries and the operand-form output need the lane-grouped layout (head_perm)");
+  WSI_CHECK_ARG(q_dtype >= 0 && q_dtype <= 2, "hetero_attn_seg_fwd: unknown query storage type %d", q_dtype);
   WSI_CHECK_ARG(!out_op || (opf >= 0 && opf <= 2 && D % 8 == 0), "hetero_attn_seg_fwd: bad operand format %d", opf);
   AttnArgs a{};
-  a.K = reinterpret_cast<const float*>(k); a.ldk = ldk; a.V = reinterpret_cast<const float*>(v); a.ldv = ldv; a.Q = qseg; a.ldq = ldq;
-  a.kv_dtype = kv_dtype;
+  a.K = reinterpret_cast<const float*>(k); a.ldk = ldk; a.V = reinterpret_cast<const float*>(v); a.ldv = ldv; a.Q = reinterpret_cast<const float*>(qseg); a.ldq = ldq;
+  a.kv_dtype = kv_dtype; a.q_dtype = q_dtype;
+  a.n_src_rows = n_src_rows > 0 ? n_src_rows : 0;
   a.rowptr = seg_ptr; a.e_src = e_src; a.seg_rel = seg_rel; a.rel_pri = rel_pri;
   a.items = reinterpret_cast<const int4*>(items);
   a.n_items = (int)n_segs; a.D = D; a.H = H; a.dk = D / H;

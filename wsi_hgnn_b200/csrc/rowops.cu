@@ -276,6 +276,41 @@ typed_layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __
 // (stack->mean of multi_update_all(..., cross_reducer='mean'), reference models/HGT.py:105-106).
 // seg_pos (optional): msg row of segment s is seg_pos[s] (the relation-sorted order of the tensor-core transforms);
 // agg_op (optional): the operand-form copy for the a_linear GEMM (lo_off as in store_operand4_rt).
+__device__ __forceinline__ float4 ld_msg4(const __half* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 ld_msg4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// 16-bit message storage (fp16 / bf16 rows straight out of the relation_msg GEMM), 4 columns per lane
+template <typename MT>
+__global__ void __launch_bounds__(256)
+segment_combine16_kernel(const MT* __restrict__ msg, int64_t ldm, const int* __restrict__ row_seg_ptr,
+                         const int* __restrict__ seg_pos, const float* __restrict__ inv_r, int n_rows, int D,
+                         float* __restrict__ agg, int64_t ldo, uint16_t* __restrict__ agg_op, int64_t lo_off) {
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 8) {
+    const int s0 = row_seg_ptr[row], s1 = row_seg_ptr[row + 1];
+    const float ir = inv_r[row];
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = s0; s < s1; ++s) {
+        const int64_t r = seg_pos ? (int64_t)__ldg(seg_pos + s) : s;
+        const float4 m = ld_msg4(msg + r * ldm + c);
+        acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+      }
+      acc.x *= ir; acc.y *= ir; acc.z *= ir; acc.w *= ir;
+      if (agg) *reinterpret_cast<float4*>(agg + (int64_t)row * ldo + c) = acc;
+      if (agg_op) store_operand4_rt(agg_op + (int64_t)row * D + c, lo_off, acc);
+    }
+  }
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
 segment_combine_kernel(const float* __restrict__ msg, int64_t ldm, const int* __restrict__ row_seg_ptr,
@@ -393,12 +428,14 @@ extern "C" int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gam
   return WSI_OK;
 }
 
-extern "C" int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t* row_seg_ptr, const int32_t* seg_pos,
+extern "C" int wsi_segment_combine(const void* msg_, int msg_dtype, int64_t ldm, const int32_t* row_seg_ptr, const int32_t* seg_pos,
                                    const float* node_inv_r, int64_t n_rows, int D, float* agg, int64_t ldo, void* agg_op,
                                    int opf, void* stream) {
   WSI_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "segment_combine: bad n_rows");
   if (n_rows == 0) return WSI_OK;
   WSI_CHECK_ARG(row_seg_ptr && node_inv_r && (agg || agg_op), "segment_combine: null pointer");
+  WSI_CHECK_ARG(msg_dtype >= 0 && msg_dtype <= 2, "segment_combine: unknown message storage type %d", msg_dtype);
+  const float* msg = reinterpret_cast<const float*>(msg_);
   const bool vec4 = D % 4 == 0 && ldm % 4 == 0 && (!agg || ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(msg) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(agg) & 15) == 0 && (reinterpret_cast<uintptr_t>(agg_op) & 7) == 0;
   WSI_CHECK_ARG(!agg_op || (vec4 && opf >= 0 && opf <= 2), "segment_combine: the operand-form output needs D %% 4 == 0, 16 B aligned rows");
@@ -406,6 +443,21 @@ extern "C" int wsi_segment_combine(const float* msg, int64_t ldm, const int32_t*
   int blocks = (int)((n_rows + 7) / 8);
   { const int sms = wsi_num_sms(); if (sms <= 0) return WSI_ERR_CUDA; if (blocks > sms * 16) blocks = sms * 16; }
   const int64_t lo_off = opf == WSI_OPF_BF16X3 ? n_rows * (int64_t)D : (opf == WSI_OPF_F16 ? 0 : -1);
+  if (msg_dtype != 0) {
+    WSI_CHECK_ARG(D % 4 == 0 && ldm % 4 == 0 && (!agg || ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(msg_) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(agg) & 15) == 0 && (reinterpret_cast<uintptr_t>(agg_op) & 7) == 0,
+                  "segment_combine: 16-bit messages need D %% 4 == 0 and 8 B aligned rows");
+    if (msg_dtype == 1)
+      segment_combine16_kernel<__half><<<blocks, 256, 0, wsi_stream(stream)>>>(
+          reinterpret_cast<const __half*>(msg_), ldm, row_seg_ptr, seg_pos, node_inv_r, (int)n_rows, D, agg, ldo,
+          reinterpret_cast<uint16_t*>(agg_op), lo_off);
+    else
+      segment_combine16_kernel<__nv_bfloat16><<<blocks, 256, 0, wsi_stream(stream)>>>(
+          reinterpret_cast<const __nv_bfloat16*>(msg_), ldm, row_seg_ptr, seg_pos, node_inv_r, (int)n_rows, D, agg, ldo,
+          reinterpret_cast<uint16_t*>(agg_op), lo_off);
+    WSI_CHECK_LAUNCH();
+    return WSI_OK;
+  }
   if (vec4)
     segment_combine_kernel<true><<<blocks, 256, 0, wsi_stream(stream)>>>(msg, ldm, row_seg_ptr, seg_pos, node_inv_r, (int)n_rows,
                                                                          D, agg, ldo, reinterpret_cast<uint16_t*>(agg_op), lo_off);

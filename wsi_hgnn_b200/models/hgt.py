@@ -42,7 +42,25 @@ def _relation_groups(plan: GraphPlan, edge_dict: Dict, tag):
             if S else torch.zeros((0, 4), dtype=torch.int32, device=plan.device)
         seg_pos = torch.empty(S, dtype=torch.int64, device=plan.device)
         seg_pos[order] = torch.arange(S, device=plan.device)
+        # the SEGMENT GRAPH in that order (rows = segments, one relation run per row): the hub-balancing work list and
+        # the kernels of HEAT's edge attention run on it unchanged (k-NN in-degrees are heavy-tailed: one warp per
+        # segment leaves the launch waiting for its largest hub)
+        lens = (sp[1:] - sp[:-1])[order]
+        sg_ptr = torch.zeros(S + 1, dtype=torch.int64, device=plan.device)
+        sg_ptr[1:] = torch.cumsum(lens, 0)
+        e_perm = torch.repeat_interleave(sp[:-1][order] - sg_ptr[:-1], lens) + torch.arange(plan.E, device=plan.device)
+        seg_graph = None
+        if S and plan.device.type == "cuda":
+            sg_rowptr = sg_ptr.to(torch.int32).contiguous()
+            sg_rel = torch.zeros(plan.E, dtype=torch.uint8, device=plan.device)
+            seg_graph = dict(rowptr=sg_rowptr, e_src=plan.e_src[e_perm].contiguous(), e_rel=sg_rel,
+                             e_sim=torch.ones(plan.E, dtype=torch.float32, device=plan.device),
+                             inv=torch.ones(S, dtype=torch.float32, device=plan.device),
+                             ew=torch.ones(1, dtype=torch.float32, device=plan.device),
+                             eb=torch.zeros(1, dtype=torch.float32, device=plan.device),
+                             work=ops.plan_attn_work_finish(ops.plan_attn_work_begin(sg_rowptr, sg_rel, S, 16)))
         plan.cache[key] = dict(
+            seg_graph=seg_graph,
             seg_rel=seg_rel.to(torch.int32).contiguous(),
             order=order.to(torch.int32).contiguous(),
             dst_of_order=segs["seg_dst"][order].contiguous(),
@@ -169,7 +187,9 @@ class HGTLayer(nn.Module):
             w_kv = torch.cat([w_kvq[:, :D][:, pm], w_kvq[:, D:2 * D][:, pm]], 1).contiguous()
             b_kv = torch.cat([b_kvq[:, :D][:, pm], b_kvq[:, D:2 * D][:, pm]], 1).contiguous()
             w_q, b_q = w_kvq[:, 2 * D:].contiguous(), b_kvq[:, 2 * D:].contiguous()
-            att = torch.stack([torch.block_diag(*self.relation_att[r]) for r in range(self.num_relations)])        # [R, D(n), D(k)]
+            # relation_pri[r, h] (the prior on the scores, :100) scales the rows of head h of the query transform
+            pri = self.relation_pri.repeat_interleave(self.d_k, 1).unsqueeze(2)                                     # [R, D, 1]
+            att = torch.stack([torch.block_diag(*self.relation_att[r]) for r in range(self.num_relations)]) * pri  # [R, D(n), D(k)]
             msg = torch.stack([torch.block_diag(*self.relation_msg[r]).t() for r in range(self.num_relations)])    # [R, D(n), D(k)]
             att, msg = att[:, pm, :].contiguous(), msg[:, :, pm].contiguous()
             return dict(w_kv=ops.to_operand(w_kv, opf), b_kv=b_kv, w_q=ops.to_operand(w_q, opf), b_q=b_q,
@@ -194,13 +214,19 @@ class HGTLayer(nn.Module):
             kv, _ = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, type_ptr_c=tpc, opf=opf)
         q, _ = ops.typed_linear_op(xs, pk["w_q"], pk["b_q"], plan.type_ptr, D, type_ptr_c=tpc, opf=opf)
         # q'_seg = relation_att[r, h] . q[dst, h] for the segments in relation order   (:88-92)
+        # (single-pass formats: q'_seg and the segment messages leave their GEMMs in the 16-bit storage form only - the two
+        #  [S, D] tensors are the bulk of the layer's HBM traffic; the 3-term format keeps them fp32)
+        st16 = opf != ops.OPF_BF16X3
         qg = ops.gather_to_operand(q, grp["dst_of_order"], opf)
-        qseg, _ = ops.typed_linear_op(qg, pk["w_att"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"], opf=opf)
-        _, aggseg = ops.hetero_attn_seg(kv[:, :D], kv[:, D:], qseg, None, grp["seg_rel_sorted"], plan.e_src,
-                                        self.relation_pri, D, H, True, items=grp["items"], want_out=False, op_out=True,
-                                        opf=opf)                                                            # :95-104
-        msgseg, _ = ops.typed_linear_op(aggseg, pk["w_msg"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"],
-                                        opf=opf)                                                            # :93
+        qseg32, qseg16 = ops.typed_linear_op(qg, pk["w_att"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"], opf=opf,
+                                             want_y=not st16, want_op=st16)
+        qseg = qseg16 if st16 else qseg32
+        sg = grp["seg_graph"]
+        aggseg = ops.hetero_attn_work(kv[:, :D], kv[:, D:], qseg, sg["work"], sg["e_src"], sg["e_sim"], sg["e_rel"], sg["inv"],
+                                      sg["ew"], sg["eb"], D, H, op_out=True, opf=opf)                       # :95-104
+        msg32, msg16 = ops.typed_linear_op(aggseg, pk["w_msg"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"],
+                                           opf=opf, want_y=not st16, want_op=st16)                          # :93
+        msgseg = msg16 if st16 else msg32
         _, aggs = ops.segment_combine(msgseg, segs["row_seg_ptr"], plan.node_inv_r, plan.N, D, seg_pos=grp["seg_pos"],
                                       want_out=False, op_out=True, opf=opf)                                 # :105-106
         mask = None

@@ -288,19 +288,22 @@ def hetero_attn(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, rowptr: torch
 def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: dict, e_src: torch.Tensor,
                      e_sim: torch.Tensor, e_rel: torch.Tensor, node_inv_r: torch.Tensor, e_w: torch.Tensor,
                      e_b: torch.Tensor, D: int, H: int, out: Optional[torch.Tensor] = None,
-                     op_out: bool = False, opf: Optional[int] = None) -> torch.Tensor:
+                     op_out: bool = False, opf: Optional[int] = None, n_rows: Optional[int] = None) -> torch.Tensor:
     """HEAT edge attention driven by the hub-balancing work list of GraphPlan.attn_work();
     see wsi_hetero_attn_work_fwd.  k/v/q/agg columns are in the head_perm(D, H) order.
-    op_out: return the result in operand form (to_operand layout, the A operand of typed_linear_op) instead of fp32."""
+    op_out: return the result in operand form (to_operand layout, the A operand of typed_linear_op) instead of fp32.
+    q may be fp32 / fp16 / bf16; its row count is the number of output rows (HGT: segments), k / v rows are gathered."""
     lib = _lib.load()
     stream = _prep(q)
     opf = matmul_opf(opf)
-    N = int(q.shape[0])
+    N = int(q.shape[0]) if n_rows is None else int(n_rows)
+    if q.dtype not in _KV_DTYPE:
+        raise TypeError(f"hetero_attn_work: q must be fp32, fp16 or bf16, got {q.dtype}")
     if k.dtype != v.dtype or k.dtype not in _KV_DTYPE:
         raise TypeError(f"hetero_attn_work: k / v must both be fp32, fp16 or bf16, got {k.dtype} / {v.dtype}")
     kp, ldk = _rows(k, "k", k.dtype)
     vp, ldv = _rows(v, "v", v.dtype)
-    qp, ldq = _rows(q, "q")
+    qp, ldq = _rows(q, "q", q.dtype)
     agg = agg_split = None
     if op_out:
         agg_split = torch.empty((operand_rows(N, opf), D), dtype=_OPF_DTYPE[opf], device=q.device)
@@ -313,9 +316,10 @@ def hetero_attn_work(k: torch.Tensor, v: torch.Tensor, q: torch.Tensor, work: di
     if n_part > 0:
         part_ms = torch.empty((n_part, 64), dtype=torch.float32, device=q.device)
         part_acc = torch.empty((n_part, D), dtype=torch.float32, device=q.device)
-    rc = lib.wsi_hetero_attn_work_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, ldq, _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
+    rc = lib.wsi_hetero_attn_work_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, _KV_DTYPE[q.dtype], ldq,
+                                      _vec(e_src, "e_src", torch.int32), _vec(e_sim, "e_sim"),
                                       _vec(e_rel, "e_rel", torch.uint8), _vec(node_inv_r, "node_inv_r"),
-                                      _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, D, H,
+                                      _vec(e_w.reshape(-1), "e_w"), _vec(e_b.reshape(-1), "e_b"), N, int(k.shape[0]), D, H,
                                       _vec(work["items"], "items", torch.int32), work["n_items"],
                                       _vec(work["split_row"], "split_row", torch.int32),
                                       _vec(work["split_ptr"], "split_ptr", torch.int32),
@@ -397,17 +401,19 @@ def hetero_attn_seg(k, v, qseg, seg_ptr, seg_rel, e_src, rel_pri, D: int, H: int
         raise TypeError(f"hetero_attn_seg: k / v must both be fp32, fp16 or bf16, got {k.dtype} / {v.dtype}")
     kp, ldk = _rows(k, "k", k.dtype)
     vp, ldv = _rows(v, "v", v.dtype)
-    qp, ldq = _rows(qseg, "qseg")
+    if qseg.dtype not in _KV_DTYPE:
+        raise TypeError(f"hetero_attn_seg: qseg must be fp32, fp16 or bf16, got {qseg.dtype}")
+    qp, ldq = _rows(qseg, "qseg", qseg.dtype)
     opf = matmul_opf(opf)
     out = torch.empty((S, D), dtype=torch.float32, device=qseg.device) if want_out or not op_out else None
     out_op = torch.empty((operand_rows(S, opf), D), dtype=_OPF_DTYPE[opf], device=qseg.device) if op_out else None
     if items is not None and (items.dtype != torch.int32 or tuple(items.shape) != (S, 4) or not items.is_contiguous()):
         raise ValueError(f"hetero_attn_seg: items must be a contiguous int32 [{S}, 4] tensor")
-    rc = lib.wsi_hetero_attn_seg_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, ldq,
+    rc = lib.wsi_hetero_attn_seg_fwd(kp, ldk, vp, ldv, _KV_DTYPE[k.dtype], qp, _KV_DTYPE[qseg.dtype], ldq,
                                      _vec(seg_ptr, "seg_ptr", torch.int32) if seg_ptr is not None else None,
                                      _vec(seg_rel, "seg_rel", torch.int32), _vec(e_src, "e_src", torch.int32),
                                      _vec(rel_pri, "rel_pri"), S, D, H, 1 if use_head_perm else 0,
-                                     items.data_ptr() if items is not None else None,
+                                     items.data_ptr() if items is not None else None, int(k.shape[0]),
                                      out.data_ptr() if out is not None else None, D,
                                      out_op.data_ptr() if out_op is not None else None, opf, stream)
     _lib.check(rc, "wsi_hetero_attn_seg_fwd")
@@ -435,11 +441,13 @@ def segment_combine(msg, row_seg_ptr, node_inv_r, N: int, D: int, seg_pos: Optio
     seg_pos int32 [S]: msg row of segment s.  With op_out: (agg or None, operand-form copy)."""
     lib = _lib.load()
     stream = _prep(node_inv_r)
-    mp, ldm = _rows(msg, "msg")
+    if msg.dtype not in _KV_DTYPE:
+        raise TypeError(f"segment_combine: msg must be fp32, fp16 or bf16, got {msg.dtype}")
+    mp, ldm = _rows(msg, "msg", msg.dtype)
     opf = matmul_opf(opf)
     agg = torch.empty((N, D), dtype=torch.float32, device=node_inv_r.device) if want_out or not op_out else None
     agg_op = torch.empty((operand_rows(N, opf), D), dtype=_OPF_DTYPE[opf], device=node_inv_r.device) if op_out else None
-    rc = lib.wsi_segment_combine(mp, ldm, _vec(row_seg_ptr, "row_seg_ptr", torch.int32),
+    rc = lib.wsi_segment_combine(mp, _KV_DTYPE[msg.dtype], ldm, _vec(row_seg_ptr, "row_seg_ptr", torch.int32),
                                  _vec(seg_pos, "seg_pos", torch.int32) if seg_pos is not None else None,
                                  _vec(node_inv_r, "node_inv_r"), N, D, agg.data_ptr() if agg is not None else None, D,
                                  agg_op.data_ptr() if agg_op is not None else None, opf, stream)
