@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 18
+#define WSI_ABI_VERSION 19
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -101,6 +101,9 @@ int wsi_to_operand(const float* src, int64_t ld_src, int64_t rows, int K, int op
  * segments of HGT pick up their dst node's query (models/HGT.py:88-92 moved to the dst side). */
 int wsi_gather_to_operand(const float* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, int opf, void* dst,
                           void* stream);
+/* The same gather on a matrix that already is in a single-plane operand form (WSI_OPF_F16 / WSI_OPF_BF16, [n, K] 16-bit,
+ * dense rows): dst row i = src row row_idx[i]. */
+int wsi_gather_rows16(const void* src, const int32_t* row_idx, int64_t rows, int K, void* dst, void* stream);
 int wsi_typed_linear_op(const void* x_op, const void* w_op, const float* bias, int K, int n_out,
                         const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
                         int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,
@@ -221,9 +224,11 @@ int wsi_segment_combine(const void* msg, int msg_dtype, int64_t ldm, const int32
  *   gamma/beta [T, D]; rows of type t = [type_ptr_host[t], type_ptr_host[t+1]).
  *   row_gate [N] or NULL: rows with gate == 0 are copied through un-normalised - the reference `continue`s before the
  *   norm for a node type without incoming relation (models/HGT.py:118-120); per ROW because in a pack()ed batch that is
- *   a per-(type, graph) property (pass node_inv_r). */
+ *   a per-(type, graph) property (pass node_inv_r).
+ *   y_op or NULL (D % 128 == 0, D <= 1024): operand-form copy of the result (wsi_to_operand layout for `opf`), the A
+ *   operand of the next layer's GEMMs - written in the same pass; y may then be NULL. */
 int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, const float* row_gate,
-                        const int32_t* type_ptr_host, int T, int D, float eps, float* y, int64_t ldy,
+                        const int32_t* type_ptr_host, int T, int D, float eps, float* y, int64_t ldy, void* y_op, int opf,
                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------

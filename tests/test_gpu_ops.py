@@ -355,6 +355,33 @@ def test_typed_layernorm():
     assert rel(y, ref) < 1e-5
 
 
+@pytest.mark.parametrize("D", [128, 512, 1024])
+def test_typed_layernorm_vector_path_with_operand_output(D):
+    """D % 128 == 0: the register-resident kernel; row gate (passthrough rows), in place, and the operand-form copy of
+    the result == the conversion of the result."""
+    g = torch.Generator().manual_seed(D)
+    ptr = [0, 33, 33, 113]
+    x = torch.randn(113, D, generator=g) * 3 + 1
+    gamma, beta = torch.randn(3, D, generator=g), torch.randn(3, D, generator=g)
+    gate = (torch.rand(113, generator=g) > 0.3).float()
+    ln = torch.cat([torch.nn.functional.layer_norm(x[ptr[t]:ptr[t + 1]].double(), (D,), gamma[t].double(),
+                                                   beta[t].double(), 1e-5) for t in range(3)])
+    ref = torch.where(gate.unsqueeze(1) != 0, ln, x.double())
+    for opf in (ops.OPF_BF16X3, ops.OPF_F16, ops.OPF_BF16):
+        xc = x.cuda()
+        y, y_op = ops.typed_layernorm(xc, gamma.cuda(), beta.cuda(), ptr, inplace=True, row_gate=gate.cuda(), op_out=True, opf=opf)
+        assert y.data_ptr() == xc.data_ptr() and rel(y, ref) < 1e-5
+        want = ops.to_operand(y, opf)
+        assert torch.equal(y_op.view(torch.int16), want.view(torch.int16))
+
+
+def test_gather_rows16():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(300, 256, generator=g).cuda().to(torch.bfloat16)
+    idx = torch.randint(0, 300, (1000,), generator=g).to(torch.int32).cuda()
+    assert torch.equal(ops.gather_rows16(x, idx), x[idx.long()])
+
+
 @pytest.mark.parametrize("dk,H", [(50, 4), (128, 4), (32, 8)])
 def test_rel_transform(dk, H):
     g = torch.Generator().manual_seed(dk)

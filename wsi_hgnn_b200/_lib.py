@@ -6,7 +6,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -61,6 +61,7 @@ PROTOTYPES = {
     "wsi_typed_linear_tc_ok": (_I, [_L, _I, _I]),
     "wsi_to_operand": (_I, [_P, _L, _L, _I, _I, _P, _P]),
     "wsi_gather_to_operand": (_I, [_P, _L, _P, _L, _I, _I, _P, _P]),
+    "wsi_gather_rows16": (_I, [_P, _P, _L, _I, _P, _P]),
     "wsi_typed_linear_op": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _I, _P]),
     "wsi_hetero_attn_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _L,
                                  _P, _P, _P, _P, _P, _L, _P, _P]),
@@ -68,7 +69,7 @@ PROTOTYPES = {
     "wsi_head_perm": (_I, [_I, _I, _P]),
     "wsi_rel_transform": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _L, _P]),
     "wsi_segment_combine": (_I, [_P, _I, _L, _P, _P, _P, _L, _I, _P, _L, _P, _I, _P]),
-    "wsi_typed_layernorm": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _F, _P, _L, _P]),
+    "wsi_typed_layernorm": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _F, _P, _L, _P, _I, _P]),
     "wsi_plan_workspace_bytes": (_L, [_L, _L]),
     "wsi_plan_build_csr": (_I, [_P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "wsi_plan_attn_work_count": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),

@@ -89,7 +89,6 @@ __device__ __forceinline__ void st_split4(__nv_bfloat16* dst, int64_t lo_off, fl
   *reinterpret_cast<uint2*>(dst + lo_off) = *reinterpret_cast<uint2*>(lv);
 }
 
-__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // 4 consecutive K / V elements of a storage type (fp32: 16 B, fp16 / bf16: 8 B) -> fp32
 __device__ __forceinline__ float4 cvt4(uint2 r, const __half*) {
   const __half2 a = *reinterpret_cast<const __half2*>(&r.x), b = *reinterpret_cast<const __half2*>(&r.y);

@@ -271,6 +271,55 @@ typed_layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __
   }
 }
 
+// Same, D = 128 * NV: the row lives in registers (one 16-byte load per lane and 128 columns, read ONCE), and the
+// operand-form copy of the result - the A operand of the next layer's K | V | Q GEMMs - is written in the same pass.
+template <int NV>
+__global__ void __launch_bounds__(256)
+typed_layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, const float* __restrict__ row_gate, TypeSegs segs, float eps,
+                           float* __restrict__ y, int64_t ldy, uint16_t* __restrict__ y_op, int64_t lo_off) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int n_rows = segs.ptr[segs.T];
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 8) {
+    int t = 0;
+    while (t + 1 < segs.T && row >= segs.ptr[t + 1]) ++t;
+    const float* xr = x + (int64_t)row * ldx;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    if (!(row_gate && __ldg(row_gate + row) == 0.f)) {     // (gate == 0: passthrough row, copied through un-normalised)
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+      const float mean = s / (float)D;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q = fmaf(v[i].x, v[i].x, q); q = fmaf(v[i].y, v[i].y, q); q = fmaf(v[i].z, v[i].z, q); q = fmaf(v[i].w, v[i].w, q);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(FULL, q, o);
+      const float rstd = rsqrtf(q / (float)D + eps);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + (int64_t)t * D + (i * 32 + lane) * 4));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + (int64_t)t * D + (i * 32 + lane) * 4));
+        v[i].x = fmaf(v[i].x * rstd, g.x, b.x); v[i].y = fmaf(v[i].y * rstd, g.y, b.y);
+        v[i].z = fmaf(v[i].z * rstd, g.z, b.z); v[i].w = fmaf(v[i].w * rstd, g.w, b.w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (y) *reinterpret_cast<float4*>(y + (int64_t)row * ldy + (i * 32 + lane) * 4) = v[i];
+      if (y_op) store_operand4_rt(y_op + (int64_t)row * D + (i * 32 + lane) * 4, lo_off, v[i]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // HGT: agg[v] = inv_r[v] * sum of the messages of the (v, relation) segments of row v
 // (stack->mean of multi_update_all(..., cross_reducer='mean'), reference models/HGT.py:105-106).
@@ -415,15 +464,31 @@ extern "C" int wsi_segment_pool_affine_fwd(const float* x, int64_t ldx, const in
 
 extern "C" int wsi_typed_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta,
                                    const float* row_gate, const int32_t* type_ptr_host, int T, int D, float eps, float* y,
-                                   int64_t ldy, void* stream) {
-  WSI_CHECK_ARG(x && gamma && beta && y && type_ptr_host, "typed_layernorm: null pointer");
+                                   int64_t ldy, void* y_op, int opf, void* stream) {
+  WSI_CHECK_ARG(x && gamma && beta && (y || y_op) && type_ptr_host, "typed_layernorm: null pointer");
   TypeSegs segs;
   WSI_CHECK_ARG(wsi_make_segs(&segs, type_ptr_host, T, 1) == 0, "typed_layernorm: bad type_ptr (T=%d)", T);
   int n_rows = segs.ptr[T];
   if (n_rows == 0) return WSI_OK;
   int blocks = (n_rows + 7) / 8;
   { const int sms = wsi_num_sms(); if (sms <= 0) return WSI_ERR_CUDA; if (blocks > sms * 16) blocks = sms * 16; }
-  typed_layernorm_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(x, ldx, gamma, beta, row_gate, segs, D, eps, y, ldy);
+  const bool vec = D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && (!y || ldy % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(beta) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_op) & 7) == 0;
+  WSI_CHECK_ARG(!y_op || (vec && opf >= 0 && opf <= 2),
+                "typed_layernorm: the operand-form output needs D %% 128 == 0, D <= 1024 and 16 B aligned rows");
+  WSI_CHECK_ARG(vec || y, "typed_layernorm: null pointer");
+  if (vec) {
+    const int64_t lo_off = opf == WSI_OPF_BF16X3 ? (int64_t)n_rows * D : (opf == WSI_OPF_F16 ? 0 : -1);
+    switch (D / 128) {
+#define CASE(NV) case NV: typed_layernorm_vec_kernel<NV><<<blocks, 256, 0, wsi_stream(stream)>>>( \
+        x, ldx, gamma, beta, row_gate, segs, eps, y, ldy, reinterpret_cast<uint16_t*>(y_op), lo_off); break;
+      CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+  } else {
+    typed_layernorm_kernel<<<blocks, 256, 0, wsi_stream(stream)>>>(x, ldx, gamma, beta, row_gate, segs, D, eps, y, ldy);
+  }
   WSI_CHECK_LAUNCH();
   return WSI_OK;
 }

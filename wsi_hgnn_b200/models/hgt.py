@@ -123,7 +123,17 @@ class HGTLayer(nn.Module):
 
         return self._packs.get(tuple(order), params, build)
 
-    def forward_packed(self, plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
+    def forward_packed(self, plan: GraphPlan, x: torch.Tensor, x_op=None, want_op: bool = False):
+        """-> h' [N, D]; with want_op -> (h', operand-form copy of h' or None): the tensor-core schedule hands the next
+        layer its GEMM operand (x_op) so that no conversion pass runs between the layers."""
+        out, out_op = self.forward_packed_pair(plan, x, x_op, want_op)
+        return (out, out_op) if want_op else out
+
+    def forward_packed_pair(self, plan: GraphPlan, x: torch.Tensor, x_op=None, want_op: bool = False):
+        out = self._forward_packed(plan, x, x_op, want_op)
+        return out if isinstance(out, tuple) else (out, None)
+
+    def _forward_packed(self, plan: GraphPlan, x: torch.Tensor, x_op, want_op: bool):
         D, H, dk = self.out_dim, self.n_heads, self.d_k
         order = _graph_type_order(plan, self.node_dict)
         w_kvq, b_kvq, wa, ba, skip, gamma, beta = self._packed(order)
@@ -134,7 +144,7 @@ class HGTLayer(nn.Module):
         opf = ops.matmul_opf()
         if (ops.head_perm(D, H) is not None and ops.tc_ok(S, D, D) and ops.tc_ok(plan.N, self.in_dim, 2 * D)
                 and ops.tc_ok(plan.N, self.in_dim, D) and ops.tc_ok(plan.N, D, D)):
-            return self._forward_packed_tc(plan, x, order, grp, segs, opf)
+            return self._forward_packed_tc(plan, x, order, grp, segs, opf, x_op, want_op)
         if opf == ops.OPF_BF16 and ops.tc_ok(plan.N, self.in_dim, 2 * D) and ops.tc_ok(plan.N, self.in_dim, D):
             # bf16 storage of K | V (set_matmul_precision("bf16"): BASELINE config 3): the K|V GEMM writes ONLY the bf16
             # operand-form copy, the edge kernel gathers half the bytes; Q stays fp32 for the relation transform.
@@ -198,7 +208,7 @@ class HGTLayer(nn.Module):
 
         return self._packs.get(("tc", opf, tuple(order)), params, build)
 
-    def _forward_packed_tc(self, plan: GraphPlan, x, order, grp, segs, opf) -> torch.Tensor:
+    def _forward_packed_tc(self, plan: GraphPlan, x, order, grp, segs, opf, x_op=None, want_op: bool = False):
         """The layer on tensor cores end to end (models/HGT.py:68-127): every dense product is a tcgen05 grouped GEMM on
         operand-form inputs, every producer writes the operand form its consumer reads (no conversion passes between
         them), the edge kernel is the lane-grouped one of HEAT running over the relation-sorted (dst, relation) segments."""
@@ -206,18 +216,19 @@ class HGTLayer(nn.Module):
         pk = self._packed_tc(order, opf, x.device)
         tpc = plan.type_ptr_c()
         S = segs["S"]
-        xs = ops.to_operand(x, opf)
+        xs = x_op if x_op is not None else ops.to_operand(x, opf)
+        st16 = opf != ops.OPF_BF16X3
         if opf == ops.OPF_BF16:        # bf16 storage of K | V (BASELINE config 3): only the 16-bit copy is written
             _, kv = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, want_y=False, want_op=True,
                                         type_ptr_c=tpc, opf=opf)
         else:
             kv, _ = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, type_ptr_c=tpc, opf=opf)
-        q, _ = ops.typed_linear_op(xs, pk["w_q"], pk["b_q"], plan.type_ptr, D, type_ptr_c=tpc, opf=opf)
         # q'_seg = relation_att[r, h] . q[dst, h] for the segments in relation order   (:88-92)
-        # (single-pass formats: q'_seg and the segment messages leave their GEMMs in the 16-bit storage form only - the two
+        # (single-pass formats: q, q'_seg and the segment messages leave their GEMMs in the 16-bit storage form only - the
         #  [S, D] tensors are the bulk of the layer's HBM traffic; the 3-term format keeps them fp32)
-        st16 = opf != ops.OPF_BF16X3
-        qg = ops.gather_to_operand(q, grp["dst_of_order"], opf)
+        q32, q16 = ops.typed_linear_op(xs, pk["w_q"], pk["b_q"], plan.type_ptr, D, type_ptr_c=tpc, opf=opf,
+                                       want_y=not st16, want_op=st16)
+        qg = ops.gather_rows16(q16, grp["dst_of_order"]) if st16 else ops.gather_to_operand(q32, grp["dst_of_order"], opf)
         qseg32, qseg16 = ops.typed_linear_op(qg, pk["w_att"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"], opf=opf,
                                              want_y=not st16, want_op=st16)
         qseg = qseg16 if st16 else qseg32
@@ -235,6 +246,9 @@ class HGTLayer(nn.Module):
         out, _ = ops.typed_linear_op(aggs, pk["wa"], pk["ba"], plan.type_ptr, D, skip=pk["skip"], res=x,
                                      row_gate=plan.node_inv_r, drop_mask=mask, type_ptr_c=tpc, opf=opf)     # :121-122
         if self.use_norm:
+            if want_op:
+                return ops.typed_layernorm(out, pk["gamma"], pk["beta"], plan.type_ptr, type_ptr_c=tpc, inplace=True,
+                                           row_gate=plan.node_inv_r, op_out=True, opf=opf)
             out = _gated_layernorm(out, pk["gamma"], pk["beta"], plan, tpc)
         return out
 
@@ -341,6 +355,7 @@ class HGT(nn.Module):
         x = ops.typed_linear(x, w_in, b_in, plan.type_ptr, act=ops.ACT_GELU, type_ptr_c=plan.type_ptr_c())  # :176-184
         scale = readout_scale(plan, G.independent)
         hg = None
+        x_op = None
         n_run = self.n_layers if return_embeddings else self.n_layers
         for i in range(n_run):                                             # :189-199
             pp = param_list(self, ("pred", i, tuple(names)), lambda: (p for nt in names for p in self.linears_prediction[nt][i].parameters()))
@@ -357,7 +372,10 @@ class HGT(nn.Module):
             # the output of the LAST layer is never read by the reference (models/HGT.py:199-209);
             # it is computed only when the caller asks for the embeddings
             if i + 1 < self.n_layers or return_embeddings:
-                x = self.gcs[i].forward_packed(plan, x)
+                # (the layer after this one runs iff i + 2 < n_layers or embeddings are asked for: only then is the
+                #  operand-form copy of h' wanted)
+                nxt = i + 2 < self.n_layers or (return_embeddings and i + 1 < self.n_layers)
+                x, x_op = self.gcs[i].forward_packed_pair(plan, x, x_op, want_op=nxt)
         if hg is None:
             hg = torch.zeros(B, self.out_dim, device=x.device)
         return (hg, unpack_rows(plan, x)) if return_embeddings else hg

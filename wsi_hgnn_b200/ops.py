@@ -226,6 +226,19 @@ def gather_to_operand(x: torch.Tensor, row_idx: torch.Tensor, opf: Optional[int]
     return out
 
 
+def gather_rows16(x_op: torch.Tensor, row_idx: torch.Tensor) -> torch.Tensor:
+    """out row i = x_op[row_idx[i]] for a single-plane 16-bit operand matrix (OPF_F16 / OPF_BF16); see wsi_gather_rows16."""
+    lib = _lib.load()
+    stream = _prep(x_op)
+    if x_op.dtype not in (torch.float16, torch.bfloat16) or x_op.dim() != 2 or not x_op.is_contiguous():
+        raise ValueError("gather_rows16: expected a contiguous fp16 / bf16 matrix")
+    rows, K = int(row_idx.numel()), int(x_op.shape[1])
+    out = torch.empty((rows, K), dtype=x_op.dtype, device=x_op.device)
+    _lib.check(lib.wsi_gather_rows16(x_op.data_ptr(), _vec(row_idx, "row_idx", torch.int32), rows, K, out.data_ptr(), stream),
+               "wsi_gather_rows16")
+    return out
+
+
 def typed_linear_op(x_op: torch.Tensor, w_op: torch.Tensor, bias: Optional[torch.Tensor],
                     type_ptr: Sequence[int], n_out: int, *, act: int = ACT_NONE,
                     skip: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
@@ -456,7 +469,8 @@ def segment_combine(msg, row_seg_ptr, node_inv_r, N: int, D: int, seg_pos: Optio
 
 
 def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, type_ptr_c=None, inplace=False,
-                    row_gate: Optional[torch.Tensor] = None):
+                    row_gate: Optional[torch.Tensor] = None, op_out: bool = False, opf: Optional[int] = None):
+    """Per-node-type LayerNorm (row-gated); with op_out -> (y, operand-form copy of y); see wsi_typed_layernorm."""
     lib = _lib.load()
     stream = _prep(x)
     T = len(type_ptr) - 1
@@ -467,10 +481,12 @@ def typed_layernorm(x, gamma, beta, type_ptr: Sequence[int], eps: float = 1e-5, 
     y = x if inplace else torch.empty_like(x)
     yp, ldy = _rows(y, "y")
     tp = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
+    opf = matmul_opf(opf)
+    y_op = torch.empty((operand_rows(int(x.shape[0]), opf), D), dtype=_OPF_DTYPE[opf], device=x.device) if op_out else None
     rc = lib.wsi_typed_layernorm(xp, ldx, _vec(gamma, "gamma"), _vec(beta, "beta"), _vec(row_gate, "row_gate"), tp, T, D,
-                                 float(eps), yp, ldy, stream)
+                                 float(eps), yp, ldy, y_op.data_ptr() if y_op is not None else None, opf, stream)
     _lib.check(rc, "wsi_typed_layernorm")
-    return y
+    return (y, y_op) if op_out else y
 
 
 def skip_mix_bwd(dout, out, x, drop_mask, skip, row_gate, type_ptr: Sequence[int], type_ptr_c=None):
