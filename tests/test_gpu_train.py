@@ -94,7 +94,8 @@ def test_train_step_reduces_loss():
 
 def test_attn_bwd_two_pass_equals_atomic_mode():
     """wsi_hetero_attn_bwd: the two-pass mode (coefficients + source-major second kernel, no atomics) and the one-pass
-    vector-atomic mode produce the same dK / dV / dQ / d e_linear (up to the atomics' summation order)."""
+    vector-atomic mode produce the same dK / dV / dQ / d e_linear (up to summation order: the atomics', and that of the
+    one-sweep accumulation the two-pass mode uses for segments of more than two edges)."""
     from wsi_hgnn_b200 import ops
     D, H = 256, 4
     G = synthetic.synth_slide_graph(900, 32, 3, 6, seed=4, noise_edges=0.3).to("cuda")
@@ -113,4 +114,3 @@ def test_attn_bwd_two_pass_equals_atomic_mode():
         outs.append((dk, dv, dq, d_e))
     for a, b in zip(*outs):
         assert helpers.rel_err(a, b) < 1e-5
-    assert torch.equal(outs[0][2], outs[1][2])            # dQ does not depend on the mode

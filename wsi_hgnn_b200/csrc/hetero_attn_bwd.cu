@@ -208,6 +208,83 @@ __global__ void __launch_bounds__(WARPS * 32, NV <= 4 ? 3 : 1) attn_bwd_kernel(B
             dw_acc = fmaf(dc0, sim0, fmaf(dc1, sim1, dw_acc));
             db_acc += dc0 + dc1;
           }
+        } else if (a.coef) {
+          // ---- ONE sweep over K[src], V[src] (two-pass mode; measured round 2: the second sweep of the AB / C scheme
+          // below missed L1 / L2 for most rows at training batch sizes - 8.2 GB of DRAM reads against 6.0 GB
+          // algorithmic).  Everything that needs the final softmax statistics is kept in a form that can be rescaled:
+          //   dQ_seg = sum_e ds_e c_e K_e,  ds_e = a_e (t_e - delta),  a_e = p_e / Z,  t_e = <g, V_e>
+          //          = (A1 - delta A2) / Z   with  A1 = sum_e p_e t_e c_e K_e,  A2 = sum_e p_e c_e K_e
+          // (online-softmax accumulators, rescaled whenever the running maximum moves), and the per-(edge, head) raw
+          // values d_e = <q, K_e>, t_e are parked in the coefficient array and turned into cK / cV by a lane-parallel
+          // fix-up once m, Z, delta are known.
+          float m = -INFINITY, z = 0.f, num = 0.f;
+          float4 a1[NV], a2[NV];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { a1[i] = make_float4(0.f, 0.f, 0.f, 0.f); a2[i] = a1[i]; }
+          for (int e = seg_beg; e < seg_end; e += 2) {
+            const bool two = e + 1 < seg_end;
+            const int s0 = __ldg(a.e_src + e), s1 = two ? __ldg(a.e_src + e + 1) : s0;
+            const float c0 = fmaf(ew, __ldg(a.e_sim + e), eb) * a.inv_sqrt_dk;
+            const float c1 = two ? fmaf(ew, __ldg(a.e_sim + e + 1), eb) * a.inv_sqrt_dk : 0.f;
+            float4 k0[NV], k1[NV], v0[NV], v1[NV];
+            const float* kr0 = a.K + (int64_t)s0 * a.ldk; const float* kr1 = a.K + (int64_t)s1 * a.ldk;
+            const float* vr0 = a.V + (int64_t)s0 * a.ldv; const float* vr1 = a.V + (int64_t)s1 * a.ldv;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              k0[i] = ld4(kr0 + (i * 32 + lane) * 4); k1[i] = ld4(kr1 + (i * 32 + lane) * 4);
+              v0[i] = ld4(vr0 + (i * 32 + lane) * 4); v1[i] = ld4(vr1 + (i * 32 + lane) * 4);
+            }
+            const float d0 = head_dot<NV>(q, k0, G), d1 = head_dot<NV>(q, k1, G);
+            const float sc0 = d0 * c0, sc1 = two ? d1 * c1 : -INFINITY;
+            const float t0 = head_dot<NV>(g, v0, G), t1 = head_dot<NV>(g, v1, G);
+            const float mn = fmaxf(m, fmaxf(sc0, sc1));
+            const float corr = __expf(m - mn), p0 = __expf(sc0 - mn), p1 = __expf(sc1 - mn);   // exp(-inf) = 0
+            z = fmaf(z, corr, p0 + p1);
+            num = fmaf(num, corr, fmaf(p0, t0, p1 * t1));
+            m = mn;
+            const float w20 = p0 * c0, w21 = p1 * c1, w10 = w20 * t0, w11 = w21 * t1;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              a1[i].x = fmaf(a1[i].x, corr, fmaf(w10, k0[i].x, w11 * k1[i].x)); a1[i].y = fmaf(a1[i].y, corr, fmaf(w10, k0[i].y, w11 * k1[i].y));
+              a1[i].z = fmaf(a1[i].z, corr, fmaf(w10, k0[i].z, w11 * k1[i].z)); a1[i].w = fmaf(a1[i].w, corr, fmaf(w10, k0[i].w, w11 * k1[i].w));
+              a2[i].x = fmaf(a2[i].x, corr, fmaf(w20, k0[i].x, w21 * k1[i].x)); a2[i].y = fmaf(a2[i].y, corr, fmaf(w20, k0[i].y, w21 * k1[i].y));
+              a2[i].z = fmaf(a2[i].z, corr, fmaf(w20, k0[i].z, w21 * k1[i].z)); a2[i].w = fmaf(a2[i].w, corr, fmaf(w20, k0[i].w, w21 * k1[i].w));
+            }
+            if (lane % G == 0) {                            // park the raw per-(edge, head) values
+              float* c = a.coef + (int64_t)e * 2 * a.H + lane / G;
+              c[0] = d0; c[a.H] = t0;
+              if (two) { c[2 * a.H] = d1; c[3 * a.H] = t1; }
+            }
+          }
+          const float inv_z = 1.f / z;
+          const float delta = num * inv_z;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            dq[i].x = fmaf(fmaf(-delta, a2[i].x, a1[i].x), inv_z, dq[i].x); dq[i].y = fmaf(fmaf(-delta, a2[i].y, a1[i].y), inv_z, dq[i].y);
+            dq[i].z = fmaf(fmaf(-delta, a2[i].z, a1[i].z), inv_z, dq[i].z); dq[i].w = fmaf(fmaf(-delta, a2[i].w, a1[i].w), inv_z, dq[i].w);
+          }
+          // ---- fix-up: every lane takes (edge, head) pairs; the head's statistics come from a lane of its group
+          __syncwarp();
+          const int pairs = n * a.H;
+          for (int p0i = 0; p0i < pairs; p0i += 32) {
+            const int p = p0i + lane;
+            const bool on = p < pairs;
+            const int h = on ? p % a.H : 0, e = seg_beg + (on ? p / a.H : 0);
+            const float mh = __shfl_sync(FULL, m, h * G), izh = __shfl_sync(FULL, inv_z, h * G), dh = __shfl_sync(FULL, delta, h * G);
+            if (on) {
+              volatile float* c = a.coef + (int64_t)e * 2 * a.H + h;
+              const float d = c[0], t = c[a.H];
+              const float sim = __ldg(a.e_sim + e);
+              const float ce = fmaf(ew, sim, eb) * a.inv_sqrt_dk;
+              const float at = __expf(d * ce - mh) * izh;
+              const float ds = at * (t - dh);
+              c[0] = ds * ce;
+              c[a.H] = at * invr;
+              const float dc = ds * d * a.inv_sqrt_dk;
+              dw_acc = fmaf(dc, sim, dw_acc);
+              db_acc += dc;
+            }
+          }
         } else {
           // ---- pass AB: m, Z and delta in one sweep (online softmax), two edges in flight
           float m = -INFINITY, z = 0.f, num = 0.f;
