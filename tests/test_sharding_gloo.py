@@ -116,3 +116,81 @@ def test_flat_grad_allreduce_equals_full_batch_gradient():
     for _, grads in res:
         for a, p in zip(grads, m.parameters()):
             assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-7)
+
+
+def _flat_model_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wsi_hgnn_b200.parallel import FlatModel
+        torch.manual_seed(0)
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.a = torch.nn.ModuleList([torch.nn.Linear(6, 5) for _ in range(3)])      # stacked per "type" below
+                self.b = torch.nn.Linear(5, 3)
+                self.unused = torch.nn.Linear(2, 2)                                          # never receives a gradient
+
+            def forward(self, x):
+                w = torch.stack([l.weight for l in self.a])                                  # grads arrive as views of d(stack)
+                bb = torch.stack([l.bias for l in self.a])
+                h = torch.tanh(torch.einsum("nk,tok->no", x, w) + bb.sum(0))
+                return self.b(h)
+
+        m = Net()
+        flat = FlatModel(m, bucket_mb=1e-4)                               # tiny buckets: several of them, launched from the hooks
+        g = torch.Generator().manual_seed(1)
+        X, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+        mine = list(range(rank, 8, world))
+        halves = [mine[:len(mine) // 2], mine[len(mine) // 2:]]           # two micro-batches
+        out = []
+        for step in range(2):                                             # step 2 launches buckets early (expected sets known)
+            flat.begin_step()
+            for i, idx in enumerate(halves):
+                if i + 1 == len(halves):
+                    flat.arm()
+                (torch.nn.functional.cross_entropy(m(X[idx]), y[idx], reduction="sum") / 8.0).backward()
+                if i + 1 < len(halves):
+                    flat.fold()
+            flat.finish()
+            out.append(([p.grad.tolist() for p in m.parameters()], list(flat._active), len(flat.buckets)))   # plain lists: no shared-memory handles in the queue
+            flat.zero_grad()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_model_buckets_adopted_gradients_two_ranks():
+    """parallel.FlatModel over 2 gloo ranks: gradients adopted from autograd (p.grad None during the step), folded per
+    bucket with multi-tensor adds, bucketed all-reduce from the hooks on the second step; p.grad after finish() == the
+    full-batch gradient; the parameter without a gradient is flagged inactive on every rank (torch.optim.Adam skips it)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flat_model_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    a = torch.nn.ModuleList([torch.nn.Linear(6, 5) for _ in range(3)])
+    b = torch.nn.Linear(5, 3)
+    g = torch.Generator().manual_seed(1)
+    X, y = torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)
+    w, bb = torch.stack([l.weight for l in a]), torch.stack([l.bias for l in a])
+    torch.nn.functional.cross_entropy(b(torch.tanh(torch.einsum("nk,tok->no", X, w) + bb.sum(0))), y).backward()
+    ref = [p.grad for p in list(a.parameters()) + list(b.parameters())]
+    for _, steps in res:
+        for grads, active, n_buckets in steps:
+            assert n_buckets > 1
+            grads = [torch.tensor(x) for x in grads]
+            for got, want in zip(grads[:len(ref)], ref):
+                assert torch.allclose(got, want, rtol=1e-5, atol=1e-7)
+            assert all(float(x.abs().max()) == 0.0 for x in grads[len(ref):])       # the unused layer
+            assert active[:len(ref)] == [True] * len(ref) and active[len(ref):] == [False, False]

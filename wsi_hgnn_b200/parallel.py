@@ -76,12 +76,21 @@ class FlatModel:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = 0
+        self.offs = offs
+        self.steps = [0] * len(self.params)             # per-parameter Adam step (torch counts only steps with a gradient)
+        self._active = [True] * len(self.params)        # parameters that received a gradient in the current step
         with torch.no_grad():
             for p, o in zip(self.params, offs):
                 n = p.numel()
                 self.flat_p[o:o + n].copy_(p.data.reshape(-1))
                 p.data = self.flat_p[o:o + n].view_as(p)
-                p.grad = self.flat_g[o:o + n].view_as(p)
+        # gradient slices.  During a step p.grad is None, so autograd's AccumulateGrad adopts the incoming gradient (a view
+        # of the stacked per-type weight gradient - no kernel) instead of launching one in-place add per parameter
+        # (~150 launches per backward for HEATNet4); fold() then adds all of them into the flat buffer with one
+        # multi-tensor launch per bucket.  After finish() p.grad is the flat slice (what the optimizer / a test reads).
+        self.views = [self.flat_g[o:o + p.numel()].view_as(p) for p, o in zip(self.params, offs)]
+        for p, v in zip(self.params, self.views):
+            p.grad = v
         # buckets: contiguous slices, filled from the LAST parameter backwards (gradients arrive roughly in reverse
         # registration order), each >= bucket_mb
         limit = int(bucket_mb * (1 << 20) / 4)
@@ -115,8 +124,33 @@ class FlatModel:
                 self._launch(b)
         return hook
 
+    def begin_step(self):
+        """Before the first backward of a step: detach the gradient slices so that autograd adopts instead of adds."""
+        for p in self.params:
+            p.grad = None
+        self._active = [False] * len(self.params)
+
+    def fold(self, ids=None):
+        """flat_g += the gradients autograd left on the parameters `ids` (default: all), which are then detached again."""
+        dst, src = [], []
+        for i in (range(len(self.params)) if ids is None else ids):
+            p = self.params[i]
+            g = p.grad
+            if g is None:                                                   # nothing arrived
+                continue
+            self._active[i] = True
+            if g.data_ptr() == self.views[i].data_ptr():                    # accumulated in place already
+                continue
+            dst.append(self.views[i])
+            src.append(g if g.shape == self.views[i].shape else g.reshape(self.views[i].shape))
+            p.grad = None
+        if dst:
+            with torch.no_grad():
+                torch._foreach_add_(dst, src)
+
     def _launch(self, b: int):
-        s, e, _ = self.buckets[b]
+        s, e, ids = self.buckets[b]
+        self.fold(ids)
         self._launched[b] = True
         self._handles.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -137,8 +171,26 @@ class FlatModel:
                     self._launch(b)
             for h in self._handles:
                 h.wait()
+            # a gradient that arrived AFTER its bucket's early launch (a parameter that received none in the previous
+            # step): its slice holds the reduced sum of nothing yet - add the local gradient and reduce that slice alone
+            late = [i for i, p in enumerate(self.params)
+                    if p.grad is not None and p.grad.data_ptr() != self.views[i].data_ptr()]
+            if late:
+                self.fold(late)
+                for i in late:
+                    dist.all_reduce(self.views[i], op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.fold()
         self.expected = [set(s) for s in self._seen]
         self._handles = []
+        if _world(self.group) > 1:
+            # a parameter is stepped iff ANY rank produced a gradient for it (the single-process reference sees the whole
+            # batch): one tiny MAX all-reduce of the flags
+            flags = torch.tensor([1 if a else 0 for a in self._active], dtype=torch.int32, device=self.flat_g.device)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+            self._active = [bool(f) for f in flags.tolist()]
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -148,12 +200,29 @@ class FlatModel:
         """torch.optim.Adam(lr, weight_decay) semantics (parser.py:35-40) over the flat buffers: one kernel."""
         from . import _lib, ops
         stream = ops._prep(self.flat_p)
+        lib = _lib.load()
         self.step_count += 1
-        rc = _lib.load().wsi_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
-                                       self.exp_avg_sq.data_ptr(), self.numel, self.step_count, float(lr), float(betas[0]),
-                                       float(betas[1]), float(eps), float(weight_decay), float(grad_scale),
-                                       1 if zero_grad else 0, stream)
-        _lib.check(rc, "wsi_adam_step")
+        # torch.optim.Adam skips a parameter whose .grad is None (no weight decay, no moment decay, its own step count):
+        # the kernel runs over the contiguous spans of parameters that received a gradient and share a step count -
+        # one span in the usual case, a handful when the model carries unused parameters (HEATNet4's `weight`, HGT's `out`)
+        spans, i, n = [], 0, len(self.params)
+        while i < n:
+            if not self._active[i]:
+                i += 1
+                continue
+            j = i
+            self.steps[i] += 1
+            while j + 1 < n and self._active[j + 1] and self.steps[j + 1] + 1 == self.steps[i]:
+                j += 1
+                self.steps[j] += 1
+            end = self.offs[j + 1] if j + 1 < n else self.numel
+            spans.append((self.offs[i], end, self.steps[i]))
+            i = j + 1
+        for s0, s1, t in spans:
+            rc = lib.wsi_adam_step(self.flat_p.data_ptr() + 4 * s0, self.flat_g.data_ptr() + 4 * s0, self.exp_avg.data_ptr() + 4 * s0,
+                                   self.exp_avg_sq.data_ptr() + 4 * s0, s1 - s0, t, float(lr), float(betas[0]), float(betas[1]),
+                                   float(eps), float(weight_decay), float(grad_scale), 1 if zero_grad else 0, stream)
+            _lib.check(rc, "wsi_adam_step")
 
 
 def train_step(model, graphs, labels: torch.Tensor, global_batch: int, optimizer, reducer: FlatGradAllReduce,
@@ -190,6 +259,7 @@ def flat_train_step(model, flat: FlatModel, micro_batches: Sequence, labels: Seq
         e.record()
         return e
     timed = events is not None and labels[0].is_cuda
+    flat.begin_step()
     for i, (G, y) in enumerate(zip(micro_batches, labels)):
         if i + 1 == len(micro_batches):
             flat.arm()
@@ -198,6 +268,8 @@ def flat_train_step(model, flat: FlatModel, micro_batches: Sequence, labels: Seq
         loss = loss_fn(logits, y, reduction="sum") / float(global_batch)
         t1 = ev() if timed else None
         loss.backward()
+        if i + 1 < len(micro_batches):
+            flat.fold()
         t2 = ev() if timed else None
         if timed:
             mark("fwd", t0, t1)
