@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 19
+#define WSI_ABI_VERSION 20
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -452,6 +452,16 @@ int wsi_typed_wgrad(const void* dy_op, const void* x_op, int M, int Nn, const in
  *   zero_grad != 0 also clears grad (the next step's zero_grad()).  All buffers 16 B aligned, n elements. */
 int wsi_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream);
+
+/* The same step with torch.optim.Adam's treatment of parameters WITHOUT a gradient (skipped: no weight decay, no moment
+ * decay, their own step count).  The flat buffer is a sequence of n_params slices [offs_dev[k], offs_dev[k+1]) (int64
+ * [n_params + 1], 16 B aligned slices, offs_dev[n_params] == n); active_dev int32 [n_params] != 0 marks the parameters that
+ * received a gradient this step (data-parallel: MAX-reduced across the ranks on the device - no host round trip);
+ * steps_dev int32 [n_params] is incremented for the active ones; corr_ws: 8 * n_params bytes of scratch. */
+int wsi_adam_step_masked(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int n_params,
+                         const int64_t* offs_dev, const int32_t* active_dev, int32_t* steps_dev, float* corr_ws, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad,
+                         void* stream);
 
 #ifdef __cplusplus
 }

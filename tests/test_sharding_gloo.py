@@ -155,7 +155,7 @@ def _flat_model_worker(rank, world, port, q):
                 if i + 1 < len(halves):
                     flat.fold()
             flat.finish()
-            out.append(([p.grad.tolist() for p in m.parameters()], list(flat._active), len(flat.buckets)))   # plain lists: no shared-memory handles in the queue
+            out.append(([p.grad.tolist() for p in m.parameters()], [bool(f) for f in flat.flags_dev.tolist()], len(flat.buckets)))   # plain lists: no shared-memory handles in the queue
             flat.zero_grad()
         q.put((rank, out))
     finally:

@@ -11,7 +11,13 @@ tail -2 gpurun_out/${TAG}_smoke.log
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -3 gpurun_out/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
-timeout 300 python tools/bench_kernels.py > gpurun_out/${TAG}_kernels.jsonl 2>&1
+timeout 400 python tools/bench_kernels.py > gpurun_out/${TAG}_kernels.jsonl 2>&1
+timeout 300 python tools/bench_hgt.py --precision bf16 > gpurun_out/${TAG}_hgt_bf16.json 2>&1
+timeout 300 python tools/bench_hgt.py --precision fp16 --check 2 > gpurun_out/${TAG}_hgt_fp16.json 2>&1
+timeout 300 python tools/bench_hgt.py --precision bf16x3 > gpurun_out/${TAG}_hgt_bf16x3.json 2>&1
+timeout 300 python tools/hgt_breakdown.py bf16 > gpurun_out/${TAG}_hgt_breakdown.json 2>&1
+timeout 300 python tools/bench_train.py --batch 16 --steps 5 --warmup 2 > gpurun_out/${TAG}_train16.json 2>&1
+timeout 300 python tools/bench_node_sharded.py --check > gpurun_out/${TAG}_config4_1gpu.json 2>&1
 timeout 300 python tools/forward_breakdown.py > gpurun_out/${TAG}_breakdown.jsonl 2>&1
 python - <<PY
 import json

@@ -6,7 +6,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -90,6 +90,7 @@ PROTOTYPES = {
     "wsi_typed_wgrad_supported": (_I, [_L, _I, _I, _I]),
     "wsi_typed_wgrad_workspace_bytes": (_L, [_I, _I, _P, _I]),
     "wsi_typed_wgrad": (_I, [_P, _P, _I, _I, _P, _I, _P, _P, _L, _P]),
+    "wsi_adam_step_masked": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I, _P]),
     "wsi_adam_step": (_I, [_P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _F, _I, _P]),
     "wsi_slide_forward_workspace_bytes": (_L, [_L, _L, _I, _I, _I, _L]),
     "wsi_slide_forward": (_I, [POINTER(SlideDesc), POINTER(HeatParams), _L, _P, _P, _L, _P, _L, _P, _P]),

@@ -13,6 +13,7 @@ a view of a second flat buffer, so that
   * a bucket = a contiguous slice of the gradient buffer, all-reduced asynchronously as soon as the last gradient of
     the slice has been accumulated (post-accumulate-grad hooks).
 """
+import os
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -77,8 +78,12 @@ class FlatModel:
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = 0
         self.offs = offs
-        self.steps = [0] * len(self.params)             # per-parameter Adam step (torch counts only steps with a gradient)
         self._active = [True] * len(self.params)        # parameters that received a gradient in the current step
+        n = len(self.params)
+        self.offs_dev = torch.tensor(offs + [total], dtype=torch.int64, device=dev)
+        self.flags_dev = torch.ones(n, dtype=torch.int32, device=dev)       # _active on the device (MAX-reduced over the ranks)
+        self.steps_dev = torch.zeros(n, dtype=torch.int32, device=dev)      # per-parameter Adam step (torch counts only steps with a gradient)
+        self.corr_ws = torch.zeros(2 * n, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for p, o in zip(self.params, offs):
                 n = p.numel()
@@ -109,6 +114,7 @@ class FlatModel:
         self._seen = [set() for _ in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._handles = []
+        self._late = []
         self.armed = False                              # hooks fire collectives only in the last micro-batch of a step
         for i, p in enumerate(self.params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
@@ -119,8 +125,9 @@ class FlatModel:
                 return
             b = self.bucket_of[i]
             self._seen[b].add(i)
-            if (self.expected is not None and not self._launched[b] and self._seen[b] >= self.expected[b]
-                    and _world(self.group) > 1):
+            if self._launched[b]:
+                self._late.append(i)                    # arrived after its bucket was reduced (see finish)
+            elif self.expected is not None and self._seen[b] >= self.expected[b] and _world(self.group) > 1:
                 self._launch(b)
         return hook
 
@@ -139,7 +146,7 @@ class FlatModel:
             if g is None:                                                   # nothing arrived
                 continue
             self._active[i] = True
-            if g.data_ptr() == self.views[i].data_ptr():                    # accumulated in place already
+            if g is self.views[i]:                                          # accumulated in place already
                 continue
             dst.append(self.views[i])
             src.append(g if g.shape == self.views[i].shape else g.reshape(self.views[i].shape))
@@ -160,6 +167,7 @@ class FlatModel:
         self._seen = [set() for _ in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._handles = []
+        self._late = []
 
     def finish(self):
         """After the last backward: reduce whatever the hooks did not (first step, parameters without a gradient), then
@@ -173,8 +181,7 @@ class FlatModel:
                 h.wait()
             # a gradient that arrived AFTER its bucket's early launch (a parameter that received none in the previous
             # step): its slice holds the reduced sum of nothing yet - add the local gradient and reduce that slice alone
-            late = [i for i, p in enumerate(self.params)
-                    if p.grad is not None and p.grad.data_ptr() != self.views[i].data_ptr()]
+            late = self._late
             if late:
                 self.fold(late)
                 for i in late:
@@ -183,12 +190,14 @@ class FlatModel:
             self.fold()
         self.expected = [set(s) for s in self._seen]
         self._handles = []
+        # a parameter is stepped iff ANY rank produced a gradient for it (the single-process reference sees the whole
+        # batch): the flags go to the device asynchronously and are MAX-reduced there - no host round trip
+        h = torch.tensor([1 if a else 0 for a in self._active], dtype=torch.int32)
+        if self.flat_g.is_cuda:
+            h = h.pin_memory()            # (cached pinned block; the allocator keeps it until the copy below has run)
+        self.flags_dev.copy_(h, non_blocking=True)
         if _world(self.group) > 1:
-            # a parameter is stepped iff ANY rank produced a gradient for it (the single-process reference sees the whole
-            # batch): one tiny MAX all-reduce of the flags
-            flags = torch.tensor([1 if a else 0 for a in self._active], dtype=torch.int32, device=self.flat_g.device)
-            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
-            self._active = [bool(f) for f in flags.tolist()]
+            dist.all_reduce(self.flags_dev, op=dist.ReduceOp.MAX, group=self.group)
         for p, v in zip(self.params, self.views):
             p.grad = v
 
@@ -203,26 +212,13 @@ class FlatModel:
         lib = _lib.load()
         self.step_count += 1
         # torch.optim.Adam skips a parameter whose .grad is None (no weight decay, no moment decay, its own step count):
-        # the kernel runs over the contiguous spans of parameters that received a gradient and share a step count -
-        # one span in the usual case, a handful when the model carries unused parameters (HEATNet4's `weight`, HGT's `out`)
-        spans, i, n = [], 0, len(self.params)
-        while i < n:
-            if not self._active[i]:
-                i += 1
-                continue
-            j = i
-            self.steps[i] += 1
-            while j + 1 < n and self._active[j + 1] and self.steps[j + 1] + 1 == self.steps[i]:
-                j += 1
-                self.steps[j] += 1
-            end = self.offs[j + 1] if j + 1 < n else self.numel
-            spans.append((self.offs[i], end, self.steps[i]))
-            i = j + 1
-        for s0, s1, t in spans:
-            rc = lib.wsi_adam_step(self.flat_p.data_ptr() + 4 * s0, self.flat_g.data_ptr() + 4 * s0, self.exp_avg.data_ptr() + 4 * s0,
-                                   self.exp_avg_sq.data_ptr() + 4 * s0, s1 - s0, t, float(lr), float(betas[0]), float(betas[1]),
-                                   float(eps), float(weight_decay), float(grad_scale), 1 if zero_grad else 0, stream)
-            _lib.check(rc, "wsi_adam_step")
+        # wsi_adam_step_masked reads the per-parameter flags on the device
+        rc = lib.wsi_adam_step_masked(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                      self.exp_avg_sq.data_ptr(), self.numel, len(self.params), self.offs_dev.data_ptr(),
+                                      self.flags_dev.data_ptr(), self.steps_dev.data_ptr(), self.corr_ws.data_ptr(), float(lr),
+                                      float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(grad_scale),
+                                      1 if zero_grad else 0, stream)
+        _lib.check(rc, "wsi_adam_step_masked")
 
 
 def train_step(model, graphs, labels: torch.Tensor, global_batch: int, optimizer, reducer: FlatGradAllReduce,
