@@ -52,16 +52,13 @@ knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn,
     int best_i = 0x7fffffff;
     float thresh = INFINITY;       // = pair held by lane CAND-1
     int thresh_i = 0x7fffffff;
-    for (int64_t base = 0; base < n; base += 32) {
-      const int64_t c = base + lane;
-      float d = INFINITY;
-      if (c < n) d = fmaf(-2.f, __ldg(drow + c), __ldg(sqn + c));
-      unsigned hits = __ballot_sync(FULL, c < n && pair_less(d, (int)c, thresh, thresh_i));
+    // insertion of the candidates flagged in `hits` (lane l offers (d, base_idx + l * idx_stride)) into the sorted list
+    auto offer = [&](unsigned hits, float d, int base_idx, int idx_stride) {
       while (hits) {
         const int src_lane = __ffs(hits) - 1;
         hits &= hits - 1;
         const float xd = __shfl_sync(FULL, d, src_lane);
-        const int xi = (int)base + src_lane;
+        const int xi = base_idx + src_lane * idx_stride;
         if (!pair_less(xd, xi, thresh, thresh_i)) continue;      // threshold moved since the ballot
         const unsigned smaller = __ballot_sync(FULL, pair_less(best_d, best_i, xd, xi));
         const int pos = __popc(smaller);                          // list is sorted: `smaller` is a prefix mask
@@ -72,6 +69,47 @@ knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn,
         thresh = __shfl_sync(FULL, best_d, CAND - 1);
         thresh_i = __shfl_sync(FULL, best_i, CAND - 1);
       }
+    };
+    // Scan, 256 candidates per step: two 16-byte loads of the dot row and of the squared norms per lane in flight, one
+    // ballot that asks "does ANY of them beat the threshold" - after the first few hundred candidates almost every step
+    // ends there (expected insertions per row ~ CAND ln(n / CAND)), so the scan runs at the rate the rows stream in.
+    // (One candidate per lane and step, as in round 1, left one dependent L2 / DRAM round trip per 32 candidates:
+    //  2.0 ms per 2560 x 100k chunk, 12x its bytes.)  The set of the CAND smallest (score, index) pairs does not depend
+    // on the order in which candidates are offered, so the result is unchanged.
+    const bool vec_ok = (ld_dot & 3) == 0 && (reinterpret_cast<uintptr_t>(drow) & 15) == 0 && (reinterpret_cast<uintptr_t>(sqn) & 15) == 0;
+    const int64_t n_vec = vec_ok ? (n & ~(int64_t)255) : 0;
+    for (int64_t base = 0; base < n_vec; base += 256) {
+      float4 dv[2], sv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        dv[u] = __ldg(reinterpret_cast<const float4*>(drow + base + u * 128 + lane * 4));
+        sv[u] = __ldg(reinterpret_cast<const float4*>(sqn + base + u * 128 + lane * 4));
+      }
+      float d[2][4];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        d[u][0] = fmaf(-2.f, dv[u].x, sv[u].x); d[u][1] = fmaf(-2.f, dv[u].y, sv[u].y);
+        d[u][2] = fmaf(-2.f, dv[u].z, sv[u].z); d[u][3] = fmaf(-2.f, dv[u].w, sv[u].w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) any |= d[u][k] <= thresh;
+      }
+      if (!__ballot_sync(FULL, any)) continue;
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c0 = (int)base + u * 128 + k;                 // lane l holds candidate c0 + 4 l
+          const unsigned hits = __ballot_sync(FULL, pair_less(d[u][k], c0 + 4 * lane, thresh, thresh_i));
+          offer(hits, d[u][k], c0, 4);
+        }
+    }
+    for (int64_t base = n_vec; base < n; base += 32) {
+      const int64_t c = base + lane;
+      float d = INFINITY;
+      if (c < n) d = fmaf(-2.f, __ldg(drow + c), __ldg(sqn + c));
+      const unsigned hits = __ballot_sync(FULL, c < n && pair_less(d, (int)c, thresh, thresh_i));
+      offer(hits, d, (int)base, 1);
     }
     // exact re-rank: candidate j (held by lane j) gets its fp64 direct-form distance, computed by the whole warp
     const float* a = feat + (q0 + qi) * F;
@@ -219,11 +257,35 @@ extern "C" int wsi_knn_topk(const float* feat, int64_t n, int F, int topn, int64
   WSI_CHECK_CUDA(cudaMemsetAsync(max_bits, 0, 4, st));
   row_sqnorm_kernel<<<blocks, 256, 0, st>>>(feat, n, F, sqn, max_bits);
   WSI_CHECK_LAUNCH();
-  for (int64_t q0 = q_begin; q0 < q_end; q0 += qc) {
-    const int n_q = (int)((q_end - q0) < qc ? (q_end - q0) : qc);
+  // query chunks of equal size (a short last chunk would fall off the tensor-core path: 160 rows of a 100k-node slide
+  // cost 2 ms on the SIMT GEMM); the candidate matrix (all rows) is converted to the operand form ONCE
+  const int64_t total_q = q_end - q_begin;
+  const int64_t n_chunks = (total_q + qc - 1) / qc;
+  int64_t chunk = (total_q + n_chunks - 1) / n_chunks;
+  chunk = (chunk + 7) / 8 * 8;
+  if (chunk > qc) chunk = qc;
+  const bool tc = wsi_typed_linear_tc_ok(chunk < total_q ? chunk : total_q, F, (int)n) && n % 4 == 0 && total_q >= 512;
+  char* a_ws = nullptr; char* w_ws = nullptr;
+  if (tc) {
+    uintptr_t wsp = (reinterpret_cast<uintptr_t>(lin_ws) + 1023) & ~(uintptr_t)1023;
+    a_ws = reinterpret_cast<char*>(wsp);
+    w_ws = reinterpret_cast<char*>(wsp + align256(2 * qc * (int64_t)F * 2));
+    int rc = wsi_to_operand(feat, F, n, F, WSI_OPF_BF16X3, w_ws, stream);
+    if (rc != WSI_OK) return rc;
+  }
+  for (int64_t q0 = q_begin; q0 < q_end; q0 += chunk) {
+    const int n_q = (int)((q_end - q0) < chunk ? (q_end - q0) : chunk);
     int32_t tp[2] = {0, n_q};
-    int rc = wsi_typed_linear_f32(feat + q0 * F, F, feat, nullptr, F, (int)n, tp, 1, WSI_ACT_NONE, nullptr, nullptr, 0,
-                                  nullptr, 0, nullptr, nullptr, dot, n4, 0, WSI_OPF_BF16X3, lin_ws, lin_ws_bytes, stream);
+    int rc;
+    if (tc && wsi_typed_linear_tc_ok(n_q, F, (int)n)) {
+      rc = wsi_to_operand(feat + q0 * F, F, n_q, F, WSI_OPF_BF16X3, a_ws, stream);
+      if (rc != WSI_OK) return rc;
+      rc = wsi_typed_linear_op(a_ws, w_ws, nullptr, F, (int)n, tp, 1, WSI_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, nullptr,
+                               nullptr, dot, n4, nullptr, WSI_OPF_BF16X3, stream);
+    } else {
+      rc = wsi_typed_linear_f32(feat + q0 * F, F, feat, nullptr, F, (int)n, tp, 1, WSI_ACT_NONE, nullptr, nullptr, 0,
+                                nullptr, 0, nullptr, nullptr, dot, n4, 0, WSI_OPF_BF16X3, lin_ws, lin_ws_bytes, stream);
+    }
     if (rc != WSI_OK) return rc;
     int sb = (int)((n_q + 7) / 8 < grid_cap ? (n_q + 7) / 8 : grid_cap);
     knn_select_kernel<<<sb, 256, 0, st>>>(feat, sqn, dot, n4, n, F, topn, q0, n_q, nbr + (q0 - q_begin) * topn,
