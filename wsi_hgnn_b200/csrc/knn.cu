@@ -70,7 +70,8 @@ knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn,
         thresh_i = __shfl_sync(FULL, best_i, CAND - 1);
       }
     };
-    // Scan, 256 candidates per step: two 16-byte loads of the dot row and of the squared norms per lane in flight, one
+    // Scan, 256 candidates per step: two 16-byte loads of the dot row and of the squared norms per lane, issued ONE STEP
+    // AHEAD of their use, one
     // ballot that asks "does ANY of them beat the threshold" - after the first few hundred candidates almost every step
     // ends there (expected insertions per row ~ CAND ln(n / CAND)), so the scan runs at the rate the rows stream in.
     // (One candidate per lane and step, as in round 1, left one dependent L2 / DRAM round trip per 32 candidates:
@@ -78,12 +79,23 @@ knn_select_kernel(const float* __restrict__ feat, const float* __restrict__ sqn,
     // on the order in which candidates are offered, so the result is unchanged.
     const bool vec_ok = (ld_dot & 3) == 0 && (reinterpret_cast<uintptr_t>(drow) & 15) == 0 && (reinterpret_cast<uintptr_t>(sqn) & 15) == 0;
     const int64_t n_vec = vec_ok ? (n & ~(int64_t)255) : 0;
-    for (int64_t base = 0; base < n_vec; base += 256) {
-      float4 dv[2], sv[2];
+    float4 dv[2], sv[2], dn[2], sn[2];                            // current step / next step (loads issued one step ahead)
+    if (n_vec > 0) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        dv[u] = __ldg(reinterpret_cast<const float4*>(drow + base + u * 128 + lane * 4));
-        sv[u] = __ldg(reinterpret_cast<const float4*>(sqn + base + u * 128 + lane * 4));
+        dn[u] = __ldg(reinterpret_cast<const float4*>(drow + u * 128 + lane * 4));
+        sn[u] = __ldg(reinterpret_cast<const float4*>(sqn + u * 128 + lane * 4));
+      }
+    }
+    for (int64_t base = 0; base < n_vec; base += 256) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { dv[u] = dn[u]; sv[u] = sn[u]; }
+      if (base + 256 < n_vec) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          dn[u] = __ldg(reinterpret_cast<const float4*>(drow + base + 256 + u * 128 + lane * 4));
+          sn[u] = __ldg(reinterpret_cast<const float4*>(sqn + base + 256 + u * 128 + lane * 4));
+        }
       }
       float d[2][4];
       bool any = false;
