@@ -498,6 +498,39 @@ def main():
             b.record()
         torch.cuda.synchronize()
         gemm_ms = sorted(a.elapsed_time(b) for a, b in gev)[reps // 2]
+        # the same kernel, and the weight-gradient kernel, at the size of one packed training micro-batch (config 5:
+        # 163 840 rows, 6 skewed node types) - where a launch has ~50 tiles per CTA pair instead of 3
+        from wsi_hgnn_b200 import synthetic as _syn
+        Nb, Tb = 163840, 6
+        cnt = [int(Nb * f) for f in _syn.TYPE_SKEW6]
+        cnt[0] += Nb - sum(cnt)
+        tpb = [0]
+        for c in cnt:
+            tpb.append(tpb[-1] + c)
+        xb = torch.randn(Nb, D, device=dev)
+        wb = torch.randn(Tb, 3 * D, D, device=dev) / D ** 0.5
+        bb = torch.randn(Tb, 3 * D, device=dev)
+        dyb = torch.randn(Nb, 3 * D, device=dev)
+        yb = torch.empty(Nb, 3 * D, device=dev)
+        xb3, wb3, dy3 = ops.to_operand(xb, ops.OPF_BF16X3), ops.to_operand(wb, ops.OPF_BF16X3), ops.to_operand(dyb, ops.OPF_BF16X3)
+        del dyb
+        batch_ms = {}
+        for tag, fn in (("fwd_bf16x3", lambda: ops.typed_linear_op(xb3, wb3, bb, tpb, 3 * D, opf=ops.OPF_BF16X3, out=yb)),
+                        ("wgrad_bf16x3", lambda: ops.typed_wgrad(dy3, xb3, tpb))):
+            for _ in range(2):
+                fn()
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                fn()
+                b_.record()
+                torch.cuda.synchronize()
+                ts.append(a_.elapsed_time(b_))
+            batch_ms[tag] = sorted(ts)[2]
+        del xb, wb, bb, yb, xb3, wb3, dy3
+        batch_flops = 2.0 * Nb * D * 3 * D
     attn_bytes = E * (2 * D * 4 + 8) + N * (2 * D * 4 + 4)          # SURVEY.md §8(d) per-layer edge-phase bytes
     achieved = attn_bytes / (attn_ms * 1e-3) / 1e9
     gemm_flops = 2.0 * N * D * 3 * D
@@ -552,6 +585,17 @@ def main():
                                "achieved": gemm_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tf / tc_peak,
                                "mma_issued_tflops": issued * gemm_tf, "frac_issued": issued * gemm_tf / tc_peak,
                                "kernel_ms": gemm_ms, "peak_source": peak_src + " (bf16 dense, burst)"},
+            "roofline_dense_batch": {
+                "what": "the tcgen05 GEMMs of the training path at the size of one packed micro-batch of config 5 "
+                        f"([{Nb}, {D}] x [{Tb}, {3 * D}, {D}], 6 skewed node types), 3-term bf16 split (fp32-grade), measured live",
+                "bound": "tensor", "unit": "TFLOP/s", "peak": tc_peak, "peak_source": peak_src + " (bf16 dense, burst)",
+                "forward": {"kernel": "typed_linear_tc_kernel<TERMS=3>", "kernel_ms": batch_ms["fwd_bf16x3"],
+                            "achieved": batch_flops / (batch_ms["fwd_bf16x3"] * 1e-3) / 1e12,
+                            "frac_issued": 3 * batch_flops / (batch_ms["fwd_bf16x3"] * 1e-3) / 1e12 / tc_peak},
+                "wgrad": {"kernel": "typed_wgrad_tc_kernel (MN-major operands) + wgrad_reduce_kernel", "kernel_ms": batch_ms["wgrad_bf16x3"],
+                          "achieved": batch_flops / (batch_ms["wgrad_bf16x3"] * 1e-3) / 1e12,
+                          "frac_issued": 3 * batch_flops / (batch_ms["wgrad_bf16x3"] * 1e-3) / 1e12 / tc_peak},
+                "ncu": "profiles/r2_batch_scale_tensor_pipe.txt (sm__pipe_tensor_cycles_active 92 % / 78 %)"},
             "clocks": clk.summary()}
     if train is not None:
         line["train_step"] = train

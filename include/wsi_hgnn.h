@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 20
+#define WSI_ABI_VERSION 21
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -102,8 +102,8 @@ int wsi_to_operand(const float* src, int64_t ld_src, int64_t rows, int K, int op
 int wsi_gather_to_operand(const float* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, int opf, void* dst,
                           void* stream);
 /* The same gather on a matrix that already is in a single-plane operand form (WSI_OPF_F16 / WSI_OPF_BF16, [n, K] 16-bit,
- * dense rows): dst row i = src row row_idx[i]. */
-int wsi_gather_rows16(const void* src, const int32_t* row_idx, int64_t rows, int K, void* dst, void* stream);
+ * row stride ld_src elements - a column slice of a wider matrix is fine): dst (dense) row i = src row row_idx[i]. */
+int wsi_gather_rows16(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst, void* stream);
 int wsi_typed_linear_op(const void* x_op, const void* w_op, const float* bias, int K, int n_out,
                         const int32_t* type_ptr_host, int T, int act, const float* skip, const float* res,
                         int64_t ldres, const float* drop_mask, int64_t ldmask, const float* row_gate,

@@ -38,14 +38,17 @@ extern "C" int wsi_gather_to_operand(const float* src, int64_t ld_src, const int
   return wsi_split_launch(src, ld_src, rows, dst, nullptr, 4, 0, nullptr, K, opf, wsi_stream(stream), row_idx);
 }
 
-int wsi_gather_rows16_launch(const void* src, const int32_t* row_idx, int64_t rows, int K, void* dst, cudaStream_t stream);
+int wsi_gather_rows16_launch(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst,
+                             cudaStream_t stream);
 
-extern "C" int wsi_gather_rows16(const void* src, const int32_t* row_idx, int64_t rows, int K, void* dst, void* stream) {
-  WSI_CHECK_ARG(rows >= 0 && K >= 8 && K % 8 == 0, "gather_rows16: K must be a multiple of 8");
+extern "C" int wsi_gather_rows16(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst,
+                                 void* stream) {
+  WSI_CHECK_ARG(rows >= 0 && K >= 8 && K % 8 == 0 && ld_src >= K && ld_src % 8 == 0,
+                "gather_rows16: K and the source row stride must be multiples of 8 elements");
   if (rows == 0) return WSI_OK;
   WSI_CHECK_ARG(src && dst && row_idx && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
                 "gather_rows16: null / unaligned pointer");
-  return wsi_gather_rows16_launch(src, row_idx, rows, K, dst, wsi_stream(stream));
+  return wsi_gather_rows16_launch(src, ld_src, row_idx, rows, K, dst, wsi_stream(stream));
 }
 
 extern "C" int wsi_typed_linear_op(const void* x_split, const void* w_split, const float* bias, int K, int n_out,

@@ -109,13 +109,13 @@ __global__ void __launch_bounds__(256) convert_operand_kernel(SplitJob a, SplitJ
 }
 
 // dst row i = src row row_idx[i] of a dense 16-bit [*, K] matrix, 16 bytes (8 elements) per thread
-__global__ void __launch_bounds__(256) gather_rows16_kernel(const uint4* __restrict__ src, const int* __restrict__ row_idx,
+__global__ void __launch_bounds__(256) gather_rows16_kernel(const uint4* __restrict__ src, int64_t ld4, const int* __restrict__ row_idx,
                                                             int64_t rows, int kv, uint4* __restrict__ dst) {
   const int64_t total = rows * kv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / kv;
     const int c = (int)(i - r * kv);
-    dst[i] = __ldg(src + (int64_t)__ldg(row_idx + r) * kv + c);
+    dst[i] = __ldg(src + (int64_t)__ldg(row_idx + r) * ld4 + c);
   }
 }
 
@@ -558,13 +558,14 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   return WSI_OK;
 }
 
-int wsi_gather_rows16_launch(const void* src, const int32_t* row_idx, int64_t rows, int K, void* dst, cudaStream_t stream) {
+int wsi_gather_rows16_launch(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst,
+                             cudaStream_t stream) {
   int sms = wsi_num_sms();
   if (sms <= 0) return WSI_ERR_CUDA;
   const int64_t total = rows * (K / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > sms * 16) blocks = sms * 16;
-  gather_rows16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), row_idx, rows, K / 8,
+  gather_rows16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), ld_src / 8, row_idx, rows, K / 8,
                                                    reinterpret_cast<uint4*>(dst));
   WSI_CHECK_LAUNCH();
   return WSI_OK;

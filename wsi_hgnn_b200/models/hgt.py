@@ -197,12 +197,14 @@ class HGTLayer(nn.Module):
             w_kv = torch.cat([w_kvq[:, :D][:, pm], w_kvq[:, D:2 * D][:, pm]], 1).contiguous()
             b_kv = torch.cat([b_kvq[:, :D][:, pm], b_kvq[:, D:2 * D][:, pm]], 1).contiguous()
             w_q, b_q = w_kvq[:, 2 * D:].contiguous(), b_kvq[:, 2 * D:].contiguous()
+            w_all, b_all = torch.cat([w_kv, w_q], 1).contiguous(), torch.cat([b_kv, b_q], 1).contiguous()
             # relation_pri[r, h] (the prior on the scores, :100) scales the rows of head h of the query transform
             pri = self.relation_pri.repeat_interleave(self.d_k, 1).unsqueeze(2)                                     # [R, D, 1]
             att = torch.stack([torch.block_diag(*self.relation_att[r]) for r in range(self.num_relations)]) * pri  # [R, D(n), D(k)]
             msg = torch.stack([torch.block_diag(*self.relation_msg[r]).t() for r in range(self.num_relations)])    # [R, D(n), D(k)]
             att, msg = att[:, pm, :].contiguous(), msg[:, :, pm].contiguous()
             return dict(w_kv=ops.to_operand(w_kv, opf), b_kv=b_kv, w_q=ops.to_operand(w_q, opf), b_q=b_q,
+                        w_kvq=ops.to_operand(w_all, opf), b_kvq=b_all,
                         w_att=ops.to_operand(att, opf), w_msg=ops.to_operand(msg, opf), wa=ops.to_operand(wa, opf), ba=ba,
                         skip=skip, gamma=gamma, beta=beta)
 
@@ -218,16 +220,22 @@ class HGTLayer(nn.Module):
         S = segs["S"]
         xs = x_op if x_op is not None else ops.to_operand(x, opf)
         st16 = opf != ops.OPF_BF16X3
-        if opf == ops.OPF_BF16:        # bf16 storage of K | V (BASELINE config 3): only the 16-bit copy is written
-            _, kv = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, want_y=False, want_op=True,
-                                        type_ptr_c=tpc, opf=opf)
-        else:
-            kv, _ = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, type_ptr_c=tpc, opf=opf)
-        # q'_seg = relation_att[r, h] . q[dst, h] for the segments in relation order   (:88-92)
         # (single-pass formats: q, q'_seg and the segment messages leave their GEMMs in the 16-bit storage form only - the
         #  [S, D] tensors are the bulk of the layer's HBM traffic; the 3-term format keeps them fp32)
-        q32, q16 = ops.typed_linear_op(xs, pk["w_q"], pk["b_q"], plan.type_ptr, D, type_ptr_c=tpc, opf=opf,
-                                       want_y=not st16, want_op=st16)
+        if opf == ops.OPF_BF16 and ops.tc_ok(plan.N, self.in_dim, 3 * D):
+            # bf16 storage of K | V (BASELINE config 3): K | V | Q leave ONE GEMM as 16-bit rows, nothing else is written
+            _, kvq = ops.typed_linear_op(xs, pk["w_kvq"], pk["b_kvq"], plan.type_ptr, 3 * D, want_y=False, want_op=True,
+                                         type_ptr_c=tpc, opf=opf)
+            kv, q32, q16 = kvq[:, :2 * D], None, kvq[:, 2 * D:]
+        else:
+            if opf == ops.OPF_BF16:
+                _, kv = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, want_y=False, want_op=True,
+                                            type_ptr_c=tpc, opf=opf)
+            else:
+                kv, _ = ops.typed_linear_op(xs, pk["w_kv"], pk["b_kv"], plan.type_ptr, 2 * D, type_ptr_c=tpc, opf=opf)
+            # q'_seg = relation_att[r, h] . q[dst, h] for the segments in relation order   (:88-92)
+            q32, q16 = ops.typed_linear_op(xs, pk["w_q"], pk["b_q"], plan.type_ptr, D, type_ptr_c=tpc, opf=opf,
+                                           want_y=not st16, want_op=st16)
         qg = ops.gather_rows16(q16, grp["dst_of_order"]) if st16 else ops.gather_to_operand(q32, grp["dst_of_order"], opf)
         qseg32, qseg16 = ops.typed_linear_op(qg, pk["w_att"], None, grp["rel_ptr"], D, type_ptr_c=grp["rel_ptr_c"], opf=opf,
                                              want_y=not st16, want_op=st16)

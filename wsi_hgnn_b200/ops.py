@@ -230,11 +230,12 @@ def gather_rows16(x_op: torch.Tensor, row_idx: torch.Tensor) -> torch.Tensor:
     """out row i = x_op[row_idx[i]] for a single-plane 16-bit operand matrix (OPF_F16 / OPF_BF16); see wsi_gather_rows16."""
     lib = _lib.load()
     stream = _prep(x_op)
-    if x_op.dtype not in (torch.float16, torch.bfloat16) or x_op.dim() != 2 or not x_op.is_contiguous():
-        raise ValueError("gather_rows16: expected a contiguous fp16 / bf16 matrix")
+    if x_op.dtype not in (torch.float16, torch.bfloat16):
+        raise ValueError("gather_rows16: expected an fp16 / bf16 matrix")
+    xp, ld = _rows(x_op, "x_op", x_op.dtype)              # (a column slice of a wider matrix is fine)
     rows, K = int(row_idx.numel()), int(x_op.shape[1])
     out = torch.empty((rows, K), dtype=x_op.dtype, device=x_op.device)
-    _lib.check(lib.wsi_gather_rows16(x_op.data_ptr(), _vec(row_idx, "row_idx", torch.int32), rows, K, out.data_ptr(), stream),
+    _lib.check(lib.wsi_gather_rows16(xp, ld, _vec(row_idx, "row_idx", torch.int32), rows, K, out.data_ptr(), stream),
                "wsi_gather_rows16")
     return out
 
