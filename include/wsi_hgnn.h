@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 21
+#define WSI_ABI_VERSION 22
 
 #define WSI_ERR_ARG (-1)
 #define WSI_ERR_CUDA (-2)
@@ -101,6 +101,13 @@ int wsi_to_operand(const float* src, int64_t ld_src, int64_t rows, int K, int op
  * segments of HGT pick up their dst node's query (models/HGT.py:88-92 moved to the dst side). */
 int wsi_gather_to_operand(const float* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, int opf, void* dst,
                           void* stream);
+/* src fp32 [N, K] -> WSI_OPF_BF16X3 operand form dst [2N, K] AND colsum [T, K] = per-type column sums, in one pass: the
+ * backward of a per-type nn.Linear needs dY as a GEMM operand (data / weight gradient) and its column sums as the bias
+ * gradient (trainer/train_gnn.py:68-71).  Deterministic (per-tile partials summed in a fixed order).
+ * workspace: wsi_to_operand_colsum_workspace_bytes(K, type_ptr_host, T) bytes. */
+int64_t wsi_to_operand_colsum_workspace_bytes(int K, const int32_t* type_ptr_host, int T);
+int wsi_to_operand_colsum(const float* src, int64_t ld_src, int K, const int32_t* type_ptr_host, int T, void* dst,
+                          float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
 /* The same gather on a matrix that already is in a single-plane operand form (WSI_OPF_F16 / WSI_OPF_BF16, [n, K] 16-bit,
  * row stride ld_src elements - a column slice of a wider matrix is fine): dst (dense) row i = src row row_idx[i]. */
 int wsi_gather_rows16(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst, void* stream);

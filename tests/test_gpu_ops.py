@@ -375,6 +375,22 @@ def test_typed_layernorm_vector_path_with_operand_output(D):
         assert torch.equal(y_op.view(torch.int16), want.view(torch.int16))
 
 
+def test_to_operand_colsum():
+    """Operand conversion fused with the per-type column sums (bias gradient) == the two separate kernels."""
+    g = torch.Generator().manual_seed(9)
+    counts = [700, 0, 255, 256, 257, 3]
+    tp = [0]
+    for c in counts:
+        tp.append(tp[-1] + c)
+    big = torch.randn(tp[-1], 520, generator=g).cuda()
+    x = big[:, :512]                                       # row-strided view
+    xs, cs = ops.to_operand_colsum(x, tp)
+    assert torch.equal(xs.view(torch.int16), ops.to_operand(x.contiguous(), ops.OPF_BF16X3).view(torch.int16))
+    ref = torch.stack([x[tp[t]:tp[t + 1]].double().sum(0) for t in range(len(counts))])
+    assert rel(cs, ref) < 1e-6 and not cs[1].any()
+    assert torch.equal(cs, ops.to_operand_colsum(x, tp)[1])            # deterministic
+
+
 def test_gather_rows16():
     g = torch.Generator().manual_seed(2)
     x = torch.randn(300, 256, generator=g).cuda().to(torch.bfloat16)

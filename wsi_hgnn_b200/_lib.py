@@ -6,7 +6,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwsi_hgnn.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -61,6 +61,8 @@ PROTOTYPES = {
     "wsi_typed_linear_tc_ok": (_I, [_L, _I, _I]),
     "wsi_to_operand": (_I, [_P, _L, _L, _I, _I, _P, _P]),
     "wsi_gather_to_operand": (_I, [_P, _L, _P, _L, _I, _I, _P, _P]),
+    "wsi_to_operand_colsum_workspace_bytes": (_L, [_I, _P, _I]),
+    "wsi_to_operand_colsum": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _L, _P]),
     "wsi_gather_rows16": (_I, [_P, _L, _P, _L, _I, _P, _P]),
     "wsi_typed_linear_op": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _I, _P]),
     "wsi_hetero_attn_bwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _L,

@@ -106,7 +106,10 @@ class TypedLinearFn(torch.autograd.Function):
         tp = ctx.type_ptr
         dx = dw = db = None
         if ctx.chain:
-            ds = ops.to_operand(dy, ops.OPF_BF16X3)
+            if ctx.has_bias and ctx.needs_input_grad[2] and dy.shape[1] % 8 == 0:
+                ds, db = ops.to_operand_colsum(dy, tp, ctx.type_ptr_c)      # operand form + bias gradient: one read of dy
+            else:
+                ds = ops.to_operand(dy, ops.OPF_BF16X3)
             if ctx.needs_input_grad[0]:                  # dgrad: the same typed GEMM with W^T
                 wt = ops.to_operand(w.transpose(1, 2).contiguous(), ops.OPF_BF16X3)
                 dx, _ = ops.typed_linear_op(ds, wt, None, tp, int(w.shape[2]), type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
@@ -118,7 +121,7 @@ class TypedLinearFn(torch.autograd.Function):
                 dx = ops.typed_linear(dy, w.transpose(1, 2).contiguous(), None, tp, type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
             if ctx.needs_input_grad[1]:                  # wgrad: plain dense GEMM per node type (cuBLAS)
                 dw = _wgrad(dy, x, tp)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and db is None:
             db = ops.typed_colsum(dy, tp) if dy.shape[1] % 4 == 0 and dy.shape[0] > 0 else \
                 torch.stack([dy[tp[t]:tp[t + 1]].sum(0) for t in range(len(tp) - 1)])
         return dx, dw, db, None, None
@@ -150,11 +153,10 @@ class ALinearSkipFn(torch.autograd.Function):
                                                gate, tp, ctx.type_ptr_c)
         alpha = torch.sigmoid(skip_t)
         d_skip = d_alpha * alpha * (1 - alpha)
-        ds = ops.to_operand(d_lin, ops.OPF_BF16X3)
+        ds, db = ops.to_operand_colsum(d_lin, tp, ctx.type_ptr_c)          # operand form + bias gradient: one read of d_lin
         wt = ops.to_operand(w.transpose(1, 2).contiguous(), ops.OPF_BF16X3)
         d_agg, _ = ops.typed_linear_op(ds, wt, None, tp, int(w.shape[2]), type_ptr_c=ctx.type_ptr_c, opf=ops.OPF_BF16X3)
         dw = _wgrad_ops(ds, ags, tp, ctx.type_ptr_c)
-        db = ops.typed_colsum(d_lin, tp)
         return d_agg, dw, db, d_x, d_skip, None, None, None, None
 
 

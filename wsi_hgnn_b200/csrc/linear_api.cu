@@ -40,6 +40,27 @@ extern "C" int wsi_gather_to_operand(const float* src, int64_t ld_src, const int
 
 int wsi_gather_rows16_launch(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst,
                              cudaStream_t stream);
+int wsi_convert_colsum_launch(const float* src, int64_t ld, int K, const int32_t* type_ptr_host, int T, void* dst,
+                              float* colsum, float* partial, cudaStream_t stream);
+int64_t wsi_convert_colsum_tiles(const int32_t* type_ptr_host, int T);
+
+extern "C" int64_t wsi_to_operand_colsum_workspace_bytes(int K, const int32_t* type_ptr_host, int T) {
+  if (!type_ptr_host || T < 1 || T > WSI_MAX_TYPES) return -1;
+  return (wsi_convert_colsum_tiles(type_ptr_host, T) + 1) * (int64_t)K * 4;
+}
+
+// fp32 [N, K] -> WSI_OPF_BF16X3 operand form [2N, K] plus colsum[t, :] = sum of the rows of type t, one pass over src.
+extern "C" int wsi_to_operand_colsum(const float* src, int64_t ld_src, int K, const int32_t* type_ptr_host, int T, void* dst,
+                                     float* colsum, void* workspace, int64_t workspace_bytes, void* stream) {
+  WSI_CHECK_ARG(type_ptr_host && T >= 1 && T <= WSI_MAX_TYPES, "to_operand_colsum: bad type_ptr / T=%d", T);
+  WSI_CHECK_ARG(K >= 8 && K % 8 == 0 && ld_src >= K && ld_src % 4 == 0, "to_operand_colsum: K must be a multiple of 8, rows 16 B aligned");
+  WSI_CHECK_ARG(src && dst && colsum && workspace && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                "to_operand_colsum: null / unaligned pointer");
+  WSI_CHECK_ARG(workspace_bytes >= wsi_to_operand_colsum_workspace_bytes(K, type_ptr_host, T), "to_operand_colsum: workspace too small");
+  return wsi_convert_colsum_launch(src, ld_src, K, type_ptr_host, T, dst, colsum, reinterpret_cast<float*>(workspace),
+                                   wsi_stream(stream));
+}
 
 extern "C" int wsi_gather_rows16(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst,
                                  void* stream) {

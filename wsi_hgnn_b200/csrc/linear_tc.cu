@@ -108,6 +108,53 @@ __global__ void __launch_bounds__(256) convert_operand_kernel(SplitJob a, SplitJ
   }
 }
 
+// fp32 -> [hi; lo] operand form AND the per-type column sums of the same matrix in one pass: the backward of a typed
+// linear needs dY as a GEMM operand (data / weight gradient) and sum_rows dY as the bias gradient - two full reads of dY
+// otherwise.  One block per tile of CS_ROWS rows of ONE type (tiles never straddle types); a thread owns 4 columns, walks
+// the rows of the tile (4 loads in flight) and leaves one partial sum per tile; colsum_finish_kernel adds the partials
+// of a type in a fixed order (deterministic, no atomics).
+constexpr int CS_ROWS = 256;
+
+__global__ void __launch_bounds__(256) convert_colsum_kernel(const float* __restrict__ src, int64_t ld, int64_t n_rows, int K,
+                                                             const __grid_constant__ TypeSegs segs, uint16_t* __restrict__ dst,
+                                                             float* __restrict__ partial) {
+  const int tile = blockIdx.x;
+  const int t = wsi_tile_group(segs, tile);
+  const int r0 = segs.ptr[t] + (tile - segs.tile_start[t]) * CS_ROWS;
+  const int r1 = min(r0 + CS_ROWS, segs.ptr[t + 1]);
+  const int64_t lo_off = n_rows * K;
+  for (int c = threadIdx.x * 4; c < K; c += 1024) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r < r1; r += 4) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + u < r1) x[u] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(r + u) * ld + c));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + u < r1) {
+          store_operand4<WSI_OPF_BF16X3>(dst + (int64_t)(r + u) * K + c, lo_off, x[u]);
+          acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w;
+        }
+    }
+    *reinterpret_cast<float4*>(partial + (int64_t)tile * K + c) = acc;
+  }
+}
+
+// out[t, c] = sum over the tiles of type t of partial[tile, c]; block = 64 columns x 4 tile lanes
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int K,
+                                                            const __grid_constant__ TypeSegs segs, float* __restrict__ out) {
+  __shared__ float red[4][64];
+  const int t = blockIdx.y;
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), q = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (c < K)
+    for (int tile = segs.tile_start[t] + q; tile < segs.tile_start[t + 1]; tile += 4) acc += __ldg(partial + (int64_t)tile * K + c);
+  red[q][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (q == 0 && c < K) out[(int64_t)t * K + c] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
 // dst row i = src row row_idx[i] of a dense 16-bit [*, K] matrix, 16 bytes (8 elements) per thread
 __global__ void __launch_bounds__(256) gather_rows16_kernel(const uint4* __restrict__ src, int64_t ld4, const int* __restrict__ row_idx,
                                                             int64_t rows, int kv, uint4* __restrict__ dst) {
@@ -556,6 +603,27 @@ int wsi_typed_linear_tc_gemm(const void* a_ws, const void* w_ws, int K, const in
   WSI_CHECK_CUDA(le);
   WSI_CHECK_LAUNCH();
   return WSI_OK;
+}
+
+int wsi_convert_colsum_launch(const float* src, int64_t ld, int K, const int32_t* type_ptr_host, int T, void* dst,
+                              float* colsum, float* partial, cudaStream_t stream) {
+  TypeSegs segs;
+  if (wsi_make_segs(&segs, type_ptr_host, T, CS_ROWS) != 0) { wsi_set_error("to_operand_colsum: bad type_ptr"); return WSI_ERR_ARG; }
+  const int tiles = segs.tile_start[T];
+  const int64_t n_rows = type_ptr_host[T];
+  if (tiles > 0) {
+    convert_colsum_kernel<<<tiles, 256, 0, stream>>>(src, ld, n_rows, K, segs, reinterpret_cast<uint16_t*>(dst), partial);
+    WSI_CHECK_LAUNCH();
+  }
+  colsum_finish_kernel<<<dim3((K + 63) / 64, T), 256, 0, stream>>>(partial, K, segs, colsum);
+  WSI_CHECK_LAUNCH();
+  return WSI_OK;
+}
+
+int64_t wsi_convert_colsum_tiles(const int32_t* type_ptr_host, int T) {
+  int64_t tiles = 0;
+  for (int t = 0; t < T; ++t) tiles += (type_ptr_host[t + 1] - type_ptr_host[t] + CS_ROWS - 1) / CS_ROWS;
+  return tiles;
 }
 
 int wsi_gather_rows16_launch(const void* src, int64_t ld_src, const int32_t* row_idx, int64_t rows, int K, void* dst,

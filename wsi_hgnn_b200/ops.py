@@ -226,6 +226,25 @@ def gather_to_operand(x: torch.Tensor, row_idx: torch.Tensor, opf: Optional[int]
     return out
 
 
+def to_operand_colsum(x: torch.Tensor, type_ptr: Sequence[int], type_ptr_c=None):
+    """fp32 [N, K] -> (OPF_BF16X3 operand form [2N, K], per-type column sums [T, K]) in one pass; see wsi_to_operand_colsum."""
+    lib = _lib.load()
+    stream = _prep(x)
+    xp, ld = _rows(x, "x")
+    N, K = int(x.shape[0]), int(x.shape[1])
+    T = len(type_ptr) - 1
+    if int(type_ptr[-1]) != N:
+        raise ValueError("to_operand_colsum: type_ptr does not cover the rows of x")
+    tpc = type_ptr_c if type_ptr_c is not None else host_i32(type_ptr)
+    out = torch.empty((2 * N, K), dtype=torch.bfloat16, device=x.device)
+    cs = torch.empty((T, K), dtype=torch.float32, device=x.device)
+    ws_bytes = int(lib.wsi_to_operand_colsum_workspace_bytes(K, tpc, T))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.wsi_to_operand_colsum(xp, ld, K, tpc, T, out.data_ptr(), cs.data_ptr(), ws.data_ptr(), ws_bytes, stream),
+               "wsi_to_operand_colsum")
+    return out, cs
+
+
 def gather_rows16(x_op: torch.Tensor, row_idx: torch.Tensor) -> torch.Tensor:
     """out row i = x_op[row_idx[i]] for a single-plane 16-bit operand matrix (OPF_F16 / OPF_BF16); see wsi_gather_rows16."""
     lib = _lib.load()
