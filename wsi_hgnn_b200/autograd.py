@@ -1,7 +1,7 @@
 """torch.autograd wiring of the C-ABI kernels: what makes `loss.backward()` of the reference's training step
-(trainer/train_gnn.py:55-79) work on the CUDA path.  Forward and backward both run libwsi_hgnn.so kernels; the one
-library call is the weight-gradient GEMM dW_t = dY_t^T X_t (a plain dense GEMM: cuBLAS through torch.matmul, see
-DESIGN.md "Training")."""
+(trainer/train_gnn.py:55-79) work on the CUDA path.  Forward and backward both run libwsi_hgnn.so kernels, including the
+weight gradient dW_t = dY_t^T X_t (wsi_typed_wgrad, tcgen05 on MN-major operands); shapes that kernel does not take
+(n_out not a multiple of 32, fewer than 512 rows: the readout heads) fall to a cuBLAS GEMM through torch.mm."""
 from typing import Sequence
 
 import torch
