@@ -292,6 +292,47 @@ def test_hetero_attn_work_list(D, H, chunk):
         assert float((back - agg).abs().max()) <= eps * float(agg.abs().max())
 
 
+@pytest.mark.parametrize("kernel", [2])
+@pytest.mark.parametrize("D,H,chunk,kv_dt,q_dt", [(512, 4, 16, torch.float32, torch.float32), (512, 4, 16, torch.bfloat16, torch.bfloat16),
+                                                  (256, 8, 4, torch.float16, torch.float32), (128, 4, 1, torch.float16, torch.float16),
+                                                  (512, 1, 64, torch.bfloat16, torch.float32)])
+def test_hetero_attn_ring_kernel(kernel, D, H, chunk, kv_dt, q_dt):
+    """The TMA-ring kernel (the one large K | V footprints get), forced through the development knob, == the
+    register-path kernel on the same (rounded) inputs: hub chunks with the fused merge, the self-re-arming work queue,
+    zero in-degree and passthrough rows, 16-bit K / V and q storage."""
+    from wsi_hgnn_b200.hetero_graph import GraphPlan
+    g = torch.Generator().manual_seed(D + H + chunk)
+    n_dst, n_rel = 301, 5
+    rowptr, src, dst, rel_, sim = _random_csr(n_dst, n_dst, 1800, n_rel, g, hub=200)
+    p = ops.head_perm(D, H)
+    k = torch.randn(n_dst, D, generator=g)[:, p].cuda().to(kv_dt)
+    v = torch.randn(n_dst, D, generator=g)[:, p].cuda().to(kv_dt)
+    kv = torch.cat([k, v], 1).contiguous()
+    q = (torch.randn(n_dst, D, generator=g) * 0.5)[:, p].cuda().to(q_dt).contiguous()
+    inv_r = torch.full((n_dst,), 1.0 / n_rel)
+    inv_r[torch.rand(n_dst, generator=g) < 0.1] = 0.0
+    inv_r[0] = 1.0 / n_rel
+    plan = GraphPlan()
+    plan.N, plan.E, plan.device = n_dst, int(src.numel()), torch.device("cuda")
+    plan.rowptr = rowptr.to(torch.int32).cuda()
+    plan.e_rel = rel_.to(torch.uint8).cuda()
+    work = plan.attn_work(chunk)
+    args = (kv[:, :D], kv[:, D:], q, work, src.to(torch.int32).cuda(), sim.float().cuda(), plan.e_rel, inv_r.cuda(),
+            torch.tensor([[-0.7]]).cuda(), torch.tensor([0.2]).cuda(), D, H)
+    try:
+        ops.dev_set("attn_kernel", 1)
+        want = ops.hetero_attn_work(*args)
+        ops.dev_set("attn_kernel", kernel)
+        got = ops.hetero_attn_work(*args)
+        got2 = ops.hetero_attn_work(*args)                       # the queue / arrival counters re-arm themselves
+        got_op = ops.hetero_attn_work(*args, op_out=True, opf=ops.OPF_F16)
+    finally:
+        ops.dev_set("attn_kernel", 0)
+    assert rel(got, want) < 2e-6 and torch.equal(got, got2)
+    assert float(got[inv_r.cuda() == 0].abs().sum()) == 0.0
+    assert rel(got_op.float(), want) < 1e-3
+
+
 def rel_ok(a, b, tol):
     e = rel(a, b)
     assert e < tol, f"rel err {e:.3e}"

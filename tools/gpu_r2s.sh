@@ -1,9 +1,9 @@
 #!/bin/bash
+# opcode mix / stall samples of the two forward attention kernels: register path on the L2-resident config-2 graph,
+# TMA ring on the DRAM-resident config-4 graph
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_slide_io.py tests/test_data.py tests/test_explainer.py -m gpu -q -x > gpurun_out/r2s_pytest.log 2>&1
-echo "pytest exit $?" >> gpurun_out/r2s_pytest.log
-tail -12 gpurun_out/r2s_pytest.log
-timeout 900 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-train > gpurun_out/r2s_bench.json 2> gpurun_out/r2s_bench.err
-tail -3 gpurun_out/r2s_bench.err
-python -c "
-import json; d=json.load(open('gpurun_out/r2s_bench.json')); print(d['value'], d['ms_per_step']); print(json.dumps(d['e2e'])[:900])"
+timeout 600 ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section SpeedOfLight --clock-control none --import-source on \
+   -k regex:"attn_fwd_vec" -s 2 -c 1 -f -o gpurun_out/r2s_vec python tools/prof_attn.py --nodes 8192 --k 5 > gpurun_out/r2s_ncu_vec.log 2>&1
+timeout 600 ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section SpeedOfLight --clock-control none --import-source on \
+   -k regex:"attn_fwd_tma" -s 2 -c 1 -f -o gpurun_out/r2s_ring python tools/prof_attn.py > gpurun_out/r2s_ncu_ring.log 2>&1
+tail -1 gpurun_out/r2s_ncu_vec.log; tail -1 gpurun_out/r2s_ncu_ring.log

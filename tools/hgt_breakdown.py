@@ -12,7 +12,11 @@ def main():
     from wsi_hgnn_b200.models import hgt as H
     prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
     ops.set_matmul_precision(prec)
-    sweep = [a for a in sys.argv[2:] if "=" in a]        # attention-only knob sweep: key=v1,v2,...
+    sweep = [a for a in sys.argv[2:] if "=" in a and not a.startswith("fix:")]        # attention-only knob sweep: key=v1,v2,...
+    for a in sys.argv[2:]:
+        if a.startswith("fix:"):                          # fix:key=value - held for the whole run
+            k_, v_ = a[4:].split("=")
+            ops.dev_set(k_, int(v_))
     dev = torch.device("cuda", 0)
     T, k, F = 6, 6, 1024
     g = torch.Generator().manual_seed(99)
