@@ -30,6 +30,18 @@ namespace {
 constexpr int WARPS = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
+// sum over the G = 32 / H lanes of a head (G a power of two): five warp-uniform predicated steps - as a run-time loop this
+// was 8 instructions per step and edge (loop counter, divergence check, branch) around one SHFL + one FADD
+__device__ __forceinline__ float head_reduce(float d, int G) {
+  if (G >= 32) d += __shfl_xor_sync(0xffffffffu, d, 16);
+  if (G >= 16) d += __shfl_xor_sync(0xffffffffu, d, 8);
+  if (G >= 8) d += __shfl_xor_sync(0xffffffffu, d, 4);
+  if (G >= 4) d += __shfl_xor_sync(0xffffffffu, d, 2);
+  if (G >= 2) d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
+
 enum { MODE_HEAT = 0, MODE_HGT_SEG = 1 };
 
 struct AttnArgs {
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_fwd_vec_kernel(AttnArgs
                 d = fmaf(q[i].x, buf[u][i].x, d); d = fmaf(q[i].y, buf[u][i].y, d);
                 d = fmaf(q[i].z, buf[u][i].z, d); d = fmaf(q[i].w, buf[u][i].w, d);
               }
-              for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+              d = head_reduce(d, G);
               float scale = seg_scale;
               if (MODE == MODE_HEAT) scale = fmaf(ew, __shfl_sync(FULL, my_sim, j + u), eb) * a.inv_sqrt_dk;
               sc[u] = d * scale;
@@ -585,7 +597,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 5 : 2) attn_fwd_tma_
           for (int u = 0; u < BMAX; ++u) {
             if (u < g) {
               float d = sc[u];
-              for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+              d = head_reduce(d, G);
               float scale = seg_scale;
               if (MODE == MODE_HEAT) scale = fmaf(ew, __shfl_sync(FULL, my_sim, j + u), eb) * a.inv_sqrt_dk;
               sc[u] = d * scale;

@@ -22,6 +22,18 @@ namespace {
 constexpr int WARPS = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
+// sum over the G = 32 / H lanes of a head (G a power of two): five warp-uniform predicated steps - as a run-time loop this
+// was 8 instructions per step and edge (loop counter, divergence check, branch) around one SHFL + one FADD
+__device__ __forceinline__ float head_reduce(float d, int G) {
+  if (G >= 32) d += __shfl_xor_sync(0xffffffffu, d, 16);
+  if (G >= 16) d += __shfl_xor_sync(0xffffffffu, d, 8);
+  if (G >= 8) d += __shfl_xor_sync(0xffffffffu, d, 4);
+  if (G >= 4) d += __shfl_xor_sync(0xffffffffu, d, 2);
+  if (G >= 2) d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
+
 struct BwdArgs {
   const float* K; int64_t ldk;
   const float* V; int64_t ldv;
@@ -60,7 +72,7 @@ __device__ __forceinline__ float head_dot(const float4* a, const float4* b, int 
     d0 = fmaf(a[i].z, b[i].z, d0); d1 = fmaf(a[i].w, b[i].w, d1);
   }
   float d = d0 + d1;
-  for (int o = G >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+  d = head_reduce(d, G);
   return d;
 }
 
