@@ -34,7 +34,7 @@ def shard_slides(graphs: Sequence, rank: int, world: int):
 
 def gather_logits(local: torch.Tensor, mine: Sequence[int], n_total: int, group=None) -> torch.Tensor:
     """All ranks' per-slide logits [len(mine), C] -> [n_total, C] in the original slide order, on every rank.
-    One all_gather of a padded block (the only collective of the inference path)."""
+    One all_gather of a padded block of logits and one of the int64 slide indices (the only collectives of the inference path)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     C = int(local.shape[1]) if local.dim() == 2 else 0
@@ -42,14 +42,17 @@ def gather_logits(local: torch.Tensor, mine: Sequence[int], n_total: int, group=
     cnts = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(cnts, cnt, group=group)
     mx = int(max(int(c) for c in cnts))
-    pad = torch.zeros((mx, C + 1), dtype=local.dtype, device=local.device)
-    pad[:len(mine), :C] = local
-    pad[:len(mine), C] = torch.tensor(list(mine), dtype=local.dtype, device=local.device)      # slide index rides along
+    pad = torch.zeros((mx, C), dtype=local.dtype, device=local.device)
+    pad[:len(mine)] = local
+    idx = torch.full((mx,), -1, dtype=torch.int64, device=local.device)      # slide indices travel as int64 (exact for any
+    idx[:len(mine)] = torch.tensor(list(mine), dtype=torch.int64, device=local.device)   # logits dtype, fp16 / bf16 included)
     blocks = [torch.zeros_like(pad) for _ in range(world)]
+    idxs = [torch.zeros_like(idx) for _ in range(world)]
     dist.all_gather(blocks, pad, group=group)
+    dist.all_gather(idxs, idx, group=group)
     out = torch.zeros((n_total, C), dtype=local.dtype, device=local.device)
-    for b, c in zip(blocks, cnts):
+    for b, ix, c in zip(blocks, idxs, cnts):
         k = int(c)
         if k:
-            out[b[:k, C].round().to(torch.int64)] = b[:k, :C]
+            out[ix[:k]] = b[:k]
     return out
