@@ -305,6 +305,8 @@ def main():
     # rank its share of the cores for that set-up phase
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     torch.cuda.set_device(local)
+    from wsi_hgnn_b200.sharding import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local)            # before any pinned allocation: NUMA-local staging buffers
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL printf()s its version banner to stdout when NCCL_DEBUG is VERSION / WARN; stdout must carry ONE JSON line:
@@ -564,6 +566,7 @@ def main():
                     "h2d_alone_ms": h2d_ms, "h2d_gb_s": h2d / (h2d_ms * 1e-3) / 1e9, "device_forward_ms": t_max / args.steps * 1e3,
                     "h2d_all_ranks_concurrent_ms": h2d_all_ms,
                     "h2d_all_ranks_aggregate_gb_s": world * h2d / (h2d_all_ms * 1e-3) / 1e9,
+                    "rank0_numa_binding": numa,
                     "fp32_feature_blobs": {"value": e2e32_value, "ms_per_step": e2e32_ms, "h2d_bytes_per_step": h2d32, "steps": 8},
                     "sync_ms_per_step": e2e_sync_ms,
                     "note": "slide_io.stream_forward over pinned FlatSlide blobs, every slide distinct and never seen before: per "
