@@ -210,6 +210,20 @@ def test_hgt_tensor_core_schedule(precision, hidden, heads):
         _check(ours, orc, G, embeddings=False)
 
 
+@pytest.mark.parametrize("use_norm", [True, False])
+def test_hgt_tensor_core_schedule_single_graph_embeddings(use_norm):
+    """One (non-packed) graph through the HGT tensor-core schedule with node embeddings returned: the operand form
+    handed from layer to layer (by the LayerNorm kernel, or re-converted when there is no norm), the last layer computed
+    only because embeddings are asked for; logits and per-type embeddings against the oracle."""
+    from wsi_hgnn_b200 import ops
+    G = synthetic.synth_slide_graph(1500, 64, 3, 6, seed=77, noise_edges=0.3)
+    kw = dict(in_dim=64, hidden_dim=256, out_dim=2, n_layers=3, n_heads=4, use_norm=use_norm)
+    ours, orc = _pair("HGT", 3, kw)
+    plan = G.to("cuda").plan()
+    assert ops.tc_ok(plan.segments()["S"], 256, 256)
+    _check(ours, orc, G, embeddings=True)
+
+
 @pytest.mark.parametrize("hidden", [512, 200])
 def test_config3_hgt_bf16_storage_full_shape(hidden):
     """BASELINE config 3 at its stated shape: 16 ESCA-shape graphs (4k-12k nodes, k = 6, T = 6), 4-layer HGT with
