@@ -525,21 +525,19 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 5 : 2) attn_fwd_tma_
           if (MODE == MODE_HEAT) { my_sim = __ldg(a.e_sim + base + lane); my_rel = __ldg(a.e_rel + base + lane); }
         }
         const int pre = min(n, ring);
-        {
-          int s = rs;
-          for (int j = 0; j < pre; ++j) {
-            const int src = __shfl_sync(FULL, my_src, j);
-            if (lane == 0 && a.dbg != 2) {
-              const uint32_t bar = bars_u32 + 8 * s, dst = slots_u32 + s * SLOT_BYTES;
-              mbar_expect_tx(bar, SLOT_BYTES);
-              if (kv_adjacent) {                        // K|V of a node are one contiguous 2 * D * 4 byte run
-                bulk_g2s(dst, Kp + (int64_t)src * a.ldk, SLOT_BYTES, bar);
-              } else {
-                bulk_g2s(dst, Kp + (int64_t)src * a.ldk, ROW_BYTES, bar);
-                bulk_g2s(dst + ROW_BYTES, Vp + (int64_t)src * a.ldv, ROW_BYTES, bar);
-              }
-            }
-            if (++s == ring) s = 0;
+        // every lane issues the copy of ITS edge (lane j < pre holds edge j): one predicated pass instead of a serial
+        // loop through lane 0
+        if (lane < pre && a.dbg != 2) {
+          int s = rs + lane;
+          if (s >= ring) s -= ring;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // (the slot was last read through the generic proxy)
+          const uint32_t bar = bars_u32 + 8 * s, dst = slots_u32 + s * SLOT_BYTES;
+          mbar_expect_tx(bar, SLOT_BYTES);
+          if (kv_adjacent) {                            // K|V of a node are one contiguous 2 * D * 4 byte run
+            bulk_g2s(dst, Kp + (int64_t)my_src * a.ldk, SLOT_BYTES, bar);
+          } else {
+            bulk_g2s(dst, Kp + (int64_t)my_src * a.ldk, ROW_BYTES, bar);
+            bulk_g2s(dst + ROW_BYTES, Vp + (int64_t)my_src * a.ldv, ROW_BYTES, bar);
           }
         }
         if (!have_q) {
@@ -627,12 +625,14 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 5 : 2) attn_fwd_tma_
             }
           }
           __syncwarp();                                 // every lane is done with these g slots
-          for (int u = 0; u < g; ++u) {                 // refill them with the edges `ring` positions ahead
-            const int nxt = j + u + ring;
+          {                                             // refill them with the edges `ring` positions ahead: lane u < g
+            const int nxt = j + lane + ring;            // takes slot rs + u, all g copies issued in one predicated pass
             const int src = __shfl_sync(FULL, my_src, nxt & 31);
-            if (nxt < n && lane == 0 && a.dbg != 2) {
+            if (lane < g && nxt < n && a.dbg != 2) {
+              int s = rs + lane;
+              if (s >= ring) s -= ring;
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              const uint32_t bar = bars_u32 + 8 * rs, dst = slots_u32 + rs * SLOT_BYTES;
+              const uint32_t bar = bars_u32 + 8 * s, dst = slots_u32 + s * SLOT_BYTES;
               mbar_expect_tx(bar, SLOT_BYTES);
               if (kv_adjacent) {                        // K|V of a node are one contiguous 2 * D * 4 byte run
                 bulk_g2s(dst, Kp + (int64_t)src * a.ldk, SLOT_BYTES, bar);
@@ -641,7 +641,8 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 5 : 2) attn_fwd_tma_
                 bulk_g2s(dst + ROW_BYTES, Vp + (int64_t)src * a.ldv, ROW_BYTES, bar);
               }
             }
-            if (++rs == ring) { rs = 0; rpar ^= 1; }
+            rs += g;
+            if (rs >= ring) { rs -= ring; rpar ^= 1; }
           }
           j += g;
         }
