@@ -457,10 +457,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 constexpr int TMA_WARPS = 4;
-constexpr int BMAX = 4;      // edges per batch of the TMA kernel
+constexpr int BMAX = 2;      // edges per batch of the TMA kernel (4 measured no faster: 408 vs 410 us on config 3, 506 vs 498 us on
+                             // config 4 - and costs 16 more registers, i.e. the sixth resident block)
 
 template <int NV, int MODE, typename KVT>
-__global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 5 : 2) attn_fwd_tma_kernel(AttnArgs a, int ring) {
+__global__ void __launch_bounds__(TMA_WARPS * 32, NV <= 4 ? 6 : 2) attn_fwd_tma_kernel(AttnArgs a, int ring) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int ROW_BYTES = NV * 128 * (int)sizeof(KVT), SLOT_BYTES = 2 * ROW_BYTES;
   const KVT* const Kp = reinterpret_cast<const KVT*>(a.K);
@@ -837,8 +838,9 @@ int launch(const AttnArgs& a_in, int head_perm, cudaStream_t stream, bool* fused
       const int slot_bytes = 2 * a.D * es;
       // The kernel is bound by latency per warp, not by bytes in flight (round-2 sweep on the HGT segment graph of
       // config 3: time ~ 1 / resident blocks from 1 to 4 blocks per SM, flat in the ring depth from 2 to 4 slots), so the
-      // ring is sized for FIVE resident blocks of 4 warps (96 registers, <= 40 KB of shared memory each): ~10 KB of K/V
-      // rows in flight per warp (config 3, bf16 rows: 555 us at 4 blocks -> 462 us at 5; config 4, fp32: 530 -> 514 us)
+      // ring is sized for FIVE to SIX resident blocks of 4 warps (80 registers, <= 40 KB of shared memory each): ~10 KB of
+      // K/V rows in flight per warp (config 3, bf16 rows: 555 us at 4 blocks -> 462 us at 5 -> 396 us at 6 with the
+      // lane-parallel copy issue; config 4, fp32: 530 -> 498 us)
       int ring = 9984 / slot_bytes;
       ring = ring < 2 ? 2 : (ring > 8 ? 8 : ring);
       if (dev.attn_ring > 0) ring = dev.attn_ring;                          // development knob
