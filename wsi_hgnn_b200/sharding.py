@@ -83,5 +83,5 @@ def bind_to_gpu_numa(device_index: int) -> dict:
             return {}
         os.sched_setaffinity(0, cpus)
         return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
-    except (OSError, ValueError, AttributeError):
+    except Exception:                 # noqa: BLE001 - best effort: no CUDA device, no /sys topology, restricted affinity ...
         return {}
