@@ -97,6 +97,10 @@ CASES = [
     dict(name="hgt_T6_norm", model="HGT",
          graph=lambda: synthetic.random_hetero_graph([20, 15, 10, 8, 6, 4], 420, 24, seed=61, hub=30),
          kw=dict(in_dim=24, hidden_dim=64, out_dim=2, n_layers=3, n_heads=4, use_norm=True, graph_pooling_type="mean")),
+    # round 2: big enough (>= 512 nodes and (dst, relation) segments, D % 128 == 0) for the tensor-core HGT schedule
+    dict(name="hgt_tc_D128_T2_knn", model="HGT",
+         graph=lambda: synthetic.synth_slide_graph(640, 24, 2, 6, seed=71, noise_edges=0.3),
+         kw=dict(in_dim=24, hidden_dim=128, out_dim=2, n_layers=3, n_heads=4, use_norm=True, graph_pooling_type="mean")),
     # a relation that EXISTS with zero edges (what DropEdge / dgl.batch of sparse slides produce): it still counts in the
     # denominator of the cross-relation mean (multi_update_all(..., 'mean')), here in a dgl.batch-style batch of two
     dict(name="heat4_batch2_zero_edge_rel", model="HEATNet4",
