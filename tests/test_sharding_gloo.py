@@ -194,3 +194,35 @@ def test_flat_model_buckets_adopted_gradients_two_ranks():
                 assert torch.allclose(got, want, rtol=1e-5, atol=1e-7)
             assert all(float(x.abs().max()) == 0.0 for x in grads[len(ref):])       # the unused layer
             assert active[:len(ref)] == [True] * len(ref) and active[len(ref):] == [False, False]
+
+
+def test_flat_model_single_process_micro_batches():
+    """FlatModel without a process group (CPU tensors): two micro-batches folded into the flat buffer == the summed
+    gradient; p.grad are views of the flat buffer afterwards; a parameter without a gradient stays inactive and zero."""
+    from wsi_hgnn_b200.parallel import FlatModel
+    torch.manual_seed(3)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+    unused = torch.nn.Linear(3, 3)
+    holder = torch.nn.ModuleList([m, unused])
+    ref = [p.detach().clone() for p in m.parameters()]
+    flat = FlatModel(holder, bucket_mb=1e-4)
+    for p, r in zip(m.parameters(), ref):
+        assert torch.equal(p, r) and p.data_ptr() >= flat.flat_p.data_ptr()        # parameters moved into the flat buffer
+    X = torch.randn(6, 5)
+    flat.begin_step()
+    for i, idx in enumerate(([0, 1, 2], [3, 4, 5])):
+        if i == 1:
+            flat.arm()
+        m(X[idx]).pow(2).sum().backward()
+        if i == 0:
+            assert all(p.grad is not None and p.grad.data_ptr() != v.data_ptr() for p, v in zip(m.parameters(), flat.views))
+            flat.fold()
+            assert all(p.grad is None for p in m.parameters())
+    flat.finish()
+    m2 = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+    m2.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    m2(X).pow(2).sum().backward()
+    for (p, v), q in zip(zip(m.parameters(), flat.views[:4]), m2.parameters()):
+        assert p.grad is v and torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+    assert flat._active == [True] * 4 + [False, False]
+    assert all(float(p.grad.abs().max()) == 0.0 for p in unused.parameters())
