@@ -428,11 +428,12 @@ __global__ void __launch_bounds__(WARPS * 32) attn_merge_kernel(MergeArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA-staged variant of the fast path (the one the forward uses): every warp owns a ring of shared-memory slots, one
-// slot = the K row and the V row of one edge (2 * D * 4 bytes), filled by cp.async.bulk (the TMA engine's 1-D bulk
-// copy, SASS UBLKCP) and signalled through one mbarrier per slot.  All edges of a work item (up to the ring depth) are
-// in flight at once while the registers only hold q / acc / out - the gather no longer waits one L2 round trip per
-// group of edges, and 8 warps x ring x 4 KB = 192 KB per SM are in flight.
+// TMA-staged variant of the fast path (chosen per launch for K | V footprints beyond L2): every warp owns a ring of
+// shared-memory slots, one slot = the K row and the V row of one edge (2 * D * element size), filled by cp.async.bulk
+// (the TMA engine's 1-D bulk copy, SASS UBLKCP) and signalled through one mbarrier per slot.  The edges of a work item
+// (up to the ring depth) are in flight at once while the registers only hold q / acc / out; the copies of a batch are
+// issued by the lanes in one predicated pass (lane u fills slot rs + u).  Six resident blocks of four warps with
+// ~8-10 KB of rows in flight per warp: ~190 KB per SM.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
